@@ -1,0 +1,410 @@
+"""Layer-list ("OARG") model graphs for the two networks on the hot path.
+
+The reference treats both networks as opaque ONNX files executed by ONNX
+Runtime (oar-ocr-core/src/core/inference/ort_infer_execution.rs:121-306); the
+files themselves (pp-ocrv5_mobile_det.onnx / pp-ocrv5_mobile_rec.onnx,
+oar-ocr-core/src/core/download/registry.rs:75-76) are not available offline.
+This module therefore builds the PP-OCRv5-mobile *architectures* (PP-LCNetV3
+backbone + RSEFPN + DBHead for detection; PP-LCNetV3 + SVTR neck + CTC head for
+recognition, re-parameterised inference form) as a flat list of ops with
+deterministic synthetic weights, and serialises them into one little-endian
+blob that both the CUDA engine (csrc/engine.cu, via oar_model_load_blob) and
+the CPU oracle (oracle/net.py) execute.  One blob = one source of truth for
+layer shapes and weights.
+
+Blob layout (all little endian):
+  magic "OARG" | u32 version=1 | u32 kind (0 det, 1 rec) | u32 n_ops |
+  u32 n_tensors | u64 n_weight_floats |
+  n_ops x OpRec{ i32 type, i32 in0, i32 in1, i32 out, i32 p[12], f32 f[4],
+                 i64 w_off[4], i64 w_len[4] }   (144 bytes)
+  f32 weights[n_weight_floats]
+Tensor 0 is the network input (NHWC f32, 3 channels, BGR-normalised).
+Activations are NHWC.  `out` may name a tensor that several ops fill by channel
+slice (concat without a copy): p[10] = channel offset, p[11] = total channels
+(0 = dense).
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MAGIC = b"OARG"
+VERSION = 1
+KIND_DET, KIND_REC = 0, 1
+
+# op types
+OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL, OP_LAYERNORM, OP_ATTN, \
+    OP_CTC_HEAD = range(1, 12)
+# activations
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID = range(6)
+
+
+@dataclass
+class Op:
+    type: int
+    in0: int
+    in1: int
+    out: int
+    p: list
+    f: list = field(default_factory=lambda: [0.0] * 4)
+    w: list = field(default_factory=list)  # up to 4 float32 arrays
+
+
+class GraphBuilder:
+    def __init__(self, kind: int, seed: int):
+        self.kind = kind
+        self.rng = np.random.default_rng(seed)
+        self.ops: list[Op] = []
+        self.n_tensors = 1
+        self.channels = {0: 3}
+        self.base_gain = 1.0
+
+    def new_tensor(self, c: int) -> int:
+        t = self.n_tensors
+        self.n_tensors += 1
+        self.channels[t] = c
+        return t
+
+    def he(self, shape, fan_in, gain=1.0):
+        # base_gain < 1 keeps hardswish/swish stacks from growing layer over layer
+        return (self.rng.standard_normal(shape) * (gain * self.base_gain * np.sqrt(2.0 / fan_in))).astype(np.float32)
+
+    def small(self, shape, s=0.05):
+        return (self.rng.standard_normal(shape) * s).astype(np.float32)
+
+    # -- ops -------------------------------------------------------------
+    def conv(self, x, cout, k=(1, 1), s=(1, 1), pad=None, act=ACT_NONE, bias=True, post=(1.0, 0.0), w=None, b=None,
+             out=None, c_off=0, c_total=0, gain=1.0):
+        cin = self.channels[x]
+        kh, kw = k
+        ph, pw = pad if pad is not None else (kh // 2, kw // 2)
+        if w is None:
+            w = self.he((cout, kh, kw, cin), kh * kw * cin, gain)
+        if b is None:
+            b = self.small((cout,)) if bias else np.zeros((cout,), np.float32)
+        if out is None:
+            out = self.new_tensor(cout)
+        self.ops.append(Op(OP_CONV, x, -1, out, [kh, kw, s[0], s[1], ph, pw, cin, cout, act, 1, c_off, c_total],
+                           [post[0], post[1], 0.0, 0.0], [w.astype(np.float32), b.astype(np.float32)]))
+        return out
+
+    def dwconv(self, x, k, s=(1, 1), act=ACT_NONE, post=(1.0, 0.0), w=None, b=None):
+        c = self.channels[x]
+        if w is None:
+            w = self.he((k, k, c), k * k)
+        if b is None:
+            b = self.small((c,))
+        out = self.new_tensor(c)
+        self.ops.append(Op(OP_DWCONV, x, -1, out, [k, k, s[0], s[1], k // 2, k // 2, c, act, 1, 0, 0, 0],
+                           [post[0], post[1], 0.0, 0.0], [w, b]))
+        return out
+
+    def se(self, x, cmid, residual=False, slope=1.0 / 6.0, offset=0.5, keep0=False):
+        c = self.channels[x]
+        w1 = self.he((cmid, c), c)
+        b1 = self.small((cmid,))
+        w2 = self.he((c, cmid), cmid)
+        b2 = self.small((c,))
+        out = self.new_tensor(c)
+        self.ops.append(Op(OP_SE, x, -1, out, [c, cmid, 1 if residual else 0] + [0] * 9, [slope, offset, 0.0, 0.0],
+                           [w1, b1, w2, b2]))
+        return out
+
+    def add(self, a, b):
+        out = self.new_tensor(self.channels[a])
+        self.ops.append(Op(OP_ADD, a, b, out, [0] * 12))
+        return out
+
+    def upadd(self, a, b, scale=2):
+        """out = a + nearest_upsample(b, scale)"""
+        out = self.new_tensor(self.channels[a])
+        self.ops.append(Op(OP_UPADD, a, b, out, [scale] + [0] * 11))
+        return out
+
+    def upsample_into(self, x, scale, out, c_off, c_total):
+        self.ops.append(Op(OP_UPSAMPLE, x, -1, out, [scale] + [0] * 9 + [c_off, c_total]))
+        return out
+
+    def deconv2(self, x, cout, act=ACT_NONE, w=None, b=None):
+        cin = self.channels[x]
+        if w is None:
+            w = self.he((2, 2, cout, cin), cin)  # [dy][dx][cout][cin]
+        if b is None:
+            b = self.small((cout,))
+        out = self.new_tensor(cout)
+        self.ops.append(Op(OP_DECONV2, x, -1, out, [cin, cout, act] + [0] * 9, [1.0, 0.0, 0.0, 0.0], [w, b]))
+        return out
+
+    def avgpool(self, x, k, s):
+        out = self.new_tensor(self.channels[x])
+        self.ops.append(Op(OP_AVGPOOL, x, -1, out, [k[0], k[1], s[0], s[1]] + [0] * 8))
+        return out
+
+    def layernorm(self, x, eps):
+        c = self.channels[x]
+        g = (1.0 + self.small((c,), 0.02)).astype(np.float32)
+        b = self.small((c,), 0.02)
+        out = self.new_tensor(c)
+        self.ops.append(Op(OP_LAYERNORM, x, -1, out, [c] + [0] * 11, [eps, 0.0, 0.0, 0.0], [g, b]))
+        return out
+
+    def attn(self, x, heads):
+        c = self.channels[x]
+        wqkv = self.he((3 * c, c), c, 0.7)
+        bqkv = self.small((3 * c,))
+        wp = self.he((c, c), c, 0.7)
+        bp = self.small((c,))
+        out = self.new_tensor(c)
+        self.ops.append(Op(OP_ATTN, x, -1, out, [c, heads] + [0] * 10, [float((c // heads) ** -0.5), 0, 0, 0],
+                           [wqkv, bqkv, wp, bp]))
+        return out
+
+    def ctc_head(self, x, vocab, w, b):
+        c = self.channels[x]
+        out = self.new_tensor(vocab)
+        self.ops.append(Op(OP_CTC_HEAD, x, -1, out, [c, vocab] + [0] * 10, [0.0] * 4, [w, b]))
+        return out
+
+    # -- serialisation ----------------------------------------------------
+    def serialize(self) -> bytes:
+        recs = []
+        weights = []
+        off = 0
+        for op in self.ops:
+            w_off = [0] * 4
+            w_len = [0] * 4
+            for i, w in enumerate(op.w):
+                w = np.ascontiguousarray(w, np.float32).ravel()
+                w_off[i] = off
+                w_len[i] = w.size
+                weights.append(w)
+                off += w.size
+                pad = (-off) % 4  # keep every array 16-byte aligned
+                if pad:
+                    weights.append(np.zeros(pad, np.float32))
+                    off += pad
+            p = list(op.p) + [0] * (12 - len(op.p))
+            f = list(op.f) + [0.0] * (4 - len(op.f))
+            recs.append(struct.pack("<4i12i4f4q4q", op.type, op.in0, op.in1, op.out, *p, *f, *w_off, *w_len))
+        wcat = np.concatenate(weights) if weights else np.zeros(0, np.float32)
+        head = MAGIC + struct.pack("<4IQ", VERSION, self.kind, len(self.ops), self.n_tensors, wcat.size)
+        return head + b"".join(recs) + wcat.tobytes()
+
+
+def make_divisible(v, divisor=16):
+    new_v = max(divisor, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+# PP-LCNetV3 stage tables: (k, in, out, stride, use_se)
+_NET_DET = {
+    2: [(3, 16, 32, (1, 1), False)],
+    3: [(3, 32, 64, (2, 2), False), (3, 64, 64, (1, 1), False)],
+    4: [(3, 64, 128, (2, 2), False), (3, 128, 128, (1, 1), False)],
+    5: [(3, 128, 256, (2, 2), False)] + [(5, 256, 256, (1, 1), False)] * 4,
+    6: [(5, 256, 512, (2, 2), True), (5, 512, 512, (1, 1), True), (5, 512, 512, (1, 1), False),
+        (5, 512, 512, (1, 1), False)],
+}
+_NET_REC = {
+    2: [(3, 16, 32, (1, 1), False)],
+    3: [(3, 32, 64, (1, 1), False), (3, 64, 64, (1, 1), False)],
+    4: [(3, 64, 128, (2, 1), False), (3, 128, 128, (1, 1), False)],
+    5: [(3, 128, 256, (1, 2), False)] + [(5, 256, 256, (1, 1), False)] * 4,
+    6: [(5, 256, 512, (2, 1), True), (5, 512, 512, (1, 1), True), (5, 512, 512, (2, 1), False),
+        (5, 512, 512, (1, 1), False)],
+}
+
+
+def _plant_row0(w, n=1):
+    """make output channels 0..n-1 copy input channels 0..n-1 through the centre tap only"""
+    for j in range(n):
+        w[j] = 0.0
+        w[j, w.shape[1] // 2, w.shape[2] // 2, j] = 1.0
+    return w
+
+
+def _lcnet_block(g: GraphBuilder, x, k, cout, stride, use_se, plant):
+    """plant = number of leading channels carried through unchanged (identity taps)"""
+    c = g.channels[x]
+    wd = g.he((k, k, c), k * k)
+    bd = g.small((c,))
+    if plant:
+        wd[:, :, :plant] = 0.0
+        wd[k // 2, k // 2, :plant] = 1.0
+        bd[:plant] = 0.0
+    # LearnableRepLayer (deploy): conv -> [hardswish unless stride 2] ; post = the Act's learnable affine
+    act = ACT_NONE if stride != (1, 1) else ACT_HSWISH
+    x = g.dwconv(x, k, stride, act=act, w=wd, b=bd)
+    if use_se:
+        x = g.se(x, c // 4)
+    wp = g.he((cout, 1, 1, c), c)
+    bp = g.small((cout,))
+    if plant:
+        wp = _plant_row0(wp, plant)
+        bp[:plant] = 0.0
+    return g.conv(x, cout, (1, 1), act=ACT_HSWISH, w=wp, b=bp)
+
+
+def build_det(seed: int = 42, scale: float = 0.75, signal_gain: float = 5.0) -> bytes:
+    """PP-OCRv5_mobile_det shaped graph: PP-LCNetV3(0.75, det) + RSEFPN(96) + DBHead.
+
+    Synthetic weights with a planted signal: channel 0 carries
+    "darkness" from the stem through the stride-4 trunk into the DB head so that
+    dark text lines map to p ~ 0.97 and light background to p ~ 0.05; every other
+    weight is He-normal so the arithmetic volume is that of the real network.
+    """
+    g = GraphBuilder(KIND_DET, seed)
+    md = lambda c: make_divisible(c * scale)
+    # stem: conv3x3 s2 + BN (no activation)
+    c1 = md(16)
+    w = g.he((c1, 3, 3, 3), 27)
+    b = g.small((c1,))
+    w[0] = 0.0
+    w[0, 1, 1, :] = -signal_gain
+    b[0] = 0.0
+    x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_NONE, w=w, b=b)
+    feats = []
+    for stage in (2, 3, 4, 5, 6):
+        for (k, _cin, cout, s, use_se) in _NET_DET[stage]:
+            x = _lcnet_block(g, x, k, md(cout), s, use_se, plant=1 if stage <= 3 else 0)
+        if stage >= 3:
+            feats.append(x)
+    mv = [16, 24, 56, 480]
+    outs = []
+    for i, f in enumerate(feats):
+        co = int(mv[i] * scale)
+        wq = g.he((co, 1, 1, g.channels[f]), g.channels[f])
+        bq = g.small((co,))
+        if i == 0:
+            wq = _plant_row0(wq)
+            bq[0] = 0.0
+        outs.append(g.conv(f, co, (1, 1), act=ACT_NONE, w=wq, b=bq))
+    # RSEFPN(out=96, shortcut=True)
+    oc = 96
+    ins = []
+    for i, f in enumerate(outs):
+        wq = g.he((oc, 1, 1, g.channels[f]), g.channels[f], 0.5)
+        if i == 0:
+            wq = _plant_row0(wq)
+        else:
+            wq[0] = 0.0  # keep the planted channel clean in the top-down sum
+        t = g.conv(f, oc, (1, 1), act=ACT_NONE, bias=False, w=wq, b=np.zeros(oc, np.float32))
+        ins.append(g.se(t, oc // 4, residual=True, slope=0.2, offset=0.5))
+    in2, in3, in4, in5 = ins
+    out4 = g.upadd(in4, in5)
+    out3 = g.upadd(in3, out4)
+    out2 = g.upadd(in2, out3)
+    fuse = g.new_tensor(oc)
+    q = oc // 4
+    ps = []
+    for i, f in enumerate((in5, out4, out3, out2)):
+        wq = g.he((q, 3, 3, oc), 9 * oc, 0.5)
+        if i == 3:
+            wq = _plant_row0(wq)
+        t = g.conv(f, q, (3, 3), act=ACT_NONE, bias=False, w=wq, b=np.zeros(q, np.float32))
+        ps.append(g.se(t, q // 4, residual=True, slope=0.2, offset=0.5))
+    p5, p4, p3, p2 = ps
+    g.upsample_into(p5, 8, fuse, 0, oc)
+    g.upsample_into(p4, 4, fuse, q, oc)
+    g.upsample_into(p3, 2, fuse, 2 * q, oc)
+    g.upsample_into(p2, 1, fuse, 3 * q, oc)
+    # DBHead binarize branch (BN folded): conv3x3 -> relu -> deconv -> relu -> deconv -> sigmoid
+    wq = g.he((q, 3, 3, oc), 9 * oc, 0.5)
+    bq = g.small((q,))
+    wq[0] = 0.0
+    wq[0, 1, 1, 3 * q] = 1.0
+    bq[0] = 0.0
+    x = g.conv(fuse, q, (3, 3), act=ACT_RELU, w=wq, b=bq)
+    wd = g.he((2, 2, q, q), q)
+    bd = g.small((q,))
+    wd[:, :, 0, :] = 0.0
+    wd[:, :, 0, 0] = 1.0
+    bd[0] = 0.0
+    x = g.deconv2(x, q, act=ACT_RELU, w=wd, b=bd)
+    wd = (g.rng.standard_normal((2, 2, 1, q)) * 0.002).astype(np.float32)
+    wd[:, :, 0, 0] = 1.0
+    x = g.deconv2(x, 1, act=ACT_SIGMOID, w=wd, b=np.array([-3.0], np.float32))
+    return g.serialize()
+
+
+def _svtr_block(g: GraphBuilder, x, heads, mlp_ratio=2.0):
+    c = g.channels[x]
+    n1 = g.layernorm(x, 1e-5)
+    a = g.attn(n1, heads)
+    x = g.add(x, a)
+    n2 = g.layernorm(x, 1e-5)
+    h = g.conv(n2, int(c * mlp_ratio), (1, 1), act=ACT_SWISH, gain=0.7)
+    h = g.conv(h, c, (1, 1), act=ACT_NONE, gain=0.7)
+    return g.add(x, h)
+
+
+def build_rec(seed: int = 42, vocab: int = 18385, scale: float = 0.95, logit_gain: float = 6.0,
+              blank_bias: float = 9.0) -> bytes:
+    """PP-OCRv5_mobile_rec shaped graph: PP-LCNetV3(0.95, rec strides) + avgpool(3,2)
+    + EncoderWithSVTR(dims 120, depth 2) + CTC Linear(120 -> vocab) + softmax.
+    vocab = len(ppocrv5_dict.txt) + 2 = 18385 (decode.rs:392-423)."""
+    g = GraphBuilder(KIND_REC, seed)
+    md = lambda c: make_divisible(c * scale)
+    # stem: NP planted channels = darkness seen through different 3x3 taps, so the
+    # per-timestep feature vector follows the local stroke texture of the crop.
+    NP = 8
+    c1 = md(16)
+    w = g.he((c1, 3, 3, 3), 27)
+    b = g.small((c1,))
+    taps = [(1, 1), (1, 0), (1, 2), (0, 1), (2, 1), (0, 0), (2, 2), (0, 2)]
+    for j, (ty, tx) in enumerate(taps):
+        w[j] = 0.0
+        w[j, ty, tx, :] = -1.5
+        w[j, 1, 1, :] += -0.5 * (j % 3)
+        b[j] = 0.5 + 0.25 * j
+    x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_NONE, w=w, b=b)
+    for stage in (2, 3, 4, 5, 6):
+        for (k, _cin, cout, s, use_se) in _NET_REC[stage]:
+            x = _lcnet_block(g, x, k, md(cout), s, use_se, plant=NP)
+    x = g.avgpool(x, (3, 2), (3, 2))
+    cin = g.channels[x]
+    h = x
+    z = g.conv(x, cin // 8, (1, 3), act=ACT_SWISH)
+    z = g.conv(z, 120, (1, 1), act=ACT_SWISH)
+    for _ in range(2):
+        z = _svtr_block(g, z, 8)
+    z = g.layernorm(z, 1e-6)
+    cat = g.new_tensor(2 * cin)
+    g.upsample_into(h, 1, cat, 0, 2 * cin)
+    g.conv(z, cin, (1, 1), act=ACT_SWISH, out=cat, c_off=cin, c_total=2 * cin)
+    # conv4 reads the planted backbone channels (first NP of the guide half) strongly
+    w4 = g.he((cin // 8, 1, 3, 2 * cin), 3 * 2 * cin, 0.5)
+    w4[:, :, :, :NP] = (g.rng.standard_normal((cin // 8, 1, 3, NP)) * 0.35).astype(np.float32)
+    z = g.conv(cat, cin // 8, (1, 3), act=ACT_SWISH, w=w4)
+    z = g.conv(z, 120, (1, 1), act=ACT_SWISH)
+    w = (g.rng.standard_normal((vocab, 120)) * (logit_gain / np.sqrt(120.0))).astype(np.float32)
+    b = g.small((vocab,), 0.1)
+    b[0] = blank_bias
+    g.ctc_head(z, vocab, w, b)
+    return g.serialize()
+
+
+def synthetic_dict(vocab: int = 18385) -> list[str]:
+    """Character list for synthetic runs: vocab-2 distinct code points (CJK block
+    onward), standing in for ppocrv5_dict.txt (one char per line, ocr.rs:386)."""
+    n = vocab - 2
+    out = []
+    cp = 0x4E00
+    while len(out) < n:
+        out.append(chr(cp))
+        cp += 1
+    return out
+
+
+_cache: dict = {}
+
+
+def get_blob(kind: str, seed: int = 42, vocab: int = 18385) -> bytes:
+    key = (kind, seed, vocab)
+    if key not in _cache:
+        _cache[key] = build_det(seed) if kind == "det" else build_rec(seed, vocab)
+    return _cache[key]

@@ -1,0 +1,263 @@
+"""ctypes binding of the CPU oracle (oracle/oar_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(oar_ocr_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboar_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "oar_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_box_score_fast.restype = C.c_float
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+u8p = lambda a: _p(a, C.c_uint8)
+f32p = lambda a: _p(a, C.c_float)
+i32p = lambda a: _p(a, C.c_int32)
+
+
+def det_resize_dims(h, w, limit=960, limit_type=0, max_side=4000):
+    oh, ow = C.c_uint32(), C.c_uint32()
+    lib().oracle_det_resize_dims(C.c_uint32(h), C.c_uint32(w), C.c_uint32(limit), limit_type, C.c_uint32(max_side),
+                                 C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
+
+
+def resize_triangle(img: np.ndarray, nw: int, nh: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, _ = img.shape
+    out = np.empty((nh, nw, 3), np.uint8)
+    lib().oracle_resize_triangle(u8p(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(nw), C.c_uint32(nh), u8p(out))
+    return out
+
+
+def norm_coeffs(scale, mean, std):
+    mean = np.asarray(mean, np.float32)
+    std = np.asarray(std, np.float32)
+    a = np.empty(3, np.float32)
+    b = np.empty(3, np.float32)
+    lib().oracle_norm_coeffs(C.c_float(scale), f32p(mean), f32p(std), f32p(a), f32p(b))
+    return a, b
+
+
+def normalize(img: np.ndarray, alpha, beta, src=(2, 1, 0), layout="chw") -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, _ = img.shape
+    src_a = np.asarray(src, np.int32)
+    alpha = np.asarray(alpha, np.float32)
+    beta = np.asarray(beta, np.float32)
+    if layout == "chw":
+        out = np.empty((3, h, w), np.float32)
+        lib().oracle_normalize_chw(u8p(img), w, h, i32p(src_a), f32p(alpha), f32p(beta), f32p(out))
+    else:
+        out = np.empty((h, w, 3), np.float32)
+        lib().oracle_normalize_hwc(u8p(img), w, h, i32p(src_a), f32p(alpha), f32p(beta), f32p(out))
+    return out
+
+
+# DB detector normalisation exactly as db.rs:409-415 configures it
+DET_SCALE = np.float32(1.0) / np.float32(255.0)
+DET_MEAN = (0.485, 0.456, 0.406)
+DET_STD = (0.229, 0.224, 0.225)
+
+
+def det_normalize(img: np.ndarray) -> np.ndarray:
+    a, b = norm_coeffs(DET_SCALE, DET_MEAN, DET_STD)
+    return normalize(img, a, b, (2, 1, 0), "chw")
+
+
+def threshold_mask(pred: np.ndarray, thresh: float) -> np.ndarray:
+    pred = np.ascontiguousarray(pred, np.float32)
+    out = np.empty(pred.shape, np.uint8)
+    lib().oracle_threshold_mask(f32p(pred), pred.size, C.c_float(thresh), u8p(out))
+    return out
+
+
+def find_contours(mask: np.ndarray):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    h, w = mask.shape
+    tot = C.c_int64()
+    n = lib().oracle_find_contours(u8p(mask), w, h, None, C.c_int64(0), None, None, 0, C.byref(tot))
+    xy = np.empty((max(tot.value, 1), 2), np.int32)
+    off = np.empty(n + 1, np.int32)
+    bt = np.empty(max(n, 1), np.int32)
+    n2 = lib().oracle_find_contours(u8p(mask), w, h, i32p(xy), C.c_int64(xy.size), i32p(off), i32p(bt), n,
+                                    C.byref(tot))
+    assert n2 == n
+    return [xy[off[i]:off[i + 1]].copy() for i in range(n)], bt[:n].copy()
+
+
+def simplify_chain(pts):
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.empty_like(pts)
+    n = lib().oracle_simplify_chain(f32p(pts), len(pts), f32p(out))
+    return out[:n]
+
+
+def order_mini_box(pts):
+    pts = np.ascontiguousarray(pts, np.float32).copy()
+    lib().oracle_order_mini_box(f32p(pts))
+    return pts
+
+
+def mini_boxes_from_points(pts):
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.empty((4, 2), np.float32)
+    ms = C.c_float()
+    ok = lib().oracle_mini_boxes_from_points(f32p(pts), len(pts), f32p(out), C.byref(ms))
+    return (out, ms.value) if ok else None
+
+
+def min_area_rect(pts):
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.empty(5, np.float32)
+    lib().oracle_min_area_rect(f32p(pts), len(pts), f32p(out))
+    return out
+
+
+def box_score_fast(pred, pts):
+    pred = np.ascontiguousarray(pred, np.float32)
+    pts = np.ascontiguousarray(pts, np.float32)
+    h, w = pred.shape
+    return float(lib().oracle_box_score_fast(f32p(pred), w, h, f32p(pts), len(pts)))
+
+
+def unclip(pts, ratio):
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.empty((4096, 2), np.float32)
+    n = lib().oracle_unclip(f32p(pts), len(pts), C.c_float(ratio), f32p(out), 4096)
+    return out[:n].copy()
+
+
+def db_postprocess(pred, dest_w, dest_h, thresh=0.3, box_thresh=0.6, unclip_ratio=2.0, max_candidates=1000,
+                   min_size=3.0, with_raw=False):
+    pred = np.ascontiguousarray(pred, np.float32)
+    h, w = pred.shape
+    cap = max_candidates
+    boxes = np.empty((cap, 4, 2), np.float32)
+    scores = np.empty(cap, np.float32)
+    raw = np.empty((cap, 4, 2), np.float32)
+    n = lib().oracle_db_postprocess(f32p(pred), w, h, C.c_uint32(dest_w), C.c_uint32(dest_h), C.c_float(thresh),
+                                    C.c_float(box_thresh), C.c_float(unclip_ratio), max_candidates,
+                                    C.c_float(min_size), f32p(boxes), f32p(scores), f32p(raw), cap)
+    if with_raw:
+        return boxes[:n].copy(), scores[:n].copy(), raw[:n].copy()
+    return boxes[:n].copy(), scores[:n].copy()
+
+
+def sort_quad_boxes(boxes):
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4, 2).copy()
+    order = np.empty(max(len(boxes), 1), np.int32)
+    lib().oracle_sort_quad_boxes(f32p(boxes), len(boxes), i32p(order))
+    return boxes, order[:len(boxes)].copy()
+
+
+def is_exact_axis_aligned(pts, w, h):
+    pts = np.ascontiguousarray(pts, np.float32)
+    return bool(lib().oracle_is_exact_axis_aligned(f32p(pts), C.c_uint32(w), C.c_uint32(h)))
+
+
+def perspective_transform(src, dst):
+    src = np.ascontiguousarray(src, np.float32)
+    dst = np.ascontiguousarray(dst, np.float32)
+    m = np.empty(9, np.float32)
+    ok = lib().oracle_perspective_transform(f32p(src), f32p(dst), f32p(m))
+    return m.reshape(3, 3) if ok else None
+
+
+def bicubic(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, _ = img.shape
+    out = np.empty(3, np.uint8)
+    lib().oracle_bicubic(u8p(img), w, h, C.c_float(x), C.c_float(y), u8p(out))
+    return out
+
+
+def rotate_crop(img, quad):
+    """get_rotate_crop_image; returns None where the reference returns Err."""
+    img = np.ascontiguousarray(img, np.uint8)
+    quad = np.ascontiguousarray(quad, np.float32)
+    h, w, _ = img.shape
+    ow, oh = C.c_int(), C.c_int()
+    rc = lib().oracle_rotate_crop(u8p(img), w, h, f32p(quad), None, C.byref(ow), C.byref(oh))
+    if rc != 0:
+        return None
+    out = np.empty((oh.value, ow.value, 3), np.uint8)
+    lib().oracle_rotate_crop(u8p(img), w, h, f32p(quad), u8p(out), C.byref(ow), C.byref(oh))
+    return out
+
+
+REC_H, REC_W, REC_MAX_W = 48, 320, 3200
+
+
+def crnn_tensor_width(crops):
+    ws = np.array([c.shape[1] for c in crops], np.int32)
+    hs = np.array([c.shape[0] for c in crops], np.int32)
+    return lib().oracle_crnn_tensor_width(i32p(ws), i32p(hs), len(crops), REC_H, REC_W, REC_MAX_W)
+
+
+def crnn_preprocess(crops):
+    """crnn.rs:71-125 -> f32 [B,3,48,tensor_w]"""
+    if not crops:
+        return np.zeros((0, 0, 0, 0), np.float32)
+    tw = crnn_tensor_width(crops)
+    out = np.zeros((len(crops), 3, REC_H, tw), np.float32)
+    for i, c in enumerate(crops):
+        c = np.ascontiguousarray(c, np.uint8)
+        lib().oracle_crnn_preprocess_one(u8p(c), c.shape[1], c.shape[0], REC_H, tw, f32p(out[i]))
+    return out
+
+
+def ctc_argmax(pred):
+    pred = np.ascontiguousarray(pred, np.float32)
+    b, t, v = pred.shape
+    if pred.size == 0:
+        return np.zeros((0, 0), np.int32), np.zeros((0, 0), np.float32)
+    idx = np.empty((b, t), np.int32)
+    prob = np.empty((b, t), np.float32)
+    lib().oracle_ctc_argmax(f32p(pred), C.c_int64(b * t), v, i32p(idx), f32p(prob))
+    return idx, prob
+
+
+def ctc_decode(idx, prob, n_chars):
+    """returns (list of kept-index arrays, scores, list of column arrays, T)"""
+    idx = np.ascontiguousarray(idx, np.int32)
+    prob = np.ascontiguousarray(prob, np.float32)
+    b, t = idx.shape
+    if b == 0:
+        return [], np.zeros(0, np.float32), [], t
+    oi = np.empty((b, max(t, 1)), np.int32)
+    oc = np.empty((b, max(t, 1)), np.int32)
+    ol = np.empty(b, np.int32)
+    osc = np.empty(b, np.float32)
+    lib().oracle_ctc_decode(i32p(idx), f32p(prob), b, t, n_chars, i32p(oi), i32p(oc), i32p(ol), f32p(osc))
+    return [oi[i, :ol[i]].copy() for i in range(b)], osc, [oc[i, :ol[i]].copy() for i in range(b)], t
