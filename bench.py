@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- end-to-end OCR images/s (PP-OCRv5-mobile det+rec, 960x960) on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port) on host cores
+
+One step = one OAROCR::predict-equivalent pass (oar_pipeline_run) over one batch of `--batch` synthetic
+960x960 pages per GPU (BASELINE.json configs[1]).  Pages shard across ranks with no data-path collective
+(SURVEY.md 8e): scaling is weak, `value` = all ranks' images / max-over-ranks device time.
+
+  value : inputs resident in HBM before the timed region; timed with CUDA events on the library's launch stream
+  e2e   : the same call with HOST (pinned) page buffers: H2D of the pages and D2H of boxes/labels inside
+  roofline : dominant kernel's achieved rate, from per-launch CUDA events in profiled steps after the timed region
+  cpu_baseline : oracle/ (CPU port of the reference path) timed on this box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "end-to-end OCR images/sec (PP-OCRv5 det+rec, 960x960)"
+UNIT = "images/s"
+SIZE = 960
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tc=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tc=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pages(rank: int, batch: int):
+    from oar_ocr_b200 import synth
+    return [synth.page(rank * batch + i, SIZE) for i in range(batch)]
+
+
+def cpu_reference_pass(pages, image_bs, region_bs, nets=None):
+    """One pass of the reference's CPU path (oracle port: Rust pre/post restated in C++, networks on torch-CPU
+    fp32 standing in for ONNX Runtime CPU) over `pages`; returns (seconds, regions)."""
+    import torch
+    from oar_ocr_b200 import models
+    from oracle import pipeline
+    from oracle.net import OracleNet
+    torch.set_num_threads(os.cpu_count() or 1)
+    if nets is None:
+        nets = (OracleNet(models.get_blob("det")), OracleNet(models.get_blob("rec")))
+    t0 = time.perf_counter()
+    res = pipeline.predict(nets[0], nets[1], pages, 18385, image_batch_size=image_bs, region_batch_size=region_bs)
+    return time.perf_counter() - t0, sum(len(r) for r in res), nets
+
+
+def workload_config(args, world):
+    return {"workload": f"PP-OCRv5-mobile det+rec end-to-end, batch {args.batch} synthetic {SIZE}x{SIZE} pages per GPU "
+                        "(BASELINE.json configs[1])",
+            "images_per_step": args.batch * world, "image_batch_size": args.image_batch_size,
+            "region_batch_size": args.region_batch_size, "weights": "synthetic planted-signal, seed 42, V=18385",
+            "l2": "flushed between steps (256 MiB memset on the launch stream)", "sharding": f"replicas x{world}"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = args.ref_sample
+    pages = make_pages(0, sample)
+    nets = None
+    for _ in range(max(args.warmup, 0)):
+        _, _, nets = cpu_reference_pass(pages[:1], args.image_batch_size, args.region_batch_size, nets)
+    total = 0.0
+    regions = 0
+    for _ in range(args.steps):
+        dt, regions, nets = cpu_reference_pass(pages, args.image_batch_size, args.region_batch_size, nets)
+        total += dt
+    value = sample * args.steps / total
+    cores = os.cpu_count() or 1
+    desc = (f"{sample} of the workload's {SIZE}x{SIZE} pages per step (seeds 0..{sample - 1}), "
+            f"{regions} text regions; oracle port (C++ pre/post + torch-CPU fp32 nets)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from oar_ocr_b200 import ffi, models
+    from oar_ocr_b200.ocr import OAROCRBuilder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ocr = (OAROCRBuilder(models.get_blob("det"), models.get_blob("rec"))
+           .character_dict_content("\n".join(models.synthetic_dict())).device_id(local_rank)
+           .image_batch_size(args.image_batch_size).region_batch_size(args.region_batch_size).build())
+    if args.engine is not None:
+        ocr.det.set_engine(args.engine)
+        ocr.rec.set_engine(args.engine)
+    ctx = ocr.ctx
+    B = args.batch
+    pages = make_pages(rank, B)
+    hs = np.full(B, SIZE, np.int32)
+    ws = np.full(B, SIZE, np.int32)
+    page_bytes = SIZE * SIZE * 3
+
+    # ---- device-resident inputs (value leg)
+    d_base = ctx.device_alloc(B * page_bytes)
+    for i, p in enumerate(pages):
+        ctx.memcpy_h2d(d_base + i * page_bytes, p)
+    dev_ptrs = (C.c_void_p * B)(*[d_base + i * page_bytes for i in range(B)])
+    # ---- pinned host inputs (e2e leg)
+    pinned = torch.empty((B, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[...] = np.stack(pages)
+    host_ptrs = (C.c_void_p * B)(*[pinned.data_ptr() + i * page_bytes for i in range(B)])
+
+    def step(ptrs, on_device):
+        ctx.l2_flush()
+        return ocr.predict_raw(ptrs, hs, ws, on_device)
+
+    def timed(ptrs, on_device, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            step(ptrs, on_device)
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
+        n0 = ffi.launch_count()
+        ctx.timer_start()
+        w0 = time.perf_counter()
+        regions = 0
+        for _ in range(steps):
+            b = step(ptrs, on_device)
+            regions = int(b.region_off[B])
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - w0) * 1000.0
+        launches = ffi.launch_count() - n0
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        return max_over_ranks(ms), max_over_ranks(wall), launches, regions, clocks
+
+    ms, wall, launches, regions, clocks = timed(dev_ptrs, True, args.steps, args.warmup, True)
+    stage = dict(ocr.last_timing)
+    value = world * B * args.steps / (ms / 1000.0)
+    e_ms, e_wall, _, _, _ = timed(host_ptrs, False, args.steps, max(1, args.warmup // 2))
+    e2e_stage = dict(ocr.last_timing)
+    e2e_value = world * B * args.steps / (e_ms / 1000.0)
+
+    # ---- per-kernel roofline from profiled steps (after the timed region; events around every launch)
+    peaks = load_peaks()
+    roof = None
+    kernels = []
+    if rank == 0:
+        ctx.profile(True)
+        agg = {}
+        P = 2
+        for _ in range(P):
+            step(dev_ptrs, True)
+            for r in ctx.profile_read():
+                a = agg.setdefault(r["name"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+                a["ms"] += r["ms"]
+                a["flops"] += r["flops"]
+                a["bytes"] += r["bytes"]
+                a["n"] += 1
+        ctx.profile(False)
+        tot = sum(a["ms"] for a in agg.values()) or 1.0
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            t = a["ms"] / 1000.0
+            gbs = a["bytes"] / t / 1e9 if t > 0 else 0.0
+            tfl = a["flops"] / t / 1e12 if t > 0 else 0.0
+            t_hbm = a["bytes"] / (peaks["hbm"] * 1e9)
+            t_tc = a["flops"] / (peaks["tc"] * 1e12)
+            kernels.append(dict(name=name, launches_per_step=a["n"] // P, ms_per_step=a["ms"] / P,
+                                share=a["ms"] / tot, gbs=gbs, tflops=tfl, bound="hbm" if t_hbm >= t_tc else "tensor",
+                                avg_launch_us=1000.0 * a["ms"] / a["n"],
+                                roofline_frac=max(t_hbm, t_tc) / t if t > 0 else 0.0))
+        top = kernels[0]
+        if top["bound"] == "hbm":
+            roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
+        else:
+            roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tc"], "unit": "TFLOP/s"}
+        roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=top["name"],
+                    share_of_step=top["share"], avg_launch_us=top["avg_launch_us"], peak_source=peaks["source"],
+                    measured="per-launch CUDA events on the launch stream, 2 profiled steps after the timed region")
+        # whole-step roofline: sum over kernels of max(bytes/BW, flops/peak) / sum of kernel times
+        roof["step_frac"] = sum(k["roofline_frac"] * k["ms_per_step"] for k in kernels) / \
+            (sum(k["ms_per_step"] for k in kernels) or 1.0)
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "bench_kernels.json"), "w") as f:
+                json.dump(dict(kernels=kernels, stage_ms=stage, e2e_stage_ms=e2e_stage), f, indent=1)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.ref_sample
+        dt0, _, nets = cpu_reference_pass(pages[:1], args.image_batch_size, args.region_batch_size)
+        dt, n_reg, _ = cpu_reference_pass(pages[:sample], args.image_batch_size, args.region_batch_size, nets)
+        cpu_base = {"value": sample / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"first {sample} of this run's {B} pages, one pass after one warm-up page "
+                              f"({n_reg} text regions, {dt:.1f} s); oracle port: C++ restatement of the Rust "
+                              "pre/post + torch-CPU fp32 networks (ONNX Runtime is not installable offline)"}
+
+    if rank == 0:
+        engine_dtype = "f32" if args.engine == 0 else ocr_dtype(ocr)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": engine_dtype, "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_stage["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(e2e_stage["d2h_bytes"]), "ms_per_step": e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "regions_per_step_rank0": regions, "wall_ms_per_step": wall / args.steps,
+            "stage_ms_last_step": {k: round(v, 3) for k, v in stage.items() if k.startswith("ms_")},
+            "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()}
+                            for kk in kernels[:6]],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ocr_dtype(ocr) -> str:
+    return os.environ.get("OAR_BENCH_DTYPE", "f32")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="pages per GPU per step")
+    ap.add_argument("--image-batch-size", type=int, default=8)
+    ap.add_argument("--region-batch-size", type=int, default=64)
+    ap.add_argument("--engine", type=int, default=None, help="0 = fp32 SIMT engine, 1 = tensor-core engine")
+    ap.add_argument("--ref-sample", type=int, default=4, help="pages per CPU-reference pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+/* oar_b200.h -- C ABI of the B200-native OCR hot path (liboar_b200.so).
+ *
+ * Drop-in boundary for oar-ocr's det+rec path.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repo,
+ * GreatV/oar-ocr v0.9.3).  Plain pointers and sizes only; no exceptions cross
+ * the boundary.  Every function returns 0 on success or a negative OAR_E_*
+ * code; oar_last_error() returns a thread-local UTF-8 message that a Rust
+ * shim wraps in OCRError::Inference{model_name, context, source}
+ * (oar-ocr-core/src/core/errors/types.rs:110-214).
+ *
+ * Threading mirrors OrtInfer's Mutex<Session>
+ * (oar-ocr-core/src/core/inference/ort_infer_execution.rs:142-155): calls on
+ * the same context serialise internally; different contexts (one per GPU) run
+ * concurrently.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * OAR_E_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef OAR_B200_H
+#define OAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OAR_OK 0
+#define OAR_E_INVALID (-1)   /* OCRError::InvalidInput / validation_error */
+#define OAR_E_NO_DEVICE (-2) /* no usable CUDA device */
+#define OAR_E_CUDA (-3)      /* CUDA runtime failure -> OCRError::Inference */
+#define OAR_E_MODEL (-4)     /* malformed model blob -> OCRError::ModelLoad */
+#define OAR_E_CAPACITY (-5)  /* caller-provided output buffer too small */
+#define OAR_E_UNSUPPORTED (-6)
+
+typedef struct oar_ctx oar_ctx;     /* one device + stream + workspace arena */
+typedef struct oar_model oar_model; /* one network resident on a context */
+
+#define OAR_KIND_DET 0
+#define OAR_KIND_REC 1
+
+/* Detection post-process configuration.
+ * = DBPostProcess{thresh, box_thresh, max_candidates, unclip_ratio, min_size}
+ *   (oar-ocr-core/src/processors/db_postprocess.rs:69-88) + the limit-side
+ *   resize parameters of DetResizeForTest
+ *   (oar-ocr-core/src/processors/resize_detection.rs:243-319).
+ * Fixed as both reference adapters fix them: use_dilation=false,
+ * ScoreMode::Fast, BoxType::Quad
+ * (oar-ocr-core/src/domain/adapters/text_detection_adapter.rs:165-173). */
+typedef struct {
+  float thresh;            /* 0.3 */
+  float box_thresh;        /* 0.6 */
+  float unclip_ratio;      /* 2.0 (OAROCRBuilder default, src/oarocr/ocr.rs:351-364); 1.5 in the predictor */
+  int32_t max_candidates;  /* 1000 */
+  float min_size;          /* 3.0 */
+  int32_t limit_side_len;  /* 960 */
+  int32_t limit_type;      /* 0 = Max, 1 = Min, 2 = ResizeLong */
+  int32_t max_side_limit;  /* 4000 */
+} oar_det_config;
+
+/* Pipeline configuration = the knobs OAROCRBuilder exposes for this path
+ * (src/oarocr/ocr.rs:249-417). */
+typedef struct {
+  oar_det_config det;
+  int32_t image_batch_size;  /* det_batch_size, ocr.rs:550-557 (accelerator default 8) */
+  int32_t region_batch_size; /* ocr.rs:818-825 (accelerator default 64) */
+  float rec_score_thresh;    /* TextRecognitionConfig.score_threshold, text_recognition_adapter.rs:88-102 */
+  int32_t n_chars;           /* len(CTCLabelDecode.character) = dict + blank + space, decode.rs:392-423 */
+} oar_pipeline_config;
+
+void oar_det_config_default(oar_det_config* cfg);           /* ocr.rs:351-364 defaults */
+void oar_pipeline_config_default(oar_pipeline_config* cfg); /* accelerator defaults 8 / 64 */
+
+const char* oar_last_error(void);
+int32_t oar_version(void);
+/* number of kernel launches issued by this library on the calling process so far */
+int64_t oar_launch_count(void);
+
+/* ---- context / model lifetime -------------------------------------------
+ * replaces OrtInfer::new / from_config + Session::builder().commit_from_memory
+ * (oar-ocr-core/src/core/inference/ort_infer_builders.rs:9-70, session.rs:21-46) */
+int32_t oar_ctx_create(int32_t device_id, oar_ctx** out);
+void oar_ctx_destroy(oar_ctx* ctx);
+int32_t oar_ctx_synchronize(oar_ctx* ctx);
+/* Loads an OARG layer-list blob (oar_ocr_b200/models.py); weights are copied to HBM. */
+int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_model** out);
+void oar_model_destroy(oar_model* m);
+int32_t oar_model_kind(const oar_model* m);
+/* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine (default where available) */
+int32_t oar_model_set_engine(oar_model* m, int32_t engine);
+
+/* ---- seam 1: OrtInfer::infer / infer_first_output_f32 --------------------
+ * (oar-ocr-core/src/core/inference/ort_infer_execution.rs:121-306)
+ * in: host f32 [B,3,H,W] row-major (the tensor the reference feeds as "x").
+ * det out: f32 [B,1,H,W] probability map; rec out: f32 [B,T,V] softmax.
+ * out_shape receives 4 dims (rec: B,T,V,1).  out_cap in floats. */
+int32_t oar_infer_f32(oar_model* m, const float* in, const int64_t in_shape[4], float* out, size_t out_cap,
+                      int64_t out_shape[4]);
+
+/* ---- row 2: NormalizeImage::normalize_batch_refs --------------------------
+ * (oar-ocr-core/src/processors/normalization.rs:429-482, simd.rs:28-45)
+ * u8 HWC RGB [B,H,W,3] -> f32 NCHW, out[c] = rgb[src[c]]*alpha[c]+beta[c]
+ * (separate multiply and add, as the reference). Host pointers. */
+int32_t oar_normalize_chw(oar_ctx* ctx, const uint8_t* rgb, int32_t batch, int32_t h, int32_t w,
+                          const int32_t src_channels[3], const float alpha[3], const float beta[3], float* out);
+
+/* ---- rows 4-9: DBPostProcess::apply ---------------------------------------
+ * (oar-ocr-core/src/processors/db_postprocess.rs:100-179, db_bitmap.rs:84-150)
+ * pred: host f32 [B,H,W]; src_h/src_w: ImageScaleInfo source dims per image.
+ * boxes: [B][max_candidates][4][2] (discovery order), scores, counts[B]. */
+int32_t oar_db_postprocess(oar_ctx* ctx, const float* pred, int32_t batch, int32_t h, int32_t w, const int32_t* src_h,
+                           const int32_t* src_w, const oar_det_config* cfg, float* boxes, float* scores,
+                           int32_t* counts);
+
+/* ---- seam 2 (detection): TextDetectionAdapter::execute --------------------
+ * (oar-ocr-core/src/domain/adapters/text_detection_adapter.rs:36-79 ->
+ *  DBModel::forward, oar-ocr-core/src/models/detection/db.rs:281-335)
+ * images: n host pointers to u8 HWC RGB; boxes [n][max_candidates][4][2] in
+ * source-image coordinates, discovery order (unsorted, as the adapter returns). */
+int32_t oar_det_run(oar_model* det, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                    const oar_det_config* cfg, float* boxes, float* scores, int32_t* counts);
+
+/* ---- row 10: sort_quad_boxes (oar-ocr-core/src/processors/sorting.rs:35-84) */
+int32_t oar_sort_quad_boxes(float* boxes, int32_t n, int32_t* order);
+
+/* ---- row 11: get_rotate_crop_image ----------------------------------------
+ * (oar-ocr-core/src/utils/transform.rs:76-191).  One image, n quads.
+ * Phase 1 (out == NULL): fills out_w/out_h/status per quad (status != 0 where
+ * the reference returns Err).  Phase 2: out = concatenated u8 HWC crops. */
+int32_t oar_rotate_crop(oar_ctx* ctx, const uint8_t* image, int32_t h, int32_t w, const float* quads, int32_t n,
+                        int32_t* out_w, int32_t* out_h, int32_t* status, uint8_t* out, size_t out_cap);
+
+/* ---- row 13: CRNNModel::preprocess_refs -----------------------------------
+ * (oar-ocr-core/src/models/recognition/crnn.rs:71-125, simd.rs:248-308)
+ * crops: n host u8 HWC images; out f32 [n,3,48,tensor_w]; *tensor_w returned. */
+int32_t oar_crnn_preprocess(oar_ctx* ctx, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws,
+                            int32_t n, float* out, size_t out_cap, int32_t* tensor_w);
+
+/* ---- rows 15-16: CTCLabelDecode::argmax_predictions + decode_argmax --------
+ * (oar-ocr-core/src/processors/decode.rs:452-614, simd.rs:190-229)
+ * pred: host f32 [B,T,V].  idx/prob [B,T]; labels/cols [B,T] (first len[b] valid). */
+int32_t oar_ctc_decode(oar_ctx* ctx, const float* pred, int32_t b, int32_t t, int32_t v, int32_t n_chars,
+                       int32_t* idx, float* prob, int32_t* labels, int32_t* cols, int32_t* lens, float* scores);
+
+/* ---- seam 2 (recognition): TextRecognitionAdapter::execute ----------------
+ * (oar-ocr-core/src/domain/adapters/text_recognition_adapter.rs:35-111 ->
+ *  CRNNModel::forward_refs, crnn.rs:247-293).  The whole input is ONE batch.
+ * labels/cols: [n][t_cap]; *t_out = sequence length T of this batch. */
+int32_t oar_rec_run(oar_model* rec, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                    int32_t n_chars, int32_t* labels, int32_t* cols, int32_t* lens, float* scores, int32_t t_cap,
+                    int32_t* t_out);
+
+/* ---- the hot path: OAROCR::predict (src/oarocr/ocr.rs:518-659) -------------
+ * Results, per input image i: regions [region_off[i], region_off[i+1]) in
+ * reading order (sort_quad_boxes), dropped where the crop failed
+ * (processors.rs:104-106).  For region r: box[r][4][2], score[r], CTC-collapsed
+ * class indices labels[label_off[r] .. label_off[r+1]) (text = chars[index];
+ * empty when score < rec_score_thresh), det_index[r] = detection_index. */
+typedef struct {
+  int32_t cap_regions; /* in: capacity of per-region arrays */
+  int32_t cap_labels;  /* in: capacity of labels */
+  int32_t* region_off; /* [n_images+1] */
+  float* boxes;        /* [cap_regions][8] */
+  float* scores;       /* [cap_regions] recognition confidence */
+  int32_t* det_index;  /* [cap_regions] */
+  int32_t* label_off;  /* [cap_regions+1] */
+  int32_t* labels;     /* [cap_labels] */
+  /* device-time breakdown of the last call, ms (0 when not measured) */
+  float ms_h2d, ms_det, ms_post, ms_crop, ms_rec, ms_total;
+  int64_t h2d_bytes, d2h_bytes;
+} oar_ocr_result;
+
+/* images_on_device != 0: `images` are device pointers already resident in HBM */
+int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
+                         const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
+                         oar_ocr_result* out);
+
+/* device memory helpers for callers that keep inputs resident (bench `value` leg) */
+int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out);
+int32_t oar_device_free(oar_ctx* ctx, void* p);
+int32_t oar_memcpy_h2d(oar_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- measurement helpers (bench.py) ----------------------------------------
+ * CUDA-event stopwatch on the context's own launch stream: start records an
+ * event, stop records another, synchronises and returns the elapsed device
+ * time.  l2_flush overwrites a scratch buffer larger than the 126 MB L2. */
+int32_t oar_timer_start(oar_ctx* ctx);
+int32_t oar_timer_stop(oar_ctx* ctx, float* ms);
+int32_t oar_l2_flush(oar_ctx* ctx);
+
+/* per-kernel timing of the most recent oar_infer / pipeline call on a model's
+ * context: enables cudaEvent brackets around every launch (bench roofline leg) */
+int32_t oar_profile_enable(oar_ctx* ctx, int32_t on);
+/* writes up to cap records; returns the count.  name: static string */
+typedef struct {
+  const char* name;
+  float ms;
+  double flops;
+  double bytes;
+} oar_kernel_record;
+int32_t oar_profile_read(oar_ctx* ctx, oar_kernel_record* recs, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAR_B200_H */

@@ -1,0 +1,1155 @@
+// capi.cu -- the C ABI of liboar_b200.so (include/oar_b200.h) and the host side of the hot path.
+//
+// Host orchestration mirrors the reference's own call stack (file:line under the reference repo):
+//   oar_pipeline_run   = OAROCR::predict                        src/oarocr/ocr.rs:518-659
+//   det chunking       = det_batch_size loop                     src/oarocr/ocr.rs:550-592
+//   same-shape groups  = DBModel::forward                        oar-ocr-core/src/models/detection/db.rs:281-335
+//   limit-side resize  = DetResizeForTest::resize_image_type0    oar-ocr-core/src/processors/resize_detection.rs:243-319
+//   reading order      = sort_quad_boxes                         oar-ocr-core/src/processors/sorting.rs:35-84
+//   crop pool + flush  = MAX_POOLED_CROPS                        src/oarocr/ocr.rs:603-633
+//   wh-ratio chunks    = OAROCR::recognize_global                src/oarocr/ocr.rs:802-897
+//   rec batch tensor   = CRNNModel::preprocess_refs              oar-ocr-core/src/models/recognition/crnn.rs:71-125
+// Everything numeric runs in the CUDA kernels of engine.cu / gemm_tc.cu / prepost.cu / dbpost.cu;
+// the host only sequences launches, sorts a few hundred boxes and lays out result buffers.
+#include <algorithm>
+#include <cmath>
+#include <exception>
+
+#include "engine.cuh"
+#include "prepost.cuh"
+
+namespace oar {
+
+thread_local char g_err[1024] = {0};
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace oar
+
+using namespace oar;
+
+// ---------------------------------------------------------------------------
+// context plumbing
+// ---------------------------------------------------------------------------
+void* oar_ctx::pinned_get(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  for (auto& s : pinned) {
+    if (s.used + bytes <= s.cap) {
+      void* p = s.base + s.used;
+      s.used += bytes;
+      return p;
+    }
+  }
+  size_t cap = std::max(bytes, (size_t)16 << 20);
+  char* p = nullptr;
+  OAR_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+  pinned.push_back(PinnedSlab{p, cap, bytes});
+  return p;
+}
+
+void oar_ctx::pinned_reset() {
+  if (pinned.size() > 1) {
+    size_t total = 0;
+    for (auto& s : pinned) {
+      total += s.cap;
+      cudaFreeHost(s.base);
+    }
+    pinned.clear();
+    char* p = nullptr;
+    OAR_CUDA(cudaHostAlloc(&p, total, cudaHostAllocDefault));
+    pinned.push_back(PinnedSlab{p, total, 0});
+  }
+  for (auto& s : pinned) s.used = 0;
+}
+
+cudaEvent_t oar_ctx::next_event() {
+  if (event_next == event_pool.size()) {
+    cudaEvent_t e;
+    OAR_CUDA(cudaEventCreate(&e));
+    event_pool.push_back(e);
+  }
+  return event_pool[event_next++];
+}
+
+void oar_ctx::begin_call() {
+  OAR_CUDA(cudaSetDevice(device));
+  OAR_CUDA(cudaStreamSynchronize(stream));
+  arena.reset();
+  pinned_reset();
+  prof.clear();
+  event_next = 0;
+}
+
+namespace {
+
+struct CallGuard {
+  std::lock_guard<std::mutex> lock;
+  explicit CallGuard(oar_ctx* c) : lock(c->mu) { c->begin_call(); }
+};
+
+#define API_TRY try {
+#define API_CATCH                                                  \
+  }                                                                \
+  catch (const oar::OarError& e) {                                 \
+    cudaGetLastError();                                            \
+    return e.code;                                                 \
+  }                                                                \
+  catch (const std::exception& e) {                                \
+    oar::set_error("internal error: %s", e.what());                \
+    return OAR_E_CUDA;                                             \
+  }                                                                \
+  return OAR_OK;
+
+template <typename T>
+T* to_device(oar_ctx* ctx, const T* host, size_t n) {
+  T* d = ctx->arena.get<T>(n ? n : 1);
+  if (n) {
+    T* staged = (T*)ctx->pinned_get(n * sizeof(T));
+    memcpy(staged, host, n * sizeof(T));
+    OAR_CUDA(cudaMemcpyAsync(d, staged, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return d;
+}
+
+// DB detector normalisation constants as DBModelBuilder configures them (db.rs:409-415):
+// scale 1/255, ImageNet mean/std applied in output (B,G,R) order, src channels [2,1,0];
+// alpha = scale/std, beta = -mean/std (normalization.rs:142-143), all in f32.
+void det_norm_coeffs(int src[3], float alpha[3], float beta[3]) {
+  const float scale = 1.0f / 255.0f;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int c = 0; c < 3; ++c) {
+    alpha[c] = scale / stdv[c];
+    beta[c] = -mean[c] / stdv[c];
+    src[c] = 2 - c;
+  }
+}
+
+// Rust `as u32` from f32: saturating, NaN -> 0
+uint32_t f32_as_u32(float v) {
+  if (!(v > 0.0f)) return 0u;
+  if (v >= 4294967296.0f) return 4294967295u;
+  return (uint32_t)v;
+}
+
+// resize_image_type0 (resize_detection.rs:243-319): target dims only
+void det_resize_dims(uint32_t h, uint32_t w, const oar_det_config& cfg, uint32_t* oh, uint32_t* ow) {
+  uint32_t limit = (uint32_t)cfg.limit_side_len;
+  float ratio = 1.0f;
+  uint32_t mx = std::max(h, w), mn = std::min(h, w);
+  if (cfg.limit_type == 0) {
+    if (mx > limit) ratio = (float)limit / (float)mx;
+  } else if (cfg.limit_type == 1) {
+    if (mn < limit) ratio = (float)limit / (float)mn;
+  } else {
+    ratio = (float)limit / (float)mx;
+  }
+  uint32_t rh = f32_as_u32((float)h * ratio), rw = f32_as_u32((float)w * ratio);
+  uint32_t side_cap = (uint32_t)cfg.max_side_limit;
+  if (std::max(rh, rw) > side_cap) {
+    float lr = (float)side_cap / (float)std::max(rh, rw);
+    rh = f32_as_u32((float)rh * lr);
+    rw = f32_as_u32((float)rw * lr);
+  }
+  rh = std::max((rh + 16) / 32 * 32, 32u);
+  rw = std::max((rw + 16) / 32 * 32, 32u);
+  *oh = rh;
+  *ow = rw;
+}
+
+struct DevImage {
+  const uint8_t* p;
+  int h, w;
+};
+
+// one same-shape detection group in flight
+struct DetGroup {
+  std::vector<int> members;  // indices into the caller's image list
+  int H = 0, W = 0;
+  float *h_boxes = nullptr, *h_scores = nullptr;
+  int32_t* h_counts = nullptr;
+  DbPostStatus status;
+  cudaEvent_t e_start = nullptr, e_net = nullptr, e_post = nullptr;
+};
+
+// Launches normalize -> DB net -> DB post for one same-shape group; results land in pinned host
+// memory once the stream is synchronised.
+void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, const std::vector<int32_t>& src_h,
+                      const std::vector<int32_t>& src_w, const oar_det_config& cfg, DetGroup& g, int comps_hint,
+                      bool timed) {
+  oar_ctx* ctx = det->ctx;
+  const int B = (int)g.members.size();
+  std::vector<const uint8_t*> ptrs(B);
+  std::vector<int32_t> sh(B), sw(B);
+  bool aligned = true;
+  for (int i = 0; i < B; ++i) {
+    ptrs[i] = resized[g.members[i]].p;
+    aligned = aligned && (((uintptr_t)ptrs[i] & 3) == 0);
+    sh[i] = src_h[g.members[i]];
+    sw[i] = src_w[g.members[i]];
+  }
+  if (timed) {
+    g.e_start = ctx->next_event();
+    g.e_net = ctx->next_event();
+    g.e_post = ctx->next_event();
+    cudaEventRecord(g.e_start, ctx->stream);
+  }
+  // persistent outputs first, then per-group scratch that the next group may reuse (stream order)
+  const int mc = cfg.max_candidates;
+  DbPostOut out;
+  out.boxes = ctx->arena.get<float>((size_t)B * mc * 8);
+  out.scores = ctx->arena.get<float>((size_t)B * mc);
+  out.counts = ctx->arena.get<int32_t>(B);
+  auto mark = ctx->arena.mark();
+  const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data(), B);
+  Tensor in;
+  in.B = B, in.H = g.H, in.W = g.W, in.C = 3;
+  in.p = ctx->arena.get<float>(in.numel());
+  int src[3];
+  float alpha[3], beta[3];
+  det_norm_coeffs(src, alpha, beta);
+  launch_normalize(ctx, nullptr, d_table, aligned, in.p, B, g.H, g.W, src, alpha, beta, /*NHWC*/ 1);
+  Tensor prob = model_forward(det, in, false, nullptr);
+  if (prob.B != B || prob.H != g.H || prob.W != g.W || prob.C != 1)
+    OAR_FAIL(OAR_E_MODEL, "detector output %dx%dx%dx%d does not match its %dx%d input", prob.B, prob.H, prob.W, prob.C,
+             g.H, g.W);
+  if (timed) cudaEventRecord(g.e_net, ctx->stream);
+  g.status = db_postprocess_device(ctx, prob.p, B, g.H, g.W, sh.data(), sw.data(), cfg, out, comps_hint);
+  g.h_boxes = (float*)ctx->pinned_get((size_t)B * mc * 8 * sizeof(float));
+  g.h_scores = (float*)ctx->pinned_get((size_t)B * mc * sizeof(float));
+  g.h_counts = (int32_t*)ctx->pinned_get((size_t)B * sizeof(int32_t));
+  OAR_CUDA(cudaMemcpyAsync(g.h_counts, out.counts, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaMemcpyAsync(g.h_boxes, out.boxes, (size_t)B * mc * 8 * sizeof(float), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  OAR_CUDA(cudaMemcpyAsync(g.h_scores, out.scores, (size_t)B * mc * sizeof(float), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  if (timed) cudaEventRecord(g.e_post, ctx->stream);
+  ctx->arena.release_to(mark);
+}
+
+// DetResizeForTest::apply on device: returns the images the detector sees (resized in HBM when needed)
+void det_resize_on_device(oar_ctx* ctx, const std::vector<DevImage>& imgs, const oar_det_config& cfg,
+                          std::vector<DevImage>& resized) {
+  const int n = (int)imgs.size();
+  resized.resize(n);
+  std::vector<ResizeJob> jobs;
+  int max_sw = 0, max_dw = 0, max_dh = 0;
+  for (int i = 0; i < n; ++i) {
+    DevImage im = imgs[i];
+    if (im.h <= 0 || im.w <= 0) OAR_FAIL(OAR_E_INVALID, "image %d has invalid dimensions %dx%d", i, im.w, im.h);
+    if (im.h + im.w < 64) {
+      // image_padding (resize_detection.rs:204-220): black canvas of at least 32x32, source at (0,0)
+      int nw = std::max(im.w, 32), nh = std::max(im.h, 32);
+      if (nw != im.w || nh != im.h) {
+        uint8_t* pad = ctx->arena.get<uint8_t>((size_t)nw * nh * 3);
+        OAR_CUDA(cudaMemsetAsync(pad, 0, (size_t)nw * nh * 3, ctx->stream));
+        OAR_CUDA(cudaMemcpy2DAsync(pad, (size_t)nw * 3, im.p, (size_t)im.w * 3, (size_t)im.w * 3, im.h,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        im = DevImage{pad, nh, nw};
+      }
+    }
+    uint32_t rh, rw;
+    det_resize_dims((uint32_t)im.h, (uint32_t)im.w, cfg, &rh, &rw);
+    if ((int)rh == im.h && (int)rw == im.w) {
+      resized[i] = im;
+      continue;
+    }
+    ResizeJob j;
+    j.src = im.p, j.sw = im.w, j.sh = im.h, j.dw = (int)rw, j.dh = (int)rh;
+    j.tmp = ctx->arena.get<float>((size_t)rh * im.w * 3);
+    j.dst = ctx->arena.get<uint8_t>((size_t)rh * rw * 3);
+    jobs.push_back(j);
+    max_sw = std::max(max_sw, j.sw), max_dw = std::max(max_dw, j.dw), max_dh = std::max(max_dh, j.dh);
+    resized[i] = DevImage{j.dst, (int)rh, (int)rw};
+  }
+  if (!jobs.empty()) {
+    ResizeJob* d_jobs = to_device(ctx, jobs.data(), jobs.size());
+    launch_resize_triangle(ctx, d_jobs, (int)jobs.size(), max_sw, max_dw, max_dh);
+  }
+}
+
+struct DetResult {
+  std::vector<std::vector<float>> boxes;   // per image: count*8, discovery order
+  std::vector<std::vector<float>> scores;  // per image: count
+  float ms_net = 0, ms_post = 0;
+};
+
+// TextDetectionAdapter::execute for one list of device images, chunked by image_batch_size.
+void run_detection(oar_model* det, const std::vector<DevImage>& imgs, const oar_det_config& cfg, int batch_size,
+                   DetResult& res, bool timed) {
+  oar_ctx* ctx = det->ctx;
+  const int n = (int)imgs.size();
+  if (cfg.max_candidates <= 0) OAR_FAIL(OAR_E_INVALID, "max_candidates must be positive");
+  res.boxes.assign(n, {});
+  res.scores.assign(n, {});
+  std::vector<DevImage> resized;
+  det_resize_on_device(ctx, imgs, cfg, resized);
+  std::vector<int32_t> src_h(n), src_w(n);
+  for (int i = 0; i < n; ++i) src_h[i] = imgs[i].h, src_w[i] = imgs[i].w;
+  std::vector<DetGroup> groups;
+  batch_size = std::max(batch_size, 1);
+  for (int start = 0; start < n; start += batch_size) {
+    int end = std::min(n, start + batch_size);
+    size_t first_group = groups.size();
+    for (int i = start; i < end; ++i) {  // first-seen shape order, db.rs:299-309
+      DetGroup* hit = nullptr;
+      for (size_t gi = first_group; gi < groups.size(); ++gi)
+        if (groups[gi].H == resized[i].h && groups[gi].W == resized[i].w) hit = &groups[gi];
+      if (!hit) {
+        groups.emplace_back();
+        hit = &groups.back();
+        hit->H = resized[i].h, hit->W = resized[i].w;
+      }
+      hit->members.push_back(i);
+    }
+  }
+  for (auto& g : groups) launch_det_group(det, resized, src_h, src_w, cfg, g, 0, timed);
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& g : groups) {
+    int need = 0;
+    int tries = 0;
+    while (db_postprocess_check(g.status, &need) == 1) {
+      if (++tries > 3) OAR_FAIL(OAR_E_CAPACITY, "DB post-process component bound did not converge");
+      launch_det_group(det, resized, src_h, src_w, cfg, g, need, false);
+      OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const int mc = cfg.max_candidates;
+    for (size_t k = 0; k < g.members.size(); ++k) {
+      int cnt = g.h_counts[k];
+      int img = g.members[k];
+      res.boxes[img].assign(g.h_boxes + k * (size_t)mc * 8, g.h_boxes + k * (size_t)mc * 8 + (size_t)cnt * 8);
+      res.scores[img].assign(g.h_scores + k * (size_t)mc, g.h_scores + k * (size_t)mc + cnt);
+    }
+    if (timed && g.e_start && tries == 0) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, g.e_start, g.e_net);
+      cudaEventElapsedTime(&b, g.e_net, g.e_post);
+      res.ms_net += a, res.ms_post += b;
+    }
+  }
+}
+
+// sort_quad_boxes (sorting.rs:35-84): stable sort by (y_min, x_min), then the adjacent-swap pass
+void sort_quads_host(const float* boxes, int n, std::vector<int>& order) {
+  order.resize(n);
+  std::vector<float> ymin(n), xmin(n);
+  for (int i = 0; i < n; ++i) {
+    order[i] = i;
+    const float* b = boxes + (size_t)i * 8;
+    float mx = INFINITY, my = INFINITY;
+    for (int k = 0; k < 4; ++k) {
+      mx = std::fmin(mx, b[2 * k]);
+      my = std::fmin(my, b[2 * k + 1]);
+    }
+    xmin[i] = mx, ymin[i] = my;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (ymin[a] < ymin[b]) return true;
+    if (ymin[a] > ymin[b]) return false;
+    return xmin[a] < xmin[b];
+  });
+  for (int i = 0; i + 1 < n; ++i) {
+    for (int j = i; j >= 0; --j) {
+      int cur = order[j], nxt = order[j + 1];
+      if (std::fabs(ymin[nxt] - ymin[cur]) < 10.0f && xmin[nxt] < xmin[cur])
+        std::swap(order[j], order[j + 1]);
+      else
+        break;
+    }
+  }
+}
+
+constexpr int REC_H = 48, REC_W = 320, REC_MAX_W = 3200;  // DEFAULT_REC_IMAGE_SHAPE, constants.rs:8
+constexpr int MAX_POOLED_CROPS = 4096;                    // ocr.rs:603
+
+int64_t f32_as_usize(float v) {
+  if (!(v > 0.0f)) return 0;
+  if (v >= 9.2e18f) return INT64_MAX;
+  return (int64_t)v;
+}
+
+struct RecCrop {
+  const uint8_t* p;  // device u8 HWC
+  int h, w;
+};
+
+struct RecBatchOut {
+  int n = 0, T = 0;
+  int32_t *h_labels = nullptr, *h_cols = nullptr, *h_lens = nullptr;
+  float* h_scores = nullptr;
+};
+
+// CRNNModel::forward_refs (crnn.rs:247-293) on one batch of device crops; outputs arrive in pinned
+// memory after the stream is synchronised.
+void launch_rec_batch(oar_model* rec, const RecCrop* crops, int n, int n_chars, RecBatchOut& out) {
+  oar_ctx* ctx = rec->ctx;
+  out.n = n;
+  if (n == 0) return;
+  const float base = (float)REC_W / (float)std::max(REC_H, 1);
+  float max_ratio = base;
+  for (int i = 0; i < n; ++i) {
+    if (crops[i].h <= 0 || crops[i].w <= 0) OAR_FAIL(OAR_E_INVALID, "crop %d has invalid dimensions", i);
+    max_ratio = std::fmax(max_ratio, (float)crops[i].w / (float)std::max(crops[i].h, 1));
+  }
+  const int tensor_w = (int)std::min<int64_t>(f32_as_usize((float)REC_H * max_ratio), REC_MAX_W);
+  auto mark = ctx->arena.mark();
+  std::vector<ResizeJob> jobs(n);
+  std::vector<CrnnJob> cj(n);
+  int max_sw = 0, max_dw = 0;
+  for (int i = 0; i < n; ++i) {
+    float ratio = (float)crops[i].w / (float)crops[i].h;
+    int rw = (int)std::min<int64_t>(f32_as_usize(std::ceil((float)REC_H * ratio)), tensor_w);
+    ResizeJob& j = jobs[i];
+    j.src = crops[i].p, j.sw = crops[i].w, j.sh = crops[i].h, j.dw = rw, j.dh = REC_H;
+    j.tmp = ctx->arena.get<float>((size_t)REC_H * crops[i].w * 3);
+    j.dst = ctx->arena.get<uint8_t>((size_t)REC_H * std::max(rw, 1) * 3);
+    cj[i].src = j.dst, cj[i].rw = rw;
+    max_sw = std::max(max_sw, j.sw), max_dw = std::max(max_dw, rw);
+  }
+  ResizeJob* d_jobs = to_device(ctx, jobs.data(), jobs.size());
+  CrnnJob* d_cj = to_device(ctx, cj.data(), cj.size());
+  launch_resize_triangle(ctx, d_jobs, n, max_sw, max_dw, REC_H);
+  Tensor in;
+  in.B = n, in.H = REC_H, in.W = tensor_w, in.C = 3;
+  in.p = ctx->arena.get<float>(in.numel());
+  launch_crnn_normalize(ctx, d_cj, n, REC_H, tensor_w, in.p, /*NHWC*/ 1);
+  CtcOut ctc;
+  model_forward(rec, in, false, &ctc);
+  if (ctc.B != n || ctc.T <= 0) OAR_FAIL(OAR_E_MODEL, "recognizer produced no CTC output");
+  const int T = ctc.T;
+  out.T = T;
+  size_t bt = (size_t)n * T;
+  int32_t* d_labels = ctx->arena.get<int32_t>(bt);
+  int32_t* d_cols = ctx->arena.get<int32_t>(bt);
+  int32_t* d_lens = ctx->arena.get<int32_t>(n);
+  float* d_scores = ctx->arena.get<float>(n);
+  launch_ctc_decode(ctx, ctc.idx, ctc.prob, n, T, n_chars, d_labels, d_cols, d_lens, d_scores);
+  out.h_labels = (int32_t*)ctx->pinned_get(bt * sizeof(int32_t));
+  out.h_cols = (int32_t*)ctx->pinned_get(bt * sizeof(int32_t));
+  out.h_lens = (int32_t*)ctx->pinned_get(n * sizeof(int32_t));
+  out.h_scores = (float*)ctx->pinned_get(n * sizeof(float));
+  cudaStream_t st = ctx->stream;
+  OAR_CUDA(cudaMemcpyAsync(out.h_labels, d_labels, bt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(out.h_cols, d_cols, bt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(out.h_lens, d_lens, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(out.h_scores, d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  ctx->arena.release_to(mark);
+}
+
+void require_device(oar_ctx* ctx) {
+  if (!ctx) OAR_FAIL(OAR_E_INVALID, "null context");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void oar_det_config_default(oar_det_config* cfg) {
+  if (!cfg) return;
+  cfg->thresh = 0.3f;
+  cfg->box_thresh = 0.6f;
+  cfg->unclip_ratio = 2.0f;
+  cfg->max_candidates = 1000;
+  cfg->min_size = 3.0f;
+  cfg->limit_side_len = 960;
+  cfg->limit_type = 0;
+  cfg->max_side_limit = 4000;
+}
+
+void oar_pipeline_config_default(oar_pipeline_config* cfg) {
+  if (!cfg) return;
+  oar_det_config_default(&cfg->det);
+  cfg->image_batch_size = 8;
+  cfg->region_batch_size = 64;
+  cfg->rec_score_thresh = 0.0f;
+  cfg->n_chars = 18385;
+}
+
+const char* oar_last_error(void) { return oar::g_err; }
+int32_t oar_version(void) { return 100; }
+int64_t oar_launch_count(void) { return oar::g_launches; }
+
+int32_t oar_ctx_create(int32_t device_id, oar_ctx** out) {
+  if (!out) {
+    set_error("null output pointer");
+    return OAR_E_INVALID;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); liboar_b200 has no CPU fallback", cudaGetErrorString(e));
+    return OAR_E_NO_DEVICE;
+  }
+  if (device_id < 0 || device_id >= count) {
+    set_error("device_id %d out of range (0..%d)", device_id, count - 1);
+    return OAR_E_INVALID;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major != 10) {
+    set_error("device %d is not an sm_100 (Blackwell B200) part; this library ships sm_100a code only", device_id);
+    return OAR_E_NO_DEVICE;
+  }
+  API_TRY
+  OAR_CUDA(cudaSetDevice(device_id));
+  oar_ctx* c = new oar_ctx();
+  c->device = device_id;
+  c->sm_count = prop.multiProcessorCount;
+  OAR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  API_CATCH
+}
+
+void oar_ctx_destroy(oar_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->arena.release();
+  for (auto& s : ctx->pinned) cudaFreeHost(s.base);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->timer0) cudaEventDestroy(ctx->timer0);
+  if (ctx->timer1) cudaEventDestroy(ctx->timer1);
+  cudaFree(ctx->flush_buf);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int32_t oar_ctx_synchronize(oar_ctx* ctx) {
+  API_TRY
+  require_device(ctx);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_model** out) {
+  API_TRY
+  require_device(ctx);
+  if (!bytes || !out) OAR_FAIL(OAR_E_INVALID, "null argument");
+  *out = nullptr;
+  const uint8_t* p = (const uint8_t*)bytes;
+  if (len < 28 || memcmp(p, "OARG", 4) != 0) OAR_FAIL(OAR_E_MODEL, "not an OARG model blob");
+  uint32_t version, kind, n_ops, n_tensors;
+  uint64_t n_w;
+  memcpy(&version, p + 4, 4);
+  memcpy(&kind, p + 8, 4);
+  memcpy(&n_ops, p + 12, 4);
+  memcpy(&n_tensors, p + 16, 4);
+  memcpy(&n_w, p + 20, 8);
+  if (version != 1) OAR_FAIL(OAR_E_MODEL, "unsupported OARG version %u", version);
+  if (kind > 1) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", kind);
+  size_t need = 28 + (size_t)n_ops * sizeof(OpRec) + (size_t)n_w * 4;
+  if (len < need) OAR_FAIL(OAR_E_MODEL, "truncated model blob: %zu bytes, need %zu", len, need);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  oar_model* m = new oar_model();
+  m->ctx = ctx;
+  m->kind = (int)kind;
+  m->n_tensors = (int)n_tensors;
+  m->ops.resize(n_ops);
+  memcpy(m->ops.data(), p + 28, (size_t)n_ops * sizeof(OpRec));
+  for (size_t i = 0; i < m->ops.size(); ++i) {
+    const OpRec& op = m->ops[i];
+    bool bad = op.in0 < 0 || op.in0 >= (int)n_tensors || op.out < 0 || op.out >= (int)n_tensors ||
+               op.in1 >= (int)n_tensors;
+    for (int k = 0; k < 4; ++k)
+      bad = bad || op.w_off[k] < 0 || op.w_len[k] < 0 || (uint64_t)(op.w_off[k] + op.w_len[k]) > n_w;
+    if (bad) {
+      delete m;
+      OAR_FAIL(OAR_E_MODEL, "op %zu references tensors or weights out of range", i);
+    }
+  }
+  m->n_weights = n_w;
+  cudaError_t e = cudaMalloc(&m->d_weights, std::max<size_t>(n_w, 1) * 4);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_weights, p + 28 + (size_t)n_ops * sizeof(OpRec), n_w * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(m->d_weights);
+    delete m;
+    OAR_FAIL(OAR_E_CUDA, "weight upload failed: %s", cudaGetErrorString(e));
+  }
+  m->engine = 1;
+  tc_model_init(m);
+  *out = m;
+  API_CATCH
+}
+
+void oar_model_destroy(oar_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  tc_model_free(m);
+  cudaFree(m->d_weights);
+  delete m;
+}
+
+int32_t oar_model_kind(const oar_model* m) { return m ? m->kind : OAR_E_INVALID; }
+
+int32_t oar_model_set_engine(oar_model* m, int32_t engine) {
+  if (!m || engine < 0 || engine > 1) {
+    set_error("invalid engine selector");
+    return OAR_E_INVALID;
+  }
+  m->engine = engine;
+  return OAR_OK;
+}
+
+int32_t oar_infer_f32(oar_model* m, const float* in, const int64_t in_shape[4], float* out, size_t out_cap,
+                      int64_t out_shape[4]) {
+  API_TRY
+  if (!m || !in || !in_shape || !out || !out_shape) OAR_FAIL(OAR_E_INVALID, "null argument");
+  int64_t B = in_shape[0], C = in_shape[1], H = in_shape[2], W = in_shape[3];
+  if (B <= 0 || C != 3 || H <= 0 || W <= 0) OAR_FAIL(OAR_E_INVALID, "input must be [B,3,H,W] with positive dims");
+  oar_ctx* ctx = m->ctx;
+  CallGuard guard(ctx);
+  size_t n = (size_t)B * C * H * W;
+  float* d_nchw = ctx->arena.get<float>(n);
+  OAR_CUDA(cudaMemcpyAsync(d_nchw, in, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  Tensor x;
+  x.B = (int)B, x.H = (int)H, x.W = (int)W, x.C = 3;
+  x.p = ctx->arena.get<float>(n);
+  launch_nchw_to_nhwc(ctx, d_nchw, x.p, (int)B, 3, (int)H, (int)W);
+  CtcOut ctc;
+  Tensor y = model_forward(m, x, true, &ctc);
+  if (!y.p) OAR_FAIL(OAR_E_MODEL, "model produced no output");
+  if (m->kind == OAR_KIND_DET) {
+    out_shape[0] = y.B, out_shape[1] = y.C, out_shape[2] = y.H, out_shape[3] = y.W;
+    if (y.C != 1) OAR_FAIL(OAR_E_MODEL, "detector output has %d channels", y.C);
+  } else {
+    out_shape[0] = y.B, out_shape[1] = (int64_t)y.H * y.W, out_shape[2] = y.C, out_shape[3] = 1;
+  }
+  if (y.numel() > out_cap) OAR_FAIL(OAR_E_CAPACITY, "output needs %zu floats, capacity %zu", y.numel(), out_cap);
+  OAR_CUDA(cudaMemcpyAsync(out, y.p, y.numel() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_normalize_chw(oar_ctx* ctx, const uint8_t* rgb, int32_t batch, int32_t h, int32_t w,
+                          const int32_t src_channels[3], const float alpha[3], const float beta[3], float* out) {
+  API_TRY
+  require_device(ctx);
+  if (batch < 0 || h < 0 || w < 0) OAR_FAIL(OAR_E_INVALID, "negative dimension");
+  for (int c = 0; c < 3; ++c)
+    if (src_channels[c] < 0 || src_channels[c] > 2) OAR_FAIL(OAR_E_INVALID, "source channel out of range");
+  size_t px = (size_t)batch * h * w;
+  if (px == 0) return OAR_OK;
+  if (!rgb || !out) OAR_FAIL(OAR_E_INVALID, "null buffer");
+  CallGuard guard(ctx);
+  uint8_t* d_in = ctx->arena.get<uint8_t>(px * 3);
+  float* d_out = ctx->arena.get<float>(px * 3);
+  OAR_CUDA(cudaMemcpyAsync(d_in, rgb, px * 3, cudaMemcpyHostToDevice, ctx->stream));
+  int src[3] = {src_channels[0], src_channels[1], src_channels[2]};
+  launch_normalize(ctx, d_in, nullptr, true, d_out, batch, h, w, src, alpha, beta, 0);
+  OAR_CUDA(cudaMemcpyAsync(out, d_out, px * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_db_postprocess(oar_ctx* ctx, const float* pred, int32_t batch, int32_t h, int32_t w, const int32_t* src_h,
+                           const int32_t* src_w, const oar_det_config* cfg, float* boxes, float* scores,
+                           int32_t* counts) {
+  API_TRY
+  require_device(ctx);
+  if (!cfg || !counts) OAR_FAIL(OAR_E_INVALID, "null argument");
+  if (batch <= 0) return OAR_OK;
+  if (h <= 0 || w <= 0 || !pred || !boxes || !scores || !src_h || !src_w) OAR_FAIL(OAR_E_INVALID, "bad argument");
+  if (cfg->max_candidates <= 0) OAR_FAIL(OAR_E_INVALID, "max_candidates must be positive");
+  CallGuard guard(ctx);
+  size_t total = (size_t)batch * h * w;
+  const int mc = cfg->max_candidates;
+  float* d_pred = ctx->arena.get<float>(total);
+  OAR_CUDA(cudaMemcpyAsync(d_pred, pred, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DbPostOut out;
+  out.boxes = ctx->arena.get<float>((size_t)batch * mc * 8);
+  out.scores = ctx->arena.get<float>((size_t)batch * mc);
+  out.counts = ctx->arena.get<int32_t>(batch);
+  int hint = 0;
+  for (int tries = 0;; ++tries) {
+    auto mark = ctx->arena.mark();
+    DbPostStatus st = db_postprocess_device(ctx, d_pred, batch, h, w, src_h, src_w, *cfg, out, hint);
+    OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->arena.release_to(mark);
+    if (db_postprocess_check(st, &hint) == 0) break;
+    if (tries >= 3) OAR_FAIL(OAR_E_CAPACITY, "DB post-process component bound did not converge");
+  }
+  OAR_CUDA(cudaMemcpyAsync(counts, out.counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaMemcpyAsync(boxes, out.boxes, (size_t)batch * mc * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaMemcpyAsync(scores, out.scores, (size_t)batch * mc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_det_run(oar_model* det, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                    const oar_det_config* cfg, float* boxes, float* scores, int32_t* counts) {
+  API_TRY
+  if (!det || det->kind != OAR_KIND_DET) OAR_FAIL(OAR_E_INVALID, "not a detection model");
+  if (!cfg) OAR_FAIL(OAR_E_INVALID, "null config");
+  if (n <= 0) return OAR_OK;  // DBModel::forward on an empty batch returns empty output, db.rs:288-293
+  if (!images || !hs || !ws || !boxes || !scores || !counts) OAR_FAIL(OAR_E_INVALID, "null argument");
+  oar_ctx* ctx = det->ctx;
+  CallGuard guard(ctx);
+  std::vector<DevImage> imgs(n);
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
+    size_t bytes = (size_t)hs[i] * ws[i] * 3;
+    uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+    OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    imgs[i] = DevImage{d, hs[i], ws[i]};
+  }
+  DetResult res;
+  run_detection(det, imgs, *cfg, n, res, false);
+  const int mc = cfg->max_candidates;
+  for (int i = 0; i < n; ++i) {
+    counts[i] = (int32_t)res.scores[i].size();
+    memcpy(boxes + (size_t)i * mc * 8, res.boxes[i].data(), res.boxes[i].size() * sizeof(float));
+    memcpy(scores + (size_t)i * mc, res.scores[i].data(), res.scores[i].size() * sizeof(float));
+  }
+  API_CATCH
+}
+
+int32_t oar_sort_quad_boxes(float* boxes, int32_t n, int32_t* order) {
+  API_TRY
+  if (n < 0 || (n > 0 && !boxes)) OAR_FAIL(OAR_E_INVALID, "bad argument");
+  std::vector<int> ord;
+  sort_quads_host(boxes, n, ord);
+  std::vector<float> tmp(boxes, boxes + (size_t)n * 8);
+  for (int i = 0; i < n; ++i) {
+    memcpy(boxes + (size_t)i * 8, tmp.data() + (size_t)ord[i] * 8, 8 * sizeof(float));
+    if (order) order[i] = ord[i];
+  }
+  API_CATCH
+}
+
+int32_t oar_rotate_crop(oar_ctx* ctx, const uint8_t* image, int32_t h, int32_t w, const float* quads, int32_t n,
+                        int32_t* out_w, int32_t* out_h, int32_t* status, uint8_t* out, size_t out_cap) {
+  API_TRY
+  require_device(ctx);
+  if (n <= 0) return OAR_OK;
+  if (!image || h <= 0 || w <= 0 || !quads || !out_w || !out_h || !status) OAR_FAIL(OAR_E_INVALID, "bad argument");
+  CallGuard guard(ctx);
+  size_t bytes = (size_t)h * w * 3;
+  uint8_t* d_img = ctx->arena.get<uint8_t>(bytes);
+  OAR_CUDA(cudaMemcpyAsync(d_img, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ImageRef ref{d_img, h, w};
+  ImageRef* d_ref = to_device(ctx, &ref, 1);
+  std::vector<CropPlan> plans(n);
+  for (int i = 0; i < n; ++i) {
+    memset(&plans[i], 0, sizeof(CropPlan));
+    memcpy(plans[i].quad, quads + (size_t)i * 8, 8 * sizeof(float));
+    plans[i].img = 0;
+  }
+  CropPlan* d_plans = to_device(ctx, plans.data(), plans.size());
+  launch_crop_plan(ctx, d_plans, n, d_ref);
+  CropPlan* h_plans = (CropPlan*)ctx->pinned_get(sizeof(CropPlan) * n);
+  OAR_CUDA(cudaMemcpyAsync(h_plans, d_plans, sizeof(CropPlan) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    status[i] = h_plans[i].status;
+    out_w[i] = h_plans[i].status ? 0 : h_plans[i].ow;
+    out_h[i] = h_plans[i].status ? 0 : h_plans[i].oh;
+    h_plans[i].out_off = total * 3;
+    if (!h_plans[i].status) total += (long long)h_plans[i].ow * h_plans[i].oh;
+  }
+  if (!out) return OAR_OK;
+  if ((size_t)total * 3 > out_cap) OAR_FAIL(OAR_E_CAPACITY, "crops need %lld bytes, capacity %zu", total * 3, out_cap);
+  if (total == 0) return OAR_OK;
+  OAR_CUDA(cudaMemcpyAsync(d_plans, h_plans, sizeof(CropPlan) * n, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* pool = ctx->arena.get<uint8_t>((size_t)total * 3);
+  launch_crop_warp(ctx, d_plans, n, d_ref, pool, total);
+  OAR_CUDA(cudaMemcpyAsync(out, pool, (size_t)total * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_crnn_preprocess(oar_ctx* ctx, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws,
+                            int32_t n, float* out, size_t out_cap, int32_t* tensor_w) {
+  API_TRY
+  require_device(ctx);
+  if (!tensor_w) OAR_FAIL(OAR_E_INVALID, "null argument");
+  *tensor_w = 0;
+  if (n <= 0) return OAR_OK;  // preprocess_refs on an empty batch yields a (0,0,0,0) tensor
+  if (!crops || !hs || !ws) OAR_FAIL(OAR_E_INVALID, "null argument");
+  float max_ratio = (float)REC_W / (float)REC_H;
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !crops[i]) OAR_FAIL(OAR_E_INVALID, "crop %d is empty", i);
+    max_ratio = std::fmax(max_ratio, (float)ws[i] / (float)std::max(hs[i], 1));
+  }
+  const int tw = (int)std::min<int64_t>(f32_as_usize((float)REC_H * max_ratio), REC_MAX_W);
+  *tensor_w = tw;
+  if (!out) return OAR_OK;
+  size_t total = (size_t)n * 3 * REC_H * tw;
+  if (total > out_cap) OAR_FAIL(OAR_E_CAPACITY, "tensor needs %zu floats, capacity %zu", total, out_cap);
+  CallGuard guard(ctx);
+  std::vector<ResizeJob> jobs(n);
+  std::vector<CrnnJob> cj(n);
+  int max_sw = 0, max_dw = 0;
+  for (int i = 0; i < n; ++i) {
+    size_t bytes = (size_t)hs[i] * ws[i] * 3;
+    uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+    OAR_CUDA(cudaMemcpyAsync(d, crops[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    float ratio = (float)ws[i] / (float)hs[i];
+    int rw = (int)std::min<int64_t>(f32_as_usize(std::ceil((float)REC_H * ratio)), tw);
+    ResizeJob& j = jobs[i];
+    j.src = d, j.sw = ws[i], j.sh = hs[i], j.dw = rw, j.dh = REC_H;
+    j.tmp = ctx->arena.get<float>((size_t)REC_H * ws[i] * 3);
+    j.dst = ctx->arena.get<uint8_t>((size_t)REC_H * std::max(rw, 1) * 3);
+    cj[i].src = j.dst, cj[i].rw = rw;
+    max_sw = std::max(max_sw, j.sw), max_dw = std::max(max_dw, rw);
+  }
+  ResizeJob* d_jobs = to_device(ctx, jobs.data(), jobs.size());
+  CrnnJob* d_cj = to_device(ctx, cj.data(), cj.size());
+  launch_resize_triangle(ctx, d_jobs, n, max_sw, max_dw, REC_H);
+  float* d_out = ctx->arena.get<float>(total);
+  launch_crnn_normalize(ctx, d_cj, n, REC_H, tw, d_out, 0);
+  OAR_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_ctc_decode(oar_ctx* ctx, const float* pred, int32_t b, int32_t t, int32_t v, int32_t n_chars,
+                       int32_t* idx, float* prob, int32_t* labels, int32_t* cols, int32_t* lens, float* scores) {
+  API_TRY
+  require_device(ctx);
+  if (b < 0 || t < 0 || v < 0) OAR_FAIL(OAR_E_INVALID, "negative dimension");
+  // decode.rs:464-476: "no batch entries are returned when any dimension is zero" -- outputs untouched
+  if (b == 0 || t == 0 || v == 0) return OAR_OK;
+  if (!idx || !prob || !labels || !cols || !lens || !scores) OAR_FAIL(OAR_E_INVALID, "null argument");
+  size_t rows = (size_t)b * t;
+  if (!pred) OAR_FAIL(OAR_E_INVALID, "null argument");
+  CallGuard guard(ctx);
+  float* d_pred = ctx->arena.get<float>(rows * v);
+  OAR_CUDA(cudaMemcpyAsync(d_pred, pred, rows * v * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t* d_idx = ctx->arena.get<int32_t>(rows);
+  float* d_prob = ctx->arena.get<float>(rows);
+  int32_t* d_labels = ctx->arena.get<int32_t>(rows);
+  int32_t* d_cols = ctx->arena.get<int32_t>(rows);
+  int32_t* d_lens = ctx->arena.get<int32_t>(b);
+  float* d_scores = ctx->arena.get<float>(b);
+  launch_ctc_argmax(ctx, d_pred, (long long)rows, v, d_idx, d_prob);
+  launch_ctc_decode(ctx, d_idx, d_prob, b, t, n_chars, d_labels, d_cols, d_lens, d_scores);
+  cudaStream_t st = ctx->stream;
+  OAR_CUDA(cudaMemcpyAsync(idx, d_idx, rows * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(prob, d_prob, rows * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(labels, d_labels, rows * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(cols, d_cols, rows * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(lens, d_lens, (size_t)b * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(scores, d_scores, (size_t)b * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaStreamSynchronize(st));
+  API_CATCH
+}
+
+int32_t oar_rec_run(oar_model* rec, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                    int32_t n_chars, int32_t* labels, int32_t* cols, int32_t* lens, float* scores, int32_t t_cap,
+                    int32_t* t_out) {
+  API_TRY
+  if (!rec || rec->kind != OAR_KIND_REC) OAR_FAIL(OAR_E_INVALID, "not a recognition model");
+  if (t_out) *t_out = 0;
+  if (n <= 0) return OAR_OK;
+  if (!crops || !hs || !ws || !labels || !cols || !lens || !scores) OAR_FAIL(OAR_E_INVALID, "null argument");
+  oar_ctx* ctx = rec->ctx;
+  CallGuard guard(ctx);
+  std::vector<RecCrop> rc(n);
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !crops[i]) OAR_FAIL(OAR_E_INVALID, "crop %d is empty", i);
+    size_t bytes = (size_t)hs[i] * ws[i] * 3;
+    uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+    OAR_CUDA(cudaMemcpyAsync(d, crops[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc[i] = RecCrop{d, hs[i], ws[i]};
+  }
+  RecBatchOut out;
+  launch_rec_batch(rec, rc.data(), n, n_chars, out);
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (out.T > t_cap) OAR_FAIL(OAR_E_CAPACITY, "sequence length %d exceeds capacity %d", out.T, t_cap);
+  if (t_out) *t_out = out.T;
+  for (int i = 0; i < n; ++i) {
+    memcpy(labels + (size_t)i * t_cap, out.h_labels + (size_t)i * out.T, (size_t)out.T * 4);
+    memcpy(cols + (size_t)i * t_cap, out.h_cols + (size_t)i * out.T, (size_t)out.T * 4);
+    lens[i] = out.h_lens[i];
+    scores[i] = out.h_scores[i];
+  }
+  API_CATCH
+}
+
+int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
+                         const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
+                         oar_ocr_result* out) {
+  API_TRY
+  if (!det || det->kind != OAR_KIND_DET || !rec || rec->kind != OAR_KIND_REC)
+    OAR_FAIL(OAR_E_INVALID, "pipeline needs one detection and one recognition model");
+  if (det->ctx != rec->ctx) OAR_FAIL(OAR_E_INVALID, "both models must live on the same context");
+  if (!cfg || !out) OAR_FAIL(OAR_E_INVALID, "null argument");
+  // OAROCR::predict rejects an empty image list (ocr.rs:525-532)
+  if (n <= 0 || !images || !hs || !ws) OAR_FAIL(OAR_E_INVALID, "images: expected non-empty slice, got empty slice");
+  if (cfg->image_batch_size <= 0 || cfg->region_batch_size <= 0)
+    OAR_FAIL(OAR_E_INVALID, "batch sizes must be positive");  // ocr.rs:1168-1195
+  if (!out->region_off) OAR_FAIL(OAR_E_INVALID, "null result buffers");
+  oar_ctx* ctx = det->ctx;
+  CallGuard guard(ctx);
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) e = ctx->next_event();
+  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = 0.0f;
+  out->h2d_bytes = out->d2h_bytes = 0;
+  cudaEventRecord(ev[0], st);
+
+  // ---- pages into HBM
+  std::vector<DevImage> imgs(n);
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
+    if (images_on_device) {
+      imgs[i] = DevImage{images[i], hs[i], ws[i]};
+    } else {
+      size_t bytes = (size_t)hs[i] * ws[i] * 3;
+      uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+      OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, st));
+      imgs[i] = DevImage{d, hs[i], ws[i]};
+      out->h2d_bytes += (int64_t)bytes;
+    }
+  }
+  cudaEventRecord(ev[1], st);
+
+  // ---- detection (chunks of image_batch_size) + reading-order sort
+  DetResult dres;
+  run_detection(det, imgs, cfg->det, cfg->image_batch_size, dres, true);
+  out->ms_det = dres.ms_net;
+  out->ms_post = dres.ms_post;
+  cudaEventRecord(ev[2], st);
+  std::vector<std::vector<float>> sorted_boxes(n);
+  std::vector<int> box_first(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    int cnt = (int)dres.scores[i].size();
+    std::vector<int> ord;
+    sort_quads_host(dres.boxes[i].data(), cnt, ord);
+    sorted_boxes[i].resize((size_t)cnt * 8);
+    for (int k = 0; k < cnt; ++k)
+      memcpy(&sorted_boxes[i][(size_t)k * 8], &dres.boxes[i][(size_t)ord[k] * 8], 8 * sizeof(float));
+    box_first[i + 1] = box_first[i] + cnt;
+    out->d2h_bytes += (int64_t)cnt * 36 + 4;
+  }
+  const int n_boxes = box_first[n];
+
+  // ---- crop every box (plan on device, sizes back to the host, one warp launch for all)
+  std::vector<CropPlan> plans(n_boxes);
+  CropPlan* h_plans = nullptr;
+  uint8_t* pool = nullptr;
+  if (n_boxes > 0) {
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < box_first[i + 1] - box_first[i]; ++k) {
+        CropPlan& p = plans[box_first[i] + k];
+        memset(&p, 0, sizeof(CropPlan));
+        memcpy(p.quad, &sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
+        p.img = i;
+      }
+    std::vector<ImageRef> refs(n);
+    for (int i = 0; i < n; ++i) refs[i] = ImageRef{imgs[i].p, imgs[i].h, imgs[i].w};
+    ImageRef* d_refs = to_device(ctx, refs.data(), refs.size());
+    CropPlan* d_plans = to_device(ctx, plans.data(), plans.size());
+    launch_crop_plan(ctx, d_plans, n_boxes, d_refs);
+    h_plans = (CropPlan*)ctx->pinned_get(sizeof(CropPlan) * n_boxes);
+    OAR_CUDA(cudaMemcpyAsync(h_plans, d_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyDeviceToHost, st));
+    OAR_CUDA(cudaStreamSynchronize(st));
+    long long total_px = 0;
+    for (int i = 0; i < n_boxes; ++i) {
+      h_plans[i].out_off = total_px * 3;
+      if (h_plans[i].status == 0) total_px += (long long)h_plans[i].ow * h_plans[i].oh;
+    }
+    if (total_px > 0) {
+      OAR_CUDA(cudaMemcpyAsync(d_plans, h_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyHostToDevice, st));
+      pool = ctx->arena.get<uint8_t>((size_t)total_px * 3);
+      launch_crop_warp(ctx, d_plans, n_boxes, d_refs, pool, total_px);
+    }
+  }
+  cudaEventRecord(ev[3], st);
+
+  // ---- recognition: pool crops across images, flush at MAX_POOLED_CROPS, sort by wh_ratio, chunk
+  struct Pooled {
+    int box;  // global box index (image-major, reading order)
+  };
+  struct Wave {
+    std::vector<int> sorted;  // global box indices, wh-ratio order
+    std::vector<RecBatchOut> chunks;
+  };
+  std::vector<Wave> waves;
+  {
+    std::vector<int> cur;
+    for (int i = 0; i < n_boxes; ++i) {
+      if (h_plans[i].status != 0) continue;  // failed crop: skipped, processors.rs:104-106
+      cur.push_back(i);
+      if ((int)cur.size() >= MAX_POOLED_CROPS) {
+        waves.push_back(Wave{cur, {}});
+        cur.clear();
+      }
+    }
+    if (!cur.empty()) waves.push_back(Wave{cur, {}});
+  }
+  for (auto& wv : waves) {
+    std::stable_sort(wv.sorted.begin(), wv.sorted.end(),
+                     [&](int a, int b) { return h_plans[a].wh_ratio < h_plans[b].wh_ratio; });
+    const int bs = cfg->region_batch_size;
+    for (size_t s0 = 0; s0 < wv.sorted.size(); s0 += bs) {
+      int m = (int)std::min<size_t>(bs, wv.sorted.size() - s0);
+      std::vector<RecCrop> rc(m);
+      for (int k = 0; k < m; ++k) {
+        const CropPlan& p = h_plans[wv.sorted[s0 + k]];
+        rc[k] = RecCrop{pool + p.out_off, p.oh, p.ow};
+      }
+      wv.chunks.emplace_back();
+      launch_rec_batch(rec, rc.data(), m, cfg->n_chars, wv.chunks.back());
+    }
+  }
+  cudaEventRecord(ev[4], st);
+  OAR_CUDA(cudaStreamSynchronize(st));
+
+  // ---- scatter to per-image, detection-index order (ocr.rs:879-892, 637-656)
+  std::vector<int> lab_len(n_boxes, -1);
+  std::vector<const int32_t*> lab_ptr(n_boxes, nullptr);
+  std::vector<float> rec_score(n_boxes, 0.0f);
+  for (auto& wv : waves) {
+    size_t s0 = 0;
+    for (auto& ch : wv.chunks) {
+      for (int k = 0; k < ch.n; ++k) {
+        int box = wv.sorted[s0 + k];
+        float sc = ch.h_scores[k];
+        rec_score[box] = sc;
+        // TextRecognitionAdapter::execute: score below the threshold keeps the slot with empty text
+        bool keep = sc >= cfg->rec_score_thresh;
+        lab_len[box] = keep ? ch.h_lens[k] : 0;
+        lab_ptr[box] = ch.h_labels + (size_t)k * ch.T;
+      }
+      out->d2h_bytes += (int64_t)ch.n * (ch.T * 8 + 8);
+      s0 += ch.n;
+    }
+  }
+  int r = 0;
+  long long nl = 0;
+  for (int i = 0; i < n; ++i) {
+    out->region_off[i] = r;
+    for (int k = 0; k < box_first[i + 1] - box_first[i]; ++k) {
+      int box = box_first[i] + k;
+      if (lab_len[box] < 0) continue;
+      if (r >= out->cap_regions || nl + lab_len[box] > out->cap_labels)
+        OAR_FAIL(OAR_E_CAPACITY, "result buffers too small (regions %d, labels %d)", out->cap_regions,
+                 out->cap_labels);
+      if (out->boxes) memcpy(out->boxes + (size_t)r * 8, &sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
+      if (out->scores) out->scores[r] = rec_score[box];
+      if (out->det_index) out->det_index[r] = k;
+      if (out->label_off) out->label_off[r] = (int32_t)nl;
+      if (out->labels && lab_len[box] > 0) memcpy(out->labels + nl, lab_ptr[box], (size_t)lab_len[box] * 4);
+      nl += lab_len[box];
+      ++r;
+    }
+  }
+  out->region_off[n] = r;
+  if (out->label_off) out->label_off[r] = (int32_t)nl;
+  cudaEventElapsedTime(&out->ms_h2d, ev[0], ev[1]);
+  cudaEventElapsedTime(&out->ms_crop, ev[2], ev[3]);
+  cudaEventElapsedTime(&out->ms_rec, ev[3], ev[4]);
+  cudaEventElapsedTime(&out->ms_total, ev[0], ev[4]);
+  API_CATCH
+}
+
+int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out) {
+  API_TRY
+  require_device(ctx);
+  if (!out) OAR_FAIL(OAR_E_INVALID, "null argument");
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  OAR_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  API_CATCH
+}
+
+int32_t oar_device_free(oar_ctx* ctx, void* p) {
+  API_TRY
+  require_device(ctx);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  OAR_CUDA(cudaFree(p));
+  API_CATCH
+}
+
+int32_t oar_memcpy_h2d(oar_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  API_TRY
+  require_device(ctx);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  OAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_timer_start(oar_ctx* ctx) {
+  API_TRY
+  require_device(ctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->timer0) {
+    OAR_CUDA(cudaEventCreate(&ctx->timer0));
+    OAR_CUDA(cudaEventCreate(&ctx->timer1));
+  }
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  OAR_CUDA(cudaEventRecord(ctx->timer0, ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_timer_stop(oar_ctx* ctx, float* ms) {
+  API_TRY
+  require_device(ctx);
+  if (!ms || !ctx->timer0) OAR_FAIL(OAR_E_INVALID, "timer was not started");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  OAR_CUDA(cudaEventRecord(ctx->timer1, ctx->stream));
+  OAR_CUDA(cudaEventSynchronize(ctx->timer1));
+  OAR_CUDA(cudaEventElapsedTime(ms, ctx->timer0, ctx->timer1));
+  API_CATCH
+}
+
+int32_t oar_l2_flush(oar_ctx* ctx) {
+  API_TRY
+  require_device(ctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  OAR_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)256 << 20;
+  if (!ctx->flush_buf) OAR_CUDA(cudaMalloc(&ctx->flush_buf, bytes));
+  OAR_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, bytes, ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_profile_enable(oar_ctx* ctx, int32_t on) {
+  if (!ctx) return OAR_E_INVALID;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->profile = on != 0;
+  return OAR_OK;
+}
+
+int32_t oar_profile_read(oar_ctx* ctx, oar_kernel_record* recs, int32_t cap) {
+  if (!ctx) return 0;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  int n = 0;
+  for (auto& r : ctx->prof) {
+    if (n >= cap) break;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+      cudaGetLastError();
+      ms = 0.0f;
+    }
+    recs[n].name = r.name;
+    recs[n].ms = ms;
+    recs[n].flops = r.flops;
+    recs[n].bytes = r.bytes;
+    ++n;
+  }
+  return n;
+}
+
+}  // extern "C"

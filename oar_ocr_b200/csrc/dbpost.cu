@@ -1,0 +1,891 @@
+// dbpost.cu -- DB detector post-processing on device (compiled with -fmad=false).
+//
+// Replaces DBPostProcess::apply (oar-ocr-core/src/processors/db_postprocess.rs:100-221),
+// boxes_from_bitmap (db_bitmap.rs:84-150) and everything it calls:
+//   threshold_to_mask (db_postprocess.rs:185-221), imageproc::find_contours (Suzuki-Abe border
+//   following, db_bitmap.rs:100), get_mini_boxes_from_contour/points (db_bitmap.rs:153-202,
+//   253-277), simplify_chain_points (:207-239), get_min_area_rect_from_points
+//   (geometry.rs:310-441), box_score_fast + process_scanline (db_score.rs:34-134,
+//   geometry.rs:1087-1164), unclip via Clipper2 round-join offsetting (db_bitmap.rs:279-368).
+//
+// The reference does this serially per image on one host thread.  Here:
+//   1. threshold + union-find connected-component labelling (8-connectivity): the root of a
+//      component is its raster-first pixel.  Border following only ever reads zero/non-zero,
+//      and the visited marks of one component never influence another, so
+//   2. one warp per component replays the raster scan restricted to that component's bounding
+//      box and follows its outer and hole borders exactly as the sequential algorithm would
+//      (8 lanes probe the 8-neighbourhood per step), appending points to a global pool;
+//   3. contour records are radix-sorted by (image, start pixel) = discovery order, which also
+//      implements the `take(max_candidates)` cut;
+//   4. one thread per candidate does the small sequential geometry in the reference's own f32
+//      operation order (row sums of box_score_fast are accumulated left-to-right, rows in order);
+//   5. survivors are compacted in discovery order.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "prepost.cuh"
+
+namespace oar {
+
+// ---------------------------------------------------------------------------
+// 1. threshold + CCL
+// ---------------------------------------------------------------------------
+__global__ void db_init_kernel(const float* __restrict__ pred, float thresh, uint8_t* __restrict__ state,
+                               int32_t* __restrict__ lab, size_t total, int HW) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  bool fg = pred[i] > thresh;  // strict, db_postprocess.rs:202
+  state[i] = fg ? 1 : 0;
+  lab[i] = fg ? (int32_t)(i % HW) : -1;
+}
+
+__device__ __forceinline__ int32_t uf_find(const int32_t* lab, int32_t x) {
+  int32_t p = lab[x];
+  while (p != x) {
+    x = p;
+    p = lab[x];
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* lab, int32_t a, int32_t b) {
+  bool done = false;
+  while (!done) {
+    a = uf_find(lab, a);
+    b = uf_find(lab, b);
+    if (a == b) return;
+    if (a > b) {
+      int32_t t = a;
+      a = b;
+      b = t;
+    }
+    int32_t old = atomicMin(&lab[b], a);
+    done = (old == b);
+    b = old;
+  }
+}
+
+__global__ void db_merge_kernel(const uint8_t* __restrict__ state, int32_t* __restrict__ lab, int B, int H, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W;
+  if (i >= total) return;
+  if (!state[i]) return;
+  int HW = H * W;
+  int b = (int)(i / HW);
+  int li = (int)(i - (size_t)b * HW);
+  int y = li / W, x = li - y * W;
+  const uint8_t* st = state + (size_t)b * HW;
+  int32_t* L = lab + (size_t)b * HW;
+  if (x > 0 && st[li - 1]) uf_union(L, li, li - 1);
+  if (y > 0) {
+    if (st[li - W]) uf_union(L, li, li - W);
+    if (x > 0 && st[li - W - 1]) uf_union(L, li, li - W - 1);
+    if (x + 1 < W && st[li - W + 1]) uf_union(L, li, li - W + 1);
+  }
+}
+
+struct Comp {
+  int img, root;
+  int ymax, xmin, xmax;
+};
+
+__global__ void db_flatten_kernel(const uint8_t* __restrict__ state, int32_t* __restrict__ lab,
+                                  int32_t* __restrict__ slot_of, Comp* __restrict__ comps, int* __restrict__ n_comps,
+                                  int comp_cap, int B, int H, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W;
+  if (i >= total) return;
+  if (!state[i]) return;
+  int HW = H * W;
+  int b = (int)(i / HW);
+  int li = (int)(i - (size_t)b * HW);
+  int32_t* L = lab + (size_t)b * HW;
+  int32_t r = uf_find(L, li);
+  L[li] = r;  // benign race: every writer stores an ancestor-or-root on the same chain
+  if (r == li) {
+    int s = atomicAdd(n_comps, 1);
+    if (s < comp_cap) {
+      int y = li / W, x = li - y * W;
+      comps[s] = Comp{b, li, y, x, x};
+      slot_of[i] = s;
+    } else {
+      slot_of[i] = -1;
+    }
+  }
+}
+
+__global__ void db_bbox_kernel(const uint8_t* __restrict__ state, const int32_t* __restrict__ lab,
+                               const int32_t* __restrict__ slot_of, Comp* __restrict__ comps, int B, int H, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W;
+  if (i >= total) return;
+  if (!state[i]) return;
+  int HW = H * W;
+  int b = (int)(i / HW);
+  int li = (int)(i - (size_t)b * HW);
+  int y = li / W, x = li - y * W;
+  bool wz = (x == 0) || !state[i - 1];
+  bool ez = (x + 1 == W) || !state[i + 1];
+  if (!wz && !ez) return;
+  int32_t r = uf_find(lab + (size_t)b * HW, li);
+  int s = slot_of[(size_t)b * HW + r];
+  if (s < 0) return;
+  atomicMax(&comps[s].ymax, y);
+  if (wz) atomicMin(&comps[s].xmin, x);
+  if (ez) atomicMax(&comps[s].xmax, x);
+}
+
+// ---------------------------------------------------------------------------
+// 2. border following, one warp per component
+// ---------------------------------------------------------------------------
+struct ContourRec {
+  int img, start;   // start = y*W + x
+  long long off;    // into the point pool
+  int len;
+};
+
+__constant__ int c_RX[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+__constant__ int c_RY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// (dx+1) + 3*(dy+1) -> ring index
+__constant__ int c_DIR[9] = {1, 2, 3, 0, -1, 4, 7, 6, 5};
+
+// Follows one border from (sx,sy).  start_dir = ring index of the adjacent zero pixel.
+// All 32 lanes execute; lanes 0..7 probe.  When pts != nullptr, writes points and the
+// visited marks (2 = +nbd, 3 = -nbd).  Returns the number of points.
+__device__ int follow_border(uint8_t* st, int W, int H, int sx, int sy, int start_dir, short2* pts, int lane) {
+  auto nonzero = [&](int x, int y) -> bool { return x >= 0 && y >= 0 && x < W && y < H && st[(size_t)y * W + x] != 0; };
+  int k = lane & 7;
+  int d = (start_dir + k) & 7;
+  bool hit = (lane < 8) && nonzero(sx + c_RX[d], sy + c_RY[d]);
+  unsigned mask = __ballot_sync(0xffffffffu, hit) & 0xffu;
+  if (!mask) {
+    if (pts && lane == 0) {
+      pts[0] = make_short2((short)sx, (short)sy);
+      st[(size_t)sy * W + sx] = 3;
+    }
+    return 1;
+  }
+  int k1 = __ffs(mask) - 1;
+  int d1 = (start_dir + k1) & 7;
+  int p1x = sx + c_RX[d1], p1y = sy + c_RY[d1];
+  int p2x = p1x, p2y = p1y, p3x = sx, p3y = sy;
+  int n = 0;
+  for (;;) {
+    if (pts && lane == 0) pts[n] = make_short2((short)p3x, (short)p3y);
+    ++n;
+    int front = c_DIR[(p2x - p3x + 1) + 3 * (p2y - p3y + 1)];
+    int dk = (front - 1 - k + 16) & 7;  // k = 7 -> front itself (examined last)
+    bool h2 = (lane < 8) && nonzero(p3x + c_RX[dk], p3y + c_RY[dk]);
+    unsigned m2 = __ballot_sync(0xffffffffu, h2) & 0xffu;
+    int k4 = __ffs(m2) - 1;  // never -1: p2 is non-zero
+    int d4 = (front - 1 - k4 + 16) & 7;
+    int p4x = p3x + c_RX[d4], p4y = p3y + c_RY[d4];
+    int kE = (front - 5 + 16) & 7;  // the probe index that looks East
+    bool right_edge = kE < k4;
+    if (pts && lane == 0) {
+      size_t o = (size_t)p3y * W + p3x;
+      if (p3x + 1 == W || right_edge)
+        st[o] = 3;
+      else if (st[o] == 1)
+        st[o] = 2;
+    }
+    if (p4x == sx && p4y == sy && p3x == p1x && p3y == p1y) break;
+    p2x = p3x, p2y = p3y;
+    p3x = p4x, p3y = p4y;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(128) db_trace_kernel(uint8_t* __restrict__ state, const int32_t* __restrict__ lab,
+                                                       const Comp* __restrict__ comps, const int* __restrict__ n_comps,
+                                                       int comp_cap, int H, int W, short2* __restrict__ pool,
+                                                       unsigned long long* __restrict__ pool_used,
+                                                       unsigned long long pool_cap, ContourRec* __restrict__ recs,
+                                                       int* __restrict__ n_recs, int rec_cap, int* __restrict__ err) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int nc = min(*n_comps, comp_cap);
+  if (warp >= nc) return;
+  Comp c = comps[warp];
+  size_t HW = (size_t)H * W;
+  uint8_t* st = state + (size_t)c.img * HW;
+  const int32_t* L = lab + (size_t)c.img * HW;
+  int y0 = c.root / W;
+  for (int y = y0; y <= c.ymax; ++y) {
+    for (int xb = c.xmin; xb <= c.xmax; xb += 32) {
+      int x = xb + lane;
+      bool cand = false;
+      if (x <= c.xmax) {
+        size_t o = (size_t)y * W + x;
+        if (st[o] != 0 && L[o] == c.root) {
+          bool wz = (x > 0) && st[o - 1] == 0;
+          bool ez = (x + 1 < W) && st[o + 1] == 0;
+          cand = wz || ez;
+        }
+      }
+      unsigned cm = __ballot_sync(0xffffffffu, cand);
+      while (cm) {
+        int l = __ffs(cm) - 1;
+        cm &= cm - 1;
+        int cx = xb + l;
+        size_t o = (size_t)y * W + cx;
+        uint8_t s = st[o];
+        int start_dir = -1;
+        if (s == 1 && cx > 0 && st[o - 1] == 0)
+          start_dir = 0;  // outer border, adjacent = West
+        else if ((s == 1 || s == 2) && cx + 1 < W && st[o + 1] == 0)
+          start_dir = 4;  // hole border, adjacent = East
+        if (start_dir < 0) continue;
+        int n = follow_border(st, W, H, cx, y, start_dir, nullptr, lane);
+        unsigned long long off = 0;
+        int ri = -1;
+        if (lane == 0) {
+          off = atomicAdd(pool_used, (unsigned long long)n);
+          ri = atomicAdd(n_recs, 1);
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        ri = __shfl_sync(0xffffffffu, ri, 0);
+        if (off + n > pool_cap || ri >= rec_cap) {
+          if (lane == 0) atomicExch(err, 1);
+          return;
+        }
+        follow_border(st, W, H, cx, y, start_dir, pool + off, lane);
+        if (lane == 0) recs[ri] = ContourRec{c.img, (int)o, (long long)off, n};
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 3. ordering helpers
+// ---------------------------------------------------------------------------
+__global__ void db_keys_kernel(const ContourRec* __restrict__ recs, const int* __restrict__ n_recs, int rec_cap,
+                               unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rec_cap) return;
+  int n = min(*n_recs, rec_cap);
+  if (i < n) {
+    keys[i] = ((unsigned long long)(unsigned)recs[i].img << 32) | (unsigned)recs[i].start;
+    vals[i] = i;
+  } else {
+    keys[i] = ~0ull;
+    vals[i] = -1;
+  }
+}
+
+__global__ void db_img_first_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ n_recs,
+                                    int rec_cap, int B, int* __restrict__ first) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  int n = min(*n_recs, rec_cap);
+  unsigned long long key = (unsigned long long)(unsigned)b << 32;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (keys[mid] < key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  first[b] = lo;
+}
+
+// ---------------------------------------------------------------------------
+// 4. per-candidate geometry (one thread each)
+// ---------------------------------------------------------------------------
+struct MinRect {
+  float cx, cy, w, h, angle;
+};
+
+__device__ __forceinline__ int total_cmp_f32(float a, float b) {
+  int ia = __float_as_int(a), ib = __float_as_int(b);
+  ia ^= (int)(((unsigned)(ia >> 31)) >> 1);
+  ib ^= (int)(((unsigned)(ib >> 31)) >> 1);
+  return ia < ib ? -1 : (ia > ib ? 1 : 0);
+}
+
+// min-area rect over a convex hull given in the reference's hull order (geometry.rs:355-440)
+__device__ MinRect min_rect_from_hull(const float* hx, const float* hy, int n) {
+  MinRect best{0.f, 0.f, 0.f, 0.f, 0.f};
+  float min_area = 3.402823466e+38f;
+  const float PI_F = 3.14159265358979323846f;
+  for (int i = 0; i < n; ++i) {
+    int j = (i + 1) % n;
+    float ex = hx[j] - hx[i], ey = hy[j] - hy[i];
+    float l2 = ex * ex + ey * ey;
+    if (l2 < 1.1920929e-7f) continue;
+    float inv = 1.0f / sqrtf(l2);
+    float nx = ex * inv, ny = ey * inv;
+    float px = -ny, py = nx;
+    float hix = hx[i], hiy = hy[i];
+    float min_n = 3.402823466e+38f, max_n = -3.402823466e+38f, min_p = 3.402823466e+38f, max_p = -3.402823466e+38f;
+    for (int q = 0; q < n; ++q) {
+      float dx = hx[q] - hix, dy = hy[q] - hiy;
+      float pn = nx * dx + ny * dy;
+      float pp = px * dx + py * dy;
+      if (pn < min_n) min_n = pn;
+      if (pn > max_n) max_n = pn;
+      if (pp < min_p) min_p = pp;
+      if (pp > max_p) max_p = pp;
+    }
+    float width = max_n - min_n, height = max_p - min_p;
+    float area = width * height;
+    if (area < min_area) {
+      min_area = area;
+      float cn = (min_n + max_n) * 0.5f, cp = (min_p + max_p) * 0.5f;
+      best.cx = hix + cn * nx + cp * px;
+      best.cy = hiy + cn * ny + cp * py;
+      best.w = width;
+      best.h = height;
+      best.angle = atan2f(ny, nx) * 180.0f / PI_F;
+    }
+  }
+  return best;
+}
+
+// degenerate hull (< 3 points) branch, geometry.rs:326-353
+__device__ MinRect aabb_rect(const float* x, const float* y, int n) {
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    if (x[i] < mnx) mnx = x[i];
+    if (x[i] > mxx) mxx = x[i];
+    if (y[i] < mny) mny = y[i];
+    if (y[i] > mxy) mxy = y[i];
+  }
+  if (!isfinite(mnx)) return MinRect{0.f, 0.f, 0.f, 0.f, 0.f};
+  return MinRect{(mnx + mxx) * 0.5f, (mny + mxy) * 0.5f, mxx - mnx, mxy - mny, 0.0f};
+}
+
+// box_points_without_reorder + paddlex_order_mini_box_points (db_bitmap.rs:187-202, 253-277)
+__device__ bool rect_to_ordered_box(const MinRect& r, float bx[4], float by[4], float* min_side) {
+  float ms = fminf(r.w, r.h);
+  if (!isfinite(ms) || ms <= 0.0f) return false;
+  const float PI_F = 3.14159265358979323846f;
+  float rad = r.angle * PI_F / 180.0f;
+  // libm cosf/sinf are evaluated in double and rounded once; do the same
+  float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+  float w2 = r.w / 2.0f, h2 = r.h / 2.0f;
+  float cxs[4] = {-w2, w2, w2, -w2}, cys[4] = {-h2, -h2, h2, h2};
+  float px[4], py[4];
+  for (int i = 0; i < 4; ++i) {
+    px[i] = cxs[i] * ca - cys[i] * sa + r.cx;
+    py[i] = cxs[i] * sa + cys[i] * ca + r.cy;
+  }
+  for (int a = 1; a < 4; ++a) {  // stable sort by x
+    float kx = px[a], ky = py[a];
+    int b = a - 1;
+    while (b >= 0 && px[b] > kx) {
+      px[b + 1] = px[b], py[b + 1] = py[b];
+      --b;
+    }
+    px[b + 1] = kx, py[b + 1] = ky;
+  }
+  int i1, i4, i2, i3;
+  if (py[1] > py[0]) i1 = 0, i4 = 1; else i1 = 1, i4 = 0;
+  if (py[3] > py[2]) i2 = 2, i3 = 3; else i2 = 3, i3 = 2;
+  bx[0] = px[i1], by[0] = py[i1];
+  bx[1] = px[i2], by[1] = py[i2];
+  bx[2] = px[i3], by[2] = py[i3];
+  bx[3] = px[i4], by[3] = py[i4];
+  *min_side = ms;
+  return true;
+}
+
+__device__ __forceinline__ long long sat_usize_dev(float v) {
+  if (!(v > 0.0f)) return 0;
+  if (v >= 9.2e18f) return 0x7fffffffffffffffLL;
+  return (long long)v;
+}
+
+// box_score_fast for a 4-point box (db_score.rs:34-134, geometry.rs:1087-1164)
+__device__ float box_score_fast_dev(const float* __restrict__ pred, int W, int H, const float bx[4], const float by[4]) {
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = 0; i < 4; ++i) {
+    if (bx[i] < mnx) mnx = bx[i];
+    if (bx[i] > mxx) mxx = bx[i];
+    if (by[i] < mny) mny = by[i];
+    if (by[i] > mxy) mxy = by[i];
+  }
+  float fminx = fminf(fmaxf(floorf(mnx), 0.0f), (float)W - 1.0f);
+  float fmaxx = fminf(fmaxf(ceilf(mxx), 0.0f), (float)W - 1.0f);
+  float fminy = fminf(fmaxf(floorf(mny), 0.0f), (float)H - 1.0f);
+  float fmaxy = fminf(fmaxf(ceilf(mxy), 0.0f), (float)H - 1.0f);
+  long long start_y = sat_usize_dev(fminy), end_y = sat_usize_dev(fmaxy) + 1;
+  long long start_x = sat_usize_dev(fminx), end_x = sat_usize_dev(fmaxx) + 1;
+  float total = 0.0f;
+  long long total_px = 0;
+  for (long long yy = start_y; yy < end_y; ++yy) {
+    float y = (float)yy + 0.5f;
+    float xs[4];
+    int nx = 0;
+    for (int i = 0; i < 4; ++i) {
+      int j = (i + 1) & 3;
+      float p1x = bx[i], p1y = by[i], p2x = bx[j], p2y = by[j];
+      if (((p1y <= y && y < p2y) || (p2y <= y && y < p1y)) && fabsf(p2y - p1y) > 1.1920929e-7f) {
+        xs[nx++] = p1x + (y - p1y) * (p2x - p1x) / (p2y - p1y);
+      }
+    }
+    for (int a = 1; a < nx; ++a) {  // stable insertion sort
+      float kx = xs[a];
+      int b = a - 1;
+      while (b >= 0 && xs[b] > kx) {
+        xs[b + 1] = xs[b];
+        --b;
+      }
+      xs[b + 1] = kx;
+    }
+    float line = 0.0f;
+    long long line_px = 0;
+    long long yi = sat_usize_dev(y);
+    if (yi < H) {
+      const float* row = pred + (size_t)yi * W;
+      for (int k = 0; k + 1 < nx; k += 2) {
+        long long x1 = sat_usize_dev(fmaxf(xs[k], (float)start_x));
+        long long x2 = sat_usize_dev(fminf(xs[k + 1], (float)end_x));
+        if (x1 < x2 && x1 >= start_x && x2 <= end_x) {
+          long long xe = x2 < W ? x2 : W;
+          if (x1 < xe) {
+            for (long long x = x1; x < xe; ++x) line += row[x];  // strictly left to right
+            line_px += xe - x1;
+          }
+        }
+      }
+    }
+    total += line;
+    total_px += line_px;
+  }
+  return total_px > 0 ? total / (float)total_px : 0.0f;
+}
+
+constexpr int UNCLIP_CAP = 768;
+
+// unclip (db_bitmap.rs:279-368): Clipper2 ClipperOffset, JoinType::Round, EndType::Polygon,
+// precision 2.  Writes the offset polygon's vertices as f32.  Returns the vertex count,
+// 0 for "empty", -1 on capacity overflow.
+__device__ int unclip_dev(const float bx[4], const float by[4], float ratio, float* ox, float* oy) {
+  double pxs[4], pys[4];
+  for (int i = 0; i < 4; ++i) pxs[i] = (double)bx[i], pys[i] = (double)by[i];
+  double a = 0.0;
+  {
+    double prx = pxs[3], pry = pys[3];
+    for (int i = 0; i < 4; ++i) {
+      a += (pry + pys[i]) * (prx - pxs[i]);
+      prx = pxs[i], pry = pys[i];
+    }
+    a *= 0.5;
+  }
+  double area = fabs(a);
+  if (area <= 2.220446049250313e-16) return 0;
+  double per = 0.0;
+  {
+    double p1x = pxs[0], p1y = pys[0];
+    for (int i = 1; i < 4; ++i) {
+      per += hypot(pxs[i] - p1x, pys[i] - p1y);
+      p1x = pxs[i], p1y = pys[i];
+    }
+    per += hypot(pxs[0] - p1x, pys[0] - p1y);
+  }
+  if (per <= 2.220446049250313e-16) return 0;
+  double delta = area * (double)ratio / per;
+  if (fabs(delta) <= 2.220446049250313e-16) return 0;
+  const double scale = 100.0;
+  long long ix[4], iy[4];
+  int n = 0;
+  for (int i = 0; i < 4; ++i) {
+    long long qx = llround(pxs[i] * scale), qy = llround(pys[i] * scale);
+    if (n > 0 && ix[n - 1] == qx && iy[n - 1] == qy) continue;
+    ix[n] = qx, iy[n] = qy, ++n;
+  }
+  if (n > 1 && ix[0] == ix[n - 1] && iy[0] == iy[n - 1]) --n;
+  if (n < 3) return 0;
+  double d = delta * scale;
+  double ia = 0.0;
+  {
+    long long prx = ix[n - 1], pry = iy[n - 1];
+    for (int i = 0; i < n; ++i) {
+      ia += (double)(pry + iy[i]) * (double)(prx - ix[i]);
+      prx = ix[i], pry = iy[i];
+    }
+  }
+  double gd = ia < 0.0 ? -d : d;
+  double ad = fabs(gd);
+  const double PI_D = 3.141592653589793238;
+  double arc_tol = log10(2.0 + ad) * 0.25;
+  double steps_per_360 = fmin(PI_D / acos(1.0 - arc_tol / ad), ad * PI_D);
+  double step_sin = sin(2.0 * PI_D / steps_per_360);
+  double step_cos = cos(2.0 * PI_D / steps_per_360);
+  if (gd < 0.0) step_sin = -step_sin;
+  double steps_per_rad = steps_per_360 / (2.0 * PI_D);
+  double nxs[4], nys[4];
+  for (int i = 0; i < n; ++i) {
+    int j = (i + 1) % n;
+    double dx = (double)(ix[j] - ix[i]), dy = (double)(iy[j] - iy[i]);
+    if (dx == 0 && dy == 0) {
+      nxs[i] = 0, nys[i] = 0;
+      continue;
+    }
+    double inv = 1.0 / hypot(dx, dy);
+    dx *= inv, dy *= inv;
+    nxs[i] = dy, nys[i] = -dx;
+  }
+  int m = 0;
+  bool overflow = false;
+  auto push = [&](double x, double y) {
+    if (m >= UNCLIP_CAP) {
+      overflow = true;
+      return;
+    }
+    long long qx = llround(x), qy = llround(y);
+    ox[m] = (float)((double)qx * (1.0 / scale));
+    oy[m] = (float)((double)qy * (1.0 / scale));
+    ++m;
+  };
+  for (int j = 0, k = n - 1; j < n; k = j, ++j) {
+    double sin_a = nys[j] * nxs[k] - nys[k] * nxs[j];
+    double cos_a = nxs[j] * nxs[k] + nys[j] * nys[k];
+    if (sin_a > 1.0) sin_a = 1.0; else if (sin_a < -1.0) sin_a = -1.0;
+    double ptx = (double)ix[j], pty = (double)iy[j];
+    if (cos_a > -0.999 && (sin_a * gd < 0)) {
+      push(ptx + nxs[k] * gd, pty + nys[k] * gd);
+      push(ptx, pty);
+      push(ptx + nxs[j] * gd, pty + nys[j] * gd);
+    } else {
+      double ang = atan2(sin_a, cos_a);
+      double vx = nxs[k] * gd, vy = nys[k] * gd;
+      push(ptx + vx, pty + vy);
+      int steps = (int)ceil(steps_per_rad * fabs(ang));
+      for (int i = 1; i < steps; ++i) {
+        double tx = vx * step_cos - step_sin * vy;
+        double ty = vx * step_sin + vy * step_cos;
+        vx = tx, vy = ty;
+        push(ptx + vx, pty + vy);
+      }
+      push(ptx + nxs[j] * gd, pty + nys[j] * gd);
+    }
+  }
+  if (overflow) return -1;
+  if (m > 1 && fabsf(ox[0] - ox[m - 1]) < 1.1920929e-7f && fabsf(oy[0] - oy[m - 1]) < 1.1920929e-7f) --m;
+  if (m < 3) return 0;
+  return m;
+}
+
+// convex_hull_from_points exactly as geometry.rs:226-274 (Graham scan with atan2 keys, stable
+// sort, pop while cross <= 0), in place on (x,y)[0..n); ang/dist are scratch.  Returns hull size.
+__device__ int graham_hull_inplace(float* x, float* y, int n, float* ang, float* dist) {
+  int s = 0;
+  for (int i = 1; i < n; ++i)
+    if (y[i] < y[s] || (y[i] == y[s] && x[i] < x[s])) s = i;
+  {
+    float tx = x[0], ty = y[0];
+    x[0] = x[s], y[0] = y[s];
+    x[s] = tx, y[s] = ty;
+  }
+  float spx = x[0], spy = y[0];
+  for (int i = 1; i < n; ++i) {
+    float dx = x[i] - spx, dy = y[i] - spy;
+    ang[i] = atan2f(dy, dx);
+    dist[i] = dx * dx + dy * dy;
+  }
+  for (int a = 2; a < n; ++a) {  // stable insertion sort on (ang total_cmp, dist total_cmp)
+    float kx = x[a], ky = y[a], ka = ang[a], kd = dist[a];
+    int b = a - 1;
+    while (b >= 1) {
+      int c = total_cmp_f32(ang[b], ka);
+      if (c == 0) c = total_cmp_f32(dist[b], kd);
+      if (c <= 0) break;
+      x[b + 1] = x[b], y[b + 1] = y[b], ang[b + 1] = ang[b], dist[b + 1] = dist[b];
+      --b;
+    }
+    x[b + 1] = kx, y[b + 1] = ky, ang[b + 1] = ka, dist[b + 1] = kd;
+  }
+  int h = 0;
+  for (int i = 0; i < n; ++i) {
+    float px = x[i], py = y[i];
+    while (h > 1) {
+      float cr = (x[h - 1] - x[h - 2]) * (py - y[h - 2]) - (y[h - 1] - y[h - 2]) * (px - x[h - 2]);
+      if (cr <= 0.0f) --h; else break;
+    }
+    x[h] = px, y[h] = py;
+    ++h;
+  }
+  return h;
+}
+
+struct Cand {
+  int valid;
+  float box[8];
+  float score;
+};
+
+__global__ void __launch_bounds__(32) db_geometry_kernel(
+    const float* __restrict__ pred, int H, int W, const ContourRec* __restrict__ recs, const int* __restrict__ order,
+    const int* __restrict__ first, int B, int max_cand, const short2* __restrict__ pool, short2* __restrict__ scratch,
+    const int32_t* __restrict__ dest_wh, float box_thresh, float unclip_ratio, float min_size,
+    Cand* __restrict__ cands, int* __restrict__ err) {
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.y;
+  int cnt = min(first[b + 1] - first[b], max_cand);
+  if (rank >= cnt) return;
+  Cand& out = cands[(size_t)b * max_cand + rank];
+  out.valid = 0;
+  const ContourRec rec = recs[order[first[b] + rank]];
+  const short2* pts = pool + rec.off;
+  short2* simp = scratch + rec.off;
+  int n = rec.len;
+  if (n < 3) return;  // get_mini_boxes_from_points: < 3 points -> None (simplified or raw)
+
+  // --- simplify_chain_points (db_bitmap.rs:207-239) ---
+  int ns = 0;
+  {
+    short2 prev = pts[n - 1], cur = pts[0];
+    for (int i = 0; i < n; ++i) {
+      short2 nxt = pts[(i + 1 == n) ? 0 : i + 1];
+      int a0 = (cur.x > prev.x) - (cur.x < prev.x), a1 = (cur.y > prev.y) - (cur.y < prev.y);
+      int b0 = (nxt.x > cur.x) - (nxt.x < cur.x), b1 = (nxt.y > cur.y) - (nxt.y < cur.y);
+      if (a0 != b0 || a1 != b1) simp[ns++] = cur;
+      prev = cur;
+      cur = nxt;
+    }
+  }
+  const short2* P = simp;
+  int np = ns;
+  if (ns < 3) {  // simplify returns the raw chain; contour helper then uses the raw points
+    P = pts;
+    np = n;
+  }
+  // --- convex hull of integer points.  All cross products are exact in f32 for |coord| < 4096,
+  // so the reference's Graham scan yields the unique strict hull, starting at the lowest-y
+  // (then lowest-x) point in increasing polar angle; Jarvis march reproduces that sequence. ---
+  int s = 0;
+  for (int i = 1; i < np; ++i)
+    if (P[i].y < P[s].y || (P[i].y == P[s].y && P[i].x < P[s].x)) s = i;
+  float hx[UNCLIP_CAP], hy[UNCLIP_CAP];
+  int nh = 0;
+  {
+    int cx = P[s].x, cy = P[s].y;
+    const int sx = cx, sy = cy;
+    for (;;) {
+      if (nh >= UNCLIP_CAP) {
+        atomicExch(err, 2);
+        return;
+      }
+      hx[nh] = (float)cx, hy[nh] = (float)cy, ++nh;
+      // next = the point q such that every other point is to the left of cur->q (cross >= 0),
+      // farthest among collinear
+      int bx_ = cx, by_ = cy;
+      bool have = false;
+      for (int i = 0; i < np; ++i) {
+        int qx = P[i].x, qy = P[i].y;
+        if (qx == cx && qy == cy) continue;
+        if (!have) {
+          bx_ = qx, by_ = qy, have = true;
+          continue;
+        }
+        long long cr = (long long)(bx_ - cx) * (qy - cy) - (long long)(by_ - cy) * (qx - cx);
+        if (cr < 0) {
+          bx_ = qx, by_ = qy;
+        } else if (cr == 0) {
+          long long d1 = (long long)(bx_ - cx) * (bx_ - cx) + (long long)(by_ - cy) * (by_ - cy);
+          long long d2 = (long long)(qx - cx) * (qx - cx) + (long long)(qy - cy) * (qy - cy);
+          // collinear: same direction -> take the farther; opposite direction cannot both be extreme
+          long long dot = (long long)(bx_ - cx) * (qx - cx) + (long long)(by_ - cy) * (qy - cy);
+          if (dot > 0 && d2 > d1) bx_ = qx, by_ = qy;
+        }
+      }
+      if (!have) break;
+      if (bx_ == sx && by_ == sy) break;
+      // collinear degenerate set: the march would bounce between the two extremes
+      if (nh >= 2 && (float)bx_ == hx[nh - 2] && (float)by_ == hy[nh - 2]) break;
+      cx = bx_, cy = by_;
+    }
+  }
+  MinRect r;
+  if (nh < 3) {
+    float tx[4], ty[4];
+    // degenerate: AABB over the source points
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = 0; i < np; ++i) {
+      float fx = (float)P[i].x, fy = (float)P[i].y;
+      if (fx < mnx) mnx = fx;
+      if (fx > mxx) mxx = fx;
+      if (fy < mny) mny = fy;
+      if (fy > mxy) mxy = fy;
+    }
+    (void)tx;
+    (void)ty;
+    r = MinRect{(mnx + mxx) * 0.5f, (mny + mxy) * 0.5f, mxx - mnx, mxy - mny, 0.0f};
+  } else {
+    r = min_rect_from_hull(hx, hy, nh);
+  }
+  float bx[4], by[4], min_side;
+  if (!rect_to_ordered_box(r, bx, by, &min_side)) return;
+  if (min_side < min_size) return;
+  float score = box_score_fast_dev(pred + (size_t)b * H * W, W, H, bx, by);
+  if (score < box_thresh) return;
+  // --- unclip + second mini box ---
+  float* ux = hx;
+  float* uy = hy;
+  int nu = unclip_dev(bx, by, unclip_ratio, ux, uy);
+  if (nu < 0) {
+    atomicExch(err, 3);
+    return;
+  }
+  if (nu == 0) return;
+  MinRect r2;
+  {
+    float ang[UNCLIP_CAP], dist[UNCLIP_CAP];
+    float sx2[UNCLIP_CAP], sy2[UNCLIP_CAP];
+    for (int i = 0; i < nu; ++i) sx2[i] = ux[i], sy2[i] = uy[i];
+    int h2 = graham_hull_inplace(sx2, sy2, nu, ang, dist);
+    if (h2 < 3)
+      r2 = aabb_rect(ux, uy, nu);
+    else
+      r2 = min_rect_from_hull(sx2, sy2, h2);
+  }
+  float qx[4], qy[4], sside;
+  if (!rect_to_ordered_box(r2, qx, qy, &sside)) return;
+  if (sside < min_size + 2.0f) return;
+  unsigned dw = (unsigned)dest_wh[2 * b], dh = (unsigned)dest_wh[2 * b + 1];
+  float width_scale = (float)dw / (float)W, height_scale = (float)dh / (float)H;
+  for (int i = 0; i < 4; ++i) {
+    out.box[2 * i] = fminf(fmaxf(roundf(qx[i] * width_scale), 0.0f), (float)dw);
+    out.box[2 * i + 1] = fminf(fmaxf(roundf(qy[i] * height_scale), 0.0f), (float)dh);
+  }
+  out.score = score;
+  out.valid = 1;
+}
+
+__global__ void db_compact_kernel(const Cand* __restrict__ cands, const int* __restrict__ first, int B, int max_cand,
+                                  float* __restrict__ boxes, float* __restrict__ scores, int32_t* __restrict__ counts) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int cnt = min(first[b + 1] - first[b], max_cand);
+  int n = 0;
+  for (int i = 0; i < cnt; ++i) {
+    const Cand& c = cands[(size_t)b * max_cand + i];
+    if (!c.valid) continue;
+    for (int k = 0; k < 8; ++k) boxes[((size_t)b * max_cand + n) * 8 + k] = c.box[k];
+    scores[(size_t)b * max_cand + n] = c.score;
+    ++n;
+  }
+  counts[b] = n;
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+DbPostStatus db_postprocess_device(oar_ctx* ctx, const float* pred, int B, int H, int W, const int32_t* h_src_h,
+                                   const int32_t* h_src_w, const oar_det_config& cfg, DbPostOut out,
+                                   int launch_comps_hint) {
+  DbPostStatus status{};
+  if (B == 0) return status;
+  if (H > 32767 || W > 32767) OAR_FAIL(OAR_E_UNSUPPORTED, "prediction map %dx%d too large", H, W);
+  cudaStream_t st = ctx->stream;
+  Arena& A = ctx->arena;
+  size_t total = (size_t)B * H * W;
+  int HW = H * W;
+  uint8_t* state = A.get<uint8_t>(total);
+  int32_t* lab = A.get<int32_t>(total);
+  int32_t* slot_of = A.get<int32_t>(total);
+  int comp_cap = (int)std::min<size_t>(total / 4 + 1024, (size_t)64 << 20);
+  int rec_cap = comp_cap;
+  Comp* comps = A.get<Comp>(comp_cap);
+  ContourRec* recs = A.get<ContourRec>(rec_cap);
+  unsigned long long pool_cap = total + 4096;
+  short2* pool = A.get<short2>(pool_cap);
+  short2* scratch = A.get<short2>(pool_cap);
+  // counters: [0] n_comps, [1] n_recs, [2] err, [4..5] pool_used (u64)
+  int* counters = A.get<int>(8);
+  OAR_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
+  int* n_comps = counters;
+  int* n_recs = counters + 1;
+  int* err = counters + 2;
+  unsigned long long* pool_used = reinterpret_cast<unsigned long long*>(counters + 4);
+  int32_t* dest_wh = A.get<int32_t>(2 * B);
+  {
+    std::vector<int32_t> h(2 * B);
+    for (int b = 0; b < B; ++b) h[2 * b] = h_src_w[b], h[2 * b + 1] = h_src_h[b];
+    int32_t* staged = (int32_t*)ctx->pinned_get(h.size() * sizeof(int32_t));
+    memcpy(staged, h.data(), h.size() * sizeof(int32_t));
+    OAR_CUDA(cudaMemcpyAsync(dest_wh, staged, h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  int nb = cdiv(total, 256);
+  {
+    Launch l(ctx, "db_threshold_init", (double)total, 9.0 * total);
+    db_init_kernel<<<nb, 256, 0, st>>>(pred, cfg.thresh, state, lab, total, HW);
+  }
+  {
+    Launch l(ctx, "db_ccl_merge", 0, 5.0 * total);
+    db_merge_kernel<<<nb, 256, 0, st>>>(state, lab, B, H, W);
+  }
+  {
+    Launch l(ctx, "db_ccl_flatten", 0, 5.0 * total);
+    db_flatten_kernel<<<nb, 256, 0, st>>>(state, lab, slot_of, comps, n_comps, comp_cap, B, H, W);
+  }
+  {
+    Launch l(ctx, "db_ccl_bbox", 0, 1.0 * total);
+    db_bbox_kernel<<<nb, 256, 0, st>>>(state, lab, slot_of, comps, B, H, W);
+  }
+  // The component count lives on the device; launch for a generous bound and let
+  // surplus warps exit.  (Typical pages have tens of components per image.)
+  int launch_comps = std::min(comp_cap, std::max(launch_comps_hint, std::max(4096, B * 2048)));
+  {
+    Launch l(ctx, "db_trace_borders", 0, 0);
+    db_trace_kernel<<<cdiv((long long)launch_comps * 32, 128), 128, 0, st>>>(
+        state, lab, comps, n_comps, launch_comps, H, W, pool, pool_used, pool_cap, recs, n_recs, rec_cap, err);
+  }
+  // sort contour records into discovery order
+  int sort_n = std::min(rec_cap, launch_comps * 2);
+  unsigned long long* keys = A.get<unsigned long long>(sort_n);
+  unsigned long long* keys2 = A.get<unsigned long long>(sort_n);
+  int* vals = A.get<int>(sort_n);
+  int* vals2 = A.get<int>(sort_n);
+  {
+    Launch l(ctx, "db_contour_keys");
+    db_keys_kernel<<<cdiv(sort_n, 256), 256, 0, st>>>(recs, n_recs, sort_n, keys, vals);
+  }
+  {
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, sort_n, 0, 64, st);
+    void* tmp = A.alloc(tmp_bytes);
+    Launch l(ctx, "db_contour_sort");
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, sort_n, 0, 64, st);
+  }
+  int* first = A.get<int>(B + 1);
+  {
+    Launch l(ctx, "db_img_first");
+    db_img_first_kernel<<<cdiv(B + 1, 64), 64, 0, st>>>(keys2, n_recs, sort_n, B, first);
+  }
+  Cand* cands = A.get<Cand>((size_t)B * cfg.max_candidates);
+  {
+    Launch l(ctx, "db_box_geometry");
+    db_geometry_kernel<<<dim3(cdiv(cfg.max_candidates, 32), B), 32, 0, st>>>(
+        pred, H, W, recs, vals2, first, B, cfg.max_candidates, pool, scratch, dest_wh, cfg.box_thresh,
+        cfg.unclip_ratio, cfg.min_size, cands, err);
+  }
+  {
+    Launch l(ctx, "db_compact");
+    db_compact_kernel<<<cdiv(B, 32), 32, 0, st>>>(cands, first, B, cfg.max_candidates, out.boxes, out.scores,
+                                                   out.counts);
+  }
+  // counters come back with the results; the caller checks them after its sync
+  status.h_counters = (int*)ctx->pinned_get(sizeof(int) * 4);
+  status.launch_comps = launch_comps;
+  status.sort_n = sort_n;
+  OAR_CUDA(cudaMemcpyAsync(status.h_counters, counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  return status;
+}
+
+// after the stream is synchronised: 0 ok, 1 = re-run with a larger launch bound, throws on hard errors
+int db_postprocess_check(const DbPostStatus& s, int* need_comps) {
+  if (!s.h_counters) return 0;
+  int n_comps = s.h_counters[0], n_recs = s.h_counters[1], err = s.h_counters[2];
+  if (err) OAR_FAIL(OAR_E_CAPACITY, "DB post-process scratch capacity exceeded (code %d)", err);
+  if (n_comps > s.launch_comps || n_recs > s.sort_n) {
+    *need_comps = std::max(n_comps, (n_recs + 1) / 2) + 1024;
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace oar

@@ -1,0 +1,693 @@
+// engine.cu -- OARG layer-list executor, fp32 SIMT kernels.
+//
+// Replaces the network half of OrtInfer::infer (oar-ocr-core/src/core/
+// inference/ort_infer_execution.rs:121-306): the reference hands an NCHW f32
+// tensor to ONNX Runtime; here the same graph runs as NHWC kernels on one
+// stream.  This file is the full-precision engine (engine 0): every op in fp32,
+// used for parity against the CPU oracle and as the on-device reference for the
+// tensor-core engine (gemm_tc.cu), which overrides the GEMM-shaped ops.
+#include "engine.cuh"
+
+namespace oar {
+
+// ---------------------------------------------------------------------------
+// activations
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU:
+      return fmaxf(v, 0.0f);
+    case ACT_HSWISH:
+      return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f;
+    case ACT_SWISH:
+      return v / (1.0f + expf(-v));
+    case ACT_SIGMOID:
+      return 1.0f / (1.0f + expf(-v));
+    case ACT_HSIGMOID:
+      return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
+    default:
+      return v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dense conv / linear / 2x2-s2 transposed conv as an implicit GEMM (SIMT)
+//   C[M,N] = A[M,K] * W[N,K]^T,  M = B*Ho*Wo, K = kh*kw*Cin (k = (ky,kx,ci))
+// ---------------------------------------------------------------------------
+struct ConvParams {
+  const float* in;
+  const float* w;
+  const float* bias;
+  float* out;
+  int B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw;
+  int N, K, M;
+  int out_ld, out_c_off;
+  int act;
+  float post_scale, post_bias;
+  int mode;  // 0 conv, 1 deconv2x2 scatter (N = 4*Cout)
+  int cout;  // deconv: real output channels
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) conv_gemm_simt(ConvParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // loader mapping: 64 rows x 4 k-segments of 4
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const int am = m0 + lrow;
+  int ab = 0, aho = 0, awo = 0;
+  const bool arow_ok = am < p.M;
+  if (arow_ok) {
+    ab = am / (p.Ho * p.Wo);
+    int r = am - ab * p.Ho * p.Wo;
+    aho = r / p.Wo;
+    awo = r - aho * p.Wo;
+  }
+  const bool pointwise = (p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0);
+  const bool vec_a = pointwise && (p.Cin % 4 == 0);
+  const bool vec_b = (p.K % 4 == 0);
+  const float* arow_ptr = p.in + (size_t)am * p.Cin;  // valid only when pointwise
+  const int bn = n0 + lrow;
+  const float* brow_ptr = p.w + (size_t)bn * p.K;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k = k0 + lk;
+    if (arow_ok) {
+      if (vec_a) {
+        if (k < p.K) {
+          float4 t = *reinterpret_cast<const float4*>(arow_ptr + k);
+          av[0] = t.x, av[1] = t.y, av[2] = t.z, av[3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int kk = k + i;
+          if (kk < p.K) {
+            int ci = kk % p.Cin;
+            int r = kk / p.Cin;
+            int kx = r % p.kw, ky = r / p.kw;
+            int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
+            if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+              av[i] = p.in[(((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci];
+          }
+        }
+      }
+    }
+    if (bn < p.N) {
+      if (vec_b) {
+        if (k < p.K) {
+          float4 t = *reinterpret_cast<const float4*>(brow_ptr + k);
+          bv[0] = t.x, bv[1] = t.y, bv[2] = t.z, bv[3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k + i < p.K) bv[i] = brow_ptr[k + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[lk + i][lrow] = av[i];
+      Bs[lk + i][lrow] = bv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    size_t obase;
+    int ob = 0, oy = 0, ox = 0;
+    if (p.mode == 0) {
+      obase = (size_t)m * p.out_ld + p.out_c_off;
+    } else {
+      ob = m / (p.Ho * p.Wo);
+      int r = m - ob * p.Ho * p.Wo;
+      oy = r / p.Wo;
+      ox = r - oy * p.Wo;
+      obase = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      if (p.mode == 0) {
+        float v = acc[i][j] + p.bias[n];
+        v = apply_act(v, p.act) * p.post_scale + p.post_bias;
+        p.out[obase + n] = v;
+      } else {
+        int q = n / p.cout, co = n - q * p.cout;
+        int dy = q >> 1, dx = q & 1;
+        float v = acc[i][j] + p.bias[co];
+        v = apply_act(v, p.act) * p.post_scale + p.post_bias;
+        p.out[(((size_t)ob * (2 * p.Ho) + 2 * oy + dy) * (2 * p.Wo) + 2 * ox + dx) * p.cout + co] = v;
+      }
+    }
+  }
+}
+
+void launch_conv_simt(oar_ctx* ctx, const ConvParams& p, const char* name) {
+  dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN));
+  Launch l(ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw) + (double)p.M * p.N));
+  conv_gemm_simt<<<grid, 256, 0, ctx->stream>>>(p);
+}
+
+// ---------------------------------------------------------------------------
+// depthwise conv, NHWC, 4 channels per thread
+// ---------------------------------------------------------------------------
+__global__ void dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int kh, int kw,
+                              int sh, int sw, int ph, int pw, int act, float ps, float pb) {
+  const int c4n = C >> 2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Ho * Wo * c4n;
+  if (idx >= total) return;
+  int c4 = (int)(idx % c4n);
+  size_t r = idx / c4n;
+  int wo = (int)(r % Wo);
+  r /= Wo;
+  int ho = (int)(r % Ho);
+  int b = (int)(r / Ho);
+  float4 acc = *reinterpret_cast<const float4*>(bias + c4 * 4);
+  for (int ky = 0; ky < kh; ++ky) {
+    int ih = ho * sh - ph + ky;
+    if (ih < 0 || ih >= H) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      int iw = wo * sw - pw + kx;
+      if (iw < 0 || iw >= W) continue;
+      float4 x = *reinterpret_cast<const float4*>(in + (((size_t)b * H + ih) * W + iw) * C + c4 * 4);
+      float4 k = *reinterpret_cast<const float4*>(w + ((size_t)ky * kw + kx) * C + c4 * 4);
+      acc.x = fmaf(x.x, k.x, acc.x);
+      acc.y = fmaf(x.y, k.y, acc.y);
+      acc.z = fmaf(x.z, k.z, acc.z);
+      acc.w = fmaf(x.w, k.w, acc.w);
+    }
+  }
+  acc.x = apply_act(acc.x, act) * ps + pb;
+  acc.y = apply_act(acc.y, act) * ps + pb;
+  acc.z = apply_act(acc.z, act) * ps + pb;
+  acc.w = apply_act(acc.w, act) * ps + pb;
+  *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4) = acc;
+}
+
+// ---------------------------------------------------------------------------
+// squeeze-excite: deterministic two-stage global average pool, tiny MLP, scale
+// ---------------------------------------------------------------------------
+__global__ void se_gap_kernel(const float* __restrict__ in, float* __restrict__ partial, int HW, int C, int S) {
+  // grid (S, B); each block sums pixels [s*chunk, (s+1)*chunk) for every channel
+  int s = blockIdx.x, b = blockIdx.y;
+  int chunk = (HW + S - 1) / S;
+  int p0 = s * chunk, p1 = min(HW, p0 + chunk);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.0f;
+    const float* base = in + ((size_t)b * HW) * C + c;
+    for (int p = p0; p < p1; ++p) acc += base[(size_t)p * C];
+    partial[((size_t)b * S + s) * C + c] = acc;
+  }
+}
+
+__global__ void se_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w1,
+                             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                             float* __restrict__ scale, int HW, int C, int Cm, int S, float slope, float offset) {
+  extern __shared__ float sm[];
+  float* mean = sm;
+  float* hid = sm + C;
+  int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.0f;
+    for (int s = 0; s < S; ++s) acc += partial[((size_t)b * S + s) * C + c];
+    mean[c] = acc / (float)HW;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cm; j += blockDim.x) {
+    float acc = b1[j];
+    for (int c = 0; c < C; ++c) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
+    hid[j] = fmaxf(acc, 0.0f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = b2[c];
+    for (int j = 0; j < Cm; ++j) acc = fmaf(w2[(size_t)c * Cm + j], hid[j], acc);
+    scale[(size_t)b * C + c] = fminf(fmaxf(acc * slope + offset, 0.0f), 1.0f);
+  }
+}
+
+__global__ void se_apply_kernel(const float* __restrict__ in, const float* __restrict__ scale, float* __restrict__ out,
+                                size_t total4, int HWC4, int C4, int residual) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int b = (int)(i / HWC4);
+  int c4 = (int)(i % C4);
+  float4 x = reinterpret_cast<const float4*>(in)[i];
+  float4 s = reinterpret_cast<const float4*>(scale)[(size_t)b * C4 + c4];
+  float4 o;
+  if (residual) {
+    o.x = x.x + x.x * s.x, o.y = x.y + x.y * s.y, o.z = x.z + x.z * s.z, o.w = x.w + x.w * s.w;
+  } else {
+    o.x = x.x * s.x, o.y = x.y * s.y, o.z = x.z * s.z, o.w = x.w * s.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+// ---------------------------------------------------------------------------
+// elementwise: add, upsample-add, upsample-into-slice, avgpool
+// ---------------------------------------------------------------------------
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+  reinterpret_cast<float4*>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+
+// out[b,y,x,:] = a[b,y,x,:] + up[b,y/s,x/s,:]
+__global__ void upadd_kernel(const float* __restrict__ a, const float* __restrict__ up, float* __restrict__ o, int B,
+                             int H, int W, int C4, int s) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W * C4;
+  if (i >= total) return;
+  int c4 = (int)(i % C4);
+  size_t r = i / C4;
+  int x = (int)(r % W);
+  r /= W;
+  int y = (int)(r % H);
+  int b = (int)(r / H);
+  float4 v = reinterpret_cast<const float4*>(a)[i];
+  float4 u = reinterpret_cast<const float4*>(up)[(((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4];
+  reinterpret_cast<float4*>(o)[i] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
+}
+
+// out[b,y,x,c_off + c] = in[b,y/s,x/s,c]   (H,W = output dims)
+__global__ void upsample_into_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C4,
+                                     int s, int ld4, int coff4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W * C4;
+  if (i >= total) return;
+  int c4 = (int)(i % C4);
+  size_t r = i / C4;
+  int x = (int)(r % W);
+  r /= W;
+  int y = (int)(r % H);
+  int b = (int)(r / H);
+  float4 u = reinterpret_cast<const float4*>(in)[(((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4];
+  reinterpret_cast<float4*>(out)[(((size_t)b * H + y) * W + x) * ld4 + coff4 + c4] = u;
+}
+
+__global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho,
+                               int Wo, int kh, int kw, int sh, int sw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Ho * Wo * C;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  size_t r = i / C;
+  int wo = (int)(r % Wo);
+  r /= Wo;
+  int ho = (int)(r % Ho);
+  int b = (int)(r / Ho);
+  float acc = 0.0f;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) acc += in[(((size_t)b * H + ho * sh + ky) * W + wo * sw + kx) * C + c];
+  out[i] = acc / (float)(kh * kw);
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm over channels: one warp per pixel
+// ---------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ in, const float* __restrict__ g, const float* __restrict__ be,
+                                 float* __restrict__ out, size_t rows, int C, float eps) {
+  size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = in + row * C;
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += x[c];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / (float)C;
+  float v = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    float d = x[c] - mean;
+    v = fmaf(d, d, v);
+  }
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = 1.0f / sqrtf(v / (float)C + eps);
+  for (int c = lane; c < C; c += 32) out[row * C + c] = (x[c] - mean) * rstd * g[c] + be[c];
+}
+
+// ---------------------------------------------------------------------------
+// attention core: qkv [B,T,3,heads,d] -> out [B,T,heads*d]; one block per (head,b)
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void attn_core_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads, float scale) {
+  extern __shared__ float sm[];
+  float* Ks = sm;
+  float* Vs = sm + (size_t)T * D;
+  int h = blockIdx.x, b = blockIdx.y;
+  int C = heads * D;
+  const float* base = qkv + (size_t)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+    int t = i / D, d = i - t * D;
+    Ks[i] = base[(size_t)t * 3 * C + C + h * D + d];
+    Vs[i] = base[(size_t)t * 3 * C + 2 * C + h * D + d];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = base[(size_t)t * 3 * C + h * D + d] * scale;
+    float mx = -INFINITY;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], Ks[j * D + d], s);
+      mx = fmaxf(mx, s);
+    }
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.0f;
+    float den = 0.0f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], Ks[j * D + d], s);
+      float e = expf(s - mx);
+      den += e;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(e, Vs[j * D + d], acc[d]);
+    }
+    float inv = 1.0f / den;
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[((size_t)b * T + t) * C + h * D + d] = acc[d] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CTC head tail: row softmax + argmax (LAST maximal index, simd.rs:194-204).
+// prob = 1 / sum(exp(z - zmax)); optionally writes the full softmax row.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __restrict__ logits, float* __restrict__ probs,
+                                                             int32_t* __restrict__ idx, float* __restrict__ prob, int V) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float s_sum[8];
+  size_t row = blockIdx.x;
+  const float* z = logits + row * V;
+  float mx = -INFINITY;
+  int mi = 0;
+  for (int i = threadIdx.x; i < V; i += 256) {
+    float v = z[i];
+    if (v >= mx) {  // i increases within a thread: later index wins ties
+      mx = v;
+      mi = i;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi > mi)) {
+      mx = ov;
+      mi = oi;
+    }
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_val[warp] = mx;
+    s_idx[warp] = mi;
+  }
+  __syncthreads();
+  mx = s_val[0];
+  mi = s_idx[0];
+  for (int wdx = 1; wdx < 8; ++wdx) {
+    float ov = s_val[wdx];
+    int oi = s_idx[wdx];
+    if (ov > mx || (ov == mx && oi > mi)) {
+      mx = ov;
+      mi = oi;
+    }
+  }
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < V; i += 256) sum += expf(z[i] - mx);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  float tot = 0.0f;
+  for (int wdx = 0; wdx < 8; ++wdx) tot += s_sum[wdx];
+  if (threadIdx.x == 0) {
+    idx[row] = mi;
+    prob[row] = 1.0f / tot;
+  }
+  if (probs) {
+    float* o = probs + row * V;
+    for (int i = threadIdx.x; i < V; i += 256) o[i] = expf(z[i] - mx) / tot;
+  }
+}
+
+// NCHW -> NHWC for the seam-1 API
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * C * H * W;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  size_t r = i / C;
+  int x = (int)(r % W);
+  r /= W;
+  int y = (int)(r % H);
+  int b = (int)(r / H);
+  out[i] = in[(((size_t)b * C + c) * H + y) * W + x];
+}
+
+void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C, int H, int W) {
+  size_t total = (size_t)B * C * H * W;
+  Launch l(ctx, "nchw_to_nhwc", 0, 8.0 * total);
+  nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(in, out, B, C, H, W);
+}
+
+// ---------------------------------------------------------------------------
+// executor
+// ---------------------------------------------------------------------------
+// tensor-core overrides (gemm_tc.cu); return false to fall through to SIMT
+bool tc_try_conv(oar_model* m, int op_index, const OpRec& op, const Tensor& in, Tensor& out, int out_ld, int c_off);
+bool tc_try_ctc_head(oar_model* m, int op_index, const OpRec& op, const Tensor& in, bool want_probs, Tensor& probs,
+                     CtcOut* ctc);
+
+static inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc) {
+  oar_ctx* ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  std::vector<Tensor> t(m->n_tensors);
+  t[0] = input;
+  Tensor last;
+  auto ensure = [&](int id, int B, int H, int W, int C) -> Tensor& {
+    Tensor& x = t[id];
+    if (!x.p) {
+      x.B = B, x.H = H, x.W = W, x.C = C;
+      x.p = ctx->arena.get<float>(x.numel());
+    } else if (x.B != B || x.H != H || x.W != W || x.C != C) {
+      OAR_FAIL(OAR_E_MODEL, "tensor %d shape mismatch: have %dx%dx%dx%d want %dx%dx%dx%d", id, x.B, x.H, x.W, x.C, B,
+               H, W, C);
+    }
+    return x;
+  };
+  for (size_t oi = 0; oi < m->ops.size(); ++oi) {
+    const OpRec& op = m->ops[oi];
+    const Tensor& a = t[op.in0];
+    if (!a.p) OAR_FAIL(OAR_E_MODEL, "op %zu reads undefined tensor %d", oi, op.in0);
+    switch (op.type) {
+      case OP_CONV: {
+        int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3], ph = op.p[4], pw = op.p[5], cin = op.p[6],
+            cout = op.p[7];
+        if (a.C != cin) OAR_FAIL(OAR_E_MODEL, "conv op %zu: Cin %d != tensor C %d", oi, cin, a.C);
+        int Ho = conv_out(a.H, kh, sh, ph), Wo = conv_out(a.W, kw, sw, pw);
+        int ctot = op.p[11] ? op.p[11] : cout, coff = op.p[11] ? op.p[10] : 0;
+        Tensor& o = ensure(op.out, a.B, Ho, Wo, ctot);
+        if (m->engine == 1 && tc_try_conv(m, (int)oi, op, a, o, ctot, coff)) break;
+        ConvParams p{};
+        p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = o.p;
+        p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = cin, p.Ho = Ho, p.Wo = Wo;
+        p.kh = kh, p.kw = kw, p.sh = sh, p.sw = sw, p.ph = ph, p.pw = pw;
+        p.N = cout, p.K = kh * kw * cin, p.M = a.B * Ho * Wo;
+        p.out_ld = ctot, p.out_c_off = coff, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
+        p.mode = 0, p.cout = cout;
+        launch_conv_simt(ctx, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt");
+        break;
+      }
+      case OP_DECONV2: {
+        int cin = op.p[0], cout = op.p[1];
+        Tensor& o = ensure(op.out, a.B, a.H * 2, a.W * 2, cout);
+        ConvParams p{};
+        p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = o.p;
+        p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = cin, p.Ho = a.H, p.Wo = a.W;
+        p.kh = p.kw = p.sh = p.sw = 1, p.ph = p.pw = 0;
+        p.N = 4 * cout, p.K = cin, p.M = a.B * a.H * a.W;
+        p.act = op.p[2], p.post_scale = 1.0f, p.post_bias = 0.0f, p.mode = 1, p.cout = cout;
+        launch_conv_simt(ctx, p, "deconv2x2_simt");
+        break;
+      }
+      case OP_DWCONV: {
+        int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3], ph = op.p[4], pw = op.p[5], c = op.p[6];
+        if (a.C != c || (c & 3)) OAR_FAIL(OAR_E_MODEL, "dwconv op %zu: bad channels %d/%d", oi, c, a.C);
+        int Ho = conv_out(a.H, kh, sh, ph), Wo = conv_out(a.W, kw, sw, pw);
+        Tensor& o = ensure(op.out, a.B, Ho, Wo, c);
+        size_t total = o.numel() / 4;
+        Launch l(ctx, "dwconv", 2.0 * o.numel() * kh * kw, 4.0 * (a.numel() + o.numel()));
+        dwconv_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo,
+                                                         kh, kw, sh, sw, ph, pw, op.p[7], op.f[0], op.f[1]);
+        break;
+      }
+      case OP_SE: {
+        int c = op.p[0], cm = op.p[1], residual = op.p[2];
+        if (a.C != c || (c & 3)) OAR_FAIL(OAR_E_MODEL, "se op %zu: bad channels", oi);
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
+        int HW = a.H * a.W;
+        int S = HW >= 4096 ? 64 : (HW >= 256 ? 16 : 1);
+        float* partial = ctx->arena.get<float>((size_t)a.B * S * c);
+        float* scale = ctx->arena.get<float>((size_t)a.B * c);
+        {
+          Launch l(ctx, "se_gap", (double)a.numel(), 4.0 * a.numel());
+          se_gap_kernel<<<dim3(S, a.B), 256, 0, st>>>(a.p, partial, HW, c, S);
+        }
+        {
+          Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
+          se_fc_kernel<<<a.B, 128, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2),
+                                                                    m->w(op, 3), scale, HW, c, cm, S, op.f[0], op.f[1]);
+        }
+        {
+          size_t n4 = a.numel() / 4;
+          Launch l(ctx, "se_apply", 2.0 * a.numel(), 8.0 * a.numel());
+          se_apply_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, scale, o.p, n4, HW * c / 4, c / 4, residual);
+        }
+        break;
+      }
+      case OP_ADD: {
+        const Tensor& b = t[op.in1];
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
+        size_t n4 = a.numel() / 4;
+        Launch l(ctx, "add", (double)a.numel(), 12.0 * a.numel());
+        add_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, b.p, o.p, n4);
+        break;
+      }
+      case OP_UPADD: {
+        const Tensor& b = t[op.in1];
+        int s = op.p[0];
+        if (b.H * s != a.H || b.W * s != a.W || b.C != a.C) OAR_FAIL(OAR_E_MODEL, "upadd op %zu: shape mismatch", oi);
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
+        size_t n4 = a.numel() / 4;
+        Launch l(ctx, "upadd", (double)a.numel(), 8.0 * a.numel() + 4.0 * b.numel());
+        upadd_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, b.p, o.p, a.B, a.H, a.W, a.C / 4, s);
+        break;
+      }
+      case OP_UPSAMPLE: {
+        int s = op.p[0];
+        int ctot = op.p[11] ? op.p[11] : a.C, coff = op.p[11] ? op.p[10] : 0;
+        if ((a.C & 3) || (ctot & 3) || (coff & 3)) OAR_FAIL(OAR_E_MODEL, "upsample op %zu: channels not /4", oi);
+        Tensor& o = ensure(op.out, a.B, a.H * s, a.W * s, ctot);
+        size_t n4 = (size_t)a.B * o.H * o.W * (a.C / 4);
+        Launch l(ctx, "upsample_into", 0, 4.0 * a.numel() + 16.0 * n4);
+        upsample_into_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, o.p, a.B, o.H, o.W, a.C / 4, s, ctot / 4, coff / 4);
+        break;
+      }
+      case OP_AVGPOOL: {
+        int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3];
+        int Ho = (a.H - kh) / sh + 1, Wo = (a.W - kw) / sw + 1;
+        Tensor& o = ensure(op.out, a.B, Ho, Wo, a.C);
+        Launch l(ctx, "avgpool", (double)a.numel(), 4.0 * (a.numel() + o.numel()));
+        avgpool_kernel<<<cdiv(o.numel(), 256), 256, 0, st>>>(a.p, o.p, a.B, a.H, a.W, a.C, Ho, Wo, kh, kw, sh, sw);
+        break;
+      }
+      case OP_LAYERNORM: {
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
+        size_t rows = (size_t)a.B * a.H * a.W;
+        Launch l(ctx, "layernorm", 8.0 * a.numel(), 8.0 * a.numel());
+        layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, rows, a.C, op.f[0]);
+        break;
+      }
+      case OP_ATTN: {
+        int c = op.p[0], heads = op.p[1];
+        int T = a.H * a.W;
+        if (c / heads != 15 || c % heads) OAR_FAIL(OAR_E_UNSUPPORTED, "attention head_dim %d unsupported", c / heads);
+        if ((size_t)T * 15 * 2 * sizeof(float) > 48 * 1024)
+          OAR_FAIL(OAR_E_UNSUPPORTED, "attention sequence length %d too long", T);
+        float* qkv = ctx->arena.get<float>((size_t)a.B * T * 3 * c);
+        float* att = ctx->arena.get<float>((size_t)a.B * T * c);
+        ConvParams p{};
+        p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = qkv;
+        p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
+        p.kh = p.kw = p.sh = p.sw = 1;
+        p.N = 3 * c, p.K = c, p.M = a.B * T, p.out_ld = 3 * c, p.post_scale = 1.0f, p.cout = 3 * c;
+        launch_conv_simt(ctx, p, "attn_qkv_simt");
+        {
+          Launch l(ctx, "attn_core", 4.0 * a.B * heads * (double)T * T * 15, 4.0 * a.B * T * 4 * c);
+          attn_core_kernel<15><<<dim3(heads, a.B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
+                                                                                                   op.f[0]);
+        }
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
+        p.in = att, p.w = m->w(op, 2), p.bias = m->w(op, 3), p.out = o.p;
+        p.N = c, p.out_ld = c, p.cout = c;
+        launch_conv_simt(ctx, p, "attn_proj_simt");
+        break;
+      }
+      case OP_CTC_HEAD: {
+        int c = op.p[0], V = op.p[1];
+        int T = a.H * a.W;
+        size_t rows = (size_t)a.B * T;
+        Tensor probs;
+        if (m->engine == 1 && tc_try_ctc_head(m, (int)oi, op, a, want_probs, probs, ctc)) {
+          last = probs;
+          t[op.out] = probs;
+          break;
+        }
+        float* logits = ctx->arena.get<float>(rows * V);
+        ConvParams p{};
+        p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = logits;
+        p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
+        p.kh = p.kw = p.sh = p.sw = 1;
+        p.N = V, p.K = c, p.M = (int)rows, p.out_ld = V, p.post_scale = 1.0f, p.cout = V;
+        launch_conv_simt(ctx, p, "ctc_head_gemm_simt");
+        CtcOut local;
+        CtcOut* co = ctc ? ctc : &local;
+        co->idx = ctx->arena.get<int32_t>(rows);
+        co->prob = ctx->arena.get<float>(rows);
+        co->B = a.B, co->T = T, co->V = V;
+        if (want_probs) {
+          probs.B = a.B, probs.H = 1, probs.W = T, probs.C = V;
+          probs.p = ctx->arena.get<float>(rows * V);
+        }
+        {
+          Launch l(ctx, "ctc_softmax_argmax", 3.0 * rows * V, (want_probs ? 12.0 : 8.0) * rows * V);
+          softmax_argmax_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, probs.p, co->idx, co->prob, V);
+        }
+        t[op.out] = probs;
+        last = probs;
+        break;
+      }
+      default:
+        OAR_FAIL(OAR_E_MODEL, "unknown op type %d", op.type);
+    }
+    if (op.type != OP_CTC_HEAD) last = t[op.out];
+  }
+  OAR_CUDA(cudaGetLastError());
+  return last;
+}
+
+}  // namespace oar

@@ -1,0 +1,77 @@
+// engine.cuh -- OARG layer-list executor (declarations)
+#pragma once
+#include "common.cuh"
+
+namespace oar {
+
+enum OpType {
+  OP_CONV = 1,
+  OP_DWCONV,
+  OP_SE,
+  OP_ADD,
+  OP_UPADD,
+  OP_UPSAMPLE,
+  OP_DECONV2,
+  OP_AVGPOOL,
+  OP_LAYERNORM,
+  OP_ATTN,
+  OP_CTC_HEAD
+};
+enum Act { ACT_NONE = 0, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID };
+
+struct OpRec {
+  int32_t type, in0, in1, out;
+  int32_t p[12];
+  float f[4];
+  int64_t w_off[4];
+  int64_t w_len[4];
+};
+static_assert(sizeof(OpRec) == 144, "OpRec layout");
+
+// NHWC activation.  ld = channel stride of the underlying buffer (>= C when the
+// tensor is a channel slice target of a concat).
+struct Tensor {
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t numel() const { return (size_t)B * H * W * C; }
+};
+
+// Output of the fused CTC head: per (b,t) argmax class and its softmax prob.
+struct CtcOut {
+  int32_t* idx = nullptr;
+  float* prob = nullptr;
+  int B = 0, T = 0, V = 0;
+};
+
+}  // namespace oar
+
+struct oar_model {
+  oar_ctx* ctx = nullptr;
+  int kind = 0;
+  int engine = 0;
+  int n_tensors = 0;
+  std::vector<oar::OpRec> ops;
+  float* d_weights = nullptr;  // all weights, fp32, resident in HBM
+  size_t n_weights = 0;
+  // tensor-core engine state (gemm_tc.cu): fp16 copies of GEMM weights etc.
+  void* tc_state = nullptr;
+
+  const float* w(const oar::OpRec& op, int i) const { return d_weights + op.w_off[i]; }
+};
+
+namespace oar {
+
+// Runs the graph on `in` (NHWC f32, C=3).  For det returns the [B,H,W,1]
+// probability map.  For rec: when `want_probs` the full [B,1,T,V] softmax is
+// materialised in the returned tensor, otherwise only `ctc` is filled (the
+// logits never leave the head kernel's launch) and the returned tensor is empty.
+Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ctc);
+
+// tensor-core engine lifetime hooks (gemm_tc.cu): build fp16 weight copies / release them
+void tc_model_init(oar_model* m);
+void tc_model_free(oar_model* m);
+
+// input layout conversion for the seam-1 API (NCHW f32 host layout -> NHWC)
+void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C, int H, int W);
+
+}  // namespace oar

@@ -1,0 +1,400 @@
+"""Host-side mirror of the reference's public API for the det+rec path.
+
+Same names, argument meaning and error behaviour as the Rust crate so parity
+tests read like the reference's own:
+
+  OAROCRBuilder / OAROCR.predict          src/oarocr/ocr.rs:66-417, 518-659
+  TextDetectionPredictor(+Builder)        oar-ocr-core/src/predictors/text_detection.rs:23-112
+  TextRecognitionPredictor(+Builder)      oar-ocr-core/src/predictors/text_recognition.rs:19-110
+  OAROCRResult / TextRegion               src/oarocr/result.rs:33-49, oar-ocr-core/src/domain/text_region.rs:10-27
+  Detection / BoundingBox                 oar-ocr-core/src/domain/tasks/text_detection.rs:15-21, processors/geometry.rs:15-70
+
+Everything numeric happens behind the C ABI (liboar_b200.so); this module only
+converts between Python objects and flat buffers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ffi
+from .ffi import OCRError
+
+MAX_BATCH_SIZE = 4096  # OAROCRBuilder::MAX_BATCH_SIZE, ocr.rs:93
+
+
+@dataclass
+class BoundingBox:
+    points: np.ndarray  # [N,2] f32
+
+    def x_min(self):
+        return float(self.points[:, 0].min())
+
+    def x_max(self):
+        return float(self.points[:, 0].max())
+
+    def y_min(self):
+        return float(self.points[:, 1].min())
+
+    def y_max(self):
+        return float(self.points[:, 1].max())
+
+
+@dataclass
+class Detection:
+    bbox: BoundingBox
+    score: float
+
+
+@dataclass
+class TextDetectionResult:
+    detections: list  # list[list[Detection]]
+
+
+@dataclass
+class TextRecognitionResult:
+    texts: list
+    scores: list
+    char_col_indices: list = field(default_factory=list)
+    sequence_lengths: list = field(default_factory=list)
+    label_indices: list = field(default_factory=list)  # CTC-collapsed class indices (not in the reference struct)
+
+
+@dataclass
+class TextRegion:
+    bounding_box: BoundingBox
+    dt_poly: BoundingBox
+    rec_poly: BoundingBox
+    text: str
+    confidence: float
+    orientation_angle: float | None = None
+    word_boxes: list | None = None
+    label: str | None = None
+    detection_index: int = 0
+    label_indices: np.ndarray | None = None
+
+
+@dataclass
+class OAROCRResult:
+    input_path: str
+    index: int
+    input_img: np.ndarray
+    text_regions: list
+    orientation_angle: float | None = None
+    rectified_img: np.ndarray | None = None
+
+
+@dataclass
+class TextDetectionConfig:
+    """tasks/text_detection.rs:33-53"""
+    score_threshold: float = 0.3
+    box_threshold: float = 0.6
+    unclip_ratio: float = 1.5
+    max_candidates: int = 1000
+    limit_side_len: int | None = None
+    limit_type: str | None = None  # "max" | "min" | "resize_long"
+    max_side_len: int | None = None
+
+    def to_ffi(self) -> ffi.DetConfig:
+        lt = {"max": 0, "min": 1, "resize_long": 2}
+        # adapter preprocessing defaults: 960 / Max / 4000 (adapters/preprocessing.rs:73-90)
+        return ffi.det_config(thresh=self.score_threshold, box_thresh=self.box_threshold,
+                              unclip_ratio=self.unclip_ratio, max_candidates=self.max_candidates,
+                              limit_side_len=self.limit_side_len or 960,
+                              limit_type=lt[(self.limit_type or "max").lower()],
+                              max_side_limit=self.max_side_len or 4000)
+
+    def validate(self):
+        for name in ("score_threshold", "box_threshold"):
+            v = getattr(self, name)
+            if not (0.0 <= v <= 1.0):
+                raise OCRError("ConfigError", f"{name} must be in [0,1], got {v}")
+        if self.unclip_ratio <= 0 or self.max_candidates <= 0:
+            raise OCRError("ConfigError", "unclip_ratio and max_candidates must be positive")
+
+
+@dataclass
+class TextRecognitionConfig:
+    score_threshold: float = 0.0
+
+
+def character_list(dict_lines: list[str]) -> list[str]:
+    """CTCLabelDecode::from_string_list(dict, use_space_char=true, has_explicit_blank=false)
+    (decode.rs:392-423, 118-141): ['blank'] + dict + [' ']"""
+    return ["\0"] + list(dict_lines) + [" "]
+
+
+def _resolve_model(source, kind: str) -> bytes:
+    """ModelSource: OARG bytes, a path to an .oarg file, or 'synthetic[:seed]'."""
+    if isinstance(source, (bytes, bytearray)):
+        return bytes(source)
+    if isinstance(source, str) and source.startswith("synthetic"):
+        from . import models
+        seed = int(source.split(":")[1]) if ":" in source else 42
+        return models.get_blob(kind, seed)
+    if isinstance(source, (str, os.PathLike)):
+        path = os.fspath(source)
+        if not os.path.exists(path):
+            raise OCRError("ModelLoad", f"model file '{path}' does not exist")
+        if path.endswith(".onnx"):
+            raise OCRError("ModelLoad", "ONNX import is not available in this build (no onnx parser offline); "
+                           "convert the graph to an OARG blob (oar_ocr_b200/models.py)")
+        with open(path, "rb") as f:
+            return f.read()
+    raise OCRError("InvalidInput", f"unsupported model source {type(source)}")
+
+
+def _decode_texts(chars, label_lists):
+    return ["".join(chars[k] for k in lab if 0 <= k < len(chars)) for lab in label_lists]
+
+
+_contexts: dict = {}
+
+
+def default_context(device_id: int = 0) -> ffi.Context:
+    if device_id not in _contexts:
+        _contexts[device_id] = ffi.Context(device_id)
+    return _contexts[device_id]
+
+
+def _validate_images(images, what):
+    if images is None or len(images) == 0:
+        # OCRError::validation_error(..., "non-empty slice", "empty slice"), ocr.rs:525-532 / validation.rs
+        raise OCRError("InvalidInput", f"{what}: images: expected non-empty slice, got empty slice", ffi.OAR_E_INVALID)
+
+
+class TextDetectionPredictorBuilder:
+    def __init__(self):
+        self._config = TextDetectionConfig()
+        self._device = 0
+
+    def score_threshold(self, v):
+        self._config.score_threshold = v
+        return self
+
+    def box_threshold(self, v):
+        self._config.box_threshold = v
+        return self
+
+    def unclip_ratio(self, v):
+        self._config.unclip_ratio = v
+        return self
+
+    def max_candidates(self, v):
+        self._config.max_candidates = v
+        return self
+
+    def with_config(self, cfg: TextDetectionConfig):
+        self._config = cfg
+        return self
+
+    def device_id(self, d):
+        self._device = d
+        return self
+
+    def build(self, model_source) -> "TextDetectionPredictor":
+        self._config.validate()
+        ctx = default_context(self._device)
+        return TextDetectionPredictor(ffi.Model(ctx, _resolve_model(model_source, "det")), self._config)
+
+
+class TextDetectionPredictor:
+    """predict(): validate_input -> TextDetectionAdapter::execute -> validate_output (predictors/core.rs:58-69).
+    Boxes come back in discovery order, unsorted, as the adapter returns them."""
+
+    def __init__(self, model: ffi.Model, config: TextDetectionConfig):
+        self.model = model
+        self.config = config
+
+    @staticmethod
+    def builder():
+        return TextDetectionPredictorBuilder()
+
+    def predict(self, images) -> TextDetectionResult:
+        _validate_images(images, "TextDetection")
+        out = self.model.det_run(images, self.config.to_ffi())
+        dets = []
+        for boxes, scores in out:
+            for s in scores:  # validate_output: scores in [0,1] (tasks/text_detection.rs:129-141)
+                if not (0.0 <= float(s) <= 1.0):
+                    raise OCRError("InvalidInput", f"detection score {s} outside [0,1]")
+            dets.append([Detection(BoundingBox(b.copy()), float(s)) for b, s in zip(boxes, scores)])
+        return TextDetectionResult(dets)
+
+
+class TextRecognitionPredictorBuilder:
+    def __init__(self):
+        self._config = TextRecognitionConfig()
+        self._dict = None
+        self._device = 0
+
+    def score_threshold(self, v):
+        self._config.score_threshold = v
+        return self
+
+    def dict_path(self, path):
+        self._dict = path
+        return self
+
+    def character_dict(self, lines):
+        self._dict = list(lines)
+        return self
+
+    def device_id(self, d):
+        self._device = d
+        return self
+
+    def build(self, model_source) -> "TextRecognitionPredictor":
+        if self._dict is None:
+            raise OCRError("ConfigError", "missing field dict_path for TextRecognitionPredictor")
+        if isinstance(self._dict, list):
+            lines = self._dict
+        else:
+            try:
+                with open(self._dict, "r", encoding="utf-8") as f:
+                    lines = f.read().splitlines()
+            except OSError as e:
+                raise OCRError("InvalidInput", f"Failed to read character dictionary from '{self._dict}': {e}")
+        ctx = default_context(self._device)
+        return TextRecognitionPredictor(ffi.Model(ctx, _resolve_model(model_source, "rec")), character_list(lines),
+                                        self._config)
+
+
+class TextRecognitionPredictor:
+    """predict(): the whole input is ONE batch (predictors/text_recognition.rs:38-45 -> crnn.rs:247-293)"""
+
+    def __init__(self, model: ffi.Model, chars: list[str], config: TextRecognitionConfig):
+        self.model = model
+        self.chars = chars
+        self.config = config
+
+    @staticmethod
+    def builder():
+        return TextRecognitionPredictorBuilder()
+
+    def predict(self, images) -> TextRecognitionResult:
+        _validate_images(images, "TextRecognition")
+        r = self.model.rec_run(images, len(self.chars))
+        texts = _decode_texts(self.chars, r["labels"])
+        scores = [float(s) for s in r["scores"]]
+        labels = list(r["labels"])
+        for i, s in enumerate(scores):  # text_recognition_adapter.rs:88-102: below threshold -> empty text, slot kept
+            if s < self.config.score_threshold:
+                texts[i] = ""
+                labels[i] = labels[i][:0]
+        return TextRecognitionResult(texts, scores, [c.tolist() for c in r["cols"]], [r["T"]] * len(texts), labels)
+
+
+class OAROCRBuilder:
+    """OAROCRBuilder::new(det_model, rec_model, dict_path) (ocr.rs:105-128)"""
+
+    def __init__(self, text_detection_model, text_recognition_model, character_dict_path=None):
+        self._det = text_detection_model
+        self._rec = text_recognition_model
+        self._dict_path = character_dict_path
+        self._dict_content = None
+        self._det_cfg = None
+        self._rec_cfg = None
+        self._image_bs = None
+        self._region_bs = None
+        self._device = 0
+
+    def character_dict_content(self, content: str):
+        self._dict_content = content
+        return self
+
+    def text_detection_config(self, cfg: TextDetectionConfig):
+        self._det_cfg = cfg
+        return self
+
+    def text_recognition_config(self, cfg: TextRecognitionConfig):
+        self._rec_cfg = cfg
+        return self
+
+    def image_batch_size(self, size: int):
+        self._image_bs = size
+        return self
+
+    def region_batch_size(self, size: int):
+        self._region_bs = size
+        return self
+
+    def device_id(self, d: int):
+        self._device = d
+        return self
+
+    @staticmethod
+    def validate_batch_size(name: str, size: int):
+        if size == 0 or size > MAX_BATCH_SIZE or size < 0:
+            raise OCRError("ConfigError", f"{name} must be in 1..={MAX_BATCH_SIZE}, got {size}")
+
+    def build(self) -> "OAROCR":
+        if self._image_bs is not None:
+            self.validate_batch_size("image_batch_size", self._image_bs)
+        if self._region_bs is not None:
+            self.validate_batch_size("region_batch_size", self._region_bs)
+        if self._dict_content is not None:
+            content = self._dict_content
+        else:
+            if self._dict_path is None:
+                raise OCRError("InvalidInput", "Failed to read character dictionary from '': no path given")
+            try:
+                with open(self._dict_path, "r", encoding="utf-8") as f:
+                    content = f.read()
+            except OSError as e:
+                raise OCRError("InvalidInput", f"Failed to read character dictionary from '{self._dict_path}': {e}")
+        chars = character_list(content.splitlines())
+        # no explicit config -> thresh .3 / box .6 / unclip 2.0 / limit 960 Max 4000 (ocr.rs:351-364)
+        det_cfg = self._det_cfg or TextDetectionConfig(unclip_ratio=2.0, limit_side_len=960, limit_type="max",
+                                                       max_side_len=4000)
+        det_cfg.validate()
+        rec_cfg = self._rec_cfg or TextRecognitionConfig()
+        ctx = default_context(self._device)
+        det = ffi.Model(ctx, _resolve_model(self._det, "det"))
+        rec = ffi.Model(ctx, _resolve_model(self._rec, "rec"))
+        # the B200 provider is an accelerator: adapter defaults 8 / 64 (builder_utils.rs:86-125)
+        return OAROCR(ctx, det, rec, chars, det_cfg, rec_cfg, self._image_bs or 8, self._region_bs or 64)
+
+
+class OAROCR:
+    def __init__(self, ctx, det, rec, chars, det_cfg, rec_cfg, image_bs, region_bs):
+        self.ctx, self.det, self.rec, self.chars = ctx, det, rec, chars
+        self.det_cfg, self.rec_cfg = det_cfg, rec_cfg
+        self.image_batch_size, self.region_batch_size = image_bs, region_bs
+        self.last_timing = {}
+        self._bufs = None
+
+    def _config(self) -> ffi.PipelineConfig:
+        cfg = ffi.pipeline_config(image_batch_size=self.image_batch_size, region_batch_size=self.region_batch_size,
+                                  rec_score_thresh=self.rec_cfg.score_threshold, n_chars=len(self.chars))
+        cfg.det = self.det_cfg.to_ffi()
+        return cfg
+
+    def predict_raw(self, image_ptrs, hs, ws, on_device=False):
+        """flat-buffer form used by the bench: returns the ffi.PipelineBuffers of this call"""
+        n = len(hs)
+        if self._bufs is None or len(self._bufs.region_off) != n + 1:
+            self._bufs = ffi.PipelineBuffers(n, cap_regions=n * self.det_cfg.max_candidates)
+        res = ffi.pipeline_run(self.det, self.rec, image_ptrs, hs, ws, on_device, self._config(), self._bufs)
+        self.last_timing = dict(ms_h2d=res.ms_h2d, ms_det=res.ms_det, ms_post=res.ms_post, ms_crop=res.ms_crop,
+                                ms_rec=res.ms_rec, ms_total=res.ms_total, h2d_bytes=res.h2d_bytes,
+                                d2h_bytes=res.d2h_bytes)
+        return self._bufs
+
+    def predict(self, images) -> list[OAROCRResult]:
+        _validate_images(images, "OCR Pipeline")
+        arrs, ptrs, hs, ws = ffi._image_table(images)
+        b = self.predict_raw(ptrs, hs, ws, False)
+        results = []
+        for i, img in enumerate(arrs):
+            regions = []
+            for r in range(b.region_off[i], b.region_off[i + 1]):
+                lab = b.labels[b.label_off[r]:b.label_off[r + 1]].copy()
+                bbox = BoundingBox(b.boxes[r].copy())
+                regions.append(TextRegion(bbox, bbox, bbox, _decode_texts(self.chars, [lab])[0], float(b.scores[r]),
+                                          detection_index=int(b.det_index[r]), label_indices=lab))
+            results.append(OAROCRResult(f"image_{i}", i, img, regions))
+        return results

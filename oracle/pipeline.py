@@ -1,0 +1,107 @@
+"""CPU restatement of the pipeline composition -- TEST INFRASTRUCTURE ONLY.
+
+Follows OAROCR::predict (src/oarocr/ocr.rs:518-659), TextDetectionAdapter::execute ->
+DBModel::forward (oar-ocr-core/src/models/detection/db.rs:281-335), crop_text_regions
+(ocr.rs:718-753), recognize_global (ocr.rs:802-897) and CRNNModel::forward_refs
+(oar-ocr-core/src/models/recognition/crnn.rs:247-293) on top of oracle/cpu.py (pre/post
+arithmetic) and oracle/net.py (the networks, fp32 torch-CPU standing in for ONNX Runtime).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import cpu
+from .net import OracleNet
+
+MAX_POOLED_CROPS = 4096  # ocr.rs:603
+
+
+def det_forward(net: OracleNet, images, thresh=0.3, box_thresh=0.6, unclip_ratio=2.0, max_candidates=1000,
+                limit=960, limit_type=0, max_side=4000, return_pred=False):
+    """DBModel::forward: resize -> same-shape groups -> normalize -> net -> DBPostProcess.
+    Returns per image (boxes [n,4,2], scores [n]) in discovery order."""
+    n = len(images)
+    resized = []
+    for img in images:
+        h, w, _ = img.shape
+        src = img
+        if h + w < 64:  # image_padding, resize_detection.rs:204-220
+            pad = np.zeros((max(h, 32), max(w, 32), 3), np.uint8)
+            pad[:h, :w] = img
+            src = pad
+        rh, rw = cpu.det_resize_dims(src.shape[0], src.shape[1], limit, limit_type, max_side)
+        if (rh, rw) != src.shape[:2]:
+            src = cpu.resize_triangle(src, rw, rh)
+        resized.append(src)
+    groups = []
+    for i, r in enumerate(resized):
+        for g in groups:
+            if resized[g[0]].shape == r.shape:
+                g.append(i)
+                break
+        else:
+            groups.append([i])
+    out = [None] * n
+    preds = [None] * n
+    for g in groups:
+        x = np.stack([cpu.det_normalize(resized[i]) for i in g])
+        pred = net.forward(x)  # [B,1,H,W]
+        for k, i in enumerate(g):
+            sh, sw = images[i].shape[:2]
+            out[i] = cpu.db_postprocess(pred[k, 0], sw, sh, thresh, box_thresh, unclip_ratio, max_candidates)
+            preds[i] = pred[k, 0]
+    return (out, preds) if return_pred else out
+
+
+def rec_forward(net: OracleNet, crops, n_chars, return_probs=False):
+    """CRNNModel::forward_refs on one batch: preprocess -> net -> argmax -> CTC decode."""
+    x = cpu.crnn_preprocess(crops)
+    probs = net.forward(x)  # [B,T,V]
+    idx, prob = cpu.ctc_argmax(probs)
+    labels, scores, cols, T = cpu.ctc_decode(idx, prob, n_chars)
+    r = dict(labels=labels, scores=scores, cols=cols, T=T, idx=idx, prob=prob)
+    if return_probs:
+        r["probs"] = probs
+    return r
+
+
+def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch_size=8, region_batch_size=64,
+            rec_score_thresh=0.0, det_kwargs=None):
+    """OAROCR::predict.  Returns per image a list of dicts
+    {box [4,2], det_index, labels (int array), score} in detection-index (reading) order."""
+    det_kwargs = det_kwargs or {}
+    n = len(images)
+    all_boxes = [None] * n
+    for s in range(0, n, image_batch_size):
+        chunk = images[s:s + image_batch_size]
+        for k, (boxes, _scores) in enumerate(det_forward(det_net, chunk, **det_kwargs)):
+            all_boxes[s + k] = cpu.sort_quad_boxes(boxes)[0] if len(boxes) else boxes
+    results = [[None] * len(b) for b in all_boxes]
+    pool = []
+
+    def recognize_global(pool):
+        order = sorted(range(len(pool)), key=lambda i: pool[i][3])  # stable sort by wh_ratio
+        for s in range(0, len(order), region_batch_size):
+            chunk = [pool[i] for i in order[s:s + region_batch_size]]
+            r = rec_forward(rec_net, [c[2] for c in chunk], n_chars)
+            for k, (img_idx, det_idx, _crop, _ratio) in enumerate(chunk):
+                score = float(r["scores"][k])
+                labels = r["labels"][k] if score >= rec_score_thresh else r["labels"][k][:0]
+                results[img_idx][det_idx] = dict(box=all_boxes[img_idx][det_idx], det_index=det_idx, labels=labels,
+                                                 score=score, cols=r["cols"][k], T=r["T"])
+
+    for i, img in enumerate(images):
+        for k, box in enumerate(all_boxes[i]):
+            crop = cpu.rotate_crop(img, box)
+            if crop is None:
+                continue
+            ratio = np.float32(crop.shape[1]) / np.float32(max(crop.shape[0], 1))
+            pool.append((i, k, crop, float(ratio)))
+            if len(pool) >= MAX_POOLED_CROPS:
+                recognize_global(pool)
+                pool = []
+    if pool:
+        recognize_global(pool)
+    return [[r for r in res if r is not None] for res in results]

@@ -1,0 +1,125 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every declared symbol; host logic that needs no
+device (config defaults, sort_quad_boxes, argument validation, builder validation) behaves like the reference."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from oar_ocr_b200 import ffi
+    header = open(os.path.join(ROOT, "include", "oar_b200.h")).read()
+    declared = set(re.findall(r"\b(oar_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(ffi.SYMBOLS)
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_device_fails_loudly(built_lib):
+    """there is no CPU fallback: without an sm_100 device every compute path is unreachable"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from oar_ocr_b200 import ffi
+    with pytest.raises(ffi.OCRError) as e:
+        ffi.Context(0)
+    assert e.value.code == ffi.OAR_E_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_config_defaults(built_lib):
+    from oar_ocr_b200 import ffi
+    d = ffi.det_config()
+    # OAROCRBuilder defaults, src/oarocr/ocr.rs:351-364
+    assert (round(d.thresh, 6), round(d.box_thresh, 6), d.unclip_ratio, d.max_candidates) == (0.3, 0.6, 2.0, 1000)
+    assert (d.limit_side_len, d.limit_type, d.max_side_limit, d.min_size) == (960, 0, 4000, 3.0)
+    p = ffi.pipeline_config()
+    assert (p.image_batch_size, p.region_batch_size, p.n_chars) == (8, 64, 18385)  # accelerator defaults
+
+
+def test_sort_quad_boxes_reference_cases(built_lib):
+    """sorting.rs:740-808 through the C ABI (host-only entry point)"""
+    from oar_ocr_b200 import ffi
+
+    def fc(x1, y1, x2, y2):
+        return [[x1, y1], [x2, y1], [x2, y2], [x1, y2]]
+
+    b, _ = ffi.sort_quad_boxes(np.array([fc(10, 50, 50, 70), fc(10, 10, 50, 30), fc(10, 30, 50, 50)], np.float32))
+    assert [float(x[:, 1].min()) for x in b] == [10.0, 30.0, 50.0]
+    b, o = ffi.sort_quad_boxes(np.array([fc(60, 10, 100, 30), fc(10, 11, 50, 31), fc(10, 50, 50, 70),
+                                         fc(60, 52, 100, 72)], np.float32))
+    assert o.tolist() == [1, 0, 2, 3]
+    b, o = ffi.sort_quad_boxes(np.zeros((0, 4, 2), np.float32))
+    assert len(b) == 0
+
+
+def test_sort_quad_boxes_matches_oracle(built_lib):
+    from oar_ocr_b200 import ffi
+    from oracle import cpu
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 64, 300):
+        tl = np.stack([rng.integers(0, 900, n), rng.integers(0, 40, n) * 9], -1).astype(np.float32)
+        boxes = tl[:, None, :] + np.array([[0, 0], [80, 0], [80, 20], [0, 20]], np.float32)[None]
+        gb, go = ffi.sort_quad_boxes(boxes)
+        wb, wo = cpu.sort_quad_boxes(boxes)
+        assert np.array_equal(go, wo) and np.array_equal(gb, wb)
+
+
+def test_builder_batch_size_validation():
+    """ocr.rs:1168-1195"""
+    from oar_ocr_b200.ocr import MAX_BATCH_SIZE, OAROCRBuilder, OCRError
+    OAROCRBuilder.validate_batch_size("image_batch_size", 1)
+    OAROCRBuilder.validate_batch_size("region_batch_size", MAX_BATCH_SIZE)
+    for name, v in (("image_batch_size", 0), ("region_batch_size", MAX_BATCH_SIZE + 1)):
+        with pytest.raises(OCRError) as e:
+            OAROCRBuilder.validate_batch_size(name, v)
+        assert name in str(e.value) and f"1..={MAX_BATCH_SIZE}" in str(e.value)
+
+
+def test_character_list_layout():
+    """decode.rs:392-423: blank first, dictionary, trailing space"""
+    from oar_ocr_b200.ocr import character_list
+    from oar_ocr_b200.models import synthetic_dict
+    chars = character_list(synthetic_dict())
+    assert len(chars) == 18385 and chars[0] == "\0" and chars[-1] == " "
+
+
+def test_recognition_builder_requires_dict():
+    from oar_ocr_b200.ocr import OCRError, TextRecognitionPredictor
+    with pytest.raises(OCRError) as e:
+        TextRecognitionPredictor.builder().build("synthetic")
+    assert "dict_path" in str(e.value)
+
+
+def test_model_blobs_are_well_formed(det_blob, rec_blob):
+    from oracle.net import parse
+    for blob, kind in ((det_blob, 0), (rec_blob, 1)):
+        k, n_tensors, ops, weights = parse(blob)
+        assert k == kind and len(ops) > 40
+        assert struct.unpack_from("<I", blob, 4)[0] == 1
+        for op in ops:
+            assert 0 <= op["in0"] < n_tensors and 0 <= op["out"] < n_tensors
+            for o, n in zip(op["w_off"], op["w_len"]):
+                assert 0 <= o and o + n <= len(weights)
+    # CTC head: V = 18385 = dict + blank + space
+    assert parse(rec_blob)[2][-1]["p"][1] == 18385
+
+
+def test_oracle_pipeline_smoke(det_blob, rec_blob):
+    """the oracle's own end-to-end composition yields boxes and label sequences on a synthetic page"""
+    from oar_ocr_b200 import synth
+    from oracle import pipeline
+    from oracle.net import OracleNet
+    res = pipeline.predict(OracleNet(det_blob), OracleNet(rec_blob), [synth.page(9, 480)], 18385,
+                           region_batch_size=4)[0]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hotpath_v1.npz"))
+    assert len(res) == len(g["pipe_boxes"]) >= 5
+    for i, r in enumerate(res):
+        assert np.array_equal(r["box"], g["pipe_boxes"][i])
+    assert np.array_equal(np.concatenate([r["labels"] for r in res]), g["pipe_labels"])
