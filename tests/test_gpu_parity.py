@@ -320,7 +320,7 @@ def test_det_run_vs_oracle_mixed_shapes(nets, oracle_nets):
     assert sum(len(w[0]) for w in want) >= 8
     for g, w in zip(got, want):
         _boxes_equal((g[0], np.zeros(0)), (w[0], np.zeros(0)))  # boxes bit-exact
-        assert np.abs(g[1] - w[1]).max() <= LOGIT_TOL           # scores are means of net outputs
+        assert len(w[1]) == 0 or np.abs(g[1] - w[1]).max() <= LOGIT_TOL  # scores are means of net outputs
     assert det.det_run([], cfg) == []
 
 
