@@ -34,20 +34,6 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // dense conv / linear / 2x2-s2 transposed conv as an implicit GEMM (SIMT)
 //   C[M,N] = A[M,K] * W[N,K]^T,  M = B*Ho*Wo, K = kh*kw*Cin (k = (ky,kx,ci))
 // ---------------------------------------------------------------------------
-struct ConvParams {
-  const float* in;
-  const float* w;
-  const float* bias;
-  float* out;
-  int B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw;
-  int N, K, M;
-  int out_ld, out_c_off;
-  int act;
-  float post_scale, post_bias;
-  int mode;  // 0 conv, 1 deconv2x2 scatter (N = 4*Cout)
-  int cout;  // deconv: real output channels
-};
-
 constexpr int BM = 64, BN = 64, BK = 16;
 
 __global__ void __launch_bounds__(256) conv_gemm_simt(ConvParams p) {
@@ -172,6 +158,12 @@ void launch_conv_simt(oar_ctx* ctx, const ConvParams& p, const char* name) {
   dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN));
   Launch l(ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw) + (double)p.M * p.N));
   conv_gemm_simt<<<grid, 256, 0, ctx->stream>>>(p);
+}
+
+// engine dispatch: tensor-core kernel when the model runs engine 1 and has packed weights for `key`
+static void launch_gemm(oar_model* m, int key, const ConvParams& p, const char* name_simt, const char* name_tc) {
+  if (m->engine == 1 && tc_gemm(m, key, p, name_tc)) return;
+  launch_conv_simt(m->ctx, p, name_simt);
 }
 
 // ---------------------------------------------------------------------------
@@ -485,11 +477,6 @@ void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C
 // ---------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------
-// tensor-core overrides (gemm_tc.cu); return false to fall through to SIMT
-bool tc_try_conv(oar_model* m, int op_index, const OpRec& op, const Tensor& in, Tensor& out, int out_ld, int c_off);
-bool tc_try_ctc_head(oar_model* m, int op_index, const OpRec& op, const Tensor& in, bool want_probs, Tensor& probs,
-                     CtcOut* ctc);
-
 static inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
 Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc) {
@@ -521,7 +508,6 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         int Ho = conv_out(a.H, kh, sh, ph), Wo = conv_out(a.W, kw, sw, pw);
         int ctot = op.p[11] ? op.p[11] : cout, coff = op.p[11] ? op.p[10] : 0;
         Tensor& o = ensure(op.out, a.B, Ho, Wo, ctot);
-        if (m->engine == 1 && tc_try_conv(m, (int)oi, op, a, o, ctot, coff)) break;
         ConvParams p{};
         p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = o.p;
         p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = cin, p.Ho = Ho, p.Wo = Wo;
@@ -529,7 +515,8 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.N = cout, p.K = kh * kw * cin, p.M = a.B * Ho * Wo;
         p.out_ld = ctot, p.out_c_off = coff, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
         p.mode = 0, p.cout = cout;
-        launch_conv_simt(ctx, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt");
+        launch_gemm(m, (int)oi * 2, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt",
+                    (kh == 1 && kw == 1) ? "conv1x1_tc" : "convkxk_tc");
         break;
       }
       case OP_DECONV2: {
@@ -541,7 +528,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.kh = p.kw = p.sh = p.sw = 1, p.ph = p.pw = 0;
         p.N = 4 * cout, p.K = cin, p.M = a.B * a.H * a.W;
         p.act = op.p[2], p.post_scale = 1.0f, p.post_bias = 0.0f, p.mode = 1, p.cout = cout;
-        launch_conv_simt(ctx, p, "deconv2x2_simt");
+        launch_gemm(m, (int)oi * 2, p, "deconv2x2_simt", "deconv2x2_tc");
         break;
       }
       case OP_DWCONV: {
@@ -635,7 +622,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
         p.kh = p.kw = p.sh = p.sw = 1;
         p.N = 3 * c, p.K = c, p.M = a.B * T, p.out_ld = 3 * c, p.post_scale = 1.0f, p.cout = 3 * c;
-        launch_conv_simt(ctx, p, "attn_qkv_simt");
+        launch_gemm(m, (int)oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
         {
           Launch l(ctx, "attn_core", 4.0 * a.B * heads * (double)T * T * 15, 4.0 * a.B * T * 4 * c);
           attn_core_kernel<15><<<dim3(heads, a.B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
@@ -644,7 +631,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         p.in = att, p.w = m->w(op, 2), p.bias = m->w(op, 3), p.out = o.p;
         p.N = c, p.out_ld = c, p.cout = c;
-        launch_conv_simt(ctx, p, "attn_proj_simt");
+        launch_gemm(m, (int)oi * 2 + 1, p, "attn_proj_simt", "attn_proj_tc");
         break;
       }
       case OP_CTC_HEAD: {
@@ -652,10 +639,31 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         int T = a.H * a.W;
         size_t rows = (size_t)a.B * T;
         Tensor probs;
-        if (m->engine == 1 && tc_try_ctc_head(m, (int)oi, op, a, want_probs, probs, ctc)) {
-          last = probs;
-          t[op.out] = probs;
-          break;
+        {
+          // tensor-core engine, results only: the head GEMM keeps the logits in TMEM and its epilogue reduces each
+          // 128 x BN tile to (max, last arg-max, sum exp); a small combine kernel finishes the softmax-max.
+          int nt = (m->engine == 1 && !want_probs) ? tc_n_tiles(m, (int)oi * 2) : 0;
+          if (nt > 0) {
+            CtcOut local;
+            CtcOut* co = ctc ? ctc : &local;
+            co->idx = ctx->arena.get<int32_t>(rows);
+            co->prob = ctx->arena.get<float>(rows);
+            co->B = a.B, co->T = T, co->V = V;
+            ConvParams p{};
+            p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = nullptr;
+            p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
+            p.kh = p.kw = p.sh = p.sw = 1;
+            p.N = V, p.K = c, p.M = (int)rows, p.out_ld = V, p.post_scale = 1.0f, p.cout = V, p.mode = 2;
+            p.part_max = ctx->arena.get<float>(rows * nt);
+            p.part_idx = ctx->arena.get<int32_t>(rows * nt);
+            p.part_sum = ctx->arena.get<float>(rows * nt);
+            if (tc_gemm(m, (int)oi * 2, p, "ctc_head_fused_tc")) {
+              launch_ctc_combine(ctx, p.part_max, p.part_idx, p.part_sum, rows, nt, co->idx, co->prob);
+              t[op.out] = probs;
+              last = probs;
+              break;
+            }
+          }
         }
         float* logits = ctx->arena.get<float>(rows * V);
         ConvParams p{};
@@ -663,7 +671,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
         p.kh = p.kw = p.sh = p.sw = 1;
         p.N = V, p.K = c, p.M = (int)rows, p.out_ld = V, p.post_scale = 1.0f, p.cout = V;
-        launch_conv_simt(ctx, p, "ctc_head_gemm_simt");
+        launch_gemm(m, (int)oi * 2, p, "ctc_head_gemm_simt", "ctc_head_gemm_tc");
         CtcOut local;
         CtcOut* co = ctc ? ctc : &local;
         co->idx = ctx->arena.get<int32_t>(rows);

@@ -36,6 +36,26 @@ struct Tensor {
   size_t numel() const { return (size_t)B * H * W * C; }
 };
 
+// Implicit-GEMM description shared by the SIMT (engine.cu) and tcgen05 (gemm_tc.cu) kernels:
+//   C[M,N] = A[M,K] * W[N,K]^T,  M = B*Ho*Wo, K = kh*kw*Cin ordered (ky,kx,ci)
+struct ConvParams {
+  const float* in;
+  const float* w;
+  const float* bias;
+  float* out;
+  int B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw;
+  int N, K, M;
+  int out_ld, out_c_off;
+  int act;
+  float post_scale, post_bias;
+  int mode;  // 0 conv, 1 deconv2x2 scatter (N = 4*Cout), 2 CTC partial softmax/argmax (tensor-core engine only)
+  int cout;  // deconv: real output channels
+  // mode 2 outputs: per (row, n-tile) running max / last arg-max / sum of exp(z - max)
+  float* part_max;
+  int32_t* part_idx;
+  float* part_sum;
+};
+
 // Output of the fused CTC head: per (b,t) argmax class and its softmax prob.
 struct CtcOut {
   int32_t* idx = nullptr;
@@ -70,6 +90,13 @@ Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ct
 // tensor-core engine lifetime hooks (gemm_tc.cu): build fp16 weight copies / release them
 void tc_model_init(oar_model* m);
 void tc_model_free(oar_model* m);
+// Launches the tcgen05 kernel for the GEMM identified by `key` (op index * 2 + sub); false if this
+// model has no packed weights for it (the caller then runs the SIMT kernel).
+bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name);
+// number of N tiles the tensor-core engine uses for `key` (0 if absent); sizes the mode-2 partials
+int tc_n_tiles(const oar_model* m, int key);
+void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
+                        int n_tiles, int32_t* idx, float* prob);
 
 // input layout conversion for the seam-1 API (NCHW f32 host layout -> NHWC)
 void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C, int H, int W);
