@@ -226,9 +226,12 @@ def run_b200(args, rank, local_rank, world):
         ctx.profile(True)
         agg = {}
         P = 2
+        raw = []
         for _ in range(P):
             step(dev_ptrs, True)
-            for r in ctx.profile_read():
+            recs = ctx.profile_read()
+            raw = recs
+            for r in recs:
                 a = agg.setdefault(r["name"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
                 a["ms"] += r["ms"]
                 a["flops"] += r["flops"]
@@ -261,6 +264,8 @@ def run_b200(args, rank, local_rank, world):
         if os.path.isdir(out_dir):
             with open(os.path.join(out_dir, "bench_kernels.json"), "w") as f:
                 json.dump(dict(kernels=kernels, stage_ms=stage, e2e_stage_ms=e2e_stage), f, indent=1)
+            with open(os.path.join(out_dir, "bench_records.json"), "w") as f:
+                json.dump([[r["name"], round(r["ms"], 5), r["flops"], r["bytes"]] for r in raw], f)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -31,14 +31,13 @@
 namespace oar {
 
 constexpr int TC_BM = 128;        // UMMA M
-constexpr int TC_BK = 32;         // k elements per stage
-constexpr int TC_KC = TC_BK / 8;  // 16-byte k-chunks per stage
+// k elements per shared-memory stage: 64 (8 16-byte chunks) when the GEMM has K > 32, else 32 (4 chunks)
 constexpr int TC_STAGES = 2;
 constexpr int TC_MAX_BN = 256;
 
 struct TcWeights {
   uint4* packed = nullptr;  // [n_tile][k_block][hi|lo][k-chunk][BN rows][8 halfs]
-  int N = 0, K = 0, BN = 0, n_tiles = 0, nkb = 0;
+  int N = 0, K = 0, BN = 0, n_tiles = 0, nkb = 0, KC = 4;
 };
 
 struct TcState {
@@ -149,21 +148,121 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 struct TcParams {
   ConvParams c;
   const uint4* wpk;
-  int BN, nkb, n_tiles, tmem_cols;
-  int a_mode;  // 0 pointwise (row pointer), 1 conv with Cin % 8 == 0 (vector taps), 2 generic scalar gather
+  int BN, nkb, n_tiles, tmem_cols, stages;
 };
 
-__global__ void __launch_bounds__(128) conv_gemm_tc(const TcParams P) {
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int TC_THREADS = 256;  // two threads per output row: each takes half the k-chunks and half the columns
+
+// A-operand gather modes
+constexpr int AM_POINTWISE = 0;  // 1x1 stride-1 conv / linear, Cin % 8 == 0: the row is contiguous
+constexpr int AM_TAPS = 1;       // kxk conv, Cin % 8 == 0: a 16-byte chunk never straddles a tap
+constexpr int AM_SCALAR = 2;     // anything else (stem Cin = 3, odd channel counts)
+// epilogues: EPI = mode * 8 + activation (mode 0 conv, 1 transposed conv), EPI_CTC = fused CTC reduction
+constexpr int EPI_CTC = 16;
+
+// One thread's share of a k-block of A: its pixel row's chunks kc = half, half + 2, ... as raw fp32 in registers.
+// Issued one k-block ahead so the HBM/L2 latency overlaps the previous block's split, barrier and MMAs.
+template <int KC>
+struct ARegs {
+  float4 v[KC];  // KC / 2 chunks x 2 float4
+};
+
+template <int KC, int A_MODE>
+__device__ __forceinline__ void load_a(const ConvParams& p, int kb, int half, bool row_ok, const float* arow, int ab,
+                                       int aho, int awo, ARegs<KC>& r) {
+#pragma unroll
+  for (int j = 0; j < KC / 2; ++j) {
+    const int k0 = kb * (KC * 8) + (2 * j + half) * 8;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+    if (row_ok && k0 < p.K) {
+      if (A_MODE == AM_POINTWISE) {
+        u = __ldg(reinterpret_cast<const float4*>(arow + k0));
+        v = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
+      } else if (A_MODE == AM_TAPS) {
+        int tap = k0 / p.Cin, ci = k0 - tap * p.Cin;
+        int ky = tap / p.kw, kx = tap - ky * p.kw;
+        int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+          const float* src = p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci;
+          u = __ldg(reinterpret_cast<const float4*>(src));
+          v = __ldg(reinterpret_cast<const float4*>(src + 4));
+        }
+      } else {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[i] = 0.0f;
+          int k = k0 + i;
+          if (k < p.K) {
+            int tap = k / p.Cin, ci = k - tap * p.Cin;
+            int ky = tap / p.kw, kx = tap - ky * p.kw;
+            int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
+            if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+              x[i] = __ldg(p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci);
+          }
+        }
+        u = make_float4(x[0], x[1], x[2], x[3]);
+        v = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
+    r.v[2 * j] = u;
+    r.v[2 * j + 1] = v;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == ACT_HSWISH) return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f;
+  if (ACT == ACT_SWISH) return v / (1.0f + expf(-v));
+  if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  if (ACT == ACT_HSIGMOID) return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
+  return v;
+}
+
+template <int KC, int A_MODE, int EPI>
+__global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BK = KC * 8;
   const ConvParams& p = P.c;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TC_BM - 1), half = tid >> 7;
   const int BN = P.BN;
-  const uint32_t a_part = TC_KC * TC_BM * 16;  // bytes of one A part (hi or lo) per stage
-  const uint32_t b_part = TC_KC * BN * 16;
+  const uint32_t a_part = KC * TC_BM * 16;  // bytes of one A part (hi or lo) per stage
+  const uint32_t b_part = KC * BN * 16;
   const uint32_t stage_bytes = 2 * a_part + 2 * b_part;
-  uint8_t* ctrl = smem + TC_STAGES * stage_bytes;
+  const int smask = P.stages - 1;
+  uint8_t* ctrl = smem + P.stages * stage_bytes;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(ctrl);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * TC_STAGES);
+
+  // this thread's output row (pixel)
+  const int m = blockIdx.x * TC_BM + row;
+  const bool row_ok = m < p.M;
+  int ab = 0, aho = 0, awo = 0;
+  if (A_MODE != AM_POINTWISE && row_ok) {
+    ab = m / (p.Ho * p.Wo);
+    int r = m - ab * p.Ho * p.Wo;
+    aho = r / p.Wo;
+    awo = r - aho * p.Wo;
+  }
+  const float* arow = p.in + (size_t)m * p.Cin;  // pointwise only
+  const int nt = blockIdx.y;
+  const uint4* wtile = P.wpk + (size_t)nt * P.nkb * (2 * KC * BN);
+  const int nvec_b = 2 * KC * BN;  // 16-byte vectors of one B stage (hi then lo)
+
+  // first k-block: A into registers, B straight into stage 0 (both in flight during the set-up below)
+  ARegs<KC> pre;
+  load_a<KC, A_MODE>(p, 0, half, row_ok, arow, ab, aho, awo, pre);
+  {
+    const uint32_t b_dst = smem_u32(smem + 2 * a_part);
+    for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, wtile + i);
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -175,75 +274,26 @@ __global__ void __launch_bounds__(128) conv_gemm_tc(const TcParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // this thread's output row (pixel)
-  const int m = blockIdx.x * TC_BM + tid;
-  const bool row_ok = m < p.M;
-  int ab = 0, aho = 0, awo = 0;
-  if (row_ok && P.a_mode != 0) {
-    ab = m / (p.Ho * p.Wo);
-    int r = m - ab * p.Ho * p.Wo;
-    aho = r / p.Wo;
-    awo = r - aho * p.Wo;
-  }
-  const float* arow = p.in + (size_t)m * p.Cin;  // a_mode 0 only
-  const int nt = blockIdx.y;
-  const uint4* wtile = P.wpk + (size_t)nt * P.nkb * (2 * TC_KC * BN);
   // instruction descriptor: D fp32, A/B fp16, both K-major, N = BN, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
   for (int kb = 0; kb < P.nkb; ++kb) {
-    const int s = kb & 1;
+    const int s = kb & smask;
     uint8_t* st = smem + s * stage_bytes;
-    if (kb >= TC_STAGES) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((kb >> 1) - 1) & 1));
-    // ---- A: gather, split, store
+    // stage s is free: its previous reader MMA(kb-2) was waited for at the end of iteration kb-1
     uint4* a_hi = reinterpret_cast<uint4*>(st);
     uint4* a_lo = reinterpret_cast<uint4*>(st + a_part);
 #pragma unroll
-    for (int kc = 0; kc < TC_KC; ++kc) {
-      const int k0 = kb * TC_BK + kc * 8;
-      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (row_ok && k0 < p.K) {
-        if (P.a_mode == 0) {
-          float4 u = __ldg(reinterpret_cast<const float4*>(arow + k0));
-          float4 v = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
-          x[0] = u.x, x[1] = u.y, x[2] = u.z, x[3] = u.w, x[4] = v.x, x[5] = v.y, x[6] = v.z, x[7] = v.w;
-        } else if (P.a_mode == 1) {
-          int tap = k0 / p.Cin, ci = k0 - tap * p.Cin;
-          int ky = tap / p.kw, kx = tap - ky * p.kw;
-          int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
-          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-            const float* src = p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci;
-            float4 u = __ldg(reinterpret_cast<const float4*>(src));
-            float4 v = __ldg(reinterpret_cast<const float4*>(src + 4));
-            x[0] = u.x, x[1] = u.y, x[2] = u.z, x[3] = u.w, x[4] = v.x, x[5] = v.y, x[6] = v.z, x[7] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int k = k0 + i;
-            if (k < p.K) {
-              int tap = k / p.Cin, ci = k - tap * p.Cin;
-              int ky = tap / p.kw, kx = tap - ky * p.kw;
-              int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
-              if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-                x[i] = __ldg(p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci);
-            }
-          }
-        }
-      }
+    for (int j = 0; j < KC / 2; ++j) {
+      float x[8] = {pre.v[2 * j].x,     pre.v[2 * j].y,     pre.v[2 * j].z,     pre.v[2 * j].w,
+                    pre.v[2 * j + 1].x, pre.v[2 * j + 1].y, pre.v[2 * j + 1].z, pre.v[2 * j + 1].w};
       uint4 hi, lo;
       split8(x, hi, lo);
-      a_hi[kc * TC_BM + tid] = hi;
-      a_lo[kc * TC_BM + tid] = lo;
+      a_hi[(2 * j + half) * TC_BM + row] = hi;
+      a_lo[(2 * j + half) * TC_BM + row] = lo;
     }
-    // ---- B: linear copy of the pre-packed stage (hi then lo)
-    {
-      uint4* b_dst = reinterpret_cast<uint4*>(st + 2 * a_part);
-      const uint4* b_src = wtile + (size_t)kb * (2 * TC_KC * BN);
-      const int nvec = 2 * TC_KC * BN;
-      for (int i = tid; i < nvec; i += 128) b_dst[i] = __ldg(b_src + i);
-    }
+    cp_async_wait_all();  // this thread's share of B(kb)
+    if (kb + 1 < P.nkb) load_a<KC, A_MODE>(p, kb + 1, half, row_ok, arow, ab, aho, awo, pre);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -252,7 +302,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc(const TcParams P) {
       const uint32_t b_hi_s = a_hi_s + 2 * a_part, b_lo_s = b_hi_s + b_part;
       const uint32_t a_lbo = TC_BM * 16, b_lbo = (uint32_t)BN * 16;
 #pragma unroll
-      for (int j = 0; j < TC_BK / 16; ++j) {
+      for (int j = 0; j < BK / 16; ++j) {
         uint64_t ah = make_desc(a_hi_s + 2 * j * a_lbo, a_lbo, 128);
         uint64_t al = make_desc(a_lo_s + 2 * j * a_lbo, a_lbo, 128);
         uint64_t bh = make_desc(b_hi_s + 2 * j * b_lbo, b_lbo, 128);
@@ -263,22 +313,32 @@ __global__ void __launch_bounds__(128) conv_gemm_tc(const TcParams P) {
       }
       umma_commit(smem_u32(&mbar[s]));
     }
+    if (kb + 1 < P.nkb) {
+      // the other stage was last read by MMA(kb-1): wait for its commit, then stream B(kb+1) into it
+      if (kb >= 1) mbar_wait(smem_u32(&mbar[s ^ 1]), (uint32_t)(((kb - 1) >> 1) & 1));
+      const uint32_t b_dst = smem_u32(smem + (s ^ 1) * stage_bytes + 2 * a_part);
+      const uint4* b_src = wtile + (size_t)(kb + 1) * nvec_b;
+      for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, b_src + i);
+    }
   }
   // all MMAs done when the last commit lands (a commit tracks every prior tcgen05 op of the issuing thread)
   {
     const int last = P.nkb - 1;
-    mbar_wait(smem_u32(&mbar[last & 1]), (uint32_t)((last >> 1) & 1));
+    mbar_wait(smem_u32(&mbar[last & smask]), (uint32_t)((P.stages == 2 ? (last >> 1) : last) & 1));
     tc_fence_after();
   }
 
-  // ---- epilogue: thread = row, 16 columns at a time out of TMEM
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  // ---- epilogue: thread = (row, column half); 16 columns at a time out of TMEM.  A warp may only touch the TMEM
+  // lanes 32*(warp%4)..+31, which is exactly `row` for both halves.
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const int n_base = nt * BN;
-  if (p.mode == 2) {
+  if (EPI == EPI_CTC) {
+    // online softmax statistics over this thread's contiguous class range (BN % 32 == 0 for this mode)
     float mx = -INFINITY, sum = 0.0f;
     int mi = 0;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n_base + c0 >= p.N) break;  // uniform across the CTA
+    const int cbeg = half * (BN >> 1), cend = cbeg + (BN >> 1);
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+      if (n_base + c0 >= p.N) break;
       float v[16];
       tmem_ld16(lane_base + c0, v);
 #pragma unroll
@@ -298,52 +358,75 @@ __global__ void __launch_bounds__(128) conv_gemm_tc(const TcParams P) {
       }
     }
     if (row_ok) {
-      size_t o = (size_t)m * P.n_tiles + nt;
+      size_t o = (size_t)m * (2 * P.n_tiles) + 2 * nt + half;
       p.part_max[o] = mx;
       p.part_idx[o] = mi;
       p.part_sum[o] = sum;
     }
-  } else {
-    int ob = 0, oy = 0, ox = 0;
-    if (p.mode == 1 && row_ok) {
-      ob = m / (p.Ho * p.Wo);
-      int r = m - ob * p.Ho * p.Wo;
-      oy = r / p.Wo;
-      ox = r - oy * p.Wo;
-    }
-    const bool vec_ok = p.mode == 0 && ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0);
-    float* orow = p.out + (size_t)m * p.out_ld + p.out_c_off;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+  } else if (EPI < 8) {
+    constexpr int ACT = EPI & 7;
+    const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0);
+    float* orow = p.out + (size_t)m * p.out_ld + p.out_c_off + n_base;
+    const float ps = p.post_scale, pb = p.post_bias;
+    for (int c0 = half * 16; c0 < BN; c0 += 32) {
       if (n_base + c0 >= p.N) break;
       float v[16];
       tmem_ld16(lane_base + c0, v);  // warp-collective: every lane takes part, stores are predicated below
       if (!row_ok) continue;
-      if (p.mode == 0) {
+      if (n_base + c0 + 16 <= p.N) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_base + c0);  // weight arrays are 16-byte aligned
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int n = n_base + c0 + i;
-          if (n < p.N) v[i] = tc_act(v[i] + __ldg(p.bias + n), p.act) * p.post_scale + p.post_bias;
+        for (int i = 0; i < 16; i += 4) {
+          float4 b = ((n_base & 3) == 0) ? __ldg(b4 + (i >> 2))
+                                         : make_float4(__ldg(p.bias + n_base + c0 + i), __ldg(p.bias + n_base + c0 + i + 1),
+                                                       __ldg(p.bias + n_base + c0 + i + 2),
+                                                       __ldg(p.bias + n_base + c0 + i + 3));
+          v[i] = act_t<ACT>(v[i] + b.x) * ps + pb;
+          v[i + 1] = act_t<ACT>(v[i + 1] + b.y) * ps + pb;
+          v[i + 2] = act_t<ACT>(v[i + 2] + b.z) * ps + pb;
+          v[i + 3] = act_t<ACT>(v[i + 3] + b.w) * ps + pb;
         }
-        if (vec_ok && n_base + c0 + 16 <= p.N) {
+        if (vec_ok) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(orow + n_base + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n_base + c0 + i < p.N) orow[n_base + c0 + i] = v[i];
+          for (int i = 0; i < 16; ++i) orow[c0 + i] = v[i];
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           int n = n_base + c0 + i;
-          if (n < p.N) {
-            int q = n / p.cout, co = n - q * p.cout;
-            int dy = q >> 1, dx = q & 1;
-            float r = tc_act(v[i] + __ldg(p.bias + co), p.act) * p.post_scale + p.post_bias;
-            p.out[(((size_t)ob * (2 * p.Ho) + 2 * oy + dy) * (2 * p.Wo) + 2 * ox + dx) * p.cout + co] = r;
-          }
+          if (n < p.N) orow[c0 + i] = act_t<ACT>(v[i] + __ldg(p.bias + n)) * ps + pb;
         }
+      }
+    }
+  } else {
+    // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co scatters to output pixel (2y+dy, 2x+dx)
+    constexpr int ACT = EPI & 7;
+    int ob = 0, oy = 0, ox = 0;
+    if (row_ok) {
+      ob = m / (p.Ho * p.Wo);
+      int r = m - ob * p.Ho * p.Wo;
+      oy = r / p.Wo;
+      ox = r - oy * p.Wo;
+    }
+    const float ps = p.post_scale, pb = p.post_bias;
+    for (int c0 = half * 16; c0 < BN; c0 += 32) {
+      if (n_base + c0 >= p.N) break;
+      float v[16];
+      tmem_ld16(lane_base + c0, v);
+      if (!row_ok) continue;
+      int n = n_base + c0;
+      int q = n / p.cout, co = n - q * p.cout;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (n + i < p.N) {
+          float r = act_t<ACT>(v[i] + __ldg(p.bias + co)) * ps + pb;
+          p.out[(((size_t)ob * (2 * p.Ho) + 2 * oy + (q >> 1)) * (2 * p.Wo) + 2 * ox + (q & 1)) * p.cout + co] = r;
+        }
+        if (++co == p.cout) co = 0, ++q;
       }
     }
   }
@@ -362,7 +445,7 @@ __global__ void ctc_combine_kernel(const float* __restrict__ pmax, const int32_t
   float mx = a[0];
   int mi = pidx[r * n_tiles];
   for (int t = 1; t < n_tiles; ++t)
-    if (a[t] >= mx) mx = a[t], mi = pidx[r * n_tiles + t];  // tiles ascend in class index
+    if (a[t] > mx || (a[t] == mx && pidx[r * n_tiles + t] > mi)) mx = a[t], mi = pidx[r * n_tiles + t];  // last index on ties
   float tot = 0.0f;
   for (int t = 0; t < n_tiles; ++t) tot += psum[r * n_tiles + t] * expf(a[t] - mx);
   idx[r] = mi;
@@ -385,6 +468,8 @@ static TcWeights pack_weights(const float* w, int N, int K) {
   t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
   t.BN = std::max(16, (per + 15) / 16 * 16);
+  t.KC = K > 32 ? 8 : 4;
+  const int TC_KC = t.KC, TC_BK = t.KC * 8;
   t.nkb = (K + TC_BK - 1) / TC_BK;
   size_t halfs = (size_t)t.n_tiles * t.nkb * 2 * TC_KC * t.BN * 8;
   std::vector<__half> buf(halfs, __float2half(0.0f));
@@ -451,7 +536,9 @@ int tc_n_tiles(const oar_model* m, int key) {
   const TcState* st = static_cast<const TcState*>(m->tc_state);
   if (!st) return 0;
   auto it = st->w.find(key);
-  return it == st->w.end() ? 0 : it->second.n_tiles;
+  // mode-2 partial slots: two column halves per N tile; needs BN % 32 == 0 so each half is whole 16-column chunks
+  if (it == st->w.end() || (it->second.BN & 31)) return 0;
+  return 2 * it->second.n_tiles;
 }
 
 bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
@@ -466,27 +553,48 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   P.c = p;
   P.wpk = w.packed;
   P.BN = w.BN, P.nkb = w.nkb, P.n_tiles = w.n_tiles;
+  P.stages = w.nkb > 1 ? 2 : 1;
   int cols = 32;
   while (cols < w.BN) cols <<= 1;
   P.tmem_cols = cols;
   const bool pointwise = p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0;
   const bool aligned = (((uintptr_t)p.in) & 15) == 0;
+  int a_mode = AM_SCALAR;
   if (pointwise && (p.Cin % 8) == 0 && aligned)
-    P.a_mode = 0;
+    a_mode = AM_POINTWISE;
   else if ((p.Cin % 8) == 0 && aligned)
-    P.a_mode = 1;
-  else
-    P.a_mode = 2;
-  size_t smem = (size_t)TC_STAGES * (2 * TC_KC * TC_BM * 16 + 2 * TC_KC * w.BN * 16) + 64;
-  static bool attr_set[64] = {false};
-  if (!attr_set[m->ctx->device & 63]) {  // the attribute is per device
-    OAR_CUDA(cudaFuncSetAttribute(conv_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set[m->ctx->device & 63] = true;
+    a_mode = AM_TAPS;
+  const int epi = p.mode == 2 ? EPI_CTC : p.mode * 8 + p.act;
+  using Kern = void (*)(const TcParams);
+  Kern kern = nullptr;
+#define TC_PICK(KCV, AM, EP) \
+  if (w.KC == KCV && a_mode == AM && epi == EP) kern = conv_gemm_tc<KCV, AM, EP>;
+#define TC_PICK_CONV(AM)                                                                                     \
+  TC_PICK(4, AM, 0) TC_PICK(4, AM, 1) TC_PICK(4, AM, 2) TC_PICK(4, AM, 3) TC_PICK(4, AM, 4) TC_PICK(8, AM, 0) \
+      TC_PICK(8, AM, 1) TC_PICK(8, AM, 2) TC_PICK(8, AM, 3) TC_PICK(8, AM, 4)
+  TC_PICK_CONV(AM_POINTWISE)
+  TC_PICK_CONV(AM_TAPS)
+  TC_PICK_CONV(AM_SCALAR)
+  TC_PICK(4, AM_POINTWISE, 8) TC_PICK(4, AM_POINTWISE, 9) TC_PICK(4, AM_POINTWISE, 12)
+  TC_PICK(8, AM_POINTWISE, 8) TC_PICK(8, AM_POINTWISE, 9) TC_PICK(8, AM_POINTWISE, 12)
+  TC_PICK(4, AM_POINTWISE, EPI_CTC) TC_PICK(8, AM_POINTWISE, EPI_CTC)
+#undef TC_PICK_CONV
+#undef TC_PICK
+  if (!kern) return false;  // combination not instantiated: the caller runs the SIMT kernel
+  if (p.mode == 2 && (w.BN & 31)) return false;
+  size_t smem = (size_t)P.stages * (2 * w.KC * TC_BM * 16 + 2 * w.KC * w.BN * 16) + 64;
+  {
+    static std::map<std::pair<const void*, int>, bool> attr_done;  // the attribute is per (kernel, device)
+    auto key_attr = std::make_pair((const void*)kern, m->ctx->device);
+    if (!attr_done.count(key_attr)) {
+      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done[key_attr] = true;
+    }
   }
   dim3 grid(cdiv(p.M, TC_BM), w.n_tiles);
-  double out_bytes = p.mode == 2 ? 12.0 * p.M * w.n_tiles : 4.0 * (double)p.M * p.N;
+  double out_bytes = p.mode == 2 ? 24.0 * p.M * w.n_tiles : 4.0 * (double)p.M * p.N;
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + out_bytes);
-  conv_gemm_tc<<<grid, 128, smem, m->ctx->stream>>>(P);
+  kern<<<grid, TC_THREADS, smem, m->ctx->stream>>>(P);
   return true;
 }
 
