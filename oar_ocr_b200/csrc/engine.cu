@@ -204,6 +204,116 @@ __global__ void dwconv_kernel(const float* __restrict__ in, const float* __restr
   *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4) = acc;
 }
 
+// Register-tiled depthwise conv: one thread = 4 channels x (TH x TW) output pixels.  The op is LSU-bound (every
+// output reads K*K inputs through L1), so each input float4 is loaded once per thread and reused by all the
+// outputs of the tile it feeds: K*K -> (rows*cols)/(TH*TW) input loads per output (25 -> 6 for 5x5 s1 2x4).
+// Accumulation order per output is bias, then (ky, kx) ascending, as in the generic kernel above.
+template <int K, int SH, int SW, int TH, int TW, int ACT>
+__global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int B, int H, int W, int C, int Ho, int Wo, float ps,
+                                                           float pb) {
+  constexpr int ROWS = (TH - 1) * SH + K, COLS = (TW - 1) * SW + K, PAD = K / 2;
+  const int c4n = C >> 2;
+  const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * tiles_h * tiles_w * c4n;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % c4n);
+  size_t r = idx / c4n;
+  const int tw = (int)(r % tiles_w);
+  r /= tiles_w;
+  const int th = (int)(r % tiles_h);
+  const int b = (int)(r / tiles_h);
+  const int ho0 = th * TH, wo0 = tw * TW;
+  const int ih0 = ho0 * SH - PAD, iw0 = wo0 * SW - PAD;
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  float4 acc[TH][TW];
+#pragma unroll
+  for (int ty = 0; ty < TH; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < TW; ++tx) acc[ty][tx] = bv;
+  const float4* in4 = reinterpret_cast<const float4*>(in) + (size_t)b * H * W * c4n + c4;
+  const float4* w4 = reinterpret_cast<const float4*>(w) + c4;
+#pragma unroll
+  for (int iy = 0; iy < ROWS; ++iy) {
+    const int ih = ih0 + iy;
+    if (ih < 0 || ih >= H) continue;
+    float4 x[COLS];
+#pragma unroll
+    for (int cx = 0; cx < COLS; ++cx) {
+      const int iw = iw0 + cx;
+      x[cx] = (iw >= 0 && iw < W) ? __ldg(in4 + ((size_t)ih * W + iw) * c4n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int ty = 0; ty < TH; ++ty) {
+      const int ky = iy - ty * SH;
+      if (ky < 0 || ky >= K) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const float4 k = __ldg(w4 + (size_t)(ky * K + kx) * c4n);
+#pragma unroll
+        for (int tx = 0; tx < TW; ++tx) {
+          const float4 v = x[tx * SW + kx];
+          acc[ty][tx].x = fmaf(v.x, k.x, acc[ty][tx].x);
+          acc[ty][tx].y = fmaf(v.y, k.y, acc[ty][tx].y);
+          acc[ty][tx].z = fmaf(v.z, k.z, acc[ty][tx].z);
+          acc[ty][tx].w = fmaf(v.w, k.w, acc[ty][tx].w);
+        }
+      }
+    }
+  }
+  float4* out4 = reinterpret_cast<float4*>(out) + (size_t)b * Ho * Wo * c4n + c4;
+#pragma unroll
+  for (int ty = 0; ty < TH; ++ty) {
+    const int ho = ho0 + ty;
+    if (ho >= Ho) continue;
+#pragma unroll
+    for (int tx = 0; tx < TW; ++tx) {
+      const int wo = wo0 + tx;
+      if (wo >= Wo) continue;
+      float4 a = acc[ty][tx];
+      a.x = apply_act(a.x, ACT) * ps + pb;
+      a.y = apply_act(a.y, ACT) * ps + pb;
+      a.z = apply_act(a.z, ACT) * ps + pb;
+      a.w = apply_act(a.w, ACT) * ps + pb;
+      out4[((size_t)ho * Wo + wo) * c4n] = a;
+    }
+  }
+}
+
+template <int K, int SH, int SW, int TH, int TW, int ACT>
+static void launch_dw_tiled(cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int B, int H,
+                            int W, int C, int Ho, int Wo, float ps, float pb) {
+  size_t total = (size_t)B * ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW) * (C >> 2);
+  dwconv_tiled_kernel<K, SH, SW, TH, TW, ACT><<<cdiv((long long)total, 128), 128, 0, st>>>(in, w, bias, out, B, H, W, C,
+                                                                                          Ho, Wo, ps, pb);
+}
+
+// picks a register-tiled instantiation; false -> caller runs the generic kernel
+static bool try_dw_tiled(cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int B, int H,
+                         int W, int C, int Ho, int Wo, int k, int sh, int sw, int ph, int pw, int act, float ps,
+                         float pb) {
+  if (ph != k / 2 || pw != k / 2) return false;
+#define DW_CASE(KV, SHV, SWV, THV, TWV, ACTV)                                                      \
+  if (k == KV && sh == SHV && sw == SWV && act == ACTV) {                                          \
+    launch_dw_tiled<KV, SHV, SWV, THV, TWV, ACTV>(st, in, w, bias, out, B, H, W, C, Ho, Wo, ps, pb); \
+    return true;                                                                                   \
+  }
+  DW_CASE(3, 1, 1, 2, 4, ACT_HSWISH)
+  DW_CASE(5, 1, 1, 2, 4, ACT_HSWISH)
+  DW_CASE(3, 1, 1, 2, 4, ACT_NONE)
+  DW_CASE(5, 1, 1, 2, 4, ACT_NONE)
+  DW_CASE(3, 2, 2, 1, 4, ACT_NONE)
+  DW_CASE(5, 2, 2, 1, 4, ACT_NONE)
+  DW_CASE(3, 2, 1, 1, 4, ACT_NONE)
+  DW_CASE(5, 2, 1, 1, 4, ACT_NONE)
+  DW_CASE(3, 1, 2, 2, 4, ACT_NONE)
+  DW_CASE(5, 1, 2, 2, 4, ACT_NONE)
+#undef DW_CASE
+  return false;
+}
+
 // ---------------------------------------------------------------------------
 // squeeze-excite: deterministic two-stage global average pool, tiny MLP, scale
 // ---------------------------------------------------------------------------
@@ -538,8 +648,10 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(op.out, a.B, Ho, Wo, c);
         size_t total = o.numel() / 4;
         Launch l(ctx, "dwconv", 2.0 * o.numel() * kh * kw, 4.0 * (a.numel() + o.numel()));
-        dwconv_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo,
-                                                         kh, kw, sh, sw, ph, pw, op.p[7], op.f[0], op.f[1]);
+        if (kh != kw || !try_dw_tiled(st, a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo, kh, sh, sw, ph, pw,
+                                      op.p[7], op.f[0], op.f[1]))
+          dwconv_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo,
+                                                           kh, kw, sh, sw, ph, pw, op.p[7], op.f[0], op.f[1]);
         break;
       }
       case OP_SE: {
