@@ -30,12 +30,32 @@ namespace oar {
 // 1. threshold + CCL
 // ---------------------------------------------------------------------------
 __global__ void db_init_kernel(const float* __restrict__ pred, float thresh, uint8_t* __restrict__ state,
-                               int32_t* __restrict__ lab, size_t total, int HW) {
+                               int32_t* __restrict__ lab, size_t total, int HW, int W) {
+  // Launched with whole warps over the linear pixel index: each lane labels its pixel with the first pixel of its
+  // horizontal run *within the warp's 32-pixel segment*, so the union pass only has to stitch segment and row
+  // boundaries instead of every pixel pair.
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool fg = false;
+  int li = 0, x = 0;
+  if (i < total) {
+    fg = pred[i] > thresh;  // strict, db_postprocess.rs:202
+    li = (int)(i % HW);
+    x = li % W;
+  }
+  const unsigned fgm = __ballot_sync(0xffffffffu, fg);
+  const bool prev_fg = lane > 0 && ((fgm >> (lane - 1)) & 1u);
+  const bool is_start = fg && (!prev_fg || x == 0 || li == 0);
+  const unsigned starts = __ballot_sync(0xffffffffu, is_start);
   if (i >= total) return;
-  bool fg = pred[i] > thresh;  // strict, db_postprocess.rs:202
   state[i] = fg ? 1 : 0;
-  lab[i] = fg ? (int32_t)(i % HW) : -1;
+  if (fg) {
+    const unsigned below = starts & (0xffffffffu >> (31 - lane));
+    const int sl = 31 - __clz(below);
+    lab[i] = li - (lane - sl);
+  } else {
+    lab[i] = -1;
+  }
 }
 
 __device__ __forceinline__ int32_t uf_find(const int32_t* lab, int32_t x) {
@@ -75,11 +95,21 @@ __global__ void db_merge_kernel(const uint8_t* __restrict__ state, int32_t* __re
   int y = li / W, x = li - y * W;
   const uint8_t* st = state + (size_t)b * HW;
   int32_t* L = lab + (size_t)b * HW;
-  if (x > 0 && st[li - 1]) uf_union(L, li, li - 1);
+  const bool left = x > 0 && st[li - 1];
+  // a run that continues across the 32-pixel segment boundary of the init pass (or an image boundary in the linear
+  // index): one union per segment instead of one per pixel
+  if (left && (i & 31) == 0) uf_union(L, li, li - 1);  // lane 0 of the init warp: its run start was cut at the segment
   if (y > 0) {
-    if (st[li - W]) uf_union(L, li, li - W);
-    if (x > 0 && st[li - W - 1]) uf_union(L, li, li - W - 1);
-    if (x + 1 < W && st[li - W + 1]) uf_union(L, li, li - W + 1);
+    const bool up = st[li - W];
+    const bool ul = x > 0 && st[li - W - 1];
+    const bool ur = x + 1 < W && st[li - W + 1];
+    if (up) {
+      // redundant when the left neighbour already joined the same upper run through (x-1, y-1)
+      if (!(left && ul)) uf_union(L, li, li - W);
+    } else {
+      if (ul && !left) uf_union(L, li, li - W - 1);
+      if (ur) uf_union(L, li, li - W + 1);
+    }
   }
 }
 
@@ -339,6 +369,60 @@ __device__ MinRect min_rect_from_hull(const float* hx, const float* hy, int n) {
       best.h = height;
       best.angle = atan2f(ny, nx) * 180.0f / PI_F;
     }
+  }
+  return best;
+}
+
+// The same search with the hull edges spread over a warp.  The sequential loop keeps the FIRST edge whose area is
+// strictly smaller (geometry.rs:419); each lane walks its edges in ascending order and the butterfly prefers the
+// smaller area, then the smaller edge index, which selects the same edge.  Per-edge arithmetic is unchanged.
+__device__ MinRect min_rect_from_hull_warp(const float* hx, const float* hy, int n, int lane) {
+  MinRect best{0.f, 0.f, 0.f, 0.f, 0.f};
+  float min_area = 3.402823466e+38f;
+  int best_i = 0x7fffffff;
+  const float PI_F = 3.14159265358979323846f;
+  for (int i = lane; i < n; i += 32) {
+    int j = (i + 1) % n;
+    float ex = hx[j] - hx[i], ey = hy[j] - hy[i];
+    float l2 = ex * ex + ey * ey;
+    if (l2 < 1.1920929e-7f) continue;
+    float inv = 1.0f / sqrtf(l2);
+    float nx = ex * inv, ny = ey * inv;
+    float px = -ny, py = nx;
+    float hix = hx[i], hiy = hy[i];
+    float min_n = 3.402823466e+38f, max_n = -3.402823466e+38f, min_p = 3.402823466e+38f, max_p = -3.402823466e+38f;
+    for (int q = 0; q < n; ++q) {
+      float dx = hx[q] - hix, dy = hy[q] - hiy;
+      float pn = nx * dx + ny * dy;
+      float pp = px * dx + py * dy;
+      if (pn < min_n) min_n = pn;
+      if (pn > max_n) max_n = pn;
+      if (pp < min_p) min_p = pp;
+      if (pp > max_p) max_p = pp;
+    }
+    float width = max_n - min_n, height = max_p - min_p;
+    float area = width * height;
+    if (area < min_area) {
+      min_area = area;
+      best_i = i;
+      float cn = (min_n + max_n) * 0.5f, cp = (min_p + max_p) * 0.5f;
+      best.cx = hix + cn * nx + cp * px;
+      best.cy = hiy + cn * ny + cp * py;
+      best.w = width;
+      best.h = height;
+      best.angle = atan2f(ny, nx) * 180.0f / PI_F;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    float oa = __shfl_xor_sync(0xffffffffu, min_area, o);
+    int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    MinRect ob;
+    ob.cx = __shfl_xor_sync(0xffffffffu, best.cx, o);
+    ob.cy = __shfl_xor_sync(0xffffffffu, best.cy, o);
+    ob.w = __shfl_xor_sync(0xffffffffu, best.w, o);
+    ob.h = __shfl_xor_sync(0xffffffffu, best.h, o);
+    ob.angle = __shfl_xor_sync(0xffffffffu, best.angle, o);
+    if (oa < min_area || (oa == min_area && oi < best_i)) min_area = oa, best_i = oi, best = ob;
   }
   return best;
 }
@@ -617,23 +701,86 @@ struct Cand {
   float score;
 };
 
-__global__ void __launch_bounds__(32) db_geometry_kernel(
-    const float* __restrict__ pred, int H, int W, const ContourRec* __restrict__ recs, const int* __restrict__ order,
-    const int* __restrict__ first, int B, int max_cand, const short2* __restrict__ pool, short2* __restrict__ scratch,
-    const int32_t* __restrict__ dest_wh, float box_thresh, float unclip_ratio, float min_size,
-    Cand* __restrict__ cands, int* __restrict__ err) {
-  int rank = blockIdx.x * blockDim.x + threadIdx.x;
-  int b = blockIdx.y;
-  int cnt = min(first[b + 1] - first[b], max_cand);
-  if (rank >= cnt) return;
-  Cand& out = cands[(size_t)b * max_cand + rank];
-  out.valid = 0;
-  const ContourRec rec = recs[order[first[b] + rank]];
+// box_score_fast with the rows of the box spread over a warp.  The reference sums each scanline left to right
+// from 0.0 and then adds the row partials in row order (db_score.rs:90-133); every lane therefore produces whole-row
+// partials into `part` and lane 0 folds them in row order, which keeps the f32 association bit-identical.
+__device__ float box_score_fast_warp(const float* __restrict__ pred, int W, int H, const float bx[4], const float by[4],
+                                     float* part, int lane) {
+  constexpr int CHUNK = 256;  // rows per pass (size of `part`)
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = 0; i < 4; ++i) {
+    if (bx[i] < mnx) mnx = bx[i];
+    if (bx[i] > mxx) mxx = bx[i];
+    if (by[i] < mny) mny = by[i];
+    if (by[i] > mxy) mxy = by[i];
+  }
+  float fminx = fminf(fmaxf(floorf(mnx), 0.0f), (float)W - 1.0f);
+  float fmaxx = fminf(fmaxf(ceilf(mxx), 0.0f), (float)W - 1.0f);
+  float fminy = fminf(fmaxf(floorf(mny), 0.0f), (float)H - 1.0f);
+  float fmaxy = fminf(fmaxf(ceilf(mxy), 0.0f), (float)H - 1.0f);
+  long long start_y = sat_usize_dev(fminy), end_y = sat_usize_dev(fmaxy) + 1;
+  long long start_x = sat_usize_dev(fminx), end_x = sat_usize_dev(fmaxx) + 1;
+  float total = 0.0f;
+  long long total_px = 0;
+  for (long long y0 = start_y; y0 < end_y; y0 += CHUNK) {
+    long long y1 = y0 + CHUNK < end_y ? y0 + CHUNK : end_y;
+    long long my_px = 0;
+    for (long long yy = y0 + lane; yy < y1; yy += 32) {
+      float y = (float)yy + 0.5f;
+      float xs[4];
+      int nx = 0;
+      for (int i = 0; i < 4; ++i) {
+        int j = (i + 1) & 3;
+        float p1x = bx[i], p1y = by[i], p2x = bx[j], p2y = by[j];
+        if (((p1y <= y && y < p2y) || (p2y <= y && y < p1y)) && fabsf(p2y - p1y) > 1.1920929e-7f) {
+          xs[nx++] = p1x + (y - p1y) * (p2x - p1x) / (p2y - p1y);
+        }
+      }
+      for (int a = 1; a < nx; ++a) {  // stable insertion sort
+        float kx = xs[a];
+        int b = a - 1;
+        while (b >= 0 && xs[b] > kx) {
+          xs[b + 1] = xs[b];
+          --b;
+        }
+        xs[b + 1] = kx;
+      }
+      float line = 0.0f;
+      long long yi = sat_usize_dev(y);
+      if (yi < H) {
+        const float* row = pred + (size_t)yi * W;
+        for (int k = 0; k + 1 < nx; k += 2) {
+          long long x1 = sat_usize_dev(fmaxf(xs[k], (float)start_x));
+          long long x2 = sat_usize_dev(fminf(xs[k + 1], (float)end_x));
+          if (x1 < x2 && x1 >= start_x && x2 <= end_x) {
+            long long xe = x2 < W ? x2 : W;
+            if (x1 < xe) {
+              for (long long x = x1; x < xe; ++x) line += row[x];  // strictly left to right
+              my_px += xe - x1;
+            }
+          }
+        }
+      }
+      part[yy - y0] = line;
+    }
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) my_px += __shfl_xor_sync(0xffffffffu, my_px, o);
+    total_px += my_px;
+    if (lane == 0)
+      for (long long yy = y0; yy < y1; ++yy) total += part[yy - y0];  // row order
+    __syncwarp();
+  }
+  total = __shfl_sync(0xffffffffu, total, 0);
+  return total_px > 0 ? total / (float)total_px : 0.0f;
+}
+
+// phase 1 (one lane): contour -> simplified chain -> convex hull -> min-area rect -> ordered mini box
+__device__ bool cand_mini_box(const ContourRec& rec, const short2* __restrict__ pool, short2* __restrict__ scratch,
+                              float* hx, float* hy, float bx[4], float by[4], float* min_side, int* err) {
   const short2* pts = pool + rec.off;
   short2* simp = scratch + rec.off;
   int n = rec.len;
-  if (n < 3) return;  // get_mini_boxes_from_points: < 3 points -> None (simplified or raw)
-
+  if (n < 3) return false;  // get_mini_boxes_from_points: < 3 points -> None (simplified or raw)
   // --- simplify_chain_points (db_bitmap.rs:207-239) ---
   int ns = 0;
   {
@@ -653,13 +800,12 @@ __global__ void __launch_bounds__(32) db_geometry_kernel(
     P = pts;
     np = n;
   }
-  // --- convex hull of integer points.  All cross products are exact in f32 for |coord| < 4096,
-  // so the reference's Graham scan yields the unique strict hull, starting at the lowest-y
-  // (then lowest-x) point in increasing polar angle; Jarvis march reproduces that sequence. ---
+  // --- convex hull of integer points.  All cross products are exact in f32 for |coord| < 4096, so the
+  // reference's Graham scan yields the unique strict hull, starting at the lowest-y (then lowest-x) point in
+  // increasing polar angle; Jarvis march reproduces that sequence. ---
   int s = 0;
   for (int i = 1; i < np; ++i)
     if (P[i].y < P[s].y || (P[i].y == P[s].y && P[i].x < P[s].x)) s = i;
-  float hx[UNCLIP_CAP], hy[UNCLIP_CAP];
   int nh = 0;
   {
     int cx = P[s].x, cy = P[s].y;
@@ -667,11 +813,10 @@ __global__ void __launch_bounds__(32) db_geometry_kernel(
     for (;;) {
       if (nh >= UNCLIP_CAP) {
         atomicExch(err, 2);
-        return;
+        return false;
       }
       hx[nh] = (float)cx, hy[nh] = (float)cy, ++nh;
-      // next = the point q such that every other point is to the left of cur->q (cross >= 0),
-      // farthest among collinear
+      // next = the point q such that every other point is to the left of cur->q, farthest among collinear
       int bx_ = cx, by_ = cy;
       bool have = false;
       for (int i = 0; i < np; ++i) {
@@ -687,7 +832,6 @@ __global__ void __launch_bounds__(32) db_geometry_kernel(
         } else if (cr == 0) {
           long long d1 = (long long)(bx_ - cx) * (bx_ - cx) + (long long)(by_ - cy) * (by_ - cy);
           long long d2 = (long long)(qx - cx) * (qx - cx) + (long long)(qy - cy) * (qy - cy);
-          // collinear: same direction -> take the farther; opposite direction cannot both be extreme
           long long dot = (long long)(bx_ - cx) * (qx - cx) + (long long)(by_ - cy) * (qy - cy);
           if (dot > 0 && d2 > d1) bx_ = qx, by_ = qy;
         }
@@ -701,9 +845,7 @@ __global__ void __launch_bounds__(32) db_geometry_kernel(
   }
   MinRect r;
   if (nh < 3) {
-    float tx[4], ty[4];
-    // degenerate: AABB over the source points
-    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;  // degenerate: AABB of the points
     for (int i = 0; i < np; ++i) {
       float fx = (float)P[i].x, fy = (float)P[i].y;
       if (fx < mnx) mnx = fx;
@@ -711,48 +853,130 @@ __global__ void __launch_bounds__(32) db_geometry_kernel(
       if (fy < mny) mny = fy;
       if (fy > mxy) mxy = fy;
     }
-    (void)tx;
-    (void)ty;
     r = MinRect{(mnx + mxx) * 0.5f, (mny + mxy) * 0.5f, mxx - mnx, mxy - mny, 0.0f};
   } else {
     r = min_rect_from_hull(hx, hy, nh);
   }
-  float bx[4], by[4], min_side;
-  if (!rect_to_ordered_box(r, bx, by, &min_side)) return;
-  if (min_side < min_size) return;
-  float score = box_score_fast_dev(pred + (size_t)b * H * W, W, H, bx, by);
-  if (score < box_thresh) return;
-  // --- unclip + second mini box ---
-  float* ux = hx;
-  float* uy = hy;
-  int nu = unclip_dev(bx, by, unclip_ratio, ux, uy);
+  return rect_to_ordered_box(r, bx, by, min_side);
+}
+
+// phase 2 (warp): unclip (lane 0) -> Graham hull with a stable rank sort spread over the lanes -> min-area rect
+// (edges spread over the lanes) -> ordered box -> rescale, clamp.  ws = per-warp shared scratch, 6 x UNCLIP_CAP floats.
+__device__ bool cand_unclip_box_warp(const float bx[4], const float by[4], float unclip_ratio, float min_size, float* ws,
+                                     unsigned dw, unsigned dh, int W, int H, float* out_box, int* err, int lane) {
+  float* ux = ws;
+  float* uy = ws + UNCLIP_CAP;
+  float* tx = ws + 2 * UNCLIP_CAP;
+  float* ty = ws + 3 * UNCLIP_CAP;
+  float* ang = ws + 4 * UNCLIP_CAP;
+  float* dist = ws + 5 * UNCLIP_CAP;
+  int nu = 0;
+  if (lane == 0) nu = unclip_dev(bx, by, unclip_ratio, ux, uy);
+  nu = __shfl_sync(0xffffffffu, nu, 0);
   if (nu < 0) {
-    atomicExch(err, 3);
-    return;
+    if (lane == 0) atomicExch(err, 3);
+    return false;
   }
-  if (nu == 0) return;
-  MinRect r2;
-  {
-    float ang[UNCLIP_CAP], dist[UNCLIP_CAP];
-    float sx2[UNCLIP_CAP], sy2[UNCLIP_CAP];
-    for (int i = 0; i < nu; ++i) sx2[i] = ux[i], sy2[i] = uy[i];
-    int h2 = graham_hull_inplace(sx2, sy2, nu, ang, dist);
-    if (h2 < 3)
-      r2 = aabb_rect(ux, uy, nu);
-    else
-      r2 = min_rect_from_hull(sx2, sy2, h2);
+  if (nu == 0) return false;
+  __syncwarp();
+  // convex_hull_from_points (geometry.rs:226-274): start = lowest y then lowest x, swapped to the front
+  if (lane == 0) {
+    int s = 0;
+    for (int i = 1; i < nu; ++i)
+      if (uy[i] < uy[s] || (uy[i] == uy[s] && ux[i] < ux[s])) s = i;
+    float t0 = ux[0], t1 = uy[0];
+    ux[0] = ux[s], uy[0] = uy[s];
+    ux[s] = t0, uy[s] = t1;
   }
+  __syncwarp();
+  const float spx = ux[0], spy = uy[0];
+  for (int i = 1 + lane; i < nu; i += 32) {
+    float dx = ux[i] - spx, dy = uy[i] - spy;
+    ang[i] = atan2f(dy, dx);
+    dist[i] = dx * dx + dy * dy;
+  }
+  __syncwarp();
+  // stable sort of points 1.. by (angle, distance) under total_cmp: rank = number of elements that sort before
+  for (int i = 1 + lane; i < nu; i += 32) {
+    const float ka = ang[i], kd = dist[i];
+    int rank = 1;
+    for (int j = 1; j < nu; ++j) {
+      int c = total_cmp_f32(ang[j], ka);
+      if (c == 0) c = total_cmp_f32(dist[j], kd);
+      if (c < 0 || (c == 0 && j < i)) ++rank;
+    }
+    tx[rank] = ux[i];
+    ty[rank] = uy[i];
+  }
+  if (lane == 0) tx[0] = spx, ty[0] = spy;
+  __syncwarp();
+  int h2 = 0;
+  if (lane == 0) {  // Graham scan: pop while cross <= 0
+    for (int i = 0; i < nu; ++i) {
+      float px = tx[i], py = ty[i];
+      while (h2 > 1) {
+        float cr = (ux[h2 - 1] - ux[h2 - 2]) * (py - uy[h2 - 2]) - (uy[h2 - 1] - uy[h2 - 2]) * (px - ux[h2 - 2]);
+        if (cr <= 0.0f) --h2; else break;
+      }
+      ux[h2] = px, uy[h2] = py;
+      ++h2;
+    }
+  }
+  h2 = __shfl_sync(0xffffffffu, h2, 0);
+  __syncwarp();
+  MinRect r2 = h2 < 3 ? aabb_rect(tx, ty, nu) : min_rect_from_hull_warp(ux, uy, h2, lane);
   float qx[4], qy[4], sside;
-  if (!rect_to_ordered_box(r2, qx, qy, &sside)) return;
-  if (sside < min_size + 2.0f) return;
-  unsigned dw = (unsigned)dest_wh[2 * b], dh = (unsigned)dest_wh[2 * b + 1];
-  float width_scale = (float)dw / (float)W, height_scale = (float)dh / (float)H;
-  for (int i = 0; i < 4; ++i) {
-    out.box[2 * i] = fminf(fmaxf(roundf(qx[i] * width_scale), 0.0f), (float)dw);
-    out.box[2 * i + 1] = fminf(fmaxf(roundf(qy[i] * height_scale), 0.0f), (float)dh);
+  if (!rect_to_ordered_box(r2, qx, qy, &sside)) return false;
+  if (sside < min_size + 2.0f) return false;
+  if (lane == 0) {
+    float width_scale = (float)dw / (float)W, height_scale = (float)dh / (float)H;
+    for (int i = 0; i < 4; ++i) {
+      out_box[2 * i] = fminf(fmaxf(roundf(qx[i] * width_scale), 0.0f), (float)dw);
+      out_box[2 * i + 1] = fminf(fmaxf(roundf(qy[i] * height_scale), 0.0f), (float)dh);
+    }
   }
-  out.score = score;
-  out.valid = 1;
+  return true;
+}
+
+// one warp per candidate: lane 0 walks the strictly sequential pieces, the lanes share box scoring, the hull sort
+// and the min-area-rectangle search
+constexpr int GEO_WARPS = 2;
+__global__ void __launch_bounds__(GEO_WARPS * 32) db_geometry_kernel(
+    const float* __restrict__ pred, int H, int W, const ContourRec* __restrict__ recs, const int* __restrict__ order,
+    const int* __restrict__ first, int B, int max_cand, const short2* __restrict__ pool, short2* __restrict__ scratch,
+    const int32_t* __restrict__ dest_wh, float box_thresh, float unclip_ratio, float min_size,
+    Cand* __restrict__ cands, int* __restrict__ err) {
+  __shared__ float s_part[GEO_WARPS][256];
+  __shared__ float s_ws[GEO_WARPS][6 * UNCLIP_CAP];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = blockIdx.x * GEO_WARPS + wib;
+  const int b = blockIdx.y;
+  const int cnt = min(first[b + 1] - first[b], max_cand);
+  if (rank >= cnt) return;  // warp-uniform
+  Cand& out = cands[(size_t)b * max_cand + rank];
+  float* ws = s_ws[wib];
+  float bx[4] = {0.f, 0.f, 0.f, 0.f}, by[4] = {0.f, 0.f, 0.f, 0.f}, min_side = 0.0f;
+  int ok = 0;
+  if (lane == 0) {
+    out.valid = 0;
+    const ContourRec rec = recs[order[first[b] + rank]];
+    ok = cand_mini_box(rec, pool, scratch, ws, ws + UNCLIP_CAP, bx, by, &min_side, err) ? 1 : 0;
+    if (ok && min_side < min_size) ok = 0;
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return;
+  for (int i = 0; i < 4; ++i) {
+    bx[i] = __shfl_sync(0xffffffffu, bx[i], 0);
+    by[i] = __shfl_sync(0xffffffffu, by[i], 0);
+  }
+  const float score = box_score_fast_warp(pred + (size_t)b * H * W, W, H, bx, by, s_part[wib], lane);
+  if (score < box_thresh) return;  // uniform: every lane holds the same score
+  const unsigned dw = (unsigned)dest_wh[2 * b], dh = (unsigned)dest_wh[2 * b + 1];
+  if (!cand_unclip_box_warp(bx, by, unclip_ratio, min_size, ws, dw, dh, W, H, out.box, err, lane)) return;
+  if (lane == 0) {
+    out.score = score;
+    out.valid = 1;
+  }
 }
 
 __global__ void db_compact_kernel(const Cand* __restrict__ cands, const int* __restrict__ first, int B, int max_cand,
@@ -812,7 +1036,7 @@ DbPostStatus db_postprocess_device(oar_ctx* ctx, const float* pred, int B, int H
   int nb = cdiv(total, 256);
   {
     Launch l(ctx, "db_threshold_init", (double)total, 9.0 * total);
-    db_init_kernel<<<nb, 256, 0, st>>>(pred, cfg.thresh, state, lab, total, HW);
+    db_init_kernel<<<nb, 256, 0, st>>>(pred, cfg.thresh, state, lab, total, HW, W);
   }
   {
     Launch l(ctx, "db_ccl_merge", 0, 5.0 * total);
@@ -859,7 +1083,7 @@ DbPostStatus db_postprocess_device(oar_ctx* ctx, const float* pred, int B, int H
   Cand* cands = A.get<Cand>((size_t)B * cfg.max_candidates);
   {
     Launch l(ctx, "db_box_geometry");
-    db_geometry_kernel<<<dim3(cdiv(cfg.max_candidates, 32), B), 32, 0, st>>>(
+    db_geometry_kernel<<<dim3(cdiv(cfg.max_candidates, GEO_WARPS), B), GEO_WARPS * 32, 0, st>>>(
         pred, H, W, recs, vals2, first, B, cfg.max_candidates, pool, scratch, dest_wh, cfg.box_thresh,
         cfg.unclip_ratio, cfg.min_size, cands, err);
   }
