@@ -1,0 +1,234 @@
+// oar_ocr.hpp -- header-only C++ mirror of the reference's Rust API for the det+rec path, over the C ABI
+// (include/oar_b200.h).  Same names, argument meaning and error behaviour as the crate:
+//   OAROCRBuilder / OAROCR::predict       src/oarocr/ocr.rs:66-417, 518-659
+//   TextDetectionPredictor                oar-ocr-core/src/predictors/text_detection.rs:23-112
+//   TextRecognitionPredictor              oar-ocr-core/src/predictors/text_recognition.rs:19-110
+//   OCRError                              oar-ocr-core/src/core/errors/types.rs:110-214
+// Errors are thrown as oar::OCRError (Rust returns Result<_, OCRError>).  No CPU fallback exists.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "oar_b200.h"
+
+namespace oar {
+
+struct OCRError : std::runtime_error {
+  std::string kind;  // variant name: InvalidInput, ConfigError, Inference, ModelLoad
+  int code;
+  OCRError(std::string k, const std::string& msg, int c = 0)
+      : std::runtime_error(k + ": " + msg), kind(std::move(k)), code(c) {}
+};
+
+inline void check(int32_t rc) {
+  if (rc == OAR_OK) return;
+  const char* kind = rc == OAR_E_INVALID ? "InvalidInput" : rc == OAR_E_MODEL ? "ModelLoad"
+                     : rc == OAR_E_UNSUPPORTED ? "ConfigError" : "Inference";
+  throw OCRError(kind, oar_last_error(), rc);
+}
+
+struct RgbImage {  // image::RgbImage: u8 HWC, row-major
+  const uint8_t* data = nullptr;
+  int32_t height = 0, width = 0;
+};
+struct Point { float x, y; };
+struct BoundingBox { std::vector<Point> points; };
+struct Detection { BoundingBox bbox; float score; };
+struct TextDetectionResult { std::vector<std::vector<Detection>> detections; };
+struct TextRecognitionResult {
+  std::vector<std::vector<int32_t>> label_indices;  // text = character[index] (decode.rs:392-423)
+  std::vector<float> scores;
+  std::vector<std::vector<int32_t>> char_col_indices;
+  std::vector<size_t> sequence_lengths;
+};
+struct TextRegion {
+  BoundingBox bounding_box;
+  std::vector<int32_t> label_indices;
+  float confidence = 0.0f;
+  int32_t detection_index = 0;
+};
+struct OAROCRResult { size_t index = 0; std::vector<TextRegion> text_regions; };
+
+class Context {
+ public:
+  explicit Context(int32_t device_id = 0) { check(oar_ctx_create(device_id, &ctx_)); }
+  ~Context() { oar_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  oar_ctx* raw() const { return ctx_; }
+ private:
+  oar_ctx* ctx_ = nullptr;
+};
+
+class Model {  // stands where OrtInfer stands in the reference
+ public:
+  Model(Context& ctx, const void* blob, size_t len) { check(oar_model_load_blob(ctx.raw(), blob, len, &m_)); }
+  ~Model() { oar_model_destroy(m_); }
+  Model(const Model&) = delete;
+  Model& operator=(const Model&) = delete;
+  oar_model* raw() const { return m_; }
+ private:
+  oar_model* m_ = nullptr;
+};
+
+namespace detail {
+inline void image_table(const std::vector<RgbImage>& images, const char* what, std::vector<const uint8_t*>& ptrs,
+                        std::vector<int32_t>& hs, std::vector<int32_t>& ws) {
+  if (images.empty())  // OCRError::validation_error(.., "non-empty slice", "empty slice"), ocr.rs:525-532
+    throw OCRError("InvalidInput", std::string(what) + ": images: expected non-empty slice, got empty slice",
+                   OAR_E_INVALID);
+  for (const auto& im : images) {
+    ptrs.push_back(im.data);
+    hs.push_back(im.height);
+    ws.push_back(im.width);
+  }
+}
+}  // namespace detail
+
+struct TextDetectionConfig {  // tasks/text_detection.rs:33-53; predictor defaults text_detection.rs:56-68
+  float score_threshold = 0.3f, box_threshold = 0.6f, unclip_ratio = 1.5f;
+  int32_t max_candidates = 1000, limit_side_len = 960, limit_type = 0, max_side_len = 4000;
+  oar_det_config to_abi() const {
+    oar_det_config c;
+    oar_det_config_default(&c);
+    c.thresh = score_threshold, c.box_thresh = box_threshold, c.unclip_ratio = unclip_ratio;
+    c.max_candidates = max_candidates, c.limit_side_len = limit_side_len, c.limit_type = limit_type;
+    c.max_side_limit = max_side_len;
+    return c;
+  }
+};
+
+class TextDetectionPredictor {
+ public:
+  TextDetectionPredictor(Model& model, TextDetectionConfig cfg = {}) : model_(model), cfg_(cfg) {}
+  // unsorted, discovery order, as TextDetectionAdapter::execute returns them
+  TextDetectionResult predict(const std::vector<RgbImage>& images) const {
+    std::vector<const uint8_t*> ptrs;
+    std::vector<int32_t> hs, ws;
+    detail::image_table(images, "TextDetection", ptrs, hs, ws);
+    const size_t n = images.size(), mc = (size_t)cfg_.max_candidates;
+    oar_det_config c = cfg_.to_abi();
+    std::vector<float> boxes(n * mc * 8), scores(n * mc);
+    std::vector<int32_t> counts(n);
+    check(oar_det_run(model_.raw(), ptrs.data(), hs.data(), ws.data(), (int32_t)n, &c, boxes.data(), scores.data(),
+                      counts.data()));
+    TextDetectionResult res;
+    res.detections.resize(n);
+    for (size_t i = 0; i < n; ++i)
+      for (int32_t k = 0; k < counts[i]; ++k) {
+        const float* p = &boxes[(i * mc + k) * 8];
+        Detection d;
+        for (int j = 0; j < 4; ++j) d.bbox.points.push_back(Point{p[2 * j], p[2 * j + 1]});
+        d.score = scores[i * mc + k];
+        if (!(d.score >= 0.0f && d.score <= 1.0f))  // validate_output, tasks/text_detection.rs:129-141
+          throw OCRError("InvalidInput", "detection score outside [0,1]");
+        res.detections[i].push_back(std::move(d));
+      }
+    return res;
+  }
+ private:
+  Model& model_;
+  TextDetectionConfig cfg_;
+};
+
+class TextRecognitionPredictor {
+ public:
+  TextRecognitionPredictor(Model& model, int32_t n_chars, float score_threshold = 0.0f)
+      : model_(model), n_chars_(n_chars), thresh_(score_threshold) {}
+  // the whole input is ONE batch (predictors/text_recognition.rs:38-45)
+  TextRecognitionResult predict(const std::vector<RgbImage>& images) const {
+    std::vector<const uint8_t*> ptrs;
+    std::vector<int32_t> hs, ws;
+    detail::image_table(images, "TextRecognition", ptrs, hs, ws);
+    const size_t n = images.size();
+    const int32_t t_cap = 3200 / 8 + 2;
+    std::vector<int32_t> labels(n * t_cap), cols(n * t_cap), lens(n);
+    std::vector<float> scores(n);
+    int32_t t_out = 0;
+    check(oar_rec_run(model_.raw(), ptrs.data(), hs.data(), ws.data(), (int32_t)n, n_chars_, labels.data(), cols.data(),
+                      lens.data(), scores.data(), t_cap, &t_out));
+    TextRecognitionResult r;
+    for (size_t i = 0; i < n; ++i) {
+      const bool keep = scores[i] >= thresh_;  // text_recognition_adapter.rs:88-102
+      r.label_indices.emplace_back(labels.begin() + i * t_cap, labels.begin() + i * t_cap + (keep ? lens[i] : 0));
+      r.char_col_indices.emplace_back(cols.begin() + i * t_cap, cols.begin() + i * t_cap + lens[i]);
+      r.scores.push_back(scores[i]);
+      r.sequence_lengths.push_back((size_t)t_out);
+    }
+    return r;
+  }
+ private:
+  Model& model_;
+  int32_t n_chars_;
+  float thresh_;
+};
+
+class OAROCR {
+ public:
+  OAROCR(Model& det, Model& rec, oar_pipeline_config cfg) : det_(det), rec_(rec), cfg_(cfg) {}
+  std::vector<OAROCRResult> predict(const std::vector<RgbImage>& images) const {
+    std::vector<const uint8_t*> ptrs;
+    std::vector<int32_t> hs, ws;
+    detail::image_table(images, "OCR Pipeline", ptrs, hs, ws);
+    const size_t n = images.size();
+    const int32_t cap_r = (int32_t)n * cfg_.det.max_candidates, cap_l = cap_r * 64;
+    std::vector<int32_t> region_off(n + 1), det_index(cap_r), label_off(cap_r + 1), labels(cap_l);
+    std::vector<float> boxes((size_t)cap_r * 8), scores(cap_r);
+    oar_ocr_result out{};
+    out.cap_regions = cap_r, out.cap_labels = cap_l;
+    out.region_off = region_off.data(), out.boxes = boxes.data(), out.scores = scores.data();
+    out.det_index = det_index.data(), out.label_off = label_off.data(), out.labels = labels.data();
+    check(oar_pipeline_run(det_.raw(), rec_.raw(), ptrs.data(), hs.data(), ws.data(), (int32_t)n, 0, &cfg_, &out));
+    std::vector<OAROCRResult> res(n);
+    for (size_t i = 0; i < n; ++i) {
+      res[i].index = i;
+      for (int32_t r = region_off[i]; r < region_off[i + 1]; ++r) {
+        TextRegion t;
+        for (int j = 0; j < 4; ++j) t.bounding_box.points.push_back(Point{boxes[r * 8 + 2 * j], boxes[r * 8 + 2 * j + 1]});
+        t.label_indices.assign(labels.begin() + label_off[r], labels.begin() + label_off[r + 1]);
+        t.confidence = scores[r];
+        t.detection_index = det_index[r];
+        res[i].text_regions.push_back(std::move(t));
+      }
+    }
+    return res;
+  }
+ private:
+  Model& det_;
+  Model& rec_;
+  oar_pipeline_config cfg_;
+};
+
+class OAROCRBuilder {
+ public:
+  static constexpr size_t MAX_BATCH_SIZE = 4096;  // ocr.rs:93
+  OAROCRBuilder(Model& det, Model& rec, int32_t n_chars) : det_(det), rec_(rec) {
+    oar_pipeline_config_default(&cfg_);  // thresh .3 / box .6 / unclip 2.0 / 960 Max 4000 (ocr.rs:351-364), 8 / 64
+    cfg_.n_chars = n_chars;
+  }
+  static void validate_batch_size(const char* name, size_t size) {  // ocr.rs:419-430
+    if (size == 0 || size > MAX_BATCH_SIZE)
+      throw OCRError("ConfigError", std::string(name) + " must be in 1..=" + std::to_string(MAX_BATCH_SIZE) + ", got " +
+                                        std::to_string(size));
+  }
+  OAROCRBuilder& image_batch_size(size_t s) { image_bs_ = s, has_image_bs_ = true; return *this; }
+  OAROCRBuilder& region_batch_size(size_t s) { region_bs_ = s, has_region_bs_ = true; return *this; }
+  OAROCRBuilder& text_detection_config(const TextDetectionConfig& c) { cfg_.det = c.to_abi(); return *this; }
+  OAROCRBuilder& rec_score_threshold(float t) { cfg_.rec_score_thresh = t; return *this; }
+  OAROCR build() {
+    if (has_image_bs_) validate_batch_size("image_batch_size", image_bs_), cfg_.image_batch_size = (int32_t)image_bs_;
+    if (has_region_bs_) validate_batch_size("region_batch_size", region_bs_), cfg_.region_batch_size = (int32_t)region_bs_;
+    return OAROCR(det_, rec_, cfg_);
+  }
+ private:
+  Model& det_;
+  Model& rec_;
+  oar_pipeline_config cfg_;
+  size_t image_bs_ = 0, region_bs_ = 0;
+  bool has_image_bs_ = false, has_region_bs_ = false;
+};
+
+}  // namespace oar

@@ -1,0 +1,68 @@
+// Exercises include/oar_ocr.hpp (the C++ mirror of the Rust API) against liboar_b200.so.
+// Without a GPU: checks the error behaviour the reference pins (ocr.rs:1168-1195, no CPU fallback).
+// With a GPU (argv[1] = det blob, argv[2] = rec blob): runs predict() on a blank page and one synthetic stripe.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+
+#include "oar_ocr.hpp"
+
+static std::vector<char> slurp(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+int main(int argc, char** argv) {
+  int failures = 0;
+  auto expect = [&](bool ok, const char* what) {
+    if (!ok) ++failures, std::printf("FAIL %s\n", what);
+  };
+  // batch-size validation (ocr.rs:1168-1195)
+  try {
+    oar::OAROCRBuilder::validate_batch_size("image_batch_size", 1);
+    oar::OAROCRBuilder::validate_batch_size("region_batch_size", oar::OAROCRBuilder::MAX_BATCH_SIZE);
+  } catch (...) {
+    expect(false, "bounds accepted");
+  }
+  try {
+    oar::OAROCRBuilder::validate_batch_size("image_batch_size", 0);
+    expect(false, "zero rejected");
+  } catch (const oar::OCRError& e) {
+    expect(std::strstr(e.what(), "image_batch_size") && std::strstr(e.what(), "1..=4096"), "zero message");
+  }
+  oar_pipeline_config pc;
+  oar_pipeline_config_default(&pc);
+  expect(pc.image_batch_size == 8 && pc.region_batch_size == 64 && pc.det.unclip_ratio == 2.0f, "defaults");
+
+  bool have_gpu = true;
+  try {
+    oar::Context probe(0);
+  } catch (const oar::OCRError& e) {
+    have_gpu = false;
+    expect(e.code == OAR_E_NO_DEVICE && std::strstr(e.what(), "no CPU fallback"), "no-device error");
+  }
+  if (have_gpu && argc >= 3) {
+    oar::Context ctx(0);
+    auto db = slurp(argv[1]), rb = slurp(argv[2]);
+    oar::Model det(ctx, db.data(), db.size()), rec(ctx, rb.data(), rb.size());
+    oar::OAROCR ocr = oar::OAROCRBuilder(det, rec, 18385).image_batch_size(2).region_batch_size(8).build();
+    try {
+      ocr.predict({});
+      expect(false, "empty input rejected");
+    } catch (const oar::OCRError& e) {
+      expect(std::strstr(e.what(), "non-empty slice") != nullptr, "empty input message");
+    }
+    std::vector<uint8_t> page(320 * 320 * 3, 240);
+    for (int y = 100; y < 130; ++y)
+      for (int x = 40; x < 280; ++x)
+        for (int c = 0; c < 3; ++c) page[(y * 320 + x) * 3 + c] = (uint8_t)(30 + 40 * ((x / 4) & 1));
+    auto res = ocr.predict({oar::RgbImage{page.data(), 320, 320}});
+    expect(res.size() == 1 && res[0].text_regions.size() == 1, "one region on the striped page");
+    auto dres = oar::TextDetectionPredictor(det).predict({oar::RgbImage{page.data(), 320, 320}});
+    expect(dres.detections.size() == 1 && dres.detections[0].size() == 1, "detector predictor");
+    std::printf("gpu path ok: %zu regions\n", res[0].text_regions.size());
+  }
+  std::printf(failures ? "FAILED %d\n" : "ok\n", failures);
+  return failures ? 1 : 0;
+}
