@@ -31,7 +31,8 @@
 namespace oar {
 
 constexpr int TC_BM = 128;        // UMMA M
-// k elements per shared-memory stage: 64 (8 16-byte chunks) when the GEMM has K > 32, else 32 (4 chunks)
+// k elements per shared-memory stage: 64 (8 16-byte chunks, one stage) when 32 < K <= 64, else 32 (4 chunks, two
+// stages): small stages keep 4+ CTAs resident per SM, which is what hides the gather latency
 constexpr int TC_STAGES = 2;
 constexpr int TC_MAX_BN = 256;
 
@@ -215,13 +216,15 @@ __device__ __forceinline__ void load_a(const ConvParams& p, int kb, int half, bo
   }
 }
 
+// Activations of the tensor-core epilogue.  Division-free forms (reciprocal multiply, __fdividef): within 2 ulp of
+// the IEEE forms the SIMT engine uses, far inside the 1e-3 parity tolerance, and ~10 instructions cheaper per value.
 template <int ACT>
 __device__ __forceinline__ float act_t(float v) {
   if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
-  if (ACT == ACT_HSWISH) return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f;
-  if (ACT == ACT_SWISH) return v / (1.0f + expf(-v));
-  if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  if (ACT == ACT_HSIGMOID) return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
+  if (ACT == ACT_HSWISH) return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+  if (ACT == ACT_SWISH) return __fdividef(v, 1.0f + __expf(-v));
+  if (ACT == ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  if (ACT == ACT_HSIGMOID) return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
   return v;
 }
 
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
     const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0);
     float* orow = p.out + (size_t)m * p.out_ld + p.out_c_off + n_base;
     const float ps = p.post_scale, pb = p.post_bias;
+    const bool affine = ps != 1.0f || pb != 0.0f;  // the Act's learnable affine; identity in deploy graphs
     for (int c0 = half * 16; c0 < BN; c0 += 32) {
       if (n_base + c0 >= p.N) break;
       float v[16];
@@ -381,10 +385,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
                                          : make_float4(__ldg(p.bias + n_base + c0 + i), __ldg(p.bias + n_base + c0 + i + 1),
                                                        __ldg(p.bias + n_base + c0 + i + 2),
                                                        __ldg(p.bias + n_base + c0 + i + 3));
-          v[i] = act_t<ACT>(v[i] + b.x) * ps + pb;
-          v[i + 1] = act_t<ACT>(v[i + 1] + b.y) * ps + pb;
-          v[i + 2] = act_t<ACT>(v[i + 2] + b.z) * ps + pb;
-          v[i + 3] = act_t<ACT>(v[i + 3] + b.w) * ps + pb;
+          v[i] = act_t<ACT>(v[i] + b.x);
+          v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
+          v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
+          v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
+        }
+        if (affine) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] * ps + pb;
         }
         if (vec_ok) {
 #pragma unroll
@@ -468,7 +476,7 @@ static TcWeights pack_weights(const float* w, int N, int K) {
   t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
   t.BN = std::max(16, (per + 15) / 16 * 16);
-  t.KC = K > 32 ? 8 : 4;
+  t.KC = (K > 32 && K <= 64) ? 8 : 4;  // 64-wide single stage for 32 < K <= 64; otherwise 32-wide double-buffered
   const int TC_KC = t.KC, TC_BK = t.KC * 8;
   t.nkb = (K + TC_BK - 1) / TC_BK;
   size_t halfs = (size_t)t.n_tiles * t.nkb * 2 * TC_KC * t.BN * 8;
