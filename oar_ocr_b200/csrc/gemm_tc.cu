@@ -12,16 +12,18 @@
 // whole contraction still runs on the tensor pipe.  These layers are HBM-bound (mobile channel widths), so the 3x
 // MMA count is free; activations stay fp32 in HBM exactly as the reference feeds them.
 //
-// Kernel shape (one CTA = one 128-row x BN-column output tile, 128 threads):
-//   A (activations): thread r gathers its pixel row's k-chunk from the fp32 NHWC tensor (im2col on the fly),
-//       splits to hi/lo fp16 and stores 16-byte core-matrix rows into shared memory in the canonical K-major,
-//       no-swizzle UMMA layout [k-chunk][row][8 halfs]  (LBO = 128 rows * 16 B, SBO = 128 B);
+// Kernel shape (one CTA = one 128-row x BN-column output tile, 256 threads):
+//   A (activations): threads gather (pixel row, 16-byte k-chunk) pairs from the fp32 NHWC tensor (im2col on the
+//       fly, lanes of a warp reading contiguous bytes of the same pixel), split to hi/lo fp16 and store 16-byte
+//       core-matrix rows into shared memory in the canonical K-major, no-swizzle UMMA layout
+//       [k-chunk][row][8 halfs]  (LBO = 128 rows * 16 B + bank padding, SBO = 128 B);
 //   B (weights): pre-split and pre-packed on the host at model load in exactly the shared-memory layout, so a stage
 //       is one linear 16-byte-vector copy;
 //   two shared-memory stages; tcgen05.commit -> mbarrier releases a stage when its MMAs have read it;
 //   D: fp32 accumulators in TMEM (128 lanes x BN columns); epilogue = tcgen05.ld 32x32b, + bias, activation,
-//       post-affine, then NHWC stores (conv), 2x2 scatter (transposed conv) or an online softmax/arg-max reduction
-//       (CTC head: the [B,T,V] logits never reach HBM).
+//       post-affine, then NHWC stores staged through shared memory so every store is a whole 128-byte row segment
+//       (conv), 2x2 scatter (transposed conv) or an online softmax/arg-max reduction (CTC head: the [B,T,V] logits
+//       never reach HBM).
 #include <cuda_fp16.h>
 
 #include <map>
@@ -150,6 +152,7 @@ struct TcParams {
   ConvParams c;
   const uint4* wpk;
   int BN, nkb, n_tiles, tmem_cols, stages;
+  uint32_t ctrl_off;  // byte offset of the mbarriers / TMEM slot behind the stages (and the epilogue staging tile)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
@@ -166,30 +169,50 @@ constexpr int AM_SCALAR = 2;     // anything else (stem Cin = 3, odd channel cou
 // epilogues: EPI = mode * 8 + activation (mode 0 conv, 1 transposed conv), EPI_CTC = fused CTC reduction
 constexpr int EPI_CTC = 16;
 
-// One thread's share of a k-block of A: its pixel row's chunks kc = half, half + 2, ... as raw fp32 in registers.
-// Issued one k-block ahead so the HBM/L2 latency overlaps the previous block's split, barrier and MMAs.
+// Per-KC geometry of the A operand.  256 threads cover the 128 x KC (row, 16-byte chunk) pairs of a k-block in
+// KC/2 passes: chunk = tid % KC, row = tid / KC + pass * (256 / KC), so KC consecutive lanes read one pixel's
+// contiguous KC*32 bytes (4 or 8 rows per warp instruction instead of 32 scattered rows).  The chunk stride in shared
+// memory (the descriptor's leading byte offset) is padded by 128/KC bytes so the 16-byte stores of a quarter warp
+// (which now differ in chunk as well as row) land in distinct bank groups.
+template <int KC>
+struct AGeo {
+  static constexpr int NP = KC / 2;
+  static constexpr int ROWS_PER_PASS = 256 / KC;
+  static constexpr uint32_t LBO = TC_BM * 16 + 128 / KC;
+  static constexpr uint32_t PART = KC * LBO;  // bytes of one A part (hi or lo) per stage
+};
+
+// One thread's share of a k-block of A as raw fp32 in registers, issued one k-block ahead so the HBM/L2 latency
+// overlaps the previous block's split, barrier and MMAs.
 template <int KC>
 struct ARegs {
-  float4 v[KC];  // KC / 2 chunks x 2 float4
+  float4 v[KC];  // NP pairs x 2 float4
+};
+
+struct ARow {  // per (thread, pass): the pixel this thread gathers for
+  const float* ptr;  // pointwise: in + m * Cin
+  int b, ho, wo;
+  bool ok;
 };
 
 template <int KC, int A_MODE>
-__device__ __forceinline__ void load_a(const ConvParams& p, int kb, int half, bool row_ok, const float* arow, int ab,
-                                       int aho, int awo, ARegs<KC>& r) {
+__device__ __forceinline__ void load_a(const ConvParams& p, int kb, int chunk, const ARow (&rows)[KC / 2],
+                                       ARegs<KC>& r) {
+  const int k0 = kb * (KC * 8) + chunk * 8;
 #pragma unroll
   for (int j = 0; j < KC / 2; ++j) {
-    const int k0 = kb * (KC * 8) + (2 * j + half) * 8;
+    const ARow& rw = rows[j];
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-    if (row_ok && k0 < p.K) {
+    if (rw.ok && k0 < p.K) {
       if (A_MODE == AM_POINTWISE) {
-        u = __ldg(reinterpret_cast<const float4*>(arow + k0));
-        v = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
+        u = __ldg(reinterpret_cast<const float4*>(rw.ptr + k0));
+        v = __ldg(reinterpret_cast<const float4*>(rw.ptr + k0 + 4));
       } else if (A_MODE == AM_TAPS) {
         int tap = k0 / p.Cin, ci = k0 - tap * p.Cin;
         int ky = tap / p.kw, kx = tap - ky * p.kw;
-        int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
+        int ih = rw.ho * p.sh - p.ph + ky, iw = rw.wo * p.sw - p.pw + kx;
         if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-          const float* src = p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci;
+          const float* src = p.in + (((size_t)rw.b * p.H + ih) * p.W + iw) * p.Cin + ci;
           u = __ldg(reinterpret_cast<const float4*>(src));
           v = __ldg(reinterpret_cast<const float4*>(src + 4));
         }
@@ -202,9 +225,9 @@ __device__ __forceinline__ void load_a(const ConvParams& p, int kb, int half, bo
           if (k < p.K) {
             int tap = k / p.Cin, ci = k - tap * p.Cin;
             int ky = tap / p.kw, kx = tap - ky * p.kw;
-            int ih = aho * p.sh - p.ph + ky, iw = awo * p.sw - p.pw + kx;
+            int ih = rw.ho * p.sh - p.ph + ky, iw = rw.wo * p.sw - p.pw + kx;
             if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-              x[i] = __ldg(p.in + (((size_t)ab * p.H + ih) * p.W + iw) * p.Cin + ci);
+              x[i] = __ldg(p.in + (((size_t)rw.b * p.H + ih) * p.W + iw) * p.Cin + ci);
           }
         }
         u = make_float4(x[0], x[1], x[2], x[3]);
@@ -228,40 +251,50 @@ __device__ __forceinline__ float act_t(float v) {
   return v;
 }
 
+constexpr int EP_LD = 36;                          // floats per row of the epilogue staging tile (32 + pad)
+constexpr int EP_BYTES = TC_BM * EP_LD * 4;        // 18432
+
 template <int KC, int A_MODE, int EPI>
 __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int BK = KC * 8;
+  using G = AGeo<KC>;
   const ConvParams& p = P.c;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & (TC_BM - 1), half = tid >> 7;
   const int BN = P.BN;
-  const uint32_t a_part = KC * TC_BM * 16;  // bytes of one A part (hi or lo) per stage
+  constexpr uint32_t a_part = G::PART;
   const uint32_t b_part = KC * BN * 16;
   const uint32_t stage_bytes = 2 * a_part + 2 * b_part;
   const int smask = P.stages - 1;
-  uint8_t* ctrl = smem + P.stages * stage_bytes;
+  uint8_t* ctrl = smem + P.ctrl_off;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(ctrl);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * TC_STAGES);
+  const int m0 = blockIdx.x * TC_BM;
 
-  // this thread's output row (pixel)
-  const int m = blockIdx.x * TC_BM + row;
-  const bool row_ok = m < p.M;
-  int ab = 0, aho = 0, awo = 0;
-  if (A_MODE != AM_POINTWISE && row_ok) {
-    ab = m / (p.Ho * p.Wo);
-    int r = m - ab * p.Ho * p.Wo;
-    aho = r / p.Wo;
-    awo = r - aho * p.Wo;
+  // the pixels this thread gathers A for
+  const int chunk = tid % KC;
+  ARow rows[G::NP];
+#pragma unroll
+  for (int j = 0; j < G::NP; ++j) {
+    const int m = m0 + tid / KC + j * G::ROWS_PER_PASS;
+    rows[j].ok = m < p.M;
+    rows[j].ptr = p.in + (size_t)m * p.Cin;
+    rows[j].b = rows[j].ho = rows[j].wo = 0;
+    if (A_MODE != AM_POINTWISE && rows[j].ok) {
+      int b = m / (p.Ho * p.Wo);
+      int r = m - b * p.Ho * p.Wo;
+      rows[j].b = b;
+      rows[j].ho = r / p.Wo;
+      rows[j].wo = r - rows[j].ho * p.Wo;
+    }
   }
-  const float* arow = p.in + (size_t)m * p.Cin;  // pointwise only
   const int nt = blockIdx.y;
   const uint4* wtile = P.wpk + (size_t)nt * P.nkb * (2 * KC * BN);
   const int nvec_b = 2 * KC * BN;  // 16-byte vectors of one B stage (hi then lo)
 
   // first k-block: A into registers, B straight into stage 0 (both in flight during the set-up below)
   ARegs<KC> pre;
-  load_a<KC, A_MODE>(p, 0, half, row_ok, arow, ab, aho, awo, pre);
+  load_a<KC, A_MODE>(p, 0, chunk, rows, pre);
   {
     const uint32_t b_dst = smem_u32(smem + 2 * a_part);
     for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, wtile + i);
@@ -279,31 +312,31 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   const uint32_t tmem_base = *tmem_slot;
   // instruction descriptor: D fp32, A/B fp16, both K-major, N = BN, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint32_t a_store_off = (uint32_t)chunk * G::LBO + (uint32_t)(tid / KC) * 16;
 
   for (int kb = 0; kb < P.nkb; ++kb) {
     const int s = kb & smask;
     uint8_t* st = smem + s * stage_bytes;
     // stage s is free: its previous reader MMA(kb-2) was waited for at the end of iteration kb-1
-    uint4* a_hi = reinterpret_cast<uint4*>(st);
-    uint4* a_lo = reinterpret_cast<uint4*>(st + a_part);
 #pragma unroll
-    for (int j = 0; j < KC / 2; ++j) {
+    for (int j = 0; j < G::NP; ++j) {
       float x[8] = {pre.v[2 * j].x,     pre.v[2 * j].y,     pre.v[2 * j].z,     pre.v[2 * j].w,
                     pre.v[2 * j + 1].x, pre.v[2 * j + 1].y, pre.v[2 * j + 1].z, pre.v[2 * j + 1].w};
       uint4 hi, lo;
       split8(x, hi, lo);
-      a_hi[(2 * j + half) * TC_BM + row] = hi;
-      a_lo[(2 * j + half) * TC_BM + row] = lo;
+      const uint32_t off = a_store_off + (uint32_t)(j * G::ROWS_PER_PASS) * 16;
+      *reinterpret_cast<uint4*>(st + off) = hi;
+      *reinterpret_cast<uint4*>(st + a_part + off) = lo;
     }
     cp_async_wait_all();  // this thread's share of B(kb)
-    if (kb + 1 < P.nkb) load_a<KC, A_MODE>(p, kb + 1, half, row_ok, arow, ab, aho, awo, pre);
+    if (kb + 1 < P.nkb) load_a<KC, A_MODE>(p, kb + 1, chunk, rows, pre);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a_hi_s = smem_u32(st), a_lo_s = a_hi_s + a_part;
       const uint32_t b_hi_s = a_hi_s + 2 * a_part, b_lo_s = b_hi_s + b_part;
-      const uint32_t a_lbo = TC_BM * 16, b_lbo = (uint32_t)BN * 16;
+      const uint32_t a_lbo = G::LBO, b_lbo = (uint32_t)BN * 16;
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {
         uint64_t ah = make_desc(a_hi_s + 2 * j * a_lbo, a_lbo, 128);
@@ -331,8 +364,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
     tc_fence_after();
   }
 
-  // ---- epilogue: thread = (row, column half); 16 columns at a time out of TMEM.  A warp may only touch the TMEM
-  // lanes 32*(warp%4)..+31, which is exactly `row` for both halves.
+  // ---- epilogue: TMEM -> registers with thread = (row, column half); a warp may only touch TMEM lanes
+  // 32*(warp%4)..+31, which is exactly `row` for both halves.
+  const int row = tid & (TC_BM - 1), half = tid >> 7;
+  const int m = m0 + row;
+  const bool row_ok = m < p.M;
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const int n_base = nt * BN;
   if (EPI == EPI_CTC) {
@@ -367,48 +403,77 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       p.part_sum[o] = sum;
     }
   } else if (EPI < 8) {
+    // conv: bias + activation in registers, then a 128 x 32 staging tile in (now idle) shared memory so that the
+    // global stores are whole 128-byte row segments (8 lanes per row) instead of 32 scattered 16-byte pieces
     constexpr int ACT = EPI & 7;
-    const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0);
-    float* orow = p.out + (size_t)m * p.out_ld + p.out_c_off + n_base;
+    float* ep = reinterpret_cast<float*>(smem);
+    const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0) &&
+                        ((((uintptr_t)p.out) & 15) == 0);
     const float ps = p.post_scale, pb = p.post_bias;
     const bool affine = ps != 1.0f || pb != 0.0f;  // the Act's learnable affine; identity in deploy graphs
-    for (int c0 = half * 16; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n_base + c0 >= p.N) break;
-      float v[16];
-      tmem_ld16(lane_base + c0, v);  // warp-collective: every lane takes part, stores are predicated below
-      if (!row_ok) continue;
-      if (n_base + c0 + 16 <= p.N) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_base + c0);  // weight arrays are 16-byte aligned
+      const int cols_here = min(min(32, BN - c0), p.N - n_base - c0);  // the tile ends at BN, the tensor at N
+      const int cc = c0 + 16 * half;
+      if (cc < BN && n_base + cc < p.N) {  // warp-uniform
+        float v[16];
+        tmem_ld16(lane_base + cc, v);
+        if (n_base + cc + 16 <= p.N) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 b = ((n_base & 3) == 0) ? __ldg(b4 + (i >> 2))
-                                         : make_float4(__ldg(p.bias + n_base + c0 + i), __ldg(p.bias + n_base + c0 + i + 1),
-                                                       __ldg(p.bias + n_base + c0 + i + 2),
-                                                       __ldg(p.bias + n_base + c0 + i + 3));
-          v[i] = act_t<ACT>(v[i] + b.x);
-          v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
-          v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
-          v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
+          for (int i = 0; i < 16; i += 4) {
+            float4 b;
+            if ((n_base & 3) == 0)
+              b = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + cc + i));  // weight arrays are 16-B aligned
+            else
+              b = make_float4(__ldg(p.bias + n_base + cc + i), __ldg(p.bias + n_base + cc + i + 1),
+                              __ldg(p.bias + n_base + cc + i + 2), __ldg(p.bias + n_base + cc + i + 3));
+            v[i] = act_t<ACT>(v[i] + b.x);
+            v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
+            v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
+            v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int n = n_base + cc + i;
+            v[i] = n < p.N ? act_t<ACT>(v[i] + __ldg(p.bias + n)) : 0.0f;
+          }
         }
         if (affine) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = v[i] * ps + pb;
         }
-        if (vec_ok) {
+        float4* dst = reinterpret_cast<float4*>(ep + row * EP_LD + 16 * half);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      __syncthreads();
+      float* obase = p.out + (size_t)m0 * p.out_ld + p.out_c_off + n_base + c0;
+      if (vec_ok && (cols_here & 3) == 0) {
+        const int cpr = cols_here >> 2;  // float4 per row
+        if (cpr == 8) {
+#pragma unroll
+          for (int idx = tid; idx < TC_BM * 8; idx += TC_THREADS) {
+            const int r = idx >> 3, c4 = idx & 7;
+            if (m0 + r < p.M)
+              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
+                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
+          }
         } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) orow[c0 + i] = v[i];
+          for (int idx = tid; idx < TC_BM * cpr; idx += TC_THREADS) {
+            const int r = idx / cpr, c4 = idx - r * cpr;
+            if (m0 + r < p.M)
+              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
+                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
+          }
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int n = n_base + c0 + i;
-          if (n < p.N) orow[c0 + i] = act_t<ACT>(v[i] + __ldg(p.bias + n)) * ps + pb;
+        for (int idx = tid; idx < TC_BM * cols_here; idx += TC_THREADS) {
+          const int r = idx / cols_here, c = idx - r * cols_here;
+          if (m0 + r < p.M) obase[(size_t)r * p.out_ld + c] = ep[r * EP_LD + c];
         }
       }
+      __syncthreads();
     }
   } else {
     // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co scatters to output pixel (2y+dy, 2x+dx)
@@ -590,7 +655,11 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
 #undef TC_PICK
   if (!kern) return false;  // combination not instantiated: the caller runs the SIMT kernel
   if (p.mode == 2 && (w.BN & 31)) return false;
-  size_t smem = (size_t)P.stages * (2 * w.KC * TC_BM * 16 + 2 * w.KC * w.BN * 16) + 64;
+  const size_t a_part_bytes = w.KC == 8 ? AGeo<8>::PART : AGeo<4>::PART;
+  size_t smem = (size_t)P.stages * (2 * a_part_bytes + 2 * (size_t)w.KC * w.BN * 16);
+  if (smem < (size_t)EP_BYTES) smem = EP_BYTES;  // the conv epilogue stages 128 x 32 outputs through shared memory
+  P.ctrl_off = (uint32_t)smem;
+  smem += 64;
   {
     static std::map<std::pair<const void*, int>, bool> attr_done;  // the attribute is per (kernel, device)
     auto key_attr = std::make_pair((const void*)kern, m->ctx->device);
