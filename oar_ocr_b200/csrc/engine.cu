@@ -228,41 +228,44 @@ __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restri
   const int ho0 = th * TH, wo0 = tw * TW;
   const int ih0 = ho0 * SH - PAD, iw0 = wo0 * SW - PAD;
   const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-  float4 acc[TH][TW];
+  // packed f32x2 FMAs (FFMA2 on sm_100): same per-component rounding as fmaf, half the issue slots
+  float2 acc_lo[TH][TW], acc_hi[TH][TW];
 #pragma unroll
   for (int ty = 0; ty < TH; ++ty)
 #pragma unroll
-    for (int tx = 0; tx < TW; ++tx) acc[ty][tx] = bv;
+    for (int tx = 0; tx < TW; ++tx) acc_lo[ty][tx] = make_float2(bv.x, bv.y), acc_hi[ty][tx] = make_float2(bv.z, bv.w);
   const float4* in4 = reinterpret_cast<const float4*>(in) + (size_t)b * H * W * c4n + c4;
   const float4* w4 = reinterpret_cast<const float4*>(w) + c4;
+  bool col_ok[COLS];
+#pragma unroll
+  for (int cx = 0; cx < COLS; ++cx) col_ok[cx] = (iw0 + cx >= 0) && (iw0 + cx < W);
 #pragma unroll
   for (int iy = 0; iy < ROWS; ++iy) {
     const int ih = ih0 + iy;
     if (ih < 0 || ih >= H) continue;
+    const float4* rowp = in4 + ((ptrdiff_t)ih * W + iw0) * c4n;
     float4 x[COLS];
 #pragma unroll
-    for (int cx = 0; cx < COLS; ++cx) {
-      const int iw = iw0 + cx;
-      x[cx] = (iw >= 0 && iw < W) ? __ldg(in4 + ((size_t)ih * W + iw) * c4n) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int cx = 0; cx < COLS; ++cx)
+      x[cx] = col_ok[cx] ? __ldg(rowp + (ptrdiff_t)cx * c4n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ty = 0; ty < TH; ++ty) {
       const int ky = iy - ty * SH;
       if (ky < 0 || ky >= K) continue;
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const float4 k = __ldg(w4 + (size_t)(ky * K + kx) * c4n);
+        const float4 k = __ldg(w4 + (ky * K + kx) * c4n);
+        const float2 klo = make_float2(k.x, k.y), khi = make_float2(k.z, k.w);
 #pragma unroll
         for (int tx = 0; tx < TW; ++tx) {
           const float4 v = x[tx * SW + kx];
-          acc[ty][tx].x = fmaf(v.x, k.x, acc[ty][tx].x);
-          acc[ty][tx].y = fmaf(v.y, k.y, acc[ty][tx].y);
-          acc[ty][tx].z = fmaf(v.z, k.z, acc[ty][tx].z);
-          acc[ty][tx].w = fmaf(v.w, k.w, acc[ty][tx].w);
+          acc_lo[ty][tx] = __ffma2_rn(make_float2(v.x, v.y), klo, acc_lo[ty][tx]);
+          acc_hi[ty][tx] = __ffma2_rn(make_float2(v.z, v.w), khi, acc_hi[ty][tx]);
         }
       }
     }
   }
+  const bool affine = ps != 1.0f || pb != 0.0f;
   float4* out4 = reinterpret_cast<float4*>(out) + (size_t)b * Ho * Wo * c4n + c4;
 #pragma unroll
   for (int ty = 0; ty < TH; ++ty) {
@@ -272,11 +275,16 @@ __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restri
     for (int tx = 0; tx < TW; ++tx) {
       const int wo = wo0 + tx;
       if (wo >= Wo) continue;
-      float4 a = acc[ty][tx];
-      a.x = apply_act(a.x, ACT) * ps + pb;
-      a.y = apply_act(a.y, ACT) * ps + pb;
-      a.z = apply_act(a.z, ACT) * ps + pb;
-      a.w = apply_act(a.w, ACT) * ps + pb;
+      float4 a = make_float4(acc_lo[ty][tx].x, acc_lo[ty][tx].y, acc_hi[ty][tx].x, acc_hi[ty][tx].y);
+      if (ACT == ACT_HSWISH) {  // reciprocal multiply instead of the IEEE divide: <= 1 ulp, inside the parity tolerance
+        a.x = a.x * fminf(fmaxf(a.x + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+        a.y = a.y * fminf(fmaxf(a.y + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+        a.z = a.z * fminf(fmaxf(a.z + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+        a.w = a.w * fminf(fmaxf(a.w + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+      } else {
+        a.x = apply_act(a.x, ACT), a.y = apply_act(a.y, ACT), a.z = apply_act(a.z, ACT), a.w = apply_act(a.w, ACT);
+      }
+      if (affine) a.x = a.x * ps + pb, a.y = a.y * ps + pb, a.z = a.z * ps + pb, a.w = a.w * ps + pb;
       out4[((size_t)ho * Wo + wo) * c4n] = a;
     }
   }
