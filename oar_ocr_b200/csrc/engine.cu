@@ -160,6 +160,66 @@ void launch_conv_simt(oar_ctx* ctx, const ConvParams& p, const char* name) {
   conv_gemm_simt<<<grid, 256, 0, ctx->stream>>>(p);
 }
 
+// ---------------------------------------------------------------------------
+// stem conv: Cin <= 4 (the RGB/BGR input), small Cout.  K = kh*kw*Cin is ~27, far too thin for a GEMM tile; one thread
+// computes one output pixel for all COUT channels with the weights broadcast from shared memory.
+// ---------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const ConvParams p) {
+  extern __shared__ float ws[];  // [K][COUT]
+  for (int i = threadIdx.x; i < p.K * COUT; i += blockDim.x) {
+    int k = i / COUT, co = i - k * COUT;
+    ws[i] = p.w[(size_t)co * p.K + k];
+  }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.M) return;
+  const int b = m / (p.Ho * p.Wo);
+  const int r = m - b * p.Ho * p.Wo;
+  const int ho = r / p.Wo, wo = r - ho * p.Wo;
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = __ldg(p.bias + co);
+  for (int ky = 0; ky < p.kh; ++ky) {
+    const int ih = ho * p.sh - p.ph + ky;
+    if (ih < 0 || ih >= p.H) continue;
+    for (int kx = 0; kx < p.kw; ++kx) {
+      const int iw = wo * p.sw - p.pw + kx;
+      if (iw < 0 || iw >= p.W) continue;
+      const float* src = p.in + (((size_t)b * p.H + ih) * p.W + iw) * p.Cin;
+      const float* wk = ws + (size_t)((ky * p.kw + kx) * p.Cin) * COUT;
+      for (int ci = 0; ci < p.Cin; ++ci) {
+        const float x = __ldg(src + ci);
+#pragma unroll
+        for (int co = 0; co < COUT; co += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wk + ci * COUT + co);
+          acc[co] = fmaf(x, w4.x, acc[co]);
+          acc[co + 1] = fmaf(x, w4.y, acc[co + 1]);
+          acc[co + 2] = fmaf(x, w4.z, acc[co + 2]);
+          acc[co + 3] = fmaf(x, w4.w, acc[co + 3]);
+        }
+      }
+    }
+  }
+  float* o = p.out + (size_t)m * p.out_ld + p.out_c_off;
+#pragma unroll
+  for (int co = 0; co < COUT; co += 4) {
+    float4 v;
+    v.x = apply_act(acc[co], p.act) * p.post_scale + p.post_bias;
+    v.y = apply_act(acc[co + 1], p.act) * p.post_scale + p.post_bias;
+    v.z = apply_act(acc[co + 2], p.act) * p.post_scale + p.post_bias;
+    v.w = apply_act(acc[co + 3], p.act) * p.post_scale + p.post_bias;
+    *reinterpret_cast<float4*>(o + co) = v;
+  }
+}
+
+static bool try_stem_conv(oar_ctx* ctx, const ConvParams& p) {
+  if (p.Cin > 4 || p.N != 16 || p.K > 64 || (p.out_ld & 3) || (p.out_c_off & 3)) return false;
+  Launch l(ctx, "stem_conv", 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw) + (double)p.M * p.N));
+  stem_conv_kernel<16><<<cdiv(p.M, 128), 128, (size_t)p.K * 16 * sizeof(float), ctx->stream>>>(p);
+  return true;
+}
+
 // engine dispatch: tensor-core kernel when the model runs engine 1 and has packed weights for `key`
 static void launch_gemm(oar_model* m, int key, const ConvParams& p, const char* name_simt, const char* name_tc) {
   if (m->engine == 1 && tc_gemm(m, key, p, name_tc)) return;
@@ -633,6 +693,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.N = cout, p.K = kh * kw * cin, p.M = a.B * Ho * Wo;
         p.out_ld = ctot, p.out_c_off = coff, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
         p.mode = 0, p.cout = cout;
+        if (m->engine == 1 && try_stem_conv(ctx, p)) break;
         launch_gemm(m, (int)oi * 2, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt",
                     (kh == 1 && kw == 1) ? "conv1x1_tc" : "convkxk_tc");
         break;

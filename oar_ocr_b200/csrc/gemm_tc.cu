@@ -254,6 +254,86 @@ __device__ __forceinline__ float act_t(float v) {
 constexpr int EP_LD = 36;                          // floats per row of the epilogue staging tile (32 + pad)
 constexpr int EP_BYTES = TC_BM * EP_LD * 4;        // 18432
 
+// Conv epilogue: bias + activation in registers, then a 128 x 32 staging tile in (now idle) shared memory so that
+// the global stores are whole 128-byte row segments (8 lanes per row) instead of 32 scattered 16-byte pieces.
+// Rows m0 .. m0+nrows-1 of the [M, out_ld] output are written.
+template <int ACT>
+__device__ __forceinline__ void epi_conv_store(const ConvParams& p, uint8_t* smem, uint32_t lane_base, int BN,
+                                               int n_base, int m0, int nrows, int tid) {
+  const int row = tid & (TC_BM - 1), half = tid >> 7;
+  {
+    float* ep = reinterpret_cast<float*>(smem);
+    const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0) &&
+                        ((((uintptr_t)p.out) & 15) == 0);
+    const float ps = p.post_scale, pb = p.post_bias;
+    const bool affine = ps != 1.0f || pb != 0.0f;  // the Act's learnable affine; identity in deploy graphs
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n_base + c0 >= p.N) break;
+      const int cols_here = min(min(32, BN - c0), p.N - n_base - c0);  // the tile ends at BN, the tensor at N
+      const int cc = c0 + 16 * half;
+      if (cc < BN && n_base + cc < p.N) {  // warp-uniform
+        float v[16];
+        tmem_ld16(lane_base + cc, v);
+        if (n_base + cc + 16 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 b;
+            if ((n_base & 3) == 0)
+              b = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + cc + i));  // weight arrays are 16-B aligned
+            else
+              b = make_float4(__ldg(p.bias + n_base + cc + i), __ldg(p.bias + n_base + cc + i + 1),
+                              __ldg(p.bias + n_base + cc + i + 2), __ldg(p.bias + n_base + cc + i + 3));
+            v[i] = act_t<ACT>(v[i] + b.x);
+            v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
+            v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
+            v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int n = n_base + cc + i;
+            v[i] = n < p.N ? act_t<ACT>(v[i] + __ldg(p.bias + n)) : 0.0f;
+          }
+        }
+        if (affine) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] * ps + pb;
+        }
+        float4* dst = reinterpret_cast<float4*>(ep + row * EP_LD + 16 * half);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      __syncthreads();
+      float* obase = p.out + (size_t)m0 * p.out_ld + p.out_c_off + n_base + c0;
+      if (vec_ok && (cols_here & 3) == 0) {
+        const int cpr = cols_here >> 2;  // float4 per row
+        if (cpr == 8) {
+#pragma unroll
+          for (int idx = tid; idx < TC_BM * 8; idx += TC_THREADS) {
+            const int r = idx >> 3, c4 = idx & 7;
+            if (r < nrows)
+              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
+                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
+          }
+        } else {
+          for (int idx = tid; idx < TC_BM * cpr; idx += TC_THREADS) {
+            const int r = idx / cpr, c4 = idx - r * cpr;
+            if (r < nrows)
+              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
+                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
+          }
+        }
+      } else {
+        for (int idx = tid; idx < TC_BM * cols_here; idx += TC_THREADS) {
+          const int r = idx / cols_here, c = idx - r * cols_here;
+          if (r < nrows) obase[(size_t)r * p.out_ld + c] = ep[r * EP_LD + c];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 template <int KC, int A_MODE, int EPI>
 __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -403,78 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       p.part_sum[o] = sum;
     }
   } else if (EPI < 8) {
-    // conv: bias + activation in registers, then a 128 x 32 staging tile in (now idle) shared memory so that the
-    // global stores are whole 128-byte row segments (8 lanes per row) instead of 32 scattered 16-byte pieces
-    constexpr int ACT = EPI & 7;
-    float* ep = reinterpret_cast<float*>(smem);
-    const bool vec_ok = ((p.out_ld & 3) == 0) && ((p.out_c_off & 3) == 0) && ((n_base & 3) == 0) &&
-                        ((((uintptr_t)p.out) & 15) == 0);
-    const float ps = p.post_scale, pb = p.post_bias;
-    const bool affine = ps != 1.0f || pb != 0.0f;  // the Act's learnable affine; identity in deploy graphs
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n_base + c0 >= p.N) break;
-      const int cols_here = min(min(32, BN - c0), p.N - n_base - c0);  // the tile ends at BN, the tensor at N
-      const int cc = c0 + 16 * half;
-      if (cc < BN && n_base + cc < p.N) {  // warp-uniform
-        float v[16];
-        tmem_ld16(lane_base + cc, v);
-        if (n_base + cc + 16 <= p.N) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 b;
-            if ((n_base & 3) == 0)
-              b = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + cc + i));  // weight arrays are 16-B aligned
-            else
-              b = make_float4(__ldg(p.bias + n_base + cc + i), __ldg(p.bias + n_base + cc + i + 1),
-                              __ldg(p.bias + n_base + cc + i + 2), __ldg(p.bias + n_base + cc + i + 3));
-            v[i] = act_t<ACT>(v[i] + b.x);
-            v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
-            v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
-            v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            int n = n_base + cc + i;
-            v[i] = n < p.N ? act_t<ACT>(v[i] + __ldg(p.bias + n)) : 0.0f;
-          }
-        }
-        if (affine) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = v[i] * ps + pb;
-        }
-        float4* dst = reinterpret_cast<float4*>(ep + row * EP_LD + 16 * half);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      __syncthreads();
-      float* obase = p.out + (size_t)m0 * p.out_ld + p.out_c_off + n_base + c0;
-      if (vec_ok && (cols_here & 3) == 0) {
-        const int cpr = cols_here >> 2;  // float4 per row
-        if (cpr == 8) {
-#pragma unroll
-          for (int idx = tid; idx < TC_BM * 8; idx += TC_THREADS) {
-            const int r = idx >> 3, c4 = idx & 7;
-            if (m0 + r < p.M)
-              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
-                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
-          }
-        } else {
-          for (int idx = tid; idx < TC_BM * cpr; idx += TC_THREADS) {
-            const int r = idx / cpr, c4 = idx - r * cpr;
-            if (m0 + r < p.M)
-              *reinterpret_cast<float4*>(obase + (size_t)r * p.out_ld + 4 * c4) =
-                  *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
-          }
-        }
-      } else {
-        for (int idx = tid; idx < TC_BM * cols_here; idx += TC_THREADS) {
-          const int r = idx / cols_here, c = idx - r * cols_here;
-          if (m0 + r < p.M) obase[(size_t)r * p.out_ld + c] = ep[r * EP_LD + c];
-        }
-      }
-      __syncthreads();
-    }
+    epi_conv_store<EPI & 7>(p, smem, lane_base, BN, n_base, m0, min(TC_BM, p.M - m0), tid);
   } else {
     // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co scatters to output pixel (2y+dy, 2x+dx)
     constexpr int ACT = EPI & 7;
