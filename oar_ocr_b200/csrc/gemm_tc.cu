@@ -41,6 +41,8 @@ constexpr int TC_MAX_BN = 256;
 struct TcWeights {
   uint4* packed = nullptr;  // [n_tile][k_block][hi|lo][k-chunk][BN rows][8 halfs]
   int N = 0, K = 0, BN = 0, n_tiles = 0, nkb = 0, KC = 4;
+  bool rowtaps = false;  // packed for conv_rowtaps_tc: [n_tile][ky][cin block][kx][hi|lo][k-chunk][BN rows][8 halfs]
+  int kh = 1, kw = 1;
 };
 
 struct TcState {
@@ -517,6 +519,153 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------
+// Stride-1 k x k convolution ("row taps"): the generic im2col gather above re-reads every input pixel kh*kw times
+// through L1/L2 (a 3x3 over 96 channels moves 9x the tensor).  Here a CTA owns up to 128 consecutive output pixels of
+// ONE image row; a k-block is (ky, 32 input channels): the CTA stages the input row ih = h + ky - ph for pixels
+// w0 - pw .. w0 + 127 + pw ONCE (130 rows of the K-major no-swizzle layout, whose row dimension is linear at 16 B per
+// row because SBO = 8 * 16 B), and the kw taps of that row are issued as MMAs whose A descriptors start kx * 16 bytes
+// further: a shifted view of the same shared-memory rows.  Gather traffic drops from kh*kw to ~kh reads per pixel.
+// ---------------------------------------------------------------------------
+constexpr int RT_KC = 4;            // 32 input channels per k-block
+constexpr int RT_MAX_KW = 3;        // halo rows that fit the padded chunk stride (130 rows)
+constexpr uint32_t RT_LBO = AGeo<RT_KC>::LBO;
+static_assert(RT_LBO >= (TC_BM + RT_MAX_KW - 1) * 16, "chunk stride must hold the halo rows");
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS) conv_rowtaps_tc(const TcParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const ConvParams& p = P.c;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int BN = P.BN, kw = p.kw;
+  constexpr uint32_t a_part = RT_KC * RT_LBO;
+  const uint32_t b_part = RT_KC * BN * 16;
+  const uint32_t stage_bytes = 2 * a_part + (uint32_t)kw * 2 * b_part;
+  const int smask = P.stages - 1;
+  uint8_t* ctrl = smem + P.ctrl_off;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(ctrl);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * TC_STAGES);
+
+  // tile -> (image, output row, 128-pixel segment)
+  const int segs = (p.Wo + TC_BM - 1) / TC_BM;
+  const int seg = blockIdx.x % segs, bh = blockIdx.x / segs;
+  const int h = bh % p.Ho, b = bh / p.Ho;
+  const int w0 = seg * TC_BM;
+  const int nrows = min(TC_BM, p.Wo - w0);
+  const int m0 = (b * p.Ho + h) * p.Wo + w0;
+  const int ncb = p.Cin / (RT_KC * 8);
+  const int halo_rows = TC_BM + kw - 1;
+
+  // this thread's (halo row, chunk) pairs: pair = tid + pass * 256, chunk = pair % 4, row = pair / 4
+  const int chunk = tid & 3;
+  const float* px_ptr[3];
+  bool px_ok[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int rr = (tid >> 2) + j * 64;
+    const int w = w0 - p.pw + rr;
+    px_ok[j] = rr < halo_rows && w >= 0 && w < p.W;
+    px_ptr[j] = p.in + (((size_t)b * p.H) * p.W + (px_ok[j] ? w : 0)) * p.Cin + chunk * 8;
+  }
+  const int nt = blockIdx.y;
+  const int nvec_b = kw * 2 * RT_KC * BN;
+  const uint4* wtile = P.wpk + (size_t)nt * P.nkb * nvec_b;
+
+  auto load_a = [&](int kb, float4 (&v)[6]) {
+    const int ky = kb / ncb, cb = kb - ky * ncb;
+    const int ih = h + ky - p.ph;
+    const bool row_in = ih >= 0 && ih < p.H;
+    const size_t off = (size_t)ih * p.W * p.Cin + (size_t)cb * (RT_KC * 8);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), q = u;
+      if (row_in && px_ok[j]) {
+        u = __ldg(reinterpret_cast<const float4*>(px_ptr[j] + off));
+        q = __ldg(reinterpret_cast<const float4*>(px_ptr[j] + off + 4));
+      }
+      v[2 * j] = u;
+      v[2 * j + 1] = q;
+    }
+  };
+
+  float4 pre[6];
+  load_a(0, pre);
+  {
+    const uint32_t b_dst = smem_u32(smem + 2 * a_part);
+    for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, wtile + i);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&mbar[s]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  for (int kb = 0; kb < P.nkb; ++kb) {
+    const int s = kb & smask;
+    uint8_t* st = smem + s * stage_bytes;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int rr = (tid >> 2) + j * 64;
+      if (rr < halo_rows) {
+        float x[8] = {pre[2 * j].x,     pre[2 * j].y,     pre[2 * j].z,     pre[2 * j].w,
+                      pre[2 * j + 1].x, pre[2 * j + 1].y, pre[2 * j + 1].z, pre[2 * j + 1].w};
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = (uint32_t)chunk * RT_LBO + (uint32_t)rr * 16;
+        *reinterpret_cast<uint4*>(st + off) = hi;
+        *reinterpret_cast<uint4*>(st + a_part + off) = lo;
+      }
+    }
+    cp_async_wait_all();
+    if (kb + 1 < P.nkb) load_a(kb + 1, pre);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi_s = smem_u32(st), a_lo_s = a_hi_s + a_part;
+      const uint32_t b_base = a_hi_s + 2 * a_part;
+      const uint32_t b_lbo = (uint32_t)BN * 16;
+      for (int kx = 0; kx < kw; ++kx) {
+        const uint32_t b_hi_s = b_base + (uint32_t)kx * 2 * b_part, b_lo_s = b_hi_s + b_part;
+#pragma unroll
+        for (int j = 0; j < RT_KC / 2; ++j) {
+          // the kx-th tap of output pixel r reads halo row r + kx: same rows, start address kx * 16 bytes on
+          uint64_t ah = make_desc(a_hi_s + 2 * j * RT_LBO + kx * 16, RT_LBO, 128);
+          uint64_t al = make_desc(a_lo_s + 2 * j * RT_LBO + kx * 16, RT_LBO, 128);
+          uint64_t bh = make_desc(b_hi_s + 2 * j * b_lbo, b_lbo, 128);
+          uint64_t bl = make_desc(b_lo_s + 2 * j * b_lbo, b_lbo, 128);
+          umma_f16(tmem_base, ah, bh, idesc, (kb | kx | j) ? 1u : 0u);
+          umma_f16(tmem_base, ah, bl, idesc, 1u);
+          umma_f16(tmem_base, al, bh, idesc, 1u);
+        }
+      }
+      umma_commit(smem_u32(&mbar[s]));
+    }
+    if (kb + 1 < P.nkb) {
+      if (kb >= 1) mbar_wait(smem_u32(&mbar[s ^ 1]), (uint32_t)(((kb - 1) >> 1) & 1));
+      const uint32_t b_dst = smem_u32(smem + (s ^ 1) * stage_bytes + 2 * a_part);
+      const uint4* b_src = wtile + (size_t)(kb + 1) * nvec_b;
+      for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, b_src + i);
+    }
+  }
+  {
+    const int last = P.nkb - 1;
+    mbar_wait(smem_u32(&mbar[last & smask]), (uint32_t)((P.stages == 2 ? (last >> 1) : last) & 1));
+    tc_fence_after();
+  }
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  epi_conv_store<EPI & 7>(p, smem, lane_base, BN, nt * BN, m0, nrows, tid);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
 // per-row combine of the CTC head's tile partials: arg-max (last index on ties) and 1 / sum exp(z - zmax)
 __global__ void ctc_combine_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx,
                                    const float* __restrict__ psum, size_t rows, int n_tiles, int32_t* __restrict__ idx,
@@ -578,6 +727,42 @@ static TcWeights pack_weights(const float* w, int N, int K) {
   return t;
 }
 
+// weights of a stride-1 kh x kw conv for conv_rowtaps_tc: k-block = (ky, 32 input channels), all kw taps per stage
+static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int Cin) {
+  TcWeights t;
+  t.N = N, t.K = kh * kw * Cin, t.rowtaps = true, t.kh = kh, t.kw = kw, t.KC = 4;
+  t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
+  int per = (N + t.n_tiles - 1) / t.n_tiles;
+  t.BN = std::max(16, (per + 15) / 16 * 16);
+  const int ncb = Cin / 32;
+  t.nkb = kh * ncb;
+  const size_t part = (size_t)4 * t.BN * 8;  // halfs of one (hi or lo) part
+  const size_t stage = (size_t)kw * 2 * part;
+  std::vector<__half> buf((size_t)t.n_tiles * t.nkb * stage, __float2half(0.0f));
+  for (int nt = 0; nt < t.n_tiles; ++nt)
+    for (int ky = 0; ky < kh; ++ky)
+      for (int cb = 0; cb < ncb; ++cb) {
+        __half* st = buf.data() + ((size_t)nt * t.nkb + ky * ncb + cb) * stage;
+        for (int kx = 0; kx < kw; ++kx)
+          for (int kc = 0; kc < 4; ++kc)
+            for (int r = 0; r < t.BN; ++r) {
+              int n = nt * t.BN + r;
+              if (n >= N) continue;
+              for (int e = 0; e < 8; ++e) {
+                int ci = cb * 32 + kc * 8 + e;
+                float x = w[(size_t)n * t.K + (size_t)(ky * kw + kx) * Cin + ci];
+                __half hi = __float2half_rn(x);
+                __half lo = __float2half_rn(x - __half2float(hi));
+                st[(size_t)kx * 2 * part + ((size_t)kc * t.BN + r) * 8 + e] = hi;
+                st[(size_t)kx * 2 * part + part + ((size_t)kc * t.BN + r) * 8 + e] = lo;
+              }
+            }
+      }
+  OAR_CUDA(cudaMalloc(&t.packed, buf.size() * sizeof(__half)));
+  OAR_CUDA(cudaMemcpy(t.packed, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return t;
+}
+
 void tc_model_init(oar_model* m) {
   TcState* st = new TcState();
   m->tc_state = st;
@@ -587,9 +772,13 @@ void tc_model_init(oar_model* m) {
     const OpRec& op = m->ops[oi];
     const float* w0 = host.data() + op.w_off[0];
     switch (op.type) {
-      case OP_CONV:
-        st->w[(int)oi * 2] = pack_weights(w0, op.p[7], op.p[0] * op.p[1] * op.p[6]);
+      case OP_CONV: {
+        const int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3], ph = op.p[4], pw = op.p[5], cin = op.p[6];
+        const bool rowtaps = kh * kw > 1 && sh == 1 && sw == 1 && (kh & 1) && (kw & 1) && ph == kh / 2 && pw == kw / 2 &&
+                             kw <= RT_MAX_KW && cin % 32 == 0;
+        st->w[(int)oi * 2] = rowtaps ? pack_weights_rowtaps(w0, op.p[7], kh, kw, cin) : pack_weights(w0, op.p[7], kh * kw * cin);
         break;
+      }
       case OP_DECONV2:
         st->w[(int)oi * 2] = pack_weights(w0, 4 * op.p[1], op.p[0]);
         break;
@@ -641,6 +830,37 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   P.tmem_cols = cols;
   const bool pointwise = p.kh == 1 && p.kw == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0;
   const bool aligned = (((uintptr_t)p.in) & 15) == 0;
+  if (w.rowtaps) {
+    if (!aligned || p.mode != 0 || p.kh != w.kh || p.kw != w.kw || p.sh != 1 || p.sw != 1 || p.Ho != p.H || p.Wo != p.W)
+      OAR_FAIL(OAR_E_MODEL, "row-taps weights for op key %d do not match its convolution", key);
+    using KernRT = void (*)(const TcParams);
+    KernRT krt = nullptr;
+    switch (p.act) {
+      case ACT_NONE: krt = conv_rowtaps_tc<0>; break;
+      case ACT_RELU: krt = conv_rowtaps_tc<1>; break;
+      case ACT_HSWISH: krt = conv_rowtaps_tc<2>; break;
+      case ACT_SWISH: krt = conv_rowtaps_tc<3>; break;
+      case ACT_SIGMOID: krt = conv_rowtaps_tc<4>; break;
+      default: return false;
+    }
+    size_t smem_rt = (size_t)P.stages * (2 * (size_t)RT_KC * RT_LBO + (size_t)w.kw * 2 * RT_KC * w.BN * 16);
+    if (smem_rt < (size_t)EP_BYTES) smem_rt = EP_BYTES;
+    P.ctrl_off = (uint32_t)smem_rt;
+    smem_rt += 64;
+    {
+      static std::map<std::pair<const void*, int>, bool> attr_done_rt;
+      auto key_attr = std::make_pair((const void*)krt, m->ctx->device);
+      if (!attr_done_rt.count(key_attr)) {
+        OAR_CUDA(cudaFuncSetAttribute(krt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done_rt[key_attr] = true;
+      }
+    }
+    const int segs = (p.Wo + TC_BM - 1) / TC_BM;
+    dim3 grid_rt((unsigned)(p.B * p.Ho * segs), w.n_tiles);
+    Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + 4.0 * (double)p.M * p.N);
+    krt<<<grid_rt, TC_THREADS, smem_rt, m->ctx->stream>>>(P);
+    return true;
+  }
   int a_mode = AM_SCALAR;
   if (pointwise && (p.Cin % 8) == 0 && aligned)
     a_mode = AM_POINTWISE;
