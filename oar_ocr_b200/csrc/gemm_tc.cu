@@ -161,6 +161,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 constexpr int TC_THREADS = 256;  // two threads per output row: each takes half the k-chunks and half the columns
 
@@ -374,12 +376,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   const uint4* wtile = P.wpk + (size_t)nt * P.nkb * (2 * KC * BN);
   const int nvec_b = 2 * KC * BN;  // 16-byte vectors of one B stage (hi then lo)
 
-  // first k-block: A into registers, B straight into stage 0 (both in flight during the set-up below)
-  ARegs<KC> pre;
-  load_a<KC, A_MODE>(p, 0, chunk, rows, pre);
+  // first two k-blocks of A into registers, B(0) straight into stage 0 (all in flight during the set-up below)
+  ARegs<KC> pre0, pre1;
+  load_a<KC, A_MODE>(p, 0, chunk, rows, pre0);
+  if (P.nkb > 1) load_a<KC, A_MODE>(p, 1, chunk, rows, pre1);
   {
     const uint32_t b_dst = smem_u32(smem + 2 * a_part);
     for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, wtile + i);
+    cp_async_commit();
   }
 
   if (tid == 0) {
@@ -396,10 +400,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   const uint32_t a_store_off = (uint32_t)chunk * G::LBO + (uint32_t)(tid / KC) * 16;
 
-  for (int kb = 0; kb < P.nkb; ++kb) {
+  // Software pipeline, per k-block kb (stage s = kb & 1):
+  //   a. split the registers loaded two iterations ago into A(kb) -> stage s   (free since MMA(kb-2), waited last time)
+  //   b. issue the global loads of A(kb+2) into the same registers
+  //   c. wait for MMA(kb-1) (it ran under a/b), which frees stage s^1
+  //   d. cp.async B(kb+1) -> stage s^1        e. wait for B(kb), issued one whole iteration ago
+  //   f. fence, barrier, one thread issues the MMAs of kb and commits to mbar[s]
+  auto step = [&](int kb, ARegs<KC>& pre) {
     const int s = kb & smask;
     uint8_t* st = smem + s * stage_bytes;
-    // stage s is free: its previous reader MMA(kb-2) was waited for at the end of iteration kb-1
 #pragma unroll
     for (int j = 0; j < G::NP; ++j) {
       float x[8] = {pre.v[2 * j].x,     pre.v[2 * j].y,     pre.v[2 * j].z,     pre.v[2 * j].w,
@@ -410,8 +419,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       *reinterpret_cast<uint4*>(st + off) = hi;
       *reinterpret_cast<uint4*>(st + a_part + off) = lo;
     }
-    cp_async_wait_all();  // this thread's share of B(kb)
-    if (kb + 1 < P.nkb) load_a<KC, A_MODE>(p, kb + 1, chunk, rows, pre);
+    if (kb + 2 < P.nkb) load_a<KC, A_MODE>(p, kb + 2, chunk, rows, pre);
+    if (kb + 1 < P.nkb) {
+      if (kb >= 1) mbar_wait(smem_u32(&mbar[s ^ 1]), (uint32_t)(((kb - 1) >> 1) & 1));
+      const uint32_t b_dst = smem_u32(smem + (s ^ 1) * stage_bytes + 2 * a_part);
+      const uint4* b_src = wtile + (size_t)(kb + 1) * nvec_b;
+      for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, b_src + i);
+      cp_async_commit();
+      cp_async_wait_1();  // B(kb) has landed; B(kb+1) stays in flight
+    } else {
+      cp_async_wait_all();
+    }
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -431,13 +449,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       }
       umma_commit(smem_u32(&mbar[s]));
     }
-    if (kb + 1 < P.nkb) {
-      // the other stage was last read by MMA(kb-1): wait for its commit, then stream B(kb+1) into it
-      if (kb >= 1) mbar_wait(smem_u32(&mbar[s ^ 1]), (uint32_t)(((kb - 1) >> 1) & 1));
-      const uint32_t b_dst = smem_u32(smem + (s ^ 1) * stage_bytes + 2 * a_part);
-      const uint4* b_src = wtile + (size_t)(kb + 1) * nvec_b;
-      for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, b_src + i);
-    }
+  };
+  for (int kb = 0; kb < P.nkb; kb += 2) {
+    step(kb, pre0);
+    if (kb + 1 < P.nkb) step(kb + 1, pre1);
   }
   // all MMAs done when the last commit lands (a commit tracks every prior tcgen05 op of the issuing thread)
   {
