@@ -473,25 +473,28 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
     float mx = -INFINITY, sum = 0.0f;
     int mi = 0;
     const int cbeg = half * (BN >> 1), cend = cbeg + (BN >> 1);
+    // branch-free per 16 classes: group max -> one rescale of the running sum -> 16 exps; the arg-max keeps the
+    // LAST maximal index (simd.rs:194-204) because classes are visited in ascending order with >=
     for (int c0 = cbeg; c0 < cend; c0 += 16) {
       if (n_base + c0 >= p.N) break;
       float v[16];
       tmem_ld16(lane_base + c0, v);
+      float gmax = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        int n = n_base + c0 + i;
-        if (n < p.N) {
-          float z = v[i] + __ldg(p.bias + n);
-          if (z > mx) {
-            sum = sum * expf(mx - z) + 1.0f;
-            mx = z;
-            mi = n;
-          } else {
-            sum += expf(z - mx);
-            if (z == mx) mi = n;  // LAST maximal index wins (simd.rs:194-204)
-          }
-        }
+        const int n = n_base + c0 + i;
+        v[i] = n < p.N ? v[i] + __ldg(p.bias + n) : -INFINITY;
+        gmax = fmaxf(gmax, v[i]);
       }
+      const float nmx = fmaxf(mx, gmax);
+      float part = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        part += __expf(v[i] - nmx);  // exp(-inf) = 0 for the padded classes
+        if (v[i] >= mx && v[i] == nmx) mi = n_base + c0 + i;
+      }
+      sum = sum * __expf(mx - nmx) + part;
+      mx = nmx;
     }
     if (row_ok) {
       size_t o = (size_t)m * (2 * P.n_tiles) + 2 * nt + half;
@@ -502,31 +505,66 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   } else if (EPI < 8) {
     epi_conv_store<EPI & 7>(p, smem, lane_base, BN, n_base, m0, min(TC_BM, p.M - m0), tid);
   } else {
-    // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co scatters to output pixel (2y+dy, 2x+dx)
+    // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co belongs to output pixel (2y+dy, 2x+dx).  For a
+    // fixed dy the 2*cout columns of an input pixel are one contiguous run of the output row 2y+dy, and consecutive
+    // input pixels continue that run, so the tile is staged through shared memory like the conv epilogue and written
+    // as 16-byte pieces of those runs.
     constexpr int ACT = EPI & 7;
-    int ob = 0, oy = 0, ox = 0;
-    if (row_ok) {
-      ob = m / (p.Ho * p.Wo);
-      int r = m - ob * p.Ho * p.Wo;
-      oy = r / p.Wo;
-      ox = r - oy * p.Wo;
-    }
+    float* ep = reinterpret_cast<float*>(smem);
     const float ps = p.post_scale, pb = p.post_bias;
-    for (int c0 = half * 16; c0 < BN; c0 += 32) {
+    const int run = 2 * p.cout;                     // columns per dy
+    const size_t dy_stride = (size_t)2 * p.Wo * p.cout;  // floats between output rows 2y and 2y+1
+    const bool vec_ok = (run & 3) == 0 && ((((uintptr_t)p.out) & 15) == 0);
+    const int nrows = min(TC_BM, p.M - m0);
+    for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n_base + c0 >= p.N) break;
-      float v[16];
-      tmem_ld16(lane_base + c0, v);
-      if (!row_ok) continue;
-      int n = n_base + c0;
-      int q = n / p.cout, co = n - q * p.cout;
+      const int cols_here = min(min(32, BN - c0), p.N - n_base - c0);
+      const int cc = c0 + 16 * half;
+      if (cc < BN && n_base + cc < p.N) {
+        float v[16];
+        tmem_ld16(lane_base + cc, v);
+        int co = (n_base + cc) % p.cout;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (n + i < p.N) {
-          float r = act_t<ACT>(v[i] + __ldg(p.bias + co)) * ps + pb;
-          p.out[(((size_t)ob * (2 * p.Ho) + 2 * oy + (q >> 1)) * (2 * p.Wo) + 2 * ox + (q & 1)) * p.cout + co] = r;
+        for (int i = 0; i < 16; ++i) {
+          v[i] = (n_base + cc + i < p.N) ? act_t<ACT>(v[i] + __ldg(p.bias + co)) * ps + pb : 0.0f;
+          if (++co == p.cout) co = 0;
         }
-        if (++co == p.cout) co = 0, ++q;
+        float4* dst = reinterpret_cast<float4*>(ep + row * EP_LD + 16 * half);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
+      __syncthreads();
+      if (vec_ok && (cols_here & 3) == 0 && ((n_base + c0) & 3) == 0) {
+        const int cpr = cols_here >> 2;
+        for (int idx = tid; idx < TC_BM * cpr; idx += TC_THREADS) {
+          const int r = idx / cpr, c4 = idx - r * cpr;
+          if (r < nrows) {
+            const int mm = m0 + r;
+            const int ob = mm / (p.Ho * p.Wo);
+            const int rem = mm - ob * p.Ho * p.Wo;
+            const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+            const int n = n_base + c0 + 4 * c4;
+            const int dy = n / run, k = n - dy * run;
+            float* o = p.out + (((size_t)ob * (2 * p.Ho) + 2 * oy) * (2 * p.Wo) + 2 * ox) * p.cout + dy * dy_stride + k;
+            *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(ep + r * EP_LD + 4 * c4);
+          }
+        }
+      } else {
+        for (int idx = tid; idx < TC_BM * cols_here; idx += TC_THREADS) {
+          const int r = idx / cols_here, c = idx - r * cols_here;
+          if (r < nrows) {
+            const int mm = m0 + r;
+            const int ob = mm / (p.Ho * p.Wo);
+            const int rem = mm - ob * p.Ho * p.Wo;
+            const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+            const int n = n_base + c0 + c;
+            const int dy = n / run, k = n - dy * run;
+            p.out[(((size_t)ob * (2 * p.Ho) + 2 * oy) * (2 * p.Wo) + 2 * ox) * p.cout + dy * dy_stride + k] =
+                ep[r * EP_LD + c];
+          }
+        }
+      }
+      __syncthreads();
     }
   }
   tc_fence_before();
