@@ -264,10 +264,80 @@ __global__ void dwconv_kernel(const float* __restrict__ in, const float* __restr
   *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4) = acc;
 }
 
-// Register-tiled depthwise conv: one thread = 4 channels x (TH x TW) output pixels.  The op is LSU-bound (every
-// output reads K*K inputs through L1), so each input float4 is loaded once per thread and reused by all the
-// outputs of the tile it feeds: K*K -> (rows*cols)/(TH*TW) input loads per output (25 -> 6 for 5x5 s1 2x4).
+// Register-tiled depthwise conv: one thread = 4 channels x (TH x TW) output pixels.  The op is instruction- and
+// LSU-bound (every output reads K*K inputs through L1), so each input float4 is loaded once per thread and reused by
+// all the outputs of the tile it feeds (25 -> 6 loads per output for 5x5 s1 2x4), FMAs are packed f32x2 (FFMA2), and
+// tiles that lie wholly inside the image take a path with no bounds predicates or zero fills (INTERIOR).
 // Accumulation order per output is bias, then (ky, kx) ascending, as in the generic kernel above.
+template <int K, int SH, int SW, int TH, int TW, int ACT, bool INTERIOR>
+__device__ __forceinline__ void dw_tile(const float4* __restrict__ in4, const float4* __restrict__ w4, float4 bv,
+                                        float4* __restrict__ out4, int H, int W, int c4n, int Ho, int Wo, int ho0,
+                                        int wo0, float ps, float pb) {
+  constexpr int ROWS = (TH - 1) * SH + K, COLS = (TW - 1) * SW + K, PAD = K / 2;
+  const int ih0 = ho0 * SH - PAD, iw0 = wo0 * SW - PAD;
+  float2 acc_lo[TH][TW], acc_hi[TH][TW];
+#pragma unroll
+  for (int ty = 0; ty < TH; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < TW; ++tx) acc_lo[ty][tx] = make_float2(bv.x, bv.y), acc_hi[ty][tx] = make_float2(bv.z, bv.w);
+  bool col_ok[COLS];
+#pragma unroll
+  for (int cx = 0; cx < COLS; ++cx) col_ok[cx] = INTERIOR || ((iw0 + cx >= 0) && (iw0 + cx < W));
+  const float4* rowp = in4 + ((ptrdiff_t)ih0 * W + iw0) * c4n;
+  const ptrdiff_t row_stride = (ptrdiff_t)W * c4n;
+#pragma unroll
+  for (int iy = 0; iy < ROWS; ++iy, rowp += row_stride) {
+    if (!INTERIOR) {
+      const int ih = ih0 + iy;
+      if (ih < 0 || ih >= H) continue;
+    }
+    float4 x[COLS];
+    const float4* px = rowp;
+#pragma unroll
+    for (int cx = 0; cx < COLS; ++cx, px += c4n)
+      x[cx] = col_ok[cx] ? __ldg(px) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ty = 0; ty < TH; ++ty) {
+      const int ky = iy - ty * SH;
+      if (ky < 0 || ky >= K) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const float4 k = __ldg(w4 + (ky * K + kx) * c4n);
+        const float2 klo = make_float2(k.x, k.y), khi = make_float2(k.z, k.w);
+#pragma unroll
+        for (int tx = 0; tx < TW; ++tx) {
+          const float4 v = x[tx * SW + kx];
+          acc_lo[ty][tx] = __ffma2_rn(make_float2(v.x, v.y), klo, acc_lo[ty][tx]);
+          acc_hi[ty][tx] = __ffma2_rn(make_float2(v.z, v.w), khi, acc_hi[ty][tx]);
+        }
+      }
+    }
+  }
+  const bool affine = ps != 1.0f || pb != 0.0f;
+  float4* orow = out4 + ((size_t)ho0 * Wo + wo0) * c4n;
+#pragma unroll
+  for (int ty = 0; ty < TH; ++ty, orow += (size_t)Wo * c4n) {
+    if (!INTERIOR && ho0 + ty >= Ho) continue;
+#pragma unroll
+    for (int tx = 0; tx < TW; ++tx) {
+      if (!INTERIOR && wo0 + tx >= Wo) continue;
+      float2 lo = acc_lo[ty][tx], hi = acc_hi[ty][tx];
+      if (ACT == ACT_HSWISH) {  // reciprocal multiply instead of the IEEE divide: <= 1 ulp, inside the parity tolerance
+        const float2 three = make_float2(3.0f, 3.0f), sixth = make_float2(0.16666667f, 0.16666667f);
+        float2 tl = __fadd2_rn(lo, three), th2 = __fadd2_rn(hi, three);
+        tl.x = fminf(fmaxf(tl.x, 0.0f), 6.0f), tl.y = fminf(fmaxf(tl.y, 0.0f), 6.0f);
+        th2.x = fminf(fmaxf(th2.x, 0.0f), 6.0f), th2.y = fminf(fmaxf(th2.y, 0.0f), 6.0f);
+        lo = __fmul2_rn(__fmul2_rn(lo, tl), sixth);
+        hi = __fmul2_rn(__fmul2_rn(hi, th2), sixth);
+      } else {
+        lo.x = apply_act(lo.x, ACT), lo.y = apply_act(lo.y, ACT), hi.x = apply_act(hi.x, ACT), hi.y = apply_act(hi.y, ACT);
+      }
+      if (affine) lo.x = lo.x * ps + pb, lo.y = lo.y * ps + pb, hi.x = hi.x * ps + pb, hi.y = hi.y * ps + pb;
+      orow[(size_t)tx * c4n] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+}
+
 template <int K, int SH, int SW, int TH, int TW, int ACT>
 __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
@@ -288,66 +358,14 @@ __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restri
   const int ho0 = th * TH, wo0 = tw * TW;
   const int ih0 = ho0 * SH - PAD, iw0 = wo0 * SW - PAD;
   const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-  // packed f32x2 FMAs (FFMA2 on sm_100): same per-component rounding as fmaf, half the issue slots
-  float2 acc_lo[TH][TW], acc_hi[TH][TW];
-#pragma unroll
-  for (int ty = 0; ty < TH; ++ty)
-#pragma unroll
-    for (int tx = 0; tx < TW; ++tx) acc_lo[ty][tx] = make_float2(bv.x, bv.y), acc_hi[ty][tx] = make_float2(bv.z, bv.w);
   const float4* in4 = reinterpret_cast<const float4*>(in) + (size_t)b * H * W * c4n + c4;
   const float4* w4 = reinterpret_cast<const float4*>(w) + c4;
-  bool col_ok[COLS];
-#pragma unroll
-  for (int cx = 0; cx < COLS; ++cx) col_ok[cx] = (iw0 + cx >= 0) && (iw0 + cx < W);
-#pragma unroll
-  for (int iy = 0; iy < ROWS; ++iy) {
-    const int ih = ih0 + iy;
-    if (ih < 0 || ih >= H) continue;
-    const float4* rowp = in4 + ((ptrdiff_t)ih * W + iw0) * c4n;
-    float4 x[COLS];
-#pragma unroll
-    for (int cx = 0; cx < COLS; ++cx)
-      x[cx] = col_ok[cx] ? __ldg(rowp + (ptrdiff_t)cx * c4n) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int ty = 0; ty < TH; ++ty) {
-      const int ky = iy - ty * SH;
-      if (ky < 0 || ky >= K) continue;
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const float4 k = __ldg(w4 + (ky * K + kx) * c4n);
-        const float2 klo = make_float2(k.x, k.y), khi = make_float2(k.z, k.w);
-#pragma unroll
-        for (int tx = 0; tx < TW; ++tx) {
-          const float4 v = x[tx * SW + kx];
-          acc_lo[ty][tx] = __ffma2_rn(make_float2(v.x, v.y), klo, acc_lo[ty][tx]);
-          acc_hi[ty][tx] = __ffma2_rn(make_float2(v.z, v.w), khi, acc_hi[ty][tx]);
-        }
-      }
-    }
-  }
-  const bool affine = ps != 1.0f || pb != 0.0f;
   float4* out4 = reinterpret_cast<float4*>(out) + (size_t)b * Ho * Wo * c4n + c4;
-#pragma unroll
-  for (int ty = 0; ty < TH; ++ty) {
-    const int ho = ho0 + ty;
-    if (ho >= Ho) continue;
-#pragma unroll
-    for (int tx = 0; tx < TW; ++tx) {
-      const int wo = wo0 + tx;
-      if (wo >= Wo) continue;
-      float4 a = make_float4(acc_lo[ty][tx].x, acc_lo[ty][tx].y, acc_hi[ty][tx].x, acc_hi[ty][tx].y);
-      if (ACT == ACT_HSWISH) {  // reciprocal multiply instead of the IEEE divide: <= 1 ulp, inside the parity tolerance
-        a.x = a.x * fminf(fmaxf(a.x + 3.0f, 0.0f), 6.0f) * 0.16666667f;
-        a.y = a.y * fminf(fmaxf(a.y + 3.0f, 0.0f), 6.0f) * 0.16666667f;
-        a.z = a.z * fminf(fmaxf(a.z + 3.0f, 0.0f), 6.0f) * 0.16666667f;
-        a.w = a.w * fminf(fmaxf(a.w + 3.0f, 0.0f), 6.0f) * 0.16666667f;
-      } else {
-        a.x = apply_act(a.x, ACT), a.y = apply_act(a.y, ACT), a.z = apply_act(a.z, ACT), a.w = apply_act(a.w, ACT);
-      }
-      if (affine) a.x = a.x * ps + pb, a.y = a.y * ps + pb, a.z = a.z * ps + pb, a.w = a.w * ps + pb;
-      out4[((size_t)ho * Wo + wo) * c4n] = a;
-    }
-  }
+  const bool interior = ih0 >= 0 && ih0 + ROWS <= H && iw0 >= 0 && iw0 + COLS <= W && ho0 + TH <= Ho && wo0 + TW <= Wo;
+  if (interior)
+    dw_tile<K, SH, SW, TH, TW, ACT, true>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb);
+  else
+    dw_tile<K, SH, SW, TH, TW, ACT, false>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb);
 }
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
