@@ -1,0 +1,109 @@
+"""Parity at BASELINE.json's full sizes (960x960 pages, 512-crop recognizer batches): direct oracle comparison on a
+few pages, and size-independent properties on the whole batch -- determinism, engine agreement (fp32 SIMT engine vs
+tcgen05 engine give the same boxes and labels), batch-composition invariance, reading-order sortedness."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ocr(ctx, det_blob, rec_blob):
+    from oar_ocr_b200 import ffi
+    from oar_ocr_b200.ocr import OAROCR, TextDetectionConfig, TextRecognitionConfig
+    det, rec = ffi.Model(ctx, det_blob), ffi.Model(ctx, rec_blob)
+    return OAROCR(ctx, det, rec, [""] * 18385, TextDetectionConfig(unclip_ratio=2.0), TextRecognitionConfig(), 8, 64)
+
+
+def _summary(results):
+    return [[(r.bounding_box.points.tobytes(), r.label_indices.tobytes(), r.detection_index) for r in res.text_regions]
+            for res in results]
+
+
+def test_960_pages_match_oracle(ocr, det_blob, rec_blob):
+    """configs[1] shape, 3 pages: boxes and CTC label sequences identical to the CPU oracle, confidences within 1e-3"""
+    from oar_ocr_b200 import synth
+    from oracle import pipeline
+    from oracle.net import OracleNet
+    pages = [synth.page(200 + i, 960) for i in range(3)]
+    ocr.image_batch_size, ocr.region_batch_size = 8, 64
+    got = ocr.predict(pages)
+    want = pipeline.predict(OracleNet(det_blob), OracleNet(rec_blob), pages, 18385, image_batch_size=8,
+                            region_batch_size=64)
+    n = 0
+    for g, w in zip(got, want):
+        assert len(g.text_regions) == len(w)
+        for r, o in zip(g.text_regions, w):
+            assert np.array_equal(r.bounding_box.points, o["box"])
+            assert np.array_equal(r.label_indices, o["labels"])
+            assert abs(r.confidence - o["score"]) <= TOL
+            n += 1
+    assert n >= 100
+
+
+def test_full_batch_properties(ocr):
+    """32 x 960x960 (the bench workload): deterministic, engine-independent, batch-size independent for detection"""
+    from oar_ocr_b200 import synth
+    pages = [synth.page(300 + i, 960) for i in range(32)]
+    ocr.image_batch_size, ocr.region_batch_size = 32, 256
+    a = ocr.predict(pages)
+    b = ocr.predict(pages)
+    assert _summary(a) == _summary(b)  # run-to-run determinism (no atomics-order dependence in results)
+    scores_a = [[r.confidence for r in res.text_regions] for res in a]
+    scores_b = [[r.confidence for r in res.text_regions] for res in b]
+    assert scores_a == scores_b
+    total = sum(len(r.text_regions) for r in a)
+    assert total >= 32 * 30
+    # reading order: detection_index ascending, and sort_quad_boxes' invariant: never a box that is on the same line
+    # (|dy| < 10) yet further left than its predecessor
+    for res in a:
+        idx = [r.detection_index for r in res.text_regions]
+        assert idx == sorted(idx)
+        for p, q in zip(res.text_regions, res.text_regions[1:]):
+            if q.detection_index == p.detection_index + 1:
+                py, qy = p.bounding_box.y_min(), q.bounding_box.y_min()
+                assert not (abs(qy - py) < 10.0 and q.bounding_box.x_min() < p.bounding_box.x_min())
+    # fp32 SIMT engine vs tensor-core engine: same boxes, same labels
+    ocr.det.set_engine(0)
+    ocr.rec.set_engine(0)
+    try:
+        c = ocr.predict(pages[:8])
+    finally:
+        ocr.det.set_engine(1)
+        ocr.rec.set_engine(1)
+    ocr.image_batch_size = 8
+    d = ocr.predict(pages[:8])
+    # detection of an image does not depend on its batch mates: boxes of the 8-page call equal those of the 32-page call
+    for x, y in zip(d, a[:8]):
+        assert [r.bounding_box.points.tobytes() for r in x.text_regions] == \
+               [r.bounding_box.points.tobytes() for r in y.text_regions]
+    for x, y in zip(c, d):
+        assert [r.bounding_box.points.tobytes() for r in x.text_regions] == \
+               [r.bounding_box.points.tobytes() for r in y.text_regions]
+    ocr.region_batch_size = 256
+    c2 = _summary(c)
+    d2 = _summary(d)
+    assert c2 == d2
+
+
+def test_rec_512_crops(ocr, rec_blob):
+    """configs[2]: 512 crops of 48x320 as ONE batch (TextRecognitionPredictor semantics)"""
+    from oar_ocr_b200 import synth
+    from oracle import pipeline
+    from oracle.net import OracleNet
+    crops = [synth.crop(j, 48, 320) for j in range(512)]
+    r = ocr.rec.rec_run(crops, 18385)
+    assert r["T"] == 40 and len(r["labels"]) == 512
+    # same-width crops: a crop's result is independent of the batch it is in
+    parts = [ocr.rec.rec_run(crops[s:s + 64], 18385) for s in range(0, 512, 64)]
+    labels = [l for p in parts for l in p["labels"]]
+    scores = np.concatenate([p["scores"] for p in parts])
+    assert all(np.array_equal(a, b) for a, b in zip(r["labels"], labels))
+    assert np.array_equal(r["scores"], scores)
+    # oracle on the first 24 crops
+    want = pipeline.rec_forward(OracleNet(rec_blob), crops[:24], 18385)
+    assert all(np.array_equal(a, b) for a, b in zip(r["labels"][:24], want["labels"]))
+    assert np.abs(r["scores"][:24] - want["scores"]).max() <= TOL
+    assert sum(len(l) for l in r["labels"]) > 512
