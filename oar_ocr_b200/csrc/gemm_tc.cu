@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
   // first two k-blocks of A into registers, B(0) straight into stage 0 (all in flight during the set-up below)
   ARegs<KC> pre0, pre1;
   load_a<KC, A_MODE>(p, 0, chunk, rows, pre0);
-  if (P.nkb > 1) load_a<KC, A_MODE>(p, 1, chunk, rows, pre1);
+  if (KC == 4 && P.nkb > 1) load_a<KC, A_MODE>(p, 1, chunk, rows, pre1);  // KC = 8 tiles have a single k-block
   {
     const uint32_t b_dst = smem_u32(smem + 2 * a_part);
     for (int i = tid; i < nvec_b; i += TC_THREADS) cp_async16(b_dst + i * 16, wtile + i);
@@ -450,9 +450,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       umma_commit(smem_u32(&mbar[s]));
     }
   };
-  for (int kb = 0; kb < P.nkb; kb += 2) {
-    step(kb, pre0);
-    if (kb + 1 < P.nkb) step(kb + 1, pre1);
+  if (KC == 4) {
+    for (int kb = 0; kb < P.nkb; kb += 2) {
+      step(kb, pre0);
+      if (kb + 1 < P.nkb) step(kb + 1, pre1);
+    }
+  } else {
+    for (int kb = 0; kb < P.nkb; ++kb) step(kb, pre0);  // nkb == 1 by construction: no second register set
   }
   // all MMAs done when the last commit lands (a commit tracks every prior tcgen05 op of the issuing thread)
   {
