@@ -17,8 +17,10 @@
 //      (8 lanes probe the 8-neighbourhood per step), appending points to a global pool;
 //   3. contour records are radix-sorted by (image, start pixel) = discovery order, which also
 //      implements the `take(max_candidates)` cut;
-//   4. one thread per candidate does the small sequential geometry in the reference's own f32
-//      operation order (row sums of box_score_fast are accumulated left-to-right, rows in order);
+//   4. one warp per candidate does the geometry in the reference's own f32 operation order: lane 0 walks the
+//      strictly sequential pieces (chain simplification, hull march, unclip), the lanes share box_score_fast
+//      (whole-row partial sums, folded in row order), the Graham-scan sort (stable rank sort) and the
+//      min-area-rectangle search (first strictly smaller edge wins);
 //   5. survivors are compacted in discovery order.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -178,19 +180,23 @@ __constant__ int c_RY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 // (dx+1) + 3*(dy+1) -> ring index
 __constant__ int c_DIR[9] = {1, 2, 3, 0, -1, 4, 7, 6, 5};
 
-// Follows one border from (sx,sy).  start_dir = ring index of the adjacent zero pixel.
-// All 32 lanes execute; lanes 0..7 probe.  When pts != nullptr, writes points and the
-// visited marks (2 = +nbd, 3 = -nbd).  Returns the number of points.
-__device__ int follow_border(uint8_t* st, int W, int H, int sx, int sy, int start_dir, short2* pts, int lane) {
-  auto nonzero = [&](int x, int y) -> bool { return x >= 0 && y >= 0 && x < W && y < H && st[(size_t)y * W + x] != 0; };
+// Follows one border from (sx,sy) inside the window `st` (bw x bh pixels, row stride `stride`, window origin
+// (ox,oy) in image coordinates; Wimg = image width for the right-edge rule).  start_dir = ring index of the adjacent
+// zero pixel.  All 32 lanes execute; lanes 0..7 probe.  When pts != nullptr, writes points (image coordinates) and
+// the visited marks (2 = +nbd, 3 = -nbd).  Returns the number of points.
+__device__ int follow_border(uint8_t* st, int stride, int bw, int bh, int ox, int oy, int Wimg, int sx, int sy,
+                             int start_dir, short2* pts, int lane) {
+  auto nonzero = [&](int x, int y) -> bool {
+    return x >= 0 && y >= 0 && x < bw && y < bh && st[(size_t)y * stride + x] != 0;
+  };
   int k = lane & 7;
   int d = (start_dir + k) & 7;
   bool hit = (lane < 8) && nonzero(sx + c_RX[d], sy + c_RY[d]);
   unsigned mask = __ballot_sync(0xffffffffu, hit) & 0xffu;
   if (!mask) {
     if (pts && lane == 0) {
-      pts[0] = make_short2((short)sx, (short)sy);
-      st[(size_t)sy * W + sx] = 3;
+      pts[0] = make_short2((short)(sx + ox), (short)(sy + oy));
+      st[(size_t)sy * stride + sx] = 3;
     }
     return 1;
   }
@@ -200,7 +206,7 @@ __device__ int follow_border(uint8_t* st, int W, int H, int sx, int sy, int star
   int p2x = p1x, p2y = p1y, p3x = sx, p3y = sy;
   int n = 0;
   for (;;) {
-    if (pts && lane == 0) pts[n] = make_short2((short)p3x, (short)p3y);
+    if (pts && lane == 0) pts[n] = make_short2((short)(p3x + ox), (short)(p3y + oy));
     ++n;
     int front = c_DIR[(p2x - p3x + 1) + 3 * (p2y - p3y + 1)];
     int dk = (front - 1 - k + 16) & 7;  // k = 7 -> front itself (examined last)
@@ -212,8 +218,8 @@ __device__ int follow_border(uint8_t* st, int W, int H, int sx, int sy, int star
     int kE = (front - 5 + 16) & 7;  // the probe index that looks East
     bool right_edge = kE < k4;
     if (pts && lane == 0) {
-      size_t o = (size_t)p3y * W + p3x;
-      if (p3x + 1 == W || right_edge)
+      size_t o = (size_t)p3y * stride + p3x;
+      if (p3x + ox + 1 == Wimg || right_edge)
         st[o] = 3;
       else if (st[o] == 1)
         st[o] = 2;
@@ -225,64 +231,103 @@ __device__ int follow_border(uint8_t* st, int W, int H, int sx, int sy, int star
   return n;
 }
 
-__global__ void __launch_bounds__(128) db_trace_kernel(uint8_t* __restrict__ state, const int32_t* __restrict__ lab,
-                                                       const Comp* __restrict__ comps, const int* __restrict__ n_comps,
-                                                       int comp_cap, int H, int W, short2* __restrict__ pool,
-                                                       unsigned long long* __restrict__ pool_used,
-                                                       unsigned long long pool_cap, ContourRec* __restrict__ recs,
-                                                       int* __restrict__ n_recs, int rec_cap, int* __restrict__ err) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int nc = min(*n_comps, comp_cap);
-  if (warp >= nc) return;
-  Comp c = comps[warp];
-  size_t HW = (size_t)H * W;
-  uint8_t* st = state + (size_t)c.img * HW;
-  const int32_t* L = lab + (size_t)c.img * HW;
-  int y0 = c.root / W;
-  for (int y = y0; y <= c.ymax; ++y) {
-    for (int xb = c.xmin; xb <= c.xmax; xb += 32) {
-      int x = xb + lane;
-      bool cand = false;
-      if (x <= c.xmax) {
-        size_t o = (size_t)y * W + x;
-        if (st[o] != 0 && L[o] == c.root) {
-          bool wz = (x > 0) && st[o - 1] == 0;
-          bool ez = (x + 1 < W) && st[o + 1] == 0;
-          cand = wz || ez;
+// One block per component (grid-stride when there are more components than blocks).  All four warps stage the
+// component's bounding box plus a one-pixel ring into shared memory as a membership mask (1 = pixel of THIS
+// component, everything else 0 -- other components are never 8-adjacent, so the borders are unchanged); warp 0 then
+// replays the raster scan and walks the borders in shared memory, where every probe costs ~30 cycles instead of an
+// L2 round trip.  The visited marks live only in that copy.  Components whose window does not fit walk the global
+// state map directly (warp 0 only).
+constexpr int TRACE_TILE_BYTES = 16 * 1024;  // ~14 blocks per SM: the walk is serial per component, concurrency is what counts
+constexpr int TRACE_THREADS = 128;
+
+__global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
+    uint8_t* __restrict__ state, const int32_t* __restrict__ lab, const Comp* __restrict__ comps,
+    const int* __restrict__ n_comps, int comp_cap, int H, int W, short2* __restrict__ pool,
+    unsigned long long* __restrict__ pool_used, unsigned long long pool_cap, ContourRec* __restrict__ recs,
+    int* __restrict__ n_recs, int rec_cap, int* __restrict__ err) {
+  extern __shared__ uint8_t tile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = min(*n_comps, comp_cap);
+  for (int comp = blockIdx.x; comp < nc; comp += gridDim.x) {
+    const Comp c = comps[comp];
+    const size_t HW = (size_t)H * W;
+    uint8_t* img = state + (size_t)c.img * HW;
+    const int32_t* L = lab + (size_t)c.img * HW;
+    const int y0 = c.root / W;
+    const int bw = c.xmax - c.xmin + 3, bh = c.ymax - y0 + 3;  // bounding box + ring
+    const bool staged = (size_t)bw * bh <= (size_t)TRACE_TILE_BYTES;
+    uint8_t* st;
+    int stride, ox, oy, ww, wh;
+    if (staged) {
+      ox = c.xmin - 1, oy = y0 - 1, stride = bw, ww = bw, wh = bh;
+      st = tile;
+      for (int ly = warp; ly < bh; ly += TRACE_THREADS / 32) {
+        const int gy = oy + ly;
+        const bool row_in = gy >= 0 && gy < H;
+        for (int lx = lane; lx < bw; lx += 32) {
+          const int gx = ox + lx;
+          uint8_t v = 0;
+          if (row_in && gx >= 0 && gx < W) {
+            const size_t o = (size_t)gy * W + gx;
+            v = (img[o] != 0 && L[o] == c.root) ? 1 : 0;
+          }
+          tile[ly * bw + lx] = v;
         }
       }
-      unsigned cm = __ballot_sync(0xffffffffu, cand);
-      while (cm) {
-        int l = __ffs(cm) - 1;
-        cm &= cm - 1;
-        int cx = xb + l;
-        size_t o = (size_t)y * W + cx;
-        uint8_t s = st[o];
-        int start_dir = -1;
-        if (s == 1 && cx > 0 && st[o - 1] == 0)
-          start_dir = 0;  // outer border, adjacent = West
-        else if ((s == 1 || s == 2) && cx + 1 < W && st[o + 1] == 0)
-          start_dir = 4;  // hole border, adjacent = East
-        if (start_dir < 0) continue;
-        int n = follow_border(st, W, H, cx, y, start_dir, nullptr, lane);
-        unsigned long long off = 0;
-        int ri = -1;
-        if (lane == 0) {
-          off = atomicAdd(pool_used, (unsigned long long)n);
-          ri = atomicAdd(n_recs, 1);
+    } else {
+      ox = 0, oy = 0, stride = W, ww = W, wh = H;
+      st = img;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      bool failed = false;
+      for (int y = y0; y <= c.ymax && !failed; ++y) {
+        for (int xb = c.xmin; xb <= c.xmax && !failed; xb += 32) {
+          const int x = xb + lane;
+          bool cand = false;
+          if (x <= c.xmax) {
+            const size_t lo = (size_t)(y - oy) * stride + (x - ox);
+            if (st[lo] != 0 && (staged || L[(size_t)y * W + x] == c.root)) {
+              const bool wz = (x > 0) && st[lo - 1] == 0;
+              const bool ez = (x + 1 < W) && st[lo + 1] == 0;
+              cand = wz || ez;
+            }
+          }
+          unsigned cm = __ballot_sync(0xffffffffu, cand);
+          while (cm) {
+            const int l = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int cx = xb + l;
+            const size_t lo = (size_t)(y - oy) * stride + (cx - ox);
+            const uint8_t s = st[lo];
+            int start_dir = -1;
+            if (s == 1 && cx > 0 && st[lo - 1] == 0)
+              start_dir = 0;  // outer border, adjacent = West
+            else if ((s == 1 || s == 2) && cx + 1 < W && st[lo + 1] == 0)
+              start_dir = 4;  // hole border, adjacent = East
+            if (start_dir < 0) continue;
+            const int n = follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, nullptr, lane);
+            unsigned long long off = 0;
+            int ri = -1;
+            if (lane == 0) {
+              off = atomicAdd(pool_used, (unsigned long long)n);
+              ri = atomicAdd(n_recs, 1);
+            }
+            off = __shfl_sync(0xffffffffu, off, 0);
+            ri = __shfl_sync(0xffffffffu, ri, 0);
+            if (off + n > pool_cap || ri >= rec_cap) {
+              if (lane == 0) atomicExch(err, 1);
+              failed = true;
+              break;
+            }
+            follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, lane);
+            if (lane == 0) recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
+            __syncwarp();
+          }
         }
-        off = __shfl_sync(0xffffffffu, off, 0);
-        ri = __shfl_sync(0xffffffffu, ri, 0);
-        if (off + n > pool_cap || ri >= rec_cap) {
-          if (lane == 0) atomicExch(err, 1);
-          return;
-        }
-        follow_border(st, W, H, cx, y, start_dir, pool + off, lane);
-        if (lane == 0) recs[ri] = ContourRec{c.img, (int)o, (long long)off, n};
-        __syncwarp();
       }
     }
+    __syncthreads();  // the tile is reused by this block's next component
   }
 }
 
@@ -481,66 +526,6 @@ __device__ __forceinline__ long long sat_usize_dev(float v) {
   return (long long)v;
 }
 
-// box_score_fast for a 4-point box (db_score.rs:34-134, geometry.rs:1087-1164)
-__device__ float box_score_fast_dev(const float* __restrict__ pred, int W, int H, const float bx[4], const float by[4]) {
-  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-  for (int i = 0; i < 4; ++i) {
-    if (bx[i] < mnx) mnx = bx[i];
-    if (bx[i] > mxx) mxx = bx[i];
-    if (by[i] < mny) mny = by[i];
-    if (by[i] > mxy) mxy = by[i];
-  }
-  float fminx = fminf(fmaxf(floorf(mnx), 0.0f), (float)W - 1.0f);
-  float fmaxx = fminf(fmaxf(ceilf(mxx), 0.0f), (float)W - 1.0f);
-  float fminy = fminf(fmaxf(floorf(mny), 0.0f), (float)H - 1.0f);
-  float fmaxy = fminf(fmaxf(ceilf(mxy), 0.0f), (float)H - 1.0f);
-  long long start_y = sat_usize_dev(fminy), end_y = sat_usize_dev(fmaxy) + 1;
-  long long start_x = sat_usize_dev(fminx), end_x = sat_usize_dev(fmaxx) + 1;
-  float total = 0.0f;
-  long long total_px = 0;
-  for (long long yy = start_y; yy < end_y; ++yy) {
-    float y = (float)yy + 0.5f;
-    float xs[4];
-    int nx = 0;
-    for (int i = 0; i < 4; ++i) {
-      int j = (i + 1) & 3;
-      float p1x = bx[i], p1y = by[i], p2x = bx[j], p2y = by[j];
-      if (((p1y <= y && y < p2y) || (p2y <= y && y < p1y)) && fabsf(p2y - p1y) > 1.1920929e-7f) {
-        xs[nx++] = p1x + (y - p1y) * (p2x - p1x) / (p2y - p1y);
-      }
-    }
-    for (int a = 1; a < nx; ++a) {  // stable insertion sort
-      float kx = xs[a];
-      int b = a - 1;
-      while (b >= 0 && xs[b] > kx) {
-        xs[b + 1] = xs[b];
-        --b;
-      }
-      xs[b + 1] = kx;
-    }
-    float line = 0.0f;
-    long long line_px = 0;
-    long long yi = sat_usize_dev(y);
-    if (yi < H) {
-      const float* row = pred + (size_t)yi * W;
-      for (int k = 0; k + 1 < nx; k += 2) {
-        long long x1 = sat_usize_dev(fmaxf(xs[k], (float)start_x));
-        long long x2 = sat_usize_dev(fminf(xs[k + 1], (float)end_x));
-        if (x1 < x2 && x1 >= start_x && x2 <= end_x) {
-          long long xe = x2 < W ? x2 : W;
-          if (x1 < xe) {
-            for (long long x = x1; x < xe; ++x) line += row[x];  // strictly left to right
-            line_px += xe - x1;
-          }
-        }
-      }
-    }
-    total += line;
-    total_px += line_px;
-  }
-  return total_px > 0 ? total / (float)total_px : 0.0f;
-}
-
 constexpr int UNCLIP_CAP = 768;
 
 // unclip (db_bitmap.rs:279-368): Clipper2 ClipperOffset, JoinType::Round, EndType::Polygon,
@@ -651,48 +636,6 @@ __device__ int unclip_dev(const float bx[4], const float by[4], float ratio, flo
   if (m > 1 && fabsf(ox[0] - ox[m - 1]) < 1.1920929e-7f && fabsf(oy[0] - oy[m - 1]) < 1.1920929e-7f) --m;
   if (m < 3) return 0;
   return m;
-}
-
-// convex_hull_from_points exactly as geometry.rs:226-274 (Graham scan with atan2 keys, stable
-// sort, pop while cross <= 0), in place on (x,y)[0..n); ang/dist are scratch.  Returns hull size.
-__device__ int graham_hull_inplace(float* x, float* y, int n, float* ang, float* dist) {
-  int s = 0;
-  for (int i = 1; i < n; ++i)
-    if (y[i] < y[s] || (y[i] == y[s] && x[i] < x[s])) s = i;
-  {
-    float tx = x[0], ty = y[0];
-    x[0] = x[s], y[0] = y[s];
-    x[s] = tx, y[s] = ty;
-  }
-  float spx = x[0], spy = y[0];
-  for (int i = 1; i < n; ++i) {
-    float dx = x[i] - spx, dy = y[i] - spy;
-    ang[i] = atan2f(dy, dx);
-    dist[i] = dx * dx + dy * dy;
-  }
-  for (int a = 2; a < n; ++a) {  // stable insertion sort on (ang total_cmp, dist total_cmp)
-    float kx = x[a], ky = y[a], ka = ang[a], kd = dist[a];
-    int b = a - 1;
-    while (b >= 1) {
-      int c = total_cmp_f32(ang[b], ka);
-      if (c == 0) c = total_cmp_f32(dist[b], kd);
-      if (c <= 0) break;
-      x[b + 1] = x[b], y[b + 1] = y[b], ang[b + 1] = ang[b], dist[b + 1] = dist[b];
-      --b;
-    }
-    x[b + 1] = kx, y[b + 1] = ky, ang[b + 1] = ka, dist[b + 1] = kd;
-  }
-  int h = 0;
-  for (int i = 0; i < n; ++i) {
-    float px = x[i], py = y[i];
-    while (h > 1) {
-      float cr = (x[h - 1] - x[h - 2]) * (py - y[h - 2]) - (y[h - 1] - y[h - 2]) * (px - x[h - 2]);
-      if (cr <= 0.0f) --h; else break;
-    }
-    x[h] = px, y[h] = py;
-    ++h;
-  }
-  return h;
 }
 
 struct Cand {
@@ -1055,7 +998,7 @@ DbPostStatus db_postprocess_device(oar_ctx* ctx, const float* pred, int B, int H
   int launch_comps = std::min(comp_cap, std::max(launch_comps_hint, std::max(4096, B * 2048)));
   {
     Launch l(ctx, "db_trace_borders", 0, 0);
-    db_trace_kernel<<<cdiv((long long)launch_comps * 32, 128), 128, 0, st>>>(
+    db_trace_kernel<<<std::min(launch_comps, 8192), TRACE_THREADS, TRACE_TILE_BYTES, st>>>(
         state, lab, comps, n_comps, launch_comps, H, W, pool, pool_used, pool_cap, recs, n_recs, rec_cap, err);
   }
   // sort contour records into discovery order

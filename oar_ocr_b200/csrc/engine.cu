@@ -429,15 +429,19 @@ __global__ void se_fc_kernel(const float* __restrict__ partial, const float* __r
     mean[c] = acc / (float)HW;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < Cm; j += blockDim.x) {
-    float acc = b1[j];
-    for (int c = 0; c < C; ++c) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
-    hid[j] = fmaxf(acc, 0.0f);
+  // one warp per hidden unit: lanes stride the (contiguous) weight row, butterfly-reduce
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Cm; j += nwarps) {
+    float acc = 0.0f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) hid[j] = fmaxf(acc + b1[j], 0.0f);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = b2[c];
-    for (int j = 0; j < Cm; ++j) acc = fmaf(w2[(size_t)c * Cm + j], hid[j], acc);
+    const float* wr = w2 + (size_t)c * Cm;
+    for (int j = 0; j < Cm; ++j) acc = fmaf(__ldg(wr + j), hid[j], acc);
     scale[(size_t)b * C + c] = fminf(fmaxf(acc * slope + offset, 0.0f), 1.0f);
   }
 }
@@ -517,6 +521,28 @@ __global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) acc += in[(((size_t)b * H + ho * sh + ky) * W + wo * sw + kx) * C + c];
   out[i] = acc / (float)(kh * kw);
+}
+
+// 4 channels per thread (C % 4 == 0)
+__global__ void avgpool4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W, int C4,
+                                int Ho, int Wo, int kh, int kw, int sh, int sw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4);
+  size_t r = i / C4;
+  int wo = (int)(r % Wo);
+  r /= Wo;
+  int ho = (int)(r % Ho);
+  int b = (int)(r / Ho);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      const float4 v = __ldg(in + (((size_t)b * H + ho * sh + ky) * W + wo * sw + kx) * C4 + c);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  const float d = (float)(kh * kw);
+  out[i] = make_float4(acc.x / d, acc.y / d, acc.z / d, acc.w / d);
 }
 
 // ---------------------------------------------------------------------------
@@ -755,7 +781,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         }
         {
           Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
-          se_fc_kernel<<<a.B, 128, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2),
+          se_fc_kernel<<<a.B, 256, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2),
                                                                     m->w(op, 3), scale, HW, c, cm, S, op.f[0], op.f[1]);
         }
         {
@@ -798,7 +824,12 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         int Ho = (a.H - kh) / sh + 1, Wo = (a.W - kw) / sw + 1;
         Tensor& o = ensure(op.out, a.B, Ho, Wo, a.C);
         Launch l(ctx, "avgpool", (double)a.numel(), 4.0 * (a.numel() + o.numel()));
-        avgpool_kernel<<<cdiv(o.numel(), 256), 256, 0, st>>>(a.p, o.p, a.B, a.H, a.W, a.C, Ho, Wo, kh, kw, sh, sw);
+        if ((a.C & 3) == 0)
+          avgpool4_kernel<<<cdiv(o.numel() / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p),
+                                                                    reinterpret_cast<float4*>(o.p), a.B, a.H, a.W,
+                                                                    a.C / 4, Ho, Wo, kh, kw, sh, sw);
+        else
+          avgpool_kernel<<<cdiv(o.numel(), 256), 256, 0, st>>>(a.p, o.p, a.B, a.H, a.W, a.C, Ho, Wo, kh, kw, sh, sw);
         break;
       }
       case OP_LAYERNORM: {

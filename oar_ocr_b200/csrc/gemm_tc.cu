@@ -118,23 +118,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46);
 }
 
-__device__ __forceinline__ float tc_act(float v, int act) {
-  switch (act) {
-    case ACT_RELU:
-      return fmaxf(v, 0.0f);
-    case ACT_HSWISH:
-      return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f;
-    case ACT_SWISH:
-      return v / (1.0f + expf(-v));
-    case ACT_SIGMOID:
-      return 1.0f / (1.0f + expf(-v));
-    case ACT_HSIGMOID:
-      return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
-    default:
-      return v;
-  }
-}
-
 // split 8 floats into hi / lo fp16 vectors (x ~= hi + lo, |x - hi - lo| <= 2^-22 |x|)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   __half2 h[4], l[4];
