@@ -24,6 +24,7 @@
 //       post-affine, then NHWC stores staged through shared memory so every store is a whole 128-byte row segment
 //       (conv), 2x2 scatter (transposed conv) or an online softmax/arg-max reduction (CTC head: the [B,T,V] logits
 //       never reach HBM).
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include <map>
@@ -138,6 +139,7 @@ struct TcParams {
   const uint4* wpk;
   int BN, nkb, n_tiles, tmem_cols, stages;
   uint32_t ctrl_off;  // byte offset of the mbarriers / TMEM slot behind the stages (and the epilogue staging tile)
+  int tma_out;        // 1: the conv epilogue stores through the TMA tensor map passed next to these parameters
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
@@ -321,9 +323,83 @@ __device__ __forceinline__ void epi_conv_store(const ConvParams& p, uint8_t* sme
   }
 }
 
+// Conv epilogue through TMA: bias + activation in registers, 128 x 32 fp32 staging tiles in shared memory in the
+// 128-byte-swizzled layout the tensor map describes (16-byte chunk index XOR row % 8: conflict-free for the
+// row-per-thread writes), then ONE cp.async.bulk.tensor store per tile issued by one thread.  The TMA engine clips
+// the box at the tensor bounds (rows >= M or pixels >= W, columns >= N), so no per-element predicates remain, and the
+// global store costs no LSU instructions at all.  Two staging tiles alternate so the store of one group overlaps the
+// TMEM reads of the next.  c1/c2 = tensor coordinates of the tile's first row.
+template <int ACT>
+__device__ __forceinline__ void epi_conv_store_tma(const ConvParams& p, const CUtensorMap* tm, uint8_t* smem,
+                                                   uint32_t lane_base, int BN, int n_base, int c1, int c2, int rank3,
+                                                   int tid) {
+  const int row = tid & (TC_BM - 1), half = tid >> 7;
+  const float ps = p.post_scale, pb = p.post_bias;
+  const bool affine = ps != 1.0f || pb != 0.0f;
+  int buf = 0;
+  for (int c0 = 0; c0 < BN; c0 += 32, buf ^= 1) {
+    if (n_base + c0 >= p.N) break;
+    uint8_t* ep = smem + buf * (TC_BM * 128);
+    const int cc = c0 + 16 * half;
+    if (cc < BN && n_base + cc < p.N) {  // warp-uniform
+      float v[16];
+      tmem_ld16(lane_base + cc, v);
+      if (n_base + cc + 16 <= p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 b;
+          if ((n_base & 3) == 0)
+            b = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + cc + i));
+          else
+            b = make_float4(__ldg(p.bias + n_base + cc + i), __ldg(p.bias + n_base + cc + i + 1),
+                            __ldg(p.bias + n_base + cc + i + 2), __ldg(p.bias + n_base + cc + i + 3));
+          v[i] = act_t<ACT>(v[i] + b.x);
+          v[i + 1] = act_t<ACT>(v[i + 1] + b.y);
+          v[i + 2] = act_t<ACT>(v[i + 2] + b.z);
+          v[i + 3] = act_t<ACT>(v[i + 3] + b.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int n = n_base + cc + i;
+          v[i] = n < p.N ? act_t<ACT>(v[i] + __ldg(p.bias + n)) : 0.0f;
+        }
+      }
+      if (affine) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * ps + pb;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c16 = 4 * half + i;  // 16-byte chunk of this row
+        *reinterpret_cast<float4*>(ep + row * 128 + ((c16 ^ (row & 7)) << 4)) =
+            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t src = smem_u32(ep);
+      if (rank3)
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm),
+                     "r"(n_base + c0), "r"(c1), "r"(c2), "r"(src)
+                     : "memory");
+      else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm),
+                     "r"(n_base + c0), "r"(c1), "r"(src)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the buffer written two groups ago must have been read out before the next group reuses it
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA retires
+}
+
 template <int KC, int A_MODE, int EPI>
-__global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P, const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // 1024: the swizzled TMA staging tiles start at offset 0
   constexpr int BK = KC * 8;
   using G = AGeo<KC>;
   const ConvParams& p = P.c;
@@ -490,7 +566,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc(const TcParams P) {
       p.part_sum[o] = sum;
     }
   } else if (EPI < 8) {
-    epi_conv_store<EPI & 7>(p, smem, lane_base, BN, n_base, m0, min(TC_BM, p.M - m0), tid);
+    if (P.tma_out)
+      epi_conv_store_tma<EPI & 7>(p, &tm_out, smem, lane_base, BN, n_base, m0, 0, 0, tid);
+    else
+      epi_conv_store<EPI & 7>(p, smem, lane_base, BN, n_base, m0, min(TC_BM, p.M - m0), tid);
   } else {
     // 2x2 stride-2 transposed conv: column n = (dy*2+dx)*cout + co belongs to output pixel (2y+dy, 2x+dx).  For a
     // fixed dy the 2*cout columns of an input pixel are one contiguous run of the output row 2y+dy, and consecutive
@@ -573,8 +652,9 @@ constexpr uint32_t RT_LBO = AGeo<RT_KC>::LBO;
 static_assert(RT_LBO >= (TC_BM + RT_MAX_KW - 1) * 16, "chunk stride must hold the halo rows");
 
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS) conv_rowtaps_tc(const TcParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(TC_THREADS) conv_rowtaps_tc(const TcParams P,
+                                                              const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams& p = P.c;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int BN = P.BN, kw = p.kw;
@@ -700,7 +780,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_rowtaps_tc(const TcParams P) 
     tc_fence_after();
   }
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  epi_conv_store<EPI & 7>(p, smem, lane_base, BN, nt * BN, m0, nrows, tid);
+  if (P.tma_out)  // 3-D map [N][Wo][B*Ho]: the box is clipped at the end of the image row
+    epi_conv_store_tma<EPI & 7>(p, &tm_out, smem, lane_base, BN, nt * BN, w0, b * p.Ho + h, 1, tid);
+  else
+    epi_conv_store<EPI & 7>(p, smem, lane_base, BN, nt * BN, m0, nrows, tid);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
@@ -738,7 +821,7 @@ static TcWeights pack_weights(const float* w, int N, int K) {
   t.N = N, t.K = K;
   t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
-  t.BN = std::max(16, (per + 15) / 16 * 16);
+  t.BN = t.n_tiles > 1 ? (per + 31) / 32 * 32 : std::max(16, (per + 15) / 16 * 16);
   t.KC = (K > 32 && K <= 64) ? 8 : 4;  // 64-wide single stage for 32 < K <= 64; otherwise 32-wide double-buffered
   const int TC_KC = t.KC, TC_BK = t.KC * 8;
   t.nkb = (K + TC_BK - 1) / TC_BK;
@@ -773,7 +856,7 @@ static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int
   t.N = N, t.K = kh * kw * Cin, t.rowtaps = true, t.kh = kh, t.kw = kw, t.KC = 4;
   t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
-  t.BN = std::max(16, (per + 15) / 16 * 16);
+  t.BN = t.n_tiles > 1 ? (per + 31) / 32 * 32 : std::max(16, (per + 15) / 16 * 16);
   const int ncb = Cin / 32;
   t.nkb = kh * ncb;
   const size_t part = (size_t)4 * t.BN * 8;  // halfs of one (hi or lo) part
@@ -852,6 +935,35 @@ int tc_n_tiles(const oar_model* m, int key) {
   return 2 * it->second.n_tiles;
 }
 
+// ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tmap_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr)
+      OAR_FAIL(OAR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// fp32 output map with 32-column x 128-row boxes, 128-byte swizzle.  rank 2: [N][M]; rank 3: [N][Wo][B*Ho].
+static bool make_out_map(CUtensorMap* tm, float* base, int N, int out_ld, long long d1, long long d2, int rank) {
+  if ((out_ld & 3) || (((uintptr_t)base) & 15)) return false;  // TMA needs 16-byte aligned base and strides
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)out_ld * 4, (cuuint64_t)out_ld * 4 * (cuuint64_t)d1};
+  cuuint32_t box[3] = {32, TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   TcState* st = static_cast<TcState*>(m->tc_state);
   if (!st) return false;
@@ -873,7 +985,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   if (w.rowtaps) {
     if (!aligned || p.mode != 0 || p.kh != w.kh || p.kw != w.kw || p.sh != 1 || p.sw != 1 || p.Ho != p.H || p.Wo != p.W)
       OAR_FAIL(OAR_E_MODEL, "row-taps weights for op key %d do not match its convolution", key);
-    using KernRT = void (*)(const TcParams);
+    using KernRT = void (*)(const TcParams, const CUtensorMap);
     KernRT krt = nullptr;
     switch (p.act) {
       case ACT_NONE: krt = conv_rowtaps_tc<0>; break;
@@ -884,7 +996,10 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
       default: return false;
     }
     size_t smem_rt = (size_t)P.stages * (2 * (size_t)RT_KC * RT_LBO + (size_t)w.kw * 2 * RT_KC * w.BN * 16);
-    if (smem_rt < (size_t)EP_BYTES) smem_rt = EP_BYTES;
+    if (smem_rt < (size_t)2 * TC_BM * 128) smem_rt = 2 * TC_BM * 128;  // two TMA staging tiles
+    CUtensorMap tm_rt;
+    memset(&tm_rt, 0, sizeof(tm_rt));
+    P.tma_out = make_out_map(&tm_rt, p.out + p.out_c_off, p.N, p.out_ld, p.Wo, (long long)p.B * p.Ho, 3) ? 1 : 0;
     P.ctrl_off = (uint32_t)smem_rt;
     smem_rt += 64;
     {
@@ -898,7 +1013,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
     const int segs = (p.Wo + TC_BM - 1) / TC_BM;
     dim3 grid_rt((unsigned)(p.B * p.Ho * segs), w.n_tiles);
     Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + 4.0 * (double)p.M * p.N);
-    krt<<<grid_rt, TC_THREADS, smem_rt, m->ctx->stream>>>(P);
+    krt<<<grid_rt, TC_THREADS, smem_rt + 1024, m->ctx->stream>>>(P, tm_rt);
     return true;
   }
   int a_mode = AM_SCALAR;
@@ -907,7 +1022,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   else if ((p.Cin % 8) == 0 && aligned)
     a_mode = AM_TAPS;
   const int epi = p.mode == 2 ? EPI_CTC : p.mode * 8 + p.act;
-  using Kern = void (*)(const TcParams);
+  using Kern = void (*)(const TcParams, const CUtensorMap);
   Kern kern = nullptr;
 #define TC_PICK(KCV, AM, EP) \
   if (w.KC == KCV && a_mode == AM && epi == EP) kern = conv_gemm_tc<KCV, AM, EP>;
@@ -926,7 +1041,13 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   if (p.mode == 2 && (w.BN & 31)) return false;
   const size_t a_part_bytes = w.KC == 8 ? AGeo<8>::PART : AGeo<4>::PART;
   size_t smem = (size_t)P.stages * (2 * a_part_bytes + 2 * (size_t)w.KC * w.BN * 16);
-  if (smem < (size_t)EP_BYTES) smem = EP_BYTES;  // the conv epilogue stages 128 x 32 outputs through shared memory
+  if (smem < (size_t)2 * TC_BM * 128) smem = 2 * TC_BM * 128;  // the conv epilogue stages outputs through shared memory
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  P.tma_out = 0;
+  // single-tile layers may have any BN; multi-tile layers need whole 32-column boxes inside a tile
+  if (p.mode == 0 && (w.n_tiles == 1 || (w.BN & 31) == 0))
+    P.tma_out = make_out_map(&tm, p.out + p.out_c_off, p.N, p.out_ld, p.M, 1, 2) ? 1 : 0;
   P.ctrl_off = (uint32_t)smem;
   smem += 64;
   {
@@ -940,7 +1061,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
   dim3 grid(cdiv(p.M, TC_BM), w.n_tiles);
   double out_bytes = p.mode == 2 ? 24.0 * p.M * w.n_tiles : 4.0 * (double)p.M * p.N;
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + out_bytes);
-  kern<<<grid, TC_THREADS, smem, m->ctx->stream>>>(P);
+  kern<<<grid, TC_THREADS, smem + 1024, m->ctx->stream>>>(P, tm);
   return true;
 }
 
