@@ -87,7 +87,8 @@ int32_t oar_ctx_synchronize(oar_ctx* ctx);
 int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_model** out);
 void oar_model_destroy(oar_model* m);
 int32_t oar_model_kind(const oar_model* m);
-/* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine (default where available) */
+/* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine (one kernel per layer), 2 = tcgen05 engine with the
+ * depthwise->pointwise blocks fused into one persistent kernel (default) */
 int32_t oar_model_set_engine(oar_model* m, int32_t engine);
 
 /* ---- seam 1: OrtInfer::infer / infer_first_output_f32 --------------------

@@ -19,6 +19,7 @@ SOURCES = {
     "capi.cu": [],
     "engine.cu": [],
     "gemm_tc.cu": [],
+    "fused_tc.cu": [],
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
 }

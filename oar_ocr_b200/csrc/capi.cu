@@ -578,7 +578,7 @@ int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_mod
     delete m;
     OAR_FAIL(OAR_E_CUDA, "weight upload failed: %s", cudaGetErrorString(e));
   }
-  m->engine = 1;
+  m->engine = 2;
   tc_model_init(m);
   *out = m;
   API_CATCH
@@ -596,7 +596,7 @@ void oar_model_destroy(oar_model* m) {
 int32_t oar_model_kind(const oar_model* m) { return m ? m->kind : OAR_E_INVALID; }
 
 int32_t oar_model_set_engine(oar_model* m, int32_t engine) {
-  if (!m || engine < 0 || engine > 1) {
+  if (!m || engine < 0 || engine > 2) {
     set_error("invalid engine selector");
     return OAR_E_INVALID;
   }

@@ -8,6 +8,8 @@
 // tensor-core engine (gemm_tc.cu), which overrides the GEMM-shaped ops.
 #include "engine.cuh"
 
+#include <cstdlib>
+
 namespace oar {
 
 // ---------------------------------------------------------------------------
@@ -222,7 +224,7 @@ static bool try_stem_conv(oar_ctx* ctx, const ConvParams& p) {
 
 // engine dispatch: tensor-core kernel when the model runs engine 1 and has packed weights for `key`
 static void launch_gemm(oar_model* m, int key, const ConvParams& p, const char* name_simt, const char* name_tc) {
-  if (m->engine == 1 && tc_gemm(m, key, p, name_tc)) return;
+  if (m->engine >= 1 && tc_gemm(m, key, p, name_tc)) return;
   launch_conv_simt(m->ctx, p, name_simt);
 }
 
@@ -718,10 +720,55 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
     }
     return x;
   };
+  // readers per tensor: an intermediate may be fused away only if exactly one op consumes it
+  std::vector<int> uses(m->n_tensors, 0);
+  for (const OpRec& o : m->ops) {
+    ++uses[o.in0];
+    if (o.in1 >= 0) ++uses[o.in1];
+  }
+  auto is_pw = [](const OpRec& o) {
+    return o.type == OP_CONV && o.p[0] == 1 && o.p[1] == 1 && o.p[2] == 1 && o.p[3] == 1 && o.p[4] == 0 && o.p[5] == 0;
+  };
+  static const bool fuse_plain_pw = getenv("OAR_FUSED_PW") && atoi(getenv("OAR_FUSED_PW")) != 0;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const OpRec& op = m->ops[oi];
     const Tensor& a = t[op.in0];
     if (!a.p) OAR_FAIL(OAR_E_MODEL, "op %zu reads undefined tensor %d", oi, op.in0);
+    if (m->engine == 2) {
+      // [depthwise -> 1x1] and [depthwise -> squeeze-excite -> 1x1] blocks on the fused persistent kernel
+      const bool dw_ok = op.type == OP_DWCONV && op.p[0] == op.p[1] && (op.p[0] == 3 || op.p[0] == 5) &&
+                         op.p[4] == op.p[0] / 2 && op.p[5] == op.p[0] / 2 && a.C == op.p[6] && uses[op.out] == 1;
+      auto fill_pw = [&](FusedBlock& f, const OpRec& pw, Tensor& o) {
+        f.bias = m->w(pw, 1), f.act = pw.p[8], f.ps = pw.f[0], f.pb = pw.f[1], f.N = pw.p[7];
+        f.out = o.p, f.out_ld = o.C, f.out_c_off = pw.p[11] ? pw.p[10] : 0, f.Ho = o.H, f.Wo = o.W;
+      };
+      if (dw_ok && oi + 1 < m->ops.size() && is_pw(m->ops[oi + 1]) && m->ops[oi + 1].in0 == op.out &&
+          m->ops[oi + 1].p[6] == a.C) {
+        const OpRec& pw = m->ops[oi + 1];
+        const int k = op.p[0], sh = op.p[2], sw = op.p[3];
+        const int Ho = conv_out(a.H, k, sh, k / 2), Wo = conv_out(a.W, k, sw, k / 2);
+        Tensor& o = ensure(pw.out, a.B, Ho, Wo, pw.p[11] ? pw.p[11] : pw.p[7]);
+        FusedBlock f{};
+        f.in = a.p, f.B = a.B, f.H = a.H, f.W = a.W, f.C = a.C, f.k = k, f.sh = sh, f.sw = sw;
+        f.dw_w = m->w(op, 0), f.dw_b = m->w(op, 1), f.dw_act = op.p[7], f.dw_ps = op.f[0], f.dw_pb = op.f[1];
+        fill_pw(f, pw, o);
+        if (tc_fused_block(m, (int)(oi + 1) * 2, f, k == 3 ? "lcblock3_tc" : "lcblock5_tc")) {
+          last = o;
+          ++oi;
+          continue;
+        }
+      }
+      if (is_pw(op) && a.C == op.p[6] && fuse_plain_pw) {
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, op.p[11] ? op.p[11] : op.p[7]);
+        FusedBlock f{};
+        f.in = a.p, f.B = a.B, f.H = a.H, f.W = a.W, f.C = a.C;
+        fill_pw(f, op, o);
+        if (tc_fused_block(m, (int)oi * 2, f, "pwconv_tc")) {
+          last = o;
+          continue;
+        }
+      }
+    }
     switch (op.type) {
       case OP_CONV: {
         int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3], ph = op.p[4], pw = op.p[5], cin = op.p[6],
@@ -737,7 +784,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.N = cout, p.K = kh * kw * cin, p.M = a.B * Ho * Wo;
         p.out_ld = ctot, p.out_c_off = coff, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
         p.mode = 0, p.cout = cout;
-        if (m->engine == 1 && try_stem_conv(ctx, p)) break;
+        if (m->engine >= 1 && try_stem_conv(ctx, p)) break;
         launch_gemm(m, (int)oi * 2, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt",
                     (kh == 1 && kw == 1) ? "conv1x1_tc" : "convkxk_tc");
         break;
@@ -872,7 +919,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         {
           // tensor-core engine, results only: the head GEMM keeps the logits in TMEM and its epilogue reduces each
           // 128 x BN tile to (max, last arg-max, sum exp); a small combine kernel finishes the softmax-max.
-          int nt = (m->engine == 1 && !want_probs) ? tc_n_tiles(m, (int)oi * 2) : 0;
+          int nt = (m->engine >= 1 && !want_probs) ? tc_n_tiles(m, (int)oi * 2) : 0;
           if (nt > 0) {
             CtcOut local;
             CtcOut* co = ctc ? ctc : &local;

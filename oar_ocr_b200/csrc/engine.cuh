@@ -56,6 +56,25 @@ struct ConvParams {
   float* part_sum;
 };
 
+// One PP-LCNetV3 block for the fused tensor-core kernel (fused_tc.cu): [depthwise k x k -> act] -> 1x1 conv -> act.
+// k == 0: no depthwise stage (plain 1x1 conv), optionally with a squeeze-excite multiplier on its input.
+struct FusedBlock {
+  const float* in;  // NHWC input of the depthwise conv (k > 0) or of the 1x1 conv (k == 0)
+  int B, H, W, C;
+  int k, sh, sw;  // depthwise kernel size (square, pad k/2) and strides
+  const float* dw_w;
+  const float* dw_b;
+  int dw_act;
+  float dw_ps, dw_pb;
+  const float* se_scale;  // k == 0 only: [B][C] multiplier or null
+  const float* bias;      // 1x1 conv
+  int act;
+  float ps, pb;
+  int N;
+  float* out;
+  int out_ld, out_c_off, Ho, Wo;
+};
+
 // Output of the fused CTC head: per (b,t) argmax class and its softmax prob.
 struct CtcOut {
   int32_t* idx = nullptr;
@@ -68,7 +87,7 @@ struct CtcOut {
 struct oar_model {
   oar_ctx* ctx = nullptr;
   int kind = 0;
-  int engine = 0;
+  int engine = 0;  // 0 fp32 SIMT, 1 tcgen05 per layer, 2 tcgen05 with fused depthwise->pointwise blocks
   int n_tensors = 0;
   std::vector<oar::OpRec> ops;
   float* d_weights = nullptr;  // all weights, fp32, resident in HBM
@@ -95,6 +114,9 @@ void tc_model_free(oar_model* m);
 bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name);
 // number of N tiles the tensor-core engine uses for `key` (0 if absent); sizes the mode-2 partials
 int tc_n_tiles(const oar_model* m, int key);
+// Fused block on the persistent tcgen05 kernel (fused_tc.cu); false if the shape is not supported (caller falls back to
+// the per-layer kernels).  `key` names the 1x1 conv's packed weights.
+bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name);
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
                         int n_tiles, int32_t* idx, float* prob);
 

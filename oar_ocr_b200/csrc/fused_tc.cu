@@ -1,0 +1,546 @@
+// fused_tc.cu -- PP-LCNetV3 block as ONE persistent, warp-specialised tcgen05 kernel (sm_100a).
+//
+// Both networks on the hot path are stacks of [depthwise k x k conv -> activation -> 1x1 conv -> activation]
+// (oar_ocr_b200/models.py:_lcnet_block; in the reference the same graph runs inside ONNX Runtime,
+// oar-ocr-core/src/core/inference/ort_infer_execution.rs:178,281).  Run as two kernels the depthwise output makes a
+// round trip through HBM (4*C bytes written + 4*C read per pixel) although both layers are bandwidth-bound.  Here the
+// depthwise result never leaves the SM: it is produced straight into the shared-memory A operand of the pointwise
+// GEMM.  The same kernel with K = 0 is a plain (optionally squeeze-excite-scaled) 1x1 convolution.
+//
+// One CTA per SM, persistent over (pixel tile, N tile) work items, 14 warps in four roles connected by mbarriers:
+//   warp 4   TMA producer.  Per 32-channel k-block: one cp.async.bulk.tensor box of the fp32 NHWC input
+//            ([32 ch] x [tile + halo]; out-of-bounds rows/columns/channels are zero-filled by the TMA unit, which IS
+//            the convolution's zero padding) into a 3-4 deep ring, plus one linear bulk copy of the pre-packed fp16
+//            hi/lo weight k-block.
+//   warps 6-13  depthwise / convert.  Thread = 2 channels x (2 x 4) output pixels: every input value is read once
+//            from shared memory into registers (LDS.64, one pixel's 128 bytes per half-warp: conflict-free) and
+//            reused by all taps (packed FFMA2), accumulating bias, then (ky, kx) ascending like the stand-alone
+//            kernel (engine.cu: dw_tile) so the values are bit-identical; activation; split x = hi + lo (fp16) and
+//            store into the K-major no-swizzle UMMA layout [k-chunk][row][8 halfs], double buffered.
+//   warp 5   MMA issuer.  One thread: 2 k16 steps x (hi*hi + hi*lo + lo*hi) tcgen05.mma.kind::f16 into a fp32 TMEM
+//            accumulator (two accumulators of 256 columns alternate between work items); tcgen05.commit releases
+//            the A/B stage and, after the last k-block, publishes the accumulator.
+//   warps 0-3  epilogue.  tcgen05.ld, bias + activation, 128-byte-swizzled staging tile, cp.async.bulk.tensor
+//            store (clipped at the image / channel bounds by the tensor map); overlaps the next item's main loop.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <map>
+
+#include "engine.cuh"
+#include "tc_ptx.cuh"
+#include "tc_state.cuh"
+
+namespace oar {
+
+constexpr int FB_THREADS = 448;
+constexpr int FB_EPI_THREADS = 128;
+constexpr int FB_WARP_TMA = 4, FB_WARP_MMA = 5, FB_WARP_C0 = 6;
+constexpr int FB_CTHREADS = 256;
+constexpr uint32_t FB_LBO = 128 * 16 + 16;   // k-chunk stride of the A operand (+16 B: conflict-free split stores)
+constexpr uint32_t FB_APART = 4 * FB_LBO;    // one part (hi or lo) of a 128 x 32 A tile
+constexpr uint32_t FB_ABUF = 2 * FB_APART;
+constexpr uint32_t FB_EP_TILE = 128 * 128;   // 128 rows x 32 fp32 staging tile
+constexpr int FB_MAX_IN = 4;
+constexpr size_t FB_SMEM_MAX = 227 * 1024;
+constexpr size_t FB_CTRL_BYTES = 256 + (512 + 32) * 4;  // mbarriers + TMEM slot, then the 1x1 conv bias
+
+enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_A_FULL = 10, FB_AB_EMPTY = 12, FB_ACC_FULL = 14,
+       FB_ACC_EMPTY = 16, FB_NBAR = 18 };
+
+struct FbParams {
+  const float* dw_w;
+  const float* dw_b;
+  int dw_act;
+  float dw_ps, dw_pb;
+  const float* se_scale;  // K == 0: per (image, channel) multiplier applied to A, or null
+  int HW, M;              // K == 0: pixels per image (row -> image for se_scale), total rows
+  const uint4* wpk;
+  const float* bias;
+  int act;
+  float ps, pb;
+  int C, N, BN, nkb, n_tiles;
+  int TH, TW, tiles_h, tiles_w, n_work;
+  int cols_in;
+  uint32_t in_bytes;
+  int ns_in;
+  uint32_t off_in, off_a, off_b, off_ctrl;
+};
+
+__device__ __forceinline__ float act_rt(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_HSWISH: return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) * 0.16666667f;
+    case ACT_SWISH: return __fdividef(v, 1.0f + __expf(-v));
+    case ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-v));
+    case ACT_HSIGMOID: return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
+    default: return v;
+  }
+}
+
+// x = hi + lo in fp16, two channels packed per 32-bit word
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  const __half2 h = __halves2half2(ha, hb);
+  const __half2 l = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int K, int SH, int SW>
+__global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, const __grid_constant__ CUtensorMap tm_in,
+                                                            const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzled staging tiles at offset 0
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = sbase + P.off_ctrl;
+#define FB_BAR(i) (bar0 + 8u * (uint32_t)(i))
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.off_ctrl + 8 * FB_NBAR);
+  const uint32_t b_bytes = (uint32_t)P.BN * 128u;  // one weight k-block: hi + lo, 4 chunks x BN rows x 16 B
+
+  if (tid == 0) {
+    for (int i = 0; i < FB_MAX_IN; ++i) {
+      mbar_init(FB_BAR(FB_IN_FULL + i), 1);
+      mbar_init(FB_BAR(FB_IN_EMPTY + i), FB_CTHREADS);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(FB_BAR(FB_B_FULL + i), 1);
+      mbar_init(FB_BAR(FB_A_FULL + i), FB_CTHREADS);
+      mbar_init(FB_BAR(FB_AB_EMPTY + i), 1);
+      mbar_init(FB_BAR(FB_ACC_FULL + i), 1);
+      mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == FB_WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == FB_WARP_TMA) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      // two independent cursors -- activation boxes run ns_in stages ahead of the depthwise warps, weight k-blocks two
+      // ahead of the MMAs -- advanced by non-blocking probes so that neither ring throttles the other
+      const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
+                               (uint32_t)P.nkb;
+      uint32_t it_in = 0, it_b = 0;
+      int t_in = blockIdx.x, kb_in = 0, t_b = blockIdx.x, kb_b = 0;
+      while (it_in < n_items || it_b < n_items) {
+        if (it_in < n_items) {
+          const uint32_t s = it_in % (uint32_t)P.ns_in, ph = (it_in / (uint32_t)P.ns_in) & 1u;
+          if (mbar_test(FB_BAR(FB_IN_EMPTY + s), ph ^ 1u)) {
+            const int sp = t_in / P.n_tiles;
+            mbar_expect_tx(FB_BAR(FB_IN_FULL + s), P.in_bytes);
+            if (K == 0) {
+              tma_load_2d(sbase + P.off_in + s * P.in_bytes, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32, sp * 128);
+            } else {
+              const int tw = sp % P.tiles_w, r = sp / P.tiles_w;
+              tma_load_4d(sbase + P.off_in + s * P.in_bytes, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32,
+                          tw * P.TW * SW - K / 2, (r % P.tiles_h) * P.TH * SH - K / 2, r / P.tiles_h);
+            }
+            ++it_in;
+            if (++kb_in == P.nkb) kb_in = 0, t_in += gridDim.x;
+          }
+        }
+        if (it_b < n_items) {
+          const uint32_t sb = it_b & 1u, phb = (it_b >> 1) & 1u;
+          if (mbar_test(FB_BAR(FB_AB_EMPTY + sb), phb ^ 1u)) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk) +
+                                  ((size_t)(t_b % P.n_tiles) * P.nkb + kb_b) * b_bytes;
+            mbar_expect_tx(FB_BAR(FB_B_FULL + sb), b_bytes);
+            bulk_load(sbase + P.off_b + sb * b_bytes, wsrc, b_bytes, FB_BAR(FB_B_FULL + sb));
+            ++it_b;
+            if (++kb_b == P.nkb) kb_b = 0, t_b += gridDim.x;
+          }
+        }
+      }
+    }
+  } else if (warp == FB_WARP_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t b_lbo = (uint32_t)P.BN * 16u, b_part = 4u * b_lbo;
+      uint32_t it = 0, ti = 0;
+      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(FB_BAR(FB_ACC_EMPTY + acc), aph ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 256u;
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait(FB_BAR(FB_A_FULL + s), ph);
+          mbar_wait(FB_BAR(FB_B_FULL + s), ph);
+          tc_fence_after();
+          const uint32_t a_hi = sbase + P.off_a + s * FB_ABUF, a_lo = a_hi + FB_APART;
+          const uint32_t b_hi = sbase + P.off_b + s * b_bytes, b_lo = b_hi + b_part;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t ah = make_desc(a_hi + 2 * j * FB_LBO, FB_LBO, 128);
+            const uint64_t al = make_desc(a_lo + 2 * j * FB_LBO, FB_LBO, 128);
+            const uint64_t bh = make_desc(b_hi + 2 * j * b_lbo, b_lbo, 128);
+            const uint64_t bl = make_desc(b_lo + 2 * j * b_lbo, b_lbo, 128);
+            umma_f16(d, ah, bh, idesc, (kb | j) ? 1u : 0u);
+            umma_f16(d, ah, bl, idesc, 1u);
+            umma_f16(d, al, bh, idesc, 1u);
+          }
+          umma_commit(FB_BAR(FB_AB_EMPTY + s));
+          if (kb == P.nkb - 1) umma_commit(FB_BAR(FB_ACC_FULL + acc));
+        }
+      }
+    }
+  } else if (warp >= FB_WARP_C0) {
+    // ------------------------------------------------------------------ depthwise / convert warps
+    const int ct = tid - FB_WARP_C0 * 32;
+    uint32_t it = 0;
+    if (K == 0) {
+      // 128 rows x 32 channels: thread = one 16-byte quad of 4 rows; the two rows of a half-warp are 4 apart (64 B in
+      // the A tile) so its eight 8-byte hi (lo) stores cover 32 distinct banks
+      const int q = ct & 7;
+      const int r0 = 8 * (ct >> 6) + 4 * ((ct >> 3) & 1) + ((ct >> 4) & 3);
+      const uint32_t a_off = (uint32_t)(q >> 1) * FB_LBO + (uint32_t)(q & 1) * 8u;
+      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x) {
+        const int sp = t / P.n_tiles;
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
+          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+          const uint8_t* src = smem + P.off_in + s * P.in_bytes + q * 16;
+          float4 x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
+          mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+          if (P.se_scale) {  // squeeze-excite: A = x * scale[image][channel] (rows past M and channels past C are zeros)
+            const int c = kb * 32 + q * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = sp * 128 + r0 + 32 * j;
+              if (c < P.C && m < P.M) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(P.se_scale + (size_t)(m / P.HW) * P.C + c));
+                x[j].x *= sc.x, x[j].y *= sc.y, x[j].z *= sc.z, x[j].w *= sc.w;
+              }
+            }
+          }
+          uint32_t hi[4][2], lo[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            split2(x[j].x, x[j].y, hi[j][0], lo[j][0]);
+            split2(x[j].z, x[j].w, hi[j][1], lo[j][1]);
+          }
+          const uint32_t sa = it & 1u, pha = (it >> 1) & 1u;
+          mbar_wait(FB_BAR(FB_AB_EMPTY + sa), pha ^ 1u);
+          uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint2*>(ab + (r0 + 32 * j) * 16) = make_uint2(hi[j][0], hi[j][1]);
+            *reinterpret_cast<uint2*>(ab + FB_APART + (r0 + 32 * j) * 16) = make_uint2(lo[j][0], lo[j][1]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(FB_BAR(FB_A_FULL + sa));
+        }
+      }
+    } else {
+      constexpr int KK = K > 0 ? K : 1;
+      constexpr int RT = SH + KK;      // input rows feeding a thread's 2 output rows
+      constexpr int CT = 3 * SW + KK;  // input columns feeding its 4 output columns
+      const int pair = ct & 15, pg = ct >> 4;
+      const int gx = P.TW >> 2;
+      const int pgy = pg / gx, pgx = pg - pgy * gx;
+      const bool active = pgy < (P.TH >> 1);
+      const uint32_t row_stride = (uint32_t)P.cols_in * 128u;
+      const uint32_t in_off = (uint32_t)(2 * pgy * SH) * row_stride + (uint32_t)(4 * pgx * SW) * 128u + (uint32_t)pair * 8u;
+      const uint32_t a_off = (uint32_t)(pair >> 2) * FB_LBO + (uint32_t)(pair & 3) * 4u +
+                             (uint32_t)((2 * pgy) * P.TW + 4 * pgx) * 16u;
+      const bool hsw = P.dw_act == ACT_HSWISH;
+      const bool affine = P.dw_ps != 1.0f || P.dw_pb != 0.0f;
+      // taps of one k-block for the thread's channel pair; fetched one k-block ahead (they depend on kb only)
+      float2 w[KK * KK], bv;
+      auto load_taps = [&](int kb) {
+        const int c = kb * 32 + 2 * pair;
+        if (c < P.C) {
+          bv = __ldg(reinterpret_cast<const float2*>(P.dw_b + c));
+#pragma unroll
+          for (int i = 0; i < KK * KK; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(P.dw_w + (size_t)i * P.C + c));
+        } else {
+          bv = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < KK * KK; ++i) w[i] = make_float2(0.f, 0.f);
+        }
+      };
+      load_taps(0);
+      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x) {
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
+          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+          float2 acc[2][4];
+#pragma unroll
+          for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = bv;
+          if (active) {
+            const uint8_t* base = smem + P.off_in + s * P.in_bytes + in_off;
+#pragma unroll
+            for (int iy = 0; iy < RT; ++iy) {
+              float2 x[CT];
+#pragma unroll
+              for (int cx = 0; cx < CT; ++cx) x[cx] = *reinterpret_cast<const float2*>(base + iy * row_stride + cx * 128);
+#pragma unroll
+              for (int ty = 0; ty < 2; ++ty) {
+                const int ky = iy - ty * SH;
+                if (ky < 0 || ky >= KK) continue;
+#pragma unroll
+                for (int kx = 0; kx < KK; ++kx)
+#pragma unroll
+                  for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = __ffma2_rn(x[tx * SW + kx], w[ky * KK + kx], acc[ty][tx]);
+              }
+            }
+          }
+          mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+          load_taps(kb + 1 < P.nkb ? kb + 1 : 0);
+          uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+          for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 4; ++tx) {
+              float2 v = acc[ty][tx];
+              if (hsw) {  // same operation order as the stand-alone kernel (engine.cu: dw_tile)
+                float2 tq = __fadd2_rn(v, make_float2(3.0f, 3.0f));
+                tq.x = fminf(fmaxf(tq.x, 0.0f), 6.0f), tq.y = fminf(fmaxf(tq.y, 0.0f), 6.0f);
+                v = __fmul2_rn(__fmul2_rn(v, tq), make_float2(0.16666667f, 0.16666667f));
+              } else if (P.dw_act != ACT_NONE) {
+                v.x = act_rt(v.x, P.dw_act), v.y = act_rt(v.y, P.dw_act);
+              }
+              if (affine) v.x = v.x * P.dw_ps + P.dw_pb, v.y = v.y * P.dw_ps + P.dw_pb;
+              split2(v.x, v.y, hi[ty][tx], lo[ty][tx]);
+            }
+          const uint32_t sa = it & 1u, pha = (it >> 1) & 1u;
+          mbar_wait(FB_BAR(FB_AB_EMPTY + sa), pha ^ 1u);
+          if (active) {
+            uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
+#pragma unroll
+            for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+              for (int tx = 0; tx < 4; ++tx) {
+                const uint32_t o = (uint32_t)(ty * P.TW + tx) * 16u;
+                *reinterpret_cast<uint32_t*>(ab + o) = hi[ty][tx];
+                *reinterpret_cast<uint32_t*>(ab + FB_APART + o) = lo[ty][tx];
+              }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(FB_BAR(FB_A_FULL + sa));
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (tid = tile row = TMEM lane)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool affine = P.ps != 1.0f || P.pb != 0.0f;
+    float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + 256);  // [n_tiles * BN + 32], zero padded
+    for (int i = tid; i < P.n_tiles * P.BN + 32; i += FB_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
+    named_bar_sync(1, FB_EPI_THREADS);
+    uint32_t ti = 0, nstore = 0;
+    for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+      const int nt = t % P.n_tiles, sp = t / P.n_tiles;
+      int c1 = sp * 128, c2 = 0, c3 = 0;
+      if (K > 0) {
+        const int tw = sp % P.tiles_w, r = sp / P.tiles_w;
+        c1 = tw * P.TW, c2 = (r % P.tiles_h) * P.TH, c3 = r / P.tiles_h;
+      }
+      const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(FB_BAR(FB_ACC_FULL + acc), aph);
+      tc_fence_after();
+      const int n_base = nt * P.BN;
+      for (int c0 = 0; c0 < P.BN && n_base + c0 < P.N; c0 += 32, ++nstore) {
+        float v[32];
+        tmem_ld16(lane_base + acc * 256u + (uint32_t)c0, v);
+        if (c0 + 16 < P.BN) {
+          tmem_ld16(lane_base + acc * 256u + (uint32_t)c0 + 16u, v + 16);
+        } else {
+#pragma unroll
+          for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+        }
+        {
+          // bias from shared memory (broadcast reads; zero past N), activation chosen once per chunk
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + n_base + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = bs[i];
+            v[4 * i] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
+          }
+          switch (P.act) {
+#define FB_ACT_CASE(A)                                      \
+  case A:                                                   \
+    _Pragma("unroll") for (int i = 0; i < 32; ++i) v[i] = act_t<A>(v[i]); \
+    break;
+            FB_ACT_CASE(ACT_RELU)
+            FB_ACT_CASE(ACT_HSWISH)
+            FB_ACT_CASE(ACT_SWISH)
+            FB_ACT_CASE(ACT_SIGMOID)
+            FB_ACT_CASE(ACT_HSIGMOID)
+#undef FB_ACT_CASE
+            default: break;
+          }
+        }
+        if (affine) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * P.ps + P.pb;
+        }
+        // staging tile nstore & 1: its previous store (two groups ago) was waited for by thread 0 before the last barrier
+        uint8_t* ep = smem + (nstore & 1u) * FB_EP_TILE + tid * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(ep + ((i ^ (tid & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async_smem();
+        if (tid == 0) bulk_wait_read_all();  // every store issued so far has read its staging tile
+        named_bar_sync(1, FB_EPI_THREADS);
+        if (tid == 0) {
+          const uint32_t src = sbase + (nstore & 1u) * FB_EP_TILE;
+          if (K == 0)
+            tma_store_2d(&tm_out, src, n_base + c0, c1);
+          else
+            tma_store_4d(&tm_out, src, n_base + c0, c1, c2, c3);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(FB_BAR(FB_ACC_EMPTY + acc));
+    }
+    if (tid == 0) bulk_wait_all();
+  }
+#undef FB_BAR
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FB_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+static bool encode_map(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                       const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+using FbKern = void (*)(const FbParams, const CUtensorMap, const CUtensorMap);
+
+static FbKern pick_kernel(int k, int sh, int sw) {
+#define FB_CASE(KV, SHV, SWV) \
+  if (k == KV && sh == SHV && sw == SWV) return lcblock_tc<KV, SHV, SWV>;
+  FB_CASE(0, 1, 1)
+  FB_CASE(3, 1, 1) FB_CASE(5, 1, 1)
+  FB_CASE(3, 2, 2) FB_CASE(5, 2, 2)
+  FB_CASE(3, 2, 1) FB_CASE(5, 2, 1)
+  FB_CASE(3, 1, 2) FB_CASE(5, 1, 2)
+#undef FB_CASE
+  return nullptr;
+}
+
+bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name) {
+  TcState* st = static_cast<TcState*>(m->tc_state);
+  if (!st) return false;
+  const TcWeights* w = nullptr;
+  auto itf = st->wf.find(key);
+  if (itf != st->wf.end()) {
+    w = &itf->second;
+  } else {
+    auto it = st->w.find(key);
+    if (it != st->w.end()) w = &it->second;
+  }
+  if (!w || w->rowtaps || w->KC != 4 || w->K != f.C || w->N != f.N) return false;
+  if (f.C < 32 || (f.C & 3) || (f.out_ld & 3) || (f.out_c_off & 3) || (((uintptr_t)f.in) & 15) || (((uintptr_t)f.out) & 15))
+    return false;
+  FbKern kern = pick_kernel(f.k, f.k ? f.sh : 1, f.k ? f.sw : 1);
+  if (!kern) return false;
+  const long long M = (long long)f.B * f.Ho * f.Wo;
+  if (M <= 0) return true;
+
+  FbParams P{};
+  P.dw_w = f.dw_w, P.dw_b = f.dw_b, P.dw_act = f.dw_act, P.dw_ps = f.dw_ps, P.dw_pb = f.dw_pb;
+  P.se_scale = f.se_scale, P.HW = f.Ho * f.Wo;
+  P.wpk = w->packed, P.bias = f.bias, P.act = f.act, P.ps = f.ps, P.pb = f.pb;
+  P.C = f.C, P.N = f.N, P.BN = w->BN, P.nkb = w->nkb, P.n_tiles = w->n_tiles;
+
+  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * (size_t)w->BN * 128 + FB_CTRL_BYTES + 1024;
+  CUtensorMap tm_in, tm_out;
+  memset(&tm_in, 0, sizeof(tm_in));
+  memset(&tm_out, 0, sizeof(tm_out));
+  int n_sp = 0;
+  if (f.k == 0) {
+    P.in_bytes = 128 * 128;
+    P.ns_in = 4;
+    while (P.ns_in > 2 && fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) --P.ns_in;
+    if (fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) return false;
+    n_sp = (int)((M + 127) / 128);
+    P.M = (int)M;
+    P.TH = P.TW = 0, P.tiles_h = P.tiles_w = 1, P.cols_in = 128;
+    cuuint64_t dims[2] = {(cuuint64_t)f.C, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)f.C * 4};
+    cuuint32_t box[2] = {32, 128};
+    if (!encode_map(&tm_in, f.in, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+    cuuint64_t odims[2] = {(cuuint64_t)f.N, (cuuint64_t)M};
+    cuuint64_t ostrides[1] = {(cuuint64_t)f.out_ld * 4};
+    if (!encode_map(&tm_out, f.out + f.out_c_off, 2, odims, ostrides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  } else {
+    // tile = TH x TW output pixels of one image (TH even, TW % 4 == 0, <= 128 pixels).  Every tile costs the
+    // depthwise warps the same time, so minimise the tile count first and the halo traffic second.
+    double best = 1e300;
+    int bTH = 0, bTW = 0, bns = 0;
+    for (int TH = 2; TH <= 32; TH += 2)
+      for (int TW = 4; TW <= 64; TW += 4) {
+        if (TH * TW > 128) continue;
+        const int rows_in = (TH - 1) * f.sh + f.k, cols_in = (TW - 1) * f.sw + f.k;
+        if (rows_in > 256 || cols_in > 256) continue;
+        const size_t in_bytes = (size_t)rows_in * cols_in * 128;
+        int ns = 3;
+        while (ns >= 2 && fixed + ns * in_bytes > FB_SMEM_MAX) --ns;
+        if (ns < 2) continue;
+        const double tiles = (double)cdiv(f.Ho, TH) * cdiv(f.Wo, TW);
+        const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.1 : 1.0);
+        if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns;
+      }
+    if (!bTH) return false;
+    P.TH = bTH, P.TW = bTW, P.ns_in = bns;
+    P.tiles_h = cdiv(f.Ho, bTH), P.tiles_w = cdiv(f.Wo, bTW);
+    const int rows_in = (bTH - 1) * f.sh + f.k;
+    P.cols_in = (bTW - 1) * f.sw + f.k;
+    P.in_bytes = (uint32_t)rows_in * P.cols_in * 128u;
+    n_sp = f.B * P.tiles_h * P.tiles_w;
+    cuuint64_t dims[4] = {(cuuint64_t)f.C, (cuuint64_t)f.W, (cuuint64_t)f.H, (cuuint64_t)f.B};
+    cuuint64_t strides[3] = {(cuuint64_t)f.C * 4, (cuuint64_t)f.C * 4 * f.W, (cuuint64_t)f.C * 4 * f.W * f.H};
+    cuuint32_t box[4] = {32, (cuuint32_t)P.cols_in, (cuuint32_t)rows_in, 1};
+    if (!encode_map(&tm_in, f.in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+    cuuint64_t odims[4] = {(cuuint64_t)f.N, (cuuint64_t)f.Wo, (cuuint64_t)f.Ho, (cuuint64_t)f.B};
+    cuuint64_t ostrides[3] = {(cuuint64_t)f.out_ld * 4, (cuuint64_t)f.out_ld * 4 * f.Wo,
+                              (cuuint64_t)f.out_ld * 4 * f.Wo * f.Ho};
+    cuuint32_t obox[4] = {32, (cuuint32_t)bTW, (cuuint32_t)bTH, 1};
+    if (!encode_map(&tm_out, f.out + f.out_c_off, 4, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  }
+  P.n_work = n_sp * w->n_tiles;
+  P.off_in = 2 * FB_EP_TILE;
+  P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
+  P.off_b = P.off_a + 2 * FB_ABUF;
+  P.off_ctrl = P.off_b + 2 * (uint32_t)w->BN * 128u;
+  // always above half the SM's shared memory: one CTA per SM owns all 512 TMEM columns
+  const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
+  {
+    static std::map<std::pair<const void*, int>, bool> attr_done;
+    auto ka = std::make_pair((const void*)kern, m->ctx->device);
+    if (!attr_done.count(ka)) {
+      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_MAX));
+      attr_done[ka] = true;
+    }
+  }
+  const int grid = std::min(P.n_work, m->ctx->sm_count);
+  const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
+  const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
+  Launch l(m->ctx, name, flops, bytes);
+  kern<<<grid, FB_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
+  return true;
+}
+
+}  // namespace oar

@@ -30,6 +30,8 @@
 #include <map>
 
 #include "engine.cuh"
+#include "tc_ptx.cuh"
+#include "tc_state.cuh"
 
 namespace oar {
 
@@ -39,101 +41,6 @@ constexpr int TC_BM = 128;        // UMMA M
 constexpr int TC_STAGES = 2;
 constexpr int TC_MAX_BN = 256;
 
-struct TcWeights {
-  uint4* packed = nullptr;  // [n_tile][k_block][hi|lo][k-chunk][BN rows][8 halfs]
-  int N = 0, K = 0, BN = 0, n_tiles = 0, nkb = 0, KC = 4;
-  bool rowtaps = false;  // packed for conv_rowtaps_tc: [n_tile][ky][cin block][kx][hi|lo][k-chunk][BN rows][8 halfs]
-  int kh = 1, kw = 1;
-};
-
-struct TcState {
-  std::map<int, TcWeights> w;
-};
-
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread issues
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// start address [0,14), leading (k-chunk) byte offset [16,30), stride (8-row group) byte offset [32,46), all >> 4
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46);
-}
-
-// split 8 floats into hi / lo fp16 vectors (x ~= hi + lo, |x - hi - lo| <= 2^-22 |x|)
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  __half2 h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half a = __float2half_rn(x[2 * i]), b = __float2half_rn(x[2 * i + 1]);
-    h[i] = __halves2half2(a, b);
-    l[i] = __halves2half2(__float2half_rn(x[2 * i] - __half2float(a)), __float2half_rn(x[2 * i + 1] - __half2float(b)));
-  }
-  hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
-                  *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-  lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                  *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-}
-
 struct TcParams {
   ConvParams c;
   const uint4* wpk;
@@ -141,13 +48,6 @@ struct TcParams {
   uint32_t ctrl_off;  // byte offset of the mbarriers / TMEM slot behind the stages (and the epilogue staging tile)
   int tma_out;        // 1: the conv epilogue stores through the TMA tensor map passed next to these parameters
 };
-
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 constexpr int TC_THREADS = 256;  // two threads per output row: each takes half the k-chunks and half the columns
 
@@ -226,18 +126,6 @@ __device__ __forceinline__ void load_a(const ConvParams& p, int kb, int chunk, c
     r.v[2 * j] = u;
     r.v[2 * j + 1] = v;
   }
-}
-
-// Activations of the tensor-core epilogue.  Division-free forms (reciprocal multiply, __fdividef): within 2 ulp of
-// the IEEE forms the SIMT engine uses, far inside the 1e-3 parity tolerance, and ~10 instructions cheaper per value.
-template <int ACT>
-__device__ __forceinline__ float act_t(float v) {
-  if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
-  if (ACT == ACT_HSWISH) return v * fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) * 0.16666667f;
-  if (ACT == ACT_SWISH) return __fdividef(v, 1.0f + __expf(-v));
-  if (ACT == ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
-  if (ACT == ACT_HSIGMOID) return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
-  return v;
 }
 
 constexpr int EP_LD = 36;                          // floats per row of the epilogue staging tile (32 + pad)
@@ -816,13 +704,13 @@ void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part
 // ---------------------------------------------------------------------------
 // host: weight packing and launch
 // ---------------------------------------------------------------------------
-static TcWeights pack_weights(const float* w, int N, int K) {
+TcWeights pack_weights(const float* w, int N, int K, bool force_kc4) {
   TcWeights t;
   t.N = N, t.K = K;
   t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
   t.BN = t.n_tiles > 1 ? (per + 31) / 32 * 32 : std::max(16, (per + 15) / 16 * 16);
-  t.KC = (K > 32 && K <= 64) ? 8 : 4;  // 64-wide single stage for 32 < K <= 64; otherwise 32-wide double-buffered
+  t.KC = (!force_kc4 && K > 32 && K <= 64) ? 8 : 4;  // 64-wide single stage for 32 < K <= 64; otherwise 32-wide double-buffered
   const int TC_KC = t.KC, TC_BK = t.KC * 8;
   t.nkb = (K + TC_BK - 1) / TC_BK;
   size_t halfs = (size_t)t.n_tiles * t.nkb * 2 * TC_KC * t.BN * 8;
@@ -900,6 +788,8 @@ void tc_model_init(oar_model* m) {
         const bool rowtaps = kh * kw > 1 && sh == 1 && sw == 1 && (kh & 1) && (kw & 1) && ph == kh / 2 && pw == kw / 2 &&
                              kw <= RT_MAX_KW && cin % 32 == 0;
         st->w[(int)oi * 2] = rowtaps ? pack_weights_rowtaps(w0, op.p[7], kh, kw, cin) : pack_weights(w0, op.p[7], kh * kw * cin);
+        // the fused depthwise->pointwise kernel (fused_tc.cu) streams 32-channel k-blocks: KC = 4 packing
+        if (kh == 1 && kw == 1 && st->w[(int)oi * 2].KC != 4) st->wf[(int)oi * 2] = pack_weights(w0, op.p[7], cin, true);
         break;
       }
       case OP_DECONV2:
@@ -922,6 +812,7 @@ void tc_model_free(oar_model* m) {
   TcState* st = static_cast<TcState*>(m->tc_state);
   if (!st) return;
   for (auto& kv : st->w) cudaFree(kv.second.packed);
+  for (auto& kv : st->wf) cudaFree(kv.second.packed);
   delete st;
   m->tc_state = nullptr;
 }
@@ -936,10 +827,7 @@ int tc_n_tiles(const oar_model* m, int key) {
 }
 
 // ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn tmap_encoder() {
+EncodeTiledFn tmap_encoder() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;

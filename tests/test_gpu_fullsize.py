@@ -65,27 +65,28 @@ def test_full_batch_properties(ocr):
             if q.detection_index == p.detection_index + 1:
                 py, qy = p.bounding_box.y_min(), q.bounding_box.y_min()
                 assert not (abs(qy - py) < 10.0 and q.bounding_box.x_min() < p.bounding_box.x_min())
-    # fp32 SIMT engine vs tensor-core engine: same boxes, same labels
-    ocr.det.set_engine(0)
-    ocr.rec.set_engine(0)
+    # fp32 SIMT engine (0) and per-layer tcgen05 engine (1) vs the default fused tcgen05 engine (2): same boxes, labels
+    others = []
     try:
-        c = ocr.predict(pages[:8])
+        for eng in (0, 1):
+            ocr.det.set_engine(eng)
+            ocr.rec.set_engine(eng)
+            others.append(ocr.predict(pages[:8]))
     finally:
-        ocr.det.set_engine(1)
-        ocr.rec.set_engine(1)
+        ocr.det.set_engine(2)
+        ocr.rec.set_engine(2)
     ocr.image_batch_size = 8
     d = ocr.predict(pages[:8])
     # detection of an image does not depend on its batch mates: boxes of the 8-page call equal those of the 32-page call
     for x, y in zip(d, a[:8]):
         assert [r.bounding_box.points.tobytes() for r in x.text_regions] == \
                [r.bounding_box.points.tobytes() for r in y.text_regions]
-    for x, y in zip(c, d):
-        assert [r.bounding_box.points.tobytes() for r in x.text_regions] == \
-               [r.bounding_box.points.tobytes() for r in y.text_regions]
     ocr.region_batch_size = 256
-    c2 = _summary(c)
-    d2 = _summary(d)
-    assert c2 == d2
+    for c in others:
+        for x, y in zip(c, d):
+            assert [r.bounding_box.points.tobytes() for r in x.text_regions] == \
+                   [r.bounding_box.points.tobytes() for r in y.text_regions]
+        assert _summary(c) == _summary(d)
 
 
 def test_rec_512_crops(ocr, rec_blob):

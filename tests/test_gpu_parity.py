@@ -11,6 +11,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
+DEFAULT_ENGINE = 2  # tcgen05 engine with fused depthwise->pointwise blocks (oar_model_set_engine)
 LOGIT_TOL = 1e-3  # BASELINE.json north_star: "float logits within 1e-3"
 
 
@@ -266,7 +267,7 @@ def test_ctc_full_vocab_vs_oracle(ctx):
 
 
 # ---------------------------------------------------------------- rows 3 / 14: the networks
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 def test_det_net_golden_and_oracle(nets, oracle_nets, G, engine):
     from oracle import cpu
     det, _ = nets
@@ -281,10 +282,10 @@ def test_det_net_golden_and_oracle(nets, oracle_nets, G, engine):
     got = det.infer(x)
     want = oracle_nets[0].forward(x)
     assert np.abs(got - want).max() <= LOGIT_TOL
-    det.set_engine(1)
+    det.set_engine(DEFAULT_ENGINE)
 
 
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 def test_rec_net_golden_and_oracle(nets, oracle_nets, G, engine):
     from oracle import cpu
     _, rec = nets
@@ -304,7 +305,7 @@ def test_rec_net_golden_and_oracle(nets, oracle_nets, G, engine):
     assert r["T"] == T
     assert all(np.array_equal(a, b) for a, b in zip(r["labels"], lab))
     assert np.abs(r["scores"] - sc).max() <= LOGIT_TOL
-    rec.set_engine(1)
+    rec.set_engine(DEFAULT_ENGINE)
 
 
 # ---------------------------------------------------------------- seam 2: adapters and the whole path
@@ -338,7 +339,7 @@ def test_pipeline_golden(nets, G):
         assert abs(r.confidence - G["pipe_scores"][i]) <= LOGIT_TOL
 
 
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 def test_pipeline_vs_oracle_batch(nets, oracle_nets, engine):
     """OAROCR::predict on 5 pages of two sizes, image_batch_size 2, region_batch_size 8: boxes and CTC label
     sequences identical to the CPU oracle, confidences within 1e-3"""
@@ -363,8 +364,8 @@ def test_pipeline_vs_oracle_batch(nets, oracle_nets, engine):
             total += 1
     assert total >= 20
     assert ocr.last_timing["ms_total"] > 0
-    det.set_engine(1)
-    rec.set_engine(1)
+    det.set_engine(DEFAULT_ENGINE)
+    rec.set_engine(DEFAULT_ENGINE)
 
 
 def test_pipeline_errors(nets):
