@@ -729,7 +729,24 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
   auto is_pw = [](const OpRec& o) {
     return o.type == OP_CONV && o.p[0] == 1 && o.p[1] == 1 && o.p[2] == 1 && o.p[3] == 1 && o.p[4] == 0 && o.p[5] == 0;
   };
-  static const bool fuse_plain_pw = getenv("OAR_FUSED_PW") && atoi(getenv("OAR_FUSED_PW")) != 0;
+  // squeeze-excite gate: global average pool (two deterministic stages) + the two tiny FCs -> scale[B][C]
+  auto se_scale = [&](const OpRec& op, const Tensor& a) -> float* {
+    const int c = op.p[0], cm = op.p[1], HW = a.H * a.W;
+    const int S = HW >= 4096 ? 64 : (HW >= 256 ? 16 : 1);
+    float* partial = ctx->arena.get<float>((size_t)a.B * S * c);
+    float* scale = ctx->arena.get<float>((size_t)a.B * c);
+    {
+      Launch l(ctx, "se_gap", (double)a.numel(), 4.0 * a.numel());
+      se_gap_kernel<<<dim3(S, a.B), 256, 0, st>>>(a.p, partial, HW, c, S);
+    }
+    {
+      Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
+      se_fc_kernel<<<a.B, 256, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2), m->w(op, 3),
+                                                                scale, HW, c, cm, S, op.f[0], op.f[1]);
+    }
+    return scale;
+  };
+  static const bool fuse_plain_pw = !(getenv("OAR_FUSED_PW") && atoi(getenv("OAR_FUSED_PW")) == 0);
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const OpRec& op = m->ops[oi];
     const Tensor& a = t[op.in0];
@@ -815,22 +832,26 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         break;
       }
       case OP_SE: {
-        int c = op.p[0], cm = op.p[1], residual = op.p[2];
+        int c = op.p[0], residual = op.p[2];
         if (a.C != c || (c & 3)) OAR_FAIL(OAR_E_MODEL, "se op %zu: bad channels", oi);
-        Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         int HW = a.H * a.W;
-        int S = HW >= 4096 ? 64 : (HW >= 256 ? 16 : 1);
-        float* partial = ctx->arena.get<float>((size_t)a.B * S * c);
-        float* scale = ctx->arena.get<float>((size_t)a.B * c);
-        {
-          Launch l(ctx, "se_gap", (double)a.numel(), 4.0 * a.numel());
-          se_gap_kernel<<<dim3(S, a.B), 256, 0, st>>>(a.p, partial, HW, c, S);
+        float* scale = se_scale(op, a);
+        // engine 2: a squeeze-excite that feeds exactly one 1x1 conv is applied while that conv builds its A operand
+        if (m->engine == 2 && !residual && uses[op.out] == 1 && oi + 1 < m->ops.size() && is_pw(m->ops[oi + 1]) &&
+            m->ops[oi + 1].in0 == op.out && m->ops[oi + 1].p[6] == c) {
+          const OpRec& pw = m->ops[oi + 1];
+          Tensor& o = ensure(pw.out, a.B, a.H, a.W, pw.p[11] ? pw.p[11] : pw.p[7]);
+          FusedBlock f{};
+          f.in = a.p, f.B = a.B, f.H = a.H, f.W = a.W, f.C = a.C, f.se_scale = scale;
+          f.bias = m->w(pw, 1), f.act = pw.p[8], f.ps = pw.f[0], f.pb = pw.f[1], f.N = pw.p[7];
+          f.out = o.p, f.out_ld = o.C, f.out_c_off = pw.p[11] ? pw.p[10] : 0, f.Ho = o.H, f.Wo = o.W;
+          if (tc_fused_block(m, (int)(oi + 1) * 2, f, "se_pwconv_tc")) {
+            last = o;
+            ++oi;
+            continue;
+          }
         }
-        {
-          Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
-          se_fc_kernel<<<a.B, 256, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2),
-                                                                    m->w(op, 3), scale, HW, c, cm, S, op.f[0], op.f[1]);
-        }
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         {
           size_t n4 = a.numel() / 4;
           Launch l(ctx, "se_apply", 2.0 * a.numel(), 8.0 * a.numel());

@@ -204,6 +204,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       for (int t = blockIdx.x; t < P.n_work; t += gridDim.x) {
         const int sp = t / P.n_tiles;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
+          float4 sc[4];
+          if (P.se_scale) {
+            const int c = kb * 32 + q * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = sp * 128 + r0 + 32 * j;
+              sc[j] = (c < P.C && m < P.M) ? __ldg(reinterpret_cast<const float4*>(P.se_scale + (size_t)(m / P.HW) * P.C + c))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M / channels past C are zeros
+            }
+          }
           const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
           mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
           const uint8_t* src = smem + P.off_in + s * P.in_bytes + q * 16;
@@ -211,16 +222,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
 #pragma unroll
           for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
           mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
-          if (P.se_scale) {  // squeeze-excite: A = x * scale[image][channel] (rows past M and channels past C are zeros)
-            const int c = kb * 32 + q * 4;
+          if (P.se_scale) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int m = sp * 128 + r0 + 32 * j;
-              if (c < P.C && m < P.M) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(P.se_scale + (size_t)(m / P.HW) * P.C + c));
-                x[j].x *= sc.x, x[j].y *= sc.y, x[j].z *= sc.z, x[j].w *= sc.w;
-              }
-            }
+            for (int j = 0; j < 4; ++j) x[j].x *= sc[j].x, x[j].y *= sc[j].y, x[j].z *= sc[j].z, x[j].w *= sc[j].w;
           }
           uint32_t hi[4][2], lo[4][2];
 #pragma unroll
@@ -452,7 +456,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     if (it != st->w.end()) w = &it->second;
   }
   if (!w || w->rowtaps || w->KC != 4 || w->K != f.C || w->N != f.N) return false;
-  if (f.C < 32 || (f.C & 3) || (f.out_ld & 3) || (f.out_c_off & 3) || (((uintptr_t)f.in) & 15) || (((uintptr_t)f.out) & 15))
+  if (f.C < 16 || (f.C & 3) || (f.out_ld & 3) || (f.out_c_off & 3) || (((uintptr_t)f.in) & 15) || (((uintptr_t)f.out) & 15))
     return false;
   FbKern kern = pick_kernel(f.k, f.k ? f.sh : 1, f.k ? f.sw : 1);
   if (!kern) return false;
