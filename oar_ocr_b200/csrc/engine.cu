@@ -767,7 +767,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(pw.out, a.B, Ho, Wo, pw.p[11] ? pw.p[11] : pw.p[7]);
         FusedBlock f{};
         f.in = a.p, f.B = a.B, f.H = a.H, f.W = a.W, f.C = a.C, f.k = k, f.sh = sh, f.sw = sw;
-        f.dw_w = m->w(op, 0), f.dw_b = m->w(op, 1), f.dw_act = op.p[7], f.dw_ps = op.f[0], f.dw_pb = op.f[1];
+        f.dw_key = (int)oi, f.dw_act = op.p[7], f.dw_ps = op.f[0], f.dw_pb = op.f[1];
         fill_pw(f, pw, o);
         if (tc_fused_block(m, (int)(oi + 1) * 2, f, k == 3 ? "lcblock3_tc" : "lcblock5_tc")) {
           last = o;

@@ -62,8 +62,7 @@ struct FusedBlock {
   const float* in;  // NHWC input of the depthwise conv (k > 0) or of the 1x1 conv (k == 0)
   int B, H, W, C;
   int k, sh, sw;  // depthwise kernel size (square, pad k/2) and strides
-  const float* dw_w;
-  const float* dw_b;
+  int dw_key;  // op index of the depthwise conv (its packed taps live in the tensor-core state)
   int dw_act;
   float dw_ps, dw_pb;
   const float* se_scale;  // k == 0 only: [B][C] multiplier or null

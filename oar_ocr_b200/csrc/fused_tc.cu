@@ -33,10 +33,10 @@
 
 namespace oar {
 
-constexpr int FB_THREADS = 448;
+constexpr int FB_THREADS = 704;  // 4 epilogue + TMA + MMA + 16 depthwise/convert warps
 constexpr int FB_EPI_THREADS = 128;
 constexpr int FB_WARP_TMA = 4, FB_WARP_MMA = 5, FB_WARP_C0 = 6;
-constexpr int FB_CTHREADS = 256;
+constexpr int FB_CTHREADS = 256;  // one team: the two teams of depthwise warps take alternate k-blocks
 constexpr uint32_t FB_LBO = 128 * 16 + 16;   // k-chunk stride of the A operand (+16 B: conflict-free split stores)
 constexpr uint32_t FB_APART = 4 * FB_LBO;    // one part (hi or lo) of a 128 x 32 A tile
 constexpr uint32_t FB_ABUF = 2 * FB_APART;
@@ -49,8 +49,7 @@ enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_A_FULL = 10, FB_AB_EMP
        FB_ACC_EMPTY = 16, FB_NBAR = 18 };
 
 struct FbParams {
-  const float* dw_w;
-  const float* dw_b;
+  const float* dw_pk;  // [k-block][K*K taps | bias][32 channels], zero padded: rides along with the activation box
   int dw_act;
   float dw_ps, dw_pb;
   const float* se_scale;  // K == 0: per (image, channel) multiplier applied to A, or null
@@ -62,7 +61,8 @@ struct FbParams {
   int C, N, BN, nkb, n_tiles;
   int TH, TW, tiles_h, tiles_w, n_work;
   int cols_in;
-  uint32_t in_bytes;
+  uint32_t in_bytes;   // activation box
+  uint32_t tap_bytes;  // depthwise taps + bias of one k-block (0 for K == 0); stage = box + taps
   int ns_in;
   uint32_t off_in, off_a, off_b, off_ctrl;
 };
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
 #define FB_BAR(i) (bar0 + 8u * (uint32_t)(i))
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.off_ctrl + 8 * FB_NBAR);
   const uint32_t b_bytes = (uint32_t)P.BN * 128u;  // one weight k-block: hi + lo, 4 chunks x BN rows x 16 B
+  const uint32_t stage_bytes = P.in_bytes + P.tap_bytes;
 
   if (tid == 0) {
     for (int i = 0; i < FB_MAX_IN; ++i) {
@@ -133,13 +134,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           const uint32_t s = it_in % (uint32_t)P.ns_in, ph = (it_in / (uint32_t)P.ns_in) & 1u;
           if (mbar_test(FB_BAR(FB_IN_EMPTY + s), ph ^ 1u)) {
             const int sp = t_in / P.n_tiles;
-            mbar_expect_tx(FB_BAR(FB_IN_FULL + s), P.in_bytes);
+            const uint32_t dst = sbase + P.off_in + s * stage_bytes;
+            mbar_expect_tx(FB_BAR(FB_IN_FULL + s), stage_bytes);
             if (K == 0) {
-              tma_load_2d(sbase + P.off_in + s * P.in_bytes, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32, sp * 128);
+              tma_load_2d(dst, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32, sp * 128);
             } else {
               const int tw = sp % P.tiles_w, r = sp / P.tiles_w;
-              tma_load_4d(sbase + P.off_in + s * P.in_bytes, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32,
-                          tw * P.TW * SW - K / 2, (r % P.tiles_h) * P.TH * SH - K / 2, r / P.tiles_h);
+              tma_load_4d(dst, &tm_in, FB_BAR(FB_IN_FULL + s), kb_in * 32, tw * P.TW * SW - K / 2,
+                          (r % P.tiles_h) * P.TH * SH - K / 2, r / P.tiles_h);
+              bulk_load(dst + P.in_bytes, reinterpret_cast<const uint8_t*>(P.dw_pk) + (size_t)kb_in * P.tap_bytes,
+                        P.tap_bytes, FB_BAR(FB_IN_FULL + s));
             }
             ++it_in;
             if (++kb_in == P.nkb) kb_in = 0, t_in += gridDim.x;
@@ -193,56 +197,59 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     }
   } else if (warp >= FB_WARP_C0) {
     // ------------------------------------------------------------------ depthwise / convert warps
-    const int ct = tid - FB_WARP_C0 * 32;
-    uint32_t it = 0;
+    // two teams of 8 warps take alternate k-blocks (team = item parity = A buffer), so twice the warps hide the
+    // shared-memory and FMA latencies of one k-block's work
+    const int team = (tid - FB_WARP_C0 * 32) >> 8;
+    const int ct = (tid - FB_WARP_C0 * 32) & 255;
+    const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
+                             (uint32_t)P.nkb;
+    const uint32_t sa = (uint32_t)team;
     if (K == 0) {
       // 128 rows x 32 channels: thread = one 16-byte quad of 4 rows; the two rows of a half-warp are 4 apart (64 B in
       // the A tile) so its eight 8-byte hi (lo) stores cover 32 distinct banks
       const int q = ct & 7;
       const int r0 = 8 * (ct >> 6) + 4 * ((ct >> 3) & 1) + ((ct >> 4) & 3);
       const uint32_t a_off = (uint32_t)(q >> 1) * FB_LBO + (uint32_t)(q & 1) * 8u;
-      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x) {
-        const int sp = t / P.n_tiles;
-        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
-          float4 sc[4];
-          if (P.se_scale) {
-            const int c = kb * 32 + q * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int m = sp * 128 + r0 + 32 * j;
-              sc[j] = (c < P.C && m < P.M) ? __ldg(reinterpret_cast<const float4*>(P.se_scale + (size_t)(m / P.HW) * P.C + c))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M / channels past C are zeros
-            }
-          }
-          const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
-          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
-          const uint8_t* src = smem + P.off_in + s * P.in_bytes + q * 16;
-          float4 x[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
-          mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
-          if (P.se_scale) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j].x *= sc[j].x, x[j].y *= sc[j].y, x[j].z *= sc[j].z, x[j].w *= sc[j].w;
-          }
-          uint32_t hi[4][2], lo[4][2];
+      for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
+        const int kb = (int)(it % (uint32_t)P.nkb);
+        // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
+        float4 sc[4];
+        if (P.se_scale) {
+          const int sp = ((int)blockIdx.x + (int)(it / (uint32_t)P.nkb) * (int)gridDim.x) / P.n_tiles;
+          const int c = kb * 32 + q * 4;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            split2(x[j].x, x[j].y, hi[j][0], lo[j][0]);
-            split2(x[j].z, x[j].w, hi[j][1], lo[j][1]);
+            const int m = sp * 128 + r0 + 32 * j;
+            sc[j] = (c < P.C && m < P.M) ? __ldg(reinterpret_cast<const float4*>(P.se_scale + (size_t)(m / P.HW) * P.C + c))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M / channels past C are zeros
           }
-          const uint32_t sa = it & 1u, pha = (it >> 1) & 1u;
-          mbar_wait(FB_BAR(FB_AB_EMPTY + sa), pha ^ 1u);
-          uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint2*>(ab + (r0 + 32 * j) * 16) = make_uint2(hi[j][0], hi[j][1]);
-            *reinterpret_cast<uint2*>(ab + FB_APART + (r0 + 32 * j) * 16) = make_uint2(lo[j][0], lo[j][1]);
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(FB_BAR(FB_A_FULL + sa));
         }
+        const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
+        mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        const uint8_t* src = smem + P.off_in + s * stage_bytes + q * 16;
+        float4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
+        mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+        if (P.se_scale) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j].x *= sc[j].x, x[j].y *= sc[j].y, x[j].z *= sc[j].z, x[j].w *= sc[j].w;
+        }
+        uint32_t hi[4][2], lo[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          split2(x[j].x, x[j].y, hi[j][0], lo[j][0]);
+          split2(x[j].z, x[j].w, hi[j][1], lo[j][1]);
+        }
+        mbar_wait(FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint2*>(ab + (r0 + 32 * j) * 16) = make_uint2(hi[j][0], hi[j][1]);
+          *reinterpret_cast<uint2*>(ab + FB_APART + (r0 + 32 * j) * 16) = make_uint2(lo[j][0], lo[j][1]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(FB_BAR(FB_A_FULL + sa));
       }
     } else {
       constexpr int KK = K > 0 ? K : 1;
@@ -258,82 +265,73 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
                              (uint32_t)((2 * pgy) * P.TW + 4 * pgx) * 16u;
       const bool hsw = P.dw_act == ACT_HSWISH;
       const bool affine = P.dw_ps != 1.0f || P.dw_pb != 0.0f;
-      // taps of one k-block for the thread's channel pair; fetched one k-block ahead (they depend on kb only)
-      float2 w[KK * KK], bv;
-      auto load_taps = [&](int kb) {
-        const int c = kb * 32 + 2 * pair;
-        if (c < P.C) {
-          bv = __ldg(reinterpret_cast<const float2*>(P.dw_b + c));
+      for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
+        const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
+        mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        const uint8_t* stage = smem + P.off_in + s * stage_bytes;
+        // taps [ky*K+kx][32 ch] and bias [32 ch] of this k-block sit behind the box; each is read once per thread,
+        // just in time (a kernel row serves output row 0 at input row ky and output row 1 at input row ky + SH)
+        const float2* taps = reinterpret_cast<const float2*>(stage + P.in_bytes) + pair;
+        const float2 bv = taps[KK * KK * 16];
+        float2 acc[2][4];
 #pragma unroll
-          for (int i = 0; i < KK * KK; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(P.dw_w + (size_t)i * P.C + c));
-        } else {
-          bv = make_float2(0.f, 0.f);
+        for (int ty = 0; ty < 2; ++ty)
 #pragma unroll
-          for (int i = 0; i < KK * KK; ++i) w[i] = make_float2(0.f, 0.f);
-        }
-      };
-      load_taps(0);
-      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x) {
-        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
-          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
-          float2 acc[2][4];
+          for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = bv;
+        if (active) {
+          const uint8_t* base = stage + in_off;
+          float2 w[KK][KK];
 #pragma unroll
-          for (int ty = 0; ty < 2; ++ty)
+          for (int iy = 0; iy < RT; ++iy) {
+            float2 x[CT];
 #pragma unroll
-            for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = bv;
-          if (active) {
-            const uint8_t* base = smem + P.off_in + s * P.in_bytes + in_off;
+            for (int cx = 0; cx < CT; ++cx) x[cx] = *reinterpret_cast<const float2*>(base + iy * row_stride + cx * 128);
+            if (iy < KK) {
 #pragma unroll
-            for (int iy = 0; iy < RT; ++iy) {
-              float2 x[CT];
+              for (int kx = 0; kx < KK; ++kx) w[iy][kx] = taps[(iy * KK + kx) * 16];
+            }
 #pragma unroll
-              for (int cx = 0; cx < CT; ++cx) x[cx] = *reinterpret_cast<const float2*>(base + iy * row_stride + cx * 128);
+            for (int ty = 0; ty < 2; ++ty) {
+              const int ky = iy - ty * SH;
+              if (ky < 0 || ky >= KK) continue;
 #pragma unroll
-              for (int ty = 0; ty < 2; ++ty) {
-                const int ky = iy - ty * SH;
-                if (ky < 0 || ky >= KK) continue;
+              for (int kx = 0; kx < KK; ++kx)
 #pragma unroll
-                for (int kx = 0; kx < KK; ++kx)
-#pragma unroll
-                  for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = __ffma2_rn(x[tx * SW + kx], w[ky * KK + kx], acc[ty][tx]);
-              }
+                for (int tx = 0; tx < 4; ++tx) acc[ty][tx] = __ffma2_rn(x[tx * SW + kx], w[ky][kx], acc[ty][tx]);
             }
           }
-          mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
-          load_taps(kb + 1 < P.nkb ? kb + 1 : 0);
-          uint32_t hi[2][4], lo[2][4];
+        }
+        mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+        uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) {
+            float2 v = acc[ty][tx];
+            if (hsw) {  // same operation order as the stand-alone kernel (engine.cu: dw_tile)
+              float2 tq = __fadd2_rn(v, make_float2(3.0f, 3.0f));
+              tq.x = fminf(fmaxf(tq.x, 0.0f), 6.0f), tq.y = fminf(fmaxf(tq.y, 0.0f), 6.0f);
+              v = __fmul2_rn(__fmul2_rn(v, tq), make_float2(0.16666667f, 0.16666667f));
+            } else if (P.dw_act != ACT_NONE) {
+              v.x = act_rt(v.x, P.dw_act), v.y = act_rt(v.y, P.dw_act);
+            }
+            if (affine) v.x = v.x * P.dw_ps + P.dw_pb, v.y = v.y * P.dw_ps + P.dw_pb;
+            split2(v.x, v.y, hi[ty][tx], lo[ty][tx]);
+          }
+        mbar_wait(FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        if (active) {
+          uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
 #pragma unroll
           for (int ty = 0; ty < 2; ++ty)
 #pragma unroll
             for (int tx = 0; tx < 4; ++tx) {
-              float2 v = acc[ty][tx];
-              if (hsw) {  // same operation order as the stand-alone kernel (engine.cu: dw_tile)
-                float2 tq = __fadd2_rn(v, make_float2(3.0f, 3.0f));
-                tq.x = fminf(fmaxf(tq.x, 0.0f), 6.0f), tq.y = fminf(fmaxf(tq.y, 0.0f), 6.0f);
-                v = __fmul2_rn(__fmul2_rn(v, tq), make_float2(0.16666667f, 0.16666667f));
-              } else if (P.dw_act != ACT_NONE) {
-                v.x = act_rt(v.x, P.dw_act), v.y = act_rt(v.y, P.dw_act);
-              }
-              if (affine) v.x = v.x * P.dw_ps + P.dw_pb, v.y = v.y * P.dw_ps + P.dw_pb;
-              split2(v.x, v.y, hi[ty][tx], lo[ty][tx]);
+              const uint32_t o = (uint32_t)(ty * P.TW + tx) * 16u;
+              *reinterpret_cast<uint32_t*>(ab + o) = hi[ty][tx];
+              *reinterpret_cast<uint32_t*>(ab + FB_APART + o) = lo[ty][tx];
             }
-          const uint32_t sa = it & 1u, pha = (it >> 1) & 1u;
-          mbar_wait(FB_BAR(FB_AB_EMPTY + sa), pha ^ 1u);
-          if (active) {
-            uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
-#pragma unroll
-            for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-              for (int tx = 0; tx < 4; ++tx) {
-                const uint32_t o = (uint32_t)(ty * P.TW + tx) * 16u;
-                *reinterpret_cast<uint32_t*>(ab + o) = hi[ty][tx];
-                *reinterpret_cast<uint32_t*>(ab + FB_APART + o) = lo[ty][tx];
-              }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(FB_BAR(FB_A_FULL + sa));
         }
+        fence_proxy_async_smem();
+        mbar_arrive(FB_BAR(FB_A_FULL + sa));
       }
     }
   } else {
@@ -464,7 +462,14 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   if (M <= 0) return true;
 
   FbParams P{};
-  P.dw_w = f.dw_w, P.dw_b = f.dw_b, P.dw_act = f.dw_act, P.dw_ps = f.dw_ps, P.dw_pb = f.dw_pb;
+  P.dw_pk = nullptr, P.dw_act = f.dw_act, P.dw_ps = f.dw_ps, P.dw_pb = f.dw_pb;
+  if (f.k) {
+    auto itd = st->dwp.find(f.dw_key);
+    if (itd == st->dwp.end()) return false;
+    P.dw_pk = itd->second;
+  }
+  const size_t tap_bytes = f.k ? (size_t)(f.k * f.k + 1) * 128 : 0;
+  P.tap_bytes = (uint32_t)tap_bytes;
   P.se_scale = f.se_scale, P.HW = f.Ho * f.Wo;
   P.wpk = w->packed, P.bias = f.bias, P.act = f.act, P.ps = f.ps, P.pb = f.pb;
   P.C = f.C, P.N = f.N, P.BN = w->BN, P.nkb = w->nkb, P.n_tiles = w->n_tiles;
@@ -500,11 +505,11 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
         const int rows_in = (TH - 1) * f.sh + f.k, cols_in = (TW - 1) * f.sw + f.k;
         if (rows_in > 256 || cols_in > 256) continue;
         const size_t in_bytes = (size_t)rows_in * cols_in * 128;
-        int ns = 3;
-        while (ns >= 2 && fixed + ns * in_bytes > FB_SMEM_MAX) --ns;
+        int ns = 4;
+        while (ns >= 2 && fixed + ns * (in_bytes + tap_bytes) > FB_SMEM_MAX) --ns;
         if (ns < 2) continue;
         const double tiles = (double)cdiv(f.Ho, TH) * cdiv(f.Wo, TW);
-        const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.1 : 1.0);
+        const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.2 : ns == 3 ? 1.05 : 1.0);
         if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns;
       }
     if (!bTH) return false;
@@ -526,7 +531,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   }
   P.n_work = n_sp * w->n_tiles;
   P.off_in = 2 * FB_EP_TILE;
-  P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
+  P.off_a = P.off_in + (uint32_t)P.ns_in * (P.in_bytes + P.tap_bytes);
   P.off_b = P.off_a + 2 * FB_ABUF;
   P.off_ctrl = P.off_b + 2 * (uint32_t)w->BN * 128u;
   // always above half the SM's shared memory: one CTA per SM owns all 512 TMEM columns

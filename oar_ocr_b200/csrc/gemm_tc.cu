@@ -792,6 +792,23 @@ void tc_model_init(oar_model* m) {
         if (kh == 1 && kw == 1 && st->w[(int)oi * 2].KC != 4) st->wf[(int)oi * 2] = pack_weights(w0, op.p[7], cin, true);
         break;
       }
+      case OP_DWCONV: {
+        const int k = op.p[0], c = op.p[6];
+        if (op.p[1] != k) break;
+        const int nkb = (c + 31) / 32, rows = k * k + 1;
+        std::vector<float> pk((size_t)nkb * rows * 32, 0.0f);
+        const float* b0 = host.data() + op.w_off[1];
+        for (int ch = 0; ch < c; ++ch) {
+          float* dst = pk.data() + (size_t)(ch / 32) * rows * 32 + (ch & 31);
+          for (int i = 0; i < k * k; ++i) dst[(size_t)i * 32] = w0[(size_t)i * c + ch];
+          dst[(size_t)k * k * 32] = b0[ch];
+        }
+        float* d = nullptr;
+        OAR_CUDA(cudaMalloc(&d, pk.size() * sizeof(float)));
+        OAR_CUDA(cudaMemcpy(d, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+        st->dwp[(int)oi] = d;
+        break;
+      }
       case OP_DECONV2:
         st->w[(int)oi * 2] = pack_weights(w0, 4 * op.p[1], op.p[0]);
         break;
@@ -813,6 +830,7 @@ void tc_model_free(oar_model* m) {
   if (!st) return;
   for (auto& kv : st->w) cudaFree(kv.second.packed);
   for (auto& kv : st->wf) cudaFree(kv.second.packed);
+  for (auto& kv : st->dwp) cudaFree(kv.second);
   delete st;
   m->tc_state = nullptr;
 }

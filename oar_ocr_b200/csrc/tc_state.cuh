@@ -18,6 +18,7 @@ struct TcWeights {
 struct TcState {
   std::map<int, TcWeights> w;
   std::map<int, TcWeights> wf;  // KC = 4 copies for the fused kernel where `w` holds a KC = 8 packing
+  std::map<int, float*> dwp;    // depthwise taps for the fused kernel: [k-block][K*K taps | bias][32 ch], zero padded
 };
 
 // fp16 hi/lo split + packing into the shared-memory layout of the tcgen05 kernels (gemm_tc.cu)
