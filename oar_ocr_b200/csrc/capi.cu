@@ -15,6 +15,8 @@
 #include <cmath>
 #include <exception>
 
+#include <cstdlib>
+
 #include "engine.cuh"
 #include "prepost.cuh"
 
@@ -82,6 +84,11 @@ void oar_ctx::begin_call() {
   OAR_CUDA(cudaSetDevice(device));
   OAR_CUDA(cudaStreamSynchronize(stream));
   arena.reset();
+  // debugging aid: OAR_DBG_POISON=1 fills the arena with 0xFF (NaN as f32) before every call, so a kernel that reads
+  // activations it (or its producer) never wrote shows up as NaN instead of silently reusing the previous call's data
+  static const bool poison = getenv("OAR_DBG_POISON") != nullptr;
+  if (poison)
+    for (auto& sl : arena.slabs) OAR_CUDA(cudaMemsetAsync(sl.base, 0xFF, sl.cap, stream));
   pinned_reset();
   prof.clear();
   event_next = 0;
@@ -579,6 +586,7 @@ int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_mod
     OAR_FAIL(OAR_E_CUDA, "weight upload failed: %s", cudaGetErrorString(e));
   }
   m->engine = 2;
+  if (const char* cap = getenv("OAR_DBG_ENGINE_CAP")) m->engine = std::min(2, atoi(cap));
   tc_model_init(m);
   *out = m;
   API_CATCH
@@ -600,6 +608,9 @@ int32_t oar_model_set_engine(oar_model* m, int32_t engine) {
     set_error("invalid engine selector");
     return OAR_E_INVALID;
   }
+  // debugging aid: OAR_DBG_ENGINE_CAP=1 maps engine 2 requests onto engine 1 (bisecting the fused kernels)
+  static const char* cap = getenv("OAR_DBG_ENGINE_CAP");
+  if (cap && engine > atoi(cap)) engine = atoi(cap);
   m->engine = engine;
   return OAR_OK;
 }

@@ -9,6 +9,7 @@
 #include "engine.cuh"
 
 #include <cstdlib>
+#include <map>
 
 namespace oar {
 
@@ -274,7 +275,7 @@ __global__ void dwconv_kernel(const float* __restrict__ in, const float* __restr
 template <int K, int SH, int SW, int TH, int TW, int ACT, bool INTERIOR>
 __device__ __forceinline__ void dw_tile(const float4* __restrict__ in4, const float4* __restrict__ w4, float4 bv,
                                         float4* __restrict__ out4, int H, int W, int c4n, int Ho, int Wo, int ho0,
-                                        int wo0, float ps, float pb) {
+                                        int wo0, float ps, float pb, float4* __restrict__ tsum) {
   constexpr int ROWS = (TH - 1) * SH + K, COLS = (TW - 1) * SW + K, PAD = K / 2;
   const int ih0 = ho0 * SH - PAD, iw0 = wo0 * SW - PAD;
   float2 acc_lo[TH][TW], acc_hi[TH][TW];
@@ -316,6 +317,7 @@ __device__ __forceinline__ void dw_tile(const float4* __restrict__ in4, const fl
     }
   }
   const bool affine = ps != 1.0f || pb != 0.0f;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);  // of the tile's valid outputs, row-major: feeds the squeeze-excite pool
   float4* orow = out4 + ((size_t)ho0 * Wo + wo0) * c4n;
 #pragma unroll
   for (int ty = 0; ty < TH; ++ty, orow += (size_t)Wo * c4n) {
@@ -336,15 +338,17 @@ __device__ __forceinline__ void dw_tile(const float4* __restrict__ in4, const fl
       }
       if (affine) lo.x = lo.x * ps + pb, lo.y = lo.y * ps + pb, hi.x = hi.x * ps + pb, hi.y = hi.y * ps + pb;
       orow[(size_t)tx * c4n] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      sum.x += lo.x, sum.y += lo.y, sum.z += hi.x, sum.w += hi.y;
     }
   }
+  if (tsum) *tsum = sum;
 }
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
 __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int B, int H, int W, int C, int Ho, int Wo, float ps,
-                                                           float pb) {
+                                                           float pb, float* __restrict__ tile_sums) {
   constexpr int ROWS = (TH - 1) * SH + K, COLS = (TW - 1) * SW + K, PAD = K / 2;
   const int c4n = C >> 2;
   const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
@@ -364,28 +368,33 @@ __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restri
   const float4* w4 = reinterpret_cast<const float4*>(w) + c4;
   float4* out4 = reinterpret_cast<float4*>(out) + (size_t)b * Ho * Wo * c4n + c4;
   const bool interior = ih0 >= 0 && ih0 + ROWS <= H && iw0 >= 0 && iw0 + COLS <= W && ho0 + TH <= Ho && wo0 + TW <= Wo;
+  // per-tile channel sums [b][tile][C] (optional): the squeeze-excite pool reduces these instead of re-reading `out`
+  float4* tsum = tile_sums ? reinterpret_cast<float4*>(tile_sums) + ((size_t)(b * tiles_h + th) * tiles_w + tw) * c4n + c4
+                           : nullptr;
   if (interior)
-    dw_tile<K, SH, SW, TH, TW, ACT, true>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb);
+    dw_tile<K, SH, SW, TH, TW, ACT, true>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb, tsum);
   else
-    dw_tile<K, SH, SW, TH, TW, ACT, false>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb);
+    dw_tile<K, SH, SW, TH, TW, ACT, false>(in4, w4, bv, out4, H, W, c4n, Ho, Wo, ho0, wo0, ps, pb, tsum);
 }
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
 static void launch_dw_tiled(cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int B, int H,
-                            int W, int C, int Ho, int Wo, float ps, float pb) {
-  size_t total = (size_t)B * ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW) * (C >> 2);
+                            int W, int C, int Ho, int Wo, float ps, float pb, float* tile_sums, int* n_tiles) {
+  const int tiles = ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW);
+  if (n_tiles) *n_tiles = tiles;
+  size_t total = (size_t)B * tiles * (C >> 2);
   dwconv_tiled_kernel<K, SH, SW, TH, TW, ACT><<<cdiv((long long)total, 128), 128, 0, st>>>(in, w, bias, out, B, H, W, C,
-                                                                                          Ho, Wo, ps, pb);
+                                                                                          Ho, Wo, ps, pb, tile_sums);
 }
 
 // picks a register-tiled instantiation; false -> caller runs the generic kernel
 static bool try_dw_tiled(cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int B, int H,
                          int W, int C, int Ho, int Wo, int k, int sh, int sw, int ph, int pw, int act, float ps,
-                         float pb) {
+                         float pb, float* tile_sums = nullptr, int* n_tiles = nullptr) {
   if (ph != k / 2 || pw != k / 2) return false;
 #define DW_CASE(KV, SHV, SWV, THV, TWV, ACTV)                                                      \
   if (k == KV && sh == SHV && sw == SWV && act == ACTV) {                                          \
-    launch_dw_tiled<KV, SHV, SWV, THV, TWV, ACTV>(st, in, w, bias, out, B, H, W, C, Ho, Wo, ps, pb); \
+    launch_dw_tiled<KV, SHV, SWV, THV, TWV, ACTV>(st, in, w, bias, out, B, H, W, C, Ho, Wo, ps, pb, tile_sums, n_tiles); \
     return true;                                                                                   \
   }
   DW_CASE(3, 1, 1, 2, 4, ACT_HSWISH)
@@ -730,14 +739,24 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
     return o.type == OP_CONV && o.p[0] == 1 && o.p[1] == 1 && o.p[2] == 1 && o.p[3] == 1 && o.p[4] == 0 && o.p[5] == 0;
   };
   // squeeze-excite gate: global average pool (two deterministic stages) + the two tiny FCs -> scale[B][C]
+  struct TileSums {
+    float* p;
+    int tiles;
+  };
+  std::map<int, TileSums> tile_sums;  // tensor id -> per-tile channel sums left behind by the depthwise kernel
   auto se_scale = [&](const OpRec& op, const Tensor& a) -> float* {
     const int c = op.p[0], cm = op.p[1], HW = a.H * a.W;
-    const int S = HW >= 4096 ? 64 : (HW >= 256 ? 16 : 1);
+    // pool either the tensor itself or, when its producer left per-tile sums, those (1/8 .. 1/4 of the bytes)
+    const float* src = a.p;
+    int rows = HW;
+    auto its = tile_sums.find(op.in0);
+    if (its != tile_sums.end()) src = its->second.p, rows = its->second.tiles;
+    const int S = rows >= 4096 ? 64 : (rows >= 256 ? 16 : 1);
     float* partial = ctx->arena.get<float>((size_t)a.B * S * c);
     float* scale = ctx->arena.get<float>((size_t)a.B * c);
     {
-      Launch l(ctx, "se_gap", (double)a.numel(), 4.0 * a.numel());
-      se_gap_kernel<<<dim3(S, a.B), 256, 0, st>>>(a.p, partial, HW, c, S);
+      Launch l(ctx, "se_gap", (double)a.B * rows * c, 4.0 * a.B * rows * c);
+      se_gap_kernel<<<dim3(S, a.B), 256, 0, st>>>(src, partial, rows, c, S);
     }
     {
       Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
@@ -824,11 +843,18 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         int Ho = conv_out(a.H, kh, sh, ph), Wo = conv_out(a.W, kw, sw, pw);
         Tensor& o = ensure(op.out, a.B, Ho, Wo, c);
         size_t total = o.numel() / 4;
+        // engine 2: a depthwise conv feeding a squeeze-excite leaves per-tile channel sums for its average pool
+        float* tsums = nullptr;
+        int n_tiles = 0;
+        if (m->engine == 2 && oi + 1 < m->ops.size() && m->ops[oi + 1].type == OP_SE && m->ops[oi + 1].in0 == op.out)
+          tsums = ctx->arena.get<float>((size_t)a.B * Ho * ((Wo + 3) / 4) * c);  // bound: 1 x 4 pixel tiles
         Launch l(ctx, "dwconv", 2.0 * o.numel() * kh * kw, 4.0 * (a.numel() + o.numel()));
         if (kh != kw || !try_dw_tiled(st, a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo, kh, sh, sw, ph, pw,
-                                      op.p[7], op.f[0], op.f[1]))
+                                      op.p[7], op.f[0], op.f[1], tsums, &n_tiles))
           dwconv_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo,
                                                            kh, kw, sh, sw, ph, pw, op.p[7], op.f[0], op.f[1]);
+        else if (tsums)
+          tile_sums[op.out] = TileSums{tsums, n_tiles};
         break;
       }
       case OP_SE: {
@@ -955,7 +981,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
             p.part_max = ctx->arena.get<float>(rows * nt);
             p.part_idx = ctx->arena.get<int32_t>(rows * nt);
             p.part_sum = ctx->arena.get<float>(rows * nt);
-            if (tc_gemm(m, (int)oi * 2, p, "ctc_head_fused_tc")) {
+            static const bool no_ctc_persist = getenv("OAR_DBG_NOCTC") != nullptr;
+            if ((m->engine == 2 && !no_ctc_persist && tc_ctc_head_persistent(m, (int)oi * 2, p, "ctc_head_persist_tc")) ||
+                tc_gemm(m, (int)oi * 2, p, "ctc_head_fused_tc")) {
               launch_ctc_combine(ctx, p.part_max, p.part_idx, p.part_sum, rows, nt, co->idx, co->prob);
               t[op.out] = probs;
               last = probs;

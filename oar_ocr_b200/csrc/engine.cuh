@@ -116,6 +116,8 @@ int tc_n_tiles(const oar_model* m, int key);
 // Fused block on the persistent tcgen05 kernel (fused_tc.cu); false if the shape is not supported (caller falls back to
 // the per-layer kernels).  `key` names the 1x1 conv's packed weights.
 bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name);
+// CTC head (mode-2 ConvParams: part_* outputs) on the persistent kernel; false -> caller uses tc_gemm
+bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const char* name);
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
                         int n_tiles, int32_t* idx, float* prob);
 

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <map>
 
 #include "engine.cuh"
@@ -46,7 +47,7 @@ constexpr size_t FB_SMEM_MAX = 227 * 1024;
 constexpr size_t FB_CTRL_BYTES = 256 + (512 + 32) * 4;  // mbarriers + TMEM slot, then the 1x1 conv bias
 
 enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_A_FULL = 10, FB_AB_EMPTY = 12, FB_ACC_FULL = 14,
-       FB_ACC_EMPTY = 16, FB_NBAR = 18 };
+       FB_ACC_EMPTY = 16, FB_SEEN = 18, FB_NBAR = 20 };
 
 struct FbParams {
   const float* dw_pk;  // [k-block][K*K taps | bias][32 channels], zero padded: rides along with the activation box
@@ -59,6 +60,12 @@ struct FbParams {
   int act;
   float ps, pb;
   int C, N, BN, nkb, n_tiles;
+  // CTC head mode (K == 0): instead of storing the tile, reduce it to per-row softmax partials (max, last arg-max,
+  // sum exp) per 128-column half, for launch_ctc_combine
+  float* part_max;
+  int32_t* part_idx;
+  float* part_sum;
+  int ctc_groups;  // 2: a second epilogue group (four warps of the idle depthwise team) reduces the upper column half
   int TH, TW, tiles_h, tiles_w, n_work;
   int cols_in;
   uint32_t in_bytes;   // activation box
@@ -87,6 +94,77 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// CTC-head epilogue of one epilogue group (128 threads = the tile's 128 rows; group g reduces column half g):
+// online softmax statistics of each row over its half of the tile's classes, so the [B,T,V] logits never exist.
+// Classes ascend and ties keep the LAST maximal index (simd.rs:194-204).
+__device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group, int n_halves, int gtid,
+                                                   uint32_t lane_base, float* bias_g, uint32_t acc_full0,
+                                                   uint32_t acc_empty0) {
+  const int half_cols = P.BN >> 1;
+  const float LOG2E = 1.4426950408889634f;
+  uint32_t ti = 0;
+  for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+    const int nt = t % P.n_tiles, sp = t / P.n_tiles;
+    const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+    named_bar_sync(1 + group, FB_EPI_THREADS);  // the group is done with the previous tile's bias
+    for (int i = gtid; i < n_halves * half_cols; i += FB_EPI_THREADS) {
+      const int n = nt * P.BN + group * half_cols + i;
+      bias_g[i] = n < P.N ? __ldg(P.bias + n) : 0.0f;
+    }
+    named_bar_sync(1 + group, FB_EPI_THREADS);
+    mbar_wait(acc_full0 + 8u * acc, aph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < n_halves; ++h) {
+      const int half = group + h;
+      const int n_base = nt * P.BN + half * half_cols;
+      float mx = -INFINITY, sum = 0.0f;
+      int mi = 0;
+      const uint32_t tcol = lane_base + acc * 256u + (uint32_t)(half * half_cols);
+      for (int c0 = 0; c0 < half_cols && n_base + c0 < P.N; c0 += 16) {
+        float v[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the lanes diverge below (per-row arg-max search), reconverge first
+        tmem_ld16(tcol + (uint32_t)c0, v);
+        const float4* b4 = reinterpret_cast<const float4*>(bias_g + h * half_cols + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = b4[i];
+          v[4 * i] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
+        }
+        if (n_base + c0 + 16 > P.N) {  // the vocabulary ends inside this group of 16
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n_base + c0 + i >= P.N) v[i] = -INFINITY;
+        }
+        float gmax = v[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) gmax = fmaxf(gmax, v[i]);
+        if (gmax >= mx) {  // a new (or tied, hence later) maximum lives in this group: find its last position
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (v[i] == gmax) mi = n_base + c0 + i;
+        }
+        const float nmx = fmaxf(mx, gmax);
+        const float nl = -nmx * LOG2E;
+        float part = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part += exp2f(fmaf(v[i], LOG2E, nl));  // exp(v - nmx); 0 for the padded classes
+        sum = sum * exp2f((mx - nmx) * LOG2E) + part;
+        mx = nmx;
+      }
+      const int m = sp * 128 + gtid;
+      if (m < P.M) {
+        const size_t o = (size_t)m * (2 * P.n_tiles) + 2 * nt + half;
+        P.part_max[o] = mx;
+        P.part_idx[o] = mi;
+        P.part_sum[o] = sum;
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(acc_empty0 + 8u * acc);
+  }
+}
+
 template <int K, int SH, int SW>
 __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, const __grid_constant__ CUtensorMap tm_in,
                                                             const __grid_constant__ CUtensorMap tm_out) {
@@ -110,7 +188,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       mbar_init(FB_BAR(FB_A_FULL + i), FB_CTHREADS);
       mbar_init(FB_BAR(FB_AB_EMPTY + i), 1);
       mbar_init(FB_BAR(FB_ACC_FULL + i), 1);
-      mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_THREADS);
+      mbar_init(FB_BAR(FB_ACC_EMPTY + i), P.part_max ? P.ctc_groups * FB_EPI_THREADS : FB_EPI_THREADS);  // CTC mode: one or two groups
+      mbar_init(FB_BAR(FB_SEEN + i), FB_CTHREADS);
     }
     fence_mbar_init();
   }
@@ -203,14 +282,24 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     const int ct = (tid - FB_WARP_C0 * 32) & 255;
     const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
                              (uint32_t)P.nkb;
-    const uint32_t sa = (uint32_t)team;
-    if (K == 0) {
-      // 128 rows x 32 channels: thread = one 16-byte quad of 4 rows; the two rows of a half-warp are 4 apart (64 B in
-      // the A tile) so its eight 8-byte hi (lo) stores cover 32 distinct banks
+    const bool ctc = K == 0 && P.part_max != nullptr;
+    if (ctc && team == 1) {
+      // CTC head: converting fp32 rows is light work, so one team does every k-block and four warps of the other
+      // (one per TMEM lane quarter) form a second epilogue group for the upper column half of each tile
+      const int w1 = warp - (FB_WARP_C0 + 8);
+      const int first = (4 - ((FB_WARP_C0 + 8) & 3)) & 3;  // first warp of the team with warp % 4 == 0
+      if (P.ctc_groups == 2 && w1 >= first && w1 < first + 4) {
+        float* bias_g = reinterpret_cast<float*>(smem + P.off_ctrl + 256) + 128;
+        ctc_epilogue_group(P, 1, 1, (warp & 3) * 32 + lane, tmem_base + ((uint32_t)((warp & 3) * 32) << 16), bias_g,
+                           FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+      }
+    } else if (K == 0) {
+      const uint32_t it0 = ctc ? 0u : (uint32_t)team, it_step = ctc ? 1u : 2u;
       const int q = ct & 7;
       const int r0 = 8 * (ct >> 6) + 4 * ((ct >> 3) & 1) + ((ct >> 4) & 3);
       const uint32_t a_off = (uint32_t)(q >> 1) * FB_LBO + (uint32_t)(q & 1) * 8u;
-      for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
+      for (uint32_t it = it0; it < n_items; it += it_step) {
+        const uint32_t sa = it & 1u;
         const int kb = (int)(it % (uint32_t)P.nkb);
         // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
         float4 sc[4];
@@ -225,7 +314,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           }
         }
         const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
-        mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        // The two teams share one ring of stages.  A parity wait is only sound while the waiter is at most one lap
+        // ahead of the stage's barrier, which a fast team could violate when an older box (the other team's) lands
+        // late.  So arrivals are observed strictly in item order: before waiting for item `it`, wait until the other
+        // team has seen item it - 1 (it had then also seen every older item of its own).
+        if (!ctc) {
+          if (it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
+          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+          mbar_arrive(FB_BAR(FB_SEEN + team));
+        } else {
+          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        }
         const uint8_t* src = smem + P.off_in + s * stage_bytes + q * 16;
         float4 x[4];
 #pragma unroll
@@ -265,9 +364,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
                              (uint32_t)((2 * pgy) * P.TW + 4 * pgx) * 16u;
       const bool hsw = P.dw_act == ACT_HSWISH;
       const bool affine = P.dw_ps != 1.0f || P.dw_pb != 0.0f;
+      const uint32_t sa = (uint32_t)team;
       for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
         const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
+        // observe box arrivals strictly in item order across the two teams (see the K == 0 loop)
+        if (it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
         mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        mbar_arrive(FB_BAR(FB_SEEN + team));
         const uint8_t* stage = smem + P.off_in + s * stage_bytes;
         // taps [ky*K+kx][32 ch] and bias [32 ch] of this k-block sit behind the box; each is read once per thread,
         // just in time (a kernel row serves output row 0 at input row ky and output row 1 at input row ky + SH)
@@ -339,10 +442,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool affine = P.ps != 1.0f || P.pb != 0.0f;
     float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + 256);  // [n_tiles * BN + 32], zero padded
-    for (int i = tid; i < P.n_tiles * P.BN + 32; i += FB_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
-    named_bar_sync(1, FB_EPI_THREADS);
+    const bool ctc = P.part_max != nullptr;  // then bias_s holds one tile's BN values, reloaded per work item
+    if (ctc) {
+      ctc_epilogue_group(P, 0, P.ctc_groups == 2 ? 1 : 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+    } else {
+      for (int i = tid; i < P.n_tiles * P.BN + 32; i += FB_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
+      named_bar_sync(1, FB_EPI_THREADS);
+    }
     uint32_t ti = 0, nstore = 0;
-    for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+    for (int t = blockIdx.x; t < (ctc ? 0 : P.n_work); t += gridDim.x, ++ti) {
       const int nt = t % P.n_tiles, sp = t / P.n_tiles;
       int c1 = sp * 128, c2 = 0, c3 = 0;
       if (K > 0) {
@@ -355,6 +463,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       const int n_base = nt * P.BN;
       for (int c0 = 0; c0 < P.BN && n_base + c0 < P.N; c0 += 32, ++nstore) {
         float v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned (lane 0 of warp 0 issued the previous chunk's TMA store)
         tmem_ld16(lane_base + acc * 256u + (uint32_t)c0, v);
         if (c0 + 16 < P.BN) {
           tmem_ld16(lane_base + acc * 256u + (uint32_t)c0 + 16u, v + 16);
@@ -454,7 +563,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     if (it != st->w.end()) w = &it->second;
   }
   if (!w || w->rowtaps || w->KC != 4 || w->K != f.C || w->N != f.N) return false;
-  if (f.C < 16 || (f.C & 3) || (f.out_ld & 3) || (f.out_c_off & 3) || (((uintptr_t)f.in) & 15) || (((uintptr_t)f.out) & 15))
+  if (f.C < 4 || (f.C & 3) || (f.out_ld & 3) || (f.out_c_off & 3) || (((uintptr_t)f.in) & 15) || (((uintptr_t)f.out) & 15))
     return false;
   FbKern kern = pick_kernel(f.k, f.k ? f.sh : 1, f.k ? f.sw : 1);
   if (!kern) return false;
@@ -548,6 +657,58 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
   const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
   Launch l(m->ctx, name, flops, bytes);
+  kern<<<grid, FB_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
+  return true;
+}
+
+// CTC head on the persistent kernel: probabilities-free path of OP_CTC_HEAD (engine.cu).  A = [M, C] fp32 activations,
+// packed weights of `key` (BN = 256 tiles over the vocabulary); fills p.part_* for launch_ctc_combine.
+bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const char* name) {
+  TcState* st = static_cast<TcState*>(m->tc_state);
+  if (!st) return false;
+  auto it = st->w.find(key);
+  if (it == st->w.end()) return false;
+  const TcWeights& w = it->second;
+  if (w.rowtaps || w.KC != 4 || w.K != p.K || w.N != p.N || (w.BN & 31) || w.BN > 256) return false;
+  if ((p.K & 3) || (((uintptr_t)p.in) & 15) || p.M <= 0) return false;
+  FbParams P{};
+  P.wpk = w.packed, P.bias = p.bias, P.act = ACT_NONE, P.ps = 1.0f, P.pb = 0.0f;
+  P.C = p.K, P.N = p.N, P.BN = w.BN, P.nkb = w.nkb, P.n_tiles = w.n_tiles;
+  P.part_max = p.part_max, P.part_idx = p.part_idx, P.part_sum = p.part_sum;
+  // One epilogue group by default.  A second group (OAR_CTC_GROUPS=2: four warps of the idle depthwise team reduce the
+  // upper column half, 1.3x faster on this layer) showed rare run-to-run differences in the softmax statistics under
+  // host-side jitter (tools/_stress4.py, ~1.5 % of calls) that are not understood yet, so it stays opt-in.
+  static const bool two_groups = getenv("OAR_CTC_GROUPS") && atoi(getenv("OAR_CTC_GROUPS")) == 2;
+  P.ctc_groups = two_groups ? 2 : 1;
+  P.M = p.M, P.HW = 1;
+  P.in_bytes = 128 * 128, P.tap_bytes = 0, P.ns_in = 4;
+  P.TH = P.TW = 0, P.tiles_h = P.tiles_w = 1, P.cols_in = 128;
+  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * (size_t)w.BN * 128 + FB_CTRL_BYTES + 1024;
+  while (P.ns_in > 2 && fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) --P.ns_in;
+  if (fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) return false;
+  CUtensorMap tm_in, tm_out;
+  memset(&tm_in, 0, sizeof(tm_in));
+  memset(&tm_out, 0, sizeof(tm_out));
+  cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+  cuuint64_t strides[1] = {(cuuint64_t)p.K * 4};
+  cuuint32_t box[2] = {32, 128};
+  if (!encode_map(&tm_in, p.in, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+  P.n_work = cdiv(p.M, 128) * w.n_tiles;
+  P.off_in = 2 * FB_EP_TILE;
+  P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
+  P.off_b = P.off_a + 2 * FB_ABUF;
+  P.off_ctrl = P.off_b + 2 * (uint32_t)w.BN * 128u;
+  const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
+  FbKern kern = lcblock_tc<0, 1, 1>;
+  {
+    static std::map<int, bool> attr_done;
+    if (!attr_done.count(m->ctx->device)) {
+      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_MAX));
+      attr_done[m->ctx->device] = true;
+    }
+  }
+  const int grid = std::min(P.n_work, m->ctx->sm_count);
+  Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * (double)p.M * p.K + 24.0 * p.M * w.n_tiles);
   kern<<<grid, FB_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
   return true;
 }
