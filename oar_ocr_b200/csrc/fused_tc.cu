@@ -72,6 +72,7 @@ struct FbParams {
   uint32_t tap_bytes;  // depthwise taps + bias of one k-block (0 for K == 0); stage = box + taps
   int ns_in;
   uint32_t off_in, off_a, off_b, off_ctrl;
+  int ep_tiles;  // epilogue staging tiles: 2 (store of one overlaps the fill of the other) or 1 when shared memory is short
 };
 
 __device__ __forceinline__ float act_rt(float v, int act) {
@@ -497,16 +498,22 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = v[i] * P.ps + P.pb;
         }
-        // staging tile nstore & 1: its previous store (two groups ago) was waited for by thread 0 before the last barrier
-        uint8_t* ep = smem + (nstore & 1u) * FB_EP_TILE + tid * 128;
+        // two staging tiles: tile nstore & 1 was released by thread 0's wait before the previous barrier (its store was
+        // issued two groups ago); one tile: wait for the previous store to have read it before anybody refills it
+        const uint32_t slot = P.ep_tiles == 2 ? (nstore & 1u) : 0u;
+        if (P.ep_tiles == 1) {
+          if (tid == 0) bulk_wait_read_all();
+          named_bar_sync(1, FB_EPI_THREADS);
+        }
+        uint8_t* ep = smem + slot * FB_EP_TILE + tid * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(ep + ((i ^ (tid & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         fence_proxy_async_smem();
-        if (tid == 0) bulk_wait_read_all();  // every store issued so far has read its staging tile
+        if (P.ep_tiles == 2 && tid == 0) bulk_wait_read_all();  // every store issued so far has read its staging tile
         named_bar_sync(1, FB_EPI_THREADS);
         if (tid == 0) {
-          const uint32_t src = sbase + (nstore & 1u) * FB_EP_TILE;
+          const uint32_t src = sbase + slot * FB_EP_TILE;
           if (K == 0)
             tma_store_2d(&tm_out, src, n_base + c0, c1);
           else
@@ -607,22 +614,28 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     // tile = TH x TW output pixels of one image (TH even, TW % 4 == 0, <= 128 pixels).  Every tile costs the
     // depthwise warps the same time, so minimise the tile count first and the halo traffic second.
     double best = 1e300;
-    int bTH = 0, bTW = 0, bns = 0;
+    int bTH = 0, bTW = 0, bns = 0, bep = 2;
     for (int TH = 2; TH <= 32; TH += 2)
       for (int TW = 4; TW <= 64; TW += 4) {
         if (TH * TW > 128) continue;
         const int rows_in = (TH - 1) * f.sh + f.k, cols_in = (TW - 1) * f.sw + f.k;
         if (rows_in > 256 || cols_in > 256) continue;
         const size_t in_bytes = (size_t)rows_in * cols_in * 128;
-        int ns = 4;
-        while (ns >= 2 && fixed + ns * (in_bytes + tap_bytes) > FB_SMEM_MAX) --ns;
-        if (ns < 2) continue;
         const double tiles = (double)cdiv(f.Ho, TH) * cdiv(f.Wo, TW);
-        const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.2 : ns == 3 ? 1.05 : 1.0);
-        if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns;
+        // input stages: 4 = two per team; 3 still lets the producer run one box ahead of both teams; with 2 every
+        // team waits out a full TMA round trip per k-block.  A single staging tile buys 16 KB for another stage.
+        for (int ep = 2; ep >= 1; --ep) {
+          const size_t fx = fixed - (size_t)(2 - ep) * FB_EP_TILE;
+          int ns = 4;
+          while (ns >= 2 && fx + ns * (in_bytes + tap_bytes) > FB_SMEM_MAX) --ns;
+          if (ns < 2) continue;
+          const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.3 : ns == 3 ? 1.05 : 1.0) *
+                              (ep == 1 ? 1.03 : 1.0);
+          if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns, bep = ep;
+        }
       }
     if (!bTH) return false;
-    P.TH = bTH, P.TW = bTW, P.ns_in = bns;
+    P.TH = bTH, P.TW = bTW, P.ns_in = bns, P.ep_tiles = bep;
     P.tiles_h = cdiv(f.Ho, bTH), P.tiles_w = cdiv(f.Wo, bTW);
     const int rows_in = (bTH - 1) * f.sh + f.k;
     P.cols_in = (bTW - 1) * f.sw + f.k;
@@ -639,7 +652,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     if (!encode_map(&tm_out, f.out + f.out_c_off, 4, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   }
   P.n_work = n_sp * w->n_tiles;
-  P.off_in = 2 * FB_EP_TILE;
+  if (f.k == 0) P.ep_tiles = 2;
+  P.off_in = (uint32_t)P.ep_tiles * FB_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * (P.in_bytes + P.tap_bytes);
   P.off_b = P.off_a + 2 * FB_ABUF;
   P.off_ctrl = P.off_b + 2 * (uint32_t)w->BN * 128u;
@@ -653,6 +667,10 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
       attr_done[ka] = true;
     }
   }
+  static const bool dbg_tiles = getenv("OAR_DBG_TILES") != nullptr;
+  if (dbg_tiles)
+    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d items %d smem %zu\n", f.k, f.sh,
+            f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.n_work, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
   const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
@@ -694,6 +712,7 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   cuuint32_t box[2] = {32, 128};
   if (!encode_map(&tm_in, p.in, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   P.n_work = cdiv(p.M, 128) * w.n_tiles;
+  P.ep_tiles = 2;
   P.off_in = 2 * FB_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
   P.off_b = P.off_a + 2 * FB_ABUF;
