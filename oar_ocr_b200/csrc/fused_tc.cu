@@ -38,6 +38,7 @@ constexpr int FB_THREADS = 704;  // 4 epilogue + TMA + MMA + 16 depthwise/conver
 constexpr int FB_EPI_THREADS = 128;
 constexpr int FB_WARP_TMA = 4, FB_WARP_MMA = 5, FB_WARP_C0 = 6;
 constexpr int FB_CTHREADS = 256;  // one team: the two teams of depthwise warps take alternate k-blocks
+constexpr int FB_CWARPS = FB_CTHREADS / 32, FB_EPI_WARPS = FB_EPI_THREADS / 32;  // mbarrier arrivals are per warp
 constexpr uint32_t FB_LBO = 128 * 16 + 16;   // k-chunk stride of the A operand (+16 B: conflict-free split stores)
 constexpr uint32_t FB_APART = 4 * FB_LBO;    // one part (hi or lo) of a 128 x 32 A tile
 constexpr uint32_t FB_ABUF = 2 * FB_APART;
@@ -46,8 +47,8 @@ constexpr int FB_MAX_IN = 4;
 constexpr size_t FB_SMEM_MAX = 227 * 1024;
 constexpr size_t FB_CTRL_BYTES = 256 + (512 + 32) * 4;  // mbarriers + TMEM slot, then the 1x1 conv bias
 
-enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_A_FULL = 10, FB_AB_EMPTY = 12, FB_ACC_FULL = 14,
-       FB_ACC_EMPTY = 16, FB_SEEN = 18, FB_NBAR = 20 };
+enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_B_EMPTY = 12, FB_A_FULL = 16, FB_AB_EMPTY = 18, FB_ACC_FULL = 20,
+       FB_ACC_EMPTY = 22, FB_SEEN = 24, FB_NBAR = 26 };  // AB_EMPTY: the A buffer of a k-block has been consumed
 
 struct FbParams {
   const float* dw_pk;  // [k-block][K*K taps | bias][32 channels], zero padded: rides along with the activation box
@@ -71,6 +72,7 @@ struct FbParams {
   uint32_t in_bytes;   // activation box
   uint32_t tap_bytes;  // depthwise taps + bias of one k-block (0 for K == 0); stage = box + taps
   int ns_in;
+  int nb;              // weight-stage ring depth (2..4): deep enough to cover the L2 round trip of a k-block
   uint32_t off_in, off_a, off_b, off_ctrl;
   int ep_tiles;  // epilogue staging tiles: 2 (store of one overlaps the fill of the other) or 1 when shared memory is short
 };
@@ -84,6 +86,14 @@ __device__ __forceinline__ float act_rt(float v, int act) {
     case ACT_HSIGMOID: return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
     default: return v;
   }
+}
+
+// One mbarrier arrival per warp: 32 lanes arriving on the same word serialise in the shared-memory atomic unit (~1 per
+// cycle), which at 3 barriers x 256 threads per k-block is hundreds of cycles.  __syncwarp orders the lanes' prior
+// shared-memory accesses (and proxy fences) before lane 0's releasing arrive.
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 // x = hi + lo in fp16, two channels packed per 32-bit word
@@ -162,7 +172,7 @@ __device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group,
       }
     }
     tc_fence_before();
-    mbar_arrive(acc_empty0 + 8u * acc);
+    warp_arrive(acc_empty0 + 8u * acc, gtid & 31);
   }
 }
 
@@ -182,15 +192,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
   if (tid == 0) {
     for (int i = 0; i < FB_MAX_IN; ++i) {
       mbar_init(FB_BAR(FB_IN_FULL + i), 1);
-      mbar_init(FB_BAR(FB_IN_EMPTY + i), FB_CTHREADS);
+      mbar_init(FB_BAR(FB_IN_EMPTY + i), FB_CWARPS);
+      mbar_init(FB_BAR(FB_B_FULL + i), 1);
+      mbar_init(FB_BAR(FB_B_EMPTY + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(FB_BAR(FB_B_FULL + i), 1);
-      mbar_init(FB_BAR(FB_A_FULL + i), FB_CTHREADS);
+      mbar_init(FB_BAR(FB_A_FULL + i), FB_CWARPS);
       mbar_init(FB_BAR(FB_AB_EMPTY + i), 1);
       mbar_init(FB_BAR(FB_ACC_FULL + i), 1);
-      mbar_init(FB_BAR(FB_ACC_EMPTY + i), P.part_max ? P.ctc_groups * FB_EPI_THREADS : FB_EPI_THREADS);  // CTC mode: one or two groups
-      mbar_init(FB_BAR(FB_SEEN + i), FB_CTHREADS);
+      mbar_init(FB_BAR(FB_ACC_EMPTY + i), P.part_max ? P.ctc_groups * FB_EPI_WARPS : FB_EPI_WARPS);  // CTC mode: one or two groups
+      mbar_init(FB_BAR(FB_SEEN + i), FB_CWARPS);
     }
     fence_mbar_init();
   }
@@ -230,8 +241,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           }
         }
         if (it_b < n_items) {
-          const uint32_t sb = it_b & 1u, phb = (it_b >> 1) & 1u;
-          if (mbar_test(FB_BAR(FB_AB_EMPTY + sb), phb ^ 1u)) {
+          const uint32_t sb = it_b % (uint32_t)P.nb, phb = (it_b / (uint32_t)P.nb) & 1u;
+          if (mbar_test(FB_BAR(FB_B_EMPTY + sb), phb ^ 1u)) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk) +
                                   ((size_t)(t_b % P.n_tiles) * P.nkb + kb_b) * b_bytes;
             mbar_expect_tx(FB_BAR(FB_B_FULL + sb), b_bytes);
@@ -256,10 +267,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
           mbar_wait(FB_BAR(FB_A_FULL + s), ph);
-          mbar_wait(FB_BAR(FB_B_FULL + s), ph);
+          const uint32_t sb = it % (uint32_t)P.nb;
+          mbar_wait(FB_BAR(FB_B_FULL + sb), (it / (uint32_t)P.nb) & 1u);
           tc_fence_after();
           const uint32_t a_hi = sbase + P.off_a + s * FB_ABUF, a_lo = a_hi + FB_APART;
-          const uint32_t b_hi = sbase + P.off_b + s * b_bytes, b_lo = b_hi + b_part;
+          const uint32_t b_hi = sbase + P.off_b + sb * b_bytes, b_lo = b_hi + b_part;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint64_t ah = make_desc(a_hi + 2 * j * FB_LBO, FB_LBO, 128);
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             umma_f16(d, al, bh, idesc, 1u);
           }
           umma_commit(FB_BAR(FB_AB_EMPTY + s));
+          umma_commit(FB_BAR(FB_B_EMPTY + sb));
           if (kb == P.nkb - 1) umma_commit(FB_BAR(FB_ACC_FULL + acc));
         }
       }
@@ -319,10 +332,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         // ahead of the stage's barrier, which a fast team could violate when an older box (the other team's) lands
         // late.  So arrivals are observed strictly in item order: before waiting for item `it`, wait until the other
         // team has seen item it - 1 (it had then also seen every older item of its own).
-        if (!ctc) {
+        // (with an even number of stages every stage belongs to one team for good, and no handshake is needed)
+        if (!ctc && (P.ns_in & 1)) {
           if (it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
           mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
-          mbar_arrive(FB_BAR(FB_SEEN + team));
+          warp_arrive(FB_BAR(FB_SEEN + team), lane);
         } else {
           mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
         }
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         float4 x[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
-        mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+        warp_arrive(FB_BAR(FB_IN_EMPTY + s), lane);
         if (P.se_scale) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) x[j].x *= sc[j].x, x[j].y *= sc[j].y, x[j].z *= sc[j].z, x[j].w *= sc[j].w;
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           *reinterpret_cast<uint2*>(ab + FB_APART + (r0 + 32 * j) * 16) = make_uint2(lo[j][0], lo[j][1]);
         }
         fence_proxy_async_smem();
-        mbar_arrive(FB_BAR(FB_A_FULL + sa));
+        warp_arrive(FB_BAR(FB_A_FULL + sa), lane);
       }
     } else {
       constexpr int KK = K > 0 ? K : 1;
@@ -369,9 +383,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
         const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
         // observe box arrivals strictly in item order across the two teams (see the K == 0 loop)
-        if (it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
+        const bool handshake = (P.ns_in & 1) != 0;  // even ring: each stage has one owner team, plain parity waits do
+        if (handshake && it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
         mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
-        mbar_arrive(FB_BAR(FB_SEEN + team));
+        if (handshake) warp_arrive(FB_BAR(FB_SEEN + team), lane);
         const uint8_t* stage = smem + P.off_in + s * stage_bytes;
         // taps [ky*K+kx][32 ch] and bias [32 ch] of this k-block sit behind the box; each is read once per thread,
         // just in time (a kernel row serves output row 0 at input row ky and output row 1 at input row ky + SH)
@@ -405,7 +420,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             }
           }
         }
-        mbar_arrive(FB_BAR(FB_IN_EMPTY + s));
+        warp_arrive(FB_BAR(FB_IN_EMPTY + s), lane);
         uint32_t hi[2][4], lo[2][4];
 #pragma unroll
         for (int ty = 0; ty < 2; ++ty)
@@ -435,7 +450,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             }
         }
         fence_proxy_async_smem();
-        mbar_arrive(FB_BAR(FB_A_FULL + sa));
+        warp_arrive(FB_BAR(FB_A_FULL + sa), lane);
       }
     }
   } else {
@@ -522,7 +537,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         }
       }
       tc_fence_before();
-      mbar_arrive(FB_BAR(FB_ACC_EMPTY + acc));
+      warp_arrive(FB_BAR(FB_ACC_EMPTY + acc), lane);
     }
     if (tid == 0) bulk_wait_all();
   }
@@ -590,7 +605,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   P.wpk = w->packed, P.bias = f.bias, P.act = f.act, P.ps = f.ps, P.pb = f.pb;
   P.C = f.C, P.N = f.N, P.BN = w->BN, P.nkb = w->nkb, P.n_tiles = w->n_tiles;
 
-  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * (size_t)w->BN * 128 + FB_CTRL_BYTES + 1024;
+  const size_t b_stage = (size_t)w->BN * 128;
+  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * b_stage + FB_CTRL_BYTES + 1024;  // with the minimum of 2 weight stages
   CUtensorMap tm_in, tm_out;
   memset(&tm_in, 0, sizeof(tm_in));
   memset(&tm_out, 0, sizeof(tm_out));
@@ -624,12 +640,12 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
         const double tiles = (double)cdiv(f.Ho, TH) * cdiv(f.Wo, TW);
         // input stages: 4 = two per team; 3 still lets the producer run one box ahead of both teams; with 2 every
         // team waits out a full TMA round trip per k-block.  A single staging tile buys 16 KB for another stage.
-        for (int ep = 2; ep >= 1; --ep) {
+        for (int ep = 2; ep >= (f.k == 5 ? 1 : 2); --ep) {  // measured: pays for the 5x5 blocks, not for the light 3x3 ones
           const size_t fx = fixed - (size_t)(2 - ep) * FB_EP_TILE;
           int ns = 4;
           while (ns >= 2 && fx + ns * (in_bytes + tap_bytes) > FB_SMEM_MAX) --ns;
           if (ns < 2) continue;
-          const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.3 : ns == 3 ? 1.05 : 1.0) *
+          const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.2 : ns == 3 ? 1.05 : 1.0) *
                               (ep == 1 ? 1.03 : 1.0);
           if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns, bep = ep;
         }
@@ -656,7 +672,10 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   P.off_in = (uint32_t)P.ep_tiles * FB_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * (P.in_bytes + P.tap_bytes);
   P.off_b = P.off_a + 2 * FB_ABUF;
-  P.off_ctrl = P.off_b + 2 * (uint32_t)w->BN * 128u;
+  // whatever shared memory is left goes to the weight ring (up to 4 stages): a k-block of weights is an L2 round trip
+  P.nb = 2;
+  while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * b_stage + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
+  P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)b_stage;
   // always above half the SM's shared memory: one CTA per SM owns all 512 TMEM columns
   const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
   {
@@ -669,8 +688,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   }
   static const bool dbg_tiles = getenv("OAR_DBG_TILES") != nullptr;
   if (dbg_tiles)
-    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d items %d smem %zu\n", f.k, f.sh,
-            f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.n_work, smem);
+    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d smem %zu\n", f.k,
+            f.sh, f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.nb, P.n_work, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
   const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
@@ -713,10 +732,12 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   if (!encode_map(&tm_in, p.in, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
   P.n_work = cdiv(p.M, 128) * w.n_tiles;
   P.ep_tiles = 2;
-  P.off_in = 2 * FB_EP_TILE;
+  P.off_in = 0;  // the CTC epilogue stores nothing through the staging tiles
   P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
   P.off_b = P.off_a + 2 * FB_ABUF;
-  P.off_ctrl = P.off_b + 2 * (uint32_t)w.BN * 128u;
+  P.nb = 2;
+  while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * w.BN * 128 + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
+  P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)w.BN * 128u;
   const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
   FbKern kern = lcblock_tc<0, 1, 1>;
   {
