@@ -105,6 +105,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // CTC-head epilogue of one epilogue group (128 threads = the tile's 128 rows; group g reduces column half g):
 // online softmax statistics of each row over its half of the tile's classes, so the [B,T,V] logits never exist.
 // Classes ascend and ties keep the LAST maximal index (simd.rs:194-204).
@@ -136,31 +142,42 @@ __device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group,
         float v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the lanes diverge below (per-row arg-max search), reconverge first
         tmem_ld16(tcol + (uint32_t)c0, v);
+        // one epilogue warp per scheduler: instruction count is what bounds this loop, so the arithmetic is packed
+        // (f32x2 add / fma), the maximum is a 3-input tree and exp is the bare MUFU.EX2
+        float2 q[8];
         const float4* b4 = reinterpret_cast<const float4*>(bias_g + h * half_cols + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 b = b4[i];
-          v[4 * i] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
+          q[2 * i] = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+          q[2 * i + 1] = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
         }
-        if (n_base + c0 + 16 > P.N) {  // the vocabulary ends inside this group of 16
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n_base + c0 + i >= P.N) v[i] = -INFINITY;
+        if (n_base + c0 + 16 > P.N) {  // the vocabulary ends inside this group of 16 (last tile only)
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (n_base + c0 + 2 * i >= P.N) q[i].x = -INFINITY;
+            if (n_base + c0 + 2 * i + 1 >= P.N) q[i].y = -INFINITY;
+          }
         }
-        float gmax = v[0];
+        float gmax = fmaxf(q[0].x, q[0].y);
 #pragma unroll
-        for (int i = 1; i < 16; ++i) gmax = fmaxf(gmax, v[i]);
+        for (int i = 1; i < 8; ++i) gmax = fmaxf(gmax, fmaxf(q[i].x, q[i].y));
         if (gmax >= mx) {  // a new (or tied, hence later) maximum lives in this group: find its last position
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (v[i] == gmax) mi = n_base + c0 + i;
+          for (int i = 0; i < 8; ++i) {
+            if (q[i].x == gmax) mi = n_base + c0 + 2 * i;
+            if (q[i].y == gmax) mi = n_base + c0 + 2 * i + 1;
+          }
         }
         const float nmx = fmaxf(mx, gmax);
         const float nl = -nmx * LOG2E;
-        float part = 0.0f;
+        float2 part = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) part += exp2f(fmaf(v[i], LOG2E, nl));  // exp(v - nmx); 0 for the padded classes
-        sum = sum * exp2f((mx - nmx) * LOG2E) + part;
+        for (int i = 0; i < 8; ++i) {
+          const float2 a = __ffma2_rn(q[i], make_float2(LOG2E, LOG2E), make_float2(nl, nl));  // (v - nmx) * log2(e)
+          part = __fadd2_rn(part, make_float2(ex2_approx(a.x), ex2_approx(a.y)));  // 0 for the padded classes
+        }
+        sum = sum * ex2_approx((mx - nmx) * LOG2E) + (part.x + part.y);
         mx = nmx;
       }
       const int m = sp * 128 + gtid;
