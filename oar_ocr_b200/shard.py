@@ -37,3 +37,137 @@ def predict_sharded(predict_fn, images, rank: int, world: int, gather: bool = Tr
     for p in parts:
         out.extend(p)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Global crop pooling across ranks: an R-rank run that equals ONE un-sharded predict()
+# ---------------------------------------------------------------------------------------------------------------
+MAX_POOLED_CROPS = 4096  # src/oarocr/ocr.rs:603
+
+
+def plan_pooled_chunks(meta, region_batch_size: int, max_pooled: int = MAX_POOLED_CROPS):
+    """The batch composition of OAROCR::recognize_global (ocr.rs:603-633, 802-827) for the WHOLE image list.
+
+    `meta` lists every successfully cropped region in (image index, detection index) order as
+    (image index, detection index, wh_ratio).  Regions are pooled in that order; a pool is flushed when it holds
+    `max_pooled` crops (and once at the end); a flush stable-sorts its pool by wh_ratio ascending and cuts it into
+    chunks of `region_batch_size`.  Returns the chunks, each a list of positions into `meta`, in processing order."""
+    if region_batch_size <= 0:
+        raise ValueError("region_batch_size must be positive")
+    chunks, pool = [], []
+
+    def flush():
+        order = sorted(pool, key=lambda i: meta[i][2])  # Python's sort is stable, like slice::sort_by
+        for s in range(0, len(order), region_batch_size):
+            chunks.append(order[s:s + region_batch_size])
+
+    for i in range(len(meta)):
+        pool.append(i)
+        if len(pool) >= max_pooled:
+            flush()
+            pool = []
+    if pool:
+        flush()
+    return chunks
+
+
+def predict_pooled(stages, images, rank: int, world: int, region_batch_size: int, rec_score_thresh: float = 0.0,
+                   max_pooled: int = MAX_POOLED_CROPS):
+    """Det + crop on this rank's contiguous block of images, then recognition batches built from the GLOBAL pool of
+    crops exactly as one un-sharded OAROCR::predict would build them, dealt to ranks as whole chunks.
+
+    Block sharding alone (predict_sharded) changes which crops share a recognition batch, hence `tensor_w` and the
+    padded logits; here every chunk has the membership, order and width of the single-process run, so results are
+    identical to it.  One exchange step: region sizes are all-gathered (a few bytes per region), each rank receives
+    the u8 crops of the chunks it was dealt (gather_object per destination; NVLink all-to-all on a GPU box would
+    carry the same payload), results are all-gathered.  world == 1 needs no process group.
+
+    `stages` provides detect(images) -> per image boxes [n,4,2] in reading order; crop(image, boxes) -> list of
+    HxWx3 u8 crops (None where cropping fails); recognize(crops) -> list of (labels, score) for ONE batch.
+    Returns, on every rank, per image a list of dicts {box, det_index, labels, score} in detection order."""
+    import numpy as np
+    start, end = block_partition(len(images), world)[rank]
+    block = images[start:end]
+    boxes = stages.detect(block) if block else []
+    local_crops, local_meta, local_boxes = {}, [], {}
+    for k, (img, b) in enumerate(zip(block, boxes)):
+        gi = start + k
+        local_boxes[gi] = np.asarray(b, np.float32).reshape(-1, 4, 2)
+        crops = stages.crop(img, local_boxes[gi]) if len(local_boxes[gi]) else []
+        for d, c in enumerate(crops):
+            if c is None:
+                continue
+            ratio = float(np.float32(c.shape[1]) / np.float32(max(c.shape[0], 1)))  # ocr.rs:739, f32
+            local_crops[(gi, d)] = c
+            local_meta.append((gi, d, ratio))
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, (local_meta, local_boxes))
+        meta = [m for p in parts for m in p[0]]  # blocks are contiguous: rank order is image order
+        all_boxes = {}
+        for p in parts:
+            all_boxes.update(p[1])
+    else:
+        meta, all_boxes = local_meta, local_boxes
+    chunks = plan_pooled_chunks(meta, region_batch_size, max_pooled)
+    owner = [j % world for j in range(len(chunks))]  # whole chunks, round robin
+    # crops travel once, to the rank that recognises their chunk
+    if world > 1:
+        need = {}
+        for dst in range(world):
+            mine = {}
+            for j, ch in enumerate(chunks):
+                if owner[j] != dst:
+                    continue
+                for pos in ch:
+                    key = (meta[pos][0], meta[pos][1])
+                    if key in local_crops:
+                        mine[key] = local_crops[key]
+            got = [None] * world if rank == dst else None
+            dist.gather_object(mine, got, dst=dst)
+            if rank == dst:
+                for g in got:
+                    need.update(g)
+    else:
+        need = local_crops
+    out = []
+    for j, ch in enumerate(chunks):
+        if owner[j] != rank:
+            continue
+        keys = [(meta[pos][0], meta[pos][1]) for pos in ch]
+        rec = stages.recognize([need[k] for k in keys])
+        for (gi, d), (labels, score) in zip(keys, rec):
+            labels = np.asarray(labels)
+            if not (float(score) >= rec_score_thresh):  # text_recognition_adapter.rs:88-102: text dropped, index kept
+                labels = labels[:0]
+            out.append((gi, d, labels, float(score)))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, out)
+        out = [r for p in parts for r in p]
+    results = [[] for _ in images]
+    for gi, d, labels, score in sorted(out, key=lambda r: (r[0], r[1])):
+        results[gi].append(dict(box=all_boxes[gi][d], det_index=d, labels=labels, score=score))
+    return results
+
+
+class GpuStages:
+    """predict_pooled stages on the CUDA library (stage entry points of include/oar_b200.h)."""
+
+    def __init__(self, ocr):
+        self.ocr = ocr
+
+    def detect(self, images):
+        from . import ffi
+        out = []
+        for boxes, _scores in self.ocr.det.det_run(images, self.ocr.det_cfg.to_ffi()):
+            out.append(ffi.sort_quad_boxes(boxes)[0] if len(boxes) else boxes)
+        return out
+
+    def crop(self, image, boxes):
+        return self.ocr.ctx.rotate_crop(image, boxes)
+
+    def recognize(self, crops):
+        r = self.ocr.rec.rec_run(crops, len(self.ocr.chars))
+        return list(zip(r["labels"], [float(s) for s in r["scores"]]))

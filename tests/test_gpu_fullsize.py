@@ -126,3 +126,25 @@ def test_rec_deterministic_under_host_jitter(ocr):
         r = ocr.rec.rec_run(crops[64 * k:64 * k + 64], 18385)
         assert np.array_equal(r["scores"], base[k]["scores"]), (i, np.abs(r["scores"] - base[k]["scores"]).max())
         assert all(np.array_equal(a, b) for a, b in zip(r["labels"], base[k]["labels"]))
+
+
+def test_pooled_stage_path_equals_fused_pipeline(ocr):
+    """shard.predict_pooled on the stage entry points (det_run -> sort -> rotate_crop -> rec_run per chunk), world 1,
+    reproduces OAROCR::predict's fused device pipeline exactly: same boxes, labels and confidences.  This is the
+    per-rank path of the cross-rank global crop pooling (tests/test_sharding_cpu.py covers the 2-rank exchange)."""
+    from oar_ocr_b200 import synth
+    from oar_ocr_b200.shard import GpuStages, predict_pooled
+    pages = [synth.page(90 + i, 480) for i in range(4)]
+    ocr.image_batch_size, ocr.region_batch_size = 4, 8
+    want = ocr.predict(pages)
+    got = predict_pooled(GpuStages(ocr), pages, 0, 1, region_batch_size=8)
+    n = 0
+    for g, w in zip(got, want):
+        assert len(g) == len(w.text_regions)
+        for a, b in zip(g, w.text_regions):
+            assert np.array_equal(a["box"], b.bounding_box.points)
+            assert a["det_index"] == b.detection_index
+            assert np.array_equal(a["labels"], b.label_indices)
+            assert a["score"] == b.confidence
+            n += 1
+    assert n >= 20

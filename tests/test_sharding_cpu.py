@@ -65,3 +65,72 @@ def test_two_rank_sharded_predict_matches_per_block_oracle(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     ok, n_regions = np.load(tmp_path / "ok.npy")
     assert ok == 1 and n_regions >= 3
+
+
+# ---------------------------------------------------------------- global crop pooling
+def test_plan_pooled_chunks_matches_recognize_global_rules():
+    from oar_ocr_b200.shard import plan_pooled_chunks
+    # (image, det, ratio): ties keep pool order (stable sort), chunks are cut after sorting
+    meta = [(0, 0, 5.0), (0, 1, 2.0), (1, 0, 5.0), (1, 1, 1.0), (2, 0, 2.0)]
+    assert plan_pooled_chunks(meta, 2) == [[3, 1], [4, 0], [2]]
+    assert plan_pooled_chunks(meta, 8) == [[3, 1, 4, 0, 2]]
+    # a pool is flushed when it reaches max_pooled (ocr.rs:603): sorting never crosses a flush boundary
+    assert plan_pooled_chunks(meta, 2, max_pooled=3) == [[1, 0], [2], [3, 4]]
+    assert plan_pooled_chunks([], 4) == []
+    with pytest.raises(ValueError):
+        plan_pooled_chunks(meta, 0)
+
+
+class _OracleStages:
+    def __init__(self):
+        from oar_ocr_b200 import models
+        from oracle.net import OracleNet
+        self.det, self.rec = OracleNet(models.get_blob("det")), OracleNet(models.get_blob("rec"))
+
+    def detect(self, images):
+        from oracle import cpu, pipeline
+        return [cpu.sort_quad_boxes(b)[0] if len(b) else b for b, _ in pipeline.det_forward(self.det, images)]
+
+    def crop(self, image, boxes):
+        from oracle import cpu
+        return [cpu.rotate_crop(image, b) for b in boxes]
+
+    def recognize(self, crops):
+        from oracle import pipeline
+        r = pipeline.rec_forward(self.rec, crops, 18385)
+        return list(zip(r["labels"], [float(s) for s in r["scores"]]))
+
+
+def _pooled_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    torch.set_num_threads(2)
+    from oar_ocr_b200 import synth
+    from oar_ocr_b200.shard import predict_pooled
+    from oracle import pipeline
+    st = _OracleStages()
+    images = [synth.page(90 + i, 320) for i in range(4)]
+    got = predict_pooled(st, images, rank, world, region_batch_size=3)
+    if rank == 0:
+        # ONE un-sharded predict() over all images: the pooled 2-rank run must reproduce it exactly (scores bit for
+        # bit).  On these pages plain block sharding does NOT (different recognition batches => different tensor_w).
+        def exact(res):
+            return [[(r["box"].tolist(), r["labels"].tolist(), float(r["score"])) for r in img] for img in res]
+        want = pipeline.predict(st.det, st.rec, images, 18385, image_batch_size=2, region_batch_size=3)
+        sharded = []
+        for s, e in block_partition(len(images), world):
+            sharded.extend(pipeline.predict(st.det, st.rec, images[s:e], 18385, image_batch_size=2, region_batch_size=3))
+        np.save(os.path.join(out_dir, "pooled.npy"),
+                np.array([exact(got) == exact(want), sum(len(x) for x in got), exact(got) == exact(sharded)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pooled_predict_equals_one_unsharded_predict(tmp_path):
+    world = 2
+    mp.spawn(_pooled_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ok, n_regions, same_as_sharded = np.load(tmp_path / "pooled.npy")
+    assert ok == 1 and n_regions >= 8
+    assert same_as_sharded == 0  # the test pages are ones where block sharding alone changes the batches
