@@ -77,10 +77,11 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise OCRError("ConfigError", f"{LIB_PATH} is not built; run `python -m oar_ocr_b200.build` "
+        path = os.environ.get("OAR_B200_LIB", LIB_PATH)  # development: A/B a differently built library
+        if not os.path.exists(path):
+            raise OCRError("ConfigError", f"{path} is not built; run `python -m oar_ocr_b200.build` "
                            "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.oar_last_error.restype = C.c_char_p
         L.oar_launch_count.restype = C.c_int64
         L.oar_ctx_destroy.restype = None

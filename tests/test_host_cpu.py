@@ -123,3 +123,23 @@ def test_oracle_pipeline_smoke(det_blob, rec_blob):
     for i, r in enumerate(res):
         assert np.array_equal(r["box"], g["pipe_boxes"][i])
     assert np.array_equal(np.concatenate([r["labels"] for r in res]), g["pipe_labels"])
+
+
+def test_roofline_layers_match_survey_estimates():
+    """roofline/layers.json is regenerated from the OARG layer lists (SURVEY.md 8d asks for exactly that) and the
+    algorithmic FLOPs land where the survey's architecture estimate puts them: ~10.2 GFLOP per 960x960 page for the
+    detector, ~1.5 GFLOP per 48x320 crop for the recogniser."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fresh = json.loads(subprocess.run([sys.executable, os.path.join(root, "roofline", "make_layers.py")],
+                                      capture_output=True, text=True, check=True).stdout)
+    with open(os.path.join(root, "roofline", "layers.json")) as f:
+        committed = json.load(f)
+    for kind, want in (("det", 10.2), ("rec", 1.5)):
+        assert committed[kind]["gflop_per_item"] == fresh[kind]["gflop_per_item"]  # committed file is in sync
+        assert abs(fresh[kind]["gflop_per_item"] - want) / want < 0.05
+        # the fused engine removes the depthwise round trip: strictly fewer bytes than one kernel per layer
+        assert fresh[kind]["mb_total_fused_engine"] < fresh[kind]["mb_total_per_layer_kernels"]
