@@ -170,6 +170,14 @@ typedef struct {
   /* device-time breakdown of the last call, ms (0 when not measured) */
   float ms_h2d, ms_det, ms_post, ms_crop, ms_rec, ms_total;
   int64_t h2d_bytes, d2h_bytes;
+  /* optional (may be NULL): what OAROCR::ctc_word_boxes needs per region when `return_word_box` is on
+   * (src/oarocr/ocr.rs:827-868, 949-1022).  cols[label_off[r] .. label_off[r+1]) = CTC timestep of each emitted
+   * character (char_col_indices), seq_len[r] = T of the recognition batch the region was in, wh_ratio[r] = the crop's
+   * w / max(h,1), max_wh_ratio[r] = max(320/48, max wh_ratio of that batch) (chunk_max_wh_ratio). */
+  int32_t* cols;       /* [cap_labels] */
+  int32_t* seq_len;    /* [cap_regions] */
+  float* wh_ratio;     /* [cap_regions] */
+  float* max_wh_ratio; /* [cap_regions] */
 } oar_ocr_result;
 
 /* images_on_device != 0: `images` are device pointers already resident in HBM */

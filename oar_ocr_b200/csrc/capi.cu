@@ -1026,11 +1026,21 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
   std::vector<int> lab_len(n_boxes, -1);
   std::vector<const int32_t*> lab_ptr(n_boxes, nullptr);
   std::vector<float> rec_score(n_boxes, 0.0f);
+  // per region, for word boxes (ocr.rs:827-868): CTC columns, T and the max wh_ratio of its recognition batch
+  std::vector<const int32_t*> col_ptr(n_boxes, nullptr);
+  std::vector<int> box_T(n_boxes, 0);
+  std::vector<float> box_max_ratio(n_boxes, 0.0f);
+  const float base_rec_ratio = (float)REC_W / (float)REC_H;  // DEFAULT_REC_IMAGE_SHAPE, ocr.rs:817
   for (auto& wv : waves) {
     size_t s0 = 0;
     for (auto& ch : wv.chunks) {
+      float chunk_max = base_rec_ratio;
+      for (int k = 0; k < ch.n; ++k) chunk_max = std::fmax(chunk_max, h_plans[wv.sorted[s0 + k]].wh_ratio);
       for (int k = 0; k < ch.n; ++k) {
         int box = wv.sorted[s0 + k];
+        col_ptr[box] = ch.h_cols + (size_t)k * ch.T;
+        box_T[box] = ch.T;
+        box_max_ratio[box] = chunk_max;
         float sc = ch.h_scores[k];
         rec_score[box] = sc;
         // TextRecognitionAdapter::execute: score below the threshold keeps the slot with empty text
@@ -1057,6 +1067,10 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
       if (out->det_index) out->det_index[r] = k;
       if (out->label_off) out->label_off[r] = (int32_t)nl;
       if (out->labels && lab_len[box] > 0) memcpy(out->labels + nl, lab_ptr[box], (size_t)lab_len[box] * 4);
+      if (out->cols && lab_len[box] > 0) memcpy(out->cols + nl, col_ptr[box], (size_t)lab_len[box] * 4);
+      if (out->seq_len) out->seq_len[r] = box_T[box];
+      if (out->wh_ratio) out->wh_ratio[r] = h_plans[box].wh_ratio;
+      if (out->max_wh_ratio) out->max_wh_ratio[r] = box_max_ratio[box];
       nl += lab_len[box];
       ++r;
     }

@@ -64,7 +64,9 @@ class OcrResult(C.Structure):
                 ("det_index", C.POINTER(C.c_int32)), ("label_off", C.POINTER(C.c_int32)),
                 ("labels", C.POINTER(C.c_int32)), ("ms_h2d", C.c_float), ("ms_det", C.c_float),
                 ("ms_post", C.c_float), ("ms_crop", C.c_float), ("ms_rec", C.c_float), ("ms_total", C.c_float),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cols", C.POINTER(C.c_int32)),
+                ("seq_len", C.POINTER(C.c_int32)), ("wh_ratio", C.POINTER(C.c_float)),
+                ("max_wh_ratio", C.POINTER(C.c_float))]
 
 
 class KernelRecord(C.Structure):
@@ -417,6 +419,15 @@ class PipelineBuffers:
         self.res.det_index = self.det_index.ctypes.data_as(P(C.c_int32))
         self.res.label_off = self.label_off.ctypes.data_as(P(C.c_int32))
         self.res.labels = self.labels.ctypes.data_as(P(C.c_int32))
+        # word-box inputs (ocr.rs:827-868): CTC column per emitted character, T / wh_ratio / batch max ratio per region
+        self.cols = np.zeros(cap_labels, np.int32)
+        self.seq_len = np.zeros(cap_regions, np.int32)
+        self.wh_ratio = np.zeros(cap_regions, np.float32)
+        self.max_wh_ratio = np.zeros(cap_regions, np.float32)
+        self.res.cols = self.cols.ctypes.data_as(P(C.c_int32))
+        self.res.seq_len = self.seq_len.ctypes.data_as(P(C.c_int32))
+        self.res.wh_ratio = self.wh_ratio.ctypes.data_as(P(C.c_float))
+        self.res.max_wh_ratio = self.max_wh_ratio.ctypes.data_as(P(C.c_float))
 
 
 def pipeline_run(det: Model, rec: Model, image_ptrs, hs: np.ndarray, ws: np.ndarray, on_device: bool,

@@ -42,6 +42,11 @@ class BoundingBox:
     def y_max(self):
         return float(self.points[:, 1].max())
 
+    @staticmethod
+    def from_coords(x1, y1, x2, y2) -> "BoundingBox":
+        """BoundingBox::from_coords (geometry.rs): the four corners clockwise from the top-left"""
+        return BoundingBox(np.array([[x1, y1], [x2, y1], [x2, y2], [x1, y2]], np.float32))
+
 
 @dataclass
 class Detection:
@@ -152,6 +157,48 @@ def _decode_texts(chars, label_lists):
 
 
 _contexts: dict = {}
+
+
+def is_cjk(ch: str) -> bool:
+    """OAROCR::is_cjk (src/oarocr/ocr.rs:1065-1084)"""
+    u = ord(ch)
+    return (0x4E00 <= u <= 0x9FFF or 0x3400 <= u <= 0x4DBF or 0x20000 <= u <= 0x2A6DF or 0x2A700 <= u <= 0x2B73F
+            or 0x2B740 <= u <= 0x2B81F)
+
+
+def ctc_word_boxes(line_bbox: BoundingBox, text: str, col_indices, seq_len: int, wh_ratio: float,
+                   max_wh_ratio: float) -> list:
+    """OAROCR::ctc_word_boxes (src/oarocr/ocr.rs:949-1022) in f32: one axis-aligned box per character, from the CTC
+    timestep it was emitted at.  CJK characters get a box of the line's average character width around their cell
+    centre; others span to the midpoints between neighbouring centres."""
+    f = np.float32
+    if len(col_indices) == 0 or seq_len == 0 or not text:
+        return []
+    effective = f(seq_len) * (f(wh_ratio) / f(max_wh_ratio))
+    eps = f(np.finfo(np.float32).eps)
+    if effective <= eps:
+        return []
+    x_min, y_min = f(line_bbox.x_min()), f(line_bbox.y_min())
+    x_max, y_max = f(line_bbox.x_max()), f(line_bbox.y_max())
+    width = f(x_max - x_min)
+    cell = f(width / max(effective, eps))
+    chars = list(text)
+    avg = f(width / f(max(len(chars), 1)))
+    centers = [f(x_min + f(f(f(int(i)) + f(0.5)) * cell)) for i in col_indices]
+    out = []
+    for i in range(len(col_indices)):
+        ch = chars[i] if i < len(chars) else "?"
+        c = centers[i]
+        if is_cjk(ch):
+            half = f(avg / f(2.0))
+            lo, hi = max(f(c - half), x_min), min(f(c + half), x_max)
+        else:
+            lo = x_min if i == 0 else f(f(centers[i - 1] + c) / f(2.0))
+            lo = max(lo, x_min)
+            hi = x_max if i == len(col_indices) - 1 else f(f(c + centers[i + 1]) / f(2.0))
+            hi = min(hi, x_max)
+        out.append(BoundingBox.from_coords(lo, y_min, hi, y_max))
+    return out
 
 
 def default_context(device_id: int = 0) -> ffi.Context:
@@ -301,6 +348,7 @@ class OAROCRBuilder:
         self._image_bs = None
         self._region_bs = None
         self._device = 0
+        self._return_word_box = False
 
     def character_dict_content(self, content: str):
         self._dict_content = content
@@ -312,6 +360,11 @@ class OAROCRBuilder:
 
     def text_recognition_config(self, cfg: TextRecognitionConfig):
         self._rec_cfg = cfg
+        return self
+
+    def return_word_box(self, enable: bool):
+        """OAROCRBuilder::return_word_box (ocr.rs:241): per-character boxes from the CTC columns"""
+        self._return_word_box = bool(enable)
         return self
 
     def image_batch_size(self, size: int):
@@ -356,7 +409,9 @@ class OAROCRBuilder:
         det = ffi.Model(ctx, _resolve_model(self._det, "det"))
         rec = ffi.Model(ctx, _resolve_model(self._rec, "rec"))
         # the B200 provider is an accelerator: adapter defaults 8 / 64 (builder_utils.rs:86-125)
-        return OAROCR(ctx, det, rec, chars, det_cfg, rec_cfg, self._image_bs or 8, self._region_bs or 64)
+        ocr = OAROCR(ctx, det, rec, chars, det_cfg, rec_cfg, self._image_bs or 8, self._region_bs or 64)
+        ocr.return_word_box = self._return_word_box
+        return ocr
 
 
 class OAROCR:
@@ -366,6 +421,7 @@ class OAROCR:
         self.image_batch_size, self.region_batch_size = image_bs, region_bs
         self.last_timing = {}
         self._bufs = None
+        self.return_word_box = False  # ocr.rs:441: per-character boxes in TextRegion.word_boxes
 
     def _config(self) -> ffi.PipelineConfig:
         cfg = ffi.pipeline_config(image_batch_size=self.image_batch_size, region_batch_size=self.region_batch_size,
@@ -394,7 +450,14 @@ class OAROCR:
             for r in range(b.region_off[i], b.region_off[i + 1]):
                 lab = b.labels[b.label_off[r]:b.label_off[r + 1]].copy()
                 bbox = BoundingBox(b.boxes[r].copy())
-                regions.append(TextRegion(bbox, bbox, bbox, _decode_texts(self.chars, [lab])[0], float(b.scores[r]),
+                text = _decode_texts(self.chars, [lab])[0]
+                word_boxes = None
+                if self.return_word_box:  # ocr.rs:860-868
+                    cols = b.cols[b.label_off[r]:b.label_off[r + 1]]
+                    if len(cols) and b.seq_len[r] > 0:
+                        word_boxes = ctc_word_boxes(bbox, text, cols, int(b.seq_len[r]), float(b.wh_ratio[r]),
+                                                    float(b.max_wh_ratio[r]))
+                regions.append(TextRegion(bbox, bbox, bbox, text, float(b.scores[r]), word_boxes=word_boxes,
                                           detection_index=int(b.det_index[r]), label_indices=lab))
             results.append(OAROCRResult(f"image_{i}", i, img, regions))
         return results

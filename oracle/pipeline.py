@@ -16,6 +16,51 @@ from . import cpu
 from .net import OracleNet
 
 MAX_POOLED_CROPS = 4096  # ocr.rs:603
+BASE_REC_RATIO = np.float32(320.0) / np.float32(48.0)  # DEFAULT_REC_IMAGE_SHAPE, ocr.rs:817
+
+
+def is_cjk(ch):
+    """OAROCR::is_cjk, ocr.rs:1065-1084"""
+    u = ord(ch)
+    for lo, hi in ((0x4E00, 0x9FFF), (0x3400, 0x4DBF), (0x20000, 0x2A6DF), (0x2A700, 0x2B73F), (0x2B740, 0x2B81F)):
+        if lo <= u <= hi:
+            return True
+    return False
+
+
+def ctc_word_boxes(box, text, col_indices, seq_len, wh_ratio, max_wh_ratio):
+    """OAROCR::ctc_word_boxes, ocr.rs:949-1022, f32 step by step.  box: [4,2] quad; returns [n,4] (x0,y0,x1,y1)."""
+    F = np.float32
+    if len(col_indices) == 0 or seq_len == 0 or len(text) == 0:
+        return np.zeros((0, 4), F)
+    eps = F(np.finfo(np.float32).eps)
+    effective = F(F(seq_len) * F(F(wh_ratio) / F(max_wh_ratio)))
+    if effective <= eps:
+        return np.zeros((0, 4), F)
+    box = np.asarray(box, F).reshape(-1, 2)
+    x_min, x_max, y_min, y_max = box[:, 0].min(), box[:, 0].max(), box[:, 1].min(), box[:, 1].max()
+    width = F(x_max - x_min)
+    cell_width = F(width / (effective if effective > eps else eps))
+    avg_char_width = F(width / F(max(len(text), 1)))
+    centers = []
+    for idx in col_indices:
+        centers.append(F(x_min + F(F(F(int(idx)) + F(0.5)) * cell_width)))
+    out = np.zeros((len(col_indices), 4), F)
+    for i in range(len(col_indices)):
+        ch = text[i] if i < len(text) else "?"
+        c = centers[i]
+        if is_cjk(ch):
+            half = F(avg_char_width / F(2.0))
+            a, b = F(c - half), F(c + half)
+            a = a if a > x_min else x_min
+            b = b if b < x_max else x_max
+        else:
+            a = x_min if i == 0 else F(F(centers[i - 1] + c) / F(2.0))
+            a = a if a > x_min else x_min
+            b = x_max if i == len(col_indices) - 1 else F(F(c + centers[i + 1]) / F(2.0))
+            b = b if b < x_max else x_max
+        out[i] = (a, y_min, b, y_max)
+    return out
 
 
 def det_forward(net: OracleNet, images, thresh=0.3, box_thresh=0.6, unclip_ratio=2.0, max_candidates=1000,
@@ -68,7 +113,7 @@ def rec_forward(net: OracleNet, crops, n_chars, return_probs=False):
 
 
 def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch_size=8, region_batch_size=64,
-            rec_score_thresh=0.0, det_kwargs=None):
+            rec_score_thresh=0.0, det_kwargs=None, chars=None):
     """OAROCR::predict.  Returns per image a list of dicts
     {box [4,2], det_index, labels (int array), score} in detection-index (reading) order."""
     det_kwargs = det_kwargs or {}
@@ -86,11 +131,20 @@ def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch
         for s in range(0, len(order), region_batch_size):
             chunk = [pool[i] for i in order[s:s + region_batch_size]]
             r = rec_forward(rec_net, [c[2] for c in chunk], n_chars)
-            for k, (img_idx, det_idx, _crop, _ratio) in enumerate(chunk):
+            chunk_max = BASE_REC_RATIO
+            for c in chunk:
+                chunk_max = max(chunk_max, np.float32(c[3]))  # ocr.rs:828-831
+            for k, (img_idx, det_idx, _crop, ratio) in enumerate(chunk):
                 score = float(r["scores"][k])
-                labels = r["labels"][k] if score >= rec_score_thresh else r["labels"][k][:0]
-                results[img_idx][det_idx] = dict(box=all_boxes[img_idx][det_idx], det_index=det_idx, labels=labels,
-                                                 score=score, cols=r["cols"][k], T=r["T"])
+                keep = score >= rec_score_thresh
+                labels = r["labels"][k] if keep else r["labels"][k][:0]
+                res = dict(box=all_boxes[img_idx][det_idx], det_index=det_idx, labels=labels, score=score,
+                           cols=r["cols"][k], T=r["T"])
+                if chars is not None:  # return_word_box (ocr.rs:860-868); chars = index -> character
+                    cols = r["cols"][k] if keep else r["cols"][k][:0]
+                    text = "".join(chars[i] for i in labels if 0 < i < len(chars))
+                    res["word_boxes"] = ctc_word_boxes(res["box"], text, cols, r["T"], ratio, chunk_max)
+                results[img_idx][det_idx] = res
 
     for i, img in enumerate(images):
         for k, box in enumerate(all_boxes[i]):

@@ -385,3 +385,30 @@ def test_launch_counter_moves(nets, G):
     n0 = ffi.launch_count()
     det.det_run([G["det_in"]])
     assert ffi.launch_count() - n0 > 50
+
+
+def test_pipeline_word_boxes_vs_oracle(nets, oracle_nets):
+    """return_word_box (ocr.rs:241, 860-868): the pipeline hands back CTC columns, T, wh_ratio and the batch's max
+    ratio per region; the per-character boxes computed from them equal the oracle's bit for bit."""
+    from oracle import pipeline
+    from oar_ocr_b200 import models, synth
+    from oar_ocr_b200.ocr import OAROCR, TextDetectionConfig, TextRecognitionConfig, character_list
+    det, rec = nets
+    chars = character_list(models.synthetic_dict())
+    imgs = [synth.page(60, 480), synth.page(61, 320), synth.page(62, 480)]
+    ocr = OAROCR(det.ctx, det, rec, chars, TextDetectionConfig(unclip_ratio=2.0), TextRecognitionConfig(), 2, 5)
+    ocr.return_word_box = True
+    got = ocr.predict(imgs)
+    want = pipeline.predict(oracle_nets[0], oracle_nets[1], imgs, len(chars), image_batch_size=2, region_batch_size=5,
+                            chars=chars)
+    n_boxes = 0
+    for g, w in zip(got, want):
+        assert len(g.text_regions) == len(w)
+        for r, o in zip(g.text_regions, w):
+            assert np.array_equal(r.label_indices, o["labels"])
+            wb = r.word_boxes or []
+            assert len(wb) == len(o["word_boxes"]) == len(o["labels"])
+            for b, row in zip(wb, o["word_boxes"]):
+                assert (b.points[0, 0], b.points[0, 1], b.points[1, 0], b.points[2, 1]) == tuple(row)
+                n_boxes += 1
+    assert n_boxes >= 100

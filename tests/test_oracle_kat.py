@@ -281,3 +281,37 @@ def test_det_resize_dims():
     assert cpu.det_resize_dims(1920, 1080) == (960, 544)  # ratio .5 -> 960x540 -> (540+16)//32*32 = 544
     assert cpu.det_resize_dims(100, 30) == (96, 32)
     assert cpu.det_resize_dims(10, 10) == (32, 32)
+
+
+# ocr.rs:1197-1232 test_ctc_word_boxes_logic, for the oracle restatement and the product-side mirror alike
+def test_ctc_word_boxes_kat_and_mirror_agreement():
+    from oar_ocr_b200.ocr import BoundingBox, ctc_word_boxes as product_word_boxes
+    from oracle.pipeline import ctc_word_boxes as oracle_word_boxes
+    line = np.array([[0, 0], [100, 0], [100, 20], [0, 20]], np.float32)
+    got = oracle_word_boxes(line, "ABC", [1, 4, 7], 10, 5.0, 5.0)
+    assert got.shape == (3, 4)
+    assert np.allclose(got[:, 0], [0.0, 30.0, 60.0], atol=1e-5) and np.allclose(got[:, 2], [30.0, 60.0, 100.0], atol=1e-5)
+    assert np.all(got[:, 1] == 0.0) and np.all(got[:, 3] == 20.0)
+    # CJK: a box of the average character width around the cell centre, clamped to the line
+    cjk = oracle_word_boxes(line, "一二", [0, 9], 10, 5.0, 5.0)
+    assert np.allclose(cjk, [[0.0, 0, 30.0, 20], [70.0, 0, 100.0, 20]], atol=1e-5)
+    # padding undone through wh_ratio / max_wh_ratio: half-width crop in a batch of full-width ones
+    half = oracle_word_boxes(line, "AB", [1, 3], 10, 2.5, 5.0)  # effective columns = 5, cell = 20
+    assert np.allclose(half[:, 0], [0.0, 50.0], atol=1e-5) and np.allclose(half[:, 2], [50.0, 100.0], atol=1e-5)
+    assert len(oracle_word_boxes(line, "", [1], 10, 5.0, 5.0)) == 0 and len(oracle_word_boxes(line, "A", [], 10, 5, 5)) == 0
+    # the product-side mirror (oar_ocr_b200/ocr.py) computes the same f32 values
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        n = int(rng.integers(1, 12))
+        cols = np.sort(rng.choice(40, n, replace=False))
+        text = "".join(rng.choice(["A", "b", "中", "文", "7"]) for _ in range(n))
+        x0, y0 = float(rng.uniform(0, 50)), float(rng.uniform(0, 50))
+        box = np.array([[x0, y0], [x0 + 200.5, y0 + 3], [x0 + 199, y0 + 40], [x0 - 2, y0 + 37]], np.float32)
+        r, mr = float(rng.uniform(1, 12)), 12.5
+        a = oracle_word_boxes(box, text, cols, 40, r, mr)
+        b = product_word_boxes(BoundingBox(box), text, cols, 40, r, mr)
+        assert len(a) == len(b) == n
+        for row, bb in zip(a, b):
+            # from_coords keeps the corners as computed (a clamped box may have x0 > x1): compare the corners
+            assert row[0] == bb.points[0, 0] and row[2] == bb.points[1, 0]
+            assert row[1] == bb.points[0, 1] and row[3] == bb.points[2, 1]
