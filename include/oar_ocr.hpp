@@ -49,7 +49,59 @@ struct TextRegion {
   std::vector<int32_t> label_indices;
   float confidence = 0.0f;
   int32_t detection_index = 0;
+  // return_word_box (ocr.rs:241): CTC column of every emitted character, the sequence length of the region's
+  // recognition batch, its crop's w/h ratio and the batch's chunk_max_wh_ratio -- the inputs of ctc_word_boxes()
+  std::vector<int32_t> char_col_indices;
+  int32_t sequence_length = 0;
+  float wh_ratio = 0.0f, max_wh_ratio = 0.0f;
 };
+
+// OAROCR::is_cjk (src/oarocr/ocr.rs:1065-1084)
+inline bool is_cjk(char32_t u) {
+  return (u >= 0x4E00 && u <= 0x9FFF) || (u >= 0x3400 && u <= 0x4DBF) || (u >= 0x20000 && u <= 0x2A6DF) ||
+         (u >= 0x2A700 && u <= 0x2B73F) || (u >= 0x2B740 && u <= 0x2B81F);
+}
+
+// OAROCR::ctc_word_boxes (src/oarocr/ocr.rs:949-1022): one box per character from its CTC timestep.  `text` holds the
+// region's characters as code points (the dictionary lives above the ABI).  f32 arithmetic in the reference's order.
+inline std::vector<BoundingBox> ctc_word_boxes(const BoundingBox& line, const std::u32string& text,
+                                               const std::vector<int32_t>& cols, size_t seq_len, float wh_ratio,
+                                               float max_wh_ratio) {
+  std::vector<BoundingBox> out;
+  if (cols.empty() || seq_len == 0 || text.empty() || line.points.empty()) return out;
+  const float eps = 1.1920929e-07f;  // f32::EPSILON
+  const float effective = (float)seq_len * (wh_ratio / max_wh_ratio);
+  if (effective <= eps) return out;
+  float x_min = line.points[0].x, x_max = x_min, y_min = line.points[0].y, y_max = y_min;
+  for (const Point& p : line.points) {
+    x_min = p.x < x_min ? p.x : x_min, x_max = p.x > x_max ? p.x : x_max;
+    y_min = p.y < y_min ? p.y : y_min, y_max = p.y > y_max ? p.y : y_max;
+  }
+  const float width = x_max - x_min;
+  const float cell = width / (effective > eps ? effective : eps);
+  const float avg = width / (float)(text.size() > 0 ? text.size() : 1);
+  std::vector<float> centers(cols.size());
+  for (size_t i = 0; i < cols.size(); ++i) centers[i] = x_min + ((float)cols[i] + 0.5f) * cell;
+  auto box = [&](float a, float b) {
+    return BoundingBox{{Point{a, y_min}, Point{b, y_min}, Point{b, y_max}, Point{a, y_max}}};  // from_coords
+  };
+  for (size_t i = 0; i < cols.size(); ++i) {
+    const char32_t ch = i < text.size() ? text[i] : U'?';
+    const float c = centers[i];
+    float a, b;
+    if (is_cjk(ch)) {
+      const float half = avg / 2.0f;
+      a = c - half, b = c + half;
+    } else {
+      a = i == 0 ? x_min : (centers[i - 1] + c) / 2.0f;
+      b = i + 1 == cols.size() ? x_max : (c + centers[i + 1]) / 2.0f;
+    }
+    a = a > x_min ? a : x_min;
+    b = b < x_max ? b : x_max;
+    out.push_back(box(a, b));
+  }
+  return out;
+}
 struct OAROCRResult { size_t index = 0; std::vector<TextRegion> text_regions; };
 
 class Context {
@@ -176,8 +228,11 @@ class OAROCR {
     const size_t n = images.size();
     const int32_t cap_r = (int32_t)n * cfg_.det.max_candidates, cap_l = cap_r * 64;
     std::vector<int32_t> region_off(n + 1), det_index(cap_r), label_off(cap_r + 1), labels(cap_l);
-    std::vector<float> boxes((size_t)cap_r * 8), scores(cap_r);
+    std::vector<float> boxes((size_t)cap_r * 8), scores(cap_r), wh_ratio(cap_r), max_wh_ratio(cap_r);
+    std::vector<int32_t> cols(cap_l), seq_len(cap_r);
     oar_ocr_result out{};
+    out.cols = cols.data(), out.seq_len = seq_len.data(), out.wh_ratio = wh_ratio.data();
+    out.max_wh_ratio = max_wh_ratio.data();
     out.cap_regions = cap_r, out.cap_labels = cap_l;
     out.region_off = region_off.data(), out.boxes = boxes.data(), out.scores = scores.data();
     out.det_index = det_index.data(), out.label_off = label_off.data(), out.labels = labels.data();
@@ -191,6 +246,8 @@ class OAROCR {
         t.label_indices.assign(labels.begin() + label_off[r], labels.begin() + label_off[r + 1]);
         t.confidence = scores[r];
         t.detection_index = det_index[r];
+        t.char_col_indices.assign(cols.begin() + label_off[r], cols.begin() + label_off[r + 1]);
+        t.sequence_length = seq_len[r], t.wh_ratio = wh_ratio[r], t.max_wh_ratio = max_wh_ratio[r];
         res[i].text_regions.push_back(std::move(t));
       }
     }

@@ -35,6 +35,22 @@ int main(int argc, char** argv) {
   oar_pipeline_config_default(&pc);
   expect(pc.image_batch_size == 8 && pc.region_batch_size == 64 && pc.det.unclip_ratio == 2.0f, "defaults");
 
+  // ctc_word_boxes: the reference's own vector (ocr.rs:1197-1232) + a CJK case
+  {
+    oar::BoundingBox line{{{0.f, 0.f}, {100.f, 0.f}, {100.f, 20.f}, {0.f, 20.f}}};
+    auto wb = oar::ctc_word_boxes(line, U"ABC", {1, 4, 7}, 10, 5.0f, 5.0f);
+    auto near = [](float a, float b) { return a - b < 1e-5f && b - a < 1e-5f; };
+    expect(wb.size() == 3 && near(wb[0].points[0].x, 0.f) && near(wb[0].points[1].x, 30.f) &&
+               near(wb[1].points[0].x, 30.f) && near(wb[1].points[1].x, 60.f) && near(wb[2].points[0].x, 60.f) &&
+               near(wb[2].points[1].x, 100.f) && wb[0].points[0].y == 0.f && wb[0].points[2].y == 20.f,
+           "ctc_word_boxes non-CJK");
+    auto cj = oar::ctc_word_boxes(line, U"\u4e00\u4e8c", {0, 9}, 10, 5.0f, 5.0f);
+    expect(cj.size() == 2 && near(cj[0].points[0].x, 0.f) && near(cj[0].points[1].x, 30.f) &&
+               near(cj[1].points[0].x, 70.f) && near(cj[1].points[1].x, 100.f),
+           "ctc_word_boxes CJK");
+    expect(oar::ctc_word_boxes(line, U"", {1}, 10, 5.0f, 5.0f).empty(), "ctc_word_boxes empty text");
+  }
+
   bool have_gpu = true;
   try {
     oar::Context probe(0);
@@ -59,6 +75,17 @@ int main(int argc, char** argv) {
         for (int c = 0; c < 3; ++c) page[(y * 320 + x) * 3 + c] = (uint8_t)(30 + 40 * ((x / 4) & 1));
     auto res = ocr.predict({oar::RgbImage{page.data(), 320, 320}});
     expect(res.size() == 1 && res[0].text_regions.size() == 1, "one region on the striped page");
+    if (res.size() == 1 && res[0].text_regions.size() == 1) {
+      // return_word_box inputs arrive with the region: one CTC column per emitted character, T, the two ratios
+      const oar::TextRegion& t = res[0].text_regions[0];
+      expect(t.char_col_indices.size() == t.label_indices.size() && t.sequence_length > 0 && t.wh_ratio > 0.f &&
+                 t.max_wh_ratio >= t.wh_ratio && t.max_wh_ratio >= 320.0f / 48.0f,
+             "word-box inputs");
+      std::u32string text(t.label_indices.size(), U'\u4e00');
+      auto wb = oar::ctc_word_boxes(t.bounding_box, text, t.char_col_indices, (size_t)t.sequence_length, t.wh_ratio,
+                                    t.max_wh_ratio);
+      expect(wb.size() == t.label_indices.size(), "one word box per character");
+    }
     auto dres = oar::TextDetectionPredictor(det).predict({oar::RgbImage{page.data(), 320, 320}});
     expect(dres.detections.size() == 1 && dres.detections[0].size() == 1, "detector predictor");
     std::printf("gpu path ok: %zu regions\n", res[0].text_regions.size());
