@@ -412,3 +412,57 @@ def test_pipeline_word_boxes_vs_oracle(nets, oracle_nets):
                 assert (b.points[0, 0], b.points[0, 1], b.points[1, 0], b.points[2, 1]) == tuple(row)
                 n_boxes += 1
     assert n_boxes >= 100
+
+
+# ---------------------------------------------------------------- fused block kernel on shapes the two nets do not hit
+def _block_graph(spec, seed):
+    """stem conv 3 -> c0, then [depthwise k, stride -> (SE) -> 1x1 conv -> hardswish] blocks, then a 1x1 conv to 1 channel"""
+    from oar_ocr_b200 import models
+    g = models.GraphBuilder(models.KIND_DET, seed)
+    g.base_gain = 0.8
+    x = g.conv(0, spec["c0"], (3, 3), spec.get("stem_stride", (1, 1)), act=models.ACT_NONE)
+    for (k, cout, stride, use_se) in spec["blocks"]:
+        x = models._lcnet_block(g, x, k, cout, stride, use_se, plant=0)
+    for cout in spec.get("pw", []):
+        x = g.conv(x, cout, (1, 1), act=models.ACT_HSWISH)
+    g.conv(x, 1, (1, 1), act=models.ACT_NONE)
+    return g.serialize()
+
+
+_BLOCK_SPECS = [
+    # odd image size, C = 16 block, stride-2 3x3, 5x5 with a 96-channel tail (3 k-blocks)
+    dict(hw=(37, 53), c0=16, blocks=[(3, 32, (1, 1), False), (3, 48, (2, 2), False), (5, 96, (1, 1), False)]),
+    # rec-like strides, 240 channels (K tail of 16), N = 480 (two N tiles)
+    dict(hw=(24, 50), c0=64, blocks=[(3, 240, (1, 2), False), (5, 240, (1, 1), False), (5, 480, (2, 1), False)]),
+    # N = 200 (not a multiple of 16 or 32), 5x5 stride 2 on an odd size
+    dict(hw=(31, 31), c0=96, blocks=[(5, 200, (2, 2), False), (3, 200, (1, 1), False)]),
+    # squeeze-excite blocks: depthwise with per-tile sums -> pool -> FCs -> 1x1 conv with the scale folded into A
+    dict(hw=(20, 44), c0=128, blocks=[(5, 256, (1, 1), True), (3, 256, (2, 1), True)]),
+    # plain 1x1 convs: C = 12 (TMA rows of 48 bytes), wide N, a 3-row image (tile taller than the image)
+    dict(hw=(3, 80), c0=12, blocks=[], pw=[96, 480, 24]),
+]
+
+
+@pytest.mark.parametrize("spec_i", range(len(_BLOCK_SPECS)))
+def test_fused_block_kernel_odd_shapes(ctx, spec_i):
+    """engine 2 (persistent fused kernel: tile choice, halo boxes, channel / class tails, clipped stores) against the
+    CPU oracle and the fp32 SIMT engine on small graphs with shapes the PP-OCRv5 nets never produce"""
+    from oar_ocr_b200 import ffi
+    from oracle.net import OracleNet
+    spec = _BLOCK_SPECS[spec_i]
+    blob = _block_graph(spec, 100 + spec_i)
+    rng = np.random.default_rng(spec_i)
+    h, w = spec["hw"]
+    x = rng.standard_normal((3, 3, h, w)).astype(np.float32)
+    want = OracleNet(blob).forward(x)
+    m = ffi.Model(ctx, blob)
+    scale = max(1.0, float(np.abs(want).max()))
+    outs = {}
+    for eng in (0, 1, 2):
+        m.set_engine(eng)
+        outs[eng] = m.infer(x)
+        assert outs[eng].shape == want.shape
+        assert np.abs(outs[eng] - want).max() <= 2e-4 * scale, (eng, np.abs(outs[eng] - want).max(), scale)
+    # same batch again: bit-stable
+    assert np.array_equal(m.infer(x), outs[2])
+    m.close()
