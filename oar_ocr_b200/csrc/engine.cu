@@ -778,8 +778,10 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         f.bias = m->w(pw, 1), f.act = pw.p[8], f.ps = pw.f[0], f.pb = pw.f[1], f.N = pw.p[7];
         f.out = o.p, f.out_ld = o.C, f.out_c_off = pw.p[11] ? pw.p[10] : 0, f.Ho = o.H, f.Wo = o.W;
       };
+      // (a 5x5 block wider than one 256-column N tile would run its depthwise stage once per N tile: measured slower
+      // than the stand-alone depthwise kernel + the persistent 1x1 conv, which converts A twice for almost nothing)
       if (dw_ok && oi + 1 < m->ops.size() && is_pw(m->ops[oi + 1]) && m->ops[oi + 1].in0 == op.out &&
-          m->ops[oi + 1].p[6] == a.C) {
+          m->ops[oi + 1].p[6] == a.C && !(op.p[0] == 5 && m->ops[oi + 1].p[7] > 256)) {
         const OpRec& pw = m->ops[oi + 1];
         const int k = op.p[0], sh = op.p[2], sw = op.p[3];
         const int Ho = conv_out(a.H, k, sh, k / 2), Wo = conv_out(a.W, k, sw, k / 2);
