@@ -143,3 +143,34 @@ def test_roofline_layers_match_survey_estimates():
         assert abs(fresh[kind]["gflop_per_item"] - want) / want < 0.05
         # the fused engine removes the depthwise round trip: strictly fewer bytes than one kernel per layer
         assert fresh[kind]["mb_total_fused_engine"] < fresh[kind]["mb_total_per_layer_kernels"]
+
+
+def test_abi_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in ffi.py must have exactly the layout a C compiler gives the structs of include/oar_b200.h
+    (oar_ocr_result grew the optional word-box arrays; a drift here corrupts memory silently)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from oar_ocr_b200 import ffi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "oar_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(oar_ocr_result), offsetof(oar_ocr_result, labels),
+         offsetof(oar_ocr_result, ms_h2d), offsetof(oar_ocr_result, h2d_bytes), offsetof(oar_ocr_result, cols),
+         offsetof(oar_ocr_result, max_wh_ratio), sizeof(oar_pipeline_config));
+  printf("%zu %zu\n", sizeof(oar_det_config), offsetof(oar_pipeline_config, image_batch_size));
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")[:2]
+    got = [int(x) for x in a.split()] + [int(x) for x in b.split()]
+    R, P = ffi.OcrResult, ffi.PipelineConfig
+    want = [C.sizeof(R), R.labels.offset, R.ms_h2d.offset, R.h2d_bytes.offset, R.cols.offset, R.max_wh_ratio.offset,
+            C.sizeof(P), C.sizeof(ffi.DetConfig), P.image_batch_size.offset]
+    assert got == want
