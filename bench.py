@@ -322,7 +322,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="pages per GPU per step")
     ap.add_argument("--image-batch-size", type=int, default=32)
     ap.add_argument("--region-batch-size", type=int, default=256)
-    ap.add_argument("--engine", type=int, default=None, help="0 = fp32 SIMT engine, 1 = tensor-core engine")
+    ap.add_argument("--engine", type=int, default=None, help="0 = fp32 SIMT engine, 1 = tcgen05 one kernel per layer, 2 = tcgen05 fused persistent blocks (default)")
     ap.add_argument("--ref-sample", type=int, default=4, help="pages per CPU-reference pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
