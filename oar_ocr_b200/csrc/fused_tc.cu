@@ -606,6 +606,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     return false;
   FbKern kern = pick_kernel(f.k, f.k ? f.sh : 1, f.k ? f.sw : 1);
   if (!kern) return false;
+  // the epilogue keeps the whole (zero-padded) bias in shared memory: FB_CTRL_BYTES reserves 512 + 32 floats
+  if ((size_t)w->n_tiles * w->BN + 32 > (FB_CTRL_BYTES - 256) / sizeof(float)) return false;
   const long long M = (long long)f.B * f.Ho * f.Wo;
   if (M <= 0) return true;
 
