@@ -133,8 +133,12 @@ def character_list(dict_lines: list[str]) -> list[str]:
 
 
 def _resolve_model(source, kind: str) -> bytes:
-    """ModelSource: OARG bytes, a path to an .oarg file, or 'synthetic[:seed]'."""
+    """ModelSource (core/config: ModelSource::Path / Memory): OARG or ONNX bytes, a path to an .oarg or .onnx file, or
+    'synthetic[:seed]'.  ONNX models are converted to the OARG layer list on load (onnx_io.import_onnx)."""
     if isinstance(source, (bytes, bytearray)):
+        if bytes(source[:4]) != b"OARG":
+            from . import onnx_io
+            return onnx_io.import_onnx(bytes(source))
         return bytes(source)
     if isinstance(source, str) and source.startswith("synthetic"):
         from . import models
@@ -144,11 +148,12 @@ def _resolve_model(source, kind: str) -> bytes:
         path = os.fspath(source)
         if not os.path.exists(path):
             raise OCRError("ModelLoad", f"model file '{path}' does not exist")
-        if path.endswith(".onnx"):
-            raise OCRError("ModelLoad", "ONNX import is not available in this build (no onnx parser offline); "
-                           "convert the graph to an OARG blob (oar_ocr_b200/models.py)")
         with open(path, "rb") as f:
-            return f.read()
+            data = f.read()
+        if path.endswith(".onnx") or data[:4] != b"OARG":
+            from . import onnx_io
+            return onnx_io.import_onnx(data)
+        return data
     raise OCRError("InvalidInput", f"unsupported model source {type(source)}")
 
 
