@@ -39,6 +39,7 @@ typedef struct oar_model oar_model; /* one network resident on a context */
 
 #define OAR_KIND_DET 0
 #define OAR_KIND_REC 1
+#define OAR_KIND_CLS 2 /* PP-LCNet classifier: text-line orientation */
 
 /* Detection post-process configuration.
  * = DBPostProcess{thresh, box_thresh, max_candidates, unclip_ratio, min_size}
@@ -178,12 +179,42 @@ typedef struct {
   int32_t* seq_len;    /* [cap_regions] */
   float* wh_ratio;     /* [cap_regions] */
   float* max_wh_ratio; /* [cap_regions] */
+  /* optional (may be NULL): TextRegion.orientation_angle of the line-orientation stage (ocr.rs:755-792, 888):
+   * 0 or 180 when oar_pipeline_run_cls ran with a classifier, -1 (None) otherwise */
+  float* line_angle;   /* [cap_regions] */
+  float ms_cls;        /* device time of the orientation stage (inside ms_rec's bracket: it runs after the crop) */
 } oar_ocr_result;
 
 /* images_on_device != 0: `images` are device pointers already resident in HBM */
 int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
                          const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
                          oar_ocr_result* out);
+
+/* ---- text-line orientation ---------------------------
+ * TextLineOrientationAdapter::execute -> PPLCNetModel::forward_refs
+ * (oar-ocr-core/src/domain/adapters/text_line_orientation_adapter.rs:63-121,
+ *  oar-ocr-core/src/models/classification/pp_lcnet.rs:139-196, 255-300): every crop is resized straight to
+ * input_w x input_h (Triangle, resize_short = None), normalised with scale 1/255 and the ImageNet mean/std in RGB
+ * order, classified, and reduced by Topk (oar-ocr-core/src/utils/topk.rs).  crops: n host u8 HWC images.
+ * class_ids/scores [n]: the top-1 (first maximal class, as the stable sort yields); probs (may be NULL) receives the
+ * full [n][*n_classes] rows so the caller can form any top-k; *n_classes is always returned.
+ * Unlike the reference's filter_map (pp_lcnet.rs:182-186), which silently drops zero-sized images and so shifts every
+ * later result, an empty crop is rejected with OAR_E_INVALID. */
+int32_t oar_cls_run(oar_model* cls, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                    int32_t input_h, int32_t input_w, int32_t* class_ids, float* scores, float* probs,
+                    size_t probs_cap, int32_t* n_classes);
+
+/* image::imageops::rotate180 as classify_line_orientations applies it to a crop of class 1 (ocr.rs:785-788).
+ * image/out: host u8 HWC [h][w][3]. */
+int32_t oar_rotate180(oar_ctx* ctx, const uint8_t* image, int32_t h, int32_t w, uint8_t* out);
+
+/* OAROCR::predict with with_text_line_orientation_classification (ocr.rs:197-203, 615): as oar_pipeline_run, and
+ * between cropping and recognition every crop is classified (input 80 x 160, DEFAULT_INPUT_SHAPE) and the crops of
+ * class 1 are rotated by 180 degrees in HBM; wh_ratio keeps its pre-rotation value.  cls == NULL: exactly
+ * oar_pipeline_run. */
+int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
+                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
+                             const oar_pipeline_config* cfg, oar_ocr_result* out);
 
 /* device memory helpers for callers that keep inputs resident (bench `value` leg) */
 int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out);

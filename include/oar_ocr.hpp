@@ -3,10 +3,13 @@
 //   OAROCRBuilder / OAROCR::predict       src/oarocr/ocr.rs:66-417, 518-659
 //   TextDetectionPredictor                oar-ocr-core/src/predictors/text_detection.rs:23-112
 //   TextRecognitionPredictor              oar-ocr-core/src/predictors/text_recognition.rs:19-110
+//   TextLineOrientationPredictor          oar-ocr-core/src/predictors/text_line_orientation.rs:18-105
 //   OCRError                              oar-ocr-core/src/core/errors/types.rs:110-214
 // Errors are thrown as oar::OCRError (Rust returns Result<_, OCRError>).  No CPU fallback exists.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -54,7 +57,26 @@ struct TextRegion {
   std::vector<int32_t> char_col_indices;
   int32_t sequence_length = 0;
   float wh_ratio = 0.0f, max_wh_ratio = 0.0f;
+  // line-orientation stage (ocr.rs:755-792): Some(0.0) / Some(180.0) when a classifier is attached, None otherwise
+  bool has_orientation_angle = false;
+  float orientation_angle = 0.0f;
 };
+struct Classification {  // domain/tasks: Classification{class_id, label, score}
+  size_t class_id;
+  std::string label;
+  float score;
+};
+struct TextLineOrientationResult { std::vector<std::vector<Classification>> orientations; };
+
+// Topk::extract_topk_from_prediction (oar-ocr-core/src/utils/topk.rs): stable sort by score descending, first k
+inline std::vector<size_t> topk_indices(const float* pred, size_t n, size_t k) {
+  if (k == 0) throw OCRError("InvalidInput", "k must be greater than 0", OAR_E_INVALID);
+  std::vector<size_t> order(n);
+  std::iota(order.begin(), order.end(), (size_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pred[a] > pred[b]; });
+  order.resize(std::min(k, n));
+  return order;
+}
 
 // OAROCR::is_cjk (src/oarocr/ocr.rs:1065-1084)
 inline bool is_cjk(char32_t u) {
@@ -218,9 +240,44 @@ class TextRecognitionPredictor {
   float thresh_;
 };
 
+class TextLineOrientationPredictor {
+ public:
+  // builder defaults: score_threshold 0.5, topk 2, input_shape (192, 48) read as (height, width)
+  // (predictors/text_line_orientation.rs:53-61); the pipeline's adapter uses (80, 160)
+  TextLineOrientationPredictor(Model& model, size_t topk = 2, int32_t input_h = 192, int32_t input_w = 48)
+      : model_(model), topk_(topk), h_(input_h), w_(input_w) {
+    if (topk == 0) throw OCRError("ConfigError", "topk must be at least 1");
+  }
+  TextLineOrientationResult predict(const std::vector<RgbImage>& images) const {
+    if (images.empty())  // tasks/text_line_orientation.rs:88-95
+      throw OCRError("InvalidInput", "No images provided for text line orientation classification", OAR_E_INVALID);
+    std::vector<const uint8_t*> ptrs;
+    std::vector<int32_t> hs, ws;
+    detail::image_table(images, "TextLineOrientation", ptrs, hs, ws);
+    const size_t n = images.size(), cap = n * 1024;
+    std::vector<int32_t> ids(n);
+    std::vector<float> scores(n), probs(cap);
+    int32_t nc = 0;
+    check(oar_cls_run(model_.raw(), ptrs.data(), hs.data(), ws.data(), (int32_t)n, h_, w_, ids.data(), scores.data(),
+                      probs.data(), cap, &nc));
+    TextLineOrientationResult r;
+    r.orientations.resize(n);
+    for (size_t i = 0; i < n; ++i)
+      for (size_t c : topk_indices(&probs[i * nc], (size_t)nc, topk_))  // labels "0" / "180" (adapter labels())
+        r.orientations[i].push_back(Classification{c, c < 2 ? std::to_string(c * 180) : "class_" + std::to_string(c),
+                                                   probs[i * nc + c]});
+    return r;
+  }
+ private:
+  Model& model_;
+  size_t topk_;
+  int32_t h_, w_;
+};
+
 class OAROCR {
  public:
-  OAROCR(Model& det, Model& rec, oar_pipeline_config cfg) : det_(det), rec_(rec), cfg_(cfg) {}
+  OAROCR(Model& det, Model& rec, oar_pipeline_config cfg, Model* cls = nullptr)
+      : det_(det), rec_(rec), cls_(cls), cfg_(cfg) {}
   std::vector<OAROCRResult> predict(const std::vector<RgbImage>& images) const {
     std::vector<const uint8_t*> ptrs;
     std::vector<int32_t> hs, ws;
@@ -230,13 +287,16 @@ class OAROCR {
     std::vector<int32_t> region_off(n + 1), det_index(cap_r), label_off(cap_r + 1), labels(cap_l);
     std::vector<float> boxes((size_t)cap_r * 8), scores(cap_r), wh_ratio(cap_r), max_wh_ratio(cap_r);
     std::vector<int32_t> cols(cap_l), seq_len(cap_r);
+    std::vector<float> line_angle(cap_r, -1.0f);
     oar_ocr_result out{};
+    out.line_angle = line_angle.data();
     out.cols = cols.data(), out.seq_len = seq_len.data(), out.wh_ratio = wh_ratio.data();
     out.max_wh_ratio = max_wh_ratio.data();
     out.cap_regions = cap_r, out.cap_labels = cap_l;
     out.region_off = region_off.data(), out.boxes = boxes.data(), out.scores = scores.data();
     out.det_index = det_index.data(), out.label_off = label_off.data(), out.labels = labels.data();
-    check(oar_pipeline_run(det_.raw(), rec_.raw(), ptrs.data(), hs.data(), ws.data(), (int32_t)n, 0, &cfg_, &out));
+    check(oar_pipeline_run_cls(det_.raw(), rec_.raw(), cls_ ? cls_->raw() : nullptr, ptrs.data(), hs.data(), ws.data(),
+                               (int32_t)n, 0, &cfg_, &out));
     std::vector<OAROCRResult> res(n);
     for (size_t i = 0; i < n; ++i) {
       res[i].index = i;
@@ -248,6 +308,7 @@ class OAROCR {
         t.detection_index = det_index[r];
         t.char_col_indices.assign(cols.begin() + label_off[r], cols.begin() + label_off[r + 1]);
         t.sequence_length = seq_len[r], t.wh_ratio = wh_ratio[r], t.max_wh_ratio = max_wh_ratio[r];
+        t.has_orientation_angle = line_angle[r] >= 0.0f, t.orientation_angle = t.has_orientation_angle ? line_angle[r] : 0.0f;
         res[i].text_regions.push_back(std::move(t));
       }
     }
@@ -256,6 +317,7 @@ class OAROCR {
  private:
   Model& det_;
   Model& rec_;
+  Model* cls_;
   oar_pipeline_config cfg_;
 };
 
@@ -275,14 +337,17 @@ class OAROCRBuilder {
   OAROCRBuilder& region_batch_size(size_t s) { region_bs_ = s, has_region_bs_ = true; return *this; }
   OAROCRBuilder& text_detection_config(const TextDetectionConfig& c) { cfg_.det = c.to_abi(); return *this; }
   OAROCRBuilder& rec_score_threshold(float t) { cfg_.rec_score_thresh = t; return *this; }
+  // OAROCRBuilder::with_text_line_orientation_classification (ocr.rs:197-203)
+  OAROCRBuilder& with_text_line_orientation_classification(Model& cls) { cls_ = &cls; return *this; }
   OAROCR build() {
     if (has_image_bs_) validate_batch_size("image_batch_size", image_bs_), cfg_.image_batch_size = (int32_t)image_bs_;
     if (has_region_bs_) validate_batch_size("region_batch_size", region_bs_), cfg_.region_batch_size = (int32_t)region_bs_;
-    return OAROCR(det_, rec_, cfg_);
+    return OAROCR(det_, rec_, cfg_, cls_);
   }
  private:
   Model& det_;
   Model& rec_;
+  Model* cls_ = nullptr;
   oar_pipeline_config cfg_;
   size_t image_bs_ = 0, region_bs_ = 0;
   bool has_image_bs_ = false, has_region_bs_ = false;

@@ -9,6 +9,8 @@
 //   crop pool + flush  = MAX_POOLED_CROPS                        src/oarocr/ocr.rs:603-633
 //   wh-ratio chunks    = OAROCR::recognize_global                src/oarocr/ocr.rs:802-897
 //   rec batch tensor   = CRNNModel::preprocess_refs              oar-ocr-core/src/models/recognition/crnn.rs:71-125
+//   line orientation   = OAROCR::classify_line_orientations      src/oarocr/ocr.rs:755-792
+//                        PPLCNetModel::preprocess_refs           oar-ocr-core/src/models/classification/pp_lcnet.rs:139-196
 // Everything numeric runs in the CUDA kernels of engine.cu / gemm_tc.cu / prepost.cu / dbpost.cu;
 // the host only sequences launches, sorts a few hundred boxes and lays out result buffers.
 #include <algorithm>
@@ -449,6 +451,60 @@ void launch_rec_batch(oar_model* rec, const RecCrop* crops, int n, int n_chars, 
   ctx->arena.release_to(mark);
 }
 
+// ImageNet normalisation in RGB order as PPLCNetModelBuilder::build configures it (pp_lcnet.rs:400-412)
+void cls_norm_coeffs(int src[3], float alpha[3], float beta[3]) {
+  det_norm_coeffs(src, alpha, beta);
+  for (int c = 0; c < 3; ++c) src[c] = c;
+}
+
+constexpr int CLS_H = 80, CLS_W = 160;  // TextLineOrientationAdapter::DEFAULT_INPUT_SHAPE
+constexpr int CLS_CHUNK = 256;          // crops per classifier launch (bounds the activation arena, not a result knob)
+
+// PPLCNetModel::forward_refs (pp_lcnet.rs:139-196, 200-243) on one batch of device crops: direct Triangle resize to
+// iw x ih, normalise, network, top-1.  d_ids / d_scores [n] and (optionally) d_probs [n][C] are device outputs owned
+// by the caller; returns C.  Scratch is released on return (stream order makes the reuse safe).
+int launch_cls_batch(oar_model* cls, const RecCrop* crops, int n, int ih, int iw, int32_t* d_ids, float* d_scores,
+                     float* d_probs, size_t probs_cap) {
+  oar_ctx* ctx = cls->ctx;
+  auto mark = ctx->arena.mark();
+  std::vector<ResizeJob> jobs(n);
+  std::vector<const uint8_t*> ptrs(n);
+  int max_sw = 0;
+  for (int i = 0; i < n; ++i) {
+    if (crops[i].h <= 0 || crops[i].w <= 0) OAR_FAIL(OAR_E_INVALID, "crop %d has invalid dimensions", i);
+    ResizeJob& j = jobs[i];
+    j.src = crops[i].p, j.sw = crops[i].w, j.sh = crops[i].h, j.dw = iw, j.dh = ih;
+    j.tmp = ctx->arena.get<float>((size_t)ih * crops[i].w * 3);
+    j.dst = ctx->arena.get<uint8_t>((size_t)ih * iw * 3);
+    ptrs[i] = j.dst;
+    max_sw = std::max(max_sw, j.sw);
+  }
+  bool aligned = true;
+  for (int i = 0; i < n; ++i) aligned = aligned && (((uintptr_t)ptrs[i] & 3) == 0);
+  ResizeJob* d_jobs = to_device(ctx, jobs.data(), jobs.size());
+  const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data(), (size_t)n);
+  launch_resize_triangle(ctx, d_jobs, n, max_sw, iw, ih);
+  Tensor in;
+  in.B = n, in.H = ih, in.W = iw, in.C = 3;
+  in.p = ctx->arena.get<float>(in.numel());
+  int src[3];
+  float alpha[3], beta[3];
+  cls_norm_coeffs(src, alpha, beta);
+  launch_normalize(ctx, nullptr, d_table, aligned, in.p, n, ih, iw, src, alpha, beta, /*NHWC*/ 1);
+  CtcOut head;
+  Tensor probs = model_forward(cls, in, /*want_probs=*/true, &head);
+  if (!probs.p || probs.B != n || probs.H * probs.W != 1 || probs.C <= 0)
+    OAR_FAIL(OAR_E_MODEL, "classifier output %dx%dx%dx%d is not [n,1,1,classes]", probs.B, probs.H, probs.W, probs.C);
+  const int C = probs.C;
+  launch_cls_top1(ctx, probs.p, n, C, d_ids, d_scores);
+  if (d_probs) {
+    if ((size_t)n * C > probs_cap) OAR_FAIL(OAR_E_CAPACITY, "probabilities need %zu floats", (size_t)n * C);
+    OAR_CUDA(cudaMemcpyAsync(d_probs, probs.p, (size_t)n * C * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  ctx->arena.release_to(mark);
+  return C;
+}
+
 void require_device(oar_ctx* ctx) {
   if (!ctx) OAR_FAIL(OAR_E_INVALID, "null context");
 }
@@ -554,7 +610,7 @@ int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_mod
   memcpy(&n_tensors, p + 16, 4);
   memcpy(&n_w, p + 20, 8);
   if (version != 1) OAR_FAIL(OAR_E_MODEL, "unsupported OARG version %u", version);
-  if (kind > 1) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", kind);
+  if (kind > OAR_KIND_CLS) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", kind);
   size_t need = 28 + (size_t)n_ops * sizeof(OpRec) + (size_t)n_w * 4;
   if (len < need) OAR_FAIL(OAR_E_MODEL, "truncated model blob: %zu bytes, need %zu", len, need);
   std::lock_guard<std::mutex> lock(ctx->mu);
@@ -892,13 +948,83 @@ int32_t oar_rec_run(oar_model* rec, const uint8_t* const* crops, const int32_t* 
   API_CATCH
 }
 
+int32_t oar_cls_run(oar_model* cls, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                    int32_t input_h, int32_t input_w, int32_t* class_ids, float* scores, float* probs,
+                    size_t probs_cap, int32_t* n_classes) {
+  API_TRY
+  if (!cls || cls->kind != OAR_KIND_CLS) OAR_FAIL(OAR_E_INVALID, "not a classification model");
+  if (n_classes) *n_classes = 0;
+  if (input_h <= 0 || input_w <= 0) OAR_FAIL(OAR_E_INVALID, "input shape must be positive");
+  if (n <= 0) return OAR_OK;  // the adapter returns an empty TextLineOrientationOutput
+  if (!crops || !hs || !ws || !class_ids || !scores) OAR_FAIL(OAR_E_INVALID, "null argument");
+  oar_ctx* ctx = cls->ctx;
+  CallGuard guard(ctx);
+  std::vector<RecCrop> rc(n);
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !crops[i]) OAR_FAIL(OAR_E_INVALID, "crop %d is empty", i);
+    size_t bytes = (size_t)hs[i] * ws[i] * 3;
+    uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+    OAR_CUDA(cudaMemcpyAsync(d, crops[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc[i] = RecCrop{d, hs[i], ws[i]};
+  }
+  int32_t* d_ids = ctx->arena.get<int32_t>(n);
+  float* d_sc = ctx->arena.get<float>(n);
+  // class count is a property of the graph: the head op's output width
+  int C = 0;
+  for (const OpRec& op : cls->ops)
+    if (op.type == OP_CTC_HEAD) C = op.p[1];
+  if (C <= 0) OAR_FAIL(OAR_E_MODEL, "classifier graph has no Linear+Softmax head");
+  float* d_probs = probs ? ctx->arena.get<float>((size_t)n * C) : nullptr;
+  if (probs && (size_t)n * C > probs_cap)
+    OAR_FAIL(OAR_E_CAPACITY, "probabilities need %zu floats, capacity %zu", (size_t)n * C, probs_cap);
+  for (int s0 = 0; s0 < n; s0 += CLS_CHUNK) {
+    int m = std::min(CLS_CHUNK, n - s0);
+    int got = launch_cls_batch(cls, rc.data() + s0, m, input_h, input_w, d_ids + s0, d_sc + s0,
+                               d_probs ? d_probs + (size_t)s0 * C : nullptr, (size_t)m * C);
+    if (got != C) OAR_FAIL(OAR_E_MODEL, "classifier produced %d classes, graph declares %d", got, C);
+  }
+  cudaStream_t st = ctx->stream;
+  OAR_CUDA(cudaMemcpyAsync(class_ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaMemcpyAsync(scores, d_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (probs) OAR_CUDA(cudaMemcpyAsync(probs, d_probs, (size_t)n * C * 4, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaStreamSynchronize(st));
+  if (n_classes) *n_classes = C;
+  API_CATCH
+}
+
+int32_t oar_rotate180(oar_ctx* ctx, const uint8_t* image, int32_t h, int32_t w, uint8_t* out) {
+  API_TRY
+  require_device(ctx);
+  if (h < 0 || w < 0) OAR_FAIL(OAR_E_INVALID, "negative dimension");
+  size_t bytes = (size_t)h * w * 3;
+  if (bytes == 0) return OAR_OK;
+  if (!image || !out) OAR_FAIL(OAR_E_INVALID, "null buffer");
+  CallGuard guard(ctx);
+  uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+  OAR_CUDA(cudaMemcpyAsync(d, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  Rot180Job job{d, h * w};
+  Rot180Job* d_job = to_device(ctx, &job, 1);
+  launch_rotate180(ctx, d_job, 1, h * w, nullptr);
+  OAR_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
 int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
                          const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
                          oar_ocr_result* out) {
+  return oar_pipeline_run_cls(det, rec, nullptr, images, hs, ws, n, images_on_device, cfg, out);
+}
+
+int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
+                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
+                             const oar_pipeline_config* cfg, oar_ocr_result* out) {
   API_TRY
   if (!det || det->kind != OAR_KIND_DET || !rec || rec->kind != OAR_KIND_REC)
     OAR_FAIL(OAR_E_INVALID, "pipeline needs one detection and one recognition model");
   if (det->ctx != rec->ctx) OAR_FAIL(OAR_E_INVALID, "both models must live on the same context");
+  if (cls && (cls->kind != OAR_KIND_CLS || cls->ctx != det->ctx))
+    OAR_FAIL(OAR_E_INVALID, "the line-orientation model must be a classifier on the same context");
   if (!cfg || !out) OAR_FAIL(OAR_E_INVALID, "null argument");
   // OAROCR::predict rejects an empty image list (ocr.rs:525-532)
   if (n <= 0 || !images || !hs || !ws) OAR_FAIL(OAR_E_INVALID, "images: expected non-empty slice, got empty slice");
@@ -908,9 +1034,9 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
   oar_ctx* ctx = det->ctx;
   CallGuard guard(ctx);
   cudaStream_t st = ctx->stream;
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[6];
   for (auto& e : ev) e = ctx->next_event();
-  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = 0.0f;
+  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
   out->h2d_bytes = out->d2h_bytes = 0;
   cudaEventRecord(ev[0], st);
 
@@ -982,6 +1108,40 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
     }
   }
   cudaEventRecord(ev[3], st);
+
+  // ---- line orientation (ocr.rs:615, 755-792): classify every crop, rotate class-1 crops by 180 degrees in the pool.
+  // The reference calls the adapter once per image; the classifier treats every crop independently (fixed 80 x 160
+  // input, per-sample pooling), so one pass over all crops in chunks gives the same classes.  No host round trip:
+  // the rotation kernel reads the class ids on the device; the host reads them after the final synchronise.
+  std::vector<int> valid_of(n_boxes, -1);
+  int32_t* h_cls_ids = nullptr;
+  if (cls && pool) {
+    std::vector<int> valid;
+    for (int i = 0; i < n_boxes; ++i)
+      if (h_plans[i].status == 0) valid_of[i] = (int)valid.size(), valid.push_back(i);
+    const int nv = (int)valid.size();
+    int32_t* d_ids = ctx->arena.get<int32_t>(nv);
+    float* d_sc = ctx->arena.get<float>(nv);
+    std::vector<Rot180Job> rj(nv);
+    int max_npix = 0;
+    for (int s0 = 0; s0 < nv; s0 += CLS_CHUNK) {
+      int m = std::min(CLS_CHUNK, nv - s0);
+      std::vector<RecCrop> rc(m);
+      for (int k = 0; k < m; ++k) {
+        const CropPlan& p = h_plans[valid[s0 + k]];
+        rc[k] = RecCrop{pool + p.out_off, p.oh, p.ow};
+        rj[s0 + k] = Rot180Job{pool + p.out_off, p.oh * p.ow};
+        max_npix = std::max(max_npix, p.oh * p.ow);
+      }
+      launch_cls_batch(cls, rc.data(), m, CLS_H, CLS_W, d_ids + s0, d_sc + s0, nullptr, 0);
+    }
+    Rot180Job* d_rj = to_device(ctx, rj.data(), rj.size());
+    launch_rotate180(ctx, d_rj, nv, max_npix, d_ids);
+    h_cls_ids = (int32_t*)ctx->pinned_get((size_t)nv * sizeof(int32_t));
+    OAR_CUDA(cudaMemcpyAsync(h_cls_ids, d_ids, (size_t)nv * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    out->d2h_bytes += (int64_t)nv * 4;
+  }
+  cudaEventRecord(ev[5], st);
 
   // ---- recognition: pool crops across images, flush at MAX_POOLED_CROPS, sort by wh_ratio, chunk
   struct Pooled {
@@ -1071,6 +1231,7 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
       if (out->seq_len) out->seq_len[r] = box_T[box];
       if (out->wh_ratio) out->wh_ratio[r] = h_plans[box].wh_ratio;
       if (out->max_wh_ratio) out->max_wh_ratio[r] = box_max_ratio[box];
+      if (out->line_angle) out->line_angle[r] = h_cls_ids ? (float)h_cls_ids[valid_of[box]] * 180.0f : -1.0f;
       nl += lab_len[box];
       ++r;
     }
@@ -1080,6 +1241,7 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
   cudaEventElapsedTime(&out->ms_h2d, ev[0], ev[1]);
   cudaEventElapsedTime(&out->ms_crop, ev[2], ev[3]);
   cudaEventElapsedTime(&out->ms_rec, ev[3], ev[4]);
+  cudaEventElapsedTime(&out->ms_cls, ev[3], ev[5]);
   cudaEventElapsedTime(&out->ms_total, ev[0], ev[4]);
   API_CATCH
 }

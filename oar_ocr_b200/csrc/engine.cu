@@ -917,6 +917,10 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
       }
       case OP_AVGPOOL: {
         int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3];
+        if (kh == 0 && kw == 0) kh = sh = a.H, kw = sw = a.W;  // global average pool (classifier trunk)
+        if (kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || kh > a.H || kw > a.W)
+          OAR_FAIL(OAR_E_MODEL, "avgpool op %zu: window %dx%d / stride %dx%d does not fit %dx%d", oi, kh, kw, sh, sw, a.H,
+                   a.W);
         int Ho = (a.H - kh) / sh + 1, Wo = (a.W - kw) / sw + 1;
         Tensor& o = ensure(op.out, a.B, Ho, Wo, a.C);
         Launch l(ctx, "avgpool", (double)a.numel(), 4.0 * (a.numel() + o.numel()));

@@ -4,6 +4,8 @@
 //   crop_plan/warp : get_rotate_crop_image, utils/transform.rs:76-191 (+ :212-283 LU, :312-316 inverse, :439-502 bicubic)
 //   crnn_normalize : normalize_crnn_chw_into, simd.rs:248-308
 //   ctc_argmax/decode: decode.rs:452-614, simd.rs:190-229
+#include <algorithm>
+
 #include "prepost.cuh"
 
 namespace oar {
@@ -553,6 +555,59 @@ void launch_ctc_decode(oar_ctx* ctx, const int32_t* idx, const float* prob, int 
   if (!B) return;
   Launch l(ctx, "ctc_decode", 0, 8.0 * B * T);
   ctc_decode_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(idx, prob, B, T, n_chars, labels, cols, lens, scores);
+}
+
+// ---------------------------------------------------------------------------
+// text-line orientation stage: top-1 class and the in-place 180-degree rotation (ocr.rs:755-792)
+// ---------------------------------------------------------------------------
+// Topk::extract_topk_from_prediction (utils/topk.rs) sorts (index, score) pairs by score descending with a stable
+// sort, so the top-1 is the first index holding the maximum.
+__global__ void cls_top1_kernel(const float* __restrict__ probs, int n, int C, int32_t* __restrict__ ids,
+                                float* __restrict__ scores) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = probs + (size_t)i * C;
+  float best = p[0];
+  int id = 0;
+  for (int c = 1; c < C; ++c) {
+    float v = p[c];
+    if (v > best) best = v, id = c;
+  }
+  ids[i] = id;
+  scores[i] = best;
+}
+
+void launch_cls_top1(oar_ctx* ctx, const float* probs, int n, int C, int32_t* ids, float* scores) {
+  if (n <= 0 || C <= 0) return;
+  Launch l(ctx, "cls_top1", 0, 4.0 * n * C + 8.0 * n);
+  cls_top1_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(probs, n, C, ids, scores);
+}
+
+// One thread per pixel pair (i, npix-1-i); 6 B read + 6 B written per pair, HBM/L2-bound.
+__global__ void __launch_bounds__(256) rotate180_kernel(const Rot180Job* __restrict__ jobs,
+                                                        const int32_t* __restrict__ class_ids) {
+  const int j = blockIdx.y;
+  if (class_ids && class_ids[j] != 1) return;
+  const Rot180Job job = jobs[j];
+  const int half = job.npix >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x) {
+    uint8_t* a = job.p + (size_t)i * 3;
+    uint8_t* b = job.p + (size_t)(job.npix - 1 - i) * 3;
+    uint8_t a0 = a[0], a1 = a[1], a2 = a[2];
+    uint8_t b0 = b[0], b1 = b[1], b2 = b[2];
+    a[0] = b0, a[1] = b1, a[2] = b2;
+    b[0] = a0, b[1] = a1, b[2] = a2;
+  }
+}
+
+void launch_rotate180(oar_ctx* ctx, const Rot180Job* d_jobs, int n_jobs, int max_npix, const int32_t* class_ids) {
+  if (n_jobs <= 0 || max_npix < 2) return;
+  Launch l(ctx, "rotate180", 0, 6.0 * max_npix * n_jobs);
+  int bx = std::max(1, std::min(cdiv(max_npix / 2, 256), 64));
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    int nj = std::min(n_jobs - j0, 65535);
+    rotate180_kernel<<<dim3(bx, nj), 256, 0, ctx->stream>>>(d_jobs + j0, class_ids ? class_ids + j0 : nullptr);
+  }
 }
 
 }  // namespace oar

@@ -63,6 +63,17 @@ void launch_ctc_argmax(oar_ctx* ctx, const float* pred, long long rows, int V, i
 void launch_ctc_decode(oar_ctx* ctx, const int32_t* idx, const float* prob, int B, int T, int n_chars, int32_t* labels,
                        int32_t* cols, int32_t* lens, float* scores);
 
+// Text-line orientation stage (src/oarocr/ocr.rs:755-792).
+// top-1 of Topk::process (utils/topk.rs): stable descending sort = the FIRST maximal class; probs [n][C].
+void launch_cls_top1(oar_ctx* ctx, const float* probs, int n, int C, int32_t* ids, float* scores);
+// image::imageops::rotate180 in place on u8 HWC images: pixel i <-> pixel npix-1-i.  class_ids (device, one per job,
+// may be null = rotate every job): only jobs whose class id is 1 ("180") are rotated.
+struct Rot180Job {
+  uint8_t* p;
+  int npix;
+};
+void launch_rotate180(oar_ctx* ctx, const Rot180Job* d_jobs, int n_jobs, int max_npix, const int32_t* class_ids);
+
 // DB post-process (db_postprocess.rs:100-179 + db_bitmap.rs:84-150), batched over images.
 // pred [B][H][W] device.  Outputs device arrays: boxes [B][max_cand][8], scores [B][max_cand], counts [B].
 struct DbPostOut {

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboar_b200.so")
 
 OAR_OK, OAR_E_INVALID, OAR_E_NO_DEVICE, OAR_E_CUDA, OAR_E_MODEL, OAR_E_CAPACITY, OAR_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-KIND_DET, KIND_REC = 0, 1
+KIND_DET, KIND_REC, KIND_CLS = 0, 1, 2
 
 # every symbol include/oar_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
@@ -23,7 +23,7 @@ SYMBOLS = [
     "oar_ctx_create", "oar_ctx_destroy", "oar_ctx_synchronize", "oar_model_load_blob", "oar_model_destroy",
     "oar_model_kind", "oar_model_set_engine", "oar_infer_f32", "oar_normalize_chw", "oar_db_postprocess",
     "oar_det_run", "oar_sort_quad_boxes", "oar_rotate_crop", "oar_crnn_preprocess", "oar_ctc_decode", "oar_rec_run",
-    "oar_pipeline_run", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
+    "oar_pipeline_run", "oar_cls_run", "oar_rotate180", "oar_pipeline_run_cls", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
     "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush",
 ]
 
@@ -66,7 +66,8 @@ class OcrResult(C.Structure):
                 ("ms_post", C.c_float), ("ms_crop", C.c_float), ("ms_rec", C.c_float), ("ms_total", C.c_float),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cols", C.POINTER(C.c_int32)),
                 ("seq_len", C.POINTER(C.c_int32)), ("wh_ratio", C.POINTER(C.c_float)),
-                ("max_wh_ratio", C.POINTER(C.c_float))]
+                ("max_wh_ratio", C.POINTER(C.c_float)), ("line_angle", C.POINTER(C.c_float)),
+                ("ms_cls", C.c_float)]
 
 
 class KernelRecord(C.Structure):
@@ -116,6 +117,11 @@ def lib():
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.oar_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
+        L.oar_cls_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
+        L.oar_rotate180.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.oar_pipeline_run_cls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
         L.oar_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.oar_device_free.argtypes = [C.c_void_p, C.c_void_p]
         L.oar_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -287,6 +293,15 @@ class Context:
         return dict(idx=idx, prob=prob, labels=[labels[i, :lens[i]].copy() for i in range(b)],
                     cols=[cols[i, :lens[i]].copy() for i in range(b)], scores=scores[:b].copy(), T=t)
 
+    # ---- line orientation: image::imageops::rotate180 (ocr.rs:785-788)
+    def rotate180(self, image: np.ndarray) -> np.ndarray:
+        image = np.ascontiguousarray(image, np.uint8)
+        if image.ndim != 3 or image.shape[2] != 3:
+            raise OCRError("InvalidInput", f"expected HxWx3 u8 image, got shape {image.shape}", OAR_E_INVALID)
+        out = np.empty_like(image)
+        check(lib().oar_rotate180(self.handle, _ptr(image), image.shape[0], image.shape[1], _ptr(out)))
+        return out
+
     def profile(self, on: bool):
         check(lib().oar_profile_enable(self.handle, 1 if on else 0))
 
@@ -352,12 +367,13 @@ class Model:
         check(lib().oar_model_set_engine(self.handle, engine))
 
     def infer(self, x: np.ndarray, vocab_hint: int = 18385) -> np.ndarray:
-        """OrtInfer::infer: x f32 [B,3,H,W] -> det [B,1,H,W] / rec [B,T,V]"""
+        """OrtInfer::infer: x f32 [B,3,H,W] -> det [B,1,H,W] / rec [B,T,V] / cls [B,classes]"""
         x = np.ascontiguousarray(x, np.float32)
         if x.ndim != 4:
             raise OCRError("InvalidInput", "input must be 4-D", OAR_E_INVALID)
         b, c, h, w = x.shape
-        cap = b * h * w if self.kind == KIND_DET else b * (w // 8 + 2) * vocab_hint
+        cap = b * h * w if self.kind == KIND_DET else (b * 4096 if self.kind == KIND_CLS else
+                                                       b * (w // 8 + 2) * vocab_hint)
         out = np.empty(max(cap, 1), np.float32)
         ishape = (C.c_int64 * 4)(b, c, h, w)
         oshape = (C.c_int64 * 4)()
@@ -365,7 +381,8 @@ class Model:
         if self.kind == KIND_DET:
             return out[:oshape[0] * oshape[1] * oshape[2] * oshape[3]].reshape(oshape[0], oshape[1], oshape[2],
                                                                                oshape[3])
-        return out[:oshape[0] * oshape[1] * oshape[2]].reshape(oshape[0], oshape[1], oshape[2])
+        y = out[:oshape[0] * oshape[1] * oshape[2]].reshape(oshape[0], oshape[1], oshape[2])
+        return y.reshape(oshape[0], oshape[2]) if self.kind == KIND_CLS else y
 
     def det_run(self, images, cfg: DetConfig | None = None):
         cfg = cfg or det_config()
@@ -395,6 +412,24 @@ class Model:
                                 _ptr(lens), _ptr(scores), t_cap, C.byref(t_out)))
         return dict(labels=[labels[i, :lens[i]].copy() for i in range(n)],
                     cols=[cols[i, :lens[i]].copy() for i in range(n)], scores=scores, T=t_out.value)
+
+
+    def cls_run(self, crops, input_shape=(80, 160), want_probs=True):
+        """TextLineOrientationAdapter::execute: returns dict(class_ids [n], scores [n], probs [n,C] or None)"""
+        if not crops:
+            return dict(class_ids=np.zeros(0, np.int32), scores=np.zeros(0, np.float32),
+                        probs=np.zeros((0, 0), np.float32) if want_probs else None)
+        arrs, ptrs, hs, ws = _image_table(crops)
+        n = len(arrs)
+        ids = np.zeros(n, np.int32)
+        scores = np.zeros(n, np.float32)
+        nc = C.c_int32()
+        cap = n * 1024
+        probs = np.zeros(cap, np.float32) if want_probs else None
+        check(lib().oar_cls_run(self.handle, ptrs, _ptr(hs), _ptr(ws), n, int(input_shape[0]), int(input_shape[1]),
+                                _ptr(ids), _ptr(scores), _ptr(probs) if want_probs else None, cap, C.byref(nc)))
+        return dict(class_ids=ids, scores=scores,
+                    probs=probs[:n * nc.value].reshape(n, nc.value).copy() if want_probs else None)
 
 
 class PipelineBuffers:
@@ -428,11 +463,18 @@ class PipelineBuffers:
         self.res.seq_len = self.seq_len.ctypes.data_as(P(C.c_int32))
         self.res.wh_ratio = self.wh_ratio.ctypes.data_as(P(C.c_float))
         self.res.max_wh_ratio = self.max_wh_ratio.ctypes.data_as(P(C.c_float))
+        # TextRegion.orientation_angle of the line-orientation stage: 0 / 180, -1 = None (no classifier)
+        self.line_angle = np.full(cap_regions, -1.0, np.float32)
+        self.res.line_angle = self.line_angle.ctypes.data_as(P(C.c_float))
 
 
 def pipeline_run(det: Model, rec: Model, image_ptrs, hs: np.ndarray, ws: np.ndarray, on_device: bool,
-                 cfg: PipelineConfig, bufs: PipelineBuffers):
-    """image_ptrs: ctypes array of c_void_p (host or device addresses)"""
-    check(lib().oar_pipeline_run(det.handle, rec.handle, image_ptrs, _ptr(hs), _ptr(ws), len(hs),
-                                 1 if on_device else 0, C.byref(cfg), C.byref(bufs.res)))
+                 cfg: PipelineConfig, bufs: PipelineBuffers, cls: Model | None = None):
+    """image_ptrs: ctypes array of c_void_p (host or device addresses); cls: optional line-orientation classifier"""
+    if cls is None:
+        check(lib().oar_pipeline_run(det.handle, rec.handle, image_ptrs, _ptr(hs), _ptr(ws), len(hs),
+                                     1 if on_device else 0, C.byref(cfg), C.byref(bufs.res)))
+    else:
+        check(lib().oar_pipeline_run_cls(det.handle, rec.handle, cls.handle, image_ptrs, _ptr(hs), _ptr(ws), len(hs),
+                                         1 if on_device else 0, C.byref(cfg), C.byref(bufs.res)))
     return bufs.res

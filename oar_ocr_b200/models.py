@@ -13,7 +13,7 @@ the CPU oracle (oracle/net.py) execute.  One blob = one source of truth for
 layer shapes and weights.
 
 Blob layout (all little endian):
-  magic "OARG" | u32 version=1 | u32 kind (0 det, 1 rec) | u32 n_ops |
+  magic "OARG" | u32 version=1 | u32 kind (0 det, 1 rec, 2 cls) | u32 n_ops |
   u32 n_tensors | u64 n_weight_floats |
   n_ops x OpRec{ i32 type, i32 in0, i32 in1, i32 out, i32 p[12], f32 f[4],
                  i64 w_off[4], i64 w_len[4] }   (144 bytes)
@@ -32,7 +32,7 @@ import numpy as np
 
 MAGIC = b"OARG"
 VERSION = 1
-KIND_DET, KIND_REC = 0, 1
+KIND_DET, KIND_REC, KIND_CLS = 0, 1, 2
 
 # op types
 OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL, OP_LAYERNORM, OP_ATTN, \
@@ -138,6 +138,7 @@ class GraphBuilder:
         return out
 
     def avgpool(self, x, k, s):
+        """k = (0, 0): global average pool"""
         out = self.new_tensor(self.channels[x])
         self.ops.append(Op(OP_AVGPOOL, x, -1, out, [k[0], k[1], s[0], s[1]] + [0] * 8))
         return out
@@ -388,6 +389,94 @@ def build_rec(seed: int = 42, vocab: int = 18385, scale: float = 0.95, logit_gai
     return g.serialize()
 
 
+# PP-LCNet (v1) stage table of the text-line orientation classifier: (k, in, out, stride, use_se).  PaddleClas'
+# textline_orientation configuration keeps the width after the stem: stride_list [2, [2,1], [2,1], [2,1], [2,1]] on
+# 80 x 160 inputs (EXT: recalled from the PULC configuration; the .onnx file is not available offline).
+_NET_CLS = {
+    2: [(3, 16, 32, (1, 1), False)],
+    3: [(3, 32, 64, (2, 1), False), (3, 64, 64, (1, 1), False)],
+    4: [(3, 64, 128, (2, 1), False), (3, 128, 128, (1, 1), False)],
+    5: [(3, 128, 256, (2, 1), False)] + [(5, 256, 256, (1, 1), False)] * 5,
+    6: [(5, 256, 512, (2, 1), True), (5, 512, 512, (1, 1), True)],
+}
+CLS_INPUT_SHAPE = (80, 160)  # TextLineOrientationAdapter::DEFAULT_INPUT_SHAPE, text_line_orientation_adapter.rs:48
+
+
+def _lcnet_v1_block(g: GraphBuilder, x, k, cout, stride, use_se, plant):
+    """PP-LCNet v1 DepthwiseSeparable: dw conv + BN + hardswish -> [SE] -> 1x1 conv + BN + hardswish.  The first
+    `plant` channels pass through untouched by the random weights (identity centre tap, or a box filter where the
+    layer is strided; identity rows in the 1x1 conv)."""
+    c = g.channels[x]
+    wd = g.he((k, k, c), k * k)
+    bd = g.small((c,))
+    if plant:
+        wd[:, :, :plant] = 0.0
+        if stride == (1, 1):
+            wd[k // 2, k // 2, :plant] = 1.0
+        else:  # strided layers average their window, so the planted statistics see every input row
+            wd[:, :, :plant] = 1.0 / (k * k)
+        bd[:plant] = 0.0
+    x = g.dwconv(x, k, stride, act=ACT_HSWISH, w=wd, b=bd)
+    if use_se:
+        x = g.se(x, c // 4)
+        if plant:  # gate of the planted channels saturated at 1
+            g.ops[-1].w[2][:plant] = 0.0
+            g.ops[-1].w[3][:plant] = 6.0
+    wp = g.he((cout, 1, 1, c), c)
+    bp = g.small((cout,))
+    if plant:
+        wp = _plant_row0(wp, plant)
+        wp[plant:, :, :, :plant] = 0.0
+        bp[:plant] = 0.0
+    return g.conv(x, cout, (1, 1), act=ACT_HSWISH, w=wp, b=bp)
+
+
+def build_cls(seed: int = 42, scale: float = 1.0, num_classes: int = 2, dark_ref: float = -5.55, dark_gain: float = 6.0) -> bytes:
+    """PP-LCNet_x1_0_textline_ori shaped graph (oar-ocr-core/src/models/classification/pp_lcnet.rs runs it through
+    ORT): stem 3x3 s2 -> 13 depthwise-separable blocks -> global average pool -> 1x1 conv 1280 + hardswish ->
+    Linear(1280 -> num_classes) + softmax.  Output [B, 1, num_classes] probabilities; class 1 = "180".
+
+    Synthetic weights with a planted, well-conditioned decision (everything else is He-normal so the arithmetic volume
+    is the real network's): stem channel 0 = 10 + darkness of the pixel (always >= 3, where hardswish is the identity),
+    carried through the trunk by identity taps / box filters, so the average pool yields D = 10 + mean darkness of the
+    crop; the head computes logit_180 - logit_0 = 2 [hs(g (D - 10 - dark_ref)) - hs(-g (D - 10 - dark_ref))]: dark
+    crops are called "180", light ones "0".  Not a real orientation cue -- it makes both classes occur on the synthetic
+    pages with wide margins, which is what the parity tests need (the rotate180 that follows changes the recognised
+    text, so a wrong or missing rotation cannot go unnoticed).
+    """
+    g = GraphBuilder(KIND_CLS, seed)
+    g.base_gain = 0.8
+    md = lambda c: make_divisible(c * scale)
+    NP = 1
+    c1 = md(16)
+    w = g.he((c1, 3, 3, 3), 27)
+    b = g.small((c1,))
+    w[0] = 0.0
+    w[0, 1, 1, :] = -1.0   # normalised input: dark < 0
+    b[0] = 10.0
+    x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_HSWISH, w=w, b=b)
+    for stage in (2, 3, 4, 5, 6):
+        for (k, _cin, cout, s, use_se) in _NET_CLS[stage]:
+            x = _lcnet_v1_block(g, x, k, md(cout), s, use_se, plant=NP)
+    x = g.avgpool(x, (0, 0), (0, 0))  # (0, 0) window = global average pool: any input shape
+    cin = g.channels[x]
+    wl = g.he((1280, 1, 1, cin), cin)
+    bl = np.zeros((1280,), np.float32)   # last_conv carries no bias in PaddleClas; the planted rows use one
+    wl[:2] = 0.0
+    wl[2:, :, :, :NP] = 0.0
+    wl[0, 0, 0, 0], bl[0] = dark_gain, -dark_gain * (10.0 + dark_ref)
+    wl[1, 0, 0, 0], bl[1] = -dark_gain, dark_gain * (10.0 + dark_ref)
+    x = g.conv(x, 1280, (1, 1), act=ACT_HSWISH, w=wl, b=bl)
+    wf = (g.rng.standard_normal((num_classes, 1280)) * 0.002).astype(np.float32)
+    bf = np.zeros((num_classes,), np.float32)
+    wf[:, :2] = 0.0
+    if num_classes >= 2:
+        wf[1, 0], wf[1, 1] = 1.0, -1.0
+        wf[0, 0], wf[0, 1] = -1.0, 1.0
+    g.ctc_head(x, num_classes, wf, bf)   # Linear + softmax over the single "timestep"
+    return g.serialize()
+
+
 def synthetic_dict(vocab: int = 18385) -> list[str]:
     """Character list for synthetic runs: vocab-2 distinct code points (CJK block
     onward), standing in for ppocrv5_dict.txt (one char per line, ocr.rs:386)."""
@@ -406,5 +495,5 @@ _cache: dict = {}
 def get_blob(kind: str, seed: int = 42, vocab: int = 18385) -> bytes:
     key = (kind, seed, vocab)
     if key not in _cache:
-        _cache[key] = build_det(seed) if kind == "det" else build_rec(seed, vocab)
+        _cache[key] = build_det(seed) if kind == "det" else (build_cls(seed) if kind == "cls" else build_rec(seed, vocab))
     return _cache[key]

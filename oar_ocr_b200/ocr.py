@@ -6,6 +6,8 @@ tests read like the reference's own:
   OAROCRBuilder / OAROCR.predict          src/oarocr/ocr.rs:66-417, 518-659
   TextDetectionPredictor(+Builder)        oar-ocr-core/src/predictors/text_detection.rs:23-112
   TextRecognitionPredictor(+Builder)      oar-ocr-core/src/predictors/text_recognition.rs:19-110
+  TextLineOrientationPredictor(+Builder)  oar-ocr-core/src/predictors/text_line_orientation.rs,
+                                          domain/adapters/text_line_orientation_adapter.rs:17-121
   OAROCRResult / TextRegion               src/oarocr/result.rs:33-49, oar-ocr-core/src/domain/text_region.rs:10-27
   Detection / BoundingBox                 oar-ocr-core/src/domain/tasks/text_detection.rs:15-21, processors/geometry.rs:15-70
 
@@ -132,13 +134,19 @@ def character_list(dict_lines: list[str]) -> list[str]:
     return ["\0"] + list(dict_lines) + [" "]
 
 
+def _seed_kind(kind: str):
+    """a classifier's ONNX graph ends in the same MatMul + Softmax pattern as a CTC head: the caller's role decides"""
+    from . import models
+    return models.KIND_CLS if kind == "cls" else None
+
+
 def _resolve_model(source, kind: str) -> bytes:
     """ModelSource (core/config: ModelSource::Path / Memory): OARG or ONNX bytes, a path to an .oarg or .onnx file, or
     'synthetic[:seed]'.  ONNX models are converted to the OARG layer list on load (onnx_io.import_onnx)."""
     if isinstance(source, (bytes, bytearray)):
         if bytes(source[:4]) != b"OARG":
             from . import onnx_io
-            return onnx_io.import_onnx(bytes(source))
+            return onnx_io.import_onnx(bytes(source), _seed_kind(kind))
         return bytes(source)
     if isinstance(source, str) and source.startswith("synthetic"):
         from . import models
@@ -152,7 +160,7 @@ def _resolve_model(source, kind: str) -> bytes:
             data = f.read()
         if path.endswith(".onnx") or data[:4] != b"OARG":
             from . import onnx_io
-            return onnx_io.import_onnx(data)
+            return onnx_io.import_onnx(data, _seed_kind(kind))
         return data
     raise OCRError("InvalidInput", f"unsupported model source {type(source)}")
 
@@ -340,6 +348,106 @@ class TextRecognitionPredictor:
         return TextRecognitionResult(texts, scores, [c.tolist() for c in r["cols"]], [r["T"]] * len(texts), labels)
 
 
+@dataclass
+class Classification:
+    """domain/tasks: Classification{class_id, label, score}"""
+    class_id: int
+    label: str
+    score: float
+
+
+@dataclass
+class TextLineOrientationConfig:
+    """tasks/text_line_orientation.rs:16-32"""
+    score_threshold: float = 0.5
+    topk: int = 2
+
+    def validate(self):
+        if not (0.0 <= self.score_threshold <= 1.0):
+            raise OCRError("ConfigError", f"score_threshold must be in [0,1], got {self.score_threshold}")
+        if self.topk < 1:
+            raise OCRError("ConfigError", f"topk must be at least 1, got {self.topk}")
+
+
+@dataclass
+class TextLineOrientationResult:
+    orientations: list  # list[list[Classification]], one list (top-k, best first) per image
+
+
+def topk_indices(probs: np.ndarray, k: int):
+    """Topk::extract_topk_from_prediction (utils/topk.rs): stable sort by score descending, first k"""
+    if k <= 0:
+        raise OCRError("InvalidInput", "k must be greater than 0", ffi.OAR_E_INVALID)
+    order = sorted(range(len(probs)), key=lambda i: -float(probs[i]))  # sorted() is stable
+    return order[:min(k, len(probs))]
+
+
+class TextLineOrientationPredictorBuilder:
+    def __init__(self):
+        self._config = TextLineOrientationConfig()
+        # the stand-alone predictor's default (predictors/text_line_orientation.rs:59) is (192, 48), read as
+        # (height, width) by PPLCNetModel; the pipeline's adapter default is (80, 160)
+        self._input_shape = (192, 48)
+        self._device = 0
+
+    def score_threshold(self, v):
+        self._config.score_threshold = v
+        return self
+
+    def topk(self, k):
+        self._config.topk = k
+        return self
+
+    def input_shape(self, shape):
+        self._input_shape = (int(shape[0]), int(shape[1]))
+        return self
+
+    def with_config(self, cfg: TextLineOrientationConfig):
+        self._config = cfg
+        return self
+
+    def device_id(self, d):
+        self._device = d
+        return self
+
+    def build(self, model_source) -> "TextLineOrientationPredictor":
+        self._config.validate()
+        ctx = default_context(self._device)
+        return TextLineOrientationPredictor(ffi.Model(ctx, _resolve_model(model_source, "cls")), self._config,
+                                            self._input_shape)
+
+
+class TextLineOrientationPredictor:
+    """predict(): TextLineOrientationAdapter::execute (text_line_orientation_adapter.rs:63-121): one batch, top-k
+    classes per crop with labels "0" / "180"."""
+
+    LABELS = ["0", "180"]  # TextLineOrientationAdapter::labels
+
+    def __init__(self, model: ffi.Model, config: TextLineOrientationConfig, input_shape=(192, 48)):
+        self.model, self.config, self.input_shape = model, config, input_shape
+
+    @staticmethod
+    def builder():
+        return TextLineOrientationPredictorBuilder()
+
+    def predict(self, images) -> TextLineOrientationResult:
+        if images is None or len(images) == 0:
+            raise OCRError("InvalidInput", "No images provided for text line orientation classification",
+                           ffi.OAR_E_INVALID)
+        r = self.model.cls_run(images, self.input_shape)
+        out = []
+        for p in r["probs"]:
+            row = []
+            for i in topk_indices(p, self.config.topk):
+                label = self.LABELS[i] if i < len(self.LABELS) else f"class_{i}"
+                s = float(p[i])
+                if not (0.0 <= s <= 1.0):  # validate_output, tasks/text_line_orientation.rs:97-110
+                    raise OCRError("InvalidInput", f"score {s} outside [0,1]")
+                row.append(Classification(int(i), label, s))
+            out.append(row)
+        return TextLineOrientationResult(out)
+
+
 class OAROCRBuilder:
     """OAROCRBuilder::new(det_model, rec_model, dict_path) (ocr.rs:105-128)"""
 
@@ -354,6 +462,12 @@ class OAROCRBuilder:
         self._region_bs = None
         self._device = 0
         self._return_word_box = False
+        self._line_ori = None
+
+    def with_text_line_orientation_classification(self, model_source):
+        """OAROCRBuilder::with_text_line_orientation_classification (ocr.rs:197-203)"""
+        self._line_ori = model_source
+        return self
 
     def character_dict_content(self, content: str):
         self._dict_content = content
@@ -416,6 +530,10 @@ class OAROCRBuilder:
         # the B200 provider is an accelerator: adapter defaults 8 / 64 (builder_utils.rs:86-125)
         ocr = OAROCR(ctx, det, rec, chars, det_cfg, rec_cfg, self._image_bs or 8, self._region_bs or 64)
         ocr.return_word_box = self._return_word_box
+        if self._line_ori is not None:
+            ocr.cls = ffi.Model(ctx, _resolve_model(self._line_ori, "cls"))
+            if ocr.cls.kind != ffi.KIND_CLS:
+                raise OCRError("ModelLoad", "text line orientation model is not a classifier")
         return ocr
 
 
@@ -427,6 +545,7 @@ class OAROCR:
         self.last_timing = {}
         self._bufs = None
         self.return_word_box = False  # ocr.rs:441: per-character boxes in TextRegion.word_boxes
+        self.cls = None  # optional text-line orientation classifier (ocr.rs:35, 755-792)
 
     def _config(self) -> ffi.PipelineConfig:
         cfg = ffi.pipeline_config(image_batch_size=self.image_batch_size, region_batch_size=self.region_batch_size,
@@ -439,9 +558,9 @@ class OAROCR:
         n = len(hs)
         if self._bufs is None or len(self._bufs.region_off) != n + 1:
             self._bufs = ffi.PipelineBuffers(n, cap_regions=n * self.det_cfg.max_candidates)
-        res = ffi.pipeline_run(self.det, self.rec, image_ptrs, hs, ws, on_device, self._config(), self._bufs)
+        res = ffi.pipeline_run(self.det, self.rec, image_ptrs, hs, ws, on_device, self._config(), self._bufs, self.cls)
         self.last_timing = dict(ms_h2d=res.ms_h2d, ms_det=res.ms_det, ms_post=res.ms_post, ms_crop=res.ms_crop,
-                                ms_rec=res.ms_rec, ms_total=res.ms_total, h2d_bytes=res.h2d_bytes,
+                                ms_rec=res.ms_rec, ms_total=res.ms_total, ms_cls=res.ms_cls, h2d_bytes=res.h2d_bytes,
                                 d2h_bytes=res.d2h_bytes)
         return self._bufs
 
@@ -462,7 +581,9 @@ class OAROCR:
                     if len(cols) and b.seq_len[r] > 0:
                         word_boxes = ctc_word_boxes(bbox, text, cols, int(b.seq_len[r]), float(b.wh_ratio[r]),
                                                     float(b.max_wh_ratio[r]))
-                regions.append(TextRegion(bbox, bbox, bbox, text, float(b.scores[r]), word_boxes=word_boxes,
-                                          detection_index=int(b.det_index[r]), label_indices=lab))
+                angle = float(b.line_angle[r]) if self.cls is not None and b.line_angle[r] >= 0 else None
+                regions.append(TextRegion(bbox, bbox, bbox, text, float(b.scores[r]), orientation_angle=angle,
+                                          word_boxes=word_boxes, detection_index=int(b.det_index[r]),
+                                          label_indices=lab))
             results.append(OAROCRResult(f"image_{i}", i, img, regions))
         return results

@@ -326,8 +326,11 @@ def export_onnx(blob: bytes) -> bytes:
             name_of[op["out"]] = emit_act(y, act, [1.0, 0.0])
         elif t == M.OP_AVGPOOL:
             y = fresh("pool")
-            nodes.append(node("AveragePool", [a], [y], kernel_shape=[p[0], p[1]], strides=[p[2], p[3]],
-                              pads=[0, 0, 0, 0]))
+            if p[0] == 0 and p[1] == 0:  # global pool (classifier trunk)
+                nodes.append(node("GlobalAveragePool", [a], [y]))
+            else:
+                nodes.append(node("AveragePool", [a], [y], kernel_shape=[p[0], p[1]], strides=[p[2], p[3]],
+                                  pads=[0, 0, 0, 0]))
             name_of[op["out"]] = y
         elif t == M.OP_LAYERNORM:
             c = p[0]
@@ -569,13 +572,19 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
                 fail(n, f"grouped convolution (group={group}) other than depthwise")
         elif ot == "GlobalAveragePool":
             # squeeze-excite: GAP -> Conv1x1 -> Relu -> Conv1x1 -> HardSigmoid -> Mul(x, gate) [-> Add(x, .)]
+            # anything else is a plain global pool (the classifier trunk's): AVGPOOL with a (0, 0) window
             seq, cur = [], outs[0]
             for want in ("Conv", "Relu", "Conv", "HardSigmoid", "Mul"):
                 j = sole_consumer(cur, want)
                 if j is None:
-                    fail(n, "GlobalAveragePool outside a squeeze-excite block")
+                    seq = None
+                    break
                 seq.append(j)
                 cur = nodes[j]["outputs"][0]
+            if seq is None:
+                tid[outs[0]] = g.avgpool(tid[ins[0]], (0, 0), (0, 0))
+                i += 1
+                continue
             c1, c2, hs, mul = nodes[seq[0]], nodes[seq[2]], nodes[seq[3]], nodes[seq[4]]
             if ins[0] not in mul["inputs"]:
                 fail(n, "squeeze-excite gate does not multiply the pooled tensor")

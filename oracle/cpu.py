@@ -261,3 +261,40 @@ def ctc_decode(idx, prob, n_chars):
     osc = np.empty(b, np.float32)
     lib().oracle_ctc_decode(i32p(idx), f32p(prob), b, t, n_chars, i32p(oi), i32p(oc), i32p(ol), f32p(osc))
     return [oi[i, :ol[i]].copy() for i in range(b)], osc, [oc[i, :ol[i]].copy() for i in range(b)], t
+
+
+# ---- text-line orientation stage ----
+CLS_INPUT_SHAPE = (80, 160)  # TextLineOrientationAdapter::DEFAULT_INPUT_SHAPE (h, w), text_line_orientation_adapter.rs:48
+
+
+def rotate180(img: np.ndarray) -> np.ndarray:
+    """image::imageops::rotate180 as classify_line_orientations applies it (ocr.rs:785-788)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().oracle_rotate180(u8p(img), img.shape[1], img.shape[0], u8p(out))
+    return out
+
+
+def cls_preprocess(crops, input_shape=CLS_INPUT_SHAPE) -> np.ndarray:
+    """PPLCNetModel::preprocess_refs with resize_short = None (pp_lcnet.rs:139-196): direct Triangle resize to
+    (w, h) = (input_shape[1], input_shape[0]), then NormalizeImage(scale 1/255, ImageNet mean/std, CHW, RGB order)
+    (pp_lcnet.rs:400-412).  Zero-sized images are dropped, as the reference's filter_map does."""
+    ih, iw = input_shape
+    a, b = norm_coeffs(DET_SCALE, DET_MEAN, DET_STD)
+    out = []
+    for c in crops:
+        if c.shape[0] == 0 or c.shape[1] == 0:
+            continue
+        out.append(normalize(resize_triangle(c, iw, ih), a, b, (0, 1, 2), "chw"))
+    return np.stack(out) if out else np.zeros((0, 3, ih, iw), np.float32)
+
+
+def topk(pred, k):
+    """Topk::process for one prediction row (utils/topk.rs): (indexes, scores) of the k best, ties in index order"""
+    pred = np.ascontiguousarray(pred, np.float32).ravel()
+    if k <= 0:
+        raise ValueError("k must be greater than 0")
+    idx = np.empty(max(len(pred), 1), np.int32)
+    sc = np.empty(max(len(pred), 1), np.float32)
+    m = lib().oracle_topk(f32p(pred), len(pred), k, i32p(idx), f32p(sc))
+    return idx[:m].copy(), sc[:m].copy()

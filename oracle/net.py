@@ -110,7 +110,10 @@ class OracleNet:
                 y = _act(F.conv_transpose2d(a, w, b, stride=2), act)
                 t[op["out"]] = y
             elif ty == OP_AVGPOOL:
-                t[op["out"]] = F.avg_pool2d(a, (p[0], p[1]), (p[2], p[3]))
+                if p[0] == 0 and p[1] == 0:  # global average pool (classifier trunk)
+                    t[op["out"]] = a.mean(dim=(2, 3), keepdim=True)
+                else:
+                    t[op["out"]] = F.avg_pool2d(a, (p[0], p[1]), (p[2], p[3]))
             elif ty == OP_LAYERNORM:
                 c = p[0]
                 y = F.layer_norm(a.permute(0, 2, 3, 1), (c,), self._w(op, 0, (c,)), self._w(op, 1, (c,)), f[0])

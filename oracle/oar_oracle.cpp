@@ -1161,4 +1161,28 @@ void oracle_ctc_decode(const int32_t* idx, const float* prob, int B, int T, int 
   }
 }
 
+// ---- text-line orientation stage ----------------------------------------------------------
+// image::imageops::rotate180 (image 0.25, EXT): out(w-1-x, h-1-y) = in(x, y); used by
+// OAROCR::classify_line_orientations (src/oarocr/ocr.rs:755-792) on crops whose top class is 1.
+void oracle_rotate180(const uint8_t* src, int w, int h, uint8_t* dst) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const uint8_t* s = src + ((size_t)y * w + x) * 3;
+      uint8_t* d = dst + ((size_t)(h - 1 - y) * w + (w - 1 - x)) * 3;
+      d[0] = s[0], d[1] = s[1], d[2] = s[2];
+    }
+}
+
+// Topk::extract_topk_from_prediction (oar-ocr-core/src/utils/topk.rs): (index, score) pairs, STABLE sort by score
+// descending with partial_cmp (incomparable = Equal), first k.  Returns the number written.
+int oracle_topk(const float* pred, int n, int k, int32_t* idx, float* score) {
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pred[a] > pred[b]; });
+  int m = std::min(k, n);
+  for (int i = 0; i < m; ++i) idx[i] = order[i], score[i] = pred[order[i]];
+  return m;
+}
+
 }  // extern "C"
+

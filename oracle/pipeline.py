@@ -112,10 +112,24 @@ def rec_forward(net: OracleNet, crops, n_chars, return_probs=False):
     return r
 
 
+def cls_forward(net: OracleNet, crops, topk=1, input_shape=cpu.CLS_INPUT_SHAPE):
+    """TextLineOrientationAdapter::execute -> PPLCNetModel::forward_refs (text_line_orientation_adapter.rs:63-121,
+    pp_lcnet.rs:139-196, 255-300): preprocess -> net -> Topk.  Returns per crop (class_ids, scores) of the top-k and
+    the full probability rows."""
+    x = cpu.cls_preprocess(crops, input_shape)
+    if len(x) == 0:
+        return [], np.zeros((0, 0), np.float32)
+    probs = net.forward(x)
+    probs = probs.reshape(probs.shape[0], -1)
+    return [cpu.topk(p, topk) for p in probs], probs
+
+
 def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch_size=8, region_batch_size=64,
-            rec_score_thresh=0.0, det_kwargs=None, chars=None):
+            rec_score_thresh=0.0, det_kwargs=None, chars=None, cls_net: OracleNet | None = None):
     """OAROCR::predict.  Returns per image a list of dicts
-    {box [4,2], det_index, labels (int array), score} in detection-index (reading) order."""
+    {box [4,2], det_index, labels (int array), score} in detection-index (reading) order.  With `cls_net` the crops of
+    each image go through classify_line_orientations (ocr.rs:615, 755-792) before they are pooled: `angle` = 0 / 180
+    and crops of class 1 are rotated by 180 degrees."""
     det_kwargs = det_kwargs or {}
     n = len(images)
     all_boxes = [None] * n
@@ -139,20 +153,32 @@ def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch
                 keep = score >= rec_score_thresh
                 labels = r["labels"][k] if keep else r["labels"][k][:0]
                 res = dict(box=all_boxes[img_idx][det_idx], det_index=det_idx, labels=labels, score=score,
-                           cols=r["cols"][k], T=r["T"])
+                           cols=r["cols"][k], T=r["T"], angle=angles.get((img_idx, det_idx)))
                 if chars is not None:  # return_word_box (ocr.rs:860-868); chars = index -> character
                     cols = r["cols"][k] if keep else r["cols"][k][:0]
                     text = "".join(chars[i] for i in labels if 0 < i < len(chars))
                     res["word_boxes"] = ctc_word_boxes(res["box"], text, cols, r["T"], ratio, chunk_max)
                 results[img_idx][det_idx] = res
 
+    angles = {}
     for i, img in enumerate(images):
+        crops = []
         for k, box in enumerate(all_boxes[i]):
             crop = cpu.rotate_crop(img, box)
             if crop is None:
                 continue
-            ratio = np.float32(crop.shape[1]) / np.float32(max(crop.shape[0], 1))
-            pool.append((i, k, crop, float(ratio)))
+            ratio = np.float32(crop.shape[1]) / np.float32(max(crop.shape[0], 1))  # before any rotation, ocr.rs:735
+            crops.append([i, k, crop, float(ratio)])
+        if cls_net is not None and crops:
+            tops, _ = cls_forward(cls_net, [c[2] for c in crops], topk=1)
+            for c, (ids, _sc) in zip(crops, tops):
+                if len(ids) == 0:
+                    continue
+                angles[(c[0], c[1])] = float(ids[0]) * 180.0
+                if ids[0] == 1:
+                    c[2] = cpu.rotate180(c[2])
+        for c in crops:
+            pool.append(tuple(c))
             if len(pool) >= MAX_POOLED_CROPS:
                 recognize_global(pool)
                 pool = []

@@ -1,6 +1,7 @@
 // Exercises include/oar_ocr.hpp (the C++ mirror of the Rust API) against liboar_b200.so.
 // Without a GPU: checks the error behaviour the reference pins (ocr.rs:1168-1195, no CPU fallback).
-// With a GPU (argv[1] = det blob, argv[2] = rec blob): runs predict() on a blank page and one synthetic stripe.
+// With a GPU (argv[1] = det blob, argv[2] = rec blob, optional argv[3] = line-orientation classifier blob): runs
+// predict() on a blank page and one synthetic stripe, with and without the classifier.
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -51,6 +52,19 @@ int main(int argc, char** argv) {
     expect(oar::ctc_word_boxes(line, U"", {1}, 10, 5.0f, 5.0f).empty(), "ctc_word_boxes empty text");
   }
 
+  // Topk (utils/topk.rs:294-344): descending, stable, k clipped to the class count
+  {
+    const float p[3] = {0.1f, 0.8f, 0.1f};
+    auto t = oar::topk_indices(p, 3, 2);
+    expect(t.size() == 2 && t[0] == 1 && t[1] == 0, "topk order");
+    expect(oar::topk_indices(p, 2, 5).size() == 2, "topk k larger than classes");
+    try {
+      oar::topk_indices(p, 3, 0);
+      expect(false, "topk k = 0 rejected");
+    } catch (const oar::OCRError&) {
+    }
+  }
+
   bool have_gpu = true;
   try {
     oar::Context probe(0);
@@ -88,6 +102,23 @@ int main(int argc, char** argv) {
     }
     auto dres = oar::TextDetectionPredictor(det).predict({oar::RgbImage{page.data(), 320, 320}});
     expect(dres.detections.size() == 1 && dres.detections[0].size() == 1, "detector predictor");
+    if (res.size() == 1 && res[0].text_regions.size() == 1)
+      expect(!res[0].text_regions[0].has_orientation_angle, "no classifier: orientation_angle is None");
+    if (argc >= 4) {  // with_text_line_orientation_classification (ocr.rs:197-203)
+      auto cb = slurp(argv[3]);
+      oar::Model cls(ctx, cb.data(), cb.size());
+      oar::OAROCR ocr2 = oar::OAROCRBuilder(det, rec, 18385).with_text_line_orientation_classification(cls).build();
+      auto res2 = ocr2.predict({oar::RgbImage{page.data(), 320, 320}});
+      expect(res2.size() == 1 && res2[0].text_regions.size() == 1 && res2[0].text_regions[0].has_orientation_angle &&
+                 (res2[0].text_regions[0].orientation_angle == 0.0f || res2[0].text_regions[0].orientation_angle == 180.0f),
+             "classifier attached: angle 0 or 180");
+      std::vector<uint8_t> line(48 * 200 * 3, 90);
+      auto ori = oar::TextLineOrientationPredictor(cls).predict({oar::RgbImage{line.data(), 48, 200}});
+      expect(ori.orientations.size() == 1 && ori.orientations[0].size() == 2 &&
+                 ori.orientations[0][0].score >= ori.orientations[0][1].score &&
+                 (ori.orientations[0][0].label == "0" || ori.orientations[0][0].label == "180"),
+             "orientation predictor: top-2, best first");
+    }
     std::printf("gpu path ok: %zu regions\n", res[0].text_regions.size());
   }
   std::printf(failures ? "FAILED %d\n" : "ok\n", failures);

@@ -28,9 +28,11 @@ def test_cpp_mirror_cpu(built_lib, tmp_path):
 
 @pytest.mark.gpu
 def test_cpp_mirror_gpu(built_lib, tmp_path, det_blob, rec_blob):
-    d, r = tmp_path / "det.oarg", tmp_path / "rec.oarg"
+    from oar_ocr_b200 import models
+    d, r, c = tmp_path / "det.oarg", tmp_path / "rec.oarg", tmp_path / "cls.oarg"
     d.write_bytes(det_blob)
     r.write_bytes(rec_blob)
-    out = subprocess.run([_build(built_lib, tmp_path), str(d), str(r)], capture_output=True, text=True)
+    c.write_bytes(models.get_blob("cls"))
+    out = subprocess.run([_build(built_lib, tmp_path), str(d), str(r), str(c)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "gpu path ok" in out.stdout

@@ -88,11 +88,12 @@ def test_wire_format_roundtrip():
     assert ins == ["x"] and outs == ["y"] and nodes[0]["inputs"] == ["x", "w"]
 
 
-@pytest.mark.parametrize("kind", ["det", "rec"])
+@pytest.mark.parametrize("kind", ["det", "rec", "cls"])
 def test_export_matches_oracle_and_import_roundtrips(kind):
     blob = models.get_blob(kind, vocab=97) if kind == "rec" else models.get_blob(kind)
     rng = np.random.default_rng(3)
-    x = rng.standard_normal((2, 3, 64, 96) if kind == "det" else (2, 3, 48, 64)).astype(np.float32)
+    shape = {"det": (2, 3, 64, 96), "rec": (2, 3, 48, 64), "cls": (2, 3, 80, 160)}[kind]
+    x = rng.standard_normal(shape).astype(np.float32)
     want = OracleNet(blob).forward(x)
     data = onnx_io.export_onnx(blob)
     # 1. the exported ONNX, evaluated operator by operator, is the same network
@@ -100,7 +101,8 @@ def test_export_matches_oracle_and_import_roundtrips(kind):
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= 2e-5
     # 2. importing it back gives a graph with the same ops, parameters and weights: identical oracle output
-    back = onnx_io.import_onnx(data)
+    # (a classifier ends in the same MatMul + Softmax pattern as a CTC head: the caller's role names the kind)
+    back = onnx_io.import_onnx(data, models.KIND_CLS if kind == "cls" else None)
     k0, _, ops0, w0 = onnx_io._parse_oarg(blob)
     k1, _, ops1, w1 = onnx_io._parse_oarg(back)
     assert k0 == k1 and sorted(o["type"] for o in ops0) == sorted(o["type"] for o in ops1)
