@@ -1003,7 +1003,11 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
         p.kh = p.kw = p.sh = p.sw = 1;
         p.N = V, p.K = c, p.M = (int)rows, p.out_ld = V, p.post_scale = 1.0f, p.cout = V;
-        launch_gemm(m, (int)oi * 2, p, "ctc_head_gemm_simt", "ctc_head_gemm_tc");
+        // a classifier head (a handful of classes on one row per image) is far below one tensor-core tile
+        if (V < 16)
+          launch_conv_simt(ctx, p, "cls_head_gemm_simt");
+        else
+          launch_gemm(m, (int)oi * 2, p, "ctc_head_gemm_simt", "ctc_head_gemm_tc");
         CtcOut local;
         CtcOut* co = ctc ? ctc : &local;
         co->idx = ctx->arena.get<int32_t>(rows);
