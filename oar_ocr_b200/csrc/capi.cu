@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <exception>
+#include <map>
 
 #include <cstdlib>
 
@@ -25,7 +26,18 @@
 namespace oar {
 
 thread_local char g_err[1024] = {0};
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
+
+void ensure_max_dynamic_smem(const void* kernel, int device, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(kernel, device);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return;
+  OAR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -539,7 +551,7 @@ void oar_pipeline_config_default(oar_pipeline_config* cfg) {
 
 const char* oar_last_error(void) { return oar::g_err; }
 int32_t oar_version(void) { return 100; }
-int64_t oar_launch_count(void) { return oar::g_launches; }
+int64_t oar_launch_count(void) { return oar::g_launches.load(); }
 
 int32_t oar_ctx_create(int32_t device_id, oar_ctx** out) {
   if (!out) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -17,7 +18,9 @@ namespace oar {
 
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[1024];
-extern long long g_launches;
+extern std::atomic<long long> g_launches;  // contexts on different GPUs launch concurrently
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); safe to call from concurrent contexts
+void ensure_max_dynamic_smem(const void* kernel, int device, int bytes);
 
 struct OarError {
   int code;

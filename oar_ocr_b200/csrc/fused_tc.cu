@@ -697,14 +697,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)b_stage;
   // always above half the SM's shared memory: one CTA per SM owns all 512 TMEM columns
   const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
-  {
-    static std::map<std::pair<const void*, int>, bool> attr_done;
-    auto ka = std::make_pair((const void*)kern, m->ctx->device);
-    if (!attr_done.count(ka)) {
-      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_MAX));
-      attr_done[ka] = true;
-    }
-  }
+  ensure_max_dynamic_smem((const void*)kern, m->ctx->device, (int)FB_SMEM_MAX);
   static const bool dbg_tiles = getenv("OAR_DBG_TILES") != nullptr;
   if (dbg_tiles)
     fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d smem %zu\n", f.k,
@@ -759,13 +752,7 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)w.BN * 128u;
   const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
   FbKern kern = lcblock_tc<0, 1, 1>;
-  {
-    static std::map<int, bool> attr_done;
-    if (!attr_done.count(m->ctx->device)) {
-      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_MAX));
-      attr_done[m->ctx->device] = true;
-    }
-  }
+  ensure_max_dynamic_smem((const void*)kern, m->ctx->device, (int)FB_SMEM_MAX);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * (double)p.M * p.K + 24.0 * p.M * w.n_tiles);
   kern<<<grid, FB_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);

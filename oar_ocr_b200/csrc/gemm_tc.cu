@@ -846,14 +846,14 @@ int tc_n_tiles(const oar_model* m, int key) {
 
 // ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda)
 EncodeTiledFn tmap_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+  // function-local static: initialised once, thread-safe (contexts on different GPUs launch concurrently)
+  static const EncodeTiledFn fn = [] {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr)
       OAR_FAIL(OAR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    fn = (EncodeTiledFn)ptr;
-  }
+    return (EncodeTiledFn)ptr;
+  }();
   return fn;
 }
 
@@ -908,14 +908,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
     P.tma_out = make_out_map(&tm_rt, p.out + p.out_c_off, p.N, p.out_ld, p.Wo, (long long)p.B * p.Ho, 3) ? 1 : 0;
     P.ctrl_off = (uint32_t)smem_rt;
     smem_rt += 64;
-    {
-      static std::map<std::pair<const void*, int>, bool> attr_done_rt;
-      auto key_attr = std::make_pair((const void*)krt, m->ctx->device);
-      if (!attr_done_rt.count(key_attr)) {
-        OAR_CUDA(cudaFuncSetAttribute(krt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done_rt[key_attr] = true;
-      }
-    }
+    ensure_max_dynamic_smem((const void*)krt, m->ctx->device, 200 * 1024);
     const int segs = (p.Wo + TC_BM - 1) / TC_BM;
     dim3 grid_rt((unsigned)(p.B * p.Ho * segs), w.n_tiles);
     Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + 4.0 * (double)p.M * p.N);
@@ -956,14 +949,7 @@ bool tc_gemm(oar_model* m, int key, const ConvParams& p, const char* name) {
     P.tma_out = make_out_map(&tm, p.out + p.out_c_off, p.N, p.out_ld, p.M, 1, 2) ? 1 : 0;
   P.ctrl_off = (uint32_t)smem;
   smem += 64;
-  {
-    static std::map<std::pair<const void*, int>, bool> attr_done;  // the attribute is per (kernel, device)
-    auto key_attr = std::make_pair((const void*)kern, m->ctx->device);
-    if (!attr_done.count(key_attr)) {
-      OAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done[key_attr] = true;
-    }
-  }
+  ensure_max_dynamic_smem((const void*)kern, m->ctx->device, 200 * 1024);
   dim3 grid(cdiv(p.M, TC_BM), w.n_tiles);
   double out_bytes = p.mode == 2 ? 24.0 * p.M * w.n_tiles : 4.0 * (double)p.M * p.N;
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.K / (p.kh * p.kw)) + out_bytes);
