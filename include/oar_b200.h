@@ -216,6 +216,44 @@ int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, con
                              const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
                              const oar_pipeline_config* cfg, oar_ocr_result* out);
 
+/* ---- layout detection, host half ----------------------
+ * LayoutDetectionAdapter::postprocess_pp_doclayout
+ * (oar-ocr-core/src/domain/adapters/layout_detection_adapter.rs:631-846) with its helpers convert_bbox_coords
+ * (:848-878), paddlex_layout_nms (:884-951), filter_large_image_boxes (:953-992), apply_paddlex_merge_modes /
+ * check_containment / is_contained (:994-1106), and unclip_boxes
+ * (oar-ocr-core/src/processors/layout_postprocess.rs:636-681).  Host code in the reference and here: it works on the
+ * few hundred rows the detector returns, needs no context and no device.
+ * Configuration = LayoutDetectionConfig (oar-ocr-core/src/domain/tasks/layout_detection.rs:45-100) with the label-keyed
+ * maps resolved to class ids by the caller (the adapter does the same through LayoutModelConfig.class_labels). */
+#define OAR_MERGE_UNSET (-1)
+#define OAR_MERGE_LARGE 0 /* MergeBboxMode::Large */
+#define OAR_MERGE_SMALL 1
+#define OAR_MERGE_UNION 2
+#define OAR_UNCLIP_NONE 0      /* layout_unclip_ratio = None */
+#define OAR_UNCLIP_RATIO 1     /* UnclipRatio::Uniform(r) -> (r, r); Separate(w, h) */
+#define OAR_UNCLIP_PER_CLASS 2 /* UnclipRatio::PerClass */
+typedef struct {
+  float score_threshold;            /* 0.5 */
+  int32_t max_elements;             /* 100 */
+  int32_t layout_nms;               /* 1 */
+  int32_t num_classes;              /* LayoutModelConfig.num_classes (23 for PP-DocLayout-L) */
+  const float* class_thresholds;    /* [num_classes], NaN = not configured; NULL = None */
+  const int32_t* class_merge_modes; /* [num_classes] OAR_MERGE_*; NULL = None */
+  int32_t image_class_id;           /* id of the label "image", -1 if the model has none */
+  int32_t formula_class_id;         /* id of the label "formula", -1 if none */
+  int32_t unclip_mode;              /* OAR_UNCLIP_* */
+  float unclip_w, unclip_h;         /* OAR_UNCLIP_RATIO */
+  const float* class_unclip;        /* OAR_UNCLIP_PER_CLASS: [num_classes][2] (w, h), NaN = (1, 1) */
+} oar_layout_config;
+void oar_layout_config_default(oar_layout_config* cfg); /* LayoutDetectionConfig::default + PP-DocLayout-L ids */
+/* pred: host f32 [batch][num_boxes][feature_dim] rows [class_id, score, x1, y1, x2, y2, (order keys)] exactly as the
+ * adapter reads them (:689-690; 7 columns = one reading-order key, 8 = (column, row)); src_w/src_h: ImageScaleInfo
+ * source dims per image.  Outputs per image: up to max_elements rows -- boxes [batch][max_elements][4] as
+ * (x1, y1, x2, y2) = the arguments of BoundingBox::from_coords, class ids, scores -- and counts[batch]. */
+int32_t oar_layout_postprocess(const float* pred, int32_t batch, int32_t num_boxes, int32_t feature_dim,
+                               const float* src_w, const float* src_h, const oar_layout_config* cfg, float* boxes,
+                               int32_t* classes, float* scores, int32_t* counts);
+
 /* device memory helpers for callers that keep inputs resident (bench `value` leg) */
 int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out);
 int32_t oar_device_free(oar_ctx* ctx, void* p);

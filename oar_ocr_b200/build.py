@@ -22,6 +22,7 @@ SOURCES = {
     "fused_tc.cu": [],
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
+    "layout.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only f32 restatement: no FMA contraction
 }
 
 

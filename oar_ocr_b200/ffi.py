@@ -23,7 +23,8 @@ SYMBOLS = [
     "oar_ctx_create", "oar_ctx_destroy", "oar_ctx_synchronize", "oar_model_load_blob", "oar_model_destroy",
     "oar_model_kind", "oar_model_set_engine", "oar_infer_f32", "oar_normalize_chw", "oar_db_postprocess",
     "oar_det_run", "oar_sort_quad_boxes", "oar_rotate_crop", "oar_crnn_preprocess", "oar_ctc_decode", "oar_rec_run",
-    "oar_pipeline_run", "oar_cls_run", "oar_rotate180", "oar_pipeline_run_cls", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
+    "oar_pipeline_run", "oar_cls_run", "oar_rotate180", "oar_pipeline_run_cls", "oar_layout_config_default",
+    "oar_layout_postprocess", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
     "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush",
 ]
 
@@ -68,6 +69,19 @@ class OcrResult(C.Structure):
                 ("seq_len", C.POINTER(C.c_int32)), ("wh_ratio", C.POINTER(C.c_float)),
                 ("max_wh_ratio", C.POINTER(C.c_float)), ("line_angle", C.POINTER(C.c_float)),
                 ("ms_cls", C.c_float)]
+
+
+class LayoutConfig(C.Structure):
+    """oar_layout_config = LayoutDetectionConfig with its label-keyed maps resolved to class ids"""
+    _fields_ = [("score_threshold", C.c_float), ("max_elements", C.c_int32), ("layout_nms", C.c_int32),
+                ("num_classes", C.c_int32), ("class_thresholds", C.POINTER(C.c_float)),
+                ("class_merge_modes", C.POINTER(C.c_int32)), ("image_class_id", C.c_int32),
+                ("formula_class_id", C.c_int32), ("unclip_mode", C.c_int32), ("unclip_w", C.c_float),
+                ("unclip_h", C.c_float), ("class_unclip", C.POINTER(C.c_float))]
+
+
+MERGE_UNSET, MERGE_LARGE, MERGE_SMALL, MERGE_UNION = -1, 0, 1, 2
+UNCLIP_NONE, UNCLIP_RATIO, UNCLIP_PER_CLASS = 0, 1, 2
 
 
 class KernelRecord(C.Structure):
@@ -122,6 +136,10 @@ def lib():
         L.oar_rotate180.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.oar_pipeline_run_cls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
+        L.oar_layout_config_default.restype = None
+        L.oar_layout_config_default.argtypes = [C.POINTER(LayoutConfig)]
+        L.oar_layout_postprocess.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.POINTER(LayoutConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oar_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.oar_device_free.argtypes = [C.c_void_p, C.c_void_p]
         L.oar_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -332,6 +350,59 @@ class Context:
 
     def memcpy_h2d(self, dst: int, src: np.ndarray):
         check(lib().oar_memcpy_h2d(self.handle, C.c_void_p(dst), _ptr(src), src.nbytes))
+
+
+def layout_postprocess(pred: np.ndarray, src_wh, num_classes: int, score_threshold=0.5, max_elements=100,
+                       layout_nms=True, class_thresholds=None, class_merge_modes=None, image_class_id=-1,
+                       formula_class_id=-1, unclip=None):
+    """oar_layout_postprocess (host only, no device).  pred [B,N,F]; src_wh: (w, h) per image; class_thresholds /
+    class_merge_modes: {class_id: value}; unclip: None | (w, h) | {class_id: (w, h)}.
+    Returns per image (boxes [n,4] x1 y1 x2 y2, classes [n], scores [n])."""
+    pred = np.ascontiguousarray(pred, np.float32)
+    if pred.ndim != 3:
+        raise OCRError("InvalidInput", "predictions must be [batch, boxes, features]", OAR_E_INVALID)
+    b, n, f = pred.shape
+    cfg = LayoutConfig()
+    lib().oar_layout_config_default(C.byref(cfg))
+    cfg.score_threshold, cfg.max_elements, cfg.layout_nms, cfg.num_classes = score_threshold, max_elements, \
+        1 if layout_nms else 0, num_classes
+    cfg.image_class_id, cfg.formula_class_id = image_class_id, formula_class_id
+    keep = []  # arrays the struct points into
+    if class_thresholds is not None:
+        a = np.full(num_classes, np.nan, np.float32)
+        for k, v in class_thresholds.items():
+            if 0 <= k < num_classes:
+                a[k] = v
+        keep.append(a)
+        cfg.class_thresholds = a.ctypes.data_as(C.POINTER(C.c_float))
+    if class_merge_modes is not None:
+        a = np.full(num_classes, MERGE_UNSET, np.int32)
+        for k, v in class_merge_modes.items():
+            if 0 <= k < num_classes:
+                a[k] = v
+        keep.append(a)
+        cfg.class_merge_modes = a.ctypes.data_as(C.POINTER(C.c_int32))
+    if isinstance(unclip, dict):
+        a = np.full((num_classes, 2), np.nan, np.float32)
+        for k, v in unclip.items():
+            if 0 <= k < num_classes:
+                a[k] = v
+        keep.append(a)
+        cfg.unclip_mode = UNCLIP_PER_CLASS
+        cfg.class_unclip = a.ctypes.data_as(C.POINTER(C.c_float))
+    elif unclip is not None:
+        cfg.unclip_mode, cfg.unclip_w, cfg.unclip_h = UNCLIP_RATIO, float(unclip[0]), float(unclip[1])
+    sw = np.array([w for w, _ in src_wh], np.float32)
+    sh = np.array([h for _, h in src_wh], np.float32)
+    me = max(int(max_elements), 1)
+    boxes = np.zeros((max(b, 1), me, 4), np.float32)
+    classes = np.zeros((max(b, 1), me), np.int32)
+    scores = np.zeros((max(b, 1), me), np.float32)
+    counts = np.zeros(max(b, 1), np.int32)
+    check(lib().oar_layout_postprocess(_ptr(pred), b, n, f, _ptr(sw), _ptr(sh), C.byref(cfg), _ptr(boxes),
+                                       _ptr(classes), _ptr(scores), _ptr(counts)))
+    return [(boxes[i, :counts[i]].copy(), classes[i, :counts[i]].copy(), scores[i, :counts[i]].copy())
+            for i in range(b)]
 
 
 def sort_quad_boxes(boxes: np.ndarray):

@@ -448,6 +448,73 @@ class TextLineOrientationPredictor:
         return TextLineOrientationResult(out)
 
 
+# ---- layout detection, host half: LayoutDetectionAdapter::postprocess_pp_doclayout ----
+# class labels of LayoutModelConfig::pp_doclayout_l (layout_detection_adapter.rs:314-348)
+PP_DOCLAYOUT_L_LABELS = ["paragraph_title", "image", "text", "number", "abstract", "content", "figure_title",
+                         "formula", "table", "table_title", "reference", "doc_title", "footnote", "header",
+                         "algorithm", "footer", "seal", "chart_title", "chart", "formula_number", "header_image",
+                         "footer_image", "aside_text"]
+
+
+@dataclass
+class LayoutDetectionConfig:
+    """tasks/layout_detection.rs:45-100.  class_thresholds / class_merge_modes are keyed by label ("large" | "small" |
+    "union"); layout_unclip_ratio: None | r | (w, h) | {class_id: (w, h)} (UnclipRatio::Uniform / Separate / PerClass)"""
+    score_threshold: float = 0.5
+    max_elements: int = 100
+    class_thresholds: dict | None = None
+    class_merge_modes: dict | None = None
+    layout_nms: bool = True
+    nms_threshold: float = 0.5
+    layout_unclip_ratio: object = None
+
+    def validate(self):
+        if not (0.0 <= self.score_threshold <= 1.0):
+            raise OCRError("ConfigError", f"score_threshold must be in [0,1], got {self.score_threshold}")
+        if self.max_elements < 1:
+            raise OCRError("ConfigError", f"max_elements must be at least 1, got {self.max_elements}")
+
+    @staticmethod
+    def with_pp_structurev3_thresholds() -> "LayoutDetectionConfig":
+        """tasks/layout_detection.rs:102-135"""
+        return LayoutDetectionConfig(class_thresholds={"paragraph_title": 0.3, "formula": 0.3, "text": 0.4,
+                                                       "seal": 0.45})
+
+
+@dataclass
+class LayoutDetectionElement:
+    bbox: BoundingBox
+    element_type: str
+    score: float
+
+
+def postprocess_pp_doclayout(predictions: np.ndarray, img_shapes, config: LayoutDetectionConfig | None = None,
+                             class_labels=None) -> list:
+    """LayoutDetectionAdapter::postprocess_pp_doclayout (layout_detection_adapter.rs:631-846): predictions
+    [B, N, 6|7|8] rows [class_id, score, x1, y1, x2, y2, (order keys)], img_shapes = (src_w, src_h) per image.
+    The label-keyed maps are resolved to class ids here, as the adapter does; the arithmetic runs behind
+    oar_layout_postprocess.  Returns one list of LayoutDetectionElement per image."""
+    config = config or LayoutDetectionConfig()
+    config.validate()
+    labels = list(class_labels) if class_labels is not None else PP_DOCLAYOUT_L_LABELS
+    ids = {lab: i for i, lab in enumerate(labels)}
+    modes = {"large": ffi.MERGE_LARGE, "small": ffi.MERGE_SMALL, "union": ffi.MERGE_UNION}
+    thr = None if config.class_thresholds is None else \
+        {ids[k]: v for k, v in config.class_thresholds.items() if k in ids}
+    mm = None if config.class_merge_modes is None else \
+        {ids[k]: modes[str(v).lower()] for k, v in config.class_merge_modes.items() if k in ids}
+    u = config.layout_unclip_ratio
+    if isinstance(u, (int, float)):
+        u = (float(u), float(u))
+    pred = np.asarray(predictions, np.float32)
+    if pred.ndim == 4:  # the model's [B, N, 1, F] layout
+        pred = pred.reshape(pred.shape[0], pred.shape[1], pred.shape[3])
+    out = ffi.layout_postprocess(pred, img_shapes, len(labels), config.score_threshold, config.max_elements,
+                                 config.layout_nms, thr, mm, ids.get("image", -1), ids.get("formula", -1), u)
+    return [[LayoutDetectionElement(BoundingBox.from_coords(*map(float, b)), labels[c] if c < len(labels) else "unknown",
+                                    float(s)) for b, c, s in zip(bs, cs, ss)] for bs, cs, ss in out]
+
+
 class OAROCRBuilder:
     """OAROCRBuilder::new(det_model, rec_model, dict_path) (ocr.rs:105-128)"""
 

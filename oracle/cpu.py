@@ -298,3 +298,55 @@ def topk(pred, k):
     sc = np.empty(max(len(pred), 1), np.float32)
     m = lib().oracle_topk(f32p(pred), len(pred), k, i32p(idx), f32p(sc))
     return idx[:m].copy(), sc[:m].copy()
+
+
+# ---- layout detection post-process (host half) ----
+def layout_nms(boxes, classes, scores, compacting=False):
+    """paddlex_layout_nms (layout_detection_adapter.rs:884-933), or with compacting=True the reference's own test
+    oracle compacting_nms_reference (:1667-1697).  boxes [n,4] = from_coords arguments.  Returns kept indices."""
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
+    classes = np.ascontiguousarray(classes, np.int32)
+    scores = np.ascontiguousarray(scores, np.float32)
+    keep = np.empty(max(len(boxes), 1), np.int32)
+    fn = lib().oracle_layout_nms_compacting if compacting else lib().oracle_layout_nms
+    m = fn(f32p(boxes), i32p(classes), f32p(scores), len(boxes), i32p(keep))
+    return keep[:m].copy()
+
+
+def layout_postprocess(pred, src_w, src_h, num_classes, score_threshold=0.5, max_elements=100, layout_nms=True,
+                       class_thresholds=None, class_merge_modes=None, image_class_id=-1, formula_class_id=-1,
+                       unclip=None):
+    """postprocess_pp_doclayout for one image (layout_detection_adapter.rs:674-840).  pred [N,F]; dict-valued
+    options are keyed by class id; unclip: None | (w, h) | {class_id: (w, h)}.  Returns (boxes [n,4], classes, scores)."""
+    pred = np.ascontiguousarray(pred, np.float32)
+    n, f = pred.shape
+    thr = mm = cu = None
+    if class_thresholds is not None:
+        thr = np.full(num_classes, np.nan, np.float32)
+        for k, v in class_thresholds.items():
+            if 0 <= k < num_classes:
+                thr[k] = v
+    if class_merge_modes is not None:
+        mm = np.full(num_classes, -1, np.int32)
+        for k, v in class_merge_modes.items():
+            if 0 <= k < num_classes:
+                mm[k] = v
+    mode, uw, uh = 0, 1.0, 1.0
+    if isinstance(unclip, dict):
+        mode = 2
+        cu = np.full((num_classes, 2), np.nan, np.float32)
+        for k, v in unclip.items():
+            if 0 <= k < num_classes:
+                cu[k] = v
+    elif unclip is not None:
+        mode, uw, uh = 1, float(unclip[0]), float(unclip[1])
+    me = max(int(max_elements), 1)
+    ob = np.zeros((me, 4), np.float32)
+    oc = np.zeros(me, np.int32)
+    os_ = np.zeros(me, np.float32)
+    m = lib().oracle_layout_postprocess(
+        f32p(pred), n, f, C.c_float(src_w), C.c_float(src_h), C.c_float(score_threshold), me, 1 if layout_nms else 0,
+        num_classes, f32p(thr) if thr is not None else None, i32p(mm) if mm is not None else None, image_class_id,
+        formula_class_id, mode, C.c_float(uw), C.c_float(uh), f32p(cu) if cu is not None else None, f32p(ob), i32p(oc),
+        f32p(os_))
+    return ob[:m].copy(), oc[:m].copy(), os_[:m].copy()

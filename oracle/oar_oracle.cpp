@@ -1186,3 +1186,247 @@ int oracle_topk(const float* pred, int n, int k, int32_t* idx, float* score) {
 
 }  // extern "C"
 
+// ---- layout detection post-process (host half) ----------------------------------------------
+// LayoutDetectionAdapter::postprocess_pp_doclayout and its helpers
+// (oar-ocr-core/src/domain/adapters/layout_detection_adapter.rs:631-1116) + unclip_boxes
+// (oar-ocr-core/src/processors/layout_postprocess.rs:636-681), restated step by step in f32.
+// A box is BoundingBox::from_coords(x1, y1, x2, y2); x_min()/x_max() are the compare-and-keep loops of
+// geometry.rs:179-209, 569-599 over its four corners (so a NaN coordinate falls back to the other corner's).
+namespace {
+struct LBox {
+  float x1, y1, x2, y2;
+  float xmin() const { float m = INFINITY; if (x1 < m) m = x1; if (x2 < m) m = x2; return m; }
+  float xmax() const { float m = -INFINITY; if (x1 > m) m = x1; if (x2 > m) m = x2; return m; }
+  float ymin() const { float m = INFINITY; if (y1 < m) m = y1; if (y2 < m) m = y2; return m; }
+  float ymax() const { float m = -INFINITY; if (y1 > m) m = y1; if (y2 > m) m = y2; return m; }
+};
+inline float rmin(float a, float b) { return std::isnan(a) ? b : (std::isnan(b) ? a : (a < b ? a : b)); }  // f32::min
+inline float rmax(float a, float b) { return std::isnan(a) ? b : (std::isnan(b) ? a : (a > b ? a : b)); }  // f32::max
+inline float rclamp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }  // f32::clamp (NaN stays)
+
+// paddlex_iou, layout_detection_adapter.rs:935-951 (the "+ 1" pixel convention of PaddleX)
+float layout_iou(const LBox& a, const LBox& b) {
+  float x1 = a.xmin(), y1 = a.ymin(), x2 = a.xmax(), y2 = a.ymax();
+  float x1p = b.xmin(), y1p = b.ymin(), x2p = b.xmax(), y2p = b.ymax();
+  float iw = rmax(rmin(x2, x2p) - rmax(x1, x1p) + 1.0f, 0.0f);
+  float ih = rmax(rmin(y2, y2p) - rmax(y1, y1p) + 1.0f, 0.0f);
+  float inter = iw * ih;
+  float area1 = (x2 - x1 + 1.0f) * (y2 - y1 + 1.0f);
+  float area2 = (x2p - x1p + 1.0f) * (y2p - y1p + 1.0f);
+  float uni = area1 + area2 - inter;
+  return uni > 0.0f ? inter / uni : 0.0f;
+}
+
+// stable sort by score descending with partial_cmp (incomparable = Equal), :889-894
+std::vector<int> score_order(const float* scores, int n) {
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return scores[a] > scores[b]; });
+  return idx;
+}
+
+// paddlex_layout_nms, :884-933: same class suppresses at IoU >= 0.6, other classes at >= 0.98, NaN IoU suppressed
+std::vector<int> layout_nms(const std::vector<LBox>& boxes, const std::vector<int>& classes,
+                            const std::vector<float>& scores) {
+  std::vector<int> indices = score_order(scores.data(), (int)boxes.size());
+  std::vector<char> suppressed(indices.size(), 0);
+  std::vector<int> selected;
+  for (size_t pos = 0; pos < indices.size(); ++pos) {
+    if (suppressed[pos]) continue;
+    int cur = indices[pos];
+    selected.push_back(cur);
+    for (size_t np = pos + 1; np < indices.size(); ++np) {
+      if (suppressed[np]) continue;
+      int idx = indices[np];
+      float thr = classes[idx] == classes[cur] ? 0.6f : 0.98f;
+      float iou = layout_iou(boxes[cur], boxes[idx]);
+      if (iou >= thr || std::isnan(iou)) suppressed[np] = 1;
+    }
+  }
+  return selected;
+}
+
+// is_contained, :1085-1106: intersection / area(inner) >= 0.9
+bool layout_is_contained(const LBox& in, const LBox& out) {
+  float x1 = in.xmin(), y1 = in.ymin(), x2 = in.xmax(), y2 = in.ymax();
+  float x1p = out.xmin(), y1p = out.ymin(), x2p = out.xmax(), y2p = out.ymax();
+  float area = (x2 - x1) * (y2 - y1);
+  if (area <= 0.0f) return false;
+  float iw = rmax(rmin(x2, x2p) - rmax(x1, x1p), 0.0f);
+  float ih = rmax(rmin(y2, y2p) - rmax(y1, y1p), 0.0f);
+  return iw * ih / area >= 0.9f;
+}
+}  // namespace
+
+extern "C" {
+
+int oracle_layout_nms(const float* boxes, const int32_t* classes, const float* scores, int n, int32_t* keep) {
+  std::vector<LBox> b(n);
+  for (int i = 0; i < n; ++i) b[i] = LBox{boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]};
+  std::vector<int> sel = layout_nms(b, std::vector<int>(classes, classes + n), std::vector<float>(scores, scores + n));
+  for (size_t i = 0; i < sel.size(); ++i) keep[i] = sel[i];
+  return (int)sel.size();
+}
+
+// the reference's own test oracle, compacting_nms_reference (layout_detection_adapter.rs:1667-1697): rebuilds the
+// candidate list after every selection and keeps idx while iou < threshold
+int oracle_layout_nms_compacting(const float* boxes, const int32_t* classes, const float* scores, int n, int32_t* keep) {
+  std::vector<LBox> b(n);
+  for (int i = 0; i < n; ++i) b[i] = LBox{boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]};
+  std::vector<int> indices = score_order(scores, n);
+  int m = 0;
+  while (!indices.empty()) {
+    int cur = indices[0];
+    keep[m++] = cur;
+    std::vector<int> next;
+    for (size_t k = 1; k < indices.size(); ++k) {
+      int idx = indices[k];
+      float thr = classes[idx] == classes[cur] ? 0.6f : 0.98f;
+      if (layout_iou(b[cur], b[idx]) < thr) next.push_back(idx);
+    }
+    indices.swap(next);
+  }
+  return m;
+}
+
+// postprocess_pp_doclayout for ONE image (:674-840).  pred [num_boxes][feature_dim] rows
+// [class_id, score, x1, y1, x2, y2, (order...)]; class_thresholds [num_classes] (NaN = not configured) or null;
+// merge_modes [num_classes] (-1 not configured, 0 Large, 1 Small, 2 Union) or null; unclip_mode 0 none,
+// 1 uniform/separate (unclip_w, unclip_h), 2 per class (class_unclip [num_classes][2], NaN = (1, 1)).
+// Outputs up to max_elements rows; returns the count.
+int oracle_layout_postprocess(const float* pred, int num_boxes, int feature_dim, float orig_w, float orig_h,
+                              float score_threshold, int max_elements, int layout_nms_on, int num_classes,
+                              const float* class_thresholds, const int32_t* merge_modes, int image_class_id,
+                              int formula_class_id, int unclip_mode, float unclip_w, float unclip_h,
+                              const float* class_unclip, float* out_boxes, int32_t* out_classes, float* out_scores) {
+  const int order_mode = feature_dim == 8 ? 2 : (feature_dim == 7 ? 3 : 0);
+  std::vector<LBox> boxes;
+  std::vector<int> classes;
+  std::vector<float> scores;
+  std::vector<std::pair<float, float>> order;
+  for (int i = 0; i < num_boxes; ++i) {
+    const float* r = pred + (size_t)i * feature_dim;
+    // `as i32` saturates and maps NaN to 0
+    float cf = r[0];
+    int class_id = std::isnan(cf) ? 0 : (cf >= 2147483648.0f ? INT32_MAX : (cf <= -2147483648.0f ? INT32_MIN : (int)cf));
+    float score = r[1];
+    if (class_id < 0 || class_id >= num_classes) continue;
+    float thr = rmax(score_threshold, 0.0f);
+    if (class_thresholds && !std::isnan(class_thresholds[class_id])) thr = class_thresholds[class_id];
+    if (score < thr) continue;
+    float x1 = r[2], y1 = r[3], x2 = r[4], y2 = r[5];
+    // convert_bbox_coords, :848-878
+    bool normalized = x2 <= 1.05f && y2 <= 1.05f && x1 >= -0.05f && y1 >= -0.05f && orig_w > 0.0f && orig_h > 0.0f;
+    float sx1, sy1, sx2, sy2;
+    if (normalized) {
+      sx1 = rclamp(x1, 0.0f, 1.0f) * orig_w, sy1 = rclamp(y1, 0.0f, 1.0f) * orig_h;
+      sx2 = rclamp(x2, 0.0f, 1.0f) * orig_w, sy2 = rclamp(y2, 0.0f, 1.0f) * orig_h;
+    } else {
+      sx1 = rclamp(x1, 0.0f, orig_w), sy1 = rclamp(y1, 0.0f, orig_h);
+      sx2 = rclamp(x2, 0.0f, orig_w), sy2 = rclamp(y2, 0.0f, orig_h);
+    }
+    if (!(sx2 > sx1 && sy2 > sy1 && std::isfinite(sx1) && std::isfinite(sy1) && std::isfinite(sx2) && std::isfinite(sy2)))
+      continue;  // is_valid_box, :880-882
+    boxes.push_back(LBox{sx1, sy1, sx2, sy2});
+    classes.push_back(class_id);
+    scores.push_back(score);
+    order.push_back(order_mode == 2 ? std::make_pair(r[6], r[7])
+                                    : (order_mode == 3 ? std::make_pair(r[6], 0.0f) : std::make_pair(0.0f, 0.0f)));
+  }
+  auto select = [&](const std::vector<int>& keep) {
+    std::vector<LBox> b;
+    std::vector<int> c;
+    std::vector<float> s;
+    std::vector<std::pair<float, float>> o;
+    for (int k : keep) b.push_back(boxes[k]), c.push_back(classes[k]), s.push_back(scores[k]), o.push_back(order[k]);
+    boxes.swap(b), classes.swap(c), scores.swap(s), order.swap(o);
+  };
+  if (layout_nms_on && !boxes.empty()) select(layout_nms(boxes, classes, scores));
+  // filter_large_image_boxes, :953-992
+  if (image_class_id >= 0 && boxes.size() > 1) {
+    float area_thres = orig_w > orig_h ? 0.82f : 0.93f;
+    float img_area = orig_w * orig_h;
+    std::vector<int> keep;
+    for (size_t i = 0; i < boxes.size(); ++i) {
+      if (classes[i] != image_class_id) {
+        keep.push_back((int)i);
+        continue;
+      }
+      float xmin = rmax(boxes[i].xmin(), 0.0f), ymin = rmax(boxes[i].ymin(), 0.0f);
+      float xmax = rmin(boxes[i].xmax(), orig_w), ymax = rmin(boxes[i].ymax(), orig_h);
+      float area = (xmax - xmin) * (ymax - ymin);
+      if (area <= area_thres * img_area) keep.push_back((int)i);
+    }
+    if (!keep.empty()) select(keep);
+  }
+  // apply_paddlex_merge_modes, :994-1037 (+ check_containment :1039-1083)
+  bool any_mode = false;
+  if (merge_modes)
+    for (int c = 0; c < num_classes; ++c) any_mode = any_mode || merge_modes[c] >= 0;
+  if (any_mode && !boxes.empty()) {
+    const int n = (int)boxes.size();
+    std::vector<char> keep_mask(n, 1);
+    for (int cls = 0; cls < num_classes; ++cls) {
+      int mode = merge_modes[cls];
+      if (mode != 0 && mode != 1) continue;  // Union (and unset) do nothing
+      std::vector<int> contains(n, 0), contained(n, 0);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          if (i == j) continue;
+          if (formula_class_id >= 0 && classes[i] == formula_class_id && classes[j] != formula_class_id) continue;
+          if (mode == 0 && classes[j] == cls && layout_is_contained(boxes[i], boxes[j])) contained[i] = 1, contains[j] = 1;
+          if (mode == 1 && classes[i] == cls && layout_is_contained(boxes[i], boxes[j])) contained[i] = 1, contains[j] = 1;
+        }
+      for (int i = 0; i < n; ++i) {
+        if (mode == 0 && contained[i] == 1) keep_mask[i] = 0;
+        if (mode == 1 && !(contains[i] == 0 || contained[i] == 1)) keep_mask[i] = 0;
+      }
+    }
+    std::vector<int> keep;
+    for (int i = 0; i < n; ++i)
+      if (keep_mask[i]) keep.push_back(i);
+    select(keep);
+  }
+  // reading-order sort, :787-812: stable, total_cmp on (column, row) for V2, on the single key for V3
+  if (order_mode != 0 && !boxes.empty()) {
+    auto total_less = [](float a, float b) {  // f32::total_cmp
+      int32_t x, y;
+      memcpy(&x, &a, 4), memcpy(&y, &b, 4);
+      x ^= (int32_t)(((uint32_t)(x >> 31)) >> 1);
+      y ^= (int32_t)(((uint32_t)(y >> 31)) >> 1);
+      return x < y;
+    };
+    std::vector<int> idx(boxes.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int i, int j) {
+      if (total_less(order[i].first, order[j].first)) return true;
+      if (total_less(order[j].first, order[i].first)) return false;
+      return order_mode == 2 && total_less(order[i].second, order[j].second);
+    });
+    select(idx);
+  }
+  // unclip_boxes, layout_postprocess.rs:636-681
+  if (unclip_mode != 0) {
+    for (size_t i = 0; i < boxes.size(); ++i) {
+      float wr = unclip_mode == 2 ? 1.0f : unclip_w, hr = unclip_mode == 2 ? 1.0f : unclip_h;
+      if (unclip_mode == 2 && class_unclip && !std::isnan(class_unclip[2 * classes[i]]))
+        wr = class_unclip[2 * classes[i]], hr = class_unclip[2 * classes[i] + 1];
+      if (std::fabs(wr - 1.0f) < 1e-6f && std::fabs(hr - 1.0f) < 1e-6f) continue;
+      float x_min = boxes[i].xmin(), y_min = boxes[i].ymin(), x_max = boxes[i].xmax(), y_max = boxes[i].ymax();
+      float width = x_max - x_min, height = y_max - y_min;
+      float cx = x_min + width * 0.5f, cy = y_min + height * 0.5f;
+      float hw = width * wr * 0.5f, hh = height * hr * 0.5f;
+      boxes[i] = LBox{cx - hw, cy - hh, cx + hw, cy + hh};
+    }
+  }
+  int m = 0;
+  for (size_t i = 0; i < boxes.size() && m < max_elements; ++i, ++m) {
+    out_boxes[4 * m] = boxes[i].x1, out_boxes[4 * m + 1] = boxes[i].y1;
+    out_boxes[4 * m + 2] = boxes[i].x2, out_boxes[4 * m + 3] = boxes[i].y2;
+    out_classes[m] = classes[i];
+    out_scores[m] = scores[i];
+  }
+  return m;
+}
+
+}  // extern "C"

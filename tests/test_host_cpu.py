@@ -163,14 +163,19 @@ int main(void) {
          offsetof(oar_ocr_result, ms_h2d), offsetof(oar_ocr_result, h2d_bytes), offsetof(oar_ocr_result, cols),
          offsetof(oar_ocr_result, max_wh_ratio), sizeof(oar_pipeline_config));
   printf("%zu %zu\n", sizeof(oar_det_config), offsetof(oar_pipeline_config, image_batch_size));
+  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(oar_ocr_result, line_angle), offsetof(oar_ocr_result, ms_cls),
+         sizeof(oar_layout_config), offsetof(oar_layout_config, class_thresholds),
+         offsetof(oar_layout_config, image_class_id), offsetof(oar_layout_config, class_unclip));
   return 0;
 }
 ''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
-    a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")[:2]
-    got = [int(x) for x in a.split()] + [int(x) for x in b.split()]
-    R, P = ffi.OcrResult, ffi.PipelineConfig
+    a, b, c = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")[:3]
+    got = [int(x) for x in a.split()] + [int(x) for x in b.split()] + [int(x) for x in c.split()]
+    R, P, L = ffi.OcrResult, ffi.PipelineConfig, ffi.LayoutConfig
     want = [C.sizeof(R), R.labels.offset, R.ms_h2d.offset, R.h2d_bytes.offset, R.cols.offset, R.max_wh_ratio.offset,
-            C.sizeof(P), C.sizeof(ffi.DetConfig), P.image_batch_size.offset]
+            C.sizeof(P), C.sizeof(ffi.DetConfig), P.image_batch_size.offset,
+            R.line_angle.offset, R.ms_cls.offset, C.sizeof(L), L.class_thresholds.offset, L.image_class_id.offset,
+            L.class_unclip.offset]
     assert got == want
