@@ -83,33 +83,47 @@ def predict_pooled(stages, images, rank: int, world: int, region_batch_size: int
     carry the same payload), results are all-gathered.  world == 1 needs no process group.
 
     `stages` provides detect(images) -> per image boxes [n,4,2] in reading order; crop(image, boxes) -> list of
-    HxWx3 u8 crops (None where cropping fails); recognize(crops) -> list of (labels, score) for ONE batch.
-    Returns, on every rank, per image a list of dicts {box, det_index, labels, score} in detection order."""
+    HxWx3 u8 crops (None where cropping fails); recognize(crops) -> list of (labels, score) for ONE batch; and
+    optionally orient(crops) -> class id per crop + rotate180(crop), the text-line orientation stage
+    (classify_line_orientations, ocr.rs:615, 755-792): it runs per page on the rank that cropped it, before the
+    exchange, so rotated crops are what travels; wh_ratio keeps its pre-rotation value as in the reference.
+    Returns, on every rank, per image a list of dicts {box, det_index, labels, score, angle} in detection order
+    (angle = None without an orientation stage)."""
     import numpy as np
     start, end = block_partition(len(images), world)[rank]
     block = images[start:end]
     boxes = stages.detect(block) if block else []
-    local_crops, local_meta, local_boxes = {}, [], {}
+    local_crops, local_meta, local_boxes, local_angles = {}, [], {}, {}
+    orient = getattr(stages, "orient", None)
     for k, (img, b) in enumerate(zip(block, boxes)):
         gi = start + k
         local_boxes[gi] = np.asarray(b, np.float32).reshape(-1, 4, 2)
         crops = stages.crop(img, local_boxes[gi]) if len(local_boxes[gi]) else []
+        page = []
         for d, c in enumerate(crops):
             if c is None:
                 continue
             ratio = float(np.float32(c.shape[1]) / np.float32(max(c.shape[0], 1)))  # ocr.rs:739, f32
-            local_crops[(gi, d)] = c
+            page.append((d, c))
             local_meta.append((gi, d, ratio))
+        if orient is not None and page:
+            for (d, c), cid in zip(page, orient([c for _, c in page])):
+                local_angles[(gi, d)] = float(int(cid)) * 180.0
+                local_crops[(gi, d)] = stages.rotate180(c) if int(cid) == 1 else c
+        else:
+            for d, c in page:
+                local_crops[(gi, d)] = c
     if world > 1:
         import torch.distributed as dist
         parts = [None] * world
-        dist.all_gather_object(parts, (local_meta, local_boxes))
+        dist.all_gather_object(parts, (local_meta, local_boxes, local_angles))
         meta = [m for p in parts for m in p[0]]  # blocks are contiguous: rank order is image order
-        all_boxes = {}
+        all_boxes, angles = {}, {}
         for p in parts:
             all_boxes.update(p[1])
+            angles.update(p[2])
     else:
-        meta, all_boxes = local_meta, local_boxes
+        meta, all_boxes, angles = local_meta, local_boxes, local_angles
     chunks = plan_pooled_chunks(meta, region_batch_size, max_pooled)
     owner = [j % world for j in range(len(chunks))]  # whole chunks, round robin
     # crops travel once, to the rank that recognises their chunk
@@ -148,7 +162,8 @@ def predict_pooled(stages, images, rank: int, world: int, region_batch_size: int
         out = [r for p in parts for r in p]
     results = [[] for _ in images]
     for gi, d, labels, score in sorted(out, key=lambda r: (r[0], r[1])):
-        results[gi].append(dict(box=all_boxes[gi][d], det_index=d, labels=labels, score=score))
+        results[gi].append(dict(box=all_boxes[gi][d], det_index=d, labels=labels, score=score,
+                                angle=angles.get((gi, d))))
     return results
 
 
@@ -171,3 +186,13 @@ class GpuStages:
     def recognize(self, crops):
         r = self.ocr.rec.rec_run(crops, len(self.ocr.chars))
         return list(zip(r["labels"], [float(s) for s in r["scores"]]))
+
+    def __getattr__(self, name):
+        # the orientation stage exists only when the pipeline was built with a classifier
+        # (OAROCRBuilder::with_text_line_orientation_classification)
+        if name == "orient" and self.__dict__.get("ocr") is not None and self.ocr.cls is not None:
+            return lambda crops: self.ocr.cls.cls_run(crops, (80, 160), want_probs=False)["class_ids"]
+        raise AttributeError(name)
+
+    def rotate180(self, crop):
+        return self.ocr.ctx.rotate180(crop)

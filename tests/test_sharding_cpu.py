@@ -101,6 +101,23 @@ class _OracleStages:
         return list(zip(r["labels"], [float(s) for s in r["scores"]]))
 
 
+class _OracleStagesWithOrientation(_OracleStages):
+    def __init__(self):
+        super().__init__()
+        from oar_ocr_b200 import models
+        from oracle.net import OracleNet
+        self.cls = OracleNet(models.get_blob("cls"))
+
+    def orient(self, crops):
+        from oracle import pipeline
+        tops, _ = pipeline.cls_forward(self.cls, crops, topk=1)
+        return [int(ids[0]) for ids, _ in tops]
+
+    def rotate180(self, crop):
+        from oracle import cpu
+        return cpu.rotate180(crop)
+
+
 def _pooled_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -113,6 +130,9 @@ def _pooled_worker(rank, world, port, out_dir):
     st = _OracleStages()
     images = [synth.page(90 + i, 320) for i in range(4)]
     got = predict_pooled(st, images, rank, world, region_batch_size=3)
+    # the same with the text-line orientation stage: classified and rotated on the cropping rank, before the exchange
+    sto = _OracleStagesWithOrientation()
+    got_o = predict_pooled(sto, images, rank, world, region_batch_size=3)
     if rank == 0:
         # ONE un-sharded predict() over all images: the pooled 2-rank run must reproduce it exactly (scores bit for
         # bit).  On these pages plain block sharding does NOT (different recognition batches => different tensor_w).
@@ -122,8 +142,14 @@ def _pooled_worker(rank, world, port, out_dir):
         sharded = []
         for s, e in block_partition(len(images), world):
             sharded.extend(pipeline.predict(st.det, st.rec, images[s:e], 18385, image_batch_size=2, region_batch_size=3))
+        def exact_o(res):
+            return [[(r["box"].tolist(), r["labels"].tolist(), float(r["score"]), r["angle"]) for r in img] for img in res]
+        want_o = pipeline.predict(st.det, st.rec, images, 18385, image_batch_size=2, region_batch_size=3,
+                                  cls_net=sto.cls)
+        n180 = sum(r["angle"] == 180.0 for img in got_o for r in img)
         np.save(os.path.join(out_dir, "pooled.npy"),
-                np.array([exact(got) == exact(want), sum(len(x) for x in got), exact(got) == exact(sharded)]))
+                np.array([exact(got) == exact(want), sum(len(x) for x in got), exact(got) == exact(sharded),
+                          exact_o(got_o) == exact_o(want_o), n180, all(r["angle"] is None for img in got for r in img)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -131,6 +157,8 @@ def _pooled_worker(rank, world, port, out_dir):
 def test_two_rank_pooled_predict_equals_one_unsharded_predict(tmp_path):
     world = 2
     mp.spawn(_pooled_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    ok, n_regions, same_as_sharded = np.load(tmp_path / "pooled.npy")
+    ok, n_regions, same_as_sharded, ok_orient, n180, plain_angles_none = np.load(tmp_path / "pooled.npy")
     assert ok == 1 and n_regions >= 8
     assert same_as_sharded == 0  # the test pages are ones where block sharding alone changes the batches
+    # with the orientation stage the pooled 2-rank run still equals one un-sharded predict(), angles included
+    assert ok_orient == 1 and 1 <= n180 < n_regions and plain_angles_none == 1
