@@ -95,8 +95,8 @@ int32_t oar_model_set_engine(oar_model* m, int32_t engine);
 /* ---- seam 1: OrtInfer::infer / infer_first_output_f32 --------------------
  * (oar-ocr-core/src/core/inference/ort_infer_execution.rs:121-306)
  * in: host f32 [B,3,H,W] row-major (the tensor the reference feeds as "x").
- * det out: f32 [B,1,H,W] probability map; rec out: f32 [B,T,V] softmax.
- * out_shape receives 4 dims (rec: B,T,V,1).  out_cap in floats. */
+ * det out: f32 [B,1,H,W] probability map; rec out: f32 [B,T,V] softmax; cls out: f32 [B,classes] softmax.
+ * out_shape receives 4 dims (rec: B,T,V,1; cls: B,1,classes,1).  out_cap in floats. */
 int32_t oar_infer_f32(oar_model* m, const float* in, const int64_t in_shape[4], float* out, size_t out_cap,
                       int64_t out_shape[4]);
 
