@@ -12,7 +12,9 @@ directions:
                                squeeze-excite (GlobalAveragePool-Conv-Relu-Conv-HardSigmoid-Mul[-Add]), Resize-nearest,
                                Add, Concat, ConvTranspose 2x2/s2, AveragePool, LayerNormalization between NHWC
                                transposes, the single-input multi-head attention block and the MatMul+Softmax CTC head
-                               in the form export_onnx writes them.
+                               in the form export_onnx writes them; for classifiers (PP-LCNet line orientation) a
+                               plain GlobalAveragePool and the Flatten | Reshape | Squeeze -> Gemm | MatMul [+ Add] ->
+                               Softmax tail as PaddleClas / torch exports spell it; Dropout / Identity pass through.
   python -m oar_ocr_b200.onnx_io convert model.onnx model.oarg | export model.oarg model.onnx
 
 No real PP-OCR .onnx file is available offline, so import_onnx is verified by round trips of both synthetic networks
@@ -685,6 +687,13 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
                 _import_ctc_head(g, nodes, inits, done, tid, i, fail)
             else:
                 fail(n, "NHWC transpose outside LayerNormalization / attention / CTC head")
+        elif ot in ("Dropout", "Identity"):  # identities at inference time
+            tid[outs[0]] = tid[ins[0]]
+        elif ot in ("Flatten", "Squeeze", "Reshape"):
+            # classifier tail as PaddleClas / torch exports spell it: pooled [B,C,1,1] -> Flatten | Reshape | Squeeze
+            # -> Gemm | MatMul [+ Add] -> Softmax
+            kind = M.KIND_CLS
+            _import_cls_head(g, nodes, inits, consumers, done, tid, i, fail)
         else:
             fail(n, "operator outside the supported subset")
         i += 1
@@ -752,6 +761,55 @@ def _import_ctc_head(g, nodes, inits, done, tid, i, fail):
     x = tid[n["inputs"][0]]
     tid[nodes[seq[-1]]["outputs"][0]] = g.ctc_head(x, w.shape[1], np.ascontiguousarray(w.T).astype(np.float32),
                                                    b.astype(np.float32))
+
+
+def _import_cls_head(g, nodes, inits, consumers, done, tid, i, fail):
+    """Flatten | Reshape | Squeeze -> Gemm | MatMul [+ Add] -> Softmax on pooled [B,C,1,1] features: the Linear + softmax
+    head op on a one-step sequence (the engine checks at run time that the spatial size really is 1 x 1)"""
+    n = nodes[i]
+
+    def sole(value, types):
+        c = [k for k in consumers.get(value, []) if k >= 0 and k not in done]
+        return c[0] if len(c) == 1 and nodes[c[0]]["op_type"] in types else None
+
+    x = tid[n["inputs"][0]]
+    j = sole(n["outputs"][0], ("Gemm", "MatMul"))
+    if j is None:
+        fail(n, "flattened features must feed exactly one Gemm / MatMul")
+    m = nodes[j]
+    if m["inputs"][1] not in inits:
+        fail(m, "classifier weights must be an initializer")
+    w = inits[m["inputs"][1]].astype(np.float32)
+    seq, cur, b = [j], m["outputs"][0], None
+    if m["op_type"] == "Gemm":
+        a = m["attrs"]
+        if a.get("alpha", 1.0) != 1.0 or a.get("beta", 1.0) != 1.0 or a.get("transA", 0):
+            fail(m, "Gemm with alpha/beta != 1 or transA")
+        w = w if a.get("transB", 0) else w.T  # -> [classes, C]
+        if len(m["inputs"]) > 2 and m["inputs"][2]:
+            b = inits[m["inputs"][2]].astype(np.float32)
+    else:
+        w = w.T
+        k = sole(cur, ("Add",))
+        if k is not None:
+            bias = [v for v in nodes[k]["inputs"] if v in inits]
+            if len(bias) != 1:
+                fail(nodes[k], "classifier bias must be an initializer")
+            b = inits[bias[0]].astype(np.float32)
+            seq.append(k)
+            cur = nodes[k]["outputs"][0]
+    k = sole(cur, ("Softmax",))
+    if k is None:
+        fail(m, "classifier head must end in Softmax")
+    if nodes[k]["attrs"].get("axis", -1) not in (1, -1):
+        fail(nodes[k], "Softmax over an axis other than the classes")
+    seq.append(k)
+    if w.ndim != 2 or w.shape[1] != g.channels[x]:
+        fail(m, f"classifier weights {w.shape} do not match the {g.channels[x]} pooled channels")
+    if b is None:
+        b = np.zeros((w.shape[0],), np.float32)
+    done.update(seq)
+    tid[nodes[k]["outputs"][0]] = g.ctc_head(x, w.shape[0], np.ascontiguousarray(w), b.reshape(-1))
 
 
 def main(argv):

@@ -60,6 +60,16 @@ def _run_onnx(data: bytes, x: np.ndarray) -> np.ndarray:
             y = F.layer_norm(i[0], i[0].shape[-1:], i[1], i[2], a["epsilon"])
         elif t == "MatMul":
             y = i[0] @ i[1]
+        elif t == "Flatten":
+            y = i[0].flatten(a.get("axis", 1))
+        elif t == "Squeeze":
+            y = i[0].squeeze(-1).squeeze(-1)
+        elif t in ("Dropout", "Identity"):
+            y = i[0]
+        elif t == "Gemm":
+            y = i[0] @ (i[1].T if a.get("transB", 0) else i[1])
+            if len(i) > 2 and i[2] is not None:
+                y = y + i[2]
         elif t == "Softmax":
             y = torch.softmax(i[0], dim=a["axis"])
         elif t == "Split":
@@ -142,6 +152,48 @@ def test_import_folds_batchnorm_and_decomposed_activations():
     _, _, ops, _ = onnx_io._parse_oarg(blob)
     assert [(o["type"], o["p"][8]) for o in ops] == [(models.OP_CONV, models.ACT_HSWISH), (models.OP_CONV, models.ACT_SWISH)]
     assert np.abs(OracleNet(blob).forward(x) - want).max() <= 1e-5
+
+
+@pytest.mark.parametrize("tail", ["flatten_gemm", "reshape_matmul_add", "squeeze_matmul"])
+def test_import_classifier_tail_spellings(tail):
+    """a PaddleClas-style classifier: conv trunk -> GlobalAveragePool -> 1x1 conv + HardSwish -> Dropout -> flatten ->
+    fc -> Softmax, with the spellings exporters use for flatten and fc; imported as kind CLS, same probabilities"""
+    rng = np.random.default_rng(4)
+    T, N = onnx_io.tensor_proto, onnx_io.node
+    w = rng.standard_normal((8, 3, 3, 3)).astype(np.float32) * 0.3
+    w2 = rng.standard_normal((16, 8, 1, 1)).astype(np.float32) * 0.4
+    fc = rng.standard_normal((2, 16)).astype(np.float32)
+    fb = np.array([0.1, -0.2], np.float32)
+    nodes = [
+        N("Conv", ["x", "w", "b"], ["c"], kernel_shape=[3, 3], strides=[2, 2], pads=[1, 1, 1, 1], dilations=[1, 1], group=1),
+        N("HardSwish", ["c"], ["h"]),
+        N("GlobalAveragePool", ["h"], ["p"]),
+        N("Conv", ["p", "w2"], ["c2"], kernel_shape=[1, 1], strides=[1, 1], pads=[0, 0, 0, 0], dilations=[1, 1], group=1),
+        N("HardSwish", ["c2"], ["h2"]),
+        N("Dropout", ["h2"], ["d"]),
+    ]
+    inits = [T("w", w), T("b", rng.standard_normal(8).astype(np.float32) * 0.1), T("w2", w2)]
+    if tail == "flatten_gemm":
+        nodes += [N("Flatten", ["d"], ["f"], axis=1), N("Gemm", ["f", "fc", "fb"], ["l"], alpha=1.0, beta=1.0, transB=1),
+                  N("Softmax", ["l"], ["y"], axis=1)]
+        inits += [T("fc", fc), T("fb", fb)]
+    elif tail == "reshape_matmul_add":
+        nodes += [N("Reshape", ["d", "shp"], ["f"]), N("MatMul", ["f", "fc"], ["mm"]), N("Add", ["mm", "fb"], ["l"]),
+                  N("Softmax", ["l"], ["y"], axis=-1)]
+        inits += [T("shp", np.array([0, -1], np.int64)), T("fc", np.ascontiguousarray(fc.T)), T("fb", fb)]
+    else:
+        nodes += [N("Squeeze", ["d"], ["f"]), N("MatMul", ["f", "fc"], ["l"]), N("Softmax", ["l"], ["y"], axis=1)]
+        inits += [T("fc", np.ascontiguousarray(fc.T))]
+    data = onnx_io.model_proto(nodes, inits, [onnx_io.value_info("x", ["N", 3, "H", "W"])],
+                               [onnx_io.value_info("y", ["N", 2])])
+    x = rng.standard_normal((3, 3, 20, 28)).astype(np.float32)
+    want = _run_onnx(data, x)
+    blob = onnx_io.import_onnx(data)
+    kind, _, ops, _ = onnx_io._parse_oarg(blob)
+    assert kind == models.KIND_CLS
+    assert [o["type"] for o in ops] == [models.OP_CONV, models.OP_AVGPOOL, models.OP_CONV, models.OP_CTC_HEAD]
+    got = OracleNet(blob).forward(x).reshape(3, 2)
+    assert np.abs(got - want).max() <= 1e-6 and np.allclose(got.sum(1), 1.0, atol=1e-6)
 
 
 def test_import_rejects_what_it_cannot_run():
