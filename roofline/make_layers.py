@@ -1,4 +1,4 @@
-"""Algorithmic FLOPs and bytes per layer of the two OARG graphs (SURVEY.md §8d asks for this table to be recomputed
+"""Algorithmic FLOPs and bytes per layer of the OARG graphs (SURVEY.md §8d asks for this table to be recomputed
 from the builder's own layer list).  Bytes are fp32 NHWC input (read once) + output per op; for the fused engine the
 depthwise output of a [depthwise -> 1x1] block is dropped (it never reaches HBM).
 Usage: python roofline/make_layers.py > roofline/layers.json"""
@@ -52,7 +52,10 @@ def layers(blob, B, H, W):
             oc = p[11] or c
             out_c = c
         elif t == models.OP_AVGPOOL:
-            oh, ow = (h - p[0]) // p[2] + 1, (w - p[1]) // p[3] + 1
+            if p[0] == 0 and p[1] == 0:  # global pool
+                oh, ow = 1, 1
+            else:
+                oh, ow = (h - p[0]) // p[2] + 1, (w - p[1]) // p[3] + 1
             out_c = c
         elif t == models.OP_ATTN:
             T = h * w
@@ -78,7 +81,8 @@ def layers(blob, B, H, W):
 
 def main():
     out = {}
-    for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320))):
+    # cls = the optional text-line orientation classifier: one chunk of 256 crops at 80 x 160
+    for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320)), ("cls", (256, 80, 160))):
         rows, saved = layers(models.get_blob(kind), B, H, W)
         tot_f = sum(r["gflop"] for r in rows)
         tot_b = sum(r["mb_in"] + r["mb_out"] for r in rows)

@@ -143,6 +143,9 @@ def test_roofline_layers_match_survey_estimates():
         assert abs(fresh[kind]["gflop_per_item"] - want) / want < 0.05
         # the fused engine removes the depthwise round trip: strictly fewer bytes than one kernel per layer
         assert fresh[kind]["mb_total_fused_engine"] < fresh[kind]["mb_total_per_layer_kernels"]
+    # the optional line-orientation classifier (PP-LCNet x1.0 at 80 x 160 with the width kept after the stem)
+    assert committed["cls"]["gflop_per_item"] == fresh["cls"]["gflop_per_item"]
+    assert 0.4 < fresh["cls"]["gflop_per_item"] < 0.8
 
 
 def test_abi_struct_layouts_match_the_header(tmp_path):
