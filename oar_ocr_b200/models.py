@@ -33,10 +33,14 @@ import numpy as np
 MAGIC = b"OARG"
 VERSION = 1
 KIND_DET, KIND_REC, KIND_CLS = 0, 1, 2
+KIND_FEAT = 3  # feature extractor (HGNetV2 backbone): spec + oracle only, the CUDA engine does not load it yet
 
 # op types
 OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL, OP_LAYERNORM, OP_ATTN, \
     OP_CTC_HEAD = range(1, 12)
+# Ops the HGNetV2 stem needs.  Executed by the oracle (oracle/net.py) and exported / imported by
+# onnx_io; csrc/engine.cu rejects them ("unknown op type") until their kernels exist -- no silent fallback.
+OP_PAD, OP_MAXPOOL = 12, 13
 # activations
 ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID = range(6)
 
@@ -141,6 +145,18 @@ class GraphBuilder:
         """k = (0, 0): global average pool"""
         out = self.new_tensor(self.channels[x])
         self.ops.append(Op(OP_AVGPOOL, x, -1, out, [k[0], k[1], s[0], s[1]] + [0] * 8))
+        return out
+
+    def pad(self, x, top, left, bottom, right):
+        """zero padding of the spatial dims (ONNX Pad, constant 0)"""
+        out = self.new_tensor(self.channels[x])
+        self.ops.append(Op(OP_PAD, x, -1, out, [top, left, bottom, right] + [0] * 8))
+        return out
+
+    def maxpool(self, x, k, s):
+        """max pool, no padding, floor mode (ONNX MaxPool)"""
+        out = self.new_tensor(self.channels[x])
+        self.ops.append(Op(OP_MAXPOOL, x, -1, out, [k[0], k[1], s[0], s[1]] + [0] * 8))
         return out
 
     def layernorm(self, x, eps):
@@ -474,6 +490,66 @@ def build_cls(seed: int = 42, scale: float = 1.0, num_classes: int = 2, dark_ref
         wf[1, 0], wf[1, 1] = 1.0, -1.0
         wf[0, 0], wf[0, 1] = -1.0, 1.0
     g.ctc_head(x, num_classes, wf, bf)   # Linear + softmax over the single "timestep"
+    return g.serialize()
+
+
+# HGNetV2-L: the backbone of PP-DocLayout-L / RT-DETR-L and, with other strides, of the
+# server-size OCR models (item 4).  Stage table as the reference's in-tree description states it
+# (oar-ocr-vl/src/models/pp_doclayout/hgnetv2.rs:13-23).
+_HG_STEM = (3, 32, 48)
+_HG_STAGES = [  # (in, mid, out, blocks, downsample, light, kernel, layers)
+    (48, 48, 128, 1, False, False, 3, 6),
+    (128, 96, 512, 1, True, False, 3, 6),
+    (512, 192, 1024, 3, True, True, 5, 6),
+    (1024, 384, 2048, 1, True, True, 5, 6),
+]
+
+
+def _hg_block(g: GraphBuilder, x, cin, mid, cout, layers, k, light, residual):
+    """HGNetV2 BasicLayer (hgnetv2.rs:161-262): `layers` convs in a chain, every output (and the input) concatenated,
+    two 1x1 aggregation convs, optional identity residual.  The concat is channel-slice writes into one buffer."""
+    total = cin + layers * mid
+    cat = g.new_tensor(total)
+    g.upsample_into(x, 1, cat, 0, total)
+    h = x
+    for i in range(layers):
+        if light:  # ConvLayerLight: 1x1 conv (no activation) then depthwise k x k + ReLU
+            h = g.conv(h, mid, (1, 1), act=ACT_NONE)
+            h = g.dwconv(h, k, (1, 1), act=ACT_RELU)
+        elif i == layers - 1:  # nothing else reads the last layer: it writes its concat slice directly
+            g.conv(h, mid, (k, k), act=ACT_RELU, out=cat, c_off=cin + i * mid, c_total=total)
+            continue
+        else:
+            h = g.conv(h, mid, (k, k), act=ACT_RELU)
+        g.upsample_into(h, 1, cat, cin + i * mid, total)
+    y = g.conv(cat, cout // 2, (1, 1), act=ACT_RELU)
+    y = g.conv(y, cout, (1, 1), act=ACT_RELU)
+    return g.add(y, x) if residual else y
+
+
+def build_hgnetv2_l(seed: int = 42, return_idx=(3,)) -> bytes:
+    """HGNetV2-L feature extractor (hgnetv2.rs: Embeddings :264-348, Stage :264-330, BasicLayer :161-262), BatchNorm
+    folded into the conv biases, He-normal synthetic weights.  The graph's output is the last requested stage
+    (strides 4 / 8 / 16 / 32, 128 / 512 / 1024 / 2048 channels).  Spec + oracle only for now (KIND_FEAT)."""
+    g = GraphBuilder(KIND_FEAT, seed)
+    g.base_gain = 0.7
+    c0, c1, c2 = _HG_STEM
+    x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_RELU)                       # stem1
+    p = g.pad(x, 0, 0, 1, 1)                                              # pad_right_bottom
+    b = g.conv(p, c1 // 2, (2, 2), pad=(0, 0), act=ACT_RELU)              # stem2a
+    cat = g.new_tensor(2 * c1)
+    g.upsample_into(g.maxpool(p, (2, 2), (1, 1)), 1, cat, 0, 2 * c1)
+    g.conv(g.pad(b, 0, 0, 1, 1), c1, (2, 2), pad=(0, 0), act=ACT_RELU, out=cat, c_off=c1, c_total=2 * c1)  # stem2b
+    x = g.conv(cat, c1, (3, 3), (2, 2), act=ACT_RELU)                     # stem3
+    x = g.conv(x, c2, (1, 1), act=ACT_RELU)                               # stem4
+    last = max(return_idx)
+    for si, (cin, mid, cout, blocks, down, light, k, layers) in enumerate(_HG_STAGES):
+        if down:  # depthwise 3x3 stride 2, no activation
+            x = g.dwconv(x, 3, (2, 2), act=ACT_NONE)
+        for bi in range(blocks):
+            x = _hg_block(g, x, cin if bi == 0 else cout, mid, cout, layers, k, light, residual=bi != 0)
+        if si == last:
+            break
     return g.serialize()
 
 

@@ -334,6 +334,15 @@ def export_onnx(blob: bytes) -> bytes:
                 nodes.append(node("AveragePool", [a], [y], kernel_shape=[p[0], p[1]], strides=[p[2], p[3]],
                                   pads=[0, 0, 0, 0]))
             name_of[op["out"]] = y
+        elif t == M.OP_PAD:
+            y = fresh("pad")
+            pads = init("pads", np.array([0, 0, p[0], p[1], 0, 0, p[2], p[3]], np.int64))  # NCHW begins, then ends
+            nodes.append(node("Pad", [a, pads], [y], mode="constant"))
+            name_of[op["out"]] = y
+        elif t == M.OP_MAXPOOL:
+            y = fresh("maxpool")
+            nodes.append(node("MaxPool", [a], [y], kernel_shape=[p[0], p[1]], strides=[p[2], p[3]], pads=[0, 0, 0, 0]))
+            name_of[op["out"]] = y
         elif t == M.OP_LAYERNORM:
             c = p[0]
             n1, n2, y = fresh("nhwc"), fresh("ln"), fresh("nchw")
@@ -383,7 +392,12 @@ def export_onnx(blob: bytes) -> bytes:
         else:
             raise OCRError("ModelLoad", f"cannot export op type {t}")
     out_name = value(ops[-1]["out"])
-    out_dims = ["N", 1, "H", "W"] if kind == M.KIND_DET else ["N", "T", ops[-1]["p"][1]]
+    if kind == M.KIND_DET:
+        out_dims = ["N", 1, "H", "W"]
+    elif kind == M.KIND_FEAT:
+        out_dims = ["N", "C", "H", "W"]
+    else:
+        out_dims = ["N", "T", ops[-1]["p"][1]]
     return model_proto(nodes, inits, [value_info("x", ["N", 3, "H", "W"])], [value_info(out_name, out_dims)])
 
 
@@ -659,6 +673,23 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
             if post != (1.0, 0.0):
                 fail(n, "affine after a transposed convolution")
             tid[y] = g.deconv2(tid[ins[0]], w.shape[1], act=act, w=np.ascontiguousarray(w.transpose(2, 3, 1, 0)), b=b)
+        elif ot == "Pad":
+            a = n["attrs"]
+            if a.get("mode", "constant") not in ("constant", b"constant"):
+                fail(n, "Pad mode other than constant")
+            if len(ins) < 2 or ins[1] not in inits:
+                fail(n, "Pad amounts must be an initializer")
+            pads = [int(v) for v in inits[ins[1]].ravel()]
+            if len(pads) != 8 or any(pads[k] for k in (0, 1, 4, 5)) or min(pads) < 0:
+                fail(n, "Pad must add zeros to the spatial dims of an NCHW tensor")
+            if len(ins) > 2 and ins[2] and (ins[2] not in inits or float(inits[ins[2]].ravel()[0]) != 0.0):
+                fail(n, "Pad with a non-zero constant")
+            tid[outs[0]] = g.pad(tid[ins[0]], pads[2], pads[3], pads[6], pads[7])
+        elif ot == "MaxPool":
+            a = n["attrs"]
+            if any(a.get("pads", [0] * 4)) or a.get("ceil_mode", 0) or any(d != 1 for d in a.get("dilations", [1, 1])):
+                fail(n, "MaxPool with padding, ceil_mode or dilation")
+            tid[outs[0]] = g.maxpool(tid[ins[0]], tuple(a["kernel_shape"]), tuple(a.get("strides", [1, 1])))
         elif ot == "AveragePool":
             a = n["attrs"]
             if any(a.get("pads", [0] * 4)):

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 
 OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL, OP_LAYERNORM, OP_ATTN, \
     OP_CTC_HEAD = range(1, 12)
+OP_PAD, OP_MAXPOOL = 12, 13  # HGNetV2 stem (models.py): zero padding, max pool
 
 
 def parse(blob: bytes):
@@ -114,6 +115,10 @@ class OracleNet:
                     t[op["out"]] = a.mean(dim=(2, 3), keepdim=True)
                 else:
                     t[op["out"]] = F.avg_pool2d(a, (p[0], p[1]), (p[2], p[3]))
+            elif ty == OP_PAD:
+                t[op["out"]] = F.pad(a, (p[1], p[3], p[0], p[2]))  # (left, right, top, bottom)
+            elif ty == OP_MAXPOOL:
+                t[op["out"]] = F.max_pool2d(a, (p[0], p[1]), (p[2], p[3]))
             elif ty == OP_LAYERNORM:
                 c = p[0]
                 y = F.layer_norm(a.permute(0, 2, 3, 1), (c,), self._w(op, 0, (c,)), self._w(op, 1, (c,)), f[0])

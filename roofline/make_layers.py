@@ -57,6 +57,12 @@ def layers(blob, B, H, W):
             else:
                 oh, ow = (h - p[0]) // p[2] + 1, (w - p[1]) // p[3] + 1
             out_c = c
+        elif t == models.OP_PAD:
+            oh, ow = h + p[0] + p[2], w + p[1] + p[3]
+            out_c = c
+        elif t == models.OP_MAXPOOL:
+            oh, ow = (h - p[0]) // p[2] + 1, (w - p[1]) // p[3] + 1
+            out_c = c
         elif t == models.OP_ATTN:
             T = h * w
             flops = 2 * T * c * 3 * c + 2 * T * c * c + 4 * T * T * c
@@ -82,8 +88,12 @@ def layers(blob, B, H, W):
 def main():
     out = {}
     # cls = the optional text-line orientation classifier: one chunk of 256 crops at 80 x 160
-    for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320)), ("cls", (256, 80, 160))):
-        rows, saved = layers(models.get_blob(kind), B, H, W)
+    # hgnetv2_l = the backbone of PP-DocLayout-L (BASELINE.json configs[4]: batch 64; the reference resizes every page
+    # to 640 x 640 before the network) -- spec + oracle only so far
+    for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320)), ("cls", (256, 80, 160)),
+                            ("hgnetv2_l", (64, 640, 640))):
+        blob = models.build_hgnetv2_l() if kind == "hgnetv2_l" else models.get_blob(kind)
+        rows, saved = layers(blob, B, H, W)
         tot_f = sum(r["gflop"] for r in rows)
         tot_b = sum(r["mb_in"] + r["mb_out"] for r in rows)
         out[kind] = dict(batch=B, input_hw=[H, W], gflop_total=round(tot_f, 2), gflop_per_item=round(tot_f / B, 3),

@@ -42,6 +42,11 @@ def _run_onnx(data: bytes, x: np.ndarray) -> np.ndarray:
             y = i[0].mean(dim=(2, 3), keepdim=True)
         elif t == "AveragePool":
             y = F.avg_pool2d(i[0], a["kernel_shape"], a["strides"])
+        elif t == "MaxPool":
+            y = F.max_pool2d(i[0], a["kernel_shape"], a["strides"])
+        elif t == "Pad":
+            pd = [int(q) for q in i[1]]
+            y = F.pad(i[0], (pd[3], pd[7], pd[2], pd[6]))
         elif t == "Resize":
             assert a["mode"] == "nearest"
             y = F.interpolate(i[0], scale_factor=float(i[2][2]), mode="nearest")
@@ -98,11 +103,14 @@ def test_wire_format_roundtrip():
     assert ins == ["x"] and outs == ["y"] and nodes[0]["inputs"] == ["x", "w"]
 
 
-@pytest.mark.parametrize("kind", ["det", "rec", "cls"])
+@pytest.mark.parametrize("kind", ["det", "rec", "cls", "hgnetv2"])
 def test_export_matches_oracle_and_import_roundtrips(kind):
-    blob = models.get_blob(kind, vocab=97) if kind == "rec" else models.get_blob(kind)
+    if kind == "hgnetv2":  # two stages of the layout / server backbone: stem with Pad + MaxPool, concat blocks
+        blob = models.build_hgnetv2_l(return_idx=(1,))
+    else:
+        blob = models.get_blob(kind, vocab=97) if kind == "rec" else models.get_blob(kind)
     rng = np.random.default_rng(3)
-    shape = {"det": (2, 3, 64, 96), "rec": (2, 3, 48, 64), "cls": (2, 3, 80, 160)}[kind]
+    shape = {"det": (2, 3, 64, 96), "rec": (2, 3, 48, 64), "cls": (2, 3, 80, 160), "hgnetv2": (1, 3, 64, 96)}[kind]
     x = rng.standard_normal(shape).astype(np.float32)
     want = OracleNet(blob).forward(x)
     data = onnx_io.export_onnx(blob)
@@ -112,7 +120,7 @@ def test_export_matches_oracle_and_import_roundtrips(kind):
     assert np.abs(got - want).max() <= 2e-5
     # 2. importing it back gives a graph with the same ops, parameters and weights: identical oracle output
     # (a classifier ends in the same MatMul + Softmax pattern as a CTC head: the caller's role names the kind)
-    back = onnx_io.import_onnx(data, models.KIND_CLS if kind == "cls" else None)
+    back = onnx_io.import_onnx(data, {"cls": models.KIND_CLS, "hgnetv2": models.KIND_FEAT}.get(kind))
     k0, _, ops0, w0 = onnx_io._parse_oarg(blob)
     k1, _, ops1, w1 = onnx_io._parse_oarg(back)
     assert k0 == k1 and sorted(o["type"] for o in ops0) == sorted(o["type"] for o in ops1)
