@@ -553,6 +553,50 @@ def build_hgnetv2_l(seed: int = 42, return_idx=(3,)) -> bytes:
     return g.serialize()
 
 
+# Server-size recogniser: PP-OCRv5_server_rec = PPHGNetV2_B4 (the table above; "B4" and "L" name the
+# same widths) with text-recognition strides + the SVTR neck + CTC head of the mobile model.  EXT: the stride table is
+# recalled from PaddleOCR's rec_pphgnetv2 (stem3 stride 1; stage downsamples (2,1), (1,2), (2,1), (2,1); every stage
+# downsamples); no .onnx file is available offline to confirm it.
+_HG_REC_STRIDES = [(2, 1), (1, 2), (2, 1), (2, 1)]
+
+
+def build_rec_server(seed: int = 42, vocab: int = 18385) -> bytes:
+    """PP-OCRv5_server_rec shaped graph: HGNetV2-B4 (rec strides: 48 x W -> 3 x W/4 x 2048) + avgpool(3,2) +
+    EncoderWithSVTR(dims 120, depth 2) + CTC Linear(120 -> vocab) + softmax; He-normal synthetic weights.
+    Spec + oracle only: the CUDA engine has no kernels for OP_PAD / OP_MAXPOOL yet and fails loudly on them."""
+    g = GraphBuilder(KIND_REC, seed)
+    g.base_gain = 0.7
+    c0, c1, c2 = _HG_STEM
+    x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_RELU)
+    p = g.pad(x, 0, 0, 1, 1)
+    b = g.conv(p, c1 // 2, (2, 2), pad=(0, 0), act=ACT_RELU)
+    cat = g.new_tensor(2 * c1)
+    g.upsample_into(g.maxpool(p, (2, 2), (1, 1)), 1, cat, 0, 2 * c1)
+    g.conv(g.pad(b, 0, 0, 1, 1), c1, (2, 2), pad=(0, 0), act=ACT_RELU, out=cat, c_off=c1, c_total=2 * c1)
+    x = g.conv(cat, c1, (3, 3), (1, 1), act=ACT_RELU)   # stem3 keeps the resolution for text recognition
+    x = g.conv(x, c2, (1, 1), act=ACT_RELU)
+    for (cin, mid, cout, blocks, _down, light, k, layers), s in zip(_HG_STAGES, _HG_REC_STRIDES):
+        x = g.dwconv(x, 3, s, act=ACT_NONE)
+        for bi in range(blocks):
+            x = _hg_block(g, x, cin if bi == 0 else cout, mid, cout, layers, k, light, residual=bi != 0)
+    x = g.avgpool(x, (3, 2), (3, 2))
+    cin = g.channels[x]
+    h = x
+    z = g.conv(x, cin // 8, (1, 3), act=ACT_SWISH)
+    z = g.conv(z, 120, (1, 1), act=ACT_SWISH)
+    for _ in range(2):
+        z = _svtr_block(g, z, 8)
+    z = g.layernorm(z, 1e-6)
+    cat = g.new_tensor(2 * cin)
+    g.upsample_into(h, 1, cat, 0, 2 * cin)
+    g.conv(z, cin, (1, 1), act=ACT_SWISH, out=cat, c_off=cin, c_total=2 * cin)
+    z = g.conv(cat, cin // 8, (1, 3), act=ACT_SWISH)
+    z = g.conv(z, 120, (1, 1), act=ACT_SWISH)
+    w = (g.rng.standard_normal((vocab, 120)) * (4.0 / np.sqrt(120.0))).astype(np.float32)
+    g.ctc_head(z, vocab, w, g.small((vocab,), 0.1))
+    return g.serialize()
+
+
 def synthetic_dict(vocab: int = 18385) -> list[str]:
     """Character list for synthetic runs: vocab-2 distinct code points (CJK block
     onward), standing in for ppocrv5_dict.txt (one char per line, ocr.rs:386)."""

@@ -88,11 +88,13 @@ def layers(blob, B, H, W):
 def main():
     out = {}
     # cls = the optional text-line orientation classifier: one chunk of 256 crops at 80 x 160
+    # rec_server = PP-OCRv5_server_rec shaped graph, spec + oracle only so far
     # hgnetv2_l = the backbone of PP-DocLayout-L (BASELINE.json configs[4]: batch 64; the reference resizes every page
     # to 640 x 640 before the network) -- spec + oracle only so far
     for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320)), ("cls", (256, 80, 160)),
-                            ("hgnetv2_l", (64, 640, 640))):
-        blob = models.build_hgnetv2_l() if kind == "hgnetv2_l" else models.get_blob(kind)
+                            ("hgnetv2_l", (64, 640, 640)), ("rec_server", (256, 48, 320))):
+        blob = models.build_hgnetv2_l() if kind == "hgnetv2_l" else (
+            models.build_rec_server() if kind == "rec_server" else models.get_blob(kind))
         rows, saved = layers(blob, B, H, W)
         tot_f = sum(r["gflop"] for r in rows)
         tot_b = sum(r["mb_in"] + r["mb_out"] for r in rows)

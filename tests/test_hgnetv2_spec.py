@@ -38,6 +38,23 @@ def test_layer_list_matches_the_reference_description():
     assert sorted(o["p"][7] for o in agg) == [64, 256, 512, 512, 512, 1024]
 
 
+def test_server_recogniser_graph():
+    """PP-OCRv5_server_rec shaped graph on the oracle: same sequence geometry as the mobile recogniser (T = W / 8), a
+    softmax over the vocabulary per timestep, ~8x the mobile model's arithmetic (roofline/layers.json)"""
+    import json
+    import os
+    from oar_ocr_b200 import models
+    from oracle.net import OracleNet
+    x = np.random.default_rng(1).standard_normal((2, 3, 48, 160)).astype(np.float32)
+    y = OracleNet(models.build_rec_server(vocab=97)).forward(x)
+    assert y.shape == (2, 20, 97) and np.allclose(y.sum(-1), 1.0, atol=1e-5)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "roofline", "layers.json")))
+    assert d["rec_server"]["gflop_per_item"] > 5 * d["rec"]["gflop_per_item"]
+    # wide dense convs: the 3-pass tensor-core time exceeds the HBM time of the per-layer traffic (tensor-bound)
+    assert d["rec_server"]["tensor_ms_at_1590_tflops_x3"] > 0.5 * d["rec_server"]["hbm_ms_at_6650_gbs_fused"]
+
+
 def test_new_ops_in_the_oracle():
     """OP_PAD = zero padding (top, left, bottom, right); OP_MAXPOOL = floor-mode max pool without padding"""
     from oar_ocr_b200 import models
