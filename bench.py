@@ -110,7 +110,9 @@ def workload_config(args, world):
                         "(BASELINE.json configs[1])",
             "images_per_step": args.batch * world, "image_batch_size": args.image_batch_size,
             "region_batch_size": args.region_batch_size, "weights": "synthetic planted-signal, seed 42, V=18385",
-            "l2": "flushed between steps (256 MiB memset on the launch stream)", "sharding": f"replicas x{world}"}
+            "l2": "flushed between steps (256 MiB memset on the launch stream)", "sharding": f"replicas x{world}",
+            **({"line_orientation": "on (optional stage; the CPU arms do not run it)"}
+               if getattr(args, "line_orientation", False) else {})}
 
 
 def run_reference(args, rank, world):
@@ -165,12 +167,17 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ocr = (OAROCRBuilder(models.get_blob("det"), models.get_blob("rec"))
-           .character_dict_content("\n".join(models.synthetic_dict())).device_id(local_rank)
-           .image_batch_size(args.image_batch_size).region_batch_size(args.region_batch_size).build())
+    builder = (OAROCRBuilder(models.get_blob("det"), models.get_blob("rec"))
+               .character_dict_content("\n".join(models.synthetic_dict())).device_id(local_rank)
+               .image_batch_size(args.image_batch_size).region_batch_size(args.region_batch_size))
+    if args.line_orientation:  # optional stage, off in the headline configuration
+        builder = builder.with_text_line_orientation_classification(models.get_blob("cls"))
+    ocr = builder.build()
     if args.engine is not None:
         ocr.det.set_engine(args.engine)
         ocr.rec.set_engine(args.engine)
+        if ocr.cls is not None:
+            ocr.cls.set_engine(args.engine)
     ctx = ocr.ctx
     B = args.batch
     pages = make_pages(rank, B)
@@ -325,6 +332,8 @@ def main():
     ap.add_argument("--engine", type=int, default=None, help="0 = fp32 SIMT engine, 1 = tcgen05 one kernel per layer, 2 = tcgen05 fused persistent blocks (default)")
     ap.add_argument("--ref-sample", type=int, default=4, help="pages per CPU-reference pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--line-orientation", action="store_true",
+                    help="also run the optional text-line orientation classifier (not the headline configuration)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
