@@ -4,11 +4,15 @@
 //   TextDetectionPredictor                oar-ocr-core/src/predictors/text_detection.rs:23-112
 //   TextRecognitionPredictor              oar-ocr-core/src/predictors/text_recognition.rs:19-110
 //   TextLineOrientationPredictor          oar-ocr-core/src/predictors/text_line_orientation.rs:18-105
+//   LayoutDetectionConfig / postprocess   oar-ocr-core/src/domain/tasks/layout_detection.rs:45-100,
+//                                         domain/adapters/layout_detection_adapter.rs:631-846 (host half of the row)
 //   OCRError                              oar-ocr-core/src/core/errors/types.rs:110-214
 // Errors are thrown as oar::OCRError (Rust returns Result<_, OCRError>).  No CPU fallback exists.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -239,6 +243,68 @@ class TextRecognitionPredictor {
   int32_t n_chars_;
   float thresh_;
 };
+
+// ---- layout detection, host half: LayoutDetectionAdapter::postprocess_pp_doclayout over oar_layout_postprocess ----
+enum class MergeBboxMode { Large = OAR_MERGE_LARGE, Small = OAR_MERGE_SMALL, Union = OAR_MERGE_UNION };
+struct LayoutDetectionElement { BoundingBox bbox; std::string element_type; float score; };
+struct LayoutDetectionConfig {  // tasks/layout_detection.rs:45-100
+  float score_threshold = 0.5f;
+  size_t max_elements = 100;
+  std::map<std::string, float> class_thresholds;           // empty = None
+  std::map<std::string, MergeBboxMode> class_merge_modes;  // empty = None
+  bool layout_nms = true;
+  int unclip_mode = OAR_UNCLIP_NONE;                       // OAR_UNCLIP_RATIO: (unclip_w, unclip_h)
+  float unclip_w = 1.0f, unclip_h = 1.0f;
+  std::map<size_t, std::pair<float, float>> class_unclip;  // OAR_UNCLIP_PER_CLASS
+};
+// predictions: [batch][num_boxes][feature_dim] rows [class_id, score, x1, y1, x2, y2, (order keys)]; src_wh = (w, h) of
+// every source page; class_labels[id] = label (LayoutModelConfig.class_labels).  Host only: no Context needed.
+inline std::vector<std::vector<LayoutDetectionElement>> postprocess_pp_doclayout(
+    const std::vector<float>& predictions, size_t batch, size_t num_boxes, size_t feature_dim,
+    const std::vector<std::pair<float, float>>& src_wh, const LayoutDetectionConfig& config,
+    const std::vector<std::string>& class_labels) {
+  if (config.max_elements < 1) throw OCRError("ConfigError", "max_elements must be at least 1");
+  if (src_wh.size() != batch || predictions.size() != batch * num_boxes * feature_dim)
+    throw OCRError("InvalidInput", "predictions / image shapes do not match the batch", OAR_E_INVALID);
+  const size_t nc = class_labels.size();
+  auto id_of = [&](const std::string& label) {
+    for (size_t i = 0; i < nc; ++i)
+      if (class_labels[i] == label) return (int32_t)i;
+    return (int32_t)-1;
+  };
+  std::vector<float> thr(nc, NAN), cu(2 * nc, NAN);
+  std::vector<int32_t> modes(nc, OAR_MERGE_UNSET);
+  for (const auto& kv : config.class_thresholds)
+    if (id_of(kv.first) >= 0) thr[id_of(kv.first)] = kv.second;
+  for (const auto& kv : config.class_merge_modes)
+    if (id_of(kv.first) >= 0) modes[id_of(kv.first)] = (int32_t)kv.second;
+  for (const auto& kv : config.class_unclip)
+    if (kv.first < nc) cu[2 * kv.first] = kv.second.first, cu[2 * kv.first + 1] = kv.second.second;
+  oar_layout_config c;
+  oar_layout_config_default(&c);
+  c.score_threshold = config.score_threshold, c.max_elements = (int32_t)config.max_elements;
+  c.layout_nms = config.layout_nms ? 1 : 0, c.num_classes = (int32_t)nc;
+  c.class_thresholds = config.class_thresholds.empty() ? nullptr : thr.data();
+  c.class_merge_modes = config.class_merge_modes.empty() ? nullptr : modes.data();
+  c.image_class_id = id_of("image"), c.formula_class_id = id_of("formula");
+  c.unclip_mode = config.unclip_mode, c.unclip_w = config.unclip_w, c.unclip_h = config.unclip_h;
+  c.class_unclip = cu.data();
+  std::vector<float> sw(batch), sh(batch), boxes(batch * config.max_elements * 4), scores(batch * config.max_elements);
+  std::vector<int32_t> classes(batch * config.max_elements), counts(batch);
+  for (size_t b = 0; b < batch; ++b) sw[b] = src_wh[b].first, sh[b] = src_wh[b].second;
+  check(oar_layout_postprocess(predictions.data(), (int32_t)batch, (int32_t)num_boxes, (int32_t)feature_dim, sw.data(),
+                               sh.data(), &c, boxes.data(), classes.data(), scores.data(), counts.data()));
+  std::vector<std::vector<LayoutDetectionElement>> out(batch);
+  for (size_t b = 0; b < batch; ++b)
+    for (int32_t k = 0; k < counts[b]; ++k) {
+      const size_t r = b * config.max_elements + (size_t)k;
+      const float* q = &boxes[r * 4];
+      BoundingBox bb{{Point{q[0], q[1]}, Point{q[2], q[1]}, Point{q[2], q[3]}, Point{q[0], q[3]}}};  // from_coords
+      const size_t cid = (size_t)classes[r];
+      out[b].push_back(LayoutDetectionElement{std::move(bb), cid < nc ? class_labels[cid] : "unknown", scores[r]});
+    }
+  return out;
+}
 
 class TextLineOrientationPredictor {
  public:

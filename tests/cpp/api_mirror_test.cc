@@ -65,6 +65,36 @@ int main(int argc, char** argv) {
     }
   }
 
+  // layout post-process through the mirror (host only): threshold, same-class NMS, page-sized "image" box, per-label
+  // threshold and merge mode resolved to class ids (layout_detection_adapter.rs:644-663), labels on the elements
+  {
+    const std::vector<std::string> labels = {"paragraph_title", "image", "text", "number", "abstract", "content",
+                                             "figure_title", "formula", "table"};
+    const std::vector<float> rows = {
+        2, 0.90f, 0.10f, 0.10f, 0.50f, 0.30f,   // text
+        2, 0.80f, 0.10f, 0.10f, 0.50f, 0.31f,   // near duplicate: suppressed
+        1, 0.95f, 0.00f, 0.00f, 1.00f, 1.00f,   // page-sized image: dropped
+        0, 0.45f, 0.12f, 0.12f, 0.30f, 0.20f,   // title inside the text box, below 0.5
+        8, 0.60f, 0.55f, 0.55f, 0.95f, 0.95f};  // table
+    oar::LayoutDetectionConfig lc;
+    auto els = oar::postprocess_pp_doclayout(rows, 1, 5, 6, {{1000.0f, 800.0f}}, lc, labels);
+    expect(els.size() == 1 && els[0].size() == 2 && els[0][0].element_type == "text" && els[0][1].element_type == "table" &&
+               els[0][0].bbox.points[0].x == 100.0f && els[0][0].bbox.points[2].x == 500.0f,
+           "layout defaults");
+    lc.class_thresholds["paragraph_title"] = 0.3f;
+    els = oar::postprocess_pp_doclayout(rows, 1, 5, 6, {{1000.0f, 800.0f}}, lc, labels);
+    // (NMS hands the survivors back in score order: text 0.90, table 0.60, title 0.45)
+    expect(els[0].size() == 3 && els[0][2].element_type == "paragraph_title", "layout per-label threshold");
+    lc.class_merge_modes["text"] = oar::MergeBboxMode::Large;
+    els = oar::postprocess_pp_doclayout(rows, 1, 5, 6, {{1000.0f, 800.0f}}, lc, labels);
+    expect(els[0].size() == 2 && els[0][1].element_type == "table", "layout Large merge removes the contained title");
+    try {
+      oar::postprocess_pp_doclayout(rows, 2, 5, 6, {{1000.0f, 800.0f}}, lc, labels);
+      expect(false, "layout batch mismatch rejected");
+    } catch (const oar::OCRError&) {
+    }
+  }
+
   bool have_gpu = true;
   try {
     oar::Context probe(0);
