@@ -16,7 +16,6 @@ converts between Python objects and flat buffers.  There is no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from dataclasses import dataclass, field
 
