@@ -527,10 +527,11 @@ def _hg_block(g: GraphBuilder, x, cin, mid, cout, layers, k, light, residual):
     return g.add(y, x) if residual else y
 
 
-def build_hgnetv2_l(seed: int = 42, return_idx=(3,)) -> bytes:
+def build_hgnetv2_l(seed: int = 42, return_idx=(3,), taps: list | None = None) -> bytes:
     """HGNetV2-L feature extractor (hgnetv2.rs: Embeddings :264-348, Stage :264-330, BasicLayer :161-262), BatchNorm
     folded into the conv biases, He-normal synthetic weights.  The graph's output is the last requested stage
-    (strides 4 / 8 / 16 / 32, 128 / 512 / 1024 / 2048 channels).  Spec + oracle only for now (KIND_FEAT)."""
+    (strides 4 / 8 / 16 / 32, 128 / 512 / 1024 / 2048 channels); `taps`, when given, receives the tensor id of every
+    stage output (a detector neck reads several of them).  Spec + oracle only for now (KIND_FEAT)."""
     g = GraphBuilder(KIND_FEAT, seed)
     g.base_gain = 0.7
     c0, c1, c2 = _HG_STEM
@@ -548,6 +549,8 @@ def build_hgnetv2_l(seed: int = 42, return_idx=(3,)) -> bytes:
             x = g.dwconv(x, 3, (2, 2), act=ACT_NONE)
         for bi in range(blocks):
             x = _hg_block(g, x, cin if bi == 0 else cout, mid, cout, layers, k, light, residual=bi != 0)
+        if taps is not None:
+            taps.append(x)
         if si == last:
             break
     return g.serialize()

@@ -1,0 +1,106 @@
+"""The oracle of the layout network (oracle-first): RT-DETR-L on torch-CPU (oracle/rtdetr.py).
+No CUDA counterpart yet and no reference outputs to pin it (PARITY UNPINNED, see the module header); these tests check
+the restated pieces against the reference's formulas / independent formulations and run the network end to end into the
+layout post-process that IS built (oar_layout_postprocess)."""
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def net():
+    from oracle.rtdetr import RTDetrL
+    return RTDetrL(seed=42)
+
+
+def test_anchors_follow_the_reference():
+    """model.rs:154-183: 0.05 * 2^level boxes on cell centres, logit space, invalid where a coordinate leaves
+    (0.01, 0.99); 80^2 + 40^2 + 20^2 = 8400 tokens at 640 x 640"""
+    from oracle.rtdetr import generate_anchors
+    a, v = generate_anchors([(80, 80), (40, 40), (20, 20)])
+    assert a.shape == (1, 8400, 4) and v.shape == (1, 8400, 1)
+    c = np.array([0.5 / 80, 0.5 / 80, 0.05, 0.05], np.float32)  # first cell: centre 0.00625 < 0.01 -> invalid
+    assert v[0, 0, 0] == 0 and a[0, 0, 0] == np.finfo(np.float32).max
+    c = np.array([1.5 / 80, 1.5 / 80, 0.05, 0.05], np.float32)
+    assert v[0, 81, 0] == 1 and np.allclose(a[0, 81].numpy(), np.log(c / (1 - c)), rtol=1e-6)
+    assert np.allclose(torch.sigmoid(a[0, 6400 + 41, 2:]).numpy(), 0.1, atol=1e-6)  # level 1: 0.05 * 2
+    assert int(v.sum()) == 78 * 78 + 40 * 40 + 20 * 20  # only the outer ring of the finest level is invalid
+
+
+def test_sine_position_embedding_layout():
+    """encoder.rs:179-216: [sin(y w), cos(y w), sin(x w), cos(x w)] with w_k = 10000^(-k / (dim/4))"""
+    from oracle.rtdetr import sine_position_embedding
+    p = sine_position_embedding(3, 5, 256)[0].numpy()
+    assert p.shape == (15, 256)
+    y, x, k = 2, 3, 7
+    om = 1.0 / 10000.0 ** (k / 64)
+    row = p[y * 5 + x]
+    assert np.allclose([row[k], row[64 + k], row[128 + k], row[192 + k]],
+                       [np.sin(y * om), np.cos(y * om), np.sin(x * om), np.cos(x * om)], atol=1e-6)
+
+
+def test_deformable_attention_equals_a_naive_gather():
+    """decoder.rs:337-470 spelled out: pixel = loc * size - 0.5, four corners, a corner counts only inside the map"""
+    from oracle.rtdetr import POINTS, deformable_attention
+    rng = np.random.default_rng(0)
+    B, Q, heads, hd = 2, 5, 2, 3
+    shapes = [(4, 6), (2, 3), (1, 2)]
+    N = sum(h * w for h, w in shapes)
+    value = torch.from_numpy(rng.standard_normal((B, N, heads, hd)).astype(np.float32))
+    loc = torch.from_numpy(rng.uniform(-0.2, 1.2, (B, Q, heads, 3, POINTS, 2)).astype(np.float32))
+    wts = torch.softmax(torch.from_numpy(rng.standard_normal((B, Q, heads, 3 * POINTS)).astype(np.float32)), -1)
+    wts = wts.reshape(B, Q, heads, 3, POINTS)
+    got = deformable_attention(value, shapes, loc, wts).numpy().reshape(B, Q, heads, hd)
+    want = np.zeros((B, Q, heads, hd), np.float64)
+    off = 0
+    for lvl, (h, w) in enumerate(shapes):
+        for b in range(B):
+            for q in range(Q):
+                for hh in range(heads):
+                    for p in range(POINTS):
+                        px = float(loc[b, q, hh, lvl, p, 0]) * w - 0.5
+                        py = float(loc[b, q, hh, lvl, p, 1]) * h - 0.5
+                        x0, y0 = int(np.floor(px)), int(np.floor(py))
+                        for dx in (0, 1):
+                            for dy in (0, 1):
+                                xi, yi = x0 + dx, y0 + dy
+                                if 0 <= xi < w and 0 <= yi < h:
+                                    cw = (px - x0 if dx else 1 - (px - x0)) * (py - y0 if dy else 1 - (py - y0))
+                                    want[b, q, hh] += cw * float(wts[b, q, hh, lvl, p]) * \
+                                        value[b, off + yi * w + xi, hh].numpy()
+        off += h * w
+    assert np.abs(got - want).max() < 1e-5
+
+
+def test_forward_shapes_and_batch_independence(net):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 3, 256, 320)).astype(np.float32)
+    logits, boxes = net.forward(x)
+    assert logits.shape == (2, 300, 23) and boxes.shape == (2, 300, 4)
+    assert np.isfinite(logits).all() and boxes.min() > 0.0 and boxes.max() < 1.0
+    l0, b0 = net.forward(x[:1])
+    assert np.abs(l0[0] - logits[0]).max() < 1e-4 and np.abs(b0[0] - boxes[0]).max() < 1e-5  # no cross-image coupling
+    l1, b1 = net.forward(x)
+    assert np.array_equal(l1, logits) and np.array_equal(b1, boxes)  # deterministic
+
+
+def test_network_rows_through_the_layout_postprocess(net, built_lib):
+    """end to end on the CPU tier: oracle network -> exported-model rows -> oar_layout_postprocess (product, host code)
+    == the oracle restatement of the adapter's post-process, bit for bit"""
+    from oracle import cpu
+    from oar_ocr_b200 import ffi
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 3, 320, 320)).astype(np.float32)
+    sizes = [(1000.0, 800.0), (640.0, 640.0)]
+    rows = net.rows(x, sizes)
+    assert rows.shape == (2, 300, 6)
+    assert (np.diff(rows[:, :, 1], axis=1) <= 0).all()  # top-300 comes out in score order
+    assert rows[:, :, 0].min() >= 0 and rows[:, :, 0].max() < 23
+    kw = dict(score_threshold=0.5, image_class_id=1, formula_class_id=7, class_merge_modes={0: 0, 2: 2, 7: 0})
+    got = ffi.layout_postprocess(rows, sizes, 23, **kw)
+    for b, (w, h) in enumerate(sizes):
+        ob, oc, os_ = cpu.layout_postprocess(rows[b], w, h, 23, **kw)
+        gb, gc, gs = got[b]
+        assert gc.tolist() == oc.tolist() and np.array_equal(gb, ob) and np.array_equal(gs, os_)
+        assert (gb[:, 0] >= 0).all() and (gb[:, 2] <= w).all() and (gb[:, 3] <= h).all() and len(gc) <= 100
+    assert sum(len(g[1]) for g in got) > 0
