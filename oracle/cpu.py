@@ -350,3 +350,32 @@ def layout_postprocess(pred, src_w, src_h, num_classes, score_threshold=0.5, max
         formula_class_id, mode, C.c_float(uw), C.c_float(uh), f32p(cu) if cu is not None else None, f32p(ob), i32p(oc),
         f32p(os_))
     return ob[:m].copy(), oc[:m].copy(), os_[:m].copy()
+
+
+FILTERS = {"triangle": 0, "catmullrom": 1, "lanczos3": 2}
+
+
+def resize_filter(img: np.ndarray, nw: int, nh: int, filter: str = "catmullrom") -> np.ndarray:
+    """image::imageops::resize / DynamicImage::resize_exact with FilterType::{Triangle, CatmullRom, Lanczos3}"""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, _ = img.shape
+    out = np.empty((nh, nw, 3), np.uint8)
+    lib().oracle_resize_filter(u8p(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(nw), C.c_uint32(nh), u8p(out),
+                               FILTERS[filter])
+    return out
+
+
+def layout_preprocess(images, image_shape=(640, 640)):
+    """ScaleAwareDetectorModel::preprocess with ScaleAwareDetectorPreprocessConfig::pp_doclayout
+    (scale_aware_detector.rs:66-80, 195-229; resize_image_type1 with keep_ratio = false, resize_detection.rs:337-366):
+    resize_exact to image_shape (h, w) with CatmullRom, scale 1/255, mean 0 / std 1, RGB, CHW.
+    Returns (tensor [B,3,h,w], scale factors [B,2] = resized / original (h, w))."""
+    th, tw = image_shape
+    a, b = norm_coeffs(DET_SCALE, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    out, scale = [], []
+    for img in images:
+        h, w, _ = img.shape
+        r = img if (h, w) == (th, tw) else resize_filter(img, tw, th, "catmullrom")
+        out.append(normalize(r, a, b, (0, 1, 2), "chw"))
+        scale.append((np.float32(th) / np.float32(h), np.float32(tw) / np.float32(w)))
+    return np.stack(out), np.array(scale, np.float32)

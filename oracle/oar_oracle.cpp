@@ -84,7 +84,37 @@ inline float tri_kernel(float x) {
   return a < 1.0f ? 1.0f - a : 0.0f;
 }
 
+// The other filters the reference uses (FilterType::CatmullRom for the PP-DocLayout detectors, Lanczos3 for PicoDet:
+// scale_aware_detector.rs:52-80): same two-pass sampler, other kernel and support (image 0.25 sample.rs, EXT).
+inline float bc_cubic_spline(float x, float b, float c) {
+  float a = std::fabs(x);
+  float k;
+  if (a < 1.0f)
+    k = (12.0f - 9.0f * b - 6.0f * c) * (a * a * a) + (-18.0f + 12.0f * b + 6.0f * c) * (a * a) + (6.0f - 2.0f * b);
+  else if (a < 2.0f)
+    k = (-b - 6.0f * c) * (a * a * a) + (6.0f * b + 30.0f * c) * (a * a) + (-12.0f * b - 48.0f * c) * a +
+        (8.0f * b + 24.0f * c);
+  else
+    k = 0.0f;
+  return k / 6.0f;
+}
+inline float sinc_f(float t) {
+  float a = t * 3.14159265358979323846f;
+  return t == 0.0f ? 1.0f : std::sin(a) / a;
+}
+inline float filter_kernel(int filter, float x) {
+  if (filter == 1) return bc_cubic_spline(x, 0.0f, 0.5f);                          // CatmullRom
+  if (filter == 2) return std::fabs(x) < 3.0f ? sinc_f(x) * sinc_f(x / 3.0f) : 0.0f;  // Lanczos3
+  return tri_kernel(x);
+}
+inline float filter_support(int filter) { return filter == 1 ? 2.0f : (filter == 2 ? 3.0f : 1.0f); }
+
+void resize_filter_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, uint8_t* dst, int filter);
 void resize_triangle_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, uint8_t* dst) {
+  resize_filter_rgb(src, w, h, nw, nh, dst, 0);
+}
+
+void resize_filter_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, uint8_t* dst, int filter) {
   if (nw == w && nh == h) {
     std::memcpy(dst, src, (size_t)w * h * 3);
     return;
@@ -94,7 +124,7 @@ void resize_triangle_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw
   {
     float ratio = (float)h / (float)nh;
     float sratio = ratio < 1.0f ? 1.0f : ratio;
-    float support = 1.0f * sratio;
+    float support = filter_support(filter) * sratio;
     std::vector<float> ws;
     for (uint32_t oy = 0; oy < nh; ++oy) {
       float in = ((float)oy + 0.5f) * ratio;
@@ -106,7 +136,7 @@ void resize_triangle_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw
       ws.clear();
       float sum = 0.0f;
       for (int64_t i = left; i < right; ++i) {
-        float wgt = tri_kernel(((float)i - in) / sratio);
+        float wgt = filter_kernel(filter, ((float)i - in) / sratio);
         ws.push_back(wgt);
         sum += wgt;
       }
@@ -130,7 +160,7 @@ void resize_triangle_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw
   {
     float ratio = (float)w / (float)nw;
     float sratio = ratio < 1.0f ? 1.0f : ratio;
-    float support = 1.0f * sratio;
+    float support = filter_support(filter) * sratio;
     std::vector<float> ws;
     for (uint32_t ox = 0; ox < nw; ++ox) {
       float in = ((float)ox + 0.5f) * ratio;
@@ -142,7 +172,7 @@ void resize_triangle_rgb(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw
       ws.clear();
       float sum = 0.0f;
       for (int64_t i = left; i < right; ++i) {
-        float wgt = tri_kernel(((float)i - in) / sratio);
+        float wgt = filter_kernel(filter, ((float)i - in) / sratio);
         ws.push_back(wgt);
         sum += wgt;
       }
@@ -757,6 +787,11 @@ extern "C" {
 void oracle_det_resize_dims(uint32_t h, uint32_t w, uint32_t limit, int limit_type, uint32_t max_side, uint32_t* oh,
                             uint32_t* ow) {
   det_resize_dims(h, w, limit, limit_type, max_side, oh, ow);
+}
+
+// filter: 0 Triangle, 1 CatmullRom, 2 Lanczos3
+void oracle_resize_filter(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, uint8_t* dst, int filter) {
+  resize_filter_rgb(src, w, h, nw, nh, dst, filter);
 }
 
 void oracle_resize_triangle(const uint8_t* src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, uint8_t* dst) {

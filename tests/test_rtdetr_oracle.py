@@ -104,3 +104,44 @@ def test_network_rows_through_the_layout_postprocess(net, built_lib):
         assert gc.tolist() == oc.tolist() and np.array_equal(gb, ob) and np.array_equal(gs, os_)
         assert (gb[:, 0] >= 0).all() and (gb[:, 2] <= w).all() and (gb[:, 3] <= h).all() and len(gc) <= 100
     assert sum(len(g[1]) for g in got) > 0
+
+
+def test_catmullrom_and_lanczos_resize_cross_checks():
+    """image::imageops::resize with the filters of the layout detectors (scale_aware_detector.rs:52-80), restated from
+    the crate's published sampler (unpinned: the crate is not vendored).  Cross-checks: CatmullRom is torch's
+    antialiased bicubic (Keys a = -0.5) to within 2 grey levels on a smooth image, both filters keep a constant
+    image constant (normalised weights) and a same-size resize is the identity"""
+    import torch.nn.functional as F
+    from oracle import cpu
+    yy, xx = np.mgrid[0:90, 0:130].astype(np.float32)
+    img = np.stack([127 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 40 + xx, 250 - 2 * yy], -1).clip(0, 255).astype(np.uint8)
+    for (nw, nh) in ((64, 48), (200, 150)):
+        got = cpu.resize_filter(img, nw, nh, "catmullrom").astype(np.float32)
+        t = torch.from_numpy(img.astype(np.float32)).permute(2, 0, 1)[None]
+        want = F.interpolate(t, size=(nh, nw), mode="bicubic", antialias=True, align_corners=False)[0].permute(1, 2, 0)
+        assert np.abs(got - want.clamp(0, 255).numpy()).max() <= 2.0
+    flat = np.full((37, 53, 3), 93, np.uint8)
+    for f in ("triangle", "catmullrom", "lanczos3"):
+        assert (cpu.resize_filter(flat, 80, 21, f) == 93).all()
+        assert np.array_equal(cpu.resize_filter(img, 130, 90, f), img)
+    # Lanczos3 overshoots at a step edge (negative lobes), Triangle cannot
+    step = np.zeros((8, 64, 3), np.uint8)
+    step[:, 32:] = 200
+    assert cpu.resize_filter(step, 256, 8, "lanczos3").max() > 200 and cpu.resize_filter(step, 256, 8, "triangle").max() == 200
+
+
+def test_oracle_chain_for_config4(net, built_lib):
+    """BASELINE.json configs[4] end to end on the CPU oracle at a reduced size: pages -> layout preprocess (CatmullRom to
+    a fixed square, 1/255, RGB) -> RT-DETR-L -> rows -> post-process; the product's host half agrees with the oracle's"""
+    from oracle import cpu
+    from oar_ocr_b200 import ffi, synth
+    pages = [synth.page(5, 480), synth.page(6, 320)[:200]]
+    x, scale = cpu.layout_preprocess(pages, (256, 256))
+    assert x.shape == (2, 3, 256, 256) and 0.0 <= x.min() and x.max() <= 1.0
+    assert np.allclose(scale, [[256 / 480, 256 / 480], [256 / 200, 256 / 320]])
+    sizes = [(float(p.shape[1]), float(p.shape[0])) for p in pages]
+    rows = net.rows(x, sizes)
+    got = ffi.layout_postprocess(rows, sizes, 23, score_threshold=0.3, image_class_id=1, formula_class_id=7)
+    for b, (w, h) in enumerate(sizes):
+        ob, oc, os_ = cpu.layout_postprocess(rows[b], w, h, 23, score_threshold=0.3, image_class_id=1, formula_class_id=7)
+        assert got[b][1].tolist() == oc.tolist() and np.array_equal(got[b][0], ob) and np.array_equal(got[b][2], os_)
