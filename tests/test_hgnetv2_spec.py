@@ -67,13 +67,3 @@ def test_new_ops_in_the_oracle():
     p = np.pad(x, ((0, 0), (0, 0), (0, 1), (0, 1)))
     want = np.maximum.reduce([p[:, :, :-1, :-1], p[:, :, 1:, :-1], p[:, :, :-1, 1:], p[:, :, 1:, 1:]])
     assert y.shape == x.shape and np.array_equal(y, want)
-
-
-@pytest.mark.gpu
-def test_engine_does_not_pretend_to_run_it(ctx):
-    """the CUDA library refuses the backbone blob outright (unknown model kind, checked in the blob header before
-    anything touches the device) instead of falling back to anything"""
-    from oar_ocr_b200 import ffi, models
-    with pytest.raises(ffi.OCRError) as e:
-        ffi.Model(ctx, models.build_hgnetv2_l(return_idx=(0,)))
-    assert e.value.code == ffi.OAR_E_MODEL and "unknown model kind" in str(e.value)

@@ -39,3 +39,13 @@ def test_config0_single_640_detection(ctx, det_blob):
     for d, b, s in zip(got, boxes, scores):
         assert np.array_equal(d.bbox.points, b)
         assert abs(d.score - float(s)) <= LOGIT_TOL
+
+
+@pytest.mark.gpu
+def test_engine_refuses_spec_only_graphs(ctx):
+    """the CUDA library refuses the backbone blob outright (unknown model kind, checked in the blob header before
+    anything touches the device) instead of falling back to anything"""
+    from oar_ocr_b200 import ffi, models
+    with pytest.raises(ffi.OCRError) as e:
+        ffi.Model(ctx, models.build_hgnetv2_l(return_idx=(0,)))
+    assert e.value.code == ffi.OAR_E_MODEL and "unknown model kind" in str(e.value)
