@@ -41,8 +41,12 @@ OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL
 # Ops the HGNetV2 stem needs.  Executed by the oracle (oracle/net.py) and exported / imported by
 # onnx_io; csrc/engine.cu rejects them ("unknown op type") until their kernels exist -- no silent fallback.
 OP_PAD, OP_MAXPOOL = 12, 13
+# OP_TOKENS: copies a [B,H,W,C] map as H*W token rows into rows [p[0], p[0] + H*W) of a [B,1,p[1],C] sequence (the
+# decoder memory of the layout detector is the concatenation of three flattened maps).  Spec + oracle only so far.
+OP_TOKENS = 14
 # activations
 ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID = range(6)
+ACT_GELU = 6  # exact (erf) GELU: the AIFI feed-forward of the layout detector; oracle / spec only so far
 
 
 @dataclass
@@ -159,23 +163,30 @@ class GraphBuilder:
         self.ops.append(Op(OP_MAXPOOL, x, -1, out, [k[0], k[1], s[0], s[1]] + [0] * 8))
         return out
 
-    def layernorm(self, x, eps):
+    def layernorm(self, x, eps, g=None, b=None):
         c = self.channels[x]
-        g = (1.0 + self.small((c,), 0.02)).astype(np.float32)
-        b = self.small((c,), 0.02)
+        g = (1.0 + self.small((c,), 0.02)).astype(np.float32) if g is None else g
+        b = self.small((c,), 0.02) if b is None else b
         out = self.new_tensor(c)
         self.ops.append(Op(OP_LAYERNORM, x, -1, out, [c] + [0] * 11, [eps, 0.0, 0.0, 0.0], [g, b]))
         return out
 
-    def attn(self, x, heads):
+    def attn(self, x, heads, wqkv=None, bqkv=None, wp=None, bp=None, positions=False):
+        """positions=True (p[2] = 1): the 2-D sin/cos position embedding of the map (temperature 10000, layout
+        [sin y, cos y, sin x, cos x], oar-ocr-vl/src/models/pp_doclayout/encoder.rs:179-216) is added to the inputs of
+        the q and k projections, not to v -- the AIFI layer of the layout detector.  Spec + oracle only so far."""
         c = self.channels[x]
-        wqkv = self.he((3 * c, c), c, 0.7)
-        bqkv = self.small((3 * c,))
-        wp = self.he((c, c), c, 0.7)
-        bp = self.small((c,))
+        wqkv = self.he((3 * c, c), c, 0.7) if wqkv is None else wqkv
+        bqkv = self.small((3 * c,)) if bqkv is None else bqkv
+        wp = self.he((c, c), c, 0.7) if wp is None else wp
+        bp = self.small((c,)) if bp is None else bp
         out = self.new_tensor(c)
-        self.ops.append(Op(OP_ATTN, x, -1, out, [c, heads] + [0] * 10, [float((c // heads) ** -0.5), 0, 0, 0],
-                           [wqkv, bqkv, wp, bp]))
+        self.ops.append(Op(OP_ATTN, x, -1, out, [c, heads, 1 if positions else 0] + [0] * 9,
+                           [float((c // heads) ** -0.5), 0, 0, 0], [wqkv, bqkv, wp, bp]))
+        return out
+
+    def tokens(self, x, out, row_off, rows_total):
+        self.ops.append(Op(OP_TOKENS, x, -1, out, [row_off, rows_total] + [0] * 10))
         return out
 
     def ctc_head(self, x, vocab, w, b):
@@ -533,6 +544,11 @@ def build_hgnetv2_l(seed: int = 42, return_idx=(3,), taps: list | None = None) -
     (strides 4 / 8 / 16 / 32, 128 / 512 / 1024 / 2048 channels); `taps`, when given, receives the tensor id of every
     stage output (a detector neck reads several of them).  Spec + oracle only for now (KIND_FEAT)."""
     g = GraphBuilder(KIND_FEAT, seed)
+    _hgnetv2_l_into(g, return_idx, taps)
+    return g.serialize()
+
+
+def _hgnetv2_l_into(g: GraphBuilder, return_idx=(3,), taps: list | None = None):
     g.base_gain = 0.7
     c0, c1, c2 = _HG_STEM
     x = g.conv(0, c1, (3, 3), (2, 2), act=ACT_RELU)                       # stem1
@@ -553,6 +569,77 @@ def build_hgnetv2_l(seed: int = 42, return_idx=(3,), taps: list | None = None) -
             taps.append(x)
         if si == last:
             break
+    return x
+
+
+def build_layout_encoder(weights: dict, seed: int = 42, shapes_hw=None) -> bytes:
+    """Backbone + hybrid encoder + decoder-input projection of the layout detector (RT-DETR-L) as ONE OARG graph whose
+    output is the decoder memory [B, 1, sum(H_l W_l), 256] (8400 tokens at 640 x 640): HGNetV2-L -> 1x1 projections ->
+    AIFI on the stride-32 map -> CCFM (top-down then bottom-up, CSPRep blocks) -> 1x1 projections -> OP_TOKENS.
+    `weights` is the detector's weight table by name (the oracle's, oracle/rtdetr.py documents the names; this module
+    never imports the oracle); the backbone is regenerated from `seed` exactly as build_hgnetv2_l does.  The RepVGG
+    3x3 + 1x1 branches are merged into one 3x3 convolution (their sum before the activation is one convolution).
+    `shapes_hw`: the three map sizes (strides 8 / 16 / 32) of the input the graph will see, needed only to lay the
+    token rows out.  Spec + oracle only: ACT_GELU, OP_ATTN with positions, OP_TOKENS have no CUDA kernels yet."""
+    W = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    g = GraphBuilder(KIND_FEAT, seed)
+    taps = []
+    _hgnetv2_l_into(g, (3,), taps)
+    d = 256
+
+    def cw(name):  # [cout, cin, kh, kw] -> [cout, kh, kw, cin]
+        return np.ascontiguousarray(W[name + ".w"].transpose(0, 2, 3, 1)), W[name + ".b"]
+
+    def conv(x, name, k=1, s=1, act=ACT_SWISH, **kw):
+        w, b = cw(name)
+        return g.conv(x, w.shape[0], (k, k), (s, s), act=act, w=w, b=b, **kw)
+
+    def lin_as_conv(x, name, act=ACT_NONE):
+        w = W[name + ".w"]
+        return g.conv(x, w.shape[0], (1, 1), act=act, w=np.ascontiguousarray(w[:, None, None, :]), b=W[name + ".b"])
+
+    def csp(x, name):
+        y = conv(x, name + ".conv1")
+        for i in range(3):
+            w3, b3 = cw(f"{name}.rep{i}.c3")
+            w1, b1 = cw(f"{name}.rep{i}.c1")
+            w3 = w3.copy()
+            w3[:, 1, 1, :] += w1[:, 0, 0, :]
+            y = g.conv(y, d, (3, 3), act=ACT_SWISH, w=w3, b=b3 + b1)
+        return g.add(y, conv(x, name + ".conv2"))
+
+    feats = [conv(taps[l + 1], f"input_proj{l}", act=ACT_NONE) for l in range(3)]
+    # AIFI: post-norm transformer layer with positions on q / k
+    t = feats[2]
+    wqkv = np.concatenate([W["aifi.q.w"], W["aifi.k.w"], W["aifi.v.w"]], 0)
+    bqkv = np.concatenate([W["aifi.q.b"], W["aifi.k.b"], W["aifi.v.b"]], 0)
+    a = g.attn(t, 8, wqkv=wqkv, bqkv=bqkv, wp=W["aifi.o.w"], bp=W["aifi.o.b"], positions=True)
+    t = g.layernorm(g.add(t, a), 1e-5, W["aifi.ln1.g"], W["aifi.ln1.b"])
+    f = lin_as_conv(lin_as_conv(t, "aifi.fc1", ACT_GELU), "aifi.fc2")
+    feats[2] = g.layernorm(g.add(t, f), 1e-5, W["aifi.ln2.g"], W["aifi.ln2.b"])
+    # CCFM
+    fpn = [feats[2]]
+    for i in range(2):
+        top = conv(fpn[-1], f"lateral{i}")
+        fpn[-1] = top
+        cat = g.new_tensor(2 * d)
+        g.upsample_into(top, 2, cat, 0, 2 * d)
+        g.upsample_into(feats[1 - i], 1, cat, d, 2 * d)
+        fpn.append(csp(cat, f"fpn{i}"))
+    fpn.reverse()
+    pan = [fpn[0]]
+    for i in range(2):
+        cat = g.new_tensor(2 * d)
+        conv(pan[-1], f"down{i}", 3, 2, out=cat, c_off=0, c_total=2 * d)
+        g.upsample_into(fpn[i + 1], 1, cat, d, 2 * d)
+        pan.append(csp(cat, f"pan{i}"))
+    # decoder memory
+    total = sum(h * w for h, w in shapes_hw)
+    mem = g.new_tensor(d)
+    off = 0
+    for l, f in enumerate(pan):
+        g.tokens(conv(f, f"dec_input_proj{l}", act=ACT_NONE), mem, off, total)
+        off += shapes_hw[l][0] * shapes_hw[l][1]
     return g.serialize()
 
 

@@ -237,6 +237,8 @@ def export_onnx(blob: bytes) -> bytes:
         return name_of[tid]
 
     def emit_act(x, act, f):
+        if act not in _ACT_NODES and act not in (M.ACT_NONE, M.ACT_SWISH, M.ACT_HSIGMOID):
+            raise OCRError("ModelLoad", f"cannot export activation {act} (spec-only so far)")
         if act in _ACT_NODES:
             y = fresh("act")
             nodes.append(node(_ACT_NODES[act], [x], [y]))
@@ -353,6 +355,8 @@ def export_onnx(blob: bytes) -> bytes:
             name_of[op["out"]] = y
         elif t == M.OP_ATTN:
             c, heads = p[:2]
+            if p[2]:
+                raise OCRError("ModelLoad", "cannot export attention with positions on q / k (spec-only so far)")
             d = c // heads
             names = [fresh("attn") for _ in range(20)]
             (t0, s0, qm, qa, q5, qt, q, k, v, qs, kt, sc, sm, av, at, ar, pm, pa, r4, y) = names

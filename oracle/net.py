@@ -22,6 +22,7 @@ import torch.nn.functional as F
 OP_CONV, OP_DWCONV, OP_SE, OP_ADD, OP_UPADD, OP_UPSAMPLE, OP_DECONV2, OP_AVGPOOL, OP_LAYERNORM, OP_ATTN, \
     OP_CTC_HEAD = range(1, 12)
 OP_PAD, OP_MAXPOOL = 12, 13  # HGNetV2 stem (models.py): zero padding, max pool
+OP_TOKENS = 14  # a map's pixels as token rows of a sequence (decoder memory of the layout detector)
 
 
 def parse(blob: bytes):
@@ -52,6 +53,8 @@ def _act(x, a):
         return torch.sigmoid(x)
     if a == 5:
         return F.hardsigmoid(x)
+    if a == 6:  # exact GELU (AIFI feed-forward of the layout detector)
+        return F.gelu(x)
     raise ValueError(a)
 
 
@@ -119,6 +122,12 @@ class OracleNet:
                 t[op["out"]] = F.pad(a, (p[1], p[3], p[0], p[2]))  # (left, right, top, bottom)
             elif ty == OP_MAXPOOL:
                 t[op["out"]] = F.max_pool2d(a, (p[0], p[1]), (p[2], p[3]))
+            elif ty == OP_TOKENS:
+                B, C_, H, W = a.shape
+                o = op["out"]
+                if o not in t:
+                    t[o] = torch.zeros((B, C_, 1, p[1]), dtype=a.dtype)
+                t[o][:, :, 0, p[0]:p[0] + H * W] = a.reshape(B, C_, H * W)
             elif ty == OP_LAYERNORM:
                 c = p[0]
                 y = F.layer_norm(a.permute(0, 2, 3, 1), (c,), self._w(op, 0, (c,)), self._w(op, 1, (c,)), f[0])
@@ -127,7 +136,13 @@ class OracleNet:
                 c, heads = p[:2]
                 B, _, H, W = a.shape
                 x2 = a.permute(0, 2, 3, 1).reshape(B, H * W, c)
-                qkv = F.linear(x2, self._w(op, 0, (3 * c, c)), self._w(op, 1, (3 * c,)))
+                if p[2] == 1:  # positions on the q / k inputs only (encoder.rs:34-79, 179-216)
+                    from .rtdetr import sine_position_embedding
+                    wq, bq = self._w(op, 0, (3 * c, c)), self._w(op, 1, (3 * c,))
+                    xp = x2 + sine_position_embedding(H, W, c)
+                    qkv = torch.cat([F.linear(xp, wq[:2 * c], bq[:2 * c]), F.linear(x2, wq[2 * c:], bq[2 * c:])], -1)
+                else:
+                    qkv = F.linear(x2, self._w(op, 0, (3 * c, c)), self._w(op, 1, (3 * c,)))
                 qkv = qkv.reshape(B, H * W, 3, heads, c // heads).permute(2, 0, 3, 1, 4)
                 q, k, v = qkv[0] * f[0], qkv[1], qkv[2]
                 att = torch.softmax(q @ k.transpose(-1, -2), dim=-1)

@@ -178,6 +178,13 @@ class RTDetrL:
     @torch.no_grad()
     def forward(self, x: np.ndarray):
         """x: f32 [B,3,H,W] (H, W multiples of 32).  Returns (logits [B,300,C], boxes [B,300,4] cxcywh in [0,1])."""
+        source, shapes = self.encode(x)
+        return self.decode(source, shapes)
+
+    @torch.no_grad()
+    def encode(self, x: np.ndarray):
+        """backbone + hybrid encoder + decoder-input projections: the decoder memory [B, sum(H_l W_l), 256] and the
+        three map sizes.  models.build_layout_encoder states the same computation as an OARG layer list."""
         cap = {}
         self.backbone.forward(x, capture=cap)
         feats = [self._conv(f"input_proj{l}", cap[self.taps[l + 1]], act=False) for l in range(3)]
@@ -206,7 +213,11 @@ class RTDetrL:
             s = self._conv(f"dec_input_proj{l}", f, act=False)
             shapes.append((s.shape[2], s.shape[3]))
             flat.append(s.flatten(2).transpose(1, 2))
-        source = torch.cat(flat, 1)
+        return torch.cat(flat, 1), shapes
+
+    @torch.no_grad()
+    def decode(self, source, shapes):
+        B = source.shape[0]
         anchors, valid = generate_anchors(shapes)
         memory = self._ln("enc_output_ln", self._lin("enc_output", source * valid))
         enc_class = self._lin("enc_score", memory)

@@ -145,3 +145,34 @@ def test_oracle_chain_for_config4(net, built_lib):
     for b, (w, h) in enumerate(sizes):
         ob, oc, os_ = cpu.layout_postprocess(rows[b], w, h, 23, score_threshold=0.3, image_class_id=1, formula_class_id=7)
         assert got[b][1].tolist() == oc.tolist() and np.array_equal(got[b][0], ob) and np.array_equal(got[b][2], os_)
+
+
+def test_encoder_as_oarg_layer_list_equals_the_oracle(net):
+    """models.build_layout_encoder states backbone + hybrid encoder + decoder-input projections as ONE OARG graph
+    (the spec the CUDA executor gets next round; new pieces: exact GELU, attention with 2-D positions on q / k, the
+    token-rows op, RepVGG branches merged into one 3x3).  Executed by oracle/net.py it reproduces oracle/rtdetr.py's
+    decoder memory."""
+    from oar_ocr_b200 import models
+    from oracle.net import OracleNet, parse
+    x = np.random.default_rng(3).standard_normal((2, 3, 192, 256)).astype(np.float32)
+    want, shapes = net.encode(x)
+    assert shapes == [(24, 32), (12, 16), (6, 8)]
+    blob = models.build_layout_encoder({k: v.numpy() for k, v in net.w.items()}, seed=42, shapes_hw=shapes)
+    kind, _, ops, _ = parse(blob)
+    types = [o["type"] for o in ops]
+    assert kind == models.KIND_FEAT and types.count(models.OP_TOKENS) == 3 and types.count(models.OP_ATTN) == 1
+    got = OracleNet(blob).forward(x)  # [B, 256, 1, N]
+    assert got.shape == (2, 256, 1, want.shape[1])
+    got = got[:, :, 0].transpose(0, 2, 1)
+    scale = np.abs(want.numpy()).max()
+    assert np.abs(got - want.numpy()).max() <= 2e-5 * max(scale, 1.0)
+
+
+def test_spec_only_ops_do_not_export_silently(net):
+    """the ONNX exporter refuses what it cannot express yet instead of dropping it (positions, GELU, token rows)"""
+    from oar_ocr_b200 import models, onnx_io
+    from oar_ocr_b200.ffi import OCRError
+    blob = models.build_layout_encoder({k: v.numpy() for k, v in net.w.items()}, seed=42,
+                                       shapes_hw=[(8, 8), (4, 4), (2, 2)])
+    with pytest.raises(OCRError):
+        onnx_io.export_onnx(blob)
