@@ -63,6 +63,13 @@ def layers(blob, B, H, W):
         elif t == models.OP_MAXPOOL:
             oh, ow = (h - p[0]) // p[2] + 1, (w - p[1]) // p[3] + 1
             out_c = c
+        elif t == models.OP_TOKENS:
+            oh, ow = 1, p[1]
+            out_c = c
+            shape[op["out"]] = (oh, ow, c)
+            rows.append(dict(op=i, type=NAMES.get(t, str(t)), in_hwc=[h, w, c], out_hwc=[oh, ow, c], gflop=0.0,
+                             mb_in=B * h * w * c * 4 / 1e6, mb_out=B * h * w * c * 4 / 1e6))
+            continue
         elif t == models.OP_ATTN:
             T = h * w
             flops = 2 * T * c * 3 * c + 2 * T * c * c + 4 * T * T * c
@@ -92,9 +99,19 @@ def main():
     # hgnetv2_l = the backbone of PP-DocLayout-L (BASELINE.json configs[4]: batch 64; the reference resizes every page
     # to 640 x 640 before the network) -- spec + oracle only so far
     for kind, (B, H, W) in (("det", (32, 960, 960)), ("rec", (256, 48, 320)), ("cls", (256, 80, 160)),
-                            ("hgnetv2_l", (64, 640, 640)), ("rec_server", (256, 48, 320))):
-        blob = models.build_hgnetv2_l() if kind == "hgnetv2_l" else (
-            models.build_rec_server() if kind == "rec_server" else models.get_blob(kind))
+                            ("hgnetv2_l", (64, 640, 640)), ("rec_server", (256, 48, 320)),
+                            ("layout_encoder", (64, 640, 640))):
+        if kind == "hgnetv2_l":
+            blob = models.build_hgnetv2_l()
+        elif kind == "rec_server":
+            blob = models.build_rec_server()
+        elif kind == "layout_encoder":
+            # backbone + hybrid encoder + decoder-input projections of RT-DETR-L (weights from the oracle's table)
+            from oracle.rtdetr import RTDetrL
+            blob = models.build_layout_encoder({k: v.numpy() for k, v in RTDetrL().w.items()},
+                                               shapes_hw=[(H // 8, W // 8), (H // 16, W // 16), (H // 32, W // 32)])
+        else:
+            blob = models.get_blob(kind)
         rows, saved = layers(blob, B, H, W)
         tot_f = sum(r["gflop"] for r in rows)
         tot_b = sum(r["mb_in"] + r["mb_out"] for r in rows)

@@ -146,6 +146,10 @@ def test_roofline_layers_match_survey_estimates():
     # the optional line-orientation classifier (PP-LCNet x1.0 at 80 x 160 with the width kept after the stem)
     assert committed["cls"]["gflop_per_item"] == fresh["cls"]["gflop_per_item"]
     assert 0.4 < fresh["cls"]["gflop_per_item"] < 0.8
+    # spec-only graphs of the next rows: in sync, and the layout encoder graph carries ~93 of RT-DETR-L's 110 GFLOPs
+    for kind in ("hgnetv2_l", "rec_server", "layout_encoder"):
+        assert committed[kind]["gflop_per_item"] == fresh[kind]["gflop_per_item"]
+    assert 85 < fresh["layout_encoder"]["gflop_per_item"] < 100
 
 
 def test_abi_struct_layouts_match_the_header(tmp_path):
