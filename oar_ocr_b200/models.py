@@ -572,6 +572,75 @@ def _hgnetv2_l_into(g: GraphBuilder, return_idx=(3,), taps: list | None = None):
     return x
 
 
+# Synthetic weight table of the layout detector's neck and decoder (RT-DETR-L: hybrid encoder + 6-layer deformable
+# decoder, d = 256, 8 heads, FFN 1024, 3 levels x 4 points, 300 queries), by name.  The backbone's weights come from
+# build_hgnetv2_l with the same seed.  Consumed by build_layout_encoder (the OARG form of backbone + encoder) and by
+# the CPU oracle of the whole detector (oracle/rtdetr.py, which documents what each name is).
+def layout_weights(seed: int = 42, num_labels: int = 23) -> dict:
+    import math
+    D, HEADS, FFN, LEVELS, POINTS, DEC_LAYERS = 256, 8, 1024, 3, 4, 6
+    rng = np.random.default_rng(seed + 1)
+    w = {}
+
+    def lin(name, cin, cout, gain=1.0, bias=0.02):
+        w[name + ".w"] = (rng.standard_normal((cout, cin)) * gain / math.sqrt(cin)).astype(np.float32)
+        w[name + ".b"] = (rng.standard_normal(cout) * bias).astype(np.float32)
+
+    def conv(name, cin, cout, k, gain=1.0):  # BatchNorm folded: a conv with bias
+        w[name + ".w"] = (rng.standard_normal((cout, cin, k, k)) * gain * math.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+        w[name + ".b"] = (rng.standard_normal(cout) * 0.02).astype(np.float32)
+
+    def ln(name):
+        w[name + ".g"] = (1.0 + rng.standard_normal(D) * 0.02).astype(np.float32)
+        w[name + ".b"] = (rng.standard_normal(D) * 0.02).astype(np.float32)
+
+    def csp(name):
+        conv(name + ".conv1", 2 * D, D, 1)
+        conv(name + ".conv2", 2 * D, D, 1)
+        for i in range(3):
+            conv(f"{name}.rep{i}.c3", D, D, 3, 0.7)
+            conv(f"{name}.rep{i}.c1", D, D, 1, 0.7)
+
+    for l, c in enumerate((512, 1024, 2048)):
+        conv(f"input_proj{l}", c, D, 1)
+        conv(f"dec_input_proj{l}", D, D, 1)
+    for n in ("q", "k", "v", "o"):
+        lin(f"aifi.{n}", D, D)
+    lin("aifi.fc1", D, FFN)
+    lin("aifi.fc2", FFN, D)
+    ln("aifi.ln1")
+    ln("aifi.ln2")
+    for i in range(2):
+        conv(f"lateral{i}", D, D, 1)
+        csp(f"fpn{i}")
+        conv(f"down{i}", D, D, 3)
+        csp(f"pan{i}")
+    lin("enc_output", D, D)
+    ln("enc_output_ln")
+    lin("enc_score", D, num_labels, 2.0, 0.5)
+    for i, (a, b) in enumerate(((D, D), (D, D), (D, 4))):
+        lin(f"enc_bbox{i}", a, b, 1.0 if i < 2 else 0.3)
+    lin("query_pos0", 4, 2 * D)
+    lin("query_pos1", 2 * D, D)
+    for i in range(DEC_LAYERS):
+        p = f"dec{i}"
+        for n in ("q", "k", "v", "o"):
+            lin(f"{p}.sa.{n}", D, D)
+        ln(f"{p}.ln1")
+        lin(f"{p}.ca.offsets", D, HEADS * LEVELS * POINTS * 2, 0.5, 1.0)
+        lin(f"{p}.ca.weights", D, HEADS * LEVELS * POINTS)
+        lin(f"{p}.ca.value", D, D)
+        lin(f"{p}.ca.out", D, D)
+        ln(f"{p}.ln2")
+        lin(f"{p}.fc1", D, FFN)
+        lin(f"{p}.fc2", FFN, D)
+        ln(f"{p}.ln3")
+        lin(f"{p}.score", D, num_labels, 2.0, 0.5)
+        for j, (a, b) in enumerate(((D, D), (D, D), (D, 4))):
+            lin(f"{p}.bbox{j}", a, b, 1.0 if j < 2 else 0.3)
+    return w
+
+
 def build_layout_encoder(weights: dict, seed: int = 42, shapes_hw=None) -> bytes:
     """Backbone + hybrid encoder + decoder-input projection of the layout detector (RT-DETR-L) as ONE OARG graph whose
     output is the decoder memory [B, 1, sum(H_l W_l), 256] (8400 tokens at 640 x 640): HGNetV2-L -> 1x1 projections ->

@@ -20,8 +20,6 @@ PaddleDetection export are not available offline, so nothing here is pinned by r
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -84,66 +82,8 @@ class RTDetrL:
         self.num_labels = num_labels
         self.taps = []
         self.backbone = OracleNet(models.build_hgnetv2_l(seed, taps=self.taps))
-        rng = np.random.default_rng(seed + 1)
-        self.w = {}
-
-        def lin(name, cin, cout, gain=1.0, bias=0.02):
-            self.w[name + ".w"] = torch.from_numpy((rng.standard_normal((cout, cin)) * gain / math.sqrt(cin)).astype(np.float32))
-            self.w[name + ".b"] = torch.from_numpy((rng.standard_normal(cout) * bias).astype(np.float32))
-
-        def conv(name, cin, cout, k, gain=1.0):  # BatchNorm folded: a conv with bias
-            self.w[name + ".w"] = torch.from_numpy(
-                (rng.standard_normal((cout, cin, k, k)) * gain * math.sqrt(2.0 / (cin * k * k))).astype(np.float32))
-            self.w[name + ".b"] = torch.from_numpy((rng.standard_normal(cout) * 0.02).astype(np.float32))
-
-        def ln(name):
-            self.w[name + ".g"] = torch.from_numpy((1.0 + rng.standard_normal(D) * 0.02).astype(np.float32))
-            self.w[name + ".b"] = torch.from_numpy((rng.standard_normal(D) * 0.02).astype(np.float32))
-
-        def csp(name):
-            conv(name + ".conv1", 2 * D, D, 1)
-            conv(name + ".conv2", 2 * D, D, 1)
-            for i in range(3):
-                conv(f"{name}.rep{i}.c3", D, D, 3, 0.7)
-                conv(f"{name}.rep{i}.c1", D, D, 1, 0.7)
-
-        for l, c in enumerate((512, 1024, 2048)):
-            conv(f"input_proj{l}", c, D, 1)
-            conv(f"dec_input_proj{l}", D, D, 1)
-        for n in ("q", "k", "v", "o"):
-            lin(f"aifi.{n}", D, D)
-        lin("aifi.fc1", D, FFN)
-        lin("aifi.fc2", FFN, D)
-        ln("aifi.ln1")
-        ln("aifi.ln2")
-        for i in range(2):
-            conv(f"lateral{i}", D, D, 1)
-            csp(f"fpn{i}")
-            conv(f"down{i}", D, D, 3)
-            csp(f"pan{i}")
-        lin("enc_output", D, D)
-        ln("enc_output_ln")
-        lin("enc_score", D, num_labels, 2.0, 0.5)
-        for i, (a, b) in enumerate(((D, D), (D, D), (D, 4))):
-            lin(f"enc_bbox{i}", a, b, 1.0 if i < 2 else 0.3)
-        lin("query_pos0", 4, 2 * D)
-        lin("query_pos1", 2 * D, D)
-        for i in range(DEC_LAYERS):
-            p = f"dec{i}"
-            for n in ("q", "k", "v", "o"):
-                lin(f"{p}.sa.{n}", D, D)
-            ln(f"{p}.ln1")
-            lin(f"{p}.ca.offsets", D, HEADS * LEVELS * POINTS * 2, 0.5, 1.0)
-            lin(f"{p}.ca.weights", D, HEADS * LEVELS * POINTS)
-            lin(f"{p}.ca.value", D, D)
-            lin(f"{p}.ca.out", D, D)
-            ln(f"{p}.ln2")
-            lin(f"{p}.fc1", D, FFN)
-            lin(f"{p}.fc2", FFN, D)
-            ln(f"{p}.ln3")
-            lin(f"{p}.score", D, num_labels, 2.0, 0.5)
-            for j, (a, b) in enumerate(((D, D), (D, D), (D, 4))):
-                lin(f"{p}.bbox{j}", a, b, 1.0 if j < 2 else 0.3)
+        # the synthetic weight table lives with the other synthetic weights (models.layout_weights); names below
+        self.w = {k: torch.from_numpy(v) for k, v in models.layout_weights(seed, num_labels).items()}
 
     # -- small helpers over the weight table
     def _lin(self, name, x):

@@ -106,9 +106,8 @@ def main():
         elif kind == "rec_server":
             blob = models.build_rec_server()
         elif kind == "layout_encoder":
-            # backbone + hybrid encoder + decoder-input projections of RT-DETR-L (weights from the oracle's table)
-            from oracle.rtdetr import RTDetrL
-            blob = models.build_layout_encoder({k: v.numpy() for k, v in RTDetrL().w.items()},
+            # backbone + hybrid encoder + decoder-input projections of RT-DETR-L
+            blob = models.build_layout_encoder(models.layout_weights(),
                                                shapes_hw=[(H // 8, W // 8), (H // 16, W // 16), (H // 32, W // 32)])
         else:
             blob = models.get_blob(kind)

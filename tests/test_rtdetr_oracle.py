@@ -157,7 +157,7 @@ def test_encoder_as_oarg_layer_list_equals_the_oracle(net):
     x = np.random.default_rng(3).standard_normal((2, 3, 192, 256)).astype(np.float32)
     want, shapes = net.encode(x)
     assert shapes == [(24, 32), (12, 16), (6, 8)]
-    blob = models.build_layout_encoder({k: v.numpy() for k, v in net.w.items()}, seed=42, shapes_hw=shapes)
+    blob = models.build_layout_encoder(models.layout_weights(42), seed=42, shapes_hw=shapes)
     kind, _, ops, _ = parse(blob)
     types = [o["type"] for o in ops]
     assert kind == models.KIND_FEAT and types.count(models.OP_TOKENS) == 3 and types.count(models.OP_ATTN) == 1
@@ -172,7 +172,6 @@ def test_spec_only_ops_do_not_export_silently(net):
     """the ONNX exporter refuses what it cannot express yet instead of dropping it (positions, GELU, token rows)"""
     from oar_ocr_b200 import models, onnx_io
     from oar_ocr_b200.ffi import OCRError
-    blob = models.build_layout_encoder({k: v.numpy() for k, v in net.w.items()}, seed=42,
-                                       shapes_hw=[(8, 8), (4, 4), (2, 2)])
+    blob = models.build_layout_encoder(models.layout_weights(42), seed=42, shapes_hw=[(8, 8), (4, 4), (2, 2)])
     with pytest.raises(OCRError):
         onnx_io.export_onnx(blob)
