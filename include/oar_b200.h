@@ -86,6 +86,22 @@ void oar_ctx_destroy(oar_ctx* ctx);
 int32_t oar_ctx_synchronize(oar_ctx* ctx);
 /* Loads an OARG layer-list blob (oar_ocr_b200/models.py); weights are copied to HBM. */
 int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_model** out);
+/* Structural validation of an OARG blob without a device (what oar_model_load_blob checks before touching the GPU):
+ * sizes bounded by `len`, tensor ids and weight slices in range, parameters positive, every weight slice exactly as
+ * long as its op's parameters imply.  OAR_OK or OAR_E_MODEL with the reason in oar_last_error(). */
+int32_t oar_model_validate_blob(const void* bytes, size_t len);
+/* ModelSource::Memory / ModelSource::Path contents as the reference hands them to ONNX Runtime
+ * (oar-ocr-core/src/core/config/model_source.rs:20-28, core/inference/ort_infer_builders.rs:9-70,
+ * Session::builder().commit_from_memory): ONNX ModelProto bytes (or an OARG blob, recognised by its magic).
+ * `kind` = OAR_KIND_DET / OAR_KIND_REC / OAR_KIND_CLS states the caller's role as the reference's per-task builders do
+ * (a mismatch with the graph is OAR_E_MODEL), -1 = take whatever the graph is.  Operators outside the supported subset
+ * fail with OAR_E_MODEL naming the node -- the ONNX graph is converted to the layer list the CUDA engine executes, it
+ * is never interpreted on the CPU. */
+int32_t oar_model_load_onnx(oar_ctx* ctx, const void* bytes, size_t len, int32_t kind, oar_model** out);
+/* The conversion alone, host only (no device needed): writes the OARG blob to `out` (capacity `cap`) and its size to
+ * `out_len`; out == NULL queries the size.  kind_hint = OAR_KIND_CLS marks a classifier (its MatMul + Softmax tail is
+ * otherwise read as a CTC head), -1 = infer. */
+int32_t oar_onnx_to_oarg(const void* onnx, size_t len, int32_t kind_hint, void* out, size_t cap, size_t* out_len);
 void oar_model_destroy(oar_model* m);
 int32_t oar_model_kind(const oar_model* m);
 /* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine (one kernel per layer), 2 = tcgen05 engine with the

@@ -37,6 +37,35 @@ inline void check(int32_t rc) {
   throw OCRError(kind, oar_last_error(), rc);
 }
 
+// The recogniser's character table from the dictionary file's UTF-8 content, as the reference derives it:
+// `content.lines()` (ocr.rs:386 -- '\n' ends a line, a '\r' directly before it belongs to the terminator, no final
+// empty line) then CTCLabelDecode::from_string_list(.., use_space_char = true, has_explicit_blank = false)
+// (decode.rs:118-141, 392-423): blank '\0', the FIRST code point of every non-empty line, ' '.  `n_chars` of the C ABI
+// is the size of this table; text = table[label index].
+inline std::vector<char32_t> character_list(const std::string& dict_utf8) {
+  std::vector<char32_t> chars{U'\0'};
+  auto first_code_point = [](const std::string& s, size_t b, size_t e, char32_t* cp) {
+    if (b >= e) return false;
+    const unsigned char c0 = (unsigned char)s[b];
+    int n = c0 < 0x80 ? 1 : (c0 >> 5) == 6 ? 2 : (c0 >> 4) == 14 ? 3 : (c0 >> 3) == 30 ? 4 : 1;
+    char32_t v = n == 1 ? c0 : (c0 & (0xFF >> (n + 1)));
+    for (int i = 1; i < n && b + i < e; ++i) v = (v << 6) | ((unsigned char)s[b + i] & 0x3F);
+    *cp = v;
+    return true;
+  };
+  size_t pos = 0;
+  while (pos < dict_utf8.size()) {
+    size_t nl = dict_utf8.find('\n', pos);
+    size_t end = nl == std::string::npos ? dict_utf8.size() : nl;
+    size_t line_end = (nl != std::string::npos && end > pos && dict_utf8[end - 1] == '\r') ? end - 1 : end;
+    char32_t cp;
+    if (first_code_point(dict_utf8, pos, line_end, &cp)) chars.push_back(cp);
+    pos = nl == std::string::npos ? dict_utf8.size() : nl + 1;
+  }
+  chars.push_back(U' ');
+  return chars;
+}
+
 struct RgbImage {  // image::RgbImage: u8 HWC, row-major
   const uint8_t* data = nullptr;
   int32_t height = 0, width = 0;

@@ -23,6 +23,7 @@ SOURCES = {
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
     "layout.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only f32 restatement: no FMA contraction
+    "onnx_import.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only; BatchNorm folding in f32 step by step like numpy
 }
 
 

@@ -517,6 +517,109 @@ int launch_cls_batch(oar_model* cls, const RecCrop* crops, int n, int ih, int iw
   return C;
 }
 
+// Structural check of one OARG op record at load time: tensor ids in range, weight slices inside the weight array
+// (no signed or unsigned wrap), parameters positive where the kernels divide or index by them, and every weight slice
+// exactly as long as the op's parameters imply -- engine.cu indexes weights by those parameters, never by w_len, so a
+// short slice would otherwise be read past its end.  Returns nullptr or the reason.
+const char* validate_op(const OpRec& op, uint32_t n_tensors, uint64_t n_w) {
+  if (op.in0 < 0 || op.in0 >= (int)n_tensors || op.out < 0 || op.out >= (int)n_tensors) return "tensor id out of range";
+  if (op.in1 < -1 || op.in1 >= (int)n_tensors) return "second input id out of range";
+  for (int k = 0; k < 4; ++k) {
+    if (op.w_off[k] < 0 || op.w_len[k] < 0) return "negative weight slice";
+    if ((uint64_t)op.w_off[k] > n_w || (uint64_t)op.w_len[k] > n_w - (uint64_t)op.w_off[k]) return "weight slice out of range";
+  }
+  const int32_t* p = op.p;
+  auto pos = [](int64_t v, int64_t hi) { return v > 0 && v <= hi; };
+  const int64_t CMAX = 1 << 20;  // channels / classes
+  int64_t want[4] = {0, 0, 0, 0};
+  switch (op.type) {
+    case OP_CONV:
+      if (!pos(p[0], 64) || !pos(p[1], 64) || !pos(p[2], 64) || !pos(p[3], 64) || p[4] < 0 || p[4] > 64 || p[5] < 0 ||
+          p[5] > 64 || !pos(p[6], CMAX) || !pos(p[7], CMAX))
+        return "convolution kernel / stride / channels out of range";
+      if (p[10] < 0 || p[11] < 0 || (p[11] > 0 && (int64_t)p[10] + p[7] > p[11])) return "channel slice outside its tensor";
+      want[0] = (int64_t)p[7] * p[0] * p[1] * p[6], want[1] = p[7];
+      break;
+    case OP_DWCONV:
+      if (!pos(p[0], 64) || !pos(p[1], 64) || !pos(p[2], 64) || !pos(p[3], 64) || p[4] < 0 || p[4] > 64 || p[5] < 0 ||
+          p[5] > 64 || !pos(p[6], CMAX))
+        return "depthwise kernel / stride / channels out of range";
+      want[0] = (int64_t)p[0] * p[1] * p[6], want[1] = p[6];
+      break;
+    case OP_SE:
+      if (!pos(p[0], CMAX) || !pos(p[1], CMAX)) return "squeeze-excite widths out of range";
+      want[0] = (int64_t)p[1] * p[0], want[1] = p[1], want[2] = (int64_t)p[0] * p[1], want[3] = p[0];
+      break;
+    case OP_ADD:
+      if (op.in1 < 0) return "add needs two inputs";
+      break;
+    case OP_UPADD:
+      if (op.in1 < 0 || !pos(p[0], 64)) return "upsample-add needs two inputs and a positive scale";
+      break;
+    case OP_UPSAMPLE:
+      if (!pos(p[0], 64) || p[10] < 0 || p[11] < 0) return "upsample scale / slice out of range";
+      break;
+    case OP_DECONV2:
+      if (!pos(p[0], CMAX) || !pos(p[1], CMAX)) return "transposed-conv channels out of range";
+      want[0] = (int64_t)4 * p[1] * p[0], want[1] = p[1];
+      break;
+    case OP_AVGPOOL:
+      if (!((p[0] == 0 && p[1] == 0) || (pos(p[0], 1 << 16) && pos(p[1], 1 << 16) && pos(p[2], 1 << 16) && pos(p[3], 1 << 16))))
+        return "pool window / stride out of range";
+      break;
+    case OP_LAYERNORM:
+      if (!pos(p[0], CMAX)) return "layer-norm width out of range";
+      want[0] = p[0], want[1] = p[0];
+      break;
+    case OP_ATTN:
+      if (!pos(p[0], CMAX) || !pos(p[1], p[0]) || p[0] % p[1]) return "attention width / heads out of range";
+      want[0] = (int64_t)3 * p[0] * p[0], want[1] = 3 * (int64_t)p[0], want[2] = (int64_t)p[0] * p[0], want[3] = p[0];
+      break;
+    case OP_CTC_HEAD:
+      if (!pos(p[0], CMAX) || !pos(p[1], CMAX)) return "head width / classes out of range";
+      want[0] = (int64_t)p[1] * p[0], want[1] = p[1];
+      break;
+    default:
+      return "unknown op type";
+  }
+  for (int k = 0; k < 4; ++k)
+    if (op.w_len[k] != want[k]) return "weight slice length does not match the op's parameters";
+  return nullptr;
+}
+
+struct BlobHeader {
+  uint32_t version, kind, n_ops, n_tensors;
+  uint64_t n_w;
+};
+
+// Parses and validates an OARG blob (host only).  Every size is bounded by the blob length BEFORE it is multiplied, so
+// a crafted 64-bit weight count cannot wrap the length check.
+void check_blob(const uint8_t* p, size_t len, BlobHeader& h, std::vector<OpRec>* ops_out) {
+  if (len < 28 || memcmp(p, "OARG", 4) != 0) OAR_FAIL(OAR_E_MODEL, "not an OARG model blob");
+  memcpy(&h.version, p + 4, 4);
+  memcpy(&h.kind, p + 8, 4);
+  memcpy(&h.n_ops, p + 12, 4);
+  memcpy(&h.n_tensors, p + 16, 4);
+  memcpy(&h.n_w, p + 20, 8);
+  if (h.version != 1) OAR_FAIL(OAR_E_MODEL, "unsupported OARG version %u", h.version);
+  if (h.kind > OAR_KIND_CLS) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", h.kind);
+  const size_t body = len - 28;
+  if ((size_t)h.n_ops > body / sizeof(OpRec))
+    OAR_FAIL(OAR_E_MODEL, "truncated model blob: %u ops do not fit %zu bytes", h.n_ops, len);
+  const size_t w_bytes = body - (size_t)h.n_ops * sizeof(OpRec);
+  if (h.n_w > w_bytes / 4)
+    OAR_FAIL(OAR_E_MODEL, "truncated model blob: %zu bytes hold fewer than %llu weights", len, (unsigned long long)h.n_w);
+  if (h.n_tensors == 0 || h.n_tensors > (1u << 20)) OAR_FAIL(OAR_E_MODEL, "implausible tensor count %u", h.n_tensors);
+  if (h.n_ops == 0) OAR_FAIL(OAR_E_MODEL, "model has no operations");
+  std::vector<OpRec> ops(h.n_ops);
+  memcpy(ops.data(), p + 28, (size_t)h.n_ops * sizeof(OpRec));
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const char* why = validate_op(ops[i], h.n_tensors, h.n_w);
+    if (why) OAR_FAIL(OAR_E_MODEL, "op %zu (type %d): %s", i, ops[i].type, why);
+  }
+  if (ops_out) *ops_out = std::move(ops);
+}
+
 void require_device(oar_ctx* ctx) {
   if (!ctx) OAR_FAIL(OAR_E_INVALID, "null context");
 }
@@ -607,47 +710,34 @@ int32_t oar_ctx_synchronize(oar_ctx* ctx) {
   API_CATCH
 }
 
+int32_t oar_model_validate_blob(const void* bytes, size_t len) {
+  API_TRY
+  if (!bytes) OAR_FAIL(OAR_E_INVALID, "null argument");
+  BlobHeader h;
+  check_blob((const uint8_t*)bytes, len, h, nullptr);
+  API_CATCH
+}
+
 int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_model** out) {
   API_TRY
   require_device(ctx);
   if (!bytes || !out) OAR_FAIL(OAR_E_INVALID, "null argument");
   *out = nullptr;
   const uint8_t* p = (const uint8_t*)bytes;
-  if (len < 28 || memcmp(p, "OARG", 4) != 0) OAR_FAIL(OAR_E_MODEL, "not an OARG model blob");
-  uint32_t version, kind, n_ops, n_tensors;
-  uint64_t n_w;
-  memcpy(&version, p + 4, 4);
-  memcpy(&kind, p + 8, 4);
-  memcpy(&n_ops, p + 12, 4);
-  memcpy(&n_tensors, p + 16, 4);
-  memcpy(&n_w, p + 20, 8);
-  if (version != 1) OAR_FAIL(OAR_E_MODEL, "unsupported OARG version %u", version);
-  if (kind > OAR_KIND_CLS) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", kind);
-  size_t need = 28 + (size_t)n_ops * sizeof(OpRec) + (size_t)n_w * 4;
-  if (len < need) OAR_FAIL(OAR_E_MODEL, "truncated model blob: %zu bytes, need %zu", len, need);
+  BlobHeader h;
+  std::vector<OpRec> ops;
+  check_blob(p, len, h, &ops);
   std::lock_guard<std::mutex> lock(ctx->mu);
   OAR_CUDA(cudaSetDevice(ctx->device));
   oar_model* m = new oar_model();
   m->ctx = ctx;
-  m->kind = (int)kind;
-  m->n_tensors = (int)n_tensors;
-  m->ops.resize(n_ops);
-  memcpy(m->ops.data(), p + 28, (size_t)n_ops * sizeof(OpRec));
-  for (size_t i = 0; i < m->ops.size(); ++i) {
-    const OpRec& op = m->ops[i];
-    bool bad = op.in0 < 0 || op.in0 >= (int)n_tensors || op.out < 0 || op.out >= (int)n_tensors ||
-               op.in1 >= (int)n_tensors;
-    for (int k = 0; k < 4; ++k)
-      bad = bad || op.w_off[k] < 0 || op.w_len[k] < 0 || (uint64_t)(op.w_off[k] + op.w_len[k]) > n_w;
-    if (bad) {
-      delete m;
-      OAR_FAIL(OAR_E_MODEL, "op %zu references tensors or weights out of range", i);
-    }
-  }
-  m->n_weights = n_w;
-  cudaError_t e = cudaMalloc(&m->d_weights, std::max<size_t>(n_w, 1) * 4);
+  m->kind = (int)h.kind;
+  m->n_tensors = (int)h.n_tensors;
+  m->ops = std::move(ops);
+  m->n_weights = h.n_w;
+  cudaError_t e = cudaMalloc(&m->d_weights, std::max<size_t>(h.n_w, 1) * 4);
   if (e == cudaSuccess)
-    e = cudaMemcpy(m->d_weights, p + 28 + (size_t)n_ops * sizeof(OpRec), n_w * 4, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(m->d_weights, p + 28 + m->ops.size() * sizeof(OpRec), h.n_w * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(m->d_weights);
     delete m;
@@ -655,9 +745,60 @@ int32_t oar_model_load_blob(oar_ctx* ctx, const void* bytes, size_t len, oar_mod
   }
   m->engine = 2;
   if (const char* cap = getenv("OAR_DBG_ENGINE_CAP")) m->engine = std::min(2, atoi(cap));
-  tc_model_init(m);
+  try {
+    tc_model_init(m);
+  } catch (...) {
+    tc_model_free(m);
+    cudaFree(m->d_weights);
+    delete m;
+    throw;
+  }
   *out = m;
   API_CATCH
+}
+
+int32_t oar_onnx_to_oarg(const void* onnx, size_t len, int32_t kind_hint, void* out, size_t cap, size_t* out_len) {
+  API_TRY
+  if (!onnx || !out_len) OAR_FAIL(OAR_E_INVALID, "null argument");
+  if (kind_hint > OAR_KIND_CLS) OAR_FAIL(OAR_E_INVALID, "unknown model kind %d", kind_hint);
+  std::vector<uint8_t> blob = onnx_to_oarg(onnx, len, kind_hint);
+  *out_len = blob.size();
+  if (!out) return OAR_OK;  // size query
+  if (blob.size() > cap) OAR_FAIL(OAR_E_CAPACITY, "OARG blob needs %zu bytes, capacity %zu", blob.size(), cap);
+  memcpy(out, blob.data(), blob.size());
+  API_CATCH
+}
+
+int32_t oar_model_load_onnx(oar_ctx* ctx, const void* bytes, size_t len, int32_t kind, oar_model** out) {
+  if (!bytes || !out) {
+    set_error("null argument");
+    return OAR_E_INVALID;
+  }
+  *out = nullptr;
+  if (len >= 4 && memcmp(bytes, "OARG", 4) == 0) return oar_model_load_blob(ctx, bytes, len, out);
+  std::vector<uint8_t> blob;
+  {
+    API_TRY
+    require_device(ctx);
+    if (kind < -1 || kind > OAR_KIND_CLS) OAR_FAIL(OAR_E_INVALID, "unknown model kind %d", kind);
+    // a classifier's graph ends in the same MatMul + Softmax pattern as a CTC head: the caller's role decides
+    blob = onnx_to_oarg(bytes, len, kind == OAR_KIND_CLS ? OAR_KIND_CLS : -1);
+    uint32_t got;
+    memcpy(&got, blob.data() + 8, 4);
+    if (kind >= 0 && (int)got != kind)
+      OAR_FAIL(OAR_E_MODEL, "the ONNX graph is a %s model, a %s model was requested", got == 0 ? "detection" : got == 1 ? "recognition" : "classification",
+               kind == 0 ? "detection" : kind == 1 ? "recognition" : "classification");
+    }
+    catch (const oar::OarError& e) {
+      cudaGetLastError();
+      return e.code;
+    }
+    catch (const std::exception& e) {
+      oar::set_error("internal error: %s", e.what());
+      return OAR_E_MODEL;
+    }
+  }
+  return oar_model_load_blob(ctx, blob.data(), blob.size(), out);
 }
 
 void oar_model_destroy(oar_model* m) {

@@ -121,6 +121,9 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
                         int n_tiles, int32_t* idx, float* prob);
 
+// ONNX ModelProto bytes -> OARG blob (onnx_import.cu; host only).  kind_hint < 0: inferred from the graph's tail.
+std::vector<uint8_t> onnx_to_oarg(const void* bytes, size_t len, int kind_hint);
+
 // input layout conversion for the seam-1 API (NCHW f32 host layout -> NHWC)
 void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C, int H, int W);
 

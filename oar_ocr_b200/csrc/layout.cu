@@ -80,7 +80,16 @@ std::vector<int> nms(const Candidates& c) {
   const int n = (int)c.size();
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c.score[a] > c.score[b]; });
+  // The reference sorts with partial_cmp(..).unwrap_or(Equal) (layout_detection_adapter.rs:890-894): memory-safe in
+  // Rust, but with a NaN score it is not a strict weak ordering, which is undefined behaviour for std::stable_sort.
+  // A total order is used instead: descending score, NaN after every number, ties by index (stable).  For NaN-free
+  // input -- the only case in which the reference's order is specified -- the result is identical.
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const float sa = c.score[a], sb = c.score[b];
+    if (sa != sa) return false;
+    if (sb != sb) return true;
+    return sa > sb;
+  });
   std::vector<float> bx1(n), by1(n), bx2(n), by2(n), area(n);
   for (int i = 0; i < n; ++i) {
     bx1[i] = c.xmin(i), by1[i] = c.ymin(i), bx2[i] = c.xmax(i), by2[i] = c.ymax(i);

@@ -79,8 +79,10 @@ void launch_normalize(oar_ctx* ctx, const uint8_t* rgb, const uint8_t* const* d_
   int vec_ok = (plane % 4 == 0) && src_ok && (((uintptr_t)out & 15) == 0);
   long long groups = (plane + 3) / 4;
   Launch l(ctx, "normalize", 2.0 * 3 * plane * B, 15.0 * plane * B);
+  if (B > 65535) OAR_FAIL(OAR_E_INVALID, "normalize: batch %d exceeds 65535 images per launch", B);
   normalize_kernel<<<dim3(cdiv(groups, 256), B), 256, 0, ctx->stream>>>(rgb, d_table, out, plane, B, k, layout,
                                                                          vec_ok);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -161,14 +163,20 @@ __global__ void resize_h_kernel(const ResizeJob* __restrict__ jobs) {
 
 void launch_resize_triangle(oar_ctx* ctx, const ResizeJob* d_jobs, int n_jobs, int max_sw, int max_dw, int max_dh) {
   if (n_jobs == 0) return;
-  {
-    Launch l(ctx, "resize_tri_v");
-    resize_v_kernel<<<dim3(cdiv(max_sw, 128), max_dh, n_jobs), 128, 0, ctx->stream>>>(d_jobs);
+  if (max_dh > 65535) OAR_FAIL(OAR_E_INVALID, "resize: %d output rows exceed 65535 per launch", max_dh);
+  // gridDim.z is limited to 65535: slice the job list
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    const int nj = std::min(n_jobs - j0, 65535);
+    {
+      Launch l(ctx, "resize_tri_v");
+      resize_v_kernel<<<dim3(cdiv(max_sw, 128), max_dh, nj), 128, 0, ctx->stream>>>(d_jobs + j0);
+    }
+    {
+      Launch l(ctx, "resize_tri_h");
+      resize_h_kernel<<<dim3(cdiv(max_dw, 128), max_dh, nj), 128, 0, ctx->stream>>>(d_jobs + j0);
+    }
   }
-  {
-    Launch l(ctx, "resize_tri_h");
-    resize_h_kernel<<<dim3(cdiv(max_dw, 128), max_dh, n_jobs), 128, 0, ctx->stream>>>(d_jobs);
-  }
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -353,6 +361,7 @@ void launch_crop_plan(oar_ctx* ctx, CropPlan* d_plans, int n, const ImageRef* d_
   if (!n) return;
   Launch l(ctx, "crop_plan");
   crop_plan_kernel<<<cdiv(n, 64), 64, 0, ctx->stream>>>(d_plans, n, d_images);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -450,7 +459,11 @@ void launch_crop_warp(oar_ctx* ctx, const CropPlan* d_plans, int n, const ImageR
                       long long total_px) {
   if (!n) return;
   Launch l(ctx, "crop_warp", 96.0 * total_px, 6.0 * total_px);
-  crop_warp_kernel<<<dim3(32, n), 256, 0, ctx->stream>>>(d_plans, d_images, pool);
+  // gridDim.y is limited to 65535 (the reference has no such limit: it flushes its crop pool every 4096 crops, but one
+  // call here plans all boxes of all pages at once): slice the plan list
+  for (int j0 = 0; j0 < n; j0 += 65535)
+    crop_warp_kernel<<<dim3(32, std::min(n - j0, 65535)), 256, 0, ctx->stream>>>(d_plans + j0, d_images, pool);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -483,8 +496,10 @@ void launch_crnn_normalize(oar_ctx* ctx, const CrnnJob* d_jobs, int n, int img_h
                            int layout) {
   if (!n) return;
   Launch l(ctx, "crnn_normalize", 0, 15.0 * n * img_h * tensor_w);
+  if (n > 65535) OAR_FAIL(OAR_E_INVALID, "crnn_normalize: %d crops exceed 65535 per launch", n);
   crnn_normalize_kernel<<<dim3(cdiv(tensor_w, 128), img_h, n), 128, 0, ctx->stream>>>(d_jobs, img_h, tensor_w, out,
                                                                                        layout);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -526,6 +541,7 @@ void launch_ctc_argmax(oar_ctx* ctx, const float* pred, long long rows, int V, i
   if (rows == 0 || V == 0) return;
   Launch l(ctx, "ctc_argmax", (double)rows * V, 4.0 * rows * V);
   ctc_argmax_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(pred, V, idx, prob);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // decode.rs:505-614: prev = blank; emit when idx != 0 && idx != prev && idx < n_chars; prev = idx always
@@ -555,6 +571,7 @@ void launch_ctc_decode(oar_ctx* ctx, const int32_t* idx, const float* prob, int 
   if (!B) return;
   Launch l(ctx, "ctc_decode", 0, 8.0 * B * T);
   ctc_decode_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(idx, prob, B, T, n_chars, labels, cols, lens, scores);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -581,6 +598,7 @@ void launch_cls_top1(oar_ctx* ctx, const float* probs, int n, int C, int32_t* id
   if (n <= 0 || C <= 0) return;
   Launch l(ctx, "cls_top1", 0, 4.0 * n * C + 8.0 * n);
   cls_top1_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(probs, n, C, ids, scores);
+  OAR_CUDA(cudaGetLastError());
 }
 
 // One thread per pixel pair (i, npix-1-i); 6 B read + 6 B written per pair, HBM/L2-bound.
@@ -608,6 +626,7 @@ void launch_rotate180(oar_ctx* ctx, const Rot180Job* d_jobs, int n_jobs, int max
     int nj = std::min(n_jobs - j0, 65535);
     rotate180_kernel<<<dim3(bx, nj), 256, 0, ctx->stream>>>(d_jobs + j0, class_ids ? class_ids + j0 : nullptr);
   }
+  OAR_CUDA(cudaGetLastError());
 }
 
 }  // namespace oar

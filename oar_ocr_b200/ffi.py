@@ -25,7 +25,8 @@ SYMBOLS = [
     "oar_det_run", "oar_sort_quad_boxes", "oar_rotate_crop", "oar_crnn_preprocess", "oar_ctc_decode", "oar_rec_run",
     "oar_pipeline_run", "oar_cls_run", "oar_rotate180", "oar_pipeline_run_cls", "oar_layout_config_default",
     "oar_layout_postprocess", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
-    "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush",
+    "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush", "oar_model_validate_blob",
+    "oar_model_load_onnx", "oar_onnx_to_oarg",
 ]
 
 
@@ -110,6 +111,10 @@ def lib():
         L.oar_ctx_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
         L.oar_ctx_synchronize.argtypes = [C.c_void_p]
         L.oar_model_load_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.oar_model_validate_blob.argtypes = [C.c_void_p, C.c_size_t]
+        L.oar_model_load_onnx.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
+        L.oar_onnx_to_oarg.argtypes = [C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t)]
         L.oar_model_kind.argtypes = [C.c_void_p]
         L.oar_model_set_engine.argtypes = [C.c_void_p, C.c_int32]
         L.oar_infer_f32.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t,
@@ -413,14 +418,35 @@ def sort_quad_boxes(boxes: np.ndarray):
     return boxes, order[:len(boxes)].copy()
 
 
-class Model:
-    """One network resident in HBM = oar_model (stands where OrtInfer stands in the reference)."""
+def validate_blob(blob: bytes) -> None:
+    """oar_model_validate_blob: structural check of an OARG blob, no device needed; raises OCRError("ModelLoad")"""
+    buf = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
+    check(lib().oar_model_validate_blob(buf, len(blob)))
 
-    def __init__(self, ctx: Context, blob: bytes):
+
+def onnx_to_oarg(data: bytes, kind_hint: int = -1) -> bytes:
+    """oar_onnx_to_oarg: the library's own ONNX -> OARG conversion (csrc/onnx_import.cu), no device needed"""
+    buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
+    n = C.c_size_t(0)
+    check(lib().oar_onnx_to_oarg(buf, len(data), kind_hint, None, 0, C.byref(n)))
+    out = (C.c_char * max(n.value, 1))()
+    check(lib().oar_onnx_to_oarg(buf, len(data), kind_hint, out, n.value, C.byref(n)))
+    return bytes(out[:n.value])
+
+
+class Model:
+    """One network resident in HBM = oar_model (stands where OrtInfer stands in the reference).  `data` is what the
+    reference's ModelSource carries: ONNX ModelProto bytes, or an OARG layer-list blob; ONNX is converted behind the
+    C ABI (oar_model_load_onnx).  `kind` states the caller's role (KIND_DET / KIND_REC / KIND_CLS) or -1."""
+
+    def __init__(self, ctx: Context, data: bytes, kind: int = -1):
         self.ctx = ctx
         self.handle = C.c_void_p()
-        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        check(lib().oar_model_load_blob(ctx.handle, buf, len(blob), C.byref(self.handle)))
+        buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        if bytes(data[:4]) == b"OARG":
+            check(lib().oar_model_load_blob(ctx.handle, buf, len(data), C.byref(self.handle)))
+        else:
+            check(lib().oar_model_load_onnx(ctx.handle, buf, len(data), kind, C.byref(self.handle)))
         self.kind = lib().oar_model_kind(self.handle)
 
     def close(self):

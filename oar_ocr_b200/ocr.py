@@ -127,25 +127,35 @@ class TextRecognitionConfig:
     score_threshold: float = 0.0
 
 
-def character_list(dict_lines: list[str]) -> list[str]:
+def dict_lines(content: str) -> list[str]:
+    """Rust `str::lines()` as the reference applies it to the dictionary file (ocr.rs:386, utils/dict.rs:43,
+    predictors/text_recognition.rs:89): split on '\\n' only, a '\\r' directly before it belongs to the terminator, no
+    final empty piece (split_inclusive('\\n') + strip_suffix, library/core/src/str/mod.rs).  (Python's str.splitlines() also breaks on \\x0b \\x0c \\x1c-\\x1e \\x85 U+2028 U+2029, which would shift
+    every later class index.)"""
+    parts = content.split("\n")
+    last = parts.pop()  # the piece after the final '\n': a line only if non-empty, and its bare '\r' is preserved
+    lines = [p[:-1] if p.endswith("\r") else p for p in parts]  # '\r' is stripped only as part of a '\r\n' terminator
+    if last:
+        lines.append(last)
+    return lines
+
+
+def character_list(lines: list[str]) -> list[str]:
     """CTCLabelDecode::from_string_list(dict, use_space_char=true, has_explicit_blank=false)
-    (decode.rs:392-423, 118-141): ['blank'] + dict + [' ']"""
-    return ["\0"] + list(dict_lines) + [" "]
+    (decode.rs:392-423, 118-141): ['\\0' blank] + the FIRST char of every non-empty dictionary line
+    (`filter_map(|s| s.chars().next())`: empty lines are dropped, longer lines truncated) + [' ']"""
+    return ["\0"] + [ln[0] for ln in lines if ln] + [" "]
 
 
-def _seed_kind(kind: str):
-    """a classifier's ONNX graph ends in the same MatMul + Softmax pattern as a CTC head: the caller's role decides"""
-    from . import models
-    return models.KIND_CLS if kind == "cls" else None
+_KIND_ID = {"det": ffi.KIND_DET, "rec": ffi.KIND_REC, "cls": ffi.KIND_CLS}
 
 
 def _resolve_model(source, kind: str) -> bytes:
-    """ModelSource (core/config: ModelSource::Path / Memory): OARG or ONNX bytes, a path to an .oarg or .onnx file, or
-    'synthetic[:seed]'.  ONNX models are converted to the OARG layer list on load (onnx_io.import_onnx)."""
+    """ModelSource (core/config/model_source.rs:20-28: ModelSource::Path / Memory): OARG or ONNX bytes, a path to an
+    .oarg or .onnx file, or 'synthetic[:seed]'.  Returns the bytes to hand to the C ABI: ONNX models go through
+    unchanged and are converted to the layer list inside the library (oar_model_load_onnx), exactly where the reference
+    hands them to ONNX Runtime."""
     if isinstance(source, (bytes, bytearray)):
-        if bytes(source[:4]) != b"OARG":
-            from . import onnx_io
-            return onnx_io.import_onnx(bytes(source), _seed_kind(kind))
         return bytes(source)
     if isinstance(source, str) and source.startswith("synthetic"):
         from . import models
@@ -156,12 +166,12 @@ def _resolve_model(source, kind: str) -> bytes:
         if not os.path.exists(path):
             raise OCRError("ModelLoad", f"model file '{path}' does not exist")
         with open(path, "rb") as f:
-            data = f.read()
-        if path.endswith(".onnx") or data[:4] != b"OARG":
-            from . import onnx_io
-            return onnx_io.import_onnx(data, _seed_kind(kind))
-        return data
+            return f.read()
     raise OCRError("InvalidInput", f"unsupported model source {type(source)}")
+
+
+def _load_model(ctx, source, kind: str) -> "ffi.Model":
+    return ffi.Model(ctx, _resolve_model(source, kind), _KIND_ID[kind])
 
 
 def _decode_texts(chars, label_lists):
@@ -257,7 +267,7 @@ class TextDetectionPredictorBuilder:
     def build(self, model_source) -> "TextDetectionPredictor":
         self._config.validate()
         ctx = default_context(self._device)
-        return TextDetectionPredictor(ffi.Model(ctx, _resolve_model(model_source, "det")), self._config)
+        return TextDetectionPredictor(_load_model(ctx, model_source, "det"), self._config)
 
 
 class TextDetectionPredictor:
@@ -313,12 +323,12 @@ class TextRecognitionPredictorBuilder:
             lines = self._dict
         else:
             try:
-                with open(self._dict, "r", encoding="utf-8") as f:
-                    lines = f.read().splitlines()
+                with open(self._dict, "r", encoding="utf-8", newline="") as f:
+                    lines = dict_lines(f.read())
             except OSError as e:
                 raise OCRError("InvalidInput", f"Failed to read character dictionary from '{self._dict}': {e}")
         ctx = default_context(self._device)
-        return TextRecognitionPredictor(ffi.Model(ctx, _resolve_model(model_source, "rec")), character_list(lines),
+        return TextRecognitionPredictor(_load_model(ctx, model_source, "rec"), character_list(lines),
                                         self._config)
 
 
@@ -412,7 +422,7 @@ class TextLineOrientationPredictorBuilder:
     def build(self, model_source) -> "TextLineOrientationPredictor":
         self._config.validate()
         ctx = default_context(self._device)
-        return TextLineOrientationPredictor(ffi.Model(ctx, _resolve_model(model_source, "cls")), self._config,
+        return TextLineOrientationPredictor(_load_model(ctx, model_source, "cls"), self._config,
                                             self._input_shape)
 
 
@@ -580,24 +590,24 @@ class OAROCRBuilder:
             if self._dict_path is None:
                 raise OCRError("InvalidInput", "Failed to read character dictionary from '': no path given")
             try:
-                with open(self._dict_path, "r", encoding="utf-8") as f:
+                with open(self._dict_path, "r", encoding="utf-8", newline="") as f:
                     content = f.read()
             except OSError as e:
                 raise OCRError("InvalidInput", f"Failed to read character dictionary from '{self._dict_path}': {e}")
-        chars = character_list(content.splitlines())
+        chars = character_list(dict_lines(content))
         # no explicit config -> thresh .3 / box .6 / unclip 2.0 / limit 960 Max 4000 (ocr.rs:351-364)
         det_cfg = self._det_cfg or TextDetectionConfig(unclip_ratio=2.0, limit_side_len=960, limit_type="max",
                                                        max_side_len=4000)
         det_cfg.validate()
         rec_cfg = self._rec_cfg or TextRecognitionConfig()
         ctx = default_context(self._device)
-        det = ffi.Model(ctx, _resolve_model(self._det, "det"))
-        rec = ffi.Model(ctx, _resolve_model(self._rec, "rec"))
+        det = _load_model(ctx, self._det, "det")
+        rec = _load_model(ctx, self._rec, "rec")
         # the B200 provider is an accelerator: adapter defaults 8 / 64 (builder_utils.rs:86-125)
         ocr = OAROCR(ctx, det, rec, chars, det_cfg, rec_cfg, self._image_bs or 8, self._region_bs or 64)
         ocr.return_word_box = self._return_word_box
         if self._line_ori is not None:
-            ocr.cls = ffi.Model(ctx, _resolve_model(self._line_ori, "cls"))
+            ocr.cls = _load_model(ctx, self._line_ori, "cls")
             if ocr.cls.kind != ffi.KIND_CLS:
                 raise OCRError("ModelLoad", "text line orientation model is not a classifier")
         return ocr

@@ -542,6 +542,17 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
         kh, kw = a.get("kernel_shape", list(w.shape[2:]))
         sh, sw = a.get("strides", [1, 1])
         pads = a.get("pads", [0, 0, 0, 0])
+        auto_pad = a.get("auto_pad", "NOTSET") or "NOTSET"
+        if auto_pad == "VALID":
+            pads = [0, 0, 0, 0]
+        elif auto_pad in ("SAME_UPPER", "SAME_LOWER"):
+            # total = (ceil(in / s) - 1) * s + k - in depends on the input size unless s == 1 (then k - 1); symmetric only
+            # for odd kernels -- anything else cannot be written as the fixed symmetric padding the engine applies
+            if (sh, sw) != (1, 1) or kh % 2 == 0 or kw % 2 == 0:
+                fail(n, f"auto_pad={auto_pad} with stride {sh}x{sw} / kernel {kh}x{kw} (needs stride 1 and an odd kernel)")
+            pads = [kh // 2, kw // 2, kh // 2, kw // 2]
+        elif auto_pad != "NOTSET":
+            fail(n, f"unknown auto_pad '{auto_pad}'")
         if pads[0] != pads[2] or pads[1] != pads[3]:
             fail(n, "asymmetric padding")
         if any(d != 1 for d in a.get("dilations", [1, 1])):
@@ -609,8 +620,17 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
             if ins[0] not in mul["inputs"]:
                 fail(n, "squeeze-excite gate does not multiply the pooled tensor")
             done.update(seq)
-            w1, b1 = inits[c1["inputs"][1]], inits[c1["inputs"][2]]
-            w2, b2 = inits[c2["inputs"][1]], inits[c2["inputs"][2]]
+            def se_fc(c):
+                if c["inputs"][1] not in inits:
+                    fail(c, "squeeze-excite weights are not an initializer")
+                w = inits[c["inputs"][1]]
+                if w.ndim != 4 or w.shape[2:] != (1, 1) or c["attrs"].get("group", 1) != 1:
+                    fail(c, "squeeze-excite convolutions must be dense 1x1")
+                has_b = len(c["inputs"]) > 2 and c["inputs"][2]
+                if has_b and c["inputs"][2] not in inits:
+                    fail(c, "squeeze-excite bias is not an initializer")
+                return w, (inits[c["inputs"][2]] if has_b else np.zeros(w.shape[0], np.float32))
+            (w1, b1), (w2, b2) = se_fc(c1), se_fc(c2)
             residual, y = False, mul["outputs"][0]
             j = sole_consumer(y, "Add")
             if j is not None and ins[0] in nodes[j]["inputs"]:
@@ -625,10 +645,25 @@ def import_onnx(data: bytes, seed_kind: int | None = None) -> bytes:
                                w2.reshape(c, cm).astype(np.float32), b2.astype(np.float32)]))
             tid[y] = out
         elif ot == "Add":
+            for x in ins:
+                if x not in tid:
+                    fail(n, f"operand '{x}' is " + ("an initializer (only activation + activation adds are supported)"
+                                                   if x in inits else "not produced by a supported node"))
             tid[outs[0]] = g.add(tid[ins[0]], tid[ins[1]])
         elif ot == "Resize":
             if n["attrs"].get("mode", "nearest") != "nearest":
                 fail(n, "Resize mode other than nearest")
+            # integer-scale pixel replication out[y] = in[y // s]: 'asymmetric' with floor, or any of the modes that
+            # coincide with it for integer scales.  half_pixel/pytorch_half_pixel + round_prefer_floor (the ONNX
+            # defaults) also replicate (src = (y + .5)/s - .5 lands strictly inside cell y // s for integer s), and so
+            # does half_pixel + floor only for s == 1; everything else is rejected.
+            ctm = n["attrs"].get("coordinate_transformation_mode", "half_pixel")
+            nm = n["attrs"].get("nearest_mode", "round_prefer_floor")
+            ok = (ctm == "asymmetric" and nm == "floor") or \
+                 (ctm in ("half_pixel", "pytorch_half_pixel") and nm in ("round_prefer_floor", "round_prefer_ceil"))
+            if not ok:
+                fail(n, f"Resize nearest with coordinate_transformation_mode={ctm}, nearest_mode={nm} is not "
+                        "integer pixel replication")
             sc = inits.get(ins[2]) if len(ins) > 2 and ins[2] else None
             if sc is None or sc.size != 4 or sc[0] != 1 or sc[1] != 1 or sc[2] != sc[3] or sc[2] != int(sc[2]):
                 fail(n, "Resize needs constant integer scales [1,1,s,s]")

@@ -1256,7 +1256,14 @@ float layout_iou(const LBox& a, const LBox& b) {
 std::vector<int> score_order(const float* scores, int n) {
   std::vector<int> idx(n);
   for (int i = 0; i < n; ++i) idx[i] = i;
-  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return scores[a] > scores[b]; });
+  // descending, NaN last, ties by index: a total order (the reference's partial_cmp().unwrap_or(Equal) leaves the
+  // order unspecified when a score is NaN; std::stable_sort needs a strict weak ordering)
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+    const float sa = scores[a], sb = scores[b];
+    if (sa != sa) return false;
+    if (sb != sb) return true;
+    return sa > sb;
+  });
   return idx;
 }
 

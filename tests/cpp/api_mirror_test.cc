@@ -36,6 +36,16 @@ int main(int argc, char** argv) {
   oar_pipeline_config_default(&pc);
   expect(pc.image_batch_size == 8 && pc.region_batch_size == 64 && pc.det.unclip_ratio == 2.0f, "defaults");
 
+  // character table from dictionary content: Rust lines() + first char of each non-empty line (ocr.rs:386,
+  // decode.rs:118-121); U+2028 / U+0085 / \x0b are ordinary characters, "\r\n" is one terminator, a bare CR is not
+  {
+    const std::string dict = "a\n\nbc\r\n\xE2\x80\xA8\n\x0bq\n\xC2\x85\n\xE4\xB8\x80z\nz\r";
+    auto t = oar::character_list(dict);
+    const std::vector<char32_t> want{U'\0', U'a', U'b', (char32_t)0x2028, (char32_t)0x0B, (char32_t)0x85, (char32_t)0x4E00, U'z', U' '};
+    expect(t == want, "character_list");
+    expect(oar::character_list("").size() == 2 && oar::character_list("x\n\n").size() == 3, "character_list edge cases");
+  }
+
   // ctc_word_boxes: the reference's own vector (ocr.rs:1197-1232) + a CJK case
   {
     oar::BoundingBox line{{{0.f, 0.f}, {100.f, 0.f}, {100.f, 20.f}, {0.f, 20.f}}};

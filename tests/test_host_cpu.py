@@ -90,6 +90,26 @@ def test_character_list_layout():
     assert len(chars) == 18385 and chars[0] == "\0" and chars[-1] == " "
 
 
+def test_dictionary_lines_follow_rust_semantics(tmp_path):
+    """Rust `str::lines()` + `filter_map(|s| s.chars().next())` (ocr.rs:386, decode.rs:118-121): only '\\n' / '\\r\\n'
+    end a line, empty lines are dropped, a multi-character line contributes its first char.  U+2028, U+0085, \\x0b,
+    \\x0c and \\x1c are ordinary characters (Python's splitlines() would split on each and shift the class indices)."""
+    from oar_ocr_b200.ocr import TextRecognitionPredictorBuilder, character_list, dict_lines
+    content = "a\n\nbc\r\n\u2028\n\x0bq\n\x85\n\x1c\n\x0c\nz"
+    lines = dict_lines(content)
+    assert lines == ["a", "", "bc", "\u2028", "\x0bq", "\x85", "\x1c", "\x0c", "z"]
+    chars = character_list(lines)
+    assert chars == ["\0", "a", "b", "\u2028", "\x0b", "\x85", "\x1c", "\x0c", "z", " "]
+    assert dict_lines("") == [] and dict_lines("x\n") == ["x"] and dict_lines("x\n\n") == ["x", ""]
+    assert dict_lines("x\r") == ["x\r"] and dict_lines("x\r\n") == ["x"]  # a bare CR is not a terminator
+    # the file-reading path must not translate newlines either (newline="")
+    f = tmp_path / "dict.txt"
+    f.write_bytes(content.encode("utf-8"))
+    b = TextRecognitionPredictorBuilder().dict_path(str(f))
+    with open(b._dict, "r", encoding="utf-8", newline="") as fh:
+        assert character_list(dict_lines(fh.read())) == chars
+
+
 def test_recognition_builder_requires_dict():
     from oar_ocr_b200.ocr import OCRError, TextRecognitionPredictor
     with pytest.raises(OCRError) as e:

@@ -213,16 +213,20 @@ def test_import_rejects_what_it_cannot_run():
     assert "Gelu" in str(e.value) and "supported subset" in str(e.value)
 
 
-def test_model_source_accepts_onnx_files(tmp_path):
-    """OAROCRBuilder takes the reference's own model files: an .onnx path (or ONNX bytes) resolves to an OARG blob"""
+def test_model_source_accepts_onnx_files(tmp_path, built_lib):
+    """OAROCRBuilder takes the reference's own model files: an .onnx path (or ONNX bytes) is handed to the C ABI
+    unchanged (oar_model_load_onnx converts it inside the library); the library's conversion and the offline tool's
+    give the same OARG blob"""
+    from oar_ocr_b200 import ffi
     from oar_ocr_b200.ocr import _resolve_model
     blob = models.get_blob("det")
     path = tmp_path / "det.onnx"
     path.write_bytes(onnx_io.export_onnx(blob))
-    got = _resolve_model(str(path), "det")
+    data = _resolve_model(str(path), "det")
+    assert data == path.read_bytes() and _resolve_model(data, "det") == data
+    got = ffi.onnx_to_oarg(data)
     assert got[:4] == b"OARG"
     x = np.random.default_rng(0).standard_normal((1, 3, 32, 32)).astype(np.float32)
     assert np.array_equal(OracleNet(got).forward(x), OracleNet(blob).forward(x))
-    assert _resolve_model(path.read_bytes(), "det") == got
     assert onnx_io.main(["onnx_io", "convert", str(path), str(tmp_path / "det.oarg")]) == 0
     assert (tmp_path / "det.oarg").read_bytes() == got
