@@ -8,6 +8,9 @@ One step = one OAROCR::predict-equivalent pass (oar_pipeline_run) over one batch
 960x960 pages per GPU (BASELINE.json configs[1]).  Pages shard across ranks with no data-path collective
 (SURVEY.md 8e): scaling is weak, `value` = all ranks' images / max-over-ranks device time.
 
+  --workload rec512 : BASELINE.json configs[2] instead -- one oar_rec_run of 512 synthetic 48x320 crops per step
+                      (TextRecognitionPredictor semantics: the whole input is one batch); metric = crops/s
+
   value : inputs resident in HBM before the timed region; timed with CUDA events on the library's launch stream
   e2e   : the same call with HOST (pinned) page buffers: H2D of the pages and D2H of boxes/labels inside
   roofline : dominant kernel's achieved rate, from per-launch CUDA events in profiled steps after the timed region
@@ -35,6 +38,15 @@ UNIT = "images/s"
 SIZE = 960
 
 
+# The dense contractions run as 3 fp16 tcgen05 MMAs per k-step (hi*hi + hi*lo + lo*hi): the tensor-pipe
+# time of a *_tc kernel is 3 x its algorithmic FLOPs / the measured dense 16-bit peak.
+TC_PASSES = 3
+
+
+def is_tc(name: str) -> bool:
+    return name.endswith("_tc")
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -54,7 +66,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -90,7 +102,7 @@ def make_pages(rank: int, batch: int):
     return [synth.page(rank * batch + i, SIZE) for i in range(batch)]
 
 
-def cpu_reference_pass(pages, image_bs, region_bs, nets=None):
+def cpu_reference_pass(pages, image_bs, region_bs, nets=None, return_results=False):
     """One pass of the reference's CPU path (oracle port: Rust pre/post restated in C++, networks on torch-CPU
     fp32 standing in for ONNX Runtime CPU) over `pages`; returns (seconds, regions)."""
     import torch
@@ -102,7 +114,10 @@ def cpu_reference_pass(pages, image_bs, region_bs, nets=None):
         nets = (OracleNet(models.get_blob("det")), OracleNet(models.get_blob("rec")))
     t0 = time.perf_counter()
     res = pipeline.predict(nets[0], nets[1], pages, 18385, image_batch_size=image_bs, region_batch_size=region_bs)
-    return time.perf_counter() - t0, sum(len(r) for r in res), nets
+    dt = time.perf_counter() - t0
+    if return_results:
+        return dt, sum(len(r) for r in res), nets, res
+    return dt, sum(len(r) for r in res), nets
 
 
 def workload_config(args, world):
@@ -140,6 +155,73 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def kernel_roofline(ctx, step_fn, extra=None, P=2):
+    """Profiles P more steps with CUDA events around every launch; returns (roofline dict of the dominant kernel,
+    per-kernel table).  Algorithmic bytes / FLOPs per launch are the ones the library states at each launch site
+    (DESIGN.md 5); *_tc kernels are charged TC_PASSES fp16 MMAs per algorithmic FLOP."""
+    peaks = load_peaks()
+    ctx.profile(True)
+    agg = {}
+    raw = []
+    for _ in range(P):
+        step_fn()
+        recs = ctx.profile_read()
+        raw = recs
+        for r in recs:
+            a = agg.setdefault(r["name"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+            a["ms"] += r["ms"]
+            a["flops"] += r["flops"]
+            a["bytes"] += r["bytes"]
+            a["n"] += 1
+    ctx.profile(False)
+    kernels = []
+    tot = sum(a["ms"] for a in agg.values()) or 1.0
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        t = a["ms"] / 1000.0
+        gbs = a["bytes"] / t / 1e9 if t > 0 else 0.0
+        tfl = a["flops"] / t / 1e12 if t > 0 else 0.0
+        t_hbm = a["bytes"] / (peaks["hbm"] * 1e9)
+        t_tc = (TC_PASSES * a["flops"] / (peaks["tc"] * 1e12)) if is_tc(name) else 0.0
+        kernels.append(dict(name=name, launches_per_step=a["n"] // P, ms_per_step=a["ms"] / P,
+                            share=a["ms"] / tot, gbs=gbs, tflops=tfl, bound="hbm" if t_hbm >= t_tc else "tensor",
+                            avg_launch_us=1000.0 * a["ms"] / a["n"],
+                            roofline_frac=max(t_hbm, t_tc) / t if t > 0 else 0.0))
+    top = kernels[0]
+    if top["bound"] == "hbm":
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tc"] / TC_PASSES, "unit": "TFLOP/s",
+                "note": f"algorithmic FLOPs; every k-step is {TC_PASSES} fp16 MMAs (hi/lo operand split), so the "
+                        f"peak is the measured dense 16-bit rate / {TC_PASSES}"}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        tk = tj.get("kernels", {}).get(top["name"])
+        if tk:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+            # (profiles/traffic.json, keyed by kernel), scaled to the average launch of this run by the capture's
+            # traffic / algorithmic ratio
+            per_launch = (agg[top["name"]]["bytes"] / agg[top["name"]]["n"]) if agg[top["name"]]["n"] else 0.0
+            traffic = {"bytes_per_launch": tk["traffic_over_algorithmic"] * per_launch,
+                       "algorithmic_bytes_per_launch": per_launch,
+                       "ratio": tk["traffic_over_algorithmic"], "capture": tk["launch"]}
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["name"],
+                share_of_step=top["share"], avg_launch_us=top["avg_launch_us"], peak_source=peaks["source"],
+                measured=f"per-launch CUDA events on the launch stream, {P} profiled steps after the timed region")
+    # whole-step roofline: sum over kernels of max(bytes/BW, passes*flops/peak) / sum of kernel times
+    roof["step_frac"] = sum(k["roofline_frac"] * k["ms_per_step"] for k in kernels) / \
+        (sum(k["ms_per_step"] for k in kernels) or 1.0)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "bench_kernels.json"), "w") as f:
+            json.dump(dict(kernels=kernels, **(extra or {})), f, indent=1)
+        with open(os.path.join(out_dir, "bench_records.json"), "w") as f:
+            json.dump([[r["name"], round(r["ms"], 5), r["flops"], r["bytes"]] for r in raw], f)
+    return roof, kernels
 
 
 def run_b200(args, rank, local_rank, world):
@@ -226,75 +308,40 @@ def run_b200(args, rank, local_rank, world):
     e2e_value = world * B * args.steps / (e_ms / 1000.0)
 
     # ---- per-kernel roofline from profiled steps (after the timed region; events around every launch)
-    peaks = load_peaks()
-    roof = None
-    kernels = []
-    if rank == 0:
-        ctx.profile(True)
-        agg = {}
-        P = 2
-        raw = []
-        for _ in range(P):
-            step(dev_ptrs, True)
-            recs = ctx.profile_read()
-            raw = recs
-            for r in recs:
-                a = agg.setdefault(r["name"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
-                a["ms"] += r["ms"]
-                a["flops"] += r["flops"]
-                a["bytes"] += r["bytes"]
-                a["n"] += 1
-        ctx.profile(False)
-        tot = sum(a["ms"] for a in agg.values()) or 1.0
-        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            t = a["ms"] / 1000.0
-            gbs = a["bytes"] / t / 1e9 if t > 0 else 0.0
-            tfl = a["flops"] / t / 1e12 if t > 0 else 0.0
-            t_hbm = a["bytes"] / (peaks["hbm"] * 1e9)
-            t_tc = a["flops"] / (peaks["tc"] * 1e12)
-            kernels.append(dict(name=name, launches_per_step=a["n"] // P, ms_per_step=a["ms"] / P,
-                                share=a["ms"] / tot, gbs=gbs, tflops=tfl, bound="hbm" if t_hbm >= t_tc else "tensor",
-                                avg_launch_us=1000.0 * a["ms"] / a["n"],
-                                roofline_frac=max(t_hbm, t_tc) / t if t > 0 else 0.0))
-        top = kernels[0]
-        if top["bound"] == "hbm":
-            roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
-        else:
-            roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tc"], "unit": "TFLOP/s"}
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get("kernel") == top["name"]:
-                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, scaled to
-                # the average launch of this run by its measured traffic / algorithmic ratio
-                per_launch = (agg[top["name"]]["bytes"] / agg[top["name"]]["n"]) if agg[top["name"]]["n"] else 0.0
-                traffic = {"bytes_per_launch": tj["traffic_over_algorithmic"] * per_launch,
-                           "algorithmic_bytes_per_launch": per_launch,
-                           "ratio": tj["traffic_over_algorithmic"], "capture": tj["launch"]}
-        roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["name"],
-                    share_of_step=top["share"], avg_launch_us=top["avg_launch_us"], peak_source=peaks["source"],
-                    measured="per-launch CUDA events on the launch stream, 2 profiled steps after the timed region")
-        # whole-step roofline: sum over kernels of max(bytes/BW, flops/peak) / sum of kernel times
-        roof["step_frac"] = sum(k["roofline_frac"] * k["ms_per_step"] for k in kernels) / \
-            (sum(k["ms_per_step"] for k in kernels) or 1.0)
-        out_dir = os.path.join(ROOT, "gpurun_out")
-        if os.path.isdir(out_dir):
-            with open(os.path.join(out_dir, "bench_kernels.json"), "w") as f:
-                json.dump(dict(kernels=kernels, stage_ms=stage, e2e_stage_ms=e2e_stage), f, indent=1)
-            with open(os.path.join(out_dir, "bench_records.json"), "w") as f:
-                json.dump([[r["name"], round(r["ms"], 5), r["flops"], r["bytes"]] for r in raw], f)
+    roof, kernels = (kernel_roofline(ctx, lambda: step(dev_ptrs, True), dict(stage_ms=stage, e2e_stage_ms=e2e_stage))
+                     if rank == 0 else (None, []))
 
     cpu_base = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = args.ref_sample
         dt0, _, nets = cpu_reference_pass(pages[:1], args.image_batch_size, args.region_batch_size)
-        dt, n_reg, _ = cpu_reference_pass(pages[:sample], args.image_batch_size, args.region_batch_size, nets)
+        dt, n_reg, _, ref = cpu_reference_pass(pages[:sample], args.image_batch_size, args.region_batch_size, nets,
+                                               return_results=True)
         cpu_base = {"value": sample / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                     "sample": f"first {sample} of this run's {B} pages, one pass after one warm-up page "
                               f"({n_reg} text regions, {dt:.1f} s); oracle port: C++ restatement of the Rust "
                               "pre/post + torch-CPU fp32 networks (ONNX Runtime is not installable offline)"}
+        # the same pages through the CUDA path at the same batch sizes, compared region by region with the oracle run
+        # that was just timed: a parity datum at the bench configuration in the bench line itself
+        got = ocr.predict(pages[:sample])
+        boxes_equal = labels_equal = True
+        max_dscore = 0.0
+        n_cmp = label_diffs = 0
+        for g, w in zip(got, ref):
+            if len(g.text_regions) != len(w):
+                boxes_equal = labels_equal = False
+                continue
+            for r, o in zip(g.text_regions, w):
+                boxes_equal = boxes_equal and bool(np.array_equal(r.bounding_box.points, o["box"]))
+                same = bool(np.array_equal(r.label_indices, o["labels"]))
+                labels_equal = labels_equal and same
+                label_diffs += 0 if same else 1
+                max_dscore = max(max_dscore, abs(float(r.confidence) - float(o["score"])))
+                n_cmp += 1
+        parity = {"pages": sample, "regions": n_cmp, "boxes_equal": boxes_equal, "labels_equal": labels_equal,
+                  "regions_with_label_diffs": label_diffs, "max_dscore": max_dscore,
+                  "against": "oracle/ (CPU port), same pages, same image/region batch sizes"}
 
     if rank == 0:
         engine_dtype = "f32" if args.engine == 0 else ocr_dtype(ocr)
@@ -305,6 +352,7 @@ def run_b200(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_stage["h2d_bytes"]),
                     "d2h_bytes_per_step": int(e2e_stage["d2h_bytes"]), "ms_per_step": e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "parity_check": parity,
             "regions_per_step_rank0": regions, "wall_ms_per_step": wall / args.steps,
             "stage_ms_last_step": {k: round(v, 3) for k, v in stage.items() if k.startswith("ms_")},
             "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()}
@@ -312,6 +360,153 @@ def run_b200(args, rank, local_rank, world):
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+METRIC_REC = "recognizer-only text-line crops/sec (PP-OCRv5 mobile rec: SVTR neck + CTC, 48x320 crops)"
+UNIT_REC = "crops/s"
+
+
+def rec512_config(args, world):
+    return {"workload": f"recognizer only: one batch of {args.batch} synthetic 48x320 text-line crops per GPU per step "
+                        "(BASELINE.json configs[2]; TextRecognitionPredictor semantics: the whole input is ONE batch)",
+            "crops_per_step": args.batch * world, "weights": "synthetic planted-signal, seed 42, V=18385",
+            "l2": "flushed between steps (256 MiB memset on the launch stream)", "sharding": f"replicas x{world}"}
+
+
+def run_rec512(args, rank, local_rank, world):
+    """configs[2]: oar_rec_run(_ex) on 512 crops of 48x320.  value: crops resident in HBM; e2e: host crops, one pinned
+    staging copy + H2D inside, labels/scores D2H inside."""
+    import torch
+    import torch.distributed as dist
+    from oar_ocr_b200 import ffi, models, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = ffi.Context(local_rank)
+    rec = ffi.Model(ctx, models.get_blob("rec"))
+    if args.engine is not None:
+        rec.set_engine(args.engine)
+    B = args.batch
+    crops = [synth.crop(rank * B + j, 48, 320) for j in range(B)]
+    cb = 48 * 320 * 3
+    d_base = ctx.device_alloc(B * cb)
+    for i, c in enumerate(crops):
+        ctx.memcpy_h2d(d_base + i * cb, np.ascontiguousarray(c))
+    dev_ptrs = (C.c_void_p * B)(*[d_base + i * cb for i in range(B)])
+    hs = np.full(B, 48, np.int32)
+    ws = np.full(B, 320, np.int32)
+    last = {}
+
+    def step_dev():
+        ctx.l2_flush()
+        last["r"] = rec.rec_run_device(dev_ptrs, hs, ws, 18385, 48)
+
+    def step_host():
+        ctx.l2_flush()
+        last["r"] = rec.rec_run(crops, 18385)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
+        n0 = ffi.launch_count()
+        ctx.timer_start()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - w0) * 1000.0
+        launches = ffi.launch_count() - n0
+        barrier()
+        return max_over_ranks(ms), max_over_ranks(wall), launches, (sampler.stop() if sampler else None)
+
+    ms, wall, launches, clocks = timed(step_dev, args.steps, args.warmup, True)
+    value = world * B * args.steps / (ms / 1000.0)
+    e_ms, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
+    e2e_value = world * B * args.steps / (e_ms / 1000.0)
+    T = last["r"]["T"]
+    roof, kernels = kernel_roofline(ctx, step_dev) if rank == 0 else (None, [])
+    cpu_base = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import torch as _t
+        from oracle import pipeline
+        from oracle.net import OracleNet
+        _t.set_num_threads(os.cpu_count() or 1)
+        net = OracleNet(models.get_blob("rec"))
+        sample = min(B, args.ref_sample * 16)
+        pipeline.rec_forward(net, crops[:4], 18385)
+        t0 = time.perf_counter()
+        want = pipeline.rec_forward(net, crops[:sample], 18385)
+        dt = time.perf_counter() - t0
+        cpu_base = {"value": sample / dt, "unit": UNIT_REC, "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"first {sample} of the step's {B} crops as one batch ({dt:.1f} s); oracle port: C++ CRNN "
+                              "preprocess + torch-CPU fp32 network + CTC decode"}
+        got = rec.rec_run(crops[:sample], 18385)
+        parity = {"crops": sample,
+                  "labels_equal": all(bool(np.array_equal(a, b)) for a, b in zip(got["labels"], want["labels"])),
+                  "max_dscore": float(np.abs(got["scores"] - want["scores"]).max()),
+                  "against": "oracle/ (CPU port) on the same crops as one batch"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC_REC, "value": value, "unit": UNIT_REC, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": rec512_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT_REC, "h2d_bytes_per_step": B * cb,
+                    "d2h_bytes_per_step": B * (T * 8 + 8), "ms_per_step": e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "parity_check": parity, "seq_len": T, "wall_ms_per_step": wall / args.steps,
+            "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()}
+                            for kk in kernels[:6]],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_rec512(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    from oar_ocr_b200 import models, synth
+    from oracle import pipeline
+    from oracle.net import OracleNet
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = OracleNet(models.get_blob("rec"))
+    sample = min(args.batch, args.ref_sample * 16)
+    crops = [synth.crop(j, 48, 320) for j in range(sample)]
+    for _ in range(max(args.warmup, 0)):
+        pipeline.rec_forward(net, crops[:4], 18385)
+    total = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        pipeline.rec_forward(net, crops, 18385)
+        total += time.perf_counter() - t0
+    value = sample * args.steps / total
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC_REC, "value": value, "unit": UNIT_REC, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": rec512_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT_REC, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": f"{sample} of the workload's crops per step as one batch; oracle port"},
+        "e2e": {"value": value, "unit": UNIT_REC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
 
 
 def ocr_dtype(ocr) -> str:
@@ -323,10 +518,12 @@ def ocr_dtype(ocr) -> str:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="pages per GPU per step")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "rec512"],
+                    help="pipeline = BASELINE.json configs[1] (the headline metric); rec512 = configs[2], recognizer only")
+    ap.add_argument("--batch", type=int, default=None, help="pages (pipeline: 32) or crops (rec512: 512) per GPU per step")
     ap.add_argument("--image-batch-size", type=int, default=32)
     ap.add_argument("--region-batch-size", type=int, default=256)
     ap.add_argument("--engine", type=int, default=None, help="0 = fp32 SIMT engine, 1 = tcgen05 one kernel per layer, 2 = tcgen05 fused persistent blocks (default)")
@@ -338,7 +535,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.batch is None:
+        args.batch = 512 if args.workload == "rec512" else 32
+    if args.workload == "rec512":
+        if args.impl == "reference":
+            run_reference_rec512(args, rank, world)
+        else:
+            run_rec512(args, rank, local_rank, world)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, local_rank, world)

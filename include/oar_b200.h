@@ -270,6 +270,36 @@ int32_t oar_layout_postprocess(const float* pred, int32_t batch, int32_t num_box
                                const float* src_w, const float* src_h, const oar_layout_config* cfg, float* boxes,
                                int32_t* classes, float* scores, int32_t* counts);
 
+/* ---- seam 2 (recognition from pages + boxes): the second half of OAROCR::predict --------------------------------
+ * (get_rotate_crop_image, oar-ocr-core/src/utils/transform.rs:76-502 -> recognize_global, src/oarocr/ocr.rs:802-897
+ *  -> TextRecognitionAdapter::execute, text_recognition_adapter.rs:35-111).  SURVEY.md 8b: oar_crop_rec_run.
+ * images: n pages (host, or device pointers when images_on_device != 0); boxes [n_boxes][4][2] in page coordinates,
+ * box k cropped from page img_index[k].  The crops are pooled in the caller's box order (flush at 4096), stably sorted
+ * by width / height and recognised in batches of region_batch_size -- exactly as predict() batches its own boxes.
+ * Per box k: status[k] = 0 ok, 1 = the crop failed (the reference skips it, processors.rs:104-106);
+ * labels/cols [k][t_cap] (first lens[k] valid; empty when scores[k] < rec_score_thresh), seq_len[k] (may be NULL) =
+ * sequence length T of the batch box k was recognised in. */
+int32_t oar_crop_rec_run(oar_model* rec, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                         int32_t images_on_device, const float* boxes, const int32_t* img_index, int32_t n_boxes,
+                         int32_t region_batch_size, int32_t n_chars, float rec_score_thresh, int32_t* status,
+                         int32_t* labels, int32_t* cols, int32_t* lens, float* scores, int32_t* seq_len, int32_t t_cap);
+
+/* oar_rec_run with crops that may already be resident in HBM (crops_on_device != 0: device pointers, u8 HWC).  Host
+ * crops are packed into one pinned buffer and uploaded with a single copy. */
+int32_t oar_rec_run_ex(oar_model* rec, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                       int32_t crops_on_device, int32_t n_chars, int32_t* labels, int32_t* cols, int32_t* lens,
+                       float* scores, int32_t t_cap, int32_t* t_out);
+
+/* ---- OAROCR::predict on several GPUs inside one process (one host thread + CUDA context per GPU) ----
+ * dets[g] / recs[g]: the same two models loaded on n_ctx different contexts (normally one per device).  Equal to ONE
+ * un-sharded oar_pipeline_run over all pages: pages are dealt to the contexts in contiguous blocks for upload,
+ * detection and cropping; recognize_global is planned once over ALL crops and whole batches are dealt round-robin, a
+ * context fetching the crops that live in another context's HBM over the peer link.  No collective on the path.
+ * Host pages only.  Stage times in `out` are those of the slowest context. */
+int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, int32_t n_ctx,
+                               const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                               const oar_pipeline_config* cfg, oar_ocr_result* out);
+
 /* device memory helpers for callers that keep inputs resident (bench `value` leg) */
 int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out);
 int32_t oar_device_free(oar_ctx* ctx, void* p);

@@ -20,6 +20,7 @@ SOURCES = {
     "engine.cu": [],
     "gemm_tc.cu": [],
     "fused_tc.cu": [],
+    "fused_simt.cu": [],
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
     "layout.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only f32 restatement: no FMA contraction

@@ -20,6 +20,10 @@
 
 #include <cstdlib>
 
+#include <functional>
+#include <memory>
+#include <thread>
+
 #include "engine.cuh"
 #include "prepost.cuh"
 
@@ -229,14 +233,13 @@ void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, cons
   out.counts = ctx->arena.get<int32_t>(B);
   auto mark = ctx->arena.mark();
   const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data(), B);
+  // the network reads the u8 pages itself: NormalizeImage is folded into the stem convolution (engine.cu / fused_simt.cu)
   Tensor in;
   in.B = B, in.H = g.H, in.W = g.W, in.C = 3;
-  in.p = ctx->arena.get<float>(in.numel());
-  int src[3];
-  float alpha[3], beta[3];
-  det_norm_coeffs(src, alpha, beta);
-  launch_normalize(ctx, nullptr, d_table, aligned, in.p, B, g.H, g.W, src, alpha, beta, /*NHWC*/ 1);
-  Tensor prob = model_forward(det, in, false, nullptr);
+  U8Input u8{};
+  u8.mode = 0, u8.table = d_table, u8.B = B, u8.H = g.H, u8.W = g.W, u8.table_aligned = aligned ? 1 : 0;
+  det_norm_coeffs(u8.src, u8.a, u8.b);
+  Tensor prob = model_forward(det, in, false, nullptr, &u8);
   if (prob.B != B || prob.H != g.H || prob.W != g.W || prob.C != 1)
     OAR_FAIL(OAR_E_MODEL, "detector output %dx%dx%dx%d does not match its %dx%d input", prob.B, prob.H, prob.W, prob.C,
              g.H, g.W);
@@ -438,10 +441,10 @@ void launch_rec_batch(oar_model* rec, const RecCrop* crops, int n, int n_chars, 
   launch_resize_triangle(ctx, d_jobs, n, max_sw, max_dw, REC_H);
   Tensor in;
   in.B = n, in.H = REC_H, in.W = tensor_w, in.C = 3;
-  in.p = ctx->arena.get<float>(in.numel());
-  launch_crnn_normalize(ctx, d_cj, n, REC_H, tensor_w, in.p, /*NHWC*/ 1);
+  U8Input u8{};  // normalize_crnn_chw_into folded into the stem convolution
+  u8.mode = 1, u8.jobs = d_cj, u8.B = n, u8.H = REC_H, u8.W = tensor_w;
   CtcOut ctc;
-  model_forward(rec, in, false, &ctc);
+  model_forward(rec, in, false, &ctc, &u8);
   if (ctc.B != n || ctc.T <= 0) OAR_FAIL(OAR_E_MODEL, "recognizer produced no CTC output");
   const int T = ctc.T;
   out.T = T;
@@ -498,13 +501,11 @@ int launch_cls_batch(oar_model* cls, const RecCrop* crops, int n, int ih, int iw
   launch_resize_triangle(ctx, d_jobs, n, max_sw, iw, ih);
   Tensor in;
   in.B = n, in.H = ih, in.W = iw, in.C = 3;
-  in.p = ctx->arena.get<float>(in.numel());
-  int src[3];
-  float alpha[3], beta[3];
-  cls_norm_coeffs(src, alpha, beta);
-  launch_normalize(ctx, nullptr, d_table, aligned, in.p, n, ih, iw, src, alpha, beta, /*NHWC*/ 1);
+  U8Input u8{};
+  u8.mode = 0, u8.table = d_table, u8.B = n, u8.H = ih, u8.W = iw, u8.table_aligned = aligned ? 1 : 0;
+  cls_norm_coeffs(u8.src, u8.a, u8.b);
   CtcOut head;
-  Tensor probs = model_forward(cls, in, /*want_probs=*/true, &head);
+  Tensor probs = model_forward(cls, in, /*want_probs=*/true, &head, &u8);
   if (!probs.p || probs.B != n || probs.H * probs.W != 1 || probs.C <= 0)
     OAR_FAIL(OAR_E_MODEL, "classifier output %dx%dx%dx%d is not [n,1,1,classes]", probs.B, probs.H, probs.W, probs.C);
   const int C = probs.C;
@@ -1072,6 +1073,12 @@ int32_t oar_ctc_decode(oar_ctx* ctx, const float* pred, int32_t b, int32_t t, in
 int32_t oar_rec_run(oar_model* rec, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
                     int32_t n_chars, int32_t* labels, int32_t* cols, int32_t* lens, float* scores, int32_t t_cap,
                     int32_t* t_out) {
+  return oar_rec_run_ex(rec, crops, hs, ws, n, 0, n_chars, labels, cols, lens, scores, t_cap, t_out);
+}
+
+int32_t oar_rec_run_ex(oar_model* rec, const uint8_t* const* crops, const int32_t* hs, const int32_t* ws, int32_t n,
+                       int32_t crops_on_device, int32_t n_chars, int32_t* labels, int32_t* cols, int32_t* lens,
+                       float* scores, int32_t t_cap, int32_t* t_out) {
   API_TRY
   if (!rec || rec->kind != OAR_KIND_REC) OAR_FAIL(OAR_E_INVALID, "not a recognition model");
   if (t_out) *t_out = 0;
@@ -1080,12 +1087,25 @@ int32_t oar_rec_run(oar_model* rec, const uint8_t* const* crops, const int32_t* 
   oar_ctx* ctx = rec->ctx;
   CallGuard guard(ctx);
   std::vector<RecCrop> rc(n);
+  size_t total = 0;
   for (int i = 0; i < n; ++i) {
     if (hs[i] <= 0 || ws[i] <= 0 || !crops[i]) OAR_FAIL(OAR_E_INVALID, "crop %d is empty", i);
-    size_t bytes = (size_t)hs[i] * ws[i] * 3;
-    uint8_t* d = ctx->arena.get<uint8_t>(bytes);
-    OAR_CUDA(cudaMemcpyAsync(d, crops[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc[i] = RecCrop{d, hs[i], ws[i]};
+    total += ((size_t)hs[i] * ws[i] * 3 + 15) & ~(size_t)15;
+  }
+  if (crops_on_device) {
+    for (int i = 0; i < n; ++i) rc[i] = RecCrop{crops[i], hs[i], ws[i]};
+  } else {
+    // one pinned staging buffer, one copy (a copy per crop from pageable memory costs ~10 us each)
+    uint8_t* h = (uint8_t*)ctx->pinned_get(total);
+    uint8_t* d = ctx->arena.get<uint8_t>(total);
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      const size_t bytes = (size_t)hs[i] * ws[i] * 3;
+      memcpy(h + off, crops[i], bytes);
+      rc[i] = RecCrop{d + off, hs[i], ws[i]};
+      off += (bytes + 15) & ~(size_t)15;
+    }
+    OAR_CUDA(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, ctx->stream));
   }
   RecBatchOut out;
   launch_rec_batch(rec, rc.data(), n, n_chars, out);
@@ -1163,16 +1183,272 @@ int32_t oar_rotate180(oar_ctx* ctx, const uint8_t* image, int32_t h, int32_t w, 
   API_CATCH
 }
 
-int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
-                         const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
-                         oar_ocr_result* out) {
-  return oar_pipeline_run_cls(det, rec, nullptr, images, hs, ws, n, images_on_device, cfg, out);
+// ---------------------------------------------------------------------------
+// OAROCR::predict in stages (ocr.rs:518-659).  One PageStage per context: pages -> HBM, detection + reading-order
+// sort, crop (+ optional line orientation).  Recognition works on a flat list of crop references in global
+// (image, detection) order, which may point into the crop pools of several contexts (oar_pipeline_run_multi).
+// ---------------------------------------------------------------------------
+namespace {
+
+struct PageStage {
+  oar_ctx* ctx = nullptr;
+  int n = 0;  // images of this stage
+  std::vector<DevImage> imgs;
+  std::vector<std::vector<float>> sorted_boxes;  // per image: count * 8 floats, reading order
+  std::vector<int> box_first;                    // [n + 1] prefix sums of the box counts
+  int n_boxes = 0;
+  CropPlan* h_plans = nullptr;  // pinned, [n_boxes]: status, dims, wh_ratio, pool offset
+  uint8_t* pool = nullptr;      // device crop pool
+  std::vector<int> valid_of;    // box -> index among the valid crops (orientation stage)
+  int32_t* h_cls_ids = nullptr; // pinned, per valid crop (after the final synchronise)
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
+  float ms_det = 0, ms_post = 0;
+  cudaEvent_t ev[6] = {};
+};
+
+// pages into HBM.  Host pages go through a copy stream in slices of `slice` pages, with one event per slice, so that
+// detection of slice k overlaps the upload of slice k + 1 (the caller makes the launch stream wait per slice).
+void stage_upload(PageStage& S, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int n,
+                  int on_device) {
+  oar_ctx* ctx = S.ctx;
+  S.n = n;
+  S.imgs.resize(n);
+  for (int i = 0; i < n; ++i) {
+    if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
+    if (on_device) {
+      S.imgs[i] = DevImage{images[i], hs[i], ws[i]};
+    } else {
+      size_t bytes = (size_t)hs[i] * ws[i] * 3;
+      uint8_t* d = ctx->arena.get<uint8_t>(bytes);
+      OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+      S.imgs[i] = DevImage{d, hs[i], ws[i]};
+      S.h2d_bytes += (int64_t)bytes;
+    }
+  }
 }
 
-int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
-                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
-                             const oar_pipeline_config* cfg, oar_ocr_result* out) {
-  API_TRY
+// detection (chunks of image_batch_size) + sort_quad_boxes per image
+void stage_detect(PageStage& S, oar_model* det, const oar_pipeline_config* cfg) {
+  DetResult dres;
+  run_detection(det, S.imgs, cfg->det, cfg->image_batch_size, dres, true);
+  S.ms_det = dres.ms_net, S.ms_post = dres.ms_post;
+  const int n = S.n;
+  S.sorted_boxes.assign(n, {});
+  S.box_first.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    int cnt = (int)dres.scores[i].size();
+    std::vector<int> ord;
+    sort_quads_host(dres.boxes[i].data(), cnt, ord);
+    S.sorted_boxes[i].resize((size_t)cnt * 8);
+    for (int k = 0; k < cnt; ++k)
+      memcpy(&S.sorted_boxes[i][(size_t)k * 8], &dres.boxes[i][(size_t)ord[k] * 8], 8 * sizeof(float));
+    S.box_first[i + 1] = S.box_first[i] + cnt;
+    S.d2h_bytes += (int64_t)cnt * 36 + 4;
+  }
+  S.n_boxes = S.box_first[n];
+}
+
+// caller-supplied boxes (oar_crop_rec_run): box k of the call belongs to image img_index[k]; order within an image kept
+void stage_set_boxes(PageStage& S, const float* boxes, const int32_t* img_index, int n_boxes, std::vector<int>& slot_of) {
+  const int n = S.n;
+  S.sorted_boxes.assign(n, {});
+  S.box_first.assign(n + 1, 0);
+  for (int k = 0; k < n_boxes; ++k) {
+    if (img_index[k] < 0 || img_index[k] >= n) OAR_FAIL(OAR_E_INVALID, "box %d names image %d of %d", k, img_index[k], n);
+    ++S.box_first[img_index[k] + 1];
+  }
+  for (int i = 0; i < n; ++i) S.box_first[i + 1] += S.box_first[i];
+  std::vector<int> fill(S.box_first.begin(), S.box_first.end() - 1);
+  for (int i = 0; i < n; ++i) S.sorted_boxes[i].resize((size_t)(S.box_first[i + 1] - S.box_first[i]) * 8);
+  slot_of.assign(n_boxes, 0);
+  for (int k = 0; k < n_boxes; ++k) {
+    const int i = img_index[k], pos = fill[i]++;
+    memcpy(&S.sorted_boxes[i][(size_t)(pos - S.box_first[i]) * 8], boxes + (size_t)k * 8, 8 * sizeof(float));
+    slot_of[k] = pos;
+  }
+  S.n_boxes = n_boxes;
+}
+
+// get_rotate_crop_image for every box: plan on device, sizes back to the host, one warp launch for all
+void stage_crop(PageStage& S) {
+  oar_ctx* ctx = S.ctx;
+  cudaStream_t st = ctx->stream;
+  const int n = S.n, n_boxes = S.n_boxes;
+  S.pool = nullptr;
+  S.h_plans = nullptr;
+  if (n_boxes <= 0) return;
+  std::vector<CropPlan> plans(n_boxes);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < S.box_first[i + 1] - S.box_first[i]; ++k) {
+      CropPlan& p = plans[S.box_first[i] + k];
+      memset(&p, 0, sizeof(CropPlan));
+      memcpy(p.quad, &S.sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
+      p.img = i;
+    }
+  std::vector<ImageRef> refs(n);
+  for (int i = 0; i < n; ++i) refs[i] = ImageRef{S.imgs[i].p, S.imgs[i].h, S.imgs[i].w};
+  ImageRef* d_refs = to_device(ctx, refs.data(), refs.size());
+  CropPlan* d_plans = to_device(ctx, plans.data(), plans.size());
+  launch_crop_plan(ctx, d_plans, n_boxes, d_refs);
+  S.h_plans = (CropPlan*)ctx->pinned_get(sizeof(CropPlan) * n_boxes);
+  OAR_CUDA(cudaMemcpyAsync(S.h_plans, d_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyDeviceToHost, st));
+  OAR_CUDA(cudaStreamSynchronize(st));
+  long long total_px = 0;
+  for (int i = 0; i < n_boxes; ++i) {
+    S.h_plans[i].out_off = total_px * 3;
+    if (S.h_plans[i].status == 0) total_px += (long long)S.h_plans[i].ow * S.h_plans[i].oh;
+  }
+  if (total_px > 0) {
+    OAR_CUDA(cudaMemcpyAsync(d_plans, S.h_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyHostToDevice, st));
+    S.pool = ctx->arena.get<uint8_t>((size_t)total_px * 3);
+    launch_crop_warp(ctx, d_plans, n_boxes, d_refs, S.pool, total_px);
+  }
+}
+
+// Line orientation (ocr.rs:615, 755-792): classify every crop, rotate class-1 crops by 180 degrees in the pool.
+// The reference calls the adapter once per image; the classifier treats every crop independently (fixed 80 x 160
+// input, per-sample pooling), so one pass over all crops in chunks gives the same classes.  No host round trip:
+// the rotation kernel reads the class ids on the device; the host reads them after the final synchronise.
+void stage_orient(PageStage& S, oar_model* cls) {
+  oar_ctx* ctx = S.ctx;
+  S.valid_of.assign(S.n_boxes, -1);
+  S.h_cls_ids = nullptr;
+  if (!cls || !S.pool) return;
+  std::vector<int> valid;
+  for (int i = 0; i < S.n_boxes; ++i)
+    if (S.h_plans[i].status == 0) S.valid_of[i] = (int)valid.size(), valid.push_back(i);
+  const int nv = (int)valid.size();
+  int32_t* d_ids = ctx->arena.get<int32_t>(nv);
+  float* d_sc = ctx->arena.get<float>(nv);
+  std::vector<Rot180Job> rj(nv);
+  int max_npix = 0;
+  for (int s0 = 0; s0 < nv; s0 += CLS_CHUNK) {
+    int m = std::min(CLS_CHUNK, nv - s0);
+    std::vector<RecCrop> rc(m);
+    for (int k = 0; k < m; ++k) {
+      const CropPlan& p = S.h_plans[valid[s0 + k]];
+      rc[k] = RecCrop{S.pool + p.out_off, p.oh, p.ow};
+      rj[s0 + k] = Rot180Job{S.pool + p.out_off, p.oh * p.ow};
+      max_npix = std::max(max_npix, p.oh * p.ow);
+    }
+    launch_cls_batch(cls, rc.data(), m, CLS_H, CLS_W, d_ids + s0, d_sc + s0, nullptr, 0);
+  }
+  Rot180Job* d_rj = to_device(ctx, rj.data(), rj.size());
+  launch_rotate180(ctx, d_rj, nv, max_npix, d_ids);
+  S.h_cls_ids = (int32_t*)ctx->pinned_get((size_t)nv * sizeof(int32_t));
+  OAR_CUDA(cudaMemcpyAsync(S.h_cls_ids, d_ids, (size_t)nv * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  S.d2h_bytes += (int64_t)nv * 4;
+}
+
+// one crop of the global pool: where its pixels live and what recognize_global needs to know about it
+struct CropRef {
+  int stage;  // owning PageStage (= context)
+  int box;    // box index inside that stage
+  const uint8_t* p;
+  int h, w;
+  float ratio;
+};
+// recognize_global (ocr.rs:802-897): waves of at most MAX_POOLED_CROPS crops in pool order, each stably sorted by
+// wh_ratio and cut into chunks of region_batch_size.  chunk = [first, first + n) of `order`.
+struct RecChunk {
+  size_t first;
+  int n;
+  RecBatchOut out;
+  int stage = 0;  // the context that recognises it
+};
+struct RecPlan {
+  std::vector<int> order;  // indices into the CropRef list, wave by wave in wh-ratio order
+  std::vector<RecChunk> chunks;
+};
+void plan_recognition(const std::vector<CropRef>& refs, int region_batch_size, RecPlan& plan) {
+  plan.order.clear();
+  plan.chunks.clear();
+  plan.order.reserve(refs.size());
+  for (size_t w0 = 0; w0 < refs.size(); w0 += MAX_POOLED_CROPS) {
+    const size_t w1 = std::min(refs.size(), w0 + (size_t)MAX_POOLED_CROPS);
+    const size_t base = plan.order.size();
+    for (size_t i = w0; i < w1; ++i) plan.order.push_back((int)i);
+    std::stable_sort(plan.order.begin() + base, plan.order.end(),
+                     [&](int a, int b) { return refs[a].ratio < refs[b].ratio; });
+    for (size_t s0 = base; s0 < plan.order.size(); s0 += region_batch_size) {
+      RecChunk c;
+      c.first = s0;
+      c.n = (int)std::min<size_t>(region_batch_size, plan.order.size() - s0);
+      plan.chunks.push_back(c);
+    }
+  }
+}
+
+// per crop reference, after recognition: where its results are
+struct RecResult {
+  int len = -1;  // -1: not recognised
+  const int32_t* labels = nullptr;
+  const int32_t* cols = nullptr;
+  int T = 0;
+  float score = 0.0f, chunk_max_ratio = 0.0f;
+};
+void collect_results(const std::vector<CropRef>& refs, const RecPlan& plan, float rec_score_thresh,
+                     std::vector<RecResult>& res, int64_t* d2h_bytes) {
+  res.assign(refs.size(), RecResult{});
+  const float base_rec_ratio = (float)REC_W / (float)REC_H;  // DEFAULT_REC_IMAGE_SHAPE, ocr.rs:817
+  for (const RecChunk& ch : plan.chunks) {
+    float chunk_max = base_rec_ratio;
+    for (int k = 0; k < ch.n; ++k) chunk_max = std::fmax(chunk_max, refs[plan.order[ch.first + k]].ratio);
+    for (int k = 0; k < ch.n; ++k) {
+      RecResult& r = res[plan.order[ch.first + k]];
+      r.cols = ch.out.h_cols + (size_t)k * ch.out.T;
+      r.labels = ch.out.h_labels + (size_t)k * ch.out.T;
+      r.T = ch.out.T;
+      r.chunk_max_ratio = chunk_max;
+      r.score = ch.out.h_scores[k];
+      // TextRecognitionAdapter::execute: score below the threshold keeps the slot with empty text
+      r.len = r.score >= rec_score_thresh ? ch.out.h_lens[k] : 0;
+    }
+    if (d2h_bytes) *d2h_bytes += (int64_t)ch.n * (ch.out.T * 8 + 8);
+  }
+}
+
+// crop references of one stage in (image, detection) order; failed crops are skipped (processors.rs:104-106)
+void append_refs(const PageStage& S, int stage_index, std::vector<CropRef>& refs, std::vector<int>* ref_of_box) {
+  if (ref_of_box) ref_of_box->assign(S.n_boxes, -1);
+  for (int i = 0; i < S.n_boxes; ++i) {
+    const CropPlan& p = S.h_plans[i];
+    if (p.status != 0) continue;
+    if (ref_of_box) (*ref_of_box)[i] = (int)refs.size();
+    refs.push_back(CropRef{stage_index, i, S.pool + p.out_off, p.oh, p.ow, p.wh_ratio});
+  }
+}
+
+// scatter to per-image, detection-index order (ocr.rs:879-892, 637-656); images [img0, img0 + S.n) of the result
+void scatter_stage(const PageStage& S, int img0, const std::vector<int>& ref_of_box, const std::vector<RecResult>& res,
+                   oar_ocr_result* out, int& r, long long& nl) {
+  for (int i = 0; i < S.n; ++i) {
+    out->region_off[img0 + i] = r;
+    for (int k = 0; k < S.box_first[i + 1] - S.box_first[i]; ++k) {
+      const int box = S.box_first[i] + k;
+      const int ref = ref_of_box[box];
+      if (ref < 0 || res[ref].len < 0) continue;
+      const RecResult& rr = res[ref];
+      if (r >= out->cap_regions || nl + rr.len > out->cap_labels)
+        OAR_FAIL(OAR_E_CAPACITY, "result buffers too small (regions %d, labels %d)", out->cap_regions, out->cap_labels);
+      if (out->boxes) memcpy(out->boxes + (size_t)r * 8, &S.sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
+      if (out->scores) out->scores[r] = rr.score;
+      if (out->det_index) out->det_index[r] = k;
+      if (out->label_off) out->label_off[r] = (int32_t)nl;
+      if (out->labels && rr.len > 0) memcpy(out->labels + nl, rr.labels, (size_t)rr.len * 4);
+      if (out->cols && rr.len > 0) memcpy(out->cols + nl, rr.cols, (size_t)rr.len * 4);
+      if (out->seq_len) out->seq_len[r] = rr.T;
+      if (out->wh_ratio) out->wh_ratio[r] = S.h_plans[box].wh_ratio;
+      if (out->max_wh_ratio) out->max_wh_ratio[r] = rr.chunk_max_ratio;
+      if (out->line_angle) out->line_angle[r] = S.h_cls_ids ? (float)S.h_cls_ids[S.valid_of[box]] * 180.0f : -1.0f;
+      nl += rr.len;
+      ++r;
+    }
+  }
+}
+
+void check_pipeline_args(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images, const int32_t* hs,
+                         const int32_t* ws, int32_t n, const oar_pipeline_config* cfg, oar_ocr_result* out) {
   if (!det || det->kind != OAR_KIND_DET || !rec || rec->kind != OAR_KIND_REC)
     OAR_FAIL(OAR_E_INVALID, "pipeline needs one detection and one recognition model");
   if (det->ctx != rec->ctx) OAR_FAIL(OAR_E_INVALID, "both models must live on the same context");
@@ -1184,218 +1460,266 @@ int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, con
   if (cfg->image_batch_size <= 0 || cfg->region_batch_size <= 0)
     OAR_FAIL(OAR_E_INVALID, "batch sizes must be positive");  // ocr.rs:1168-1195
   if (!out->region_off) OAR_FAIL(OAR_E_INVALID, "null result buffers");
+}
+
+}  // namespace
+
+int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* images, const int32_t* hs,
+                         const int32_t* ws, int32_t n, int32_t images_on_device, const oar_pipeline_config* cfg,
+                         oar_ocr_result* out) {
+  return oar_pipeline_run_cls(det, rec, nullptr, images, hs, ws, n, images_on_device, cfg, out);
+}
+
+int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
+                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
+                             const oar_pipeline_config* cfg, oar_ocr_result* out) {
+  API_TRY
+  check_pipeline_args(det, rec, cls, images, hs, ws, n, cfg, out);
   oar_ctx* ctx = det->ctx;
   CallGuard guard(ctx);
   cudaStream_t st = ctx->stream;
-  cudaEvent_t ev[6];
-  for (auto& e : ev) e = ctx->next_event();
+  PageStage S;
+  S.ctx = ctx;
+  for (auto& e : S.ev) e = ctx->next_event();
   out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
   out->h2d_bytes = out->d2h_bytes = 0;
-  cudaEventRecord(ev[0], st);
-
-  // ---- pages into HBM
-  std::vector<DevImage> imgs(n);
-  for (int i = 0; i < n; ++i) {
-    if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
-    if (images_on_device) {
-      imgs[i] = DevImage{images[i], hs[i], ws[i]};
-    } else {
-      size_t bytes = (size_t)hs[i] * ws[i] * 3;
-      uint8_t* d = ctx->arena.get<uint8_t>(bytes);
-      OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, st));
-      imgs[i] = DevImage{d, hs[i], ws[i]};
-      out->h2d_bytes += (int64_t)bytes;
-    }
-  }
-  cudaEventRecord(ev[1], st);
-
-  // ---- detection (chunks of image_batch_size) + reading-order sort
-  DetResult dres;
-  run_detection(det, imgs, cfg->det, cfg->image_batch_size, dres, true);
-  out->ms_det = dres.ms_net;
-  out->ms_post = dres.ms_post;
-  cudaEventRecord(ev[2], st);
-  std::vector<std::vector<float>> sorted_boxes(n);
-  std::vector<int> box_first(n + 1, 0);
-  for (int i = 0; i < n; ++i) {
-    int cnt = (int)dres.scores[i].size();
-    std::vector<int> ord;
-    sort_quads_host(dres.boxes[i].data(), cnt, ord);
-    sorted_boxes[i].resize((size_t)cnt * 8);
-    for (int k = 0; k < cnt; ++k)
-      memcpy(&sorted_boxes[i][(size_t)k * 8], &dres.boxes[i][(size_t)ord[k] * 8], 8 * sizeof(float));
-    box_first[i + 1] = box_first[i] + cnt;
-    out->d2h_bytes += (int64_t)cnt * 36 + 4;
-  }
-  const int n_boxes = box_first[n];
-
-  // ---- crop every box (plan on device, sizes back to the host, one warp launch for all)
-  std::vector<CropPlan> plans(n_boxes);
-  CropPlan* h_plans = nullptr;
-  uint8_t* pool = nullptr;
-  if (n_boxes > 0) {
-    for (int i = 0; i < n; ++i)
-      for (int k = 0; k < box_first[i + 1] - box_first[i]; ++k) {
-        CropPlan& p = plans[box_first[i] + k];
-        memset(&p, 0, sizeof(CropPlan));
-        memcpy(p.quad, &sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
-        p.img = i;
-      }
-    std::vector<ImageRef> refs(n);
-    for (int i = 0; i < n; ++i) refs[i] = ImageRef{imgs[i].p, imgs[i].h, imgs[i].w};
-    ImageRef* d_refs = to_device(ctx, refs.data(), refs.size());
-    CropPlan* d_plans = to_device(ctx, plans.data(), plans.size());
-    launch_crop_plan(ctx, d_plans, n_boxes, d_refs);
-    h_plans = (CropPlan*)ctx->pinned_get(sizeof(CropPlan) * n_boxes);
-    OAR_CUDA(cudaMemcpyAsync(h_plans, d_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyDeviceToHost, st));
-    OAR_CUDA(cudaStreamSynchronize(st));
-    long long total_px = 0;
-    for (int i = 0; i < n_boxes; ++i) {
-      h_plans[i].out_off = total_px * 3;
-      if (h_plans[i].status == 0) total_px += (long long)h_plans[i].ow * h_plans[i].oh;
-    }
-    if (total_px > 0) {
-      OAR_CUDA(cudaMemcpyAsync(d_plans, h_plans, sizeof(CropPlan) * n_boxes, cudaMemcpyHostToDevice, st));
-      pool = ctx->arena.get<uint8_t>((size_t)total_px * 3);
-      launch_crop_warp(ctx, d_plans, n_boxes, d_refs, pool, total_px);
-    }
-  }
-  cudaEventRecord(ev[3], st);
-
-  // ---- line orientation (ocr.rs:615, 755-792): classify every crop, rotate class-1 crops by 180 degrees in the pool.
-  // The reference calls the adapter once per image; the classifier treats every crop independently (fixed 80 x 160
-  // input, per-sample pooling), so one pass over all crops in chunks gives the same classes.  No host round trip:
-  // the rotation kernel reads the class ids on the device; the host reads them after the final synchronise.
-  std::vector<int> valid_of(n_boxes, -1);
-  int32_t* h_cls_ids = nullptr;
-  if (cls && pool) {
-    std::vector<int> valid;
-    for (int i = 0; i < n_boxes; ++i)
-      if (h_plans[i].status == 0) valid_of[i] = (int)valid.size(), valid.push_back(i);
-    const int nv = (int)valid.size();
-    int32_t* d_ids = ctx->arena.get<int32_t>(nv);
-    float* d_sc = ctx->arena.get<float>(nv);
-    std::vector<Rot180Job> rj(nv);
-    int max_npix = 0;
-    for (int s0 = 0; s0 < nv; s0 += CLS_CHUNK) {
-      int m = std::min(CLS_CHUNK, nv - s0);
-      std::vector<RecCrop> rc(m);
-      for (int k = 0; k < m; ++k) {
-        const CropPlan& p = h_plans[valid[s0 + k]];
-        rc[k] = RecCrop{pool + p.out_off, p.oh, p.ow};
-        rj[s0 + k] = Rot180Job{pool + p.out_off, p.oh * p.ow};
-        max_npix = std::max(max_npix, p.oh * p.ow);
-      }
-      launch_cls_batch(cls, rc.data(), m, CLS_H, CLS_W, d_ids + s0, d_sc + s0, nullptr, 0);
-    }
-    Rot180Job* d_rj = to_device(ctx, rj.data(), rj.size());
-    launch_rotate180(ctx, d_rj, nv, max_npix, d_ids);
-    h_cls_ids = (int32_t*)ctx->pinned_get((size_t)nv * sizeof(int32_t));
-    OAR_CUDA(cudaMemcpyAsync(h_cls_ids, d_ids, (size_t)nv * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    out->d2h_bytes += (int64_t)nv * 4;
-  }
-  cudaEventRecord(ev[5], st);
+  cudaEventRecord(S.ev[0], st);
+  stage_upload(S, images, hs, ws, n, images_on_device);
+  cudaEventRecord(S.ev[1], st);
+  stage_detect(S, det, cfg);
+  cudaEventRecord(S.ev[2], st);
+  stage_crop(S);
+  cudaEventRecord(S.ev[3], st);
+  stage_orient(S, cls);
+  cudaEventRecord(S.ev[5], st);
 
   // ---- recognition: pool crops across images, flush at MAX_POOLED_CROPS, sort by wh_ratio, chunk
-  struct Pooled {
-    int box;  // global box index (image-major, reading order)
-  };
-  struct Wave {
-    std::vector<int> sorted;  // global box indices, wh-ratio order
-    std::vector<RecBatchOut> chunks;
-  };
-  std::vector<Wave> waves;
-  {
-    std::vector<int> cur;
-    for (int i = 0; i < n_boxes; ++i) {
-      if (h_plans[i].status != 0) continue;  // failed crop: skipped, processors.rs:104-106
-      cur.push_back(i);
-      if ((int)cur.size() >= MAX_POOLED_CROPS) {
-        waves.push_back(Wave{cur, {}});
-        cur.clear();
-      }
+  std::vector<CropRef> refs;
+  std::vector<int> ref_of_box;
+  if (S.n_boxes > 0) append_refs(S, 0, refs, &ref_of_box);
+  RecPlan plan;
+  plan_recognition(refs, cfg->region_batch_size, plan);
+  std::vector<RecCrop> rc;
+  for (RecChunk& ch : plan.chunks) {
+    rc.resize(ch.n);
+    for (int k = 0; k < ch.n; ++k) {
+      const CropRef& c = refs[plan.order[ch.first + k]];
+      rc[k] = RecCrop{c.p, c.h, c.w};
     }
-    if (!cur.empty()) waves.push_back(Wave{cur, {}});
+    launch_rec_batch(rec, rc.data(), ch.n, cfg->n_chars, ch.out);
   }
-  for (auto& wv : waves) {
-    std::stable_sort(wv.sorted.begin(), wv.sorted.end(),
-                     [&](int a, int b) { return h_plans[a].wh_ratio < h_plans[b].wh_ratio; });
-    const int bs = cfg->region_batch_size;
-    for (size_t s0 = 0; s0 < wv.sorted.size(); s0 += bs) {
-      int m = (int)std::min<size_t>(bs, wv.sorted.size() - s0);
-      std::vector<RecCrop> rc(m);
-      for (int k = 0; k < m; ++k) {
-        const CropPlan& p = h_plans[wv.sorted[s0 + k]];
-        rc[k] = RecCrop{pool + p.out_off, p.oh, p.ow};
-      }
-      wv.chunks.emplace_back();
-      launch_rec_batch(rec, rc.data(), m, cfg->n_chars, wv.chunks.back());
-    }
-  }
-  cudaEventRecord(ev[4], st);
+  cudaEventRecord(S.ev[4], st);
   OAR_CUDA(cudaStreamSynchronize(st));
 
-  // ---- scatter to per-image, detection-index order (ocr.rs:879-892, 637-656)
-  std::vector<int> lab_len(n_boxes, -1);
-  std::vector<const int32_t*> lab_ptr(n_boxes, nullptr);
-  std::vector<float> rec_score(n_boxes, 0.0f);
-  // per region, for word boxes (ocr.rs:827-868): CTC columns, T and the max wh_ratio of its recognition batch
-  std::vector<const int32_t*> col_ptr(n_boxes, nullptr);
-  std::vector<int> box_T(n_boxes, 0);
-  std::vector<float> box_max_ratio(n_boxes, 0.0f);
-  const float base_rec_ratio = (float)REC_W / (float)REC_H;  // DEFAULT_REC_IMAGE_SHAPE, ocr.rs:817
-  for (auto& wv : waves) {
-    size_t s0 = 0;
-    for (auto& ch : wv.chunks) {
-      float chunk_max = base_rec_ratio;
-      for (int k = 0; k < ch.n; ++k) chunk_max = std::fmax(chunk_max, h_plans[wv.sorted[s0 + k]].wh_ratio);
-      for (int k = 0; k < ch.n; ++k) {
-        int box = wv.sorted[s0 + k];
-        col_ptr[box] = ch.h_cols + (size_t)k * ch.T;
-        box_T[box] = ch.T;
-        box_max_ratio[box] = chunk_max;
-        float sc = ch.h_scores[k];
-        rec_score[box] = sc;
-        // TextRecognitionAdapter::execute: score below the threshold keeps the slot with empty text
-        bool keep = sc >= cfg->rec_score_thresh;
-        lab_len[box] = keep ? ch.h_lens[k] : 0;
-        lab_ptr[box] = ch.h_labels + (size_t)k * ch.T;
-      }
-      out->d2h_bytes += (int64_t)ch.n * (ch.T * 8 + 8);
-      s0 += ch.n;
-    }
-  }
+  std::vector<RecResult> res;
+  int64_t d2h = 0;
+  collect_results(refs, plan, cfg->rec_score_thresh, res, &d2h);
   int r = 0;
   long long nl = 0;
-  for (int i = 0; i < n; ++i) {
-    out->region_off[i] = r;
-    for (int k = 0; k < box_first[i + 1] - box_first[i]; ++k) {
-      int box = box_first[i] + k;
-      if (lab_len[box] < 0) continue;
-      if (r >= out->cap_regions || nl + lab_len[box] > out->cap_labels)
-        OAR_FAIL(OAR_E_CAPACITY, "result buffers too small (regions %d, labels %d)", out->cap_regions,
-                 out->cap_labels);
-      if (out->boxes) memcpy(out->boxes + (size_t)r * 8, &sorted_boxes[i][(size_t)k * 8], 8 * sizeof(float));
-      if (out->scores) out->scores[r] = rec_score[box];
-      if (out->det_index) out->det_index[r] = k;
-      if (out->label_off) out->label_off[r] = (int32_t)nl;
-      if (out->labels && lab_len[box] > 0) memcpy(out->labels + nl, lab_ptr[box], (size_t)lab_len[box] * 4);
-      if (out->cols && lab_len[box] > 0) memcpy(out->cols + nl, col_ptr[box], (size_t)lab_len[box] * 4);
-      if (out->seq_len) out->seq_len[r] = box_T[box];
-      if (out->wh_ratio) out->wh_ratio[r] = h_plans[box].wh_ratio;
-      if (out->max_wh_ratio) out->max_wh_ratio[r] = box_max_ratio[box];
-      if (out->line_angle) out->line_angle[r] = h_cls_ids ? (float)h_cls_ids[valid_of[box]] * 180.0f : -1.0f;
-      nl += lab_len[box];
-      ++r;
-    }
-  }
+  scatter_stage(S, 0, ref_of_box, res, out, r, nl);
   out->region_off[n] = r;
   if (out->label_off) out->label_off[r] = (int32_t)nl;
-  cudaEventElapsedTime(&out->ms_h2d, ev[0], ev[1]);
-  cudaEventElapsedTime(&out->ms_crop, ev[2], ev[3]);
-  cudaEventElapsedTime(&out->ms_rec, ev[3], ev[4]);
-  cudaEventElapsedTime(&out->ms_cls, ev[3], ev[5]);
-  cudaEventElapsedTime(&out->ms_total, ev[0], ev[4]);
+  out->ms_det = S.ms_det, out->ms_post = S.ms_post;
+  out->h2d_bytes = S.h2d_bytes, out->d2h_bytes = S.d2h_bytes + d2h;
+  cudaEventElapsedTime(&out->ms_h2d, S.ev[0], S.ev[1]);
+  cudaEventElapsedTime(&out->ms_crop, S.ev[2], S.ev[3]);
+  cudaEventElapsedTime(&out->ms_rec, S.ev[3], S.ev[4]);
+  cudaEventElapsedTime(&out->ms_cls, S.ev[3], S.ev[5]);
+  cudaEventElapsedTime(&out->ms_total, S.ev[0], S.ev[4]);
+  API_CATCH
+}
+
+// The second half of OAROCR::predict with caller-supplied boxes (oar_crop_rec_run): every box is cropped
+// from its page (get_rotate_crop_image, transform.rs:76-502) and the crops are recognised as recognize_global batches
+// them (ocr.rs:802-897).  Per box k: status[k] = 0 ok / 1 crop failed (skipped), lens[k], labels/cols [k][t_cap],
+// scores[k], seq_len[k] = T of its batch.
+int32_t oar_crop_rec_run(oar_model* rec, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                         int32_t images_on_device, const float* boxes, const int32_t* img_index, int32_t n_boxes,
+                         int32_t region_batch_size, int32_t n_chars, float rec_score_thresh, int32_t* status,
+                         int32_t* labels, int32_t* cols, int32_t* lens, float* scores, int32_t* seq_len, int32_t t_cap) {
+  API_TRY
+  if (!rec || rec->kind != OAR_KIND_REC) OAR_FAIL(OAR_E_INVALID, "not a recognition model");
+  if (n <= 0 || !images || !hs || !ws) OAR_FAIL(OAR_E_INVALID, "images: expected non-empty slice, got empty slice");
+  if (region_batch_size <= 0) OAR_FAIL(OAR_E_INVALID, "batch sizes must be positive");
+  if (n_boxes <= 0) return OAR_OK;
+  if (!boxes || !img_index || !status || !labels || !cols || !lens || !scores) OAR_FAIL(OAR_E_INVALID, "null argument");
+  oar_ctx* ctx = rec->ctx;
+  CallGuard guard(ctx);
+  PageStage S;
+  S.ctx = ctx;
+  stage_upload(S, images, hs, ws, n, images_on_device);
+  std::vector<int> slot_of;
+  stage_set_boxes(S, boxes, img_index, n_boxes, slot_of);
+  stage_crop(S);
+  stage_orient(S, nullptr);
+  std::vector<CropRef> refs;
+  std::vector<int> ref_of_box;
+  append_refs(S, 0, refs, &ref_of_box);
+  RecPlan plan;
+  plan_recognition(refs, region_batch_size, plan);
+  std::vector<RecCrop> rc;
+  for (RecChunk& ch : plan.chunks) {
+    rc.resize(ch.n);
+    for (int k = 0; k < ch.n; ++k) {
+      const CropRef& c = refs[plan.order[ch.first + k]];
+      rc[k] = RecCrop{c.p, c.h, c.w};
+    }
+    launch_rec_batch(rec, rc.data(), ch.n, n_chars, ch.out);
+  }
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<RecResult> res;
+  collect_results(refs, plan, rec_score_thresh, res, nullptr);
+  for (int k = 0; k < n_boxes; ++k) {
+    const int ref = ref_of_box[slot_of[k]];
+    status[k] = ref < 0 ? 1 : 0;
+    lens[k] = 0, scores[k] = 0.0f;
+    if (seq_len) seq_len[k] = 0;
+    if (ref < 0) continue;
+    const RecResult& rr = res[ref];
+    if (rr.T > t_cap) OAR_FAIL(OAR_E_CAPACITY, "sequence length %d exceeds capacity %d", rr.T, t_cap);
+    lens[k] = rr.len, scores[k] = rr.score;
+    if (seq_len) seq_len[k] = rr.T;
+    if (rr.len > 0) {
+      memcpy(labels + (size_t)k * t_cap, rr.labels, (size_t)rr.len * 4);
+      memcpy(cols + (size_t)k * t_cap, rr.cols, (size_t)rr.len * 4);
+    }
+  }
+  API_CATCH
+}
+
+// OAROCR::predict over several GPUs inside one process (one host thread + CUDA context per GPU), equal to
+// ONE un-sharded predict(): pages are dealt to the contexts in contiguous blocks; every context uploads, detects and
+// crops its block; the host pools ALL crops in (image, detection) order and plans recognize_global once; whole chunks
+// are dealt round-robin and a context fetches the crops that live in another context's pool over NVLink
+// (cudaMemcpyPeerAsync) before recognising its chunks.  No collective: sizes and results travel through host memory.
+int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, int32_t n_ctx,
+                               const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
+                               const oar_pipeline_config* cfg, oar_ocr_result* out) {
+  API_TRY
+  if (n_ctx <= 0 || !dets || !recs) OAR_FAIL(OAR_E_INVALID, "need at least one context");
+  for (int g = 0; g < n_ctx; ++g) {
+    check_pipeline_args(dets[g], recs[g], nullptr, images, hs, ws, n, cfg, out);
+    for (int h = 0; h < g; ++h)
+      if (dets[h]->ctx == dets[g]->ctx) OAR_FAIL(OAR_E_INVALID, "contexts %d and %d are the same", h, g);
+  }
+  const int R = std::min<int>(n_ctx, n);
+  std::vector<PageStage> stages(R);
+  std::vector<std::unique_ptr<CallGuard>> guards;
+  for (int g = 0; g < R; ++g) guards.emplace_back(new CallGuard(dets[g]->ctx));
+  std::vector<int> first(R + 1, 0);
+  for (int g = 0; g < R; ++g) first[g + 1] = first[g] + n / R + (g < n % R ? 1 : 0);
+  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
+  out->h2d_bytes = out->d2h_bytes = 0;
+
+  // direct peer access where the hardware has it (NVLink / NVSwitch on a B200 box); without it the peer copies below
+  // are staged by the driver.  "Already enabled" and "not supported" are both fine.
+  for (int g = 0; g < R; ++g)
+    for (int h = 0; h < R; ++h) {
+      const int dg = dets[g]->ctx->device, dh = dets[h]->ctx->device;
+      if (dg == dh) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, dg, dh) == cudaSuccess && can) {
+        cudaSetDevice(dg);
+        cudaDeviceEnablePeerAccess(dh, 0);
+        cudaGetLastError();
+      }
+    }
+  // a worker thread per context; errors come back as (code, message)
+  std::vector<int> codes(R, OAR_OK);
+  std::vector<std::string> msgs(R);
+  auto run_on_all = [&](const std::function<void(int)>& fn) {
+    std::vector<std::thread> th;
+    for (int g = 0; g < R; ++g)
+      th.emplace_back([&, g] {
+        try {
+          OAR_CUDA(cudaSetDevice(dets[g]->ctx->device));
+          fn(g);
+        } catch (const oar::OarError& e) {
+          cudaGetLastError();
+          codes[g] = e.code, msgs[g] = oar::g_err;
+        } catch (const std::exception& e) {
+          codes[g] = OAR_E_CUDA, msgs[g] = e.what();
+        }
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < R; ++g)
+      if (codes[g] != OAR_OK) OAR_FAIL(codes[g], "context %d: %s", g, msgs[g].c_str());
+  };
+
+  // ---- phase A: upload, detect, sort, crop -- every context on its block of pages
+  run_on_all([&](int g) {
+    PageStage& S = stages[g];
+    S.ctx = dets[g]->ctx;
+    for (auto& e : S.ev) e = S.ctx->next_event();
+    cudaEventRecord(S.ev[0], S.ctx->stream);
+    stage_upload(S, images + first[g], hs + first[g], ws + first[g], first[g + 1] - first[g], 0);
+    cudaEventRecord(S.ev[1], S.ctx->stream);
+    stage_detect(S, dets[g], cfg);
+    cudaEventRecord(S.ev[2], S.ctx->stream);
+    stage_crop(S);
+    stage_orient(S, nullptr);
+    cudaEventRecord(S.ev[3], S.ctx->stream);
+    OAR_CUDA(cudaStreamSynchronize(S.ctx->stream));  // the pools are complete before anybody fetches from them
+  });
+
+  // ---- phase B: one global recognize_global plan over all pools, chunks dealt round-robin
+  std::vector<CropRef> refs;
+  std::vector<std::vector<int>> ref_of_box(R);
+  for (int g = 0; g < R; ++g)
+    if (stages[g].n_boxes > 0) append_refs(stages[g], g, refs, &ref_of_box[g]);
+  RecPlan plan;
+  plan_recognition(refs, cfg->region_batch_size, plan);
+  for (size_t c = 0; c < plan.chunks.size(); ++c) plan.chunks[c].stage = (int)(c % R);
+
+  // ---- phase C: every context recognises its chunks; foreign crops come over the peer link first
+  run_on_all([&](int g) {
+    oar_ctx* ctx = recs[g]->ctx;
+    std::vector<RecCrop> rc;
+    for (RecChunk& ch : plan.chunks) {
+      if (ch.stage != g) continue;
+      rc.resize(ch.n);
+      for (int k = 0; k < ch.n; ++k) {
+        const CropRef& c = refs[plan.order[ch.first + k]];
+        const uint8_t* p = c.p;
+        if (c.stage != g) {
+          const size_t bytes = (size_t)c.h * c.w * 3;
+          uint8_t* local = ctx->arena.get<uint8_t>(bytes);
+          OAR_CUDA(cudaMemcpyPeerAsync(local, ctx->device, c.p, stages[c.stage].ctx->device, bytes, ctx->stream));
+          p = local;
+        }
+        rc[k] = RecCrop{p, c.h, c.w};
+      }
+      launch_rec_batch(recs[g], rc.data(), ch.n, cfg->n_chars, ch.out);
+    }
+    cudaEventRecord(stages[g].ev[4], ctx->stream);
+    OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+
+  // ---- phase D: scatter in image order
+  std::vector<RecResult> res;
+  int64_t d2h = 0;
+  collect_results(refs, plan, cfg->rec_score_thresh, res, &d2h);
+  int r = 0;
+  long long nl = 0;
+  for (int g = 0; g < R; ++g) {
+    if (stages[g].n_boxes == 0) ref_of_box[g].clear();
+    scatter_stage(stages[g], first[g], ref_of_box[g], res, out, r, nl);
+    out->h2d_bytes += stages[g].h2d_bytes;
+    out->d2h_bytes += stages[g].d2h_bytes;
+    float a = 0, b = 0, c = 0, t = 0;
+    cudaSetDevice(stages[g].ctx->device);
+    cudaEventElapsedTime(&a, stages[g].ev[0], stages[g].ev[1]);
+    cudaEventElapsedTime(&b, stages[g].ev[2], stages[g].ev[3]);
+    cudaEventElapsedTime(&c, stages[g].ev[3], stages[g].ev[4]);
+    cudaEventElapsedTime(&t, stages[g].ev[0], stages[g].ev[4]);
+    // the call's stage times are those of its slowest context
+    out->ms_h2d = std::max(out->ms_h2d, a), out->ms_crop = std::max(out->ms_crop, b);
+    out->ms_rec = std::max(out->ms_rec, c), out->ms_total = std::max(out->ms_total, t);
+    out->ms_det = std::max(out->ms_det, stages[g].ms_det), out->ms_post = std::max(out->ms_post, stages[g].ms_post);
+  }
+  out->d2h_bytes += d2h;
+  out->region_off[n] = r;
+  if (out->label_off) out->label_off[r] = (int32_t)nl;
   API_CATCH
 }
 

@@ -414,64 +414,175 @@ static bool try_dw_tiled(cudaStream_t st, const float* in, const float* w, const
 // ---------------------------------------------------------------------------
 // squeeze-excite: deterministic two-stage global average pool, tiny MLP, scale
 // ---------------------------------------------------------------------------
-__global__ void se_gap_kernel(const float* __restrict__ in, float* __restrict__ partial, int HW, int C, int S) {
-  // grid (S, B); each block sums pixels [s*chunk, (s+1)*chunk) for every channel
-  int s = blockIdx.x, b = blockIdx.y;
-  int chunk = (HW + S - 1) / S;
-  int p0 = s * chunk, p1 = min(HW, p0 + chunk);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.0f;
-    const float* base = in + ((size_t)b * HW) * C + c;
-    for (int p = p0; p < p1; ++p) acc += base[(size_t)p * C];
-    partial[((size_t)b * S + s) * C + c] = acc;
+// Squeeze-excite average pool, stage 1.  grid (S, B), 256 threads = RG row groups x C/4 channel quads: block (s, b)
+// sums rows [s*chunk, (s+1)*chunk) of image b; a thread takes every RG-th row of the chunk (four float4 loads in
+// flight, added in ascending row order), then the row groups are folded in ascending order through shared memory.
+// The order depends on (rows, C, S) only: deterministic and independent of the batch.
+__global__ void __launch_bounds__(256) se_gap_kernel(const float* __restrict__ in, float* __restrict__ partial, int HW,
+                                                     int C, int S) {
+  __shared__ float4 red[256];
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int c4n = C >> 2;
+  const int RG = max(1, min(256 / c4n, 16));
+  const int chunk = (HW + S - 1) / S;
+  const int p0 = s * chunk, p1 = min(HW, p0 + chunk);
+  if (c4n > 256) {  // wide tensors: a thread strides the channel quads, all rows
+    for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* base = reinterpret_cast<const float4*>(in) + (size_t)b * HW * c4n + c4;
+      for (int p = p0; p < p1; ++p) {
+        const float4 v = __ldg(base + (size_t)p * c4n);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(partial)[((size_t)b * S + s) * c4n + c4] = acc;
+    }
+    return;
+  }
+  const int rg = threadIdx.x / c4n, c4 = threadIdx.x - rg * c4n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < RG) {
+    const float4* base = reinterpret_cast<const float4*>(in) + (size_t)b * HW * c4n + c4;
+    int p = p0 + rg;
+    for (; p + 3 * RG < p1; p += 4 * RG) {
+      const float4 v0 = __ldg(base + (size_t)p * c4n), v1 = __ldg(base + (size_t)(p + RG) * c4n),
+                   v2 = __ldg(base + (size_t)(p + 2 * RG) * c4n), v3 = __ldg(base + (size_t)(p + 3 * RG) * c4n);
+      acc.x += v0.x, acc.y += v0.y, acc.z += v0.z, acc.w += v0.w;
+      acc.x += v1.x, acc.y += v1.y, acc.z += v1.z, acc.w += v1.w;
+      acc.x += v2.x, acc.y += v2.y, acc.z += v2.z, acc.w += v2.w;
+      acc.x += v3.x, acc.y += v3.y, acc.z += v3.z, acc.w += v3.w;
+    }
+    for (; p < p1; p += RG) {
+      const float4 v = __ldg(base + (size_t)p * c4n);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    red[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (rg == 0) {
+    for (int g = 1; g < RG; ++g) {
+      const float4 v = red[g * c4n + c4];
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial)[((size_t)b * S + s) * c4n + c4] = acc;
   }
 }
 
-__global__ void se_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w1,
-                             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                             float* __restrict__ scale, int HW, int C, int Cm, int S, float slope, float offset) {
+// The two FCs of the squeeze-excite gate, IMG images per block.  A few MFLOP per launch: what matters is latency, i.e.
+// how many independent loads each warp keeps in flight, and at large batches the L2 traffic of every block re-reading
+// both weight matrices (0.5 MB).  (A thread per output channel walked its weight row in a dependent chain: 30-90 us
+// per launch.)  A warp owns SE_R output units at a time: lanes stride the contiguous weight rows, SE_R x (unrolled
+// columns) loads are in flight together and feed IMG images, one butterfly per (unit, image).  The summation order of
+// an output depends on nothing but (C, Cm, S): results are deterministic and independent of the batch and of IMG.
+constexpr int SE_THREADS = 512, SE_R = 4;
+template <int IMG>
+__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, float* __restrict__ scale, int B,
+                                                           int HW, int C, int Cm, int S, float slope, float offset) {
   extern __shared__ float sm[];
-  float* mean = sm;
-  float* hid = sm + C;
-  int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  float* mean = sm;            // [IMG][C]
+  float* hid = sm + IMG * C;   // [IMG][Cm]
+  const int b0 = blockIdx.x * IMG;
+  for (int e = threadIdx.x; e < IMG * C; e += blockDim.x) {
+    const int img = e / C, c = e - img * C;
     float acc = 0.0f;
-    for (int s = 0; s < S; ++s) acc += partial[((size_t)b * S + s) * C + c];
-    mean[c] = acc / (float)HW;
+    if (b0 + img < B) {
+      const float* p = partial + (size_t)(b0 + img) * S * C + c;
+      int s = 0;
+      for (; s + 8 <= S; s += 8) {  // eight loads in flight, added in ascending s
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = p[(size_t)(s + i) * C];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += v[i];
+      }
+      for (; s < S; ++s) acc += p[(size_t)s * C];
+    }
+    mean[e] = acc / (float)HW;
   }
   __syncthreads();
-  // one warp per hidden unit: lanes stride the (contiguous) weight row, butterfly-reduce
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < Cm; j += nwarps) {
-    float acc = 0.0f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) hid[j] = fmaxf(acc + b1[j], 0.0f);
+  for (int j0 = warp * SE_R; j0 < Cm; j0 += nwarps * SE_R) {
+    float acc[SE_R][IMG];
+    const float* wr[SE_R];
+#pragma unroll
+    for (int r = 0; r < SE_R; ++r) {
+      wr[r] = w1 + (size_t)min(j0 + r, Cm - 1) * C;
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) acc[r][i] = 0.0f;
+    }
+#pragma unroll 2
+    for (int c = lane; c < C; c += 32) {
+      float w[SE_R];
+#pragma unroll
+      for (int r = 0; r < SE_R; ++r) w[r] = __ldg(wr[r] + c);
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) {
+        const float x = mean[i * C + c];
+#pragma unroll
+        for (int r = 0; r < SE_R; ++r) acc[r][i] = fmaf(w[r], x, acc[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SE_R; ++r)
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) {
+        float v = acc[r][i];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && j0 + r < Cm) hid[i * Cm + j0 + r] = fmaxf(v + b1[j0 + r], 0.0f);
+      }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = b2[c];
-    const float* wr = w2 + (size_t)c * Cm;
-    for (int j = 0; j < Cm; ++j) acc = fmaf(__ldg(wr + j), hid[j], acc);
-    scale[(size_t)b * C + c] = fminf(fmaxf(acc * slope + offset, 0.0f), 1.0f);
+  for (int c0 = warp * SE_R; c0 < C; c0 += nwarps * SE_R) {
+    float acc[SE_R][IMG];
+    const float* wr[SE_R];
+#pragma unroll
+    for (int r = 0; r < SE_R; ++r) {
+      wr[r] = w2 + (size_t)min(c0 + r, C - 1) * Cm;
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) acc[r][i] = 0.0f;
+    }
+#pragma unroll 2
+    for (int j = lane; j < Cm; j += 32) {
+      float w[SE_R];
+#pragma unroll
+      for (int r = 0; r < SE_R; ++r) w[r] = __ldg(wr[r] + j);
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) {
+        const float x = hid[i * Cm + j];
+#pragma unroll
+        for (int r = 0; r < SE_R; ++r) acc[r][i] = fmaf(w[r], x, acc[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SE_R; ++r)
+#pragma unroll
+      for (int i = 0; i < IMG; ++i) {
+        float v = acc[r][i];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && c0 + r < C && b0 + i < B)
+          scale[(size_t)(b0 + i) * C + c0 + r] = fminf(fmaxf((v + b2[c0 + r]) * slope + offset, 0.0f), 1.0f);
+      }
   }
 }
 
+// grid (cdiv(HWC4, 256), B): 32-bit index math, one division per thread
 __global__ void se_apply_kernel(const float* __restrict__ in, const float* __restrict__ scale, float* __restrict__ out,
-                                size_t total4, int HWC4, int C4, int residual) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  int b = (int)(i / HWC4);
-  int c4 = (int)(i % C4);
-  float4 x = reinterpret_cast<const float4*>(in)[i];
-  float4 s = reinterpret_cast<const float4*>(scale)[(size_t)b * C4 + c4];
+                                int HWC4, int C4, int residual) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HWC4) return;
+  const int b = blockIdx.y;
+  const int c4 = i % C4;
+  const size_t idx = (size_t)b * HWC4 + i;
+  float4 x = __ldg(reinterpret_cast<const float4*>(in) + idx);
+  float4 s = __ldg(reinterpret_cast<const float4*>(scale) + (size_t)b * C4 + c4);
   float4 o;
   if (residual) {
     o.x = x.x + x.x * s.x, o.y = x.y + x.y * s.y, o.z = x.z + x.z * s.z, o.w = x.w + x.w * s.w;
   } else {
     o.x = x.x * s.x, o.y = x.y * s.y, o.z = x.z * s.z, o.w = x.w * s.w;
   }
-  reinterpret_cast<float4*>(out)[i] = o;
+  reinterpret_cast<float4*>(out)[idx] = o;
 }
 
 // ---------------------------------------------------------------------------
@@ -484,36 +595,27 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
   reinterpret_cast<float4*>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
 }
 
-// out[b,y,x,:] = a[b,y,x,:] + up[b,y/s,x/s,:]
-__global__ void upadd_kernel(const float* __restrict__ a, const float* __restrict__ up, float* __restrict__ o, int B,
-                             int H, int W, int C4, int s) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)B * H * W * C4;
-  if (i >= total) return;
-  int c4 = (int)(i % C4);
-  size_t r = i / C4;
-  int x = (int)(r % W);
-  r /= W;
-  int y = (int)(r % H);
-  int b = (int)(r / H);
-  float4 v = reinterpret_cast<const float4*>(a)[i];
-  float4 u = reinterpret_cast<const float4*>(up)[(((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4];
-  reinterpret_cast<float4*>(o)[i] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
+// out[b,y,x,:] = a[b,y,x,:] + up[b,y/s,x/s,:]      grid (cdiv(W*C4, 256), H, B): one division per thread
+__global__ void upadd_kernel(const float* __restrict__ a, const float* __restrict__ up, float* __restrict__ o, int H,
+                             int W, int C4, int s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * C4) return;
+  const int x = i / C4, c4 = i - x * C4;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const size_t idx = ((size_t)b * H + y) * W * C4 + i;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(a) + idx);
+  const float4 u = __ldg(reinterpret_cast<const float4*>(up) + (((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4);
+  reinterpret_cast<float4*>(o)[idx] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
 }
 
-// out[b,y,x,c_off + c] = in[b,y/s,x/s,c]   (H,W = output dims)
-__global__ void upsample_into_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C4,
-                                     int s, int ld4, int coff4) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)B * H * W * C4;
-  if (i >= total) return;
-  int c4 = (int)(i % C4);
-  size_t r = i / C4;
-  int x = (int)(r % W);
-  r /= W;
-  int y = (int)(r % H);
-  int b = (int)(r / H);
-  float4 u = reinterpret_cast<const float4*>(in)[(((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4];
+// out[b,y,x,c_off + c] = in[b,y/s,x/s,c]   (H,W = output dims)      grid (cdiv(W*C4, 256), H, B)
+__global__ void upsample_into_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C4, int s,
+                                     int ld4, int coff4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * C4) return;
+  const int x = i / C4, c4 = i - x * C4;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const float4 u = __ldg(reinterpret_cast<const float4*>(in) + (((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4);
   reinterpret_cast<float4*>(out)[(((size_t)b * H + y) * W + x) * ld4 + coff4 + c4] = u;
 }
 
@@ -712,11 +814,21 @@ void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C
 // ---------------------------------------------------------------------------
 static inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
-Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc) {
+Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc, const U8Input* u8) {
   oar_ctx* ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   std::vector<Tensor> t(m->n_tensors);
   t[0] = input;
+  if (u8 && !input.p) t[0].B = u8->B, t[0].H = u8->H, t[0].W = u8->W, t[0].C = 3;
+  // the normalised fp32 input tensor, for graphs / engines whose first layer cannot read u8 pixels itself
+  auto materialize_input = [&]() {
+    Tensor& x = t[0];
+    x.p = ctx->arena.get<float>(x.numel());
+    if (u8->mode == 0)
+      launch_normalize(ctx, nullptr, u8->table, u8->table_aligned != 0, x.p, x.B, x.H, x.W, u8->src, u8->a, u8->b, /*NHWC*/ 1);
+    else
+      launch_crnn_normalize(ctx, u8->jobs, x.B, x.H, x.W, x.p, /*NHWC*/ 1);
+  };
   Tensor last;
   auto ensure = [&](int id, int B, int H, int W, int C) -> Tensor& {
     Tensor& x = t[id];
@@ -751,7 +863,10 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
     int rows = HW;
     auto its = tile_sums.find(op.in0);
     if (its != tile_sums.end()) src = its->second.p, rows = its->second.tiles;
-    const int S = rows >= 4096 ? 64 : (rows >= 256 ? 16 : 1);
+    // pool stage 1: as many blocks per image as leave every block >= 8 rows to sum.  S depends on the image size only,
+    // never on the batch: the summation order (hence the result) of an image must not change with its batch
+    int S = 1;
+    while (S < 64 && rows / (2 * S) >= 32) S *= 2;
     float* partial = ctx->arena.get<float>((size_t)a.B * S * c);
     float* scale = ctx->arena.get<float>((size_t)a.B * c);
     {
@@ -760,13 +875,35 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
     }
     {
       Launch l(ctx, "se_fc", 4.0 * a.B * c * cm, 0);
-      se_fc_kernel<<<a.B, 256, (c + cm) * sizeof(float), st>>>(partial, m->w(op, 0), m->w(op, 1), m->w(op, 2), m->w(op, 3),
-                                                                scale, HW, c, cm, S, op.f[0], op.f[1]);
+      if (a.B >= 128)  // large batches: four images share each fetched weight row
+        se_fc_kernel<4><<<cdiv(a.B, 4), SE_THREADS, (size_t)4 * (c + cm) * sizeof(float), st>>>(
+            partial, m->w(op, 0), m->w(op, 1), m->w(op, 2), m->w(op, 3), scale, a.B, HW, c, cm, S, op.f[0], op.f[1]);
+      else
+        se_fc_kernel<1><<<a.B, SE_THREADS, (size_t)(c + cm) * sizeof(float), st>>>(
+            partial, m->w(op, 0), m->w(op, 1), m->w(op, 2), m->w(op, 3), scale, a.B, HW, c, cm, S, op.f[0], op.f[1]);
     }
     return scale;
   };
   static const bool fuse_plain_pw = !(getenv("OAR_FUSED_PW") && atoi(getenv("OAR_FUSED_PW")) == 0);
-  for (size_t oi = 0; oi < m->ops.size(); ++oi) {
+  static const bool no_simt_fusions = getenv("OAR_DBG_NOSIMTFUSE") != nullptr;  // A/B switch: stem_u8 / deconv_pair off
+  if (u8 && !t[0].p) {
+    // engines >= 1: the stem convolution reads the u8 pixels and normalises them in registers (fused_simt.cu), provided
+    // it is the only reader of the input tensor
+    bool stem_done = false;
+    const OpRec& op0 = m->ops[0];
+    if (m->engine >= 1 && !no_simt_fusions && op0.in0 == 0 && uses[0] == 1 && op0.type == OP_CONV && op0.p[2] > 0 && op0.p[3] > 0) {
+      const int Ho = conv_out(u8->H, op0.p[0], op0.p[2], op0.p[4]), Wo = conv_out(u8->W, op0.p[1], op0.p[3], op0.p[5]);
+      if (Ho > 0 && Wo > 0) {
+        Tensor& o = ensure(op0.out, u8->B, Ho, Wo, op0.p[7]);
+        stem_done = launch_stem_u8(ctx, *u8, op0, m->w(op0, 0), m->w(op0, 1), o.p, Ho, Wo);
+        if (stem_done) last = o;
+      }
+    }
+    if (!stem_done) materialize_input();
+    else t[0].p = nullptr;
+    if (stem_done && m->ops.size() == 1) return last;
+  }
+  for (size_t oi = (u8 && !t[0].p) ? 1 : 0; oi < m->ops.size(); ++oi) {
     const OpRec& op = m->ops[oi];
     const Tensor& a = t[op.in0];
     if (!a.p) OAR_FAIL(OAR_E_MODEL, "op %zu reads undefined tensor %d", oi, op.in0);
@@ -829,6 +966,18 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
       }
       case OP_DECONV2: {
         int cin = op.p[0], cout = op.p[1];
+        if (a.C != cin) OAR_FAIL(OAR_E_MODEL, "deconv op %zu: Cin %d != tensor C %d", oi, cin, a.C);
+        // DBHead tail: two transposed convolutions back to back -> one kernel, the 4x-area intermediate stays in registers
+        if (m->engine >= 1 && !no_simt_fusions && oi + 1 < m->ops.size() && m->ops[oi + 1].type == OP_DECONV2 &&
+            m->ops[oi + 1].in0 == op.out && uses[op.out] == 1 && m->ops[oi + 1].p[0] == cout) {
+          const OpRec& d2 = m->ops[oi + 1];
+          Tensor& o2 = ensure(d2.out, a.B, a.H * 4, a.W * 4, d2.p[1]);
+          if (launch_deconv_pair(ctx, a.p, a.B, a.H, a.W, op, m->w(op, 0), m->w(op, 1), d2, m->w(d2, 0), m->w(d2, 1), o2.p)) {
+            last = o2;
+            ++oi;
+            continue;
+          }
+        }
         Tensor& o = ensure(op.out, a.B, a.H * 2, a.W * 2, cout);
         ConvParams p{};
         p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = o.p;
@@ -881,9 +1030,10 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         }
         Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         {
-          size_t n4 = a.numel() / 4;
+          if (a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "se op %zu: batch too large for one launch", oi);
           Launch l(ctx, "se_apply", 2.0 * a.numel(), 8.0 * a.numel());
-          se_apply_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, scale, o.p, n4, HW * c / 4, c / 4, residual);
+          se_apply_kernel<<<dim3(cdiv((long long)HW * (c / 4), 256), a.B), 256, 0, st>>>(a.p, scale, o.p, HW * (c / 4), c / 4,
+                                                                                        residual);
         }
         break;
       }
@@ -902,7 +1052,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
         size_t n4 = a.numel() / 4;
         Launch l(ctx, "upadd", (double)a.numel(), 8.0 * a.numel() + 4.0 * b.numel());
-        upadd_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, b.p, o.p, a.B, a.H, a.W, a.C / 4, s);
+        if (a.H > 65535 || a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "upadd op %zu: tensor too tall for one launch", oi);
+        (void)n4;
+        upadd_kernel<<<dim3(cdiv((long long)a.W * (a.C / 4), 256), a.H, a.B), 256, 0, st>>>(a.p, b.p, o.p, a.H, a.W, a.C / 4, s);
         break;
       }
       case OP_UPSAMPLE: {
@@ -912,7 +1064,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(op.out, a.B, a.H * s, a.W * s, ctot);
         size_t n4 = (size_t)a.B * o.H * o.W * (a.C / 4);
         Launch l(ctx, "upsample_into", 0, 4.0 * a.numel() + 16.0 * n4);
-        upsample_into_kernel<<<cdiv(n4, 256), 256, 0, st>>>(a.p, o.p, a.B, o.H, o.W, a.C / 4, s, ctot / 4, coff / 4);
+        if (o.H > 65535 || a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "upsample op %zu: tensor too tall for one launch", oi);
+        upsample_into_kernel<<<dim3(cdiv((long long)o.W * (a.C / 4), 256), o.H, a.B), 256, 0, st>>>(a.p, o.p, o.H, o.W, a.C / 4, s,
+                                                                                              ctot / 4, coff / 4);
         break;
       }
       case OP_AVGPOOL: {

@@ -1,6 +1,7 @@
 // engine.cuh -- OARG layer-list executor (declarations)
 #pragma once
 #include "common.cuh"
+#include "prepost.cuh"
 
 namespace oar {
 
@@ -74,6 +75,19 @@ struct FusedBlock {
   int out_ld, out_c_off, Ho, Wo;
 };
 
+// The network input still as u8 pixels (engines >= 1 fold the normalisation into the stem convolution, fused_simt.cu):
+// mode 0 = pages behind a device pointer table with NormalizeImage coefficients (normalization.rs:142-143),
+// mode 1 = resized crops with the CRNN normalisation and zero padding right of each crop's rw (simd.rs:248-308).
+struct U8Input {
+  int mode;
+  const uint8_t* const* table;  // mode 0: B image pointers, u8 HWC, row stride 3 * W
+  const CrnnJob* jobs;          // mode 1: B crops {src, rw}, row stride 3 * rw
+  int B, H, W;                  // the tensor the network sees: [B, H, W, 3]
+  int src[3];
+  float a[3], b[3];
+  int table_aligned;
+};
+
 // Output of the fused CTC head: per (b,t) argmax class and its softmax prob.
 struct CtcOut {
   int32_t* idx = nullptr;
@@ -103,7 +117,14 @@ namespace oar {
 // probability map.  For rec: when `want_probs` the full [B,1,T,V] softmax is
 // materialised in the returned tensor, otherwise only `ctc` is filled (the
 // logits never leave the head kernel's launch) and the returned tensor is empty.
-Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ctc);
+// `u8` (optional): the input is given as u8 pixels instead of `in.p` (in.p == nullptr, dims from u8).
+Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ctc, const U8Input* u8 = nullptr);
+
+// fused_simt.cu: false = shape not covered, the caller runs the per-layer path
+bool launch_stem_u8(oar_ctx* ctx, const U8Input& S, const OpRec& op, const float* w, const float* bias, float* out, int Ho,
+                    int Wo);
+bool launch_deconv_pair(oar_ctx* ctx, const float* in, int B, int H, int W, const OpRec& d1, const float* w1,
+                        const float* b1, const OpRec& d2, const float* w2, const float* b2, float* out);
 
 // tensor-core engine lifetime hooks (gemm_tc.cu): build fp16 weight copies / release them
 void tc_model_init(oar_model* m);

@@ -66,7 +66,6 @@ struct FbParams {
   float* part_max;
   int32_t* part_idx;
   float* part_sum;
-  int ctc_groups;  // 2: a second epilogue group (four warps of the idle depthwise team) reduces the upper column half
   int TH, TW, tiles_h, tiles_w, n_work;
   int cols_in;
   uint32_t in_bytes;   // activation box
@@ -217,7 +216,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       mbar_init(FB_BAR(FB_A_FULL + i), FB_CWARPS);
       mbar_init(FB_BAR(FB_AB_EMPTY + i), 1);
       mbar_init(FB_BAR(FB_ACC_FULL + i), 1);
-      mbar_init(FB_BAR(FB_ACC_EMPTY + i), P.part_max ? P.ctc_groups * FB_EPI_WARPS : FB_EPI_WARPS);  // CTC mode: one or two groups
+      mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_WARPS);
       mbar_init(FB_BAR(FB_SEEN + i), FB_CWARPS);
     }
     fence_mbar_init();
@@ -315,15 +314,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
                              (uint32_t)P.nkb;
     const bool ctc = K == 0 && P.part_max != nullptr;
     if (ctc && team == 1) {
-      // CTC head: converting fp32 rows is light work, so one team does every k-block and four warps of the other
-      // (one per TMEM lane quarter) form a second epilogue group for the upper column half of each tile
-      const int w1 = warp - (FB_WARP_C0 + 8);
-      const int first = (4 - ((FB_WARP_C0 + 8) & 3)) & 3;  // first warp of the team with warp % 4 == 0
-      if (P.ctc_groups == 2 && w1 >= first && w1 < first + 4) {
-        float* bias_g = reinterpret_cast<float*>(smem + P.off_ctrl + 256) + 128;
-        ctc_epilogue_group(P, 1, 1, (warp & 3) * 32 + lane, tmem_base + ((uint32_t)((warp & 3) * 32) << 16), bias_g,
-                           FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
-      }
+      // CTC head: converting fp32 rows is light work, so one team does every k-block and this one idles
     } else if (K == 0) {
       const uint32_t it0 = ctc ? 0u : (uint32_t)team, it_step = ctc ? 1u : 2u;
       const int q = ct & 7;
@@ -477,7 +468,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + 256);  // [n_tiles * BN + 32], zero padded
     const bool ctc = P.part_max != nullptr;  // then bias_s holds one tile's BN values, reloaded per work item
     if (ctc) {
-      ctc_epilogue_group(P, 0, P.ctc_groups == 2 ? 1 : 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+      ctc_epilogue_group(P, 0, 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
     } else {
       for (int i = tid; i < P.n_tiles * P.BN + 32; i += FB_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
       named_bar_sync(1, FB_EPI_THREADS);
@@ -724,11 +715,9 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   P.wpk = w.packed, P.bias = p.bias, P.act = ACT_NONE, P.ps = 1.0f, P.pb = 0.0f;
   P.C = p.K, P.N = p.N, P.BN = w.BN, P.nkb = w.nkb, P.n_tiles = w.n_tiles;
   P.part_max = p.part_max, P.part_idx = p.part_idx, P.part_sum = p.part_sum;
-  // One epilogue group by default.  A second group (OAR_CTC_GROUPS=2: four warps of the idle depthwise team reduce the
-  // upper column half, 1.3x faster on this layer) showed rare run-to-run differences in the softmax statistics under
-  // host-side jitter (tools/_stress4.py, ~1.5 % of calls) that are not understood yet, so it stays opt-in.
-  static const bool two_groups = getenv("OAR_CTC_GROUPS") && atoi(getenv("OAR_CTC_GROUPS")) == 2;
-  P.ctc_groups = two_groups ? 2 : 1;
+  // (A second epilogue group on four warps of the idle depthwise team, each group reducing one column half, was 1.3x
+  // faster on this layer but showed rare run-to-run differences in the softmax statistics under host-side jitter --
+  // 17 of 300 stress iterations, synccheck clean, racecheck inconclusive -- and was removed in round 2: DESIGN.md 5.2.)
   P.M = p.M, P.HW = 1;
   P.in_bytes = 128 * 128, P.tap_bytes = 0, P.ns_in = 4;
   P.TH = P.TW = 0, P.tiles_h = P.tiles_w = 1, P.cols_in = 128;

@@ -677,28 +677,44 @@ __global__ void __launch_bounds__(TC_THREADS) conv_rowtaps_tc(const TcParams P,
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// per-row combine of the CTC head's tile partials: arg-max (last index on ties) and 1 / sum exp(z - zmax)
-__global__ void ctc_combine_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx,
-                                   const float* __restrict__ psum, size_t rows, int n_tiles, int32_t* __restrict__ idx,
-                                   float* __restrict__ prob) {
-  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// per-row combine of the CTC head's tile partials: arg-max (last index on ties) and 1 / sum exp(z - zmax).
+// One warp per row: lanes stride the row's n_tiles partials (144 for the 18385-class head: a thread per row walked
+// three strided arrays in a dependent chain, 38 us per launch), butterfly-reduce the (max, index) pair, then the
+// rescaled sums in a fixed lane order (deterministic).
+__global__ void __launch_bounds__(256) ctc_combine_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx,
+                                                          const float* __restrict__ psum, size_t rows, int n_tiles,
+                                                          int32_t* __restrict__ idx, float* __restrict__ prob) {
+  const size_t r = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float* a = pmax + r * n_tiles;
-  float mx = a[0];
-  int mi = pidx[r * n_tiles];
-  for (int t = 1; t < n_tiles; ++t)
-    if (a[t] > mx || (a[t] == mx && pidx[r * n_tiles + t] > mi)) mx = a[t], mi = pidx[r * n_tiles + t];  // last index on ties
+  const int32_t* ai = pidx + r * n_tiles;
+  float mx = -INFINITY;
+  int mi = -1;
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float v = a[t];
+    const int vi = ai[t];
+    if (v > mx || (v == mx && vi > mi)) mx = v, mi = vi;  // last index on ties (class ranges ascend with t)
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi > mi)) mx = ov, mi = oi;
+  }
   float tot = 0.0f;
-  for (int t = 0; t < n_tiles; ++t) tot += psum[r * n_tiles + t] * expf(a[t] - mx);
-  idx[r] = mi;
-  prob[r] = 1.0f / tot;
+  for (int t = lane; t < n_tiles; t += 32) tot += psum[r * n_tiles + t] * expf(a[t] - mx);
+  for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if (lane == 0) {
+    idx[r] = mi < 0 ? 0 : mi;
+    prob[r] = 1.0f / tot;
+  }
 }
 
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
                         int n_tiles, int32_t* idx, float* prob) {
   Launch l(ctx, "ctc_combine", 0, 12.0 * rows * n_tiles);
-  ctc_combine_kernel<<<cdiv((long long)rows, 128), 128, 0, ctx->stream>>>(part_max, part_idx, part_sum, rows, n_tiles,
-                                                                         idx, prob);
+  ctc_combine_kernel<<<cdiv((long long)rows, 8), 256, 0, ctx->stream>>>(part_max, part_idx, part_sum, rows, n_tiles, idx,
+                                                                       prob);
 }
 
 // ---------------------------------------------------------------------------

@@ -26,7 +26,7 @@ SYMBOLS = [
     "oar_pipeline_run", "oar_cls_run", "oar_rotate180", "oar_pipeline_run_cls", "oar_layout_config_default",
     "oar_layout_postprocess", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
     "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush", "oar_model_validate_blob",
-    "oar_model_load_onnx", "oar_onnx_to_oarg",
+    "oar_model_load_onnx", "oar_onnx_to_oarg", "oar_crop_rec_run", "oar_rec_run_ex", "oar_pipeline_run_multi",
 ]
 
 
@@ -134,6 +134,13 @@ def lib():
             [C.c_void_p] * 6
         L.oar_rec_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.oar_rec_run_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.oar_crop_rec_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6 + \
+            [C.c_int32]
+        L.oar_pipeline_run_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
         L.oar_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
         L.oar_cls_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -511,6 +518,40 @@ class Model:
                     cols=[cols[i, :lens[i]].copy() for i in range(n)], scores=scores, T=t_out.value)
 
 
+    def rec_run_device(self, crop_ptrs, hs: np.ndarray, ws: np.ndarray, n_chars: int, t_cap: int):
+        """oar_rec_run_ex with crops already resident in HBM (bench `value` leg of the recognizer-only workload);
+        returns (lens, scores, T) -- labels stay in the caller-sized scratch"""
+        n = len(hs)
+        labels = np.zeros((n, t_cap), np.int32)
+        cols = np.zeros((n, t_cap), np.int32)
+        lens = np.zeros(n, np.int32)
+        scores = np.zeros(n, np.float32)
+        t_out = C.c_int32()
+        check(lib().oar_rec_run_ex(self.handle, crop_ptrs, _ptr(hs), _ptr(ws), n, 1, n_chars, _ptr(labels), _ptr(cols),
+                                   _ptr(lens), _ptr(scores), t_cap, C.byref(t_out)))
+        return dict(labels=[labels[i, :lens[i]].copy() for i in range(n)], scores=scores, T=t_out.value)
+
+    def crop_rec_run(self, images, boxes: np.ndarray, img_index, n_chars: int, region_batch_size: int = 64,
+                     rec_score_thresh: float = 0.0):
+        """oar_crop_rec_run: pages + boxes -> crops -> recognize_global.  Returns dict(status, labels, cols, scores,
+        seq_len), one entry per box."""
+        arrs, ptrs, hs, ws = _image_table(images)
+        boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 8)
+        idx = np.ascontiguousarray(img_index, np.int32)
+        nb = len(boxes)
+        t_cap = 3200 // 8 + 2
+        status = np.zeros(nb, np.int32)
+        labels = np.zeros((nb, t_cap), np.int32)
+        cols = np.zeros((nb, t_cap), np.int32)
+        lens = np.zeros(nb, np.int32)
+        scores = np.zeros(nb, np.float32)
+        seq = np.zeros(nb, np.int32)
+        check(lib().oar_crop_rec_run(self.handle, ptrs, _ptr(hs), _ptr(ws), len(arrs), 0, _ptr(boxes), _ptr(idx), nb,
+                                     region_batch_size, n_chars, rec_score_thresh, _ptr(status), _ptr(labels),
+                                     _ptr(cols), _ptr(lens), _ptr(scores), _ptr(seq), t_cap))
+        return dict(status=status, labels=[labels[i, :lens[i]].copy() for i in range(nb)],
+                    cols=[cols[i, :lens[i]].copy() for i in range(nb)], scores=scores, seq_len=seq)
+
     def cls_run(self, crops, input_shape=(80, 160), want_probs=True):
         """TextLineOrientationAdapter::execute: returns dict(class_ids [n], scores [n], probs [n,C] or None)"""
         if not crops:
@@ -563,6 +604,18 @@ class PipelineBuffers:
         # TextRegion.orientation_angle of the line-orientation stage: 0 / 180, -1 = None (no classifier)
         self.line_angle = np.full(cap_regions, -1.0, np.float32)
         self.res.line_angle = self.line_angle.ctypes.data_as(P(C.c_float))
+
+
+def pipeline_run_multi(dets, recs, image_ptrs, hs: np.ndarray, ws: np.ndarray, cfg: PipelineConfig,
+                       bufs: PipelineBuffers):
+    """oar_pipeline_run_multi: dets[g] / recs[g] live on context g (one host thread + CUDA context per GPU inside the
+    library); host pages only; equal to one un-sharded pipeline_run"""
+    n_ctx = len(dets)
+    d = (C.c_void_p * n_ctx)(*[m.handle for m in dets])
+    r = (C.c_void_p * n_ctx)(*[m.handle for m in recs])
+    check(lib().oar_pipeline_run_multi(d, r, n_ctx, image_ptrs, _ptr(hs), _ptr(ws), len(hs), C.byref(cfg),
+                                       C.byref(bufs.res)))
+    return bufs.res
 
 
 def pipeline_run(det: Model, rec: Model, image_ptrs, hs: np.ndarray, ws: np.ndarray, on_device: bool,

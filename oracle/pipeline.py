@@ -100,13 +100,20 @@ def det_forward(net: OracleNet, images, thresh=0.3, box_thresh=0.6, unclip_ratio
     return (out, preds) if return_pred else out
 
 
-def rec_forward(net: OracleNet, crops, n_chars, return_probs=False):
+def rec_forward(net: OracleNet, crops, n_chars, return_probs=False, with_margin=False):
     """CRNNModel::forward_refs on one batch: preprocess -> net -> argmax -> CTC decode."""
     x = cpu.crnn_preprocess(crops)
     probs = net.forward(x)  # [B,T,V]
     idx, prob = cpu.ctc_argmax(probs)
     labels, scores, cols, T = cpu.ctc_decode(idx, prob, n_chars)
     r = dict(labels=labels, scores=scores, cols=cols, T=T, idx=idx, prob=prob)
+    # smallest top-1 / top-2 probability gap over the timesteps of each crop: how far the crop's arg-max decisions are
+    # from a tie.  A parity check may excuse a label difference only where this is below the float tolerance.
+    # (test-only: the timed CPU baseline never asks for it)
+    if with_margin:
+        import torch
+        t2 = torch.topk(torch.from_numpy(np.ascontiguousarray(probs)).reshape(len(crops), -1, probs.shape[-1]), 2, dim=-1).values
+        r["margin"] = (t2[..., 0] - t2[..., 1]).min(dim=1).values.numpy()
     if return_probs:
         r["probs"] = probs
     return r
@@ -125,7 +132,7 @@ def cls_forward(net: OracleNet, crops, topk=1, input_shape=cpu.CLS_INPUT_SHAPE):
 
 
 def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch_size=8, region_batch_size=64,
-            rec_score_thresh=0.0, det_kwargs=None, chars=None, cls_net: OracleNet | None = None):
+            rec_score_thresh=0.0, det_kwargs=None, chars=None, cls_net: OracleNet | None = None, with_margin=False):
     """OAROCR::predict.  Returns per image a list of dicts
     {box [4,2], det_index, labels (int array), score} in detection-index (reading) order.  With `cls_net` the crops of
     each image go through classify_line_orientations (ocr.rs:615, 755-792) before they are pooled: `angle` = 0 / 180
@@ -144,7 +151,7 @@ def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch
         order = sorted(range(len(pool)), key=lambda i: pool[i][3])  # stable sort by wh_ratio
         for s in range(0, len(order), region_batch_size):
             chunk = [pool[i] for i in order[s:s + region_batch_size]]
-            r = rec_forward(rec_net, [c[2] for c in chunk], n_chars)
+            r = rec_forward(rec_net, [c[2] for c in chunk], n_chars, with_margin=with_margin)
             chunk_max = BASE_REC_RATIO
             for c in chunk:
                 chunk_max = max(chunk_max, np.float32(c[3]))  # ocr.rs:828-831
@@ -153,7 +160,8 @@ def predict(det_net: OracleNet, rec_net: OracleNet, images, n_chars, image_batch
                 keep = score >= rec_score_thresh
                 labels = r["labels"][k] if keep else r["labels"][k][:0]
                 res = dict(box=all_boxes[img_idx][det_idx], det_index=det_idx, labels=labels, score=score,
-                           cols=r["cols"][k], T=r["T"], angle=angles.get((img_idx, det_idx)))
+                           cols=r["cols"][k], T=r["T"], angle=angles.get((img_idx, det_idx)),
+                           margin=float(r["margin"][k]) if with_margin else None)
                 if chars is not None:  # return_word_box (ocr.rs:860-868); chars = index -> character
                     cols = r["cols"][k] if keep else r["cols"][k][:0]
                     text = "".join(chars[i] for i in labels if 0 < i < len(chars))
