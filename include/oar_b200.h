@@ -40,6 +40,7 @@ typedef struct oar_model oar_model; /* one network resident on a context */
 #define OAR_KIND_DET 0
 #define OAR_KIND_REC 1
 #define OAR_KIND_CLS 2 /* PP-LCNet classifier: text-line orientation */
+#define OAR_KIND_FEAT 3 /* feature extractor (HGNetV2 backbone, layout-detector encoder): oar_infer_f32 only */
 
 /* Detection post-process configuration.
  * = DBPostProcess{thresh, box_thresh, max_candidates, unclip_ratio, min_size}

@@ -580,6 +580,16 @@ const char* validate_op(const OpRec& op, uint32_t n_tensors, uint64_t n_w) {
       if (!pos(p[0], CMAX) || !pos(p[1], CMAX)) return "head width / classes out of range";
       want[0] = (int64_t)p[1] * p[0], want[1] = p[1];
       break;
+    case OP_PAD:
+      if (p[0] < 0 || p[1] < 0 || p[2] < 0 || p[3] < 0 || p[0] > 4096 || p[1] > 4096 || p[2] > 4096 || p[3] > 4096)
+        return "padding out of range";
+      break;
+    case OP_MAXPOOL:
+      if (!pos(p[0], 64) || !pos(p[1], 64) || !pos(p[2], 64) || !pos(p[3], 64)) return "pool window / stride out of range";
+      break;
+    case OP_TOKENS:
+      if (p[0] < 0 || !pos(p[1], 1 << 24) || p[0] >= p[1]) return "token rows out of range";
+      break;
     default:
       return "unknown op type";
   }
@@ -603,7 +613,7 @@ void check_blob(const uint8_t* p, size_t len, BlobHeader& h, std::vector<OpRec>*
   memcpy(&h.n_tensors, p + 16, 4);
   memcpy(&h.n_w, p + 20, 8);
   if (h.version != 1) OAR_FAIL(OAR_E_MODEL, "unsupported OARG version %u", h.version);
-  if (h.kind > OAR_KIND_CLS) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", h.kind);
+  if (h.kind > OAR_KIND_FEAT) OAR_FAIL(OAR_E_MODEL, "unknown model kind %u", h.kind);
   const size_t body = len - 28;
   if ((size_t)h.n_ops > body / sizeof(OpRec))
     OAR_FAIL(OAR_E_MODEL, "truncated model blob: %u ops do not fit %zu bytes", h.n_ops, len);
@@ -846,6 +856,8 @@ int32_t oar_infer_f32(oar_model* m, const float* in, const int64_t in_shape[4], 
   if (m->kind == OAR_KIND_DET) {
     out_shape[0] = y.B, out_shape[1] = y.C, out_shape[2] = y.H, out_shape[3] = y.W;
     if (y.C != 1) OAR_FAIL(OAR_E_MODEL, "detector output has %d channels", y.C);
+  } else if (m->kind == OAR_KIND_FEAT) {
+    out_shape[0] = y.B, out_shape[1] = y.H, out_shape[2] = y.W, out_shape[3] = y.C;  // the feature map as stored: NHWC
   } else {
     out_shape[0] = y.B, out_shape[1] = (int64_t)y.H * y.W, out_shape[2] = y.C, out_shape[3] = 1;
   }

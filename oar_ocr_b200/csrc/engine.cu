@@ -6,6 +6,8 @@
 // stream.  This file is the full-precision engine (engine 0): every op in fp32,
 // used for parity against the CPU oracle and as the on-device reference for the
 // tensor-core engine (gemm_tc.cu), which overrides the GEMM-shaped ops.
+#include <cmath>
+
 #include "engine.cuh"
 
 #include <cstdlib>
@@ -28,6 +30,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
       return 1.0f / (1.0f + expf(-v));
     case ACT_HSIGMOID:
       return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
+    case ACT_GELU:
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default:
       return v;
   }
@@ -401,6 +405,8 @@ static bool try_dw_tiled(cudaStream_t st, const float* in, const float* w, const
   DW_CASE(5, 1, 1, 2, 4, ACT_HSWISH)
   DW_CASE(3, 1, 1, 2, 4, ACT_NONE)
   DW_CASE(5, 1, 1, 2, 4, ACT_NONE)
+  DW_CASE(3, 1, 1, 2, 4, ACT_RELU)
+  DW_CASE(5, 1, 1, 2, 4, ACT_RELU)
   DW_CASE(3, 2, 2, 1, 4, ACT_NONE)
   DW_CASE(5, 2, 2, 1, 4, ACT_NONE)
   DW_CASE(3, 2, 1, 1, 4, ACT_NONE)
@@ -723,6 +729,116 @@ __global__ void attn_core_kernel(const float* __restrict__ qkv, float* __restric
       for (int d = 0; d < D; ++d) acc[d] = fmaf(e, Vs[j * D + d], acc[d]);
     }
     float inv = 1.0f / den;
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[((size_t)b * T + t) * C + h * D + d] = acc[d] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// zero padding / max pool / map -> token rows (HGNetV2 stem, layout-detector memory): float4 per thread, NHWC
+// ---------------------------------------------------------------------------
+__global__ void pad_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, int Ho, int Wo,
+                           int top, int left, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  size_t r = i / C4;
+  const int x = (int)(r % Wo);
+  r /= Wo;
+  const int y = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const int iy = y - top, ix = x - left;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(in + (((size_t)b * H + iy) * W + ix) * C4 + c4);
+  out[i] = v;
+}
+
+__global__ void maxpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, int Ho, int Wo,
+                               int kh, int kw, int sh, int sw, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  size_t r = i / C4;
+  const int x = (int)(r % Wo);
+  r /= Wo;
+  const int y = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      const float4 v = __ldg(in + (((size_t)b * H + y * sh + ky) * W + x * sw + kx) * C4 + c4);
+      m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+    }
+  out[i] = m;
+}
+
+// out[b, row_off + p, :] = in[b, p, :]   (p = pixel of the map, rows_total rows per image in `out`)
+__global__ void tokens_kernel(const float4* __restrict__ in, float4* __restrict__ out, int HWC4, int row_off_c4,
+                              size_t out_img_c4, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t b = i / HWC4, r = i - b * HWC4;
+  out[b * out_img_c4 + row_off_c4 + r] = __ldg(in + i);
+}
+
+// x + sine position embedding (one [T, C] table per map size, computed on the host in f64 like the reference)
+__global__ void add_rows_kernel(const float4* __restrict__ x, const float4* __restrict__ pos, float4* __restrict__ out,
+                                int TC4, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float4 a = __ldg(x + i), b = __ldg(pos + i % TC4);
+  out[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// ---------------------------------------------------------------------------
+// attention core, any head width D <= 64 and any sequence length: q / k rows from `qk`, v rows from `vv` (the same
+// buffer, or -- with positions on the q / k inputs only -- the projection of the position-free input).  Both are
+// [B, T, 3, heads, D].  One block per (head, image, 128-query tile); keys / values pass through shared memory in
+// chunks of 64 or 128 rows; a thread owns one query row with an online softmax (running max, rescaled sum).
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) attn_core_any_kernel(const float* __restrict__ qk, const float* __restrict__ vv,
+                                                            float* __restrict__ out, int T, int heads, float scale) {
+  constexpr int ATT_TK = D > 32 ? 64 : 128;  // 2 x TK x D floats stay under the static 48 KB
+  __shared__ float Ks[ATT_TK * D];
+  __shared__ float Vs[ATT_TK * D];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int C = heads * D;
+  const float* qkb = qk + (size_t)b * T * 3 * C;
+  const float* vb = vv + (size_t)b * T * 3 * C;
+  const int t = blockIdx.z * blockDim.x + threadIdx.x;
+  float q[D], acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) q[d] = t < T ? qkb[(size_t)t * 3 * C + h * D + d] * scale : 0.0f, acc[d] = 0.0f;
+  float mx = -INFINITY, den = 0.0f;
+  for (int j0 = 0; j0 < T; j0 += ATT_TK) {
+    const int nj = min(ATT_TK, T - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nj * D; i += blockDim.x) {
+      const int j = i / D, d = i - j * D;
+      Ks[i] = qkb[(size_t)(j0 + j) * 3 * C + C + h * D + d];
+      Vs[i] = vb[(size_t)(j0 + j) * 3 * C + 2 * C + h * D + d];
+    }
+    __syncthreads();
+    for (int j = 0; j < nj; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], Ks[j * D + d], s);
+      if (s > mx) {  // rescale what has been accumulated so far
+        const float r = expf(mx - s);
+        den *= r;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] *= r;
+        mx = s;
+      }
+      const float e = expf(s - mx);
+      den += e;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(e, Vs[j * D + d], acc[d]);
+    }
+  }
+  if (t < T) {
+    const float inv = 1.0f / den;
 #pragma unroll
     for (int d = 0; d < D; ++d) out[((size_t)b * T + t) * C + h * D + d] = acc[d] * inv;
   }
@@ -1095,10 +1211,14 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
       }
       case OP_ATTN: {
         int c = op.p[0], heads = op.p[1];
+        const bool with_pos = op.p[2] == 1;  // sine positions on the q / k inputs only (encoder.rs:34-79, 179-216)
         int T = a.H * a.W;
-        if (c / heads != 15 || c % heads) OAR_FAIL(OAR_E_UNSUPPORTED, "attention head_dim %d unsupported", c / heads);
-        if ((size_t)T * 15 * 2 * sizeof(float) > 48 * 1024)
-          OAR_FAIL(OAR_E_UNSUPPORTED, "attention sequence length %d too long", T);
+        if (heads <= 0 || c % heads) OAR_FAIL(OAR_E_MODEL, "attention op %zu: %d channels / %d heads", oi, c, heads);
+        const int hd = c / heads;
+        const bool small = hd == 15 && !with_pos && (size_t)T * 15 * 2 * sizeof(float) <= 48 * 1024;
+        if (!small && hd != 16 && hd != 32 && hd != 64 && hd != 15)
+          OAR_FAIL(OAR_E_UNSUPPORTED, "attention head_dim %d unsupported", hd);
+        if (a.C != c || (c & 3)) OAR_FAIL(OAR_E_MODEL, "attention op %zu: bad channels", oi);
         float* qkv = ctx->arena.get<float>((size_t)a.B * T * 3 * c);
         float* att = ctx->arena.get<float>((size_t)a.B * T * c);
         ConvParams p{};
@@ -1107,10 +1227,52 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.kh = p.kw = p.sh = p.sw = 1;
         p.N = 3 * c, p.K = c, p.M = a.B * T, p.out_ld = 3 * c, p.post_scale = 1.0f, p.cout = 3 * c;
         launch_gemm(m, (int)oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
+        const float* qk_src = qkv;
+        if (with_pos) {
+          // q, k = Linear(x + pos), v = Linear(x): the projection runs twice (once per input; the sequence is a few
+          // hundred tokens), the core reads q / k from the first result and v from the second
+          std::vector<float> pos((size_t)T * c);
+          const int pd = c / 4;
+          for (int y = 0; y < a.H; ++y)
+            for (int x = 0; x < a.W; ++x) {
+              float* row = pos.data() + ((size_t)y * a.W + x) * c;
+              for (int k = 0; k < pd; ++k) {
+                const double om = 1.0 / std::pow(10000.0, (double)k / pd);
+                row[k] = (float)std::sin(y * om), row[pd + k] = (float)std::cos(y * om);
+                row[2 * pd + k] = (float)std::sin(x * om), row[3 * pd + k] = (float)std::cos(x * om);
+              }
+            }
+          float* d_pos = ctx->arena.get<float>(pos.size());
+          float* h_pos = (float*)ctx->pinned_get(pos.size() * sizeof(float));
+          memcpy(h_pos, pos.data(), pos.size() * sizeof(float));
+          OAR_CUDA(cudaMemcpyAsync(d_pos, h_pos, pos.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+          float* xp = ctx->arena.get<float>(a.numel());
+          float* qkv2 = ctx->arena.get<float>((size_t)a.B * T * 3 * c);
+          {
+            Launch l(ctx, "add_pos", (double)a.numel(), 8.0 * a.numel());
+            add_rows_kernel<<<cdiv(a.numel() / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p),
+                                                                      reinterpret_cast<const float4*>(d_pos),
+                                                                      reinterpret_cast<float4*>(xp), T * c / 4, a.numel() / 4);
+          }
+          p.in = xp, p.out = qkv2;
+          launch_gemm(m, (int)oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
+          qk_src = qkv2;
+        }
         {
-          Launch l(ctx, "attn_core", 4.0 * a.B * heads * (double)T * T * 15, 4.0 * a.B * T * 4 * c);
-          attn_core_kernel<15><<<dim3(heads, a.B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
-                                                                                                   op.f[0]);
+          Launch l(ctx, "attn_core", 4.0 * a.B * heads * (double)T * T * hd, 4.0 * a.B * T * 4 * c);
+          if (small) {
+            attn_core_kernel<15><<<dim3(heads, a.B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
+                                                                                                     op.f[0]);
+          } else {
+            if (a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "attention op %zu: batch too large for one launch", oi);
+            dim3 grid(heads, a.B, cdiv(T, 128));
+            switch (hd) {
+              case 15: attn_core_any_kernel<15><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+              case 16: attn_core_any_kernel<16><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+              case 32: attn_core_any_kernel<32><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+              default: attn_core_any_kernel<64><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+            }
+          }
         }
         Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         p.in = att, p.w = m->w(op, 2), p.bias = m->w(op, 3), p.out = o.p;
@@ -1177,6 +1339,43 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         }
         t[op.out] = probs;
         last = probs;
+        break;
+      }
+      case OP_PAD: {
+        const int top = op.p[0], left = op.p[1], bottom = op.p[2], right = op.p[3];
+        if (top < 0 || left < 0 || bottom < 0 || right < 0 || (a.C & 3))
+          OAR_FAIL(OAR_E_MODEL, "pad op %zu: negative padding or channels not /4", oi);
+        Tensor& o = ensure(op.out, a.B, a.H + top + bottom, a.W + left + right, a.C);
+        const size_t total = o.numel() / 4;
+        Launch l(ctx, "pad", 0, 4.0 * (a.numel() + o.numel()));
+        pad_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p), reinterpret_cast<float4*>(o.p),
+                                                     a.H, a.W, a.C / 4, o.H, o.W, top, left, total);
+        break;
+      }
+      case OP_MAXPOOL: {
+        const int kh = op.p[0], kw = op.p[1], sh = op.p[2], sw = op.p[3];
+        if (kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || kh > a.H || kw > a.W || (a.C & 3))
+          OAR_FAIL(OAR_E_MODEL, "maxpool op %zu: window %dx%d / stride %dx%d does not fit %dx%d", oi, kh, kw, sh, sw, a.H,
+                   a.W);
+        Tensor& o = ensure(op.out, a.B, (a.H - kh) / sh + 1, (a.W - kw) / sw + 1, a.C);
+        const size_t total = o.numel() / 4;
+        Launch l(ctx, "maxpool", (double)o.numel() * kh * kw, 4.0 * (a.numel() + o.numel()));
+        maxpool_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p),
+                                                         reinterpret_cast<float4*>(o.p), a.H, a.W, a.C / 4, o.H, o.W, kh, kw,
+                                                         sh, sw, total);
+        break;
+      }
+      case OP_TOKENS: {
+        const int row_off = op.p[0], rows_total = op.p[1];
+        const int HW = a.H * a.W;
+        if (row_off < 0 || rows_total <= 0 || row_off + HW > rows_total || (a.C & 3))
+          OAR_FAIL(OAR_E_MODEL, "tokens op %zu: rows [%d, %d) do not fit %d", oi, row_off, row_off + HW, rows_total);
+        Tensor& o = ensure(op.out, a.B, 1, rows_total, a.C);
+        const size_t total = a.numel() / 4;
+        Launch l(ctx, "tokens", 0, 8.0 * a.numel());
+        tokens_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p), reinterpret_cast<float4*>(o.p),
+                                                        HW * (a.C / 4), row_off * (a.C / 4),
+                                                        (size_t)rows_total * (a.C / 4), total);
         break;
       }
       default:

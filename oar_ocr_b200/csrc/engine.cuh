@@ -16,9 +16,12 @@ enum OpType {
   OP_AVGPOOL,
   OP_LAYERNORM,
   OP_ATTN,
-  OP_CTC_HEAD
+  OP_CTC_HEAD,
+  OP_PAD,      // zero padding p = {top, left, bottom, right}: HGNetV2 stem (hgnetv2.rs:264-348)
+  OP_MAXPOOL,  // p = {kh, kw, sh, sw}, no padding
+  OP_TOKENS    // a map's pixels as rows [p[0], p[0] + H*W) of a [B, 1, p[1], C] sequence (layout detector memory)
 };
-enum Act { ACT_NONE = 0, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID };
+enum Act { ACT_NONE = 0, ACT_RELU, ACT_HSWISH, ACT_SWISH, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU /* exact, erf */ };
 
 struct OpRec {
   int32_t type, in0, in1, out;

@@ -23,6 +23,7 @@ __device__ __forceinline__ float act_simt(float v, int act) {
     case ACT_SWISH: return v / (1.0f + expf(-v));
     case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
     case ACT_HSIGMOID: return fminf(fmaxf(v / 6.0f + 0.5f, 0.0f), 1.0f);
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }

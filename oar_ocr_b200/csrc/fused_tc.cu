@@ -83,6 +83,7 @@ __device__ __forceinline__ float act_rt(float v, int act) {
     case ACT_SWISH: return __fdividef(v, 1.0f + __expf(-v));
     case ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-v));
     case ACT_HSIGMOID: return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }
@@ -513,6 +514,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             FB_ACT_CASE(ACT_SWISH)
             FB_ACT_CASE(ACT_SIGMOID)
             FB_ACT_CASE(ACT_HSIGMOID)
+            FB_ACT_CASE(ACT_GELU)
 #undef FB_ACT_CASE
             default: break;
           }

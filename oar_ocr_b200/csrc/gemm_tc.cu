@@ -758,7 +758,9 @@ TcWeights pack_weights(const float* w, int N, int K, bool force_kc4) {
 static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int Cin) {
   TcWeights t;
   t.N = N, t.K = kh * kw * Cin, t.rowtaps = true, t.kh = kh, t.kw = kw, t.KC = 4;
-  t.n_tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
+  // two stages of (A halo rows + kw weight taps) must fit the kernel's 200 KB: 2 * (2 * 4 * RT_LBO + kw * 128 * BN)
+  const int bn_cap = std::min(TC_MAX_BN, (int)((200 * 1024 - 2048) / 2 - 2 * RT_KC * (int)RT_LBO) / (kw * 128) / 32 * 32);
+  t.n_tiles = (N + bn_cap - 1) / bn_cap;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
   t.BN = t.n_tiles > 1 ? (per + 31) / 32 * 32 : std::max(16, (per + 15) / 16 * 16);
   const int ncb = Cin / 32;

@@ -170,6 +170,7 @@ __device__ __forceinline__ float act_t(float v) {
   if (ACT == ACT_SWISH) return __fdividef(v, 1.0f + __expf(-v));
   if (ACT == ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
   if (ACT == ACT_HSIGMOID) return fminf(fmaxf(v * 0.16666667f + 0.5f, 0.0f), 1.0f);
+  if (ACT == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   return v;
 }
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboar_b200.so")
 
 OAR_OK, OAR_E_INVALID, OAR_E_NO_DEVICE, OAR_E_CUDA, OAR_E_MODEL, OAR_E_CAPACITY, OAR_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-KIND_DET, KIND_REC, KIND_CLS = 0, 1, 2
+KIND_DET, KIND_REC, KIND_CLS, KIND_FEAT = 0, 1, 2, 3
 
 # every symbol include/oar_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
@@ -470,14 +470,17 @@ class Model:
     def set_engine(self, engine: int):
         check(lib().oar_model_set_engine(self.handle, engine))
 
-    def infer(self, x: np.ndarray, vocab_hint: int = 18385) -> np.ndarray:
-        """OrtInfer::infer: x f32 [B,3,H,W] -> det [B,1,H,W] / rec [B,T,V] / cls [B,classes]"""
+    def infer(self, x: np.ndarray, vocab_hint: int = 18385, out_cap: int | None = None) -> np.ndarray:
+        """OrtInfer::infer: x f32 [B,3,H,W] -> det [B,1,H,W] / rec [B,T,V] / cls [B,classes] / feature extractor
+        [B,C,H,W] (out_cap: capacity in floats for a feature extractor, default = the input's size)"""
         x = np.ascontiguousarray(x, np.float32)
         if x.ndim != 4:
             raise OCRError("InvalidInput", "input must be 4-D", OAR_E_INVALID)
         b, c, h, w = x.shape
         cap = b * h * w if self.kind == KIND_DET else (b * 4096 if self.kind == KIND_CLS else
                                                        b * (w // 8 + 2) * vocab_hint)
+        if self.kind == KIND_FEAT:
+            cap = out_cap or b * h * w * 16
         out = np.empty(max(cap, 1), np.float32)
         ishape = (C.c_int64 * 4)(b, c, h, w)
         oshape = (C.c_int64 * 4)()
@@ -485,6 +488,9 @@ class Model:
         if self.kind == KIND_DET:
             return out[:oshape[0] * oshape[1] * oshape[2] * oshape[3]].reshape(oshape[0], oshape[1], oshape[2],
                                                                                oshape[3])
+        if self.kind == KIND_FEAT:  # stored NHWC; returned in the reference's NCHW
+            return np.ascontiguousarray(out[:oshape[0] * oshape[1] * oshape[2] * oshape[3]].reshape(
+                oshape[0], oshape[1], oshape[2], oshape[3]).transpose(0, 3, 1, 2))
         y = out[:oshape[0] * oshape[1] * oshape[2]].reshape(oshape[0], oshape[1], oshape[2])
         return y.reshape(oshape[0], oshape[2]) if self.kind == KIND_CLS else y
 

@@ -42,10 +42,13 @@ def test_config0_single_640_detection(ctx, det_blob):
 
 
 @pytest.mark.gpu
-def test_engine_refuses_spec_only_graphs(ctx):
-    """the CUDA library refuses the backbone blob outright (unknown model kind, checked in the blob header before
-    anything touches the device) instead of falling back to anything"""
+def test_engine_refuses_unknown_model_kinds(ctx):
+    """a blob whose header names a model kind the library does not know is refused outright (checked in the blob
+    header before anything touches the device) instead of falling back to anything"""
+    import struct
     from oar_ocr_b200 import ffi, models
+    blob = bytearray(models.build_hgnetv2_l(return_idx=(0,)))
+    struct.pack_into("<I", blob, 8, 9)
     with pytest.raises(ffi.OCRError) as e:
-        ffi.Model(ctx, models.build_hgnetv2_l(return_idx=(0,)))
+        ffi.Model(ctx, bytes(blob))
     assert e.value.code == ffi.OAR_E_MODEL and "unknown model kind" in str(e.value)
