@@ -301,6 +301,21 @@ int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, i
                                const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
                                const oar_pipeline_config* cfg, oar_ocr_result* out);
 
+/* ---- layout detection on the device (BASELINE.json configs[4]) --------------------------------
+ * LayoutDetectionAdapter::execute (oar-ocr-core/src/domain/adapters/layout_detection_adapter.rs:1128-1197) ->
+ * ScaleAwareDetectorModel::preprocess / infer (models/detection/scale_aware_detector.rs:150-333) for the PP-DocLayout
+ * family: resize_exact to (input_h, input_w) with FilterType::CatmullRom, scale 1/255, RGB; RT-DETR-L
+ * (HGNetV2-L, hybrid encoder, 6-layer deformable decoder; oar-ocr-vl/src/models/pp_doclayout/) ; the exported model's
+ * own tail (sigmoid, top-300 over (query, class), cxcywh -> xyxy scaled to the source image).
+ * encoder / head: two OAR_KIND_FEAT models on one context (oar_ocr_b200.models.build_layout_encoder for this input
+ * size, build_layout_head).  oar_layout_rows returns the model's output tensor, rows [n][300][6] =
+ * [class_id, score, x1, y1, x2, y2] -- what the adapter reads; oar_layout_run feeds it to oar_layout_postprocess. */
+int32_t oar_layout_rows(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
+                        const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, float* rows, size_t rows_cap);
+int32_t oar_layout_run(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
+                       const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, const oar_layout_config* cfg,
+                       float* boxes, int32_t* classes, float* scores, int32_t* counts);
+
 /* device memory helpers for callers that keep inputs resident (bench `value` leg) */
 int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out);
 int32_t oar_device_free(oar_ctx* ctx, void* p);

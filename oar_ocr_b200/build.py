@@ -23,6 +23,7 @@ SOURCES = {
     "fused_simt.cu": [],
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
+    "layout_net.cu": ["-fmad=false"],  # the exported-model tail restates f32 box arithmetic step by step
     "layout.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only f32 restatement: no FMA contraction
     "onnx_import.cu": ["-Xcompiler", "-ffp-contract=off"],  # host-only; BatchNorm folding in f32 step by step like numpy
 }

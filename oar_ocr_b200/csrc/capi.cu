@@ -1735,6 +1735,44 @@ int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, i
   API_CATCH
 }
 
+// ---- layout detection: LayoutDetectionAdapter::execute on the device ---------------------
+int32_t oar_layout_rows(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
+                        const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, float* rows, size_t rows_cap) {
+  API_TRY
+  if (!encoder || !head || encoder->kind != OAR_KIND_FEAT || head->kind != OAR_KIND_FEAT)
+    OAR_FAIL(OAR_E_INVALID, "layout detection needs an encoder model and a head model (feature-extractor kind)");
+  if (encoder->ctx != head->ctx) OAR_FAIL(OAR_E_INVALID, "both models must live on the same context");
+  if (n <= 0 || !images || !hs || !ws) OAR_FAIL(OAR_E_INVALID, "images: expected non-empty slice, got empty slice");
+  if (!rows) OAR_FAIL(OAR_E_INVALID, "null argument");
+  if ((size_t)n * 300 * 6 > rows_cap) OAR_FAIL(OAR_E_CAPACITY, "rows need %zu floats, capacity %zu", (size_t)n * 1800, rows_cap);
+  oar_ctx* ctx = encoder->ctx;
+  CallGuard guard(ctx);
+  const float* d_rows = layout_rows_device(encoder, head, images, hs, ws, n, input_h, input_w);
+  OAR_CUDA(cudaMemcpyAsync(rows, d_rows, (size_t)n * 1800 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_CATCH
+}
+
+int32_t oar_layout_run(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
+                       const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, const oar_layout_config* cfg,
+                       float* boxes, int32_t* classes, float* scores, int32_t* counts) {
+  if (!cfg || !boxes || !classes || !scores || !counts) {
+    oar::set_error("null argument");
+    return OAR_E_INVALID;
+  }
+  if (n <= 0) {
+    oar::set_error("images: expected non-empty slice, got empty slice");
+    return OAR_E_INVALID;
+  }
+  std::vector<float> rows((size_t)n * 1800);
+  int32_t rc = oar_layout_rows(encoder, head, images, hs, ws, n, input_h, input_w, rows.data(), rows.size());
+  if (rc != OAR_OK) return rc;
+  std::vector<float> sw(n), sh(n);
+  for (int i = 0; i < n; ++i) sw[i] = (float)ws[i], sh[i] = (float)hs[i];
+  // postprocess_pp_doclayout (layout_detection_adapter.rs:631-1116): host code in the reference and here (csrc/layout.cu)
+  return oar_layout_postprocess(rows.data(), n, 300, 6, sw.data(), sh.data(), cfg, boxes, classes, scores, counts);
+}
+
 int32_t oar_device_alloc(oar_ctx* ctx, size_t bytes, void** out) {
   API_TRY
   require_device(ctx);

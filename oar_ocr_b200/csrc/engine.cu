@@ -928,6 +928,81 @@ void launch_nchw_to_nhwc(oar_ctx* ctx, const float* in, float* out, int B, int C
 // ---------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// single layers of a model, callable outside a graph walk (model_forward uses them too; csrc/layout_net.cu runs the
+// layout detector's decoder with them)
+// ---------------------------------------------------------------------------
+// y[rows, N] = act(x[rows, K] W^T + b) for a 1x1 OP_CONV; out_ld / out_off place y in a wider row
+void op_linear(oar_model* m, int oi, const float* in, int rows, float* out, int out_ld, int out_off) {
+  const OpRec& op = m->ops[oi];
+  if (op.type != OP_CONV || op.p[0] != 1 || op.p[1] != 1) OAR_FAIL(OAR_E_MODEL, "layer %d is not a 1x1 convolution", oi);
+  ConvParams p{};
+  p.in = in, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = out;
+  p.B = 1, p.H = 1, p.W = rows, p.Cin = op.p[6], p.Ho = 1, p.Wo = rows;
+  p.kh = p.kw = p.sh = p.sw = 1;
+  p.N = op.p[7], p.K = op.p[6], p.M = rows;
+  p.out_ld = out_ld ? out_ld : op.p[7], p.out_c_off = out_off, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
+  p.cout = op.p[7];
+  launch_gemm(m, oi * 2, p, "linear_simt", "linear_tc");
+}
+
+void op_layernorm(oar_model* m, int oi, const float* in, int rows, float* out) {
+  const OpRec& op = m->ops[oi];
+  if (op.type != OP_LAYERNORM) OAR_FAIL(OAR_E_MODEL, "layer %d is not a LayerNorm", oi);
+  const int c = op.p[0];
+  Launch l(m->ctx, "layernorm", 8.0 * rows * c, 8.0 * rows * c);
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, m->ctx->stream>>>(in, m->w(op, 0), m->w(op, 1), out, (size_t)rows, c, op.f[0]);
+}
+
+// multi-head attention block of an OP_ATTN layer over B sequences of T tokens: q, k = Linear(x_qk ? x_qk : x),
+// v = Linear(x), softmax(q k^T * scale) v, output projection.  x_qk = the input with positions added.
+void op_attention(oar_model* m, int oi, const float* x, const float* x_qk, int B, int T, float* out) {
+  oar_ctx* ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const OpRec& op = m->ops[oi];
+  if (op.type != OP_ATTN) OAR_FAIL(OAR_E_MODEL, "layer %d is not an attention block", oi);
+  const int c = op.p[0], heads = op.p[1];
+  if (heads <= 0 || c % heads) OAR_FAIL(OAR_E_MODEL, "attention layer %d: %d channels / %d heads", oi, c, heads);
+  const int hd = c / heads;
+  const bool small = hd == 15 && !x_qk && (size_t)T * 15 * 2 * sizeof(float) <= 48 * 1024;
+  if (hd != 15 && hd != 16 && hd != 32 && hd != 64) OAR_FAIL(OAR_E_UNSUPPORTED, "attention head_dim %d unsupported", hd);
+  float* qkv = ctx->arena.get<float>((size_t)B * T * 3 * c);
+  float* att = ctx->arena.get<float>((size_t)B * T * c);
+  ConvParams p{};
+  p.in = x, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = qkv;
+  p.B = B, p.H = 1, p.W = T, p.Cin = c, p.Ho = 1, p.Wo = T;
+  p.kh = p.kw = p.sh = p.sw = 1;
+  p.N = 3 * c, p.K = c, p.M = B * T, p.out_ld = 3 * c, p.post_scale = 1.0f, p.cout = 3 * c;
+  launch_gemm(m, oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
+  const float* qk_src = qkv;
+  if (x_qk) {
+    // the projection runs twice (once per input; these sequences are a few hundred tokens): the core reads q / k from
+    // the positioned result and v from the plain one
+    float* qkv2 = ctx->arena.get<float>((size_t)B * T * 3 * c);
+    p.in = x_qk, p.out = qkv2;
+    launch_gemm(m, oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
+    qk_src = qkv2;
+  }
+  {
+    Launch l(ctx, "attn_core", 4.0 * B * heads * (double)T * T * hd, 4.0 * B * T * 4 * c);
+    if (small) {
+      attn_core_kernel<15><<<dim3(heads, B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads, op.f[0]);
+    } else {
+      if (B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "attention layer %d: batch too large for one launch", oi);
+      dim3 grid(heads, B, cdiv(T, 128));
+      switch (hd) {
+        case 15: attn_core_any_kernel<15><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+        case 16: attn_core_any_kernel<16><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+        case 32: attn_core_any_kernel<32><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+        default: attn_core_any_kernel<64><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
+      }
+    }
+  }
+  p.in = att, p.w = m->w(op, 2), p.bias = m->w(op, 3), p.out = out;
+  p.N = c, p.out_ld = c, p.cout = c;
+  launch_gemm(m, oi * 2 + 1, p, "attn_proj_simt", "attn_proj_tc");
+}
+
 static inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
 Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc, const U8Input* u8) {
@@ -1210,29 +1285,14 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         break;
       }
       case OP_ATTN: {
-        int c = op.p[0], heads = op.p[1];
-        const bool with_pos = op.p[2] == 1;  // sine positions on the q / k inputs only (encoder.rs:34-79, 179-216)
-        int T = a.H * a.W;
-        if (heads <= 0 || c % heads) OAR_FAIL(OAR_E_MODEL, "attention op %zu: %d channels / %d heads", oi, c, heads);
-        const int hd = c / heads;
-        const bool small = hd == 15 && !with_pos && (size_t)T * 15 * 2 * sizeof(float) <= 48 * 1024;
-        if (!small && hd != 16 && hd != 32 && hd != 64 && hd != 15)
-          OAR_FAIL(OAR_E_UNSUPPORTED, "attention head_dim %d unsupported", hd);
-        if (a.C != c || (c & 3)) OAR_FAIL(OAR_E_MODEL, "attention op %zu: bad channels", oi);
-        float* qkv = ctx->arena.get<float>((size_t)a.B * T * 3 * c);
-        float* att = ctx->arena.get<float>((size_t)a.B * T * c);
-        ConvParams p{};
-        p.in = a.p, p.w = m->w(op, 0), p.bias = m->w(op, 1), p.out = qkv;
-        p.B = a.B, p.H = a.H, p.W = a.W, p.Cin = c, p.Ho = a.H, p.Wo = a.W;
-        p.kh = p.kw = p.sh = p.sw = 1;
-        p.N = 3 * c, p.K = c, p.M = a.B * T, p.out_ld = 3 * c, p.post_scale = 1.0f, p.cout = 3 * c;
-        launch_gemm(m, (int)oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
-        const float* qk_src = qkv;
-        if (with_pos) {
-          // q, k = Linear(x + pos), v = Linear(x): the projection runs twice (once per input; the sequence is a few
-          // hundred tokens), the core reads q / k from the first result and v from the second
+        if (a.C != op.p[0] || (a.C & 3)) OAR_FAIL(OAR_E_MODEL, "attention op %zu: bad channels", oi);
+        const int T = a.H * a.W;
+        const float* x_qk = nullptr;
+        if (op.p[2] == 1) {
+          // sine positions on the q / k inputs only (encoder.rs:34-79, 179-216): the [T, C] table is computed on the host
+          // in f64 like the reference, x + pos goes through the q / k projection
+          const int c = a.C, pd = c / 4;
           std::vector<float> pos((size_t)T * c);
-          const int pd = c / 4;
           for (int y = 0; y < a.H; ++y)
             for (int x = 0; x < a.W; ++x) {
               float* row = pos.data() + ((size_t)y * a.W + x) * c;
@@ -1247,37 +1307,14 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
           memcpy(h_pos, pos.data(), pos.size() * sizeof(float));
           OAR_CUDA(cudaMemcpyAsync(d_pos, h_pos, pos.size() * sizeof(float), cudaMemcpyHostToDevice, st));
           float* xp = ctx->arena.get<float>(a.numel());
-          float* qkv2 = ctx->arena.get<float>((size_t)a.B * T * 3 * c);
-          {
-            Launch l(ctx, "add_pos", (double)a.numel(), 8.0 * a.numel());
-            add_rows_kernel<<<cdiv(a.numel() / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p),
-                                                                      reinterpret_cast<const float4*>(d_pos),
-                                                                      reinterpret_cast<float4*>(xp), T * c / 4, a.numel() / 4);
-          }
-          p.in = xp, p.out = qkv2;
-          launch_gemm(m, (int)oi * 2, p, "attn_qkv_simt", "attn_qkv_tc");
-          qk_src = qkv2;
+          Launch l(ctx, "add_pos", (double)a.numel(), 8.0 * a.numel());
+          add_rows_kernel<<<cdiv(a.numel() / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a.p),
+                                                                    reinterpret_cast<const float4*>(d_pos),
+                                                                    reinterpret_cast<float4*>(xp), T * c / 4, a.numel() / 4);
+          x_qk = xp;
         }
-        {
-          Launch l(ctx, "attn_core", 4.0 * a.B * heads * (double)T * T * hd, 4.0 * a.B * T * 4 * c);
-          if (small) {
-            attn_core_kernel<15><<<dim3(heads, a.B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
-                                                                                                     op.f[0]);
-          } else {
-            if (a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "attention op %zu: batch too large for one launch", oi);
-            dim3 grid(heads, a.B, cdiv(T, 128));
-            switch (hd) {
-              case 15: attn_core_any_kernel<15><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
-              case 16: attn_core_any_kernel<16><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
-              case 32: attn_core_any_kernel<32><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
-              default: attn_core_any_kernel<64><<<grid, 128, 0, st>>>(qk_src, qkv, att, T, heads, op.f[0]); break;
-            }
-          }
-        }
-        Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
-        p.in = att, p.w = m->w(op, 2), p.bias = m->w(op, 3), p.out = o.p;
-        p.N = c, p.out_ld = c, p.cout = c;
-        launch_gemm(m, (int)oi * 2 + 1, p, "attn_proj_simt", "attn_proj_tc");
+        Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
+        op_attention(m, (int)oi, a.p, x_qk, a.B, T, o.p);
         break;
       }
       case OP_CTC_HEAD: {

@@ -123,6 +123,18 @@ namespace oar {
 // `u8` (optional): the input is given as u8 pixels instead of `in.p` (in.p == nullptr, dims from u8).
 Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ctc, const U8Input* u8 = nullptr);
 
+// Single layers of a loaded model, run outside a graph walk (engine.cu; the layout decoder in layout_net.cu calls them by
+// position): 1x1 convolution as a Linear over `rows` rows, LayerNorm, multi-head attention over B sequences of T tokens
+// (x_qk: the input with positions added for the q / k projections, or null).
+void op_linear(oar_model* m, int oi, const float* in, int rows, float* out, int out_ld = 0, int out_off = 0);
+void op_layernorm(oar_model* m, int oi, const float* in, int rows, float* out);
+void op_attention(oar_model* m, int oi, const float* x, const float* x_qk, int B, int T, float* out);
+
+// layout_net.cu: ScaleAwareDetectorModel::preprocess (pp_doclayout) + RT-DETR-L on the device.  Host pages in, the
+// exported model's rows [n, 300, 6] = [class_id, score, x1, y1, x2, y2] (source pixels) out, in the context's arena.
+float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const* images, const int32_t* hs, const int32_t* ws,
+                          int n, int in_h, int in_w);
+
 // fused_simt.cu: false = shape not covered, the caller runs the per-layer path
 bool launch_stem_u8(oar_ctx* ctx, const U8Input& S, const OpRec& op, const float* w, const float* bias, float* out, int Ho,
                     int Wo);

@@ -93,15 +93,31 @@ __device__ __forceinline__ float tri_kernel(float x) {
   return a < 1.0f ? 1.0f - a : 0.0f;
 }
 
+// image 0.25 sample.rs: bc_cubic_spline(x, b = 0, c = 0.5) = CatmullRom, support 2
+__device__ __forceinline__ float catmull_kernel(float x) {
+  const float b = 0.0f, c = 0.5f;
+  float a = fabsf(x);
+  float k;
+  if (a < 1.0f)
+    k = (12.0f - 9.0f * b - 6.0f * c) * (a * a * a) + (-18.0f + 12.0f * b + 6.0f * c) * (a * a) + (6.0f - 2.0f * b);
+  else if (a < 2.0f)
+    k = (-b - 6.0f * c) * (a * a * a) + (6.0f * b + 30.0f * c) * (a * a) + (-12.0f * b - 48.0f * c) * a +
+        (8.0f * b + 24.0f * c);
+  else
+    k = 0.0f;
+  return k / 6.0f;
+}
+__device__ __forceinline__ float filter_kernel(int filter, float x) { return filter == 1 ? catmull_kernel(x) : tri_kernel(x); }
+
 struct TapRange {
   int left, right;
   float in, sratio;
 };
-__device__ __forceinline__ TapRange tap_range(int o, int in_len, int out_len) {
+__device__ __forceinline__ TapRange tap_range(int o, int in_len, int out_len, int filter = 0) {
   TapRange t;
   float ratio = (float)in_len / (float)out_len;
   t.sratio = ratio < 1.0f ? 1.0f : ratio;
-  float support = 1.0f * t.sratio;
+  float support = (filter == 1 ? 2.0f : 1.0f) * t.sratio;
   float c = ((float)o + 0.5f) * ratio;
   long long l = (long long)floorf(c - support);
   l = l < 0 ? 0 : (l > (long long)in_len - 1 ? (long long)in_len - 1 : l);
@@ -120,11 +136,11 @@ __global__ void resize_v_kernel(const ResizeJob* __restrict__ jobs) {
   if (x >= j.sw || oy >= j.dh) return;
   float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
   if (j.dh == j.sh && j.dw == j.sw) return;  // identity handled in the h pass
-  TapRange tr = tap_range(oy, j.sh, j.dh);
+  TapRange tr = tap_range(oy, j.sh, j.dh, j.filter);
   float sum = 0.0f;
-  for (int i = tr.left; i < tr.right; ++i) sum += tri_kernel(((float)i - tr.in) / tr.sratio);
+  for (int i = tr.left; i < tr.right; ++i) sum += filter_kernel(j.filter, ((float)i - tr.in) / tr.sratio);
   for (int i = tr.left; i < tr.right; ++i) {
-    float w = tri_kernel(((float)i - tr.in) / tr.sratio) / sum;
+    float w = filter_kernel(j.filter, ((float)i - tr.in) / tr.sratio) / sum;
     const uint8_t* p = j.src + ((size_t)i * j.sw + x) * 3;
     t0 += (float)p[0] * w;
     t1 += (float)p[1] * w;
@@ -145,12 +161,12 @@ __global__ void resize_h_kernel(const ResizeJob* __restrict__ jobs) {
     o[0] = s[0], o[1] = s[1], o[2] = s[2];
     return;
   }
-  TapRange tr = tap_range(ox, j.sw, j.dw);
+  TapRange tr = tap_range(ox, j.sw, j.dw, j.filter);
   float sum = 0.0f;
-  for (int i = tr.left; i < tr.right; ++i) sum += tri_kernel(((float)i - tr.in) / tr.sratio);
+  for (int i = tr.left; i < tr.right; ++i) sum += filter_kernel(j.filter, ((float)i - tr.in) / tr.sratio);
   float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
   for (int i = tr.left; i < tr.right; ++i) {
-    float w = tri_kernel(((float)i - tr.in) / tr.sratio) / sum;
+    float w = filter_kernel(j.filter, ((float)i - tr.in) / tr.sratio) / sum;
     const float* p = j.tmp + ((size_t)y * j.sw + i) * 3;
     t0 += p[0] * w;
     t1 += p[1] * w;

@@ -22,6 +22,8 @@ struct ResizeJob {
   float* tmp;          // [dh][sw][3]
   uint8_t* dst;        // [dh][dw][3]
   int sw, sh, dw, dh;
+  int filter = 0;  // 0 = Triangle (text detection / recognition), 1 = CatmullRom (PP-DocLayout detectors,
+                   // scale_aware_detector.rs:66-80): same two-pass sampler, other kernel and support
 };
 void launch_resize_triangle(oar_ctx* ctx, const ResizeJob* d_jobs, int n_jobs, int max_sw, int max_dw, int max_dh);
 

@@ -27,6 +27,7 @@ SYMBOLS = [
     "oar_layout_postprocess", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
     "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush", "oar_model_validate_blob",
     "oar_model_load_onnx", "oar_onnx_to_oarg", "oar_crop_rec_run", "oar_rec_run_ex", "oar_pipeline_run_multi",
+    "oar_layout_rows", "oar_layout_run",
 ]
 
 
@@ -139,6 +140,10 @@ def lib():
         L.oar_crop_rec_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6 + \
             [C.c_int32]
+        L.oar_layout_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p, C.c_size_t]
+        L.oar_layout_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.POINTER(LayoutConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oar_pipeline_run_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
         L.oar_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
@@ -610,6 +615,16 @@ class PipelineBuffers:
         # TextRegion.orientation_angle of the line-orientation stage: 0 / 180, -1 = None (no classifier)
         self.line_angle = np.full(cap_regions, -1.0, np.float32)
         self.res.line_angle = self.line_angle.ctypes.data_as(P(C.c_float))
+
+
+def layout_rows(encoder: "Model", head: "Model", images, input_hw=(640, 640)) -> np.ndarray:
+    """oar_layout_rows: pages -> the layout detector's output tensor [n, 300, 6] = [class_id, score, x1, y1, x2, y2]"""
+    arrs, ptrs, hs, ws = _image_table(images)
+    n = len(arrs)
+    rows = np.zeros((n, 300, 6), np.float32)
+    check(lib().oar_layout_rows(encoder.handle, head.handle, ptrs, _ptr(hs), _ptr(ws), n, int(input_hw[0]),
+                                int(input_hw[1]), _ptr(rows), rows.size))
+    return rows
 
 
 def pipeline_run_multi(dets, recs, image_ptrs, hs: np.ndarray, ws: np.ndarray, cfg: PipelineConfig,

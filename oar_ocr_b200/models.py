@@ -712,6 +712,53 @@ def build_layout_encoder(weights: dict, seed: int = 42, shapes_hw=None) -> bytes
     return g.serialize()
 
 
+# Layout detector head (RT-DETR-L decoder) as a table of single layers in OARG form.  It is NOT a graph to execute in
+# order: csrc/layout_net.cu runs the decoder (query selection, 6 layers of self-attention + multi-scale deformable
+# attention + FFN, box refinement) and calls these layers by POSITION, so that their weights get the same packing /
+# tensor-core kernels as every other 1x1 convolution, LayerNorm and attention block.  The order below is the ABI between
+# this builder and layout_net.cu (LH_* constants there).
+LAYOUT_HEAD_FIXED = 8        # enc_output, enc_output_ln, enc_score, enc_bbox0..2, query_pos0, query_pos1
+LAYOUT_HEAD_PER_LAYER = 14   # sa, ln1, ca.offsets, ca.weights, ca.value, ca.out, ln2, fc1, fc2, ln3, score, bbox0..2
+
+
+def build_layout_head(weights: dict, dec_layers: int = 6) -> bytes:
+    W = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    g = GraphBuilder(KIND_FEAT, 0)
+    d = 256
+    src = {}
+
+    def inp(c):  # one placeholder tensor per input width (the ops are never chained)
+        if c not in src:
+            src[c] = g.new_tensor(c)
+        return src[c]
+
+    def lin(name, act=ACT_NONE):
+        w = W[name + ".w"]
+        return g.conv(inp(w.shape[1]), w.shape[0], (1, 1), act=act, w=np.ascontiguousarray(w[:, None, None, :]), b=W[name + ".b"])
+
+    def ln(name):
+        return g.layernorm(inp(d), 1e-5, W[name + ".g"], W[name + ".b"])
+
+    lin("enc_output"); ln("enc_output_ln"); lin("enc_score")
+    lin("enc_bbox0", ACT_RELU); lin("enc_bbox1", ACT_RELU); lin("enc_bbox2")
+    lin("query_pos0", ACT_RELU); lin("query_pos1")
+    assert len(g.ops) == LAYOUT_HEAD_FIXED
+    for i in range(dec_layers):
+        p = f"dec{i}"
+        wqkv = np.concatenate([W[p + ".sa.q.w"], W[p + ".sa.k.w"], W[p + ".sa.v.w"]], 0)
+        bqkv = np.concatenate([W[p + ".sa.q.b"], W[p + ".sa.k.b"], W[p + ".sa.v.b"]], 0)
+        g.attn(inp(d), 8, wqkv=wqkv, bqkv=bqkv, wp=W[p + ".sa.o.w"], bp=W[p + ".sa.o.b"])
+        ln(p + ".ln1")
+        lin(p + ".ca.offsets"); lin(p + ".ca.weights"); lin(p + ".ca.value"); lin(p + ".ca.out")
+        ln(p + ".ln2")
+        lin(p + ".fc1", ACT_RELU); lin(p + ".fc2")
+        ln(p + ".ln3")
+        lin(p + ".score")
+        lin(p + ".bbox0", ACT_RELU); lin(p + ".bbox1", ACT_RELU); lin(p + ".bbox2")
+    assert len(g.ops) == LAYOUT_HEAD_FIXED + LAYOUT_HEAD_PER_LAYER * dec_layers
+    return g.serialize()
+
+
 # Server-size recogniser: PP-OCRv5_server_rec = PPHGNetV2_B4 (the table above; "B4" and "L" name the
 # same widths) with text-recognition strides + the SVTR neck + CTC head of the mobile model.  EXT: the stride table is
 # recalled from PaddleOCR's rec_pphgnetv2 (stem3 stride 1; stage downsamples (2,1), (1,2), (2,1), (2,1); every stage

@@ -84,3 +84,77 @@ def test_layout_encoder_memory(ctx, engine):
     got = m.infer(x, out_cap=want.size + 64)
     assert got.shape == want.shape == (2, 256, 1, sum(h * w for h, w in shapes))
     assert _rel(got, want) <= 2e-4
+
+
+def _layout_models(ctx, in_hw):
+    from oar_ocr_b200 import ffi, models
+    w = models.layout_weights(42)
+    shapes = [(in_hw[0] // s, in_hw[1] // s) for s in (8, 16, 32)]
+    enc = ffi.Model(ctx, models.build_layout_encoder(w, seed=42, shapes_hw=shapes))
+    head = ffi.Model(ctx, models.build_layout_head(w))
+    return enc, head
+
+
+def test_layout_rows_match_oracle(ctx):
+    """BASELINE.json configs[4] at a reduced input size, whole network on the device: pages -> CatmullRom resize ->
+    RT-DETR-L -> the exported model's rows, against oracle/rtdetr.py fed by the oracle's preprocessing.  Rows are
+    score-ordered; near-equal scores may swap places, so every oracle row is matched to a product row of the same class
+    (score within 2e-3, box corners within 0.25 px of a page that is hundreds of pixels wide)."""
+    from oar_ocr_b200 import ffi, synth
+    from oracle import cpu
+    from oracle.rtdetr import RTDetrL
+    in_hw = (256, 256)
+    pages = [synth.page(400, 480), synth.page(401, 320), synth.page(402, 256)]
+    enc, head = _layout_models(ctx, in_hw)
+    got = ffi.layout_rows(enc, head, pages, in_hw)
+    x, _ = cpu.layout_preprocess(pages, in_hw)
+    want = RTDetrL(42).rows(x, [(p.shape[1], p.shape[0]) for p in pages])
+    assert got.shape == want.shape == (3, 300, 6)
+    for b in range(3):
+        g, w = got[b], want[b]
+        assert np.all(np.diff(g[:, 1]) <= 1e-7)  # descending scores
+        assert abs(g[0, 1] - w[0, 1]) <= 2e-3
+        used = np.zeros(300, bool)
+        for r in range(100):  # the 100 best oracle rows
+            cand = np.where((g[:, 0] == w[r, 0]) & (np.abs(g[:, 1] - w[r, 1]) <= 2e-3) & ~used)[0]
+            d = [np.abs(g[c, 2:] - w[r, 2:]).max() for c in cand]
+            assert len(d) and min(d) <= 0.25, (b, r, w[r], len(d), min(d) if d else None)
+            used[cand[int(np.argmin(d))]] = True
+
+
+def test_layout_run_end_to_end(ctx):
+    """oar_layout_run = rows + postprocess_pp_doclayout: the kept elements equal the oracle's on its own rows
+    (same classes, scores within 2e-3, boxes within 0.25 px)"""
+    import ctypes as C
+    from oar_ocr_b200 import ffi, synth
+    from oracle import cpu
+    from oracle.rtdetr import RTDetrL
+    in_hw = (256, 256)
+    pages = [synth.page(410, 480), synth.page(411, 320)]
+    enc, head = _layout_models(ctx, in_hw)
+    arrs, ptrs, hs, ws = ffi._image_table(pages)
+    cfg = ffi.LayoutConfig()
+    ffi.lib().oar_layout_config_default(C.byref(cfg))
+    cfg.score_threshold = 0.3
+    cfg.num_classes = 23
+    me = cfg.max_elements
+    boxes = np.zeros((2, me, 4), np.float32)
+    classes = np.zeros((2, me), np.int32)
+    scores = np.zeros((2, me), np.float32)
+    counts = np.zeros(2, np.int32)
+    ffi.check(ffi.lib().oar_layout_run(enc.handle, head.handle, ptrs, ffi._ptr(hs), ffi._ptr(ws), 2, in_hw[0], in_hw[1],
+                                       C.byref(cfg), ffi._ptr(boxes), ffi._ptr(classes), ffi._ptr(scores), ffi._ptr(counts)))
+    x, _ = cpu.layout_preprocess(pages, in_hw)
+    rows = RTDetrL(42).rows(x, [(p.shape[1], p.shape[0]) for p in pages])
+    total = 0
+    for b, p in enumerate(pages):
+        ob, oc, os_ = cpu.layout_postprocess(rows[b], p.shape[1], p.shape[0], 23, score_threshold=0.3,
+                                             image_class_id=cfg.image_class_id, formula_class_id=cfg.formula_class_id)
+        n = int(counts[b])
+        assert n == len(ob), (n, len(ob))
+        for k in range(n):
+            j = [i for i in range(n) if classes[b, i] == oc[k] and abs(scores[b, i] - os_[k]) <= 2e-3 and
+                 np.abs(boxes[b, i] - ob[k]).max() <= 0.25]
+            assert j, (b, k, oc[k], os_[k], ob[k])
+        total += n
+    assert total >= 1
