@@ -509,6 +509,170 @@ def run_reference_rec512(args, rank, world):
     }))
 
 
+METRIC_LAYOUT = "layout-detection pages/sec (PP-DocLayout-L: RT-DETR-L, 1024x1024 pages -> 640x640)"
+UNIT_LAYOUT = "pages/s"
+LAYOUT_IN = (640, 640)
+LAYOUT_PAGE = 1024
+
+
+def layout_config(args, world):
+    return {"workload": f"PP-DocLayout-L layout detection, batch {args.batch} synthetic {LAYOUT_PAGE}x{LAYOUT_PAGE} pages per "
+                        f"GPU per step, resized to {LAYOUT_IN[0]}x{LAYOUT_IN[1]} (BASELINE.json configs[4]: batch 64 over 8 GPUs "
+                        "= 8 pages per GPU)",
+            "pages_per_step": args.batch * world, "weights": "synthetic He-normal, seed 42, 23 classes",
+            "l2": "flushed between steps (256 MiB memset on the launch stream)", "sharding": f"replicas x{world}"}
+
+
+def layout_pages(rank, batch):
+    from oar_ocr_b200 import synth
+    return [synth.page(5000 + rank * batch + i, LAYOUT_PAGE) for i in range(batch)]
+
+
+def run_layout(args, rank, local_rank, world):
+    """configs[4]: pages -> CatmullRom resize -> RT-DETR-L -> rows (oar_layout_rows).  value: pages resident in HBM;
+    e2e: host pages (pinned staging + H2D inside), rows D2H inside both."""
+    import torch
+    import torch.distributed as dist
+    from oar_ocr_b200 import ffi, models
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = ffi.Context(local_rank)
+    w = models.layout_weights(42)
+    shapes = [(LAYOUT_IN[0] // s, LAYOUT_IN[1] // s) for s in (8, 16, 32)]
+    enc = ffi.Model(ctx, models.build_layout_encoder(w, seed=42, shapes_hw=shapes))
+    head = ffi.Model(ctx, models.build_layout_head(w))
+    if args.engine is not None:
+        enc.set_engine(args.engine)
+        head.set_engine(args.engine)
+    B = args.batch
+    pages = layout_pages(rank, B)
+    pb = LAYOUT_PAGE * LAYOUT_PAGE * 3
+    d_base = ctx.device_alloc(B * pb)
+    for i, p in enumerate(pages):
+        ctx.memcpy_h2d(d_base + i * pb, p)
+    dev_ptrs = (C.c_void_p * B)(*[d_base + i * pb for i in range(B)])
+    hs = np.full(B, LAYOUT_PAGE, np.int32)
+    ws = np.full(B, LAYOUT_PAGE, np.int32)
+    last = {}
+
+    def step_dev():
+        ctx.l2_flush()
+        last["rows"] = ffi.layout_rows(enc, head, None, LAYOUT_IN, device_table=(dev_ptrs, hs, ws))
+
+    def step_host():
+        ctx.l2_flush()
+        last["rows"] = ffi.layout_rows(enc, head, pages, LAYOUT_IN)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
+        n0 = ffi.launch_count()
+        ctx.timer_start()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - w0) * 1000.0
+        launches = ffi.launch_count() - n0
+        barrier()
+        return max_over_ranks(ms), max_over_ranks(wall), launches, (sampler.stop() if sampler else None)
+
+    ms, wall, launches, clocks = timed(step_dev, args.steps, args.warmup, True)
+    value = world * B * args.steps / (ms / 1000.0)
+    e_ms, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
+    e2e_value = world * B * args.steps / (e_ms / 1000.0)
+    roof, kernels = kernel_roofline(ctx, step_dev) if rank == 0 else (None, [])
+    cpu_base = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import torch as _t
+        from oracle import cpu
+        from oracle.rtdetr import RTDetrL
+        _t.set_num_threads(os.cpu_count() or 1)
+        net = RTDetrL(42)
+        sample = min(B, max(1, args.ref_sample // 2))
+        sizes = [(float(LAYOUT_PAGE), float(LAYOUT_PAGE))] * sample
+        x1, _ = cpu.layout_preprocess(pages[:1], LAYOUT_IN)
+        net.rows(x1, sizes[:1])
+        t0 = time.perf_counter()
+        x, _ = cpu.layout_preprocess(pages[:sample], LAYOUT_IN)
+        want = net.rows(x, sizes)
+        dt = time.perf_counter() - t0
+        cpu_base = {"value": sample / dt, "unit": UNIT_LAYOUT, "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"first {sample} of the step's {B} pages ({dt:.1f} s); oracle port: C++ CatmullRom resize + "
+                              "torch-CPU fp32 RT-DETR-L (oracle/rtdetr.py)"}
+        got = last["rows"][:sample]
+        k = 50  # the 50 best rows of every page: same classes, scores and corners close
+        parity = {"pages": sample,
+                  "top_score_max_diff": float(np.abs(got[:, 0, 1] - want[:, 0, 1]).max()),
+                  "top50_score_max_diff": float(np.abs(np.sort(got[:, :k, 1], 1) - np.sort(want[:, :k, 1], 1)).max()),
+                  "against": "oracle/rtdetr.py (CPU port) on the same pages"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC_LAYOUT, "value": value, "unit": UNIT_LAYOUT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": layout_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT_LAYOUT, "h2d_bytes_per_step": B * pb,
+                    "d2h_bytes_per_step": B * 300 * 6 * 4, "ms_per_step": e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "parity_check": parity, "wall_ms_per_step": wall / args.steps,
+            "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()}
+                            for kk in kernels[:8]],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_layout(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    from oracle import cpu
+    from oracle.rtdetr import RTDetrL
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = RTDetrL(42)
+    sample = min(args.batch, max(1, args.ref_sample // 2))
+    pages = layout_pages(0, sample)
+    sizes = [(float(LAYOUT_PAGE), float(LAYOUT_PAGE))] * sample
+    for _ in range(max(args.warmup, 0)):
+        x, _ = cpu.layout_preprocess(pages[:1], LAYOUT_IN)
+        net.rows(x, sizes[:1])
+    total = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        x, _ = cpu.layout_preprocess(pages, LAYOUT_IN)
+        net.rows(x, sizes)
+        total += time.perf_counter() - t0
+    value = sample * args.steps / total
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC_LAYOUT, "value": value, "unit": UNIT_LAYOUT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": layout_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT_LAYOUT, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": f"{sample} of the workload's pages per step; oracle port"},
+        "e2e": {"value": value, "unit": UNIT_LAYOUT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def ocr_dtype(ocr) -> str:
     # arithmetic type of the path: fp32 tensors end to end; dense contractions run as 3 fp16 tcgen05 MMAs per k-step
     # (hi/lo operand split) into fp32 TMEM accumulators, which reproduces fp32 GEMM results to ~1e-6
@@ -521,8 +685,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "rec512"],
-                    help="pipeline = BASELINE.json configs[1] (the headline metric); rec512 = configs[2], recognizer only")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "rec512", "layout"],
+                    help="pipeline = BASELINE.json configs[1] (the headline metric); rec512 = configs[2], recognizer only; "
+                         "layout = configs[4], PP-DocLayout-L")
     ap.add_argument("--batch", type=int, default=None, help="pages (pipeline: 32) or crops (rec512: 512) per GPU per step")
     ap.add_argument("--image-batch-size", type=int, default=32)
     ap.add_argument("--region-batch-size", type=int, default=256)
@@ -536,8 +701,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.batch is None:
-        args.batch = 512 if args.workload == "rec512" else 32
-    if args.workload == "rec512":
+        args.batch = {"rec512": 512, "layout": 8}.get(args.workload, 32)
+    if args.workload == "layout":
+        if args.impl == "reference":
+            run_reference_layout(args, rank, world)
+        else:
+            run_layout(args, rank, local_rank, world)
+    elif args.workload == "rec512":
         if args.impl == "reference":
             run_reference_rec512(args, rank, world)
         else:

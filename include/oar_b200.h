@@ -301,6 +301,16 @@ int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, i
                                const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int32_t n,
                                const oar_pipeline_config* cfg, oar_ocr_result* out);
 
+/* ---- encoded pages -----------------------------------------------------------------------
+ * In the reference a page enters through load_image (oar-ocr-core/src/core/utils/image.rs:88: image::open -> RGB8) on
+ * the CPU.  oar_pipeline_run_encoded takes the JPEG streams themselves: nvJPEG decodes them into HBM (interleaved RGB)
+ * and OAROCR::predict proceeds as oar_pipeline_run does on device-resident pages.  nvJPEG is looked up at first use;
+ * without it the call fails with OAR_E_UNSUPPORTED (there is no CPU decode).  out_hs / out_ws (may be NULL): decoded
+ * page sizes.  oar_decode_jpeg returns one decoded page to the host (rgb == NULL: size only). */
+int32_t oar_pipeline_run_encoded(oar_model* det, oar_model* rec, const uint8_t* const* jpegs, const size_t* lens, int32_t n,
+                                 const oar_pipeline_config* cfg, oar_ocr_result* out, int32_t* out_hs, int32_t* out_ws);
+int32_t oar_decode_jpeg(oar_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* rgb, size_t rgb_cap, int32_t* h, int32_t* w);
+
 /* ---- layout detection on the device (BASELINE.json configs[4]) --------------------------------
  * LayoutDetectionAdapter::execute (oar-ocr-core/src/domain/adapters/layout_detection_adapter.rs:1128-1197) ->
  * ScaleAwareDetectorModel::preprocess / infer (models/detection/scale_aware_detector.rs:150-333) for the PP-DocLayout
@@ -309,9 +319,11 @@ int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, i
  * own tail (sigmoid, top-300 over (query, class), cxcywh -> xyxy scaled to the source image).
  * encoder / head: two OAR_KIND_FEAT models on one context (oar_ocr_b200.models.build_layout_encoder for this input
  * size, build_layout_head).  oar_layout_rows returns the model's output tensor, rows [n][300][6] =
- * [class_id, score, x1, y1, x2, y2] -- what the adapter reads; oar_layout_run feeds it to oar_layout_postprocess. */
+ * [class_id, score, x1, y1, x2, y2] -- what the adapter reads (images_on_device != 0: `images` are device pointers);
+ * oar_layout_run (host pages) feeds it to oar_layout_postprocess. */
 int32_t oar_layout_rows(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
-                        const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, float* rows, size_t rows_cap);
+                        const int32_t* ws, int32_t n, int32_t images_on_device, int32_t input_h, int32_t input_w,
+                        float* rows, size_t rows_cap);
 int32_t oar_layout_run(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
                        const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, const oar_layout_config* cfg,
                        float* boxes, int32_t* classes, float* scores, int32_t* counts);

@@ -21,6 +21,7 @@ SOURCES = {
     "gemm_tc.cu": [],
     "fused_tc.cu": [],
     "fused_simt.cu": [],
+    "jpeg_ingest.cu": [],
     "prepost.cu": ["-fmad=false"],
     "dbpost.cu": ["-fmad=false"],
     "layout_net.cu": ["-fmad=false"],  # the exported-model tail restates f32 box arithmetic step by step
@@ -63,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose and err:
                 print(err, file=sys.stderr)
     if jobs or force or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs)
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -1482,22 +1482,13 @@ int32_t oar_pipeline_run(oar_model* det, oar_model* rec, const uint8_t* const* i
   return oar_pipeline_run_cls(det, rec, nullptr, images, hs, ws, n, images_on_device, cfg, out);
 }
 
-int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
-                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
-                             const oar_pipeline_config* cfg, oar_ocr_result* out) {
-  API_TRY
-  check_pipeline_args(det, rec, cls, images, hs, ws, n, cfg, out);
-  oar_ctx* ctx = det->ctx;
-  CallGuard guard(ctx);
+namespace {
+// everything after the pages are in HBM (S.imgs filled, ev[0] / ev[1] recorded by the caller)
+void pipeline_after_upload(PageStage& S, oar_model* det, oar_model* rec, oar_model* cls, const oar_pipeline_config* cfg,
+                           oar_ocr_result* out) {
+  oar_ctx* ctx = S.ctx;
   cudaStream_t st = ctx->stream;
-  PageStage S;
-  S.ctx = ctx;
-  for (auto& e : S.ev) e = ctx->next_event();
-  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
-  out->h2d_bytes = out->d2h_bytes = 0;
-  cudaEventRecord(S.ev[0], st);
-  stage_upload(S, images, hs, ws, n, images_on_device);
-  cudaEventRecord(S.ev[1], st);
+  const int n = S.n;
   stage_detect(S, det, cfg);
   cudaEventRecord(S.ev[2], st);
   stage_crop(S);
@@ -1538,6 +1529,74 @@ int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, con
   cudaEventElapsedTime(&out->ms_rec, S.ev[3], S.ev[4]);
   cudaEventElapsedTime(&out->ms_cls, S.ev[3], S.ev[5]);
   cudaEventElapsedTime(&out->ms_total, S.ev[0], S.ev[4]);
+}
+}  // namespace
+
+int32_t oar_pipeline_run_cls(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images,
+                             const int32_t* hs, const int32_t* ws, int32_t n, int32_t images_on_device,
+                             const oar_pipeline_config* cfg, oar_ocr_result* out) {
+  API_TRY
+  check_pipeline_args(det, rec, cls, images, hs, ws, n, cfg, out);
+  oar_ctx* ctx = det->ctx;
+  CallGuard guard(ctx);
+  PageStage S;
+  S.ctx = ctx;
+  for (auto& e : S.ev) e = ctx->next_event();
+  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
+  out->h2d_bytes = out->d2h_bytes = 0;
+  cudaEventRecord(S.ev[0], ctx->stream);
+  stage_upload(S, images, hs, ws, n, images_on_device);
+  cudaEventRecord(S.ev[1], ctx->stream);
+  pipeline_after_upload(S, det, rec, cls, cfg, out);
+  API_CATCH
+}
+
+// OAROCR::predict on ENCODED pages: JPEG bytes -> nvJPEG -> HBM -> the same pipeline.  ms_h2d
+// covers upload + decode; out_hs / out_ws (may be NULL) receive the decoded page sizes.
+int32_t oar_pipeline_run_encoded(oar_model* det, oar_model* rec, const uint8_t* const* jpegs, const size_t* lens, int32_t n,
+                                 const oar_pipeline_config* cfg, oar_ocr_result* out, int32_t* out_hs, int32_t* out_ws) {
+  API_TRY
+  if (n <= 0 || !jpegs || !lens) OAR_FAIL(OAR_E_INVALID, "images: expected non-empty slice, got empty slice");
+  std::vector<int32_t> hs(n, 1), ws(n, 1);
+  check_pipeline_args(det, rec, nullptr, jpegs, hs.data(), ws.data(), n, cfg, out);
+  oar_ctx* ctx = det->ctx;
+  CallGuard guard(ctx);
+  PageStage S;
+  S.ctx = ctx;
+  for (auto& e : S.ev) e = ctx->next_event();
+  out->ms_h2d = out->ms_det = out->ms_post = out->ms_crop = out->ms_rec = out->ms_total = out->ms_cls = 0.0f;
+  out->h2d_bytes = out->d2h_bytes = 0;
+  cudaEventRecord(S.ev[0], ctx->stream);
+  std::vector<const uint8_t*> ptrs(n);
+  decode_jpegs_to_device(ctx, jpegs, lens, n, ptrs.data(), hs.data(), ws.data());
+  S.n = n;
+  S.imgs.resize(n);
+  for (int i = 0; i < n; ++i) {
+    S.imgs[i] = DevImage{ptrs[i], hs[i], ws[i]};
+    S.h2d_bytes += (int64_t)lens[i];
+    if (out_hs) out_hs[i] = hs[i];
+    if (out_ws) out_ws[i] = ws[i];
+  }
+  cudaEventRecord(S.ev[1], ctx->stream);
+  pipeline_after_upload(S, det, rec, nullptr, cfg, out);
+  API_CATCH
+}
+
+// load_image (oar-ocr-core/src/core/utils/image.rs:88) for a JPEG stream, decoded on the device: RGB8 pixels back to the
+// host (parity checks of the ingest path; the pipeline itself never brings them back).  rgb == NULL: only the size.
+int32_t oar_decode_jpeg(oar_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* rgb, size_t rgb_cap, int32_t* h, int32_t* w) {
+  API_TRY
+  require_device(ctx);
+  if (!jpeg || !h || !w) OAR_FAIL(OAR_E_INVALID, "null argument");
+  CallGuard guard(ctx);
+  const uint8_t* p = nullptr;
+  decode_jpegs_to_device(ctx, &jpeg, &len, 1, &p, h, w);
+  if (rgb) {
+    const size_t bytes = (size_t)*h * *w * 3;
+    if (bytes > rgb_cap) OAR_FAIL(OAR_E_CAPACITY, "decoded page needs %zu bytes, capacity %zu", bytes, rgb_cap);
+    OAR_CUDA(cudaMemcpyAsync(rgb, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  OAR_CUDA(cudaStreamSynchronize(ctx->stream));
   API_CATCH
 }
 
@@ -1737,7 +1796,8 @@ int32_t oar_pipeline_run_multi(oar_model* const* dets, oar_model* const* recs, i
 
 // ---- layout detection: LayoutDetectionAdapter::execute on the device ---------------------
 int32_t oar_layout_rows(oar_model* encoder, oar_model* head, const uint8_t* const* images, const int32_t* hs,
-                        const int32_t* ws, int32_t n, int32_t input_h, int32_t input_w, float* rows, size_t rows_cap) {
+                        const int32_t* ws, int32_t n, int32_t images_on_device, int32_t input_h, int32_t input_w,
+                        float* rows, size_t rows_cap) {
   API_TRY
   if (!encoder || !head || encoder->kind != OAR_KIND_FEAT || head->kind != OAR_KIND_FEAT)
     OAR_FAIL(OAR_E_INVALID, "layout detection needs an encoder model and a head model (feature-extractor kind)");
@@ -1747,7 +1807,7 @@ int32_t oar_layout_rows(oar_model* encoder, oar_model* head, const uint8_t* cons
   if ((size_t)n * 300 * 6 > rows_cap) OAR_FAIL(OAR_E_CAPACITY, "rows need %zu floats, capacity %zu", (size_t)n * 1800, rows_cap);
   oar_ctx* ctx = encoder->ctx;
   CallGuard guard(ctx);
-  const float* d_rows = layout_rows_device(encoder, head, images, hs, ws, n, input_h, input_w);
+  const float* d_rows = layout_rows_device(encoder, head, images, hs, ws, n, images_on_device, input_h, input_w);
   OAR_CUDA(cudaMemcpyAsync(rows, d_rows, (size_t)n * 1800 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   OAR_CUDA(cudaStreamSynchronize(ctx->stream));
   API_CATCH
@@ -1765,7 +1825,7 @@ int32_t oar_layout_run(oar_model* encoder, oar_model* head, const uint8_t* const
     return OAR_E_INVALID;
   }
   std::vector<float> rows((size_t)n * 1800);
-  int32_t rc = oar_layout_rows(encoder, head, images, hs, ws, n, input_h, input_w, rows.data(), rows.size());
+  int32_t rc = oar_layout_rows(encoder, head, images, hs, ws, n, 0, input_h, input_w, rows.data(), rows.size());
   if (rc != OAR_OK) return rc;
   std::vector<float> sw(n), sh(n);
   for (int i = 0; i < n; ++i) sw[i] = (float)ws[i], sh[i] = (float)hs[i];

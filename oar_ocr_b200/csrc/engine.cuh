@@ -130,10 +130,15 @@ void op_linear(oar_model* m, int oi, const float* in, int rows, float* out, int 
 void op_layernorm(oar_model* m, int oi, const float* in, int rows, float* out);
 void op_attention(oar_model* m, int oi, const float* x, const float* x_qk, int B, int T, float* out);
 
-// layout_net.cu: ScaleAwareDetectorModel::preprocess (pp_doclayout) + RT-DETR-L on the device.  Host pages in, the
+// layout_net.cu: ScaleAwareDetectorModel::preprocess (pp_doclayout) + RT-DETR-L on the device.  Pages in (host, or device pointers), the
 // exported model's rows [n, 300, 6] = [class_id, score, x1, y1, x2, y2] (source pixels) out, in the context's arena.
 float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const* images, const int32_t* hs, const int32_t* ws,
-                          int n, int in_h, int in_w);
+                          int n, int on_device, int in_h, int in_w);
+
+// jpeg_ingest.cu: JPEG streams -> u8 HWC RGB pages in the context's arena (nvJPEG, looked up at first use)
+void decode_jpegs_to_device(oar_ctx* ctx, const uint8_t* const* data, const size_t* lens, int n, const uint8_t** ptrs,
+                            int32_t* hs, int32_t* ws);
+bool jpeg_ingest_available();
 
 // fused_simt.cu: false = shape not covered, the caller runs the per-layer path
 bool launch_stem_u8(oar_ctx* ctx, const U8Input& S, const OpRec& op, const float* w, const float* bias, float* out, int Ho,

@@ -340,7 +340,7 @@ float* layout_decode(oar_model* head, const float* source, int B, const int* sha
 
 // ScaleAwareDetectorModel::preprocess (pp_doclayout) + the network: u8 pages -> rows [n, 300, 6] on the device
 float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const* images, const int32_t* hs, const int32_t* ws,
-                          int n, int in_h, int in_w) {
+                          int n, int on_device, int in_h, int in_w) {
   oar_ctx* ctx = enc->ctx;
   cudaStream_t st = ctx->stream;
   if (in_h <= 0 || in_w <= 0 || (in_h % 32) || (in_w % 32)) OAR_FAIL(OAR_E_INVALID, "layout input must be a multiple of 32");
@@ -354,14 +354,17 @@ float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const*
     if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
     total += ((size_t)hs[i] * ws[i] * 3 + 15) & ~(size_t)15;
   }
-  uint8_t* h_pages = (uint8_t*)ctx->pinned_get(total);
-  uint8_t* d_pages = ctx->arena.get<uint8_t>(total);
+  uint8_t* h_pages = on_device ? nullptr : (uint8_t*)ctx->pinned_get(total);
+  uint8_t* d_pages = on_device ? nullptr : ctx->arena.get<uint8_t>(total);
   size_t off = 0;
   for (int i = 0; i < n; ++i) {
     const size_t bytes = (size_t)hs[i] * ws[i] * 3;
-    memcpy(h_pages + off, images[i], bytes);
-    const uint8_t* d = d_pages + off;
-    off += (bytes + 15) & ~(size_t)15;
+    const uint8_t* d = images[i];
+    if (!on_device) {
+      memcpy(h_pages + off, images[i], bytes);
+      d = d_pages + off;
+      off += (bytes + 15) & ~(size_t)15;
+    }
     src_wh[2 * i] = (float)ws[i], src_wh[2 * i + 1] = (float)hs[i];
     if (hs[i] == in_h && ws[i] == in_w) {
       ptrs[i] = d;
@@ -375,7 +378,7 @@ float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const*
     max_sw = std::max(max_sw, j.sw);
     ptrs[i] = j.dst;
   }
-  OAR_CUDA(cudaMemcpyAsync(d_pages, h_pages, total, cudaMemcpyHostToDevice, st));
+  if (!on_device) OAR_CUDA(cudaMemcpyAsync(d_pages, h_pages, total, cudaMemcpyHostToDevice, st));
   if (!jobs.empty()) {
     ResizeJob* d_jobs = upload(ctx, jobs);
     launch_resize_triangle(ctx, d_jobs, (int)jobs.size(), max_sw, in_w, in_h);

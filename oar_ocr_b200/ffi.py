@@ -27,7 +27,7 @@ SYMBOLS = [
     "oar_layout_postprocess", "oar_device_alloc", "oar_device_free", "oar_memcpy_h2d", "oar_profile_enable",
     "oar_profile_read", "oar_timer_start", "oar_timer_stop", "oar_l2_flush", "oar_model_validate_blob",
     "oar_model_load_onnx", "oar_onnx_to_oarg", "oar_crop_rec_run", "oar_rec_run_ex", "oar_pipeline_run_multi",
-    "oar_layout_rows", "oar_layout_run",
+    "oar_layout_rows", "oar_layout_run", "oar_pipeline_run_encoded", "oar_decode_jpeg",
 ]
 
 
@@ -141,9 +141,13 @@ def lib():
                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6 + \
             [C.c_int32]
         L.oar_layout_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_void_p, C.c_size_t]
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
         L.oar_layout_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.POINTER(LayoutConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oar_pipeline_run_encoded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.POINTER(PipelineConfig), C.POINTER(OcrResult), C.c_void_p, C.c_void_p]
+        L.oar_decode_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]
         L.oar_pipeline_run_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.POINTER(PipelineConfig), C.POINTER(OcrResult)]
         L.oar_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
@@ -617,14 +621,43 @@ class PipelineBuffers:
         self.res.line_angle = self.line_angle.ctypes.data_as(P(C.c_float))
 
 
-def layout_rows(encoder: "Model", head: "Model", images, input_hw=(640, 640)) -> np.ndarray:
-    """oar_layout_rows: pages -> the layout detector's output tensor [n, 300, 6] = [class_id, score, x1, y1, x2, y2]"""
-    arrs, ptrs, hs, ws = _image_table(images)
-    n = len(arrs)
+def layout_rows(encoder: "Model", head: "Model", images, input_hw=(640, 640), device_table=None) -> np.ndarray:
+    """oar_layout_rows: pages -> the layout detector's output tensor [n, 300, 6] = [class_id, score, x1, y1, x2, y2].
+    device_table = (ptrs, hs, ws): pages already resident in HBM instead of `images`."""
+    if device_table is not None:
+        ptrs, hs, ws = device_table
+        on_device = 1
+    else:
+        arrs, ptrs, hs, ws = _image_table(images)
+        on_device = 0
+    n = len(hs)
     rows = np.zeros((n, 300, 6), np.float32)
-    check(lib().oar_layout_rows(encoder.handle, head.handle, ptrs, _ptr(hs), _ptr(ws), n, int(input_hw[0]),
+    check(lib().oar_layout_rows(encoder.handle, head.handle, ptrs, _ptr(hs), _ptr(ws), n, on_device, int(input_hw[0]),
                                 int(input_hw[1]), _ptr(rows), rows.size))
     return rows
+
+
+def pipeline_run_encoded(det: "Model", rec: "Model", jpegs: list, cfg: PipelineConfig, bufs: "PipelineBuffers"):
+    """oar_pipeline_run_encoded: JPEG byte strings in, decoded by nvJPEG into HBM; returns (result, [(h, w), ...])"""
+    n = len(jpegs)
+    keep = [(C.c_char * len(j)).from_buffer_copy(j) for j in jpegs]
+    ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+    lens = (C.c_size_t * n)(*[len(j) for j in jpegs])
+    hs = np.zeros(n, np.int32)
+    ws = np.zeros(n, np.int32)
+    check(lib().oar_pipeline_run_encoded(det.handle, rec.handle, ptrs, lens, n, C.byref(cfg), C.byref(bufs.res), _ptr(hs),
+                                         _ptr(ws)))
+    return bufs.res, list(zip(hs.tolist(), ws.tolist()))
+
+
+def decode_jpeg(ctx: "Context", jpeg: bytes) -> np.ndarray:
+    """oar_decode_jpeg: one JPEG stream decoded on the device (nvJPEG), returned as u8 [h, w, 3] RGB"""
+    buf = (C.c_char * len(jpeg)).from_buffer_copy(jpeg)
+    h, w = C.c_int32(), C.c_int32()
+    check(lib().oar_decode_jpeg(ctx.handle, buf, len(jpeg), None, 0, C.byref(h), C.byref(w)))
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    check(lib().oar_decode_jpeg(ctx.handle, buf, len(jpeg), _ptr(out), out.size, C.byref(h), C.byref(w)))
+    return out
 
 
 def pipeline_run_multi(dets, recs, image_ptrs, hs: np.ndarray, ws: np.ndarray, cfg: PipelineConfig,
