@@ -40,6 +40,7 @@ def _compare(got, want, tol=TOL, max_tie_frac=0.0):
             if not np.array_equal(r.label_indices, o["labels"]):
                 assert max_tie_frac > 0 and o["margin"] < tol, (r.label_indices, o["labels"], o["margin"])
                 ties += 1
+                n += 1
                 continue  # the confidence averages over the emitted characters, which differ in a tie
             assert abs(r.confidence - o["score"]) <= tol
             n += 1
