@@ -101,7 +101,10 @@ cudaEvent_t oar_ctx::next_event() {
 void oar_ctx::begin_call() {
   OAR_CUDA(cudaSetDevice(device));
   OAR_CUDA(cudaStreamSynchronize(stream));
+  if (stream_aux) OAR_CUDA(cudaStreamSynchronize(stream_aux));
+  if (stream_copy) OAR_CUDA(cudaStreamSynchronize(stream_copy));
   arena.reset();
+  arena_aux.reset();
   // debugging aid: OAR_DBG_POISON=1 fills the arena with 0xFF (NaN as f32) before every call, so a kernel that reads
   // activations it (or its producer) never wrote shows up as NaN instead of silently reusing the previous call's data
   static const bool poison = getenv("OAR_DBG_POISON") != nullptr;
@@ -203,11 +206,12 @@ struct DetGroup {
   cudaEvent_t e_start = nullptr, e_net = nullptr, e_post = nullptr;
 };
 
-// Launches normalize -> DB net -> DB post for one same-shape group; results land in pinned host
-// memory once the stream is synchronised.
+// Launches DB net -> DB post for one same-shape group; results land in pinned host memory once the streams are
+// synchronised.  With `post_lane` the post-process (threshold, labelling, border tracing, box geometry: latency-bound,
+// a fraction of the SMs) runs on the context's second lane behind an event, so it overlaps the NEXT group's network.
 void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, const std::vector<int32_t>& src_h,
                       const std::vector<int32_t>& src_w, const oar_det_config& cfg, DetGroup& g, int comps_hint,
-                      bool timed) {
+                      bool timed, bool post_lane) {
   oar_ctx* ctx = det->ctx;
   const int B = (int)g.members.size();
   std::vector<const uint8_t*> ptrs(B);
@@ -225,12 +229,14 @@ void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, cons
     g.e_post = ctx->next_event();
     cudaEventRecord(g.e_start, ctx->stream);
   }
-  // persistent outputs first, then per-group scratch that the next group may reuse (stream order)
+  // persistent outputs first (the probability map too: the post lane reads it after this lane has moved on), then
+  // per-group scratch that the next group may reuse (stream order)
   const int mc = cfg.max_candidates;
   DbPostOut out;
   out.boxes = ctx->arena.get<float>((size_t)B * mc * 8);
   out.scores = ctx->arena.get<float>((size_t)B * mc);
   out.counts = ctx->arena.get<int32_t>(B);
+  float* prob_keep = post_lane ? ctx->arena.get<float>((size_t)B * g.H * g.W) : nullptr;
   auto mark = ctx->arena.mark();
   const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data(), B);
   // the network reads the u8 pages itself: NormalizeImage is folded into the stem convolution (engine.cu / fused_simt.cu)
@@ -243,18 +249,49 @@ void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, cons
   if (prob.B != B || prob.H != g.H || prob.W != g.W || prob.C != 1)
     OAR_FAIL(OAR_E_MODEL, "detector output %dx%dx%dx%d does not match its %dx%d input", prob.B, prob.H, prob.W, prob.C,
              g.H, g.W);
+  const float* prob_p = prob.p;
+  if (post_lane) {
+    OAR_CUDA(cudaMemcpyAsync(prob_keep, prob.p, (size_t)B * g.H * g.W * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    prob_p = prob_keep;
+  }
   if (timed) cudaEventRecord(g.e_net, ctx->stream);
-  g.status = db_postprocess_device(ctx, prob.p, B, g.H, g.W, sh.data(), sw.data(), cfg, out, comps_hint);
-  g.h_boxes = (float*)ctx->pinned_get((size_t)B * mc * 8 * sizeof(float));
-  g.h_scores = (float*)ctx->pinned_get((size_t)B * mc * sizeof(float));
-  g.h_counts = (int32_t*)ctx->pinned_get((size_t)B * sizeof(int32_t));
-  OAR_CUDA(cudaMemcpyAsync(g.h_counts, out.counts, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  OAR_CUDA(cudaMemcpyAsync(g.h_boxes, out.boxes, (size_t)B * mc * 8 * sizeof(float), cudaMemcpyDeviceToHost,
-                           ctx->stream));
-  OAR_CUDA(cudaMemcpyAsync(g.h_scores, out.scores, (size_t)B * mc * sizeof(float), cudaMemcpyDeviceToHost,
-                           ctx->stream));
-  if (timed) cudaEventRecord(g.e_post, ctx->stream);
-  ctx->arena.release_to(mark);
+  // post lane: the activations can go now (the kept copy of the map lives outside the mark); otherwise the post-process
+  // below still reads the map inside them, and they are released after it has been enqueued
+  if (post_lane) ctx->arena.release_to(mark);
+  cudaStream_t main_stream = ctx->stream;
+  if (post_lane) {
+    cudaEvent_t ready = ctx->next_event();
+    OAR_CUDA(cudaEventRecord(ready, main_stream));
+    OAR_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ready, 0));
+    std::swap(ctx->stream, ctx->stream_aux);
+    std::swap(ctx->arena, ctx->arena_aux);
+  }
+  try {
+    auto pmark = post_lane ? ctx->arena.mark() : mark;
+    g.status = db_postprocess_device(ctx, prob_p, B, g.H, g.W, sh.data(), sw.data(), cfg, out, comps_hint);
+    g.h_boxes = (float*)ctx->pinned_get((size_t)B * mc * 8 * sizeof(float));
+    g.h_scores = (float*)ctx->pinned_get((size_t)B * mc * sizeof(float));
+    g.h_counts = (int32_t*)ctx->pinned_get((size_t)B * sizeof(int32_t));
+    OAR_CUDA(cudaMemcpyAsync(g.h_counts, out.counts, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    OAR_CUDA(cudaMemcpyAsync(g.h_boxes, out.boxes, (size_t)B * mc * 8 * sizeof(float), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    OAR_CUDA(cudaMemcpyAsync(g.h_scores, out.scores, (size_t)B * mc * sizeof(float), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    if (timed) cudaEventRecord(g.e_post, ctx->stream);
+    if (post_lane) ctx->arena.release_to(pmark);
+  } catch (...) {
+    if (post_lane) {
+      std::swap(ctx->stream, ctx->stream_aux);
+      std::swap(ctx->arena, ctx->arena_aux);
+    }
+    throw;
+  }
+  if (post_lane) {
+    std::swap(ctx->stream, ctx->stream_aux);
+    std::swap(ctx->arena, ctx->arena_aux);
+  } else {
+    ctx->arena.release_to(mark);
+  }
 }
 
 // DetResizeForTest::apply on device: returns the images the detector sees (resized in HBM when needed)
@@ -305,26 +342,48 @@ struct DetResult {
 };
 
 // TextDetectionAdapter::execute for one list of device images, chunked by image_batch_size.
+// `ready` (optional): per image, the event after which its pixels are in HBM (uploads run on the copy stream).
 void run_detection(oar_model* det, const std::vector<DevImage>& imgs, const oar_det_config& cfg, int batch_size,
-                   DetResult& res, bool timed) {
+                   DetResult& res, bool timed, const std::vector<cudaEvent_t>* ready = nullptr) {
   oar_ctx* ctx = det->ctx;
   const int n = (int)imgs.size();
   if (cfg.max_candidates <= 0) OAR_FAIL(OAR_E_INVALID, "max_candidates must be positive");
   res.boxes.assign(n, {});
   res.scores.assign(n, {});
+  auto wait_for = [&](int i) {
+    if (ready && (*ready)[i]) OAR_CUDA(cudaStreamWaitEvent(ctx->stream, (*ready)[i], 0));
+  };
   std::vector<DevImage> resized;
+  if (ready) {  // only the images that get resized need their pixels now
+    oar_det_config c = cfg;
+    for (int i = 0; i < n; ++i) {
+      uint32_t rh, rw;
+      det_resize_dims((uint32_t)std::max(imgs[i].h, 1), (uint32_t)std::max(imgs[i].w, 1), c, &rh, &rw);
+      if ((int)rh != imgs[i].h || (int)rw != imgs[i].w || imgs[i].h + imgs[i].w < 64) wait_for(i);
+    }
+  }
   det_resize_on_device(ctx, imgs, cfg, resized);
   std::vector<int32_t> src_h(n), src_w(n);
   for (int i = 0; i < n; ++i) src_h[i] = imgs[i].h, src_w[i] = imgs[i].w;
   std::vector<DetGroup> groups;
   batch_size = std::max(batch_size, 1);
+  // An image's boxes do not depend on its batch mates, so a same-shape group of the reference (db.rs:299-309) is cut
+  // into sub-groups of at most DET_SUB pages: the post-process of one sub-group (second lane) and the upload of the
+  // later pages (copy stream) overlap the network of the next.
+  // Measured on B200 (32 pages 960x960): sub-groups of 8 made the step SLOWER (30.2 vs 29.1 ms) -- the post-process
+  // kernels on the second lane take SM slots from the persistent one-CTA-per-SM network kernels, whose grids then run
+  // with stragglers -- so the split stays opt-in (OAR_DET_SUB=8).
+  static const int det_sub = getenv("OAR_DET_SUB") ? atoi(getenv("OAR_DET_SUB")) : 0;
+  const bool lanes = det_sub > 0 && !ctx->profile && ctx->stream_aux;
   for (int start = 0; start < n; start += batch_size) {
     int end = std::min(n, start + batch_size);
     size_t first_group = groups.size();
     for (int i = start; i < end; ++i) {  // first-seen shape order, db.rs:299-309
       DetGroup* hit = nullptr;
       for (size_t gi = first_group; gi < groups.size(); ++gi)
-        if (groups[gi].H == resized[i].h && groups[gi].W == resized[i].w) hit = &groups[gi];
+        if (groups[gi].H == resized[i].h && groups[gi].W == resized[i].w &&
+            (!lanes || (int)groups[gi].members.size() < det_sub))
+          hit = &groups[gi];
       if (!hit) {
         groups.emplace_back();
         hit = &groups.back();
@@ -333,14 +392,23 @@ void run_detection(oar_model* det, const std::vector<DevImage>& imgs, const oar_
       hit->members.push_back(i);
     }
   }
-  for (auto& g : groups) launch_det_group(det, resized, src_h, src_w, cfg, g, 0, timed);
+  const bool post_lane = lanes && groups.size() >= 2;
+  for (auto& g : groups) {
+    for (int i : g.members) wait_for(i);
+    launch_det_group(det, resized, src_h, src_w, cfg, g, 0, timed, post_lane);
+  }
+  if (post_lane) {
+    cudaEvent_t join = ctx->next_event();
+    OAR_CUDA(cudaEventRecord(join, ctx->stream_aux));
+    OAR_CUDA(cudaStreamWaitEvent(ctx->stream, join, 0));
+  }
   OAR_CUDA(cudaStreamSynchronize(ctx->stream));
   for (auto& g : groups) {
     int need = 0;
     int tries = 0;
     while (db_postprocess_check(g.status, &need) == 1) {
       if (++tries > 3) OAR_FAIL(OAR_E_CAPACITY, "DB post-process component bound did not converge");
-      launch_det_group(det, resized, src_h, src_w, cfg, g, need, false);
+      launch_det_group(det, resized, src_h, src_w, cfg, g, need, false, false);
       OAR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     const int mc = cfg.max_candidates;
@@ -695,6 +763,8 @@ int32_t oar_ctx_create(int32_t device_id, oar_ctx** out) {
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
   OAR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OAR_CUDA(cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking));
+  OAR_CUDA(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
   *out = c;
   API_CATCH
 }
@@ -703,13 +773,17 @@ void oar_ctx_destroy(oar_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
   ctx->arena.release();
+  ctx->arena_aux.release();
   for (auto& s : ctx->pinned) cudaFreeHost(s.base);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->timer0) cudaEventDestroy(ctx->timer0);
   if (ctx->timer1) cudaEventDestroy(ctx->timer1);
   cudaFree(ctx->flush_buf);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+  if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   delete ctx;
 }
 
@@ -1206,6 +1280,7 @@ struct PageStage {
   oar_ctx* ctx = nullptr;
   int n = 0;  // images of this stage
   std::vector<DevImage> imgs;
+  std::vector<cudaEvent_t> ready;                // per image: its upload has landed (null: already resident)
   std::vector<std::vector<float>> sorted_boxes;  // per image: count * 8 floats, reading order
   std::vector<int> box_first;                    // [n + 1] prefix sums of the box counts
   int n_boxes = 0;
@@ -1218,13 +1293,17 @@ struct PageStage {
   cudaEvent_t ev[6] = {};
 };
 
-// pages into HBM.  Host pages go through a copy stream in slices of `slice` pages, with one event per slice, so that
-// detection of slice k overlaps the upload of slice k + 1 (the caller makes the launch stream wait per slice).
+// pages into HBM.  Host pages go through the context's copy stream, one event per page: the launch stream waits for
+// exactly the pages a detection sub-group needs, so the upload of the later pages overlaps the network of the earlier.
 void stage_upload(PageStage& S, const uint8_t* const* images, const int32_t* hs, const int32_t* ws, int n,
                   int on_device) {
   oar_ctx* ctx = S.ctx;
   S.n = n;
   S.imgs.resize(n);
+  S.ready.assign(n, nullptr);
+  static const bool no_copy_stream = getenv("OAR_DBG_ONE_STREAM") != nullptr;
+  const bool async = !on_device && !no_copy_stream && ctx->stream_copy && n > 1;
+  cudaStream_t cs = async ? ctx->stream_copy : ctx->stream;
   for (int i = 0; i < n; ++i) {
     if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
     if (on_device) {
@@ -1232,7 +1311,11 @@ void stage_upload(PageStage& S, const uint8_t* const* images, const int32_t* hs,
     } else {
       size_t bytes = (size_t)hs[i] * ws[i] * 3;
       uint8_t* d = ctx->arena.get<uint8_t>(bytes);
-      OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+      OAR_CUDA(cudaMemcpyAsync(d, images[i], bytes, cudaMemcpyHostToDevice, cs));
+      if (async) {
+        S.ready[i] = ctx->next_event();
+        OAR_CUDA(cudaEventRecord(S.ready[i], cs));
+      }
       S.imgs[i] = DevImage{d, hs[i], ws[i]};
       S.h2d_bytes += (int64_t)bytes;
     }
@@ -1242,7 +1325,7 @@ void stage_upload(PageStage& S, const uint8_t* const* images, const int32_t* hs,
 // detection (chunks of image_batch_size) + sort_quad_boxes per image
 void stage_detect(PageStage& S, oar_model* det, const oar_pipeline_config* cfg) {
   DetResult dres;
-  run_detection(det, S.imgs, cfg->det, cfg->image_batch_size, dres, true);
+  run_detection(det, S.imgs, cfg->det, cfg->image_batch_size, dres, true, S.ready.empty() ? nullptr : &S.ready);
   S.ms_det = dres.ms_net, S.ms_post = dres.ms_post;
   const int n = S.n;
   S.sorted_boxes.assign(n, {});
@@ -1285,6 +1368,8 @@ void stage_set_boxes(PageStage& S, const float* boxes, const int32_t* img_index,
 void stage_crop(PageStage& S) {
   oar_ctx* ctx = S.ctx;
   cudaStream_t st = ctx->stream;
+  for (cudaEvent_t e : S.ready)  // every page must have landed (a no-op after detection, which waited group by group)
+    if (e) OAR_CUDA(cudaStreamWaitEvent(st, e, 0));
   const int n = S.n, n_boxes = S.n_boxes;
   S.pool = nullptr;
   S.h_plans = nullptr;
@@ -1459,6 +1544,54 @@ void scatter_stage(const PageStage& S, int img0, const std::vector<int>& ref_of_
   }
 }
 
+// Recognition batches of one context.  The batches are independent, so they alternate between the context's two launch
+// lanes (stream + arena each): the latency-bound tail of one batch (SVTR neck: ~30 small launches, CTC combine, decode)
+// overlaps the bandwidth-bound backbone of the next.  A lane's arena is released batch by batch in its own stream order;
+// the crop pool and the job tables the batches read were written on the main lane before the fork event.
+void recognize_chunks(oar_model* rec, const std::vector<CropRef>& refs, RecPlan& plan, int n_chars, int only_stage = -1) {
+  oar_ctx* ctx = rec->ctx;
+  static const bool one_lane = getenv("OAR_DBG_ONE_STREAM") != nullptr;  // A/B switch
+  int mine = 0;
+  for (const RecChunk& ch : plan.chunks) mine += (only_stage < 0 || ch.stage == only_stage) ? 1 : 0;
+  const bool two = !one_lane && !ctx->profile && mine >= 2 && ctx->stream_aux;
+  cudaStream_t main_stream = ctx->stream;
+  bool on_aux = false;
+  auto lane = [&](bool aux) {
+    if (aux == on_aux) return;
+    std::swap(ctx->stream, ctx->stream_aux);
+    std::swap(ctx->arena, ctx->arena_aux);
+    on_aux = aux;
+  };
+  if (two) {
+    cudaEvent_t fork = ctx->next_event();
+    OAR_CUDA(cudaEventRecord(fork, main_stream));
+    OAR_CUDA(cudaStreamWaitEvent(ctx->stream_aux, fork, 0));
+  }
+  std::vector<RecCrop> rc;
+  int i = 0;
+  try {
+    for (RecChunk& ch : plan.chunks) {
+      if (only_stage >= 0 && ch.stage != only_stage) continue;
+      lane(two && (i++ & 1));
+      rc.resize(ch.n);
+      for (int k = 0; k < ch.n; ++k) {
+        const CropRef& c = refs[plan.order[ch.first + k]];
+        rc[k] = RecCrop{c.p, c.h, c.w};
+      }
+      launch_rec_batch(rec, rc.data(), ch.n, n_chars, ch.out);
+    }
+  } catch (...) {
+    lane(false);
+    throw;
+  }
+  lane(false);
+  if (two) {
+    cudaEvent_t join = ctx->next_event();
+    OAR_CUDA(cudaEventRecord(join, ctx->stream_aux));
+    OAR_CUDA(cudaStreamWaitEvent(main_stream, join, 0));
+  }
+}
+
 void check_pipeline_args(oar_model* det, oar_model* rec, oar_model* cls, const uint8_t* const* images, const int32_t* hs,
                          const int32_t* ws, int32_t n, const oar_pipeline_config* cfg, oar_ocr_result* out) {
   if (!det || det->kind != OAR_KIND_DET || !rec || rec->kind != OAR_KIND_REC)
@@ -1502,15 +1635,7 @@ void pipeline_after_upload(PageStage& S, oar_model* det, oar_model* rec, oar_mod
   if (S.n_boxes > 0) append_refs(S, 0, refs, &ref_of_box);
   RecPlan plan;
   plan_recognition(refs, cfg->region_batch_size, plan);
-  std::vector<RecCrop> rc;
-  for (RecChunk& ch : plan.chunks) {
-    rc.resize(ch.n);
-    for (int k = 0; k < ch.n; ++k) {
-      const CropRef& c = refs[plan.order[ch.first + k]];
-      rc[k] = RecCrop{c.p, c.h, c.w};
-    }
-    launch_rec_batch(rec, rc.data(), ch.n, cfg->n_chars, ch.out);
-  }
+  recognize_chunks(rec, refs, plan, cfg->n_chars);
   cudaEventRecord(S.ev[4], st);
   OAR_CUDA(cudaStreamSynchronize(st));
 
@@ -1628,15 +1753,7 @@ int32_t oar_crop_rec_run(oar_model* rec, const uint8_t* const* images, const int
   append_refs(S, 0, refs, &ref_of_box);
   RecPlan plan;
   plan_recognition(refs, region_batch_size, plan);
-  std::vector<RecCrop> rc;
-  for (RecChunk& ch : plan.chunks) {
-    rc.resize(ch.n);
-    for (int k = 0; k < ch.n; ++k) {
-      const CropRef& c = refs[plan.order[ch.first + k]];
-      rc[k] = RecCrop{c.p, c.h, c.w};
-    }
-    launch_rec_batch(rec, rc.data(), ch.n, n_chars, ch.out);
-  }
+  recognize_chunks(rec, refs, plan, n_chars);
   OAR_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<RecResult> res;
   collect_results(refs, plan, rec_score_thresh, res, nullptr);

@@ -112,6 +112,11 @@ struct oar_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   oar::Arena arena;
+  // second launch stream with its own arena (capi.cu: two-stream recognition).  Every launch helper reads ctx->stream /
+  // ctx->arena, so "the other lane" is entered by swapping both pairs; outside that bracket they are never visible.
+  cudaStream_t stream_aux = nullptr;
+  oar::Arena arena_aux;
+  cudaStream_t stream_copy = nullptr;  // page uploads of a pipeline call: overlap the detector (capi.cu: stage_upload)
   std::mutex mu;
   bool profile = false;
   std::vector<oar::ProfRec> prof;
