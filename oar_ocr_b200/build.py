@@ -20,6 +20,7 @@ SOURCES = {
     "engine.cu": [],
     "gemm_tc.cu": [],
     "fused_tc.cu": [],
+    "conv_halo_tc.cu": [],
     "fused_simt.cu": [],
     "jpeg_ingest.cu": [],
     "prepost.cu": ["-fmad=false"],

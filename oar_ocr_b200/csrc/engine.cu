@@ -1151,6 +1151,8 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.out_ld = ctot, p.out_c_off = coff, p.act = op.p[8], p.post_scale = op.f[0], p.post_bias = op.f[1];
         p.mode = 0, p.cout = cout;
         if (m->engine >= 1 && try_stem_conv(ctx, p)) break;
+        // engine 2: dense stride-1 k x k convolutions on the persistent TMA-halo kernel (conv_halo_tc.cu)
+        if (m->engine == 2 && kh * kw > 1 && tc_conv_halo(m, (int)oi * 2, p, "convkxk_tc")) break;
         launch_gemm(m, (int)oi * 2, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt",
                     (kh == 1 && kw == 1) ? "conv1x1_tc" : "convkxk_tc");
         break;

@@ -42,6 +42,34 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// One lane of a converged warp (the same one every time for a full mask).  tcgen05.mma / commit and the TMA copies take
+// their operands in UNIFORM registers: when the issuing code sits under `if (lane == 0)` the compiler cannot prove the
+// operands warp-uniform and wraps every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- measured
+// ~150 cycles per MMA.  Running the loop on the whole warp (uniform values stay in uniform registers) and electing
+// only around the instruction itself removes that.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity);
+// mbarrier waits of a converged warp: ONE lane polls (32 lanes spinning on the same shared-memory word serialise in the
+// atomic unit and starve the other warps' shared-memory traffic: measured 6x slower), the others park at the warp barrier
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if (elect_one_sync()) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  if (elect_one_sync()) ok = mbar_test(bar, parity) ? 1u : 0u;
+  return __any_sync(0xffffffffu, ok != 0);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, one elected thread issues
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
