@@ -687,6 +687,45 @@ __global__ void layernorm_kernel(const float* __restrict__ in, const float* __re
   for (int c = lane; c < C; c += 32) out[row * C + c] = (x[c] - mean) * rstd * g[c] + be[c];
 }
 
+// channels in registers: C <= 128, C % 4 == 0 -- lane l holds channels 4l..4l+3, the row is read once (one float4 per
+// lane), both reductions are warp butterflies over register values.  (The strided three-pass kernel above spent its
+// time on three dependent trips to L1 per row: 10 us for 10240 rows x 120 channels, latency not bandwidth.)
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ in, const float* __restrict__ g,
+                                                            const float* __restrict__ be, float* __restrict__ out, size_t rows,
+                                                            int C, float eps) {
+  const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool on = 4 * lane < C;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f), gg = x, bb = x;
+  if (on) {
+    x = __ldg(reinterpret_cast<const float4*>(in + row * C) + lane);
+    const float* gp = g + 4 * lane;  // weight slices carry no 16-byte guarantee
+    const float* bp = be + 4 * lane;
+    gg = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3));
+    bb = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+  }
+  float s = (x.x + x.y) + (x.z + x.w);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float4 d = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
+  float v = on ? fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, d.w * d.w))) : 0.0f;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = 1.0f / sqrtf(v / (float)C + eps);
+  if (on)
+    reinterpret_cast<float4*>(out + row * C)[lane] =
+        make_float4(d.x * rstd * gg.x + bb.x, d.y * rstd * gg.y + bb.y, d.z * rstd * gg.z + bb.z, d.w * rstd * gg.w + bb.w);
+}
+
+static void launch_layernorm(cudaStream_t st, const float* in, const float* g, const float* be, float* out, size_t rows, int C,
+                             float eps) {
+  const bool reg = C <= 128 && (C & 3) == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+  if (reg)
+    layernorm_reg_kernel<<<cdiv(rows, 8), 256, 0, st>>>(in, g, be, out, rows, C, eps);
+  else
+    layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(in, g, be, out, rows, C, eps);
+}
+
 // ---------------------------------------------------------------------------
 // attention core: qkv [B,T,3,heads,d] -> out [B,T,heads*d]; one block per (head,b)
 // ---------------------------------------------------------------------------
@@ -731,6 +770,72 @@ __global__ void attn_core_kernel(const float* __restrict__ qkv, float* __restric
     float inv = 1.0f / den;
 #pragma unroll
     for (int d = 0; d < D; ++d) out[((size_t)b * T + t) * C + h * D + d] = acc[d] * inv;
+  }
+}
+
+// Same contract, S = 4 lanes per query: lane part p of a query takes keys p, p + 4, ... in both passes and the four
+// partial (max, sum, weighted V) sets are folded with two butterfly steps.  The one-thread-per-query kernel above kept
+// 40 of 128 threads busy on a 40-token sequence and ran 2 x T serial 15-deep FMA chains per thread (40 us per launch
+// at 2048 blocks: pure latency); this one keeps 4 x T threads busy on chains a quarter as long.
+template <int D>
+__global__ void __launch_bounds__(256) attn_core_split_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T,
+                                                              int heads, float scale) {
+  extern __shared__ float sm[];
+  float* Ks = sm;
+  float* Vs = sm + (size_t)T * D;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int C = heads * D;
+  const float* base = qkv + (size_t)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
+    Ks[i] = base[(size_t)t * 3 * C + C + h * D + d];
+    Vs[i] = base[(size_t)t * 3 * C + 2 * C + h * D + d];
+  }
+  __syncthreads();
+  const int part = threadIdx.x & 3;
+  // whole quads stay together: a quad whose query is past T still takes part in the shuffles
+  for (int t0 = 0; t0 < T; t0 += blockDim.x >> 2) {
+    const int t = t0 + (threadIdx.x >> 2);
+    const bool on = t < T;
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = on ? base[(size_t)t * 3 * C + h * D + d] * scale : 0.0f;
+    float mx = -INFINITY;
+    for (int j = part; j < T; j += 4) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], Ks[j * D + d], s);
+      mx = fmaxf(mx, s);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.0f;
+    float den = 0.0f;
+    for (int j = part; j < T; j += 4) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], Ks[j * D + d], s);
+      const float e = expf(s - mx);
+      den += e;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(e, Vs[j * D + d], acc[d]);
+    }
+    den += __shfl_xor_sync(0xffffffffu, den, 1);
+    den += __shfl_xor_sync(0xffffffffu, den, 2);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 1);
+      acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 2);
+    }
+    if (on) {
+      const float inv = 1.0f / den;
+      // the quad shares the row's D outputs: part p writes d = p, p + 4, ...
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        if ((d & 3) == part) out[((size_t)b * T + t) * C + h * D + d] = acc[d] * inv;
+    }
   }
 }
 
@@ -951,7 +1056,7 @@ void op_layernorm(oar_model* m, int oi, const float* in, int rows, float* out) {
   if (op.type != OP_LAYERNORM) OAR_FAIL(OAR_E_MODEL, "layer %d is not a LayerNorm", oi);
   const int c = op.p[0];
   Launch l(m->ctx, "layernorm", 8.0 * rows * c, 8.0 * rows * c);
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, m->ctx->stream>>>(in, m->w(op, 0), m->w(op, 1), out, (size_t)rows, c, op.f[0]);
+  launch_layernorm(m->ctx->stream, in, m->w(op, 0), m->w(op, 1), out, (size_t)rows, c, op.f[0]);
 }
 
 // multi-head attention block of an OP_ATTN layer over B sequences of T tokens: q, k = Linear(x_qk ? x_qk : x),
@@ -986,7 +1091,14 @@ void op_attention(oar_model* m, int oi, const float* x, const float* x_qk, int B
   {
     Launch l(ctx, "attn_core", 4.0 * B * heads * (double)T * T * hd, 4.0 * B * T * 4 * c);
     if (small) {
-      attn_core_kernel<15><<<dim3(heads, B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads, op.f[0]);
+      static const bool one_lane = getenv("OAR_DBG_ATTN1") != nullptr;  // A/B switch: one thread per query
+      if (one_lane) {
+        attn_core_kernel<15><<<dim3(heads, B), 128, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads, op.f[0]);
+      } else {
+        const int threads = std::min(256, ((4 * T + 31) / 32) * 32);
+        attn_core_split_kernel<15><<<dim3(heads, B), threads, (size_t)T * 15 * 2 * sizeof(float), st>>>(qkv, att, T, heads,
+                                                                                                         op.f[0]);
+      }
     } else {
       if (B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "attention layer %d: batch too large for one launch", oi);
       dim3 grid(heads, B, cdiv(T, 128));
@@ -1283,7 +1395,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Tensor& o = ensure(op.out, a.B, a.H, a.W, a.C);
         size_t rows = (size_t)a.B * a.H * a.W;
         Launch l(ctx, "layernorm", 8.0 * a.numel(), 8.0 * a.numel());
-        layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a.p, m->w(op, 0), m->w(op, 1), o.p, rows, a.C, op.f[0]);
+        launch_layernorm(st, a.p, m->w(op, 0), m->w(op, 1), o.p, rows, a.C, op.f[0]);
         break;
       }
       case OP_ATTN: {
