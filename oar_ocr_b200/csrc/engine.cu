@@ -1219,9 +1219,13 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         f.out = o.p, f.out_ld = o.C, f.out_c_off = pw.p[11] ? pw.p[10] : 0, f.Ho = o.H, f.Wo = o.W;
       };
       // (a 5x5 block wider than one 256-column N tile would run its depthwise stage once per N tile: measured slower
-      // than the stand-alone depthwise kernel + the persistent 1x1 conv, which converts A twice for almost nothing)
+      // than the stand-alone depthwise kernel + the persistent 1x1 conv.  With OAR_FB_SHARE=1 the fused kernel feeds two
+      // N tiles' accumulators from one A operand instead -- fused_tc.cu: share_a -- which measured equal, not faster:
+      // that kernel is bound by its shared-memory port, and the fusion only trades HBM bytes for shared-memory bytes)
+      static const bool no_share = !getenv("OAR_FB_SHARE") || atoi(getenv("OAR_FB_SHARE")) == 0;
       if (dw_ok && oi + 1 < m->ops.size() && is_pw(m->ops[oi + 1]) && m->ops[oi + 1].in0 == op.out &&
-          m->ops[oi + 1].p[6] == a.C && !(op.p[0] == 5 && m->ops[oi + 1].p[7] > 256)) {
+          m->ops[oi + 1].p[6] == a.C &&
+          !(op.p[0] == 5 && (m->ops[oi + 1].p[7] > 512 || (no_share && m->ops[oi + 1].p[7] > 256)))) {
         const OpRec& pw = m->ops[oi + 1];
         const int k = op.p[0], sh = op.p[2], sw = op.p[3];
         const int Ho = conv_out(a.H, k, sh, k / 2), Wo = conv_out(a.W, k, sw, k / 2);

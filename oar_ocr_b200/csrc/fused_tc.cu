@@ -74,6 +74,18 @@ struct FbParams {
   int nb;              // weight-stage ring depth (2..4): deep enough to cover the L2 round trip of a k-block
   uint32_t off_in, off_a, off_b, off_ctrl;
   int ep_tiles;  // epilogue staging tiles: 2 (store of one overlaps the fill of the other) or 1 when shared memory is short
+  // share_a = 1 (two N tiles only): a work item is a PIXEL tile; its A operand -- the depthwise stage's output -- is built
+  // once per k-block and multiplied into both N tiles' accumulators (TMEM columns 0.. and 256..), so a block wider
+  // than 256 output channels no longer runs its depthwise stage once per N tile.  n_work counts pixel tiles then.
+  int share_a;
+  // b_resident = 1 (CTC head): the grid is a multiple of n_tiles, so a CTA meets ONE N tile for its whole life; the nkb
+  // weight k-blocks of that tile are loaded once into an nkb-deep ring and never released.  Without it every
+  // 128-row item re-streamed its 128 KB of hi/lo weights from L2 (192 KB per item with the activations: the chip-wide
+  // L2 throughput, not the tensor pipe, set the pace).
+  int b_resident;
+  int ctc_two_pass;  // CTC-head epilogue form (OAR_DBG_CTC_EPI1 selects the one-pass online softmax)
+  int one_team;      // K == 0: one convert team takes every k-block (the CTC head's arrangement)
+  int dbg_fence;     // bisecting aid: the producer fences (gpu scope + async proxy) before its first TMA load
 };
 
 __device__ __forceinline__ float act_rt(float v, int act) {
@@ -193,6 +205,113 @@ __device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group,
   }
 }
 
+// The same statistics in two passes over the accumulator (TMEM reads are cheap): pass 1 finds the row's maximum over
+// the half tile, pass 2 sums exp(v - max) and records the last column equal to the maximum.  The one-pass form above
+// carries (max, sum) from one 16-column group to the next and waits on a TMEM load per group: one warp per scheduler ran
+// its 86 instructions per group at 0.19 IPC (ncu source view: the four epilogue warps busy 100 % of the kernel, 11.6 k
+// cycles per work item against 3.5 k for the item's MMAs).  Here every 32-column batch is independent work: the
+// exponentials have a fixed reference, the sums go to four separate accumulators, nothing but `mx` crosses batches.
+__device__ __forceinline__ void ctc_epilogue_two_pass(const FbParams& P, int gtid, uint32_t lane_base, float* bias_g,
+                                                      uint32_t acc_full0, uint32_t acc_empty0) {
+  const int half_cols = P.BN >> 1;
+  const float LOG2E = 1.4426950408889634f;
+  uint32_t ti = 0;
+  for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+    const int nt = t % P.n_tiles, sp = t / P.n_tiles;
+    const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+    if (ti == 0 || !P.b_resident) {  // resident weights: the CTA keeps its N tile, and with it this bias slice
+      named_bar_sync(1, FB_EPI_THREADS);
+      for (int i = gtid; i < P.BN; i += FB_EPI_THREADS) {
+        const int n = nt * P.BN + i;
+        bias_g[i] = n < P.N ? __ldg(P.bias + n) : 0.0f;
+      }
+      named_bar_sync(1, FB_EPI_THREADS);
+    }
+    mbar_wait(acc_full0 + 8u * acc, aph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int n_base = nt * P.BN + half * half_cols;
+      const uint32_t tcol = lane_base + acc * 256u + (uint32_t)(half * half_cols);
+      const float* bh = bias_g + half * half_cols;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < half_cols && n_base + c0 < P.N; c0 += 32) {
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tcol + (uint32_t)c0, v);
+        const float4* b4 = reinterpret_cast<const float4*>(bh + c0);
+        float2 q[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[i];
+          q[2 * i] = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+          q[2 * i + 1] = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+        }
+        if (n_base + c0 + 32 > P.N) {  // the vocabulary ends inside this batch (last tile only)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (n_base + c0 + 2 * i >= P.N) q[i].x = -INFINITY;
+            if (n_base + c0 + 2 * i + 1 >= P.N) q[i].y = -INFINITY;
+          }
+        }
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(q[2 * i].x, q[2 * i].y), fmaxf(q[2 * i + 1].x, q[2 * i + 1].y));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7]))));
+      }
+      const float nl = -mx * LOG2E;
+      float2 part[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part[i] = make_float2(0.f, 0.f);
+      int mi = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < half_cols && n_base + c0 < P.N; c0 += 32) {
+        float v[32];
+        __syncwarp();  // the arg-max selects below diverge per row; tcgen05.ld is .sync.aligned
+        tmem_ld32(tcol + (uint32_t)c0, v);
+        const float4* b4 = reinterpret_cast<const float4*>(bh + c0);
+        float2 q[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[i];
+          q[2 * i] = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+          q[2 * i + 1] = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+        }
+        if (n_base + c0 + 32 > P.N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (n_base + c0 + 2 * i >= P.N) q[i].x = -INFINITY;
+            if (n_base + c0 + 2 * i + 1 >= P.N) q[i].y = -INFINITY;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 a = __ffma2_rn(q[i], make_float2(LOG2E, LOG2E), make_float2(nl, nl));  // (v - mx) * log2(e)
+          part[i & 3] = __fadd2_rn(part[i & 3], make_float2(ex2_approx(a.x), ex2_approx(a.y)));  // 0 for padded classes
+        }
+        // classes ascend, so the last assignment is the last maximal index (simd.rs:194-204)
+        const int cb = n_base + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (q[i].x == mx) mi = cb + 2 * i;
+          if (q[i].y == mx) mi = cb + 2 * i + 1;
+        }
+      }
+      const float2 s2 = __fadd2_rn(__fadd2_rn(part[0], part[1]), __fadd2_rn(part[2], part[3]));
+      const int m = sp * 128 + gtid;
+      if (m < P.M) {
+        const size_t o = (size_t)m * (2 * P.n_tiles) + 2 * nt + half;
+        P.part_max[o] = mx;
+        P.part_idx[o] = mi;
+        P.part_sum[o] = s2.x + s2.y;
+      }
+    }
+    tc_fence_before();
+    warp_arrive(acc_empty0 + 8u * acc, gtid & 31);
+  }
+}
+
 template <int K, int SH, int SW>
 __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, const __grid_constant__ CUtensorMap tm_in,
                                                             const __grid_constant__ CUtensorMap tm_out) {
@@ -231,17 +350,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
   if (warp == FB_WARP_TMA) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
+      if (P.dbg_fence) {
+        __threadfence();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+      }
       // two independent cursors -- activation boxes run ns_in stages ahead of the depthwise warps, weight k-blocks two
       // ahead of the MMAs -- advanced by non-blocking probes so that neither ring throttles the other
       const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
                                (uint32_t)P.nkb;
+      const uint32_t n_items_b = P.b_resident ? (n_items ? (uint32_t)P.nkb : 0u)  // resident weights: one lap of the ring
+                                 : P.share_a  ? n_items * (uint32_t)P.n_tiles      // shared A: every N tile's k-block
+                                              : n_items;
+      const int sp_div = P.share_a ? 1 : P.n_tiles;
       uint32_t it_in = 0, it_b = 0;
-      int t_in = blockIdx.x, kb_in = 0, t_b = blockIdx.x, kb_b = 0;
-      while (it_in < n_items || it_b < n_items) {
+      int t_in = blockIdx.x, kb_in = 0, t_b = blockIdx.x, kb_b = 0, nt_b = 0;
+      while (it_in < n_items || it_b < n_items_b) {
         if (it_in < n_items) {
           const uint32_t s = it_in % (uint32_t)P.ns_in, ph = (it_in / (uint32_t)P.ns_in) & 1u;
           if (mbar_test(FB_BAR(FB_IN_EMPTY + s), ph ^ 1u)) {
-            const int sp = t_in / P.n_tiles;
+            const int sp = t_in / sp_div;
             const uint32_t dst = sbase + P.off_in + s * stage_bytes;
             mbar_expect_tx(FB_BAR(FB_IN_FULL + s), stage_bytes);
             if (K == 0) {
@@ -257,14 +384,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             if (++kb_in == P.nkb) kb_in = 0, t_in += gridDim.x;
           }
         }
-        if (it_b < n_items) {
+        if (it_b < n_items_b) {
           const uint32_t sb = it_b % (uint32_t)P.nb, phb = (it_b / (uint32_t)P.nb) & 1u;
           if (mbar_test(FB_BAR(FB_B_EMPTY + sb), phb ^ 1u)) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk) +
-                                  ((size_t)(t_b % P.n_tiles) * P.nkb + kb_b) * b_bytes;
+            // weight k-blocks in the order the MMA warp consumes them: (item, kb) -- or (item, kb, N tile) with a shared A
+            const int nt = P.share_a ? nt_b : t_b % P.n_tiles;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk) + ((size_t)nt * P.nkb + kb_b) * b_bytes;
             mbar_expect_tx(FB_BAR(FB_B_FULL + sb), b_bytes);
             bulk_load(sbase + P.off_b + sb * b_bytes, wsrc, b_bytes, FB_BAR(FB_B_FULL + sb));
             ++it_b;
+            if (P.share_a && ++nt_b < P.n_tiles) continue;
+            nt_b = 0;
             if (++kb_b == P.nkb) kb_b = 0, t_b += gridDim.x;
           }
         }
@@ -275,33 +405,37 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)P.BN * 16u, b_part = 4u * b_lbo;
-      uint32_t it = 0, ti = 0;
+      const uint32_t nt_loop = P.share_a ? (uint32_t)P.n_tiles : 1u;  // accumulators fed from one A buffer
+      uint32_t it = 0, it_b = 0, ti = 0;
       for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
-        mbar_wait(FB_BAR(FB_ACC_EMPTY + acc), aph ^ 1u);  // the epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * 256u;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
           mbar_wait(FB_BAR(FB_A_FULL + s), ph);
-          const uint32_t sb = it % (uint32_t)P.nb;
-          mbar_wait(FB_BAR(FB_B_FULL + sb), (it / (uint32_t)P.nb) & 1u);
-          tc_fence_after();
           const uint32_t a_hi = sbase + P.off_a + s * FB_ABUF, a_lo = a_hi + FB_APART;
-          const uint32_t b_hi = sbase + P.off_b + sb * b_bytes, b_lo = b_hi + b_part;
+          for (uint32_t ntl = 0; ntl < nt_loop; ++ntl, ++it_b) {
+            // accumulators alternate over the sequence of (item, N tile) pairs, which is the order the epilogue drains
+            const uint32_t v = ti * nt_loop + ntl, acc = v & 1u, aph = (v >> 1) & 1u;
+            if (kb == 0) mbar_wait(FB_BAR(FB_ACC_EMPTY + acc), aph ^ 1u);  // the epilogue has drained this accumulator
+            // resident weights: stage kb was filled once (phase 0 stays complete) and is never handed back
+            const uint32_t sb = P.b_resident ? (uint32_t)kb : it_b % (uint32_t)P.nb;
+            mbar_wait(FB_BAR(FB_B_FULL + sb), P.b_resident ? 0u : (it_b / (uint32_t)P.nb) & 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * 256u;
+            const uint32_t b_hi = sbase + P.off_b + sb * b_bytes, b_lo = b_hi + b_part;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t ah = make_desc(a_hi + 2 * j * FB_LBO, FB_LBO, 128);
-            const uint64_t al = make_desc(a_lo + 2 * j * FB_LBO, FB_LBO, 128);
-            const uint64_t bh = make_desc(b_hi + 2 * j * b_lbo, b_lbo, 128);
-            const uint64_t bl = make_desc(b_lo + 2 * j * b_lbo, b_lbo, 128);
-            umma_f16(d, ah, bh, idesc, (kb | j) ? 1u : 0u);
-            umma_f16(d, ah, bl, idesc, 1u);
-            umma_f16(d, al, bh, idesc, 1u);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ah = make_desc(a_hi + 2 * j * FB_LBO, FB_LBO, 128);
+              const uint64_t al = make_desc(a_lo + 2 * j * FB_LBO, FB_LBO, 128);
+              const uint64_t bh = make_desc(b_hi + 2 * j * b_lbo, b_lbo, 128);
+              const uint64_t bl = make_desc(b_lo + 2 * j * b_lbo, b_lbo, 128);
+              umma_f16(d, ah, bh, idesc, (kb | j) ? 1u : 0u);
+              umma_f16(d, ah, bl, idesc, 1u);
+              umma_f16(d, al, bh, idesc, 1u);
+            }
+            if (!P.b_resident) umma_commit(FB_BAR(FB_B_EMPTY + sb));
+            if (kb == P.nkb - 1) umma_commit(FB_BAR(FB_ACC_FULL + acc));
           }
           umma_commit(FB_BAR(FB_AB_EMPTY + s));
-          umma_commit(FB_BAR(FB_B_EMPTY + sb));
-          if (kb == P.nkb - 1) umma_commit(FB_BAR(FB_ACC_FULL + acc));
         }
       }
     }
@@ -313,7 +447,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     const int ct = (tid - FB_WARP_C0 * 32) & 255;
     const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
                              (uint32_t)P.nkb;
-    const bool ctc = K == 0 && P.part_max != nullptr;
+    const bool ctc = K == 0 && (P.part_max != nullptr || P.one_team);
     if (ctc && team == 1) {
       // CTC head: converting fp32 rows is light work, so one team does every k-block and this one idles
     } else if (K == 0) {
@@ -327,7 +461,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
         float4 sc[4];
         if (P.se_scale) {
-          const int sp = ((int)blockIdx.x + (int)(it / (uint32_t)P.nkb) * (int)gridDim.x) / P.n_tiles;
+          const int sp = ((int)blockIdx.x + (int)(it / (uint32_t)P.nkb) * (int)gridDim.x) / (P.share_a ? 1 : P.n_tiles);
           const int c = kb * 32 + q * 4;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -469,20 +603,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + 256);  // [n_tiles * BN + 32], zero padded
     const bool ctc = P.part_max != nullptr;  // then bias_s holds one tile's BN values, reloaded per work item
     if (ctc) {
-      ctc_epilogue_group(P, 0, 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+      if (P.ctc_two_pass)
+        ctc_epilogue_two_pass(P, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+      else
+        ctc_epilogue_group(P, 0, 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
     } else {
       for (int i = tid; i < P.n_tiles * P.BN + 32; i += FB_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
       named_bar_sync(1, FB_EPI_THREADS);
     }
-    uint32_t ti = 0, nstore = 0;
-    for (int t = blockIdx.x; t < (ctc ? 0 : P.n_work); t += gridDim.x, ++ti) {
-      const int nt = t % P.n_tiles, sp = t / P.n_tiles;
+    const uint32_t nt_loop = P.share_a ? (uint32_t)P.n_tiles : 1u;
+    uint32_t vi = 0, nstore = 0;  // vi counts (item, N tile) pairs: the accumulator sequence of the MMA warp
+    for (int t = blockIdx.x; t < (ctc ? 0 : P.n_work); t += gridDim.x)
+    for (uint32_t ntl = 0; ntl < nt_loop; ++ntl, ++vi) {
+      const int nt = P.share_a ? (int)ntl : t % P.n_tiles, sp = P.share_a ? t : t / P.n_tiles;
       int c1 = sp * 128, c2 = 0, c3 = 0;
       if (K > 0) {
         const int tw = sp % P.tiles_w, r = sp / P.tiles_w;
         c1 = tw * P.TW, c2 = (r % P.tiles_h) * P.TH, c3 = r / P.tiles_h;
       }
-      const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint32_t acc = vi & 1u, aph = (vi >> 1) & 1u;
       mbar_wait(FB_BAR(FB_ACC_FULL + acc), aph);
       tc_fence_after();
       const int n_base = nt * P.BN;
@@ -557,6 +696,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
   if (warp == FB_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
+// bisecting aid (OAR_DBG_FB_PAD = cycles): a one-warp kernel that spins, launched in front of the 1x1 kernel
+__global__ void fb_pad_kernel(int cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
@@ -599,6 +745,22 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     return false;
   FbKern kern = pick_kernel(f.k, f.k ? f.sh : 1, f.k ? f.sw : 1);
   if (!kern) return false;
+  // bisecting aid: OAR_DBG_FB_OFF bit 0 = plain 1x1, 1 = squeeze-excite 1x1, 2 = 3x3 blocks, 3 = 5x5 blocks fall back to
+  // the per-layer kernels; OAR_DBG_FB_NS forces the input ring depth (an even ring needs no team handshake)
+  static const int dbg_off = getenv("OAR_DBG_FB_OFF") ? atoi(getenv("OAR_DBG_FB_OFF")) : 0;
+  static const int dbg_ns = getenv("OAR_DBG_FB_NS") ? atoi(getenv("OAR_DBG_FB_NS")) : 0;
+  if (dbg_off) {
+    const int cls = f.k == 0 ? (f.se_scale ? 1 : 0) : (f.k == 3 ? 2 : 3);
+    if ((dbg_off >> cls) & 1) return false;
+    // bits 4 / 5: plain 1x1 with two N tiles / with one N tile; bits 6 / 7: plain 1x1 over more / fewer than 148 row tiles
+    if (f.k == 0 && !f.se_scale) {
+      const long long tiles = ((long long)f.B * f.Ho * f.Wo + 127) / 128;
+      if (((dbg_off >> 4) & 1) && w->n_tiles >= 2) return false;
+      if (((dbg_off >> 5) & 1) && w->n_tiles == 1) return false;
+      if (((dbg_off >> 6) & 1) && tiles * w->n_tiles > 148) return false;
+      if (((dbg_off >> 7) & 1) && tiles * w->n_tiles <= 148) return false;
+    }
+  }
   // the epilogue keeps the whole (zero-padded) bias in shared memory: FB_CTRL_BYTES reserves 512 + 32 floats
   if ((size_t)w->n_tiles * w->BN + 32 > (FB_CTRL_BYTES - 256) / sizeof(float)) return false;
   const long long M = (long long)f.B * f.Ho * f.Wo;
@@ -618,7 +780,19 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   P.C = f.C, P.N = f.N, P.BN = w->BN, P.nkb = w->nkb, P.n_tiles = w->n_tiles;
 
   const size_t b_stage = (size_t)w->BN * 128;
-  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * b_stage + FB_CTRL_BYTES + 1024;  // with the minimum of 2 weight stages
+  // two N tiles: the depthwise blocks can share one A operand between them (OAR_FB_SHARE=1; =2 also the plain 1x1
+  // convs, whose A costs a conversion, not a convolution).  Opt-in: measured on B200 it is no faster than the
+  // stand-alone depthwise kernel + the 1x1 kernel it replaces (recogniser blocks 6c / 6d: 1.01 + 1.01 ms against
+  // 1.02 + 0.96 per 5 chunks; 512 fixed-size crops: 2.6 % slower) -- see the shared-memory budget below.
+  static const int share_mode = getenv("OAR_FB_SHARE") ? atoi(getenv("OAR_FB_SHARE")) : 0;  // 0 off, 1 k > 0, 2 all
+  P.share_a = (w->n_tiles == 2 && (share_mode == 2 || (share_mode == 1 && f.k > 0))) ? 1 : 0;
+  // A shared A consumes two weight stages per k-block.  Measured on the recogniser's 480-channel blocks: 4370 cycles per
+  // k-block against 2750 for a 240-channel block, and a third weight stage (OAR_FB_SHARE_NB=3) changes nothing -- the
+  // ring is not what waits.  The shared-memory port is: 12 MMAs x 12 KB of operand reads + 96 KB of TMA writes + the
+  // depthwise loads + the staging tile come to ~3800 cycles of 128 B/clk traffic per k-block.
+  static const int share_nb = getenv("OAR_FB_SHARE_NB") ? atoi(getenv("OAR_FB_SHARE_NB")) : 2;
+  const int min_b = P.share_a ? std::max(2, std::min(4, share_nb)) : 2;
+  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + min_b * b_stage + FB_CTRL_BYTES + 1024;  // with the minimum of weight stages
   CUtensorMap tm_in, tm_out;
   memset(&tm_in, 0, sizeof(tm_in));
   memset(&tm_out, 0, sizeof(tm_out));
@@ -627,6 +801,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     P.in_bytes = 128 * 128;
     P.ns_in = 4;
     while (P.ns_in > 2 && fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) --P.ns_in;
+    if (dbg_ns && dbg_ns <= P.ns_in) P.ns_in = dbg_ns;
     if (fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) return false;
     n_sp = (int)((M + 127) / 128);
     P.M = (int)M;
@@ -657,6 +832,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
           int ns = 4;
           while (ns >= 2 && fx + ns * (in_bytes + tap_bytes) > FB_SMEM_MAX) --ns;
           if (ns < 2) continue;
+          if (dbg_ns && dbg_ns <= ns) ns = dbg_ns;
           const double cost = tiles * (1000.0 + rows_in * cols_in) * (ns == 2 ? 1.2 : ns == 3 ? 1.05 : 1.0) *
                               (ep == 1 ? 1.03 : 1.0);
           if (cost < best) best = cost, bTH = TH, bTW = TW, bns = ns, bep = ep;
@@ -679,22 +855,31 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     cuuint32_t obox[4] = {32, (cuuint32_t)bTW, (cuuint32_t)bTH, 1};
     if (!encode_map(&tm_out, f.out + f.out_c_off, 4, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   }
-  P.n_work = n_sp * w->n_tiles;
+  P.n_work = P.share_a ? n_sp : n_sp * w->n_tiles;
   if (f.k == 0) P.ep_tiles = 2;
+  static const int dbg_one_team = getenv("OAR_DBG_FB_ONE_TEAM") ? atoi(getenv("OAR_DBG_FB_ONE_TEAM")) : 0;
+  static const int dbg_ep = getenv("OAR_DBG_FB_EP") ? atoi(getenv("OAR_DBG_FB_EP")) : 0;
+  if (f.k == 0 && dbg_one_team) P.one_team = 1;
+  static const int dbg_fence = getenv("OAR_DBG_FB_FENCE") ? atoi(getenv("OAR_DBG_FB_FENCE")) : 0;
+  static const int dbg_pad = getenv("OAR_DBG_FB_PAD") ? atoi(getenv("OAR_DBG_FB_PAD")) : 0;
+  P.dbg_fence = dbg_fence;
+  if (dbg_pad && f.k == 0) fb_pad_kernel<<<1, 32, 0, m->ctx->stream>>>(dbg_pad);
+  if (f.k == 0 && dbg_ep == 1) P.ep_tiles = 1;
   P.off_in = (uint32_t)P.ep_tiles * FB_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * (P.in_bytes + P.tap_bytes);
   P.off_b = P.off_a + 2 * FB_ABUF;
   // whatever shared memory is left goes to the weight ring (up to 4 stages): a k-block of weights is an L2 round trip
-  P.nb = 2;
+  P.nb = min_b;
   while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * b_stage + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
   P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)b_stage;
   // always above half the SM's shared memory: one CTA per SM owns all 512 TMEM columns
-  const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
+  static const bool dbg_smem_max = getenv("OAR_DBG_FB_SMEMMAX") != nullptr;  // bisecting aid: nothing co-resident
+  const size_t smem = dbg_smem_max ? FB_SMEM_MAX : std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
   ensure_max_dynamic_smem((const void*)kern, m->ctx->device, (int)FB_SMEM_MAX);
   static const bool dbg_tiles = getenv("OAR_DBG_TILES") != nullptr;
   if (dbg_tiles)
-    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d smem %zu\n", f.k,
-            f.sh, f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.nb, P.n_work, smem);
+    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d share %d smem %zu\n",
+            f.k, f.sh, f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.nb, P.n_work, P.share_a, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
   const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
@@ -721,9 +906,17 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   // faster on this layer but showed rare run-to-run differences in the softmax statistics under host-side jitter --
   // 17 of 300 stress iterations, synccheck clean, racecheck inconclusive -- and was removed in round 2: DESIGN.md 5.2.)
   P.M = p.M, P.HW = 1;
+  static const bool one_pass = getenv("OAR_DBG_CTC_EPI1") != nullptr;  // A/B switch
+  P.ctc_two_pass = one_pass ? 0 : 1;
   P.in_bytes = 128 * 128, P.tap_bytes = 0, P.ns_in = 4;
   P.TH = P.TW = 0, P.tiles_h = P.tiles_w = 1, P.cols_in = 128;
-  const size_t fixed = 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * (size_t)w.BN * 128 + FB_CTRL_BYTES + 1024;
+  const size_t b_stage = (size_t)w.BN * 128;
+  // resident weights: all nkb k-blocks of the CTA's N tile stay in shared memory (the staging tiles are not used here)
+  static const bool no_resident = getenv("OAR_DBG_CTC_STREAM") != nullptr;  // A/B switch
+  const int sm_count = m->ctx->sm_count;
+  const size_t res_fixed = 2 * FB_ABUF + (size_t)w.nkb * b_stage + FB_CTRL_BYTES + 1024;
+  P.b_resident = (!no_resident && w.nkb <= FB_MAX_IN && w.n_tiles <= sm_count && res_fixed + 2 * (size_t)P.in_bytes <= FB_SMEM_MAX) ? 1 : 0;
+  const size_t fixed = P.b_resident ? res_fixed : 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * b_stage + FB_CTRL_BYTES + 1024;
   while (P.ns_in > 2 && fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) --P.ns_in;
   if (fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) return false;
   CUtensorMap tm_in, tm_out;
@@ -739,12 +932,17 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
   P.off_b = P.off_a + 2 * FB_ABUF;
   P.nb = 2;
-  while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * w.BN * 128 + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
+  if (P.b_resident) {
+    P.nb = w.nkb;
+  } else {
+    while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * w.BN * 128 + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
+  }
   P.off_ctrl = P.off_b + (uint32_t)P.nb * (uint32_t)w.BN * 128u;
   const size_t smem = std::max<size_t>((size_t)P.off_ctrl + FB_CTRL_BYTES + 1024, 120 * 1024);
   FbKern kern = lcblock_tc<0, 1, 1>;
   ensure_max_dynamic_smem((const void*)kern, m->ctx->device, (int)FB_SMEM_MAX);
-  const int grid = std::min(P.n_work, m->ctx->sm_count);
+  // resident weights: item t = blockIdx + i * grid keeps t % n_tiles fixed when the grid is a multiple of n_tiles
+  const int grid = P.b_resident ? std::min(P.n_work, sm_count / w.n_tiles * w.n_tiles) : std::min(P.n_work, sm_count);
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * (double)p.M * p.K + 24.0 * p.M * w.n_tiles);
   kern<<<grid, FB_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
   return true;
