@@ -1550,15 +1550,11 @@ void scatter_stage(const PageStage& S, int img0, const std::vector<int>& ref_of_
 // the crop pool and the job tables the batches read were written on the main lane before the fork event.
 void recognize_chunks(oar_model* rec, const std::vector<CropRef>& refs, RecPlan& plan, int n_chars, int only_stage = -1) {
   oar_ctx* ctx = rec->ctx;
-  // Two lanes are OPT-IN (OAR_REC_LANES=2).  They buy 0.8 ms per 32-page step, but with kernels of two batches in flight
-  // at once a handful of regions per run (2-30 of 1527) come out with confidences a few 1e-4 apart from run to run, a
-  // label now and then.  Bisected on B200 (tools/det_diff.py, profiles/r2_two_lane_bisect.txt): only with real overlap
-  // (lanes chained by events: clean), only through lcblock_tc<0> as a plain 1x1 conv over more items than CTAs (the
-  // squeeze-excite form, the 3x3 / 5x5 blocks, the CTC head and the per-layer kernel are clean), independent of
-  // co-residency (same with all of the SM's shared memory claimed), of one or two convert teams, of the staging tiles,
-  // of a fence or a spacer kernel in front.  Not root-caused; results must not depend on timing, so one lane it is.
-  static const bool one_lane = getenv("OAR_DBG_ONE_STREAM") != nullptr || !getenv("OAR_REC_LANES") ||
-                               atoi(getenv("OAR_REC_LANES")) < 2;
+  // (Round 2 found run-to-run differences with two batches in flight and bisected them -- tools/det_diff.py,
+  // profiles/r2_two_lane_bisect.txt -- to lcblock_tc handing its TMA stage back before the loads from it had completed,
+  // fused_tc.cu: dep_zero.  Fixed there; OAR_REC_LANES=1 keeps the single-lane form for A/B runs.)
+  static const bool one_lane = getenv("OAR_DBG_ONE_STREAM") != nullptr ||
+                               (getenv("OAR_REC_LANES") && atoi(getenv("OAR_REC_LANES")) < 2);
   int mine = 0;
   for (const RecChunk& ch : plan.chunks) mine += (only_stage < 0 || ch.stage == only_stage) ? 1 : 0;
   const bool two = !one_lane && !ctx->profile && mine >= 2 && ctx->stream_aux;

@@ -1461,6 +1461,19 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
             static const bool no_ctc_persist = getenv("OAR_DBG_NOCTC") != nullptr;
             if ((m->engine == 2 && !no_ctc_persist && tc_ctc_head_persistent(m, (int)oi * 2, p, "ctc_head_persist_tc")) ||
                 tc_gemm(m, (int)oi * 2, p, "ctc_head_fused_tc")) {
+              // race hunting: OAR_DBG_DUMP_CTC=<file> appends [rows, nt, part_max.., part_sum..] of every head launch
+              if (const char* dump = getenv("OAR_DBG_DUMP_CTC")) {
+                std::vector<float> h(2 * rows * nt);
+                OAR_CUDA(cudaMemcpyAsync(h.data(), p.part_max, rows * nt * 4, cudaMemcpyDeviceToHost, st));
+                OAR_CUDA(cudaMemcpyAsync(h.data() + rows * nt, p.part_sum, rows * nt * 4, cudaMemcpyDeviceToHost, st));
+                OAR_CUDA(cudaStreamSynchronize(st));
+                if (FILE* f = fopen(dump, "ab")) {
+                  const int64_t hdr[2] = {(int64_t)rows, (int64_t)nt};
+                  fwrite(hdr, sizeof(hdr), 1, f);
+                  fwrite(h.data(), 4, h.size(), f);
+                  fclose(f);
+                }
+              }
               launch_ctc_combine(ctx, p.part_max, p.part_idx, p.part_sum, rows, nt, co->idx, co->prob);
               t[op.out] = probs;
               last = probs;

@@ -84,7 +84,9 @@ struct FbParams {
   // L2 throughput, not the tensor pipe, set the pace).
   int b_resident;
   int ctc_two_pass;  // CTC-head epilogue form (OAR_DBG_CTC_EPI1 selects the one-pass online softmax)
+  int ctc_groups;    // CTC head: 2 = a second epilogue group (warps 16-19 of the idle convert team) reduces column half 1
   int one_team;      // K == 0: one convert team takes every k-block (the CTC head's arrangement)
+  uint32_t zero;     // always 0, but only the host knows: lets an address depend on loaded data (dep_zero below)
   int dbg_fence;     // bisecting aid: the producer fences (gpu scope + async proxy) before its first TMA load
 };
 
@@ -106,6 +108,12 @@ __device__ __forceinline__ float act_rt(float v, int act) {
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
+}
+
+// 0, computed FROM the given values with a mask the compiler cannot see through: adding it to an mbarrier address makes
+// the arrive wait (register scoreboard) for the loads that produced the values.
+__device__ __forceinline__ uint32_t dep_zero(uint32_t zero, float a, float b, float c, float d) {
+  return (__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c) | __float_as_uint(d)) & zero;
 }
 
 // x = hi + lo in fp16, two channels packed per 32-bit word
@@ -211,26 +219,31 @@ __device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group,
 // its 86 instructions per group at 0.19 IPC (ncu source view: the four epilogue warps busy 100 % of the kernel, 11.6 k
 // cycles per work item against 3.5 k for the item's MMAs).  Here every 32-column batch is independent work: the
 // exponentials have a fixed reference, the sums go to four separate accumulators, nothing but `mx` crosses batches.
+// half0 / n_halves: the column halves this group of four warps reduces (both, or one each with two groups; then the bias
+// slice was staged by the kernel prologue and the group shares nothing writable with the other one)
 __device__ __forceinline__ void ctc_epilogue_two_pass(const FbParams& P, int gtid, uint32_t lane_base, float* bias_g,
-                                                      uint32_t acc_full0, uint32_t acc_empty0) {
+                                                      uint32_t acc_full0, uint32_t acc_empty0, int half0, int n_halves,
+                                                      bool bias_staged) {
   const int half_cols = P.BN >> 1;
   const float LOG2E = 1.4426950408889634f;
   uint32_t ti = 0;
   for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
     const int nt = t % P.n_tiles, sp = t / P.n_tiles;
     const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
-    if (ti == 0 || !P.b_resident) {  // resident weights: the CTA keeps its N tile, and with it this bias slice
+    if (!bias_staged && (ti == 0 || !P.b_resident)) {  // resident weights: the CTA keeps its N tile, and with it this bias slice
       named_bar_sync(1, FB_EPI_THREADS);
+      // classes past the vocabulary get a bias of -inf: their accumulators are exact zeros (zero-padded weights), so
+      // they can never be the maximum and their exponentials are exact zeros -- no per-element tail masks below
       for (int i = gtid; i < P.BN; i += FB_EPI_THREADS) {
         const int n = nt * P.BN + i;
-        bias_g[i] = n < P.N ? __ldg(P.bias + n) : 0.0f;
+        bias_g[i] = n < P.N ? __ldg(P.bias + n) : -INFINITY;
       }
       named_bar_sync(1, FB_EPI_THREADS);
     }
     mbar_wait(acc_full0 + 8u * acc, aph);
     tc_fence_after();
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    for (int half = half0; half < half0 + n_halves; ++half) {
       const int n_base = nt * P.BN + half * half_cols;
       const uint32_t tcol = lane_base + acc * 256u + (uint32_t)(half * half_cols);
       const float* bh = bias_g + half * half_cols;
@@ -241,23 +254,14 @@ __device__ __forceinline__ void ctc_epilogue_two_pass(const FbParams& P, int gti
         __syncwarp();
         tmem_ld32(tcol + (uint32_t)c0, v);
         const float4* b4 = reinterpret_cast<const float4*>(bh + c0);
-        float2 q[16];
+        float m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 b = b4[i];
-          q[2 * i] = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
-          q[2 * i + 1] = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+          const float2 q0 = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+          const float2 q1 = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+          m[i] = fmaxf(fmaxf(q0.x, q0.y), fmaxf(q1.x, q1.y));
         }
-        if (n_base + c0 + 32 > P.N) {  // the vocabulary ends inside this batch (last tile only)
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (n_base + c0 + 2 * i >= P.N) q[i].x = -INFINITY;
-            if (n_base + c0 + 2 * i + 1 >= P.N) q[i].y = -INFINITY;
-          }
-        }
-        float m[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(q[2 * i].x, q[2 * i].y), fmaxf(q[2 * i + 1].x, q[2 * i + 1].y));
         mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7]))));
       }
       const float nl = -mx * LOG2E;
@@ -271,32 +275,22 @@ __device__ __forceinline__ void ctc_epilogue_two_pass(const FbParams& P, int gti
         __syncwarp();  // the arg-max selects below diverge per row; tcgen05.ld is .sync.aligned
         tmem_ld32(tcol + (uint32_t)c0, v);
         const float4* b4 = reinterpret_cast<const float4*>(bh + c0);
-        float2 q[16];
+        int loc = -1;  // last column of this batch equal to the maximum (classes ascend: simd.rs:194-204)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 b = b4[i];
-          q[2 * i] = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
-          q[2 * i + 1] = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+          const float2 q0 = __fadd2_rn(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+          const float2 q1 = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+          const float2 a0 = __ffma2_rn(q0, make_float2(LOG2E, LOG2E), make_float2(nl, nl));  // (v - mx) * log2(e)
+          const float2 a1 = __ffma2_rn(q1, make_float2(LOG2E, LOG2E), make_float2(nl, nl));
+          part[(2 * i) & 3] = __fadd2_rn(part[(2 * i) & 3], make_float2(ex2_approx(a0.x), ex2_approx(a0.y)));
+          part[(2 * i + 1) & 3] = __fadd2_rn(part[(2 * i + 1) & 3], make_float2(ex2_approx(a1.x), ex2_approx(a1.y)));
+          loc = q0.x == mx ? 4 * i : loc;
+          loc = q0.y == mx ? 4 * i + 1 : loc;
+          loc = q1.x == mx ? 4 * i + 2 : loc;
+          loc = q1.y == mx ? 4 * i + 3 : loc;
         }
-        if (n_base + c0 + 32 > P.N) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (n_base + c0 + 2 * i >= P.N) q[i].x = -INFINITY;
-            if (n_base + c0 + 2 * i + 1 >= P.N) q[i].y = -INFINITY;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 a = __ffma2_rn(q[i], make_float2(LOG2E, LOG2E), make_float2(nl, nl));  // (v - mx) * log2(e)
-          part[i & 3] = __fadd2_rn(part[i & 3], make_float2(ex2_approx(a.x), ex2_approx(a.y)));  // 0 for padded classes
-        }
-        // classes ascend, so the last assignment is the last maximal index (simd.rs:194-204)
-        const int cb = n_base + c0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (q[i].x == mx) mi = cb + 2 * i;
-          if (q[i].y == mx) mi = cb + 2 * i + 1;
-        }
+        mi = loc >= 0 ? n_base + c0 + loc : mi;
       }
       const float2 s2 = __fadd2_rn(__fadd2_rn(part[0], part[1]), __fadd2_rn(part[2], part[3]));
       const int m = sp * 128 + gtid;
@@ -336,12 +330,22 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       mbar_init(FB_BAR(FB_A_FULL + i), FB_CWARPS);
       mbar_init(FB_BAR(FB_AB_EMPTY + i), 1);
       mbar_init(FB_BAR(FB_ACC_FULL + i), 1);
-      mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_WARPS);
+      mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_WARPS * (P.ctc_groups == 2 ? 2 : 1));
       mbar_init(FB_BAR(FB_SEEN + i), FB_CWARPS);
     }
     fence_mbar_init();
   }
   if (warp == FB_WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (K == 0 && P.ctc_groups == 2) {
+    // two CTC epilogue groups (resident weights: one N tile per CTA): its bias slice is staged once, by everybody;
+    // classes past the vocabulary get -inf (see ctc_epilogue_two_pass)
+    float* bias_all = reinterpret_cast<float*>(smem + P.off_ctrl + 256);
+    const int nt = (int)blockIdx.x % P.n_tiles;
+    for (int i = tid; i < P.BN; i += FB_THREADS) {
+      const int n = nt * P.BN + i;
+      bias_all[i] = n < P.N ? __ldg(P.bias + n) : -INFINITY;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -448,7 +452,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     const uint32_t n_items = (P.n_work > (int)blockIdx.x ? (uint32_t)((P.n_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u) *
                              (uint32_t)P.nkb;
     const bool ctc = K == 0 && (P.part_max != nullptr || P.one_team);
-    if (ctc && team == 1) {
+    if (K == 0 && P.ctc_groups == 2 && warp >= 16 && warp < 20) {
+      // CTC head, second epilogue group: TMEM lanes 32 * (warp % 4) are this warp's, like warps 0-3
+      const uint32_t lane_base2 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      ctc_epilogue_two_pass(P, tid - 16 * 32, lane_base2, reinterpret_cast<float*>(smem + P.off_ctrl + 256),
+                            FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY), 1, 1, true);
+    } else if (ctc && team == 1) {
       // CTC head: converting fp32 rows is light work, so one team does every k-block and this one idles
     } else if (K == 0) {
       const uint32_t it0 = ctc ? 0u : (uint32_t)team, it_step = ctc ? 1u : 2u;
@@ -487,7 +496,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         float4 x[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(src + (r0 + 32 * j) * 128);
-        warp_arrive(FB_BAR(FB_IN_EMPTY + s), lane);
+        // The stage may be handed back only once its values sit in registers.  An arrive issued right behind the LDS
+        // instructions is NOT ordered behind their data: with the tensor pipe streaming operands at full rate the
+        // shared-memory port is saturated (N = 256: 72 KB of operand reads + 48 KB of copies per 870 cycles), the loads
+        // queue, the arrive does not, the producer refills the stage and a warp converts the NEXT lap's pixels --
+        // one warp's 16 rows of one k-block wrong, a few times per hundred calls (tools/ctc_dump_diff.py; this was the
+        // "two-group CTC race" of round 1 and the two-lane differences of round 2).  An arrive must follow the data in
+        // registers -- so the barrier address is made to depend on the loaded values (dep_zero).
+        warp_arrive(FB_BAR(FB_IN_EMPTY + s) + dep_zero(P.zero, x[0].x, x[1].x, x[2].x, x[3].x), lane);
         if (P.se_scale) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) x[j].x *= sc[j].x, x[j].y *= sc[j].y, x[j].z *= sc[j].z, x[j].w *= sc[j].w;
@@ -563,7 +579,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             }
           }
         }
-        warp_arrive(FB_BAR(FB_IN_EMPTY + s), lane);
+        // (as in the K == 0 loop: every loaded value has been consumed before the stage is handed back)
+        warp_arrive(FB_BAR(FB_IN_EMPTY + s) + (dep_zero(P.zero, acc[0][0].x, acc[0][1].x, acc[0][2].x, acc[0][3].x) |
+                                                 dep_zero(P.zero, acc[1][0].x, acc[1][1].x, acc[1][2].x, acc[1][3].x)),
+                    lane);
         uint32_t hi[2][4], lo[2][4];
 #pragma unroll
         for (int ty = 0; ty < 2; ++ty)
@@ -604,7 +623,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
     const bool ctc = P.part_max != nullptr;  // then bias_s holds one tile's BN values, reloaded per work item
     if (ctc) {
       if (P.ctc_two_pass)
-        ctc_epilogue_two_pass(P, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
+        ctc_epilogue_two_pass(P, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY), 0,
+                              P.ctc_groups == 2 ? 1 : 2, P.ctc_groups == 2);
       else
         ctc_epilogue_group(P, 0, 2, tid, lane_base, bias_s, FB_BAR(FB_ACC_FULL), FB_BAR(FB_ACC_EMPTY));
     } else {
@@ -908,6 +928,10 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   P.M = p.M, P.HW = 1;
   static const bool one_pass = getenv("OAR_DBG_CTC_EPI1") != nullptr;  // A/B switch
   P.ctc_two_pass = one_pass ? 0 : 1;
+  // A second epilogue group (warps 16-19 of the idle convert team, one column half each): 1.00 -> 0.81 ms per step.
+  // (Rounds 1 and 2 saw run-to-run differences with two groups; the cause was the early hand-back of the TMA stage in
+  // the convert loop -- dep_zero above, profiles/r2_ctc_two_group_bisect.txt -- which a faster epilogue merely exposed.)
+  static const bool one_group = getenv("OAR_CTC_GROUPS") && atoi(getenv("OAR_CTC_GROUPS")) == 1;
   P.in_bytes = 128 * 128, P.tap_bytes = 0, P.ns_in = 4;
   P.TH = P.TW = 0, P.tiles_h = P.tiles_w = 1, P.cols_in = 128;
   const size_t b_stage = (size_t)w.BN * 128;
@@ -916,6 +940,8 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   const int sm_count = m->ctx->sm_count;
   const size_t res_fixed = 2 * FB_ABUF + (size_t)w.nkb * b_stage + FB_CTRL_BYTES + 1024;
   P.b_resident = (!no_resident && w.nkb <= FB_MAX_IN && w.n_tiles <= sm_count && res_fixed + 2 * (size_t)P.in_bytes <= FB_SMEM_MAX) ? 1 : 0;
+  // two epilogue groups need the prologue-staged bias, i.e. one N tile per CTA (resident weights), and the two-pass form
+  P.ctc_groups = (P.b_resident && P.ctc_two_pass && !one_group) ? 2 : 1;
   const size_t fixed = P.b_resident ? res_fixed : 2 * FB_EP_TILE + 2 * FB_ABUF + 2 * b_stage + FB_CTRL_BYTES + 1024;
   while (P.ns_in > 2 && fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) --P.ns_in;
   if (fixed + (size_t)P.ns_in * P.in_bytes > FB_SMEM_MAX) return false;
