@@ -209,9 +209,13 @@ struct DetGroup {
 // Launches DB net -> DB post for one same-shape group; results land in pinned host memory once the streams are
 // synchronised.  With `post_lane` the post-process (threshold, labelling, border tracing, box geometry: latency-bound,
 // a fraction of the SMs) runs on the context's second lane behind an event, so it overlaps the NEXT group's network.
+// `ready` (optional): per image of the caller's list, the event after which its pixels are in HBM.  With uploads in
+// flight the network runs in two halves -- the second half's pages land while the first half is in the detector -- and
+// the post-process still sees ONE batch (an image's map does not depend on its batch mates, and the post-process is
+// latency-bound: two half-size passes would cost more than the copy that joins the halves).
 void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, const std::vector<int32_t>& src_h,
                       const std::vector<int32_t>& src_w, const oar_det_config& cfg, DetGroup& g, int comps_hint,
-                      bool timed, bool post_lane) {
+                      bool timed, bool post_lane, const std::vector<cudaEvent_t>* ready = nullptr) {
   oar_ctx* ctx = det->ctx;
   const int B = (int)g.members.size();
   std::vector<const uint8_t*> ptrs(B);
@@ -236,23 +240,39 @@ void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, cons
   out.boxes = ctx->arena.get<float>((size_t)B * mc * 8);
   out.scores = ctx->arena.get<float>((size_t)B * mc);
   out.counts = ctx->arena.get<int32_t>(B);
-  float* prob_keep = post_lane ? ctx->arena.get<float>((size_t)B * g.H * g.W) : nullptr;
+  static const int split_min = getenv("OAR_DET_SPLIT_MIN") ? atoi(getenv("OAR_DET_SPLIT_MIN")) : 16;  // 0 = never split
+  bool pending = false;  // pages of this group still on their way?
+  if (ready)
+    for (int i = 0; i < B; ++i) pending = pending || (*ready)[g.members[i]] != nullptr;
+  static const int split_parts = getenv("OAR_DET_SPLIT_PARTS") ? std::max(1, atoi(getenv("OAR_DET_SPLIT_PARTS"))) : 2;
+  const int halves = (pending && split_min > 0 && B >= split_min) ? std::min(split_parts, B) : 1;
+  const size_t plane = (size_t)g.H * g.W;
+  float* prob_keep = (post_lane || halves > 1) ? ctx->arena.get<float>((size_t)B * plane) : nullptr;
   auto mark = ctx->arena.mark();
-  const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data(), B);
-  // the network reads the u8 pages itself: NormalizeImage is folded into the stem convolution (engine.cu / fused_simt.cu)
-  Tensor in;
-  in.B = B, in.H = g.H, in.W = g.W, in.C = 3;
-  U8Input u8{};
-  u8.mode = 0, u8.table = d_table, u8.B = B, u8.H = g.H, u8.W = g.W, u8.table_aligned = aligned ? 1 : 0;
-  det_norm_coeffs(u8.src, u8.a, u8.b);
-  Tensor prob = model_forward(det, in, false, nullptr, &u8);
-  if (prob.B != B || prob.H != g.H || prob.W != g.W || prob.C != 1)
-    OAR_FAIL(OAR_E_MODEL, "detector output %dx%dx%dx%d does not match its %dx%d input", prob.B, prob.H, prob.W, prob.C,
-             g.H, g.W);
-  const float* prob_p = prob.p;
-  if (post_lane) {
-    OAR_CUDA(cudaMemcpyAsync(prob_keep, prob.p, (size_t)B * g.H * g.W * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-    prob_p = prob_keep;
+  const float* prob_p = nullptr;
+  for (int hf = 0; hf < halves; ++hf) {
+    const int b0 = hf * B / halves, nb = (hf + 1) * B / halves - b0;
+    if (ready)
+      for (int i = b0; i < b0 + nb; ++i)
+        if ((*ready)[g.members[i]]) OAR_CUDA(cudaStreamWaitEvent(ctx->stream, (*ready)[g.members[i]], 0));
+    const uint8_t** d_table = (const uint8_t**)to_device(ctx, (const uint8_t* const*)ptrs.data() + b0, nb);
+    // the network reads the u8 pages itself: NormalizeImage is folded into the stem convolution (engine.cu / fused_simt.cu)
+    Tensor in;
+    in.B = nb, in.H = g.H, in.W = g.W, in.C = 3;
+    U8Input u8{};
+    u8.mode = 0, u8.table = d_table, u8.B = nb, u8.H = g.H, u8.W = g.W, u8.table_aligned = aligned ? 1 : 0;
+    det_norm_coeffs(u8.src, u8.a, u8.b);
+    Tensor prob = model_forward(det, in, false, nullptr, &u8);
+    if (prob.B != nb || prob.H != g.H || prob.W != g.W || prob.C != 1)
+      OAR_FAIL(OAR_E_MODEL, "detector output %dx%dx%dx%d does not match its %dx%d input", prob.B, prob.H, prob.W, prob.C,
+               g.H, g.W);
+    prob_p = prob.p;
+    if (prob_keep) {
+      OAR_CUDA(cudaMemcpyAsync(prob_keep + (size_t)b0 * plane, prob.p, (size_t)nb * plane * sizeof(float),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+      prob_p = prob_keep;
+      if (halves > 1 && hf + 1 < halves) ctx->arena.release_to(mark);  // the next half reuses the activations (stream order)
+    }
   }
   if (timed) cudaEventRecord(g.e_net, ctx->stream);
   // post lane: the activations can go now (the kept copy of the map lives outside the mark); otherwise the post-process
@@ -393,10 +413,7 @@ void run_detection(oar_model* det, const std::vector<DevImage>& imgs, const oar_
     }
   }
   const bool post_lane = lanes && groups.size() >= 2;
-  for (auto& g : groups) {
-    for (int i : g.members) wait_for(i);
-    launch_det_group(det, resized, src_h, src_w, cfg, g, 0, timed, post_lane);
-  }
+  for (auto& g : groups) launch_det_group(det, resized, src_h, src_w, cfg, g, 0, timed, post_lane, ready);
   if (post_lane) {
     cudaEvent_t join = ctx->next_event();
     OAR_CUDA(cudaEventRecord(join, ctx->stream_aux));
