@@ -43,13 +43,14 @@ constexpr int CH_THREADS = 448;  // 4 epilogue + TMA + MMA + 8 convert warps
 constexpr int CH_EPI_THREADS = 128;
 constexpr int CH_WARP_TMA = 4, CH_WARP_MMA = 5, CH_WARP_C0 = 6;
 constexpr int CH_CWARPS = 8, CH_CTHREADS = CH_CWARPS * 32;
-constexpr int CH_MAX_IN = 4, CH_MAX_B = 6;
+constexpr int CH_MAX_IN = 4, CH_MAX_B = 12;
 constexpr uint32_t CH_EP_TILE = 128 * 128;
 constexpr size_t CH_SMEM_MAX = 227 * 1024;
-constexpr size_t CH_CTRL_BYTES = 256 + (512 + 32) * 4;
+constexpr uint32_t CH_BIAS_OFF = 384;  // mbarriers + TMEM slot below, the bias behind
+constexpr size_t CH_CTRL_BYTES = CH_BIAS_OFF + (512 + 32) * 4;
 
-enum { CB_IN_FULL = 0, CB_IN_EMPTY = 4, CB_B_FULL = 8, CB_B_EMPTY = 14, CB_A_FULL = 20, CB_A_EMPTY = 22, CB_ACC_FULL = 24,
-       CB_ACC_EMPTY = 26, CB_NBAR = 28 };
+enum { CB_IN_FULL = 0, CB_IN_EMPTY = 4, CB_B_FULL = 8, CB_B_EMPTY = 20, CB_A_FULL = 32, CB_A_EMPTY = 34, CB_ACC_FULL = 36,
+       CB_ACC_EMPTY = 38, CB_NBAR = 40 };
 
 struct ChParams {
   const uint4* wpk;
@@ -66,6 +67,10 @@ struct ChParams {
   uint32_t in_bytes, b_bytes, lbo_a;
   int ns_in, nb, ep_tiles;
   uint32_t off_in, off_a, off_b, off_ctrl;
+  // b_resident = 1: the weight ring holds every stage of an item (nb = ncb * taps / TPS) and is filled ONCE per CTA.  A
+  // narrow layer (the detector's 96 -> 24 convs: 108 KB of hi/lo weights) otherwise re-streams all of its weights from
+  // L2 for every 128-row tile -- more bytes than the tile's activations -- behind nine stage handshakes.
+  int b_resident;
 };
 
 __device__ __forceinline__ void ch_warp_arrive(uint32_t bar, int lane) {
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
       const uint32_t n_in = n_items * (uint32_t)P.ncb, n_b = n_in * (uint32_t)taps;
       const uint32_t one = P.b_bytes / (uint32_t)(P.n_tiles * P.TPS);  // one N tile's block of one tap
       const uint32_t n_st = (uint32_t)(taps / P.TPS);                  // weight stages per channel block
-      const uint32_t n_b2 = n_in * n_st;
+      const uint32_t n_b2 = P.b_resident ? (n_items ? (uint32_t)P.ncb * n_st : 0u) : n_in * n_st;
       const size_t nt_stride = (size_t)P.kh * P.ncb * P.kw * one;  // row-taps packing: [n tile][ky][cin block][kx] blocks
       uint32_t it_in = 0, it_b = 0;
       uint32_t s_in = 0, ph_in = 0, s_b = 0, ph_b = 0;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
           const uint32_t a_hi = (sbase + P.off_a + sa * a_buf) >> 4, a_lo = a_hi + (a_part >> 4);
           uint32_t row_shift = 0, kx = 0;  // the tap's rows start this many 16-byte rows into the tile
           for (int tap0 = 0; tap0 < taps; tap0 += P.TPS) {
-            mbar_wait_warp(CH_BAR(CB_B_FULL + sb), phb);
+            mbar_wait_warp(CH_BAR(CB_B_FULL + sb), P.b_resident ? 0u : phb);  // resident: filled once, phase 0 stays complete
             tc_fence_after();
             const uint32_t bst = (sbase + P.off_b + sb * P.b_bytes) >> 4;
             for (int tt = 0; tt < P.TPS; ++tt) {
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
                     umma_f16(d, al, bh, idesc, 1u);
                   }
                 }
-                if (tt == P.TPS - 1) umma_commit(CH_BAR(CB_B_EMPTY + sb));
+                if (tt == P.TPS - 1 && !P.b_resident) umma_commit(CH_BAR(CB_B_EMPTY + sb));
                 if (last_tap) {
                   umma_commit(CH_BAR(CB_A_EMPTY + sa));
                   if (last_cb) umma_commit(CH_BAR(CB_ACC_FULL + acc));
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
     // ------------------------------------------------------------------ epilogue (tid = accumulator row = TMEM lane)
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool affine = P.ps != 1.0f || P.pb != 0.0f;
-    float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + 256);
+    float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + CH_BIAS_OFF);
     for (int i = tid; i < P.n_tiles * P.BN + 32; i += CH_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
     named_bar_sync(1, CH_EPI_THREADS);
     const int y = tid / P.P, x = tid - y * P.P;
@@ -393,7 +398,14 @@ bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name) 
   // kernel's per-stage handshakes, not by its MMAs (timing bisect, OAR_DBG_HALO: 0.53 ms of 0.94 ms per launch remain
   // with MMAs, conversion and epilogue all switched off); three co-resident row-taps CTAs per SM do better there.
   static const bool force = getenv("OAR_DBG_HALO_ALL") != nullptr;
-  if (!force && w.n_tiles * w.BN < 64) return false;
+  // Resident weights (b_resident, round 2) remove the nine weight-stage handshakes and the L2 re-stream, and it is
+  // still slower there: 0.98 ms per launch against 0.63 for conv_rowtaps_tc on the 240 x 240 maps (18.5 k cycles per
+  // 120-pixel tile against an MMA issue floor of 7.3 k).  So narrow layers stay on the row-taps kernel unless
+  // OAR_HALO_NARROW=1.  (tools/microbench/tma_row_bench.cu rules the TMA unit out: 128-byte box rows stream at
+  // 6.1-6.8 TB/s once 60 KB are in flight per SM.)
+  static const bool no_narrow = !(getenv("OAR_HALO_NARROW") && atoi(getenv("OAR_HALO_NARROW")) == 1);
+  const bool narrow = w.n_tiles * w.BN < 64;
+  if (narrow && no_narrow && !force) return false;
   if ((size_t)w.n_tiles * w.BN + 32 > (CH_CTRL_BYTES - 256) / sizeof(float)) return false;
   if (p.M <= 0) return true;
   // a kernel of height 1 never mixes rows: all images stack into one tall image and tiles span several of them
@@ -435,6 +447,23 @@ bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name) 
   if (n_work > 0x7fffffffLL) return false;
   P.n_work = (int)n_work;
   const size_t a_bytes = 2 * 2 * 4 * (size_t)P.lbo_a;
+  // resident weights when every stage of an item fits beside two input stages
+  static const bool no_resident = getenv("OAR_DBG_HALO_STREAM") != nullptr;  // A/B switch
+  const int nb_res = P.ncb * (p.kh * p.kw / P.TPS);
+  P.b_resident = 0;
+  if (!no_resident && nb_res <= CH_MAX_B) {
+    for (P.ep_tiles = 2; P.ep_tiles >= 1 && !P.b_resident; --P.ep_tiles)
+      for (P.ns_in = 3; P.ns_in >= 2; --P.ns_in) {
+        const size_t need = (size_t)P.ep_tiles * CH_EP_TILE + a_bytes + CH_CTRL_BYTES + 1024 + 512 +
+                            (size_t)P.ns_in * P.in_bytes + (size_t)nb_res * P.b_bytes;
+        if (need <= CH_SMEM_MAX) {
+          P.b_resident = 1, P.nb = nb_res;
+          break;
+        }
+      }
+    if (P.b_resident) ++P.ep_tiles;  // the loop header stepped past the accepted value
+  }
+  if (!P.b_resident)
   for (P.ep_tiles = 2; P.ep_tiles >= 1; --P.ep_tiles) {
     const size_t fixed = (size_t)P.ep_tiles * CH_EP_TILE + a_bytes + CH_CTRL_BYTES + 1024;
     for (P.ns_in = 3; P.ns_in >= 2; --P.ns_in) {
@@ -444,7 +473,8 @@ bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name) 
     }
     if (P.nb >= 3) break;
   }
-  if (P.nb < 3 || P.ns_in < 2) return false;
+  if (!P.b_resident && (P.nb < 3 || P.ns_in < 2)) return false;
+  if (narrow && !P.b_resident && !force) return false;
   P.off_in = (uint32_t)P.ep_tiles * CH_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
   P.off_a = (P.off_a + 127u) & ~127u;
@@ -468,8 +498,8 @@ bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name) 
   ensure_max_dynamic_smem((const void*)conv_halo_tc, m->ctx->device, (int)CH_SMEM_MAX);
   static const bool dbg = getenv("OAR_DBG_TILES") != nullptr;
   if (dbg)
-    fprintf(stderr, "[halo] k=%dx%d B=%d %dx%d C=%d N=%d (%d x %d) chains %d -> tile %dx%d pitch %d stages in %d w %d x %d taps staging %d items %d smem %zu\n",
-            p.kh, p.kw, p.B, p.H, p.W, p.Cin, p.N, w.n_tiles, w.BN, P.KS, P.TH, P.TW, P.P, P.ns_in, P.nb, P.TPS, P.ep_tiles, P.n_work, smem);
+    fprintf(stderr, "[halo] k=%dx%d B=%d %dx%d C=%d N=%d (%d x %d) chains %d -> tile %dx%d pitch %d stages in %d w %d x %d taps resident %d staging %d items %d smem %zu\n",
+            p.kh, p.kw, p.B, p.H, p.W, p.Cin, p.N, w.n_tiles, w.BN, P.KS, P.TH, P.TW, P.P, P.ns_in, P.nb, P.TPS, P.b_resident, P.ep_tiles, P.n_work, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.Cin + (double)p.M * p.N));
   conv_halo_tc<<<grid, CH_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
