@@ -71,6 +71,15 @@ struct ChParams {
   // narrow layer (the detector's 96 -> 24 convs: 108 KB of hi/lo weights) otherwise re-streams all of its weights from
   // L2 for every 128-row tile -- more bytes than the tile's activations -- behind nine stage handshakes.
   int b_resident;
+  // fold = 1: a narrow 3 x 3 convolution run as a 3 x 1 one with 3 * fold_n output columns (column block kx = the
+  // weights of kernel column kx) on a tile whose pitch keeps two halo columns (P = TW + 2, a multiple of a warp or
+  // half of one).  D[r][kx * n + co] is then the partial sum of kernel column kx at box pixel r, and the output is
+  // out[r][co] = D[r][co] + D[r + 1][n + co] + D[r + 2][2n + co]: rows r + 1, r + 2 live in the neighbouring TMEM lanes =
+  // the neighbouring threads of the same warp, so the epilogue folds with two shuffles per channel and stores straight
+  // from registers.  A third of the MMAs and of the operand bytes of the tap-by-tap form.
+  int fold, fold_n;
+  float* out;
+  int out_ld, H, W;
 };
 
 __device__ __forceinline__ void ch_warp_arrive(uint32_t bar, int lane) {
@@ -276,7 +285,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool affine = P.ps != 1.0f || P.pb != 0.0f;
     float* bias_s = reinterpret_cast<float*>(smem + P.off_ctrl + CH_BIAS_OFF);
-    for (int i = tid; i < P.n_tiles * P.BN + 32; i += CH_EPI_THREADS) bias_s[i] = i < P.N ? __ldg(P.bias + i) : 0.0f;
+    const int n_bias = P.fold ? P.fold_n : P.N;  // fold: N counts the folded columns, the bias has fold_n entries
+    for (int i = tid; i < P.n_tiles * P.BN + 32; i += CH_EPI_THREADS) bias_s[i] = i < n_bias ? __ldg(P.bias + i) : 0.0f;
     named_bar_sync(1, CH_EPI_THREADS);
     const int y = tid / P.P, x = tid - y * P.P;
     const bool valid = y < P.TH && x < P.TW;
@@ -289,6 +299,46 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
       const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(CH_BAR(CB_ACC_FULL + acc), aph);
       tc_fence_after();
+      if (P.fold) {
+        constexpr int FN = 24;  // fold_n (checked by the host)
+        float v[80];
+        __syncwarp();
+#pragma unroll
+        for (int c16 = 0; c16 < 5; ++c16) tmem_ld16(lane_base + acc * 256u + (uint32_t)(c16 * 16), v + 16 * c16);
+        float o[FN];
+#pragma unroll
+        for (int co = 0; co < FN; ++co)
+          o[co] = v[co] + __shfl_down_sync(0xffffffffu, v[FN + co], 1) + __shfl_down_sync(0xffffffffu, v[2 * FN + co], 2);
+        const int oy = c2 + y, ox = c1 + x;
+        if (valid && oy < P.H && ox < P.W) {
+#pragma unroll
+          for (int co = 0; co < FN; ++co) o[co] += bias_s[co];
+          switch (P.act) {
+#define CH_ACT_CASE_F(A)                                     \
+  case A:                                                    \
+    _Pragma("unroll") for (int i = 0; i < FN; ++i) o[i] = act_t<A>(o[i]); \
+    break;
+            CH_ACT_CASE_F(ACT_RELU)
+            CH_ACT_CASE_F(ACT_HSWISH)
+            CH_ACT_CASE_F(ACT_SWISH)
+            CH_ACT_CASE_F(ACT_SIGMOID)
+            CH_ACT_CASE_F(ACT_HSIGMOID)
+            CH_ACT_CASE_F(ACT_GELU)
+#undef CH_ACT_CASE_F
+            default: break;
+          }
+          if (affine) {
+#pragma unroll
+            for (int i = 0; i < FN; ++i) o[i] = o[i] * P.ps + P.pb;
+          }
+          float4* dst = reinterpret_cast<float4*>(P.out + (((size_t)c3 * P.H + oy) * P.W + ox) * P.out_ld);
+#pragma unroll
+          for (int i = 0; i < FN / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        tc_fence_before();
+        ch_warp_arrive(CH_BAR(CB_ACC_EMPTY + acc), lane);
+        continue;
+      }
       for (int nt = 0; nt < P.n_tiles && !(P.dbg & 4); ++nt) {
         const int n_base = nt * P.BN;
         const uint32_t col0 = lane_base + acc * 256u + (uint32_t)(nt * P.KS * P.BN);
@@ -500,6 +550,70 @@ bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name) 
   if (dbg)
     fprintf(stderr, "[halo] k=%dx%d B=%d %dx%d C=%d N=%d (%d x %d) chains %d -> tile %dx%d pitch %d stages in %d w %d x %d taps resident %d staging %d items %d smem %zu\n",
             p.kh, p.kw, p.B, p.H, p.W, p.Cin, p.N, w.n_tiles, w.BN, P.KS, P.TH, P.TW, P.P, P.ns_in, P.nb, P.TPS, P.b_resident, P.ep_tiles, P.n_work, smem);
+  const int grid = std::min(P.n_work, m->ctx->sm_count);
+  Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.Cin + (double)p.M * p.N));
+  conv_halo_tc<<<grid, CH_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);
+  return true;
+}
+
+// Narrow 3 x 3 convolutions (Cout <= 32: the detector's 96 -> 24 neck / head convs) with the kernel columns folded
+// into N: see ChParams::fold.  false = shape not covered.
+bool tc_conv_fold(oar_model* m, int key, const ConvParams& p, const char* name) {
+  static const bool off = getenv("OAR_DBG_NOFOLD") != nullptr;  // A/B switch
+  if (off) return false;
+  TcState* st = static_cast<TcState*>(m->tc_state);
+  if (!st) return false;
+  auto it = st->wfold.find(key);
+  if (it == st->wfold.end()) return false;
+  const TcWeights& w = it->second;
+  if (p.mode != 0 || p.kh != 3 || p.kw != 3 || p.sh != 1 || p.sw != 1 || p.ph != 1 || p.pw != 1) return false;
+  if (p.N != 24 || w.N != 3 * p.N || w.n_tiles != 1 || w.BN != 80 || !w.rowtaps || w.kh != 3 || w.kw != 1) return false;
+  if ((p.Cin & 31) || p.Ho != p.H || p.Wo != p.W || (p.out_ld & 3) || (p.out_c_off & 3)) return false;
+  if ((((uintptr_t)p.in) & 15) || (((uintptr_t)(p.out + p.out_c_off)) & 15)) return false;
+  if (p.M <= 0) return true;
+  ChParams P{};
+  P.wpk = w.packed, P.bias = p.bias, P.act = p.act, P.ps = p.post_scale, P.pb = p.post_bias;
+  P.N = w.N, P.BN = w.BN, P.n_tiles = 1, P.ncb = p.Cin / 32, P.kh = 3, P.kw = 1;  // the MMA loop sees a 3 x 1 conv
+  P.fold = 1, P.fold_n = p.N, P.out = p.out + p.out_c_off, P.out_ld = p.out_ld, P.H = p.H, P.W = p.W;
+  // pitch 32 (one tile row per warp) or 16 (two): the two dropped columns of a row sit at a warp's / half-warp's end, so
+  // the shuffles never cross a row; the fewer tiles win
+  const long long t32 = (long long)cdiv(p.H, 4) * cdiv(p.W, 30), t16 = (long long)cdiv(p.H, 8) * cdiv(p.W, 14);
+  P.P = t32 <= t16 ? 32 : 16;
+  P.TW = P.P - 2, P.TH = 128 / P.P;
+  P.rows_box = (P.TH + 2) * P.P;
+  P.tiles_h = cdiv(p.H, P.TH), P.tiles_w = cdiv(p.W, P.TW);
+  P.ph = 1, P.pw = 1;
+  P.in_bytes = (uint32_t)P.rows_box * 128u;
+  P.TPS = 1, P.KS = 1, P.dbg = 0;
+  P.b_bytes = 128u * (uint32_t)w.BN;
+  P.lbo_a = (((uint32_t)std::max(P.rows_box + 1, 128 + 2 * P.P + 1) * 16u + 127u) & ~127u) + 32u;
+  const long long n_work = (long long)p.B * P.tiles_h * P.tiles_w;
+  if (n_work > 0x7fffffffLL) return false;
+  P.n_work = (int)n_work;
+  const size_t a_bytes = 2 * 2 * 4 * (size_t)P.lbo_a;
+  P.b_resident = 1, P.nb = P.ncb * 3, P.ep_tiles = 0;
+  if (P.nb > CH_MAX_B) return false;
+  for (P.ns_in = 3; P.ns_in >= 2; --P.ns_in)
+    if (a_bytes + CH_CTRL_BYTES + 1024 + 512 + (size_t)P.ns_in * P.in_bytes + (size_t)P.nb * P.b_bytes <= CH_SMEM_MAX) break;
+  if (P.ns_in < 2) return false;
+  P.off_in = 0;
+  P.off_a = (P.off_in + (uint32_t)P.ns_in * P.in_bytes + 127u) & ~127u;
+  P.off_b = (P.off_a + (uint32_t)a_bytes + 127u) & ~127u;
+  P.off_ctrl = (P.off_b + (uint32_t)P.nb * P.b_bytes + 127u) & ~127u;
+  if ((size_t)P.off_ctrl + CH_CTRL_BYTES + 1024 > CH_SMEM_MAX) return false;
+  CUtensorMap tm_in, tm_out;
+  memset(&tm_in, 0, sizeof(tm_in));
+  memset(&tm_out, 0, sizeof(tm_out));
+  cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * 4 * p.W, (cuuint64_t)p.Cin * 4 * p.W * p.H};
+  cuuint32_t box[4] = {32, (cuuint32_t)P.P, (cuuint32_t)(P.TH + 2), 1};
+  if (!ch_encode_map(&tm_in, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+  const size_t smem = std::max<size_t>((size_t)P.off_ctrl + CH_CTRL_BYTES + 1024, 120 * 1024);
+  ensure_max_dynamic_smem((const void*)conv_halo_tc, m->ctx->device, (int)CH_SMEM_MAX);
+  static const bool dbg = getenv("OAR_DBG_TILES") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[fold] 3x3 B=%d %dx%d C=%d N=%d -> tile %dx%d pitch %d stages in %d resident w %d items %d smem %zu\n", p.B, p.H,
+            p.W, p.Cin, p.N, P.TH, P.TW, P.P, P.ns_in, P.nb, P.n_work, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   Launch l(m->ctx, name, 2.0 * p.M * p.N * p.K, 4.0 * ((double)p.M * p.Cin + (double)p.M * p.N));
   conv_halo_tc<<<grid, CH_THREADS, smem, m->ctx->stream>>>(P, tm_in, tm_out);

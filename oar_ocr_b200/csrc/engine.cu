@@ -349,7 +349,7 @@ __device__ __forceinline__ void dw_tile(const float4* __restrict__ in4, const fl
 }
 
 template <int K, int SH, int SW, int TH, int TW, int ACT>
-__global__ void __launch_bounds__(128) dwconv_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(128, 4) dwconv_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int B, int H, int W, int C, int Ho, int Wo, float ps,
                                                            float pb, float* __restrict__ tile_sums) {
@@ -1268,6 +1268,7 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         p.mode = 0, p.cout = cout;
         if (m->engine >= 1 && try_stem_conv(ctx, p)) break;
         // engine 2: dense stride-1 k x k convolutions on the persistent TMA-halo kernel (conv_halo_tc.cu)
+        if (m->engine == 2 && kh == 3 && kw == 3 && tc_conv_fold(m, (int)oi * 2, p, "convkxk_tc")) break;
         if (m->engine == 2 && kh * kw > 1 && tc_conv_halo(m, (int)oi * 2, p, "convkxk_tc")) break;
         launch_gemm(m, (int)oi * 2, p, (kh == 1 && kw == 1) ? "conv1x1_simt" : "convkxk_simt",
                     (kh == 1 && kw == 1) ? "conv1x1_tc" : "convkxk_tc");

@@ -160,6 +160,7 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
 // Dense stride-1 k x k convolution (k <= 3, Cin % 32 == 0) on the persistent TMA-halo kernel (conv_halo_tc.cu); false ->
 // the caller uses tc_gemm (row-taps / im2col kernels)
 bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name);
+bool tc_conv_fold(oar_model* m, int key, const ConvParams& p, const char* name);  // narrow 3 x 3: kernel columns folded into N
 // CTC head (mode-2 ConvParams: part_* outputs) on the persistent kernel; false -> caller uses tc_gemm
 bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const char* name);
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,

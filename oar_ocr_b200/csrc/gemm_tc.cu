@@ -806,6 +806,16 @@ void tc_model_init(oar_model* m) {
         const bool rowtaps = kh * kw > 1 && sh == 1 && sw == 1 && (kh & 1) && (kw & 1) && ph == kh / 2 && pw == kw / 2 &&
                              kw <= RT_MAX_KW && cin % 32 == 0;
         st->w[(int)oi * 2] = rowtaps ? pack_weights_rowtaps(w0, op.p[7], kh, kw, cin) : pack_weights(w0, op.p[7], kh * kw * cin);
+        if (rowtaps && kh == 3 && kw == 3 && op.p[7] <= 32 && op.p[7] % 4 == 0) {
+          const int n = op.p[7];
+          std::vector<float> wf((size_t)3 * n * 3 * cin);  // [kx * n + co][ky][0][ci]
+          for (int co = 0; co < n; ++co)
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx)
+                for (int ci = 0; ci < cin; ++ci)
+                  wf[((size_t)(kx * n + co) * 3 + ky) * cin + ci] = w0[(size_t)co * 9 * cin + (size_t)(ky * 3 + kx) * cin + ci];
+          st->wfold[(int)oi * 2] = pack_weights_rowtaps(wf.data(), 3 * n, 3, 1, cin);
+        }
         // the fused depthwise->pointwise kernel (fused_tc.cu) streams 32-channel k-blocks: KC = 4 packing
         if (kh == 1 && kw == 1 && st->w[(int)oi * 2].KC != 4) st->wf[(int)oi * 2] = pack_weights(w0, op.p[7], cin, true);
         break;
@@ -848,6 +858,7 @@ void tc_model_free(oar_model* m) {
   if (!st) return;
   for (auto& kv : st->w) cudaFree(kv.second.packed);
   for (auto& kv : st->wf) cudaFree(kv.second.packed);
+  for (auto& kv : st->wfold) cudaFree(kv.second.packed);
   for (auto& kv : st->dwp) cudaFree(kv.second);
   delete st;
   m->tc_state = nullptr;

@@ -19,6 +19,9 @@ struct TcState {
   std::map<int, TcWeights> w;
   std::map<int, TcWeights> wf;  // KC = 4 copies for the fused kernel where `w` holds a KC = 8 packing
   std::map<int, float*> dwp;    // depthwise taps for the fused kernel: [k-block][K*K taps | bias][32 ch], zero padded
+  // narrow 3 x 3 convs with the kernel COLUMNS folded into N (conv_halo_tc.cu: fold mode): packed as a 3 x 1 convolution
+  // with 3 * Cout output channels, row kx * Cout + co = the weights of tap column kx
+  std::map<int, TcWeights> wfold;
 };
 
 // fp16 hi/lo split + packing into the shared-memory layout of the tcgen05 kernels (gemm_tc.cu)
