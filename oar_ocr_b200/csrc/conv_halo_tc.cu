@@ -198,6 +198,52 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
       // descriptor = constant upper half | (address >> 4) in the low 14 bits: one add per operand and MMA
       const uint64_t adesc0 = make_desc(0, P.lbo_a, 128), bdesc0 = make_desc(0, b_lbo, 128);
       const uint32_t a_j = P.lbo_a >> 3, b_j = b_lbo >> 3, b_lo_off = b_part >> 4;
+      if (P.fold) {
+        // Fold mode: everything about a tile's 54 MMAs is static -- three kernel rows x two k16 steps x (hi*hi, hi*lo,
+        // lo*hi) per channel block, weights resident -- so the loop below is three waits and three unrolled issue
+        // blocks per tile.  (The general loop spends ~150 instructions of uniform-register bookkeeping per tap: ncu put
+        // the MMA warp at ~1100 cycles per tap on this layer, the convert warps waiting on it 63 % of the time.)
+        for (int s2 = 0; s2 < P.nb; ++s2) mbar_wait_warp(CH_BAR(CB_B_FULL + s2), 0u);  // resident weights: once
+        tc_fence_after();
+        const uint32_t b16 = (sbase + P.off_b) >> 4, stage16 = P.b_bytes >> 4, pitch = (uint32_t)P.P;
+        const uint32_t ks = (uint32_t)P.KS, bn = (uint32_t)P.BN;
+        for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+          const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+          mbar_wait_warp(CH_BAR(CB_ACC_EMPTY + acc), aph ^ 1u);
+          const uint32_t d0 = tmem_base + acc * 256u;
+          for (int cb = 0; cb < P.ncb; ++cb, ++it_a) {
+            const uint32_t sa = it_a & 1u;
+            mbar_wait_warp(CH_BAR(CB_A_FULL + sa), (it_a >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = (sbase + P.off_a + sa * a_buf) >> 4, a_lo = a_hi + (a_part >> 4);
+            const uint32_t bcb = b16 + (uint32_t)(cb * 3) * stage16;
+            const bool last_cb = cb == P.ncb - 1;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint32_t g = (uint32_t)(ky * 2 + j);  // group index within the channel block
+                  const uint32_t chain = g % ks;
+                  const uint32_t accum = (cb == 0 && g < ks) ? 0u : 1u;  // a chain's first group starts it
+                  const uint32_t shift = (uint32_t)ky * pitch;          // kernel row ky: box rows r + ky * P
+                  const uint64_t ah = adesc0 + (uint64_t)(a_hi + j * a_j + shift);
+                  const uint64_t al = adesc0 + (uint64_t)(a_lo + j * a_j + shift);
+                  const uint32_t bb = bcb + (uint32_t)ky * stage16 + j * b_j;
+                  const uint64_t bh = bdesc0 + (uint64_t)bb, bl = bdesc0 + (uint64_t)(bb + b_lo_off);
+                  const uint32_t d = d0 + chain * bn;
+                  umma_f16(d, ah, bh, idesc, accum);
+                  umma_f16(d, ah, bl, idesc, 1u);
+                  umma_f16(d, al, bh, idesc, 1u);
+                }
+              }
+              umma_commit(CH_BAR(CB_A_EMPTY + sa));
+              if (last_cb) umma_commit(CH_BAR(CB_ACC_FULL + acc));
+            }
+            __syncwarp();
+          }
+        }
+      } else
       for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait_warp(CH_BAR(CB_ACC_EMPTY + acc), aph ^ 1u);
@@ -305,6 +351,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
         __syncwarp();
 #pragma unroll
         for (int c16 = 0; c16 < 5; ++c16) tmem_ld16(lane_base + acc * 256u + (uint32_t)(c16 * 16), v + 16 * c16);
+        for (int ch = 1; ch < P.KS; ++ch) {  // the other partial accumulators (independent MMA chains)
+#pragma unroll
+          for (int c16 = 0; c16 < 5; ++c16) {
+            float u[16];
+            tmem_ld16(lane_base + acc * 256u + (uint32_t)(ch * P.BN + c16 * 16), u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[16 * c16 + i] += u[i];
+          }
+        }
         float o[FN];
 #pragma unroll
         for (int co = 0; co < FN; ++co)
@@ -584,6 +639,8 @@ bool tc_conv_fold(oar_model* m, int key, const ConvParams& p, const char* name) 
   P.tiles_h = cdiv(p.H, P.TH), P.tiles_w = cdiv(p.W, P.TW);
   P.ph = 1, P.pw = 1;
   P.in_bytes = (uint32_t)P.rows_box * 128u;
+  // one accumulator per set: two partial accumulators (independent MMA chains, BN padded to 96) measured the same --
+  // tcgen05.mma into one accumulator is not a dependent chain (tools/microbench/mma_issue_bench.cu)
   P.TPS = 1, P.KS = 1, P.dbg = 0;
   P.b_bytes = 128u * (uint32_t)w.BN;
   P.lbo_a = (((uint32_t)std::max(P.rows_box + 1, 128 + 2 * P.P + 1) * 16u + 127u) & ~127u) + 32u;

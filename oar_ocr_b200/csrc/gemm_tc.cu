@@ -755,7 +755,7 @@ TcWeights pack_weights(const float* w, int N, int K, bool force_kc4) {
 }
 
 // weights of a stride-1 kh x kw conv for conv_rowtaps_tc: k-block = (ky, 32 input channels), all kw taps per stage
-static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int Cin) {
+static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int Cin, int force_bn = 0) {
   TcWeights t;
   t.N = N, t.K = kh * kw * Cin, t.rowtaps = true, t.kh = kh, t.kw = kw, t.KC = 4;
   // two stages of (A halo rows + kw weight taps) must fit the kernel's 200 KB: 2 * (2 * 4 * RT_LBO + kw * 128 * BN)
@@ -763,6 +763,7 @@ static TcWeights pack_weights_rowtaps(const float* w, int N, int kh, int kw, int
   t.n_tiles = (N + bn_cap - 1) / bn_cap;
   int per = (N + t.n_tiles - 1) / t.n_tiles;
   t.BN = t.n_tiles > 1 ? (per + 31) / 32 * 32 : std::max(16, (per + 15) / 16 * 16);
+  if (force_bn && t.n_tiles == 1 && force_bn >= t.BN) t.BN = force_bn;  // zero rows behind N
   const int ncb = Cin / 32;
   t.nkb = kh * ncb;
   const size_t part = (size_t)4 * t.BN * 8;  // halfs of one (hi or lo) part
