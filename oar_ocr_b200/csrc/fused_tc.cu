@@ -87,6 +87,7 @@ struct FbParams {
   int ctc_groups;    // CTC head: 2 = a second epilogue group (warps 16-19 of the idle convert team) reduces column half 1
   int one_team;      // K == 0: one convert team takes every k-block (the CTC head's arrangement)
   uint32_t zero;     // always 0, but only the host knows: lets an address depend on loaded data (dep_zero below)
+  int lean_mma;      // MMA warp: whole-warp loop with one elected issue block per k-block (OAR_FB_LEAN=0: lane-0 loop)
   int dbg_fence;     // bisecting aid: the producer fences (gpu scope + async proxy) before its first TMA load
 };
 
@@ -400,6 +401,51 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             if (P.share_a && ++nt_b < P.n_tiles) continue;
             nt_b = 0;
             if (++kb_b == P.nkb) kb_b = 0, t_b += gridDim.x;
+          }
+        }
+      }
+    }
+  } else if (warp == FB_WARP_MMA && P.lean_mma) {
+    // ------------------------------------------------------------------ MMA issuer, lean form: the whole warp runs the
+    // loop (values warp-uniform, in uniform registers), one elected lane polls each barrier and issues one block of
+    // 6 MMAs + commits per (k-block, N tile); descriptors are a constant upper half plus (address >> 4) adds.
+    {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t b_lbo = (uint32_t)P.BN * 16u, b_part = 4u * b_lbo;
+      const uint64_t adesc0 = make_desc(0, FB_LBO, 128), bdesc0 = make_desc(0, b_lbo, 128);
+      const uint32_t a0 = (sbase + P.off_a) >> 4, b0 = (sbase + P.off_b) >> 4;
+      const uint32_t a_j = FB_LBO >> 3, b_j = b_lbo >> 3, a_lo16 = FB_APART >> 4, b_lo16 = b_part >> 4, b_st16 = b_bytes >> 4;
+      const uint32_t nt_loop = P.share_a ? (uint32_t)P.n_tiles : 1u;
+      uint32_t it = 0, ti = 0, sb = 0, phb = 0;
+      for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t s = it & 1u;
+          mbar_wait_warp(FB_BAR(FB_A_FULL + s), (it >> 1) & 1u);
+          const uint32_t a_hi = a0 + s * (FB_ABUF >> 4), a_lo = a_hi + a_lo16;
+          for (uint32_t ntl = 0; ntl < nt_loop; ++ntl) {
+            const uint32_t v = ti * nt_loop + ntl, acc = v & 1u, aph = (v >> 1) & 1u;
+            if (kb == 0) mbar_wait_warp(FB_BAR(FB_ACC_EMPTY + acc), aph ^ 1u);
+            const uint32_t sbk = P.b_resident ? (uint32_t)kb : sb;
+            mbar_wait_warp(FB_BAR(FB_B_FULL + sbk), P.b_resident ? 0u : phb);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * 256u;
+            const uint32_t b_hi = b0 + sbk * b_st16, b_lo = b_hi + b_lo16;
+            const bool last = kb == P.nkb - 1, last_nt = ntl + 1 == nt_loop;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t ah = adesc0 + (uint64_t)(a_hi + j * a_j), al = adesc0 + (uint64_t)(a_lo + j * a_j);
+                const uint64_t bh = bdesc0 + (uint64_t)(b_hi + j * b_j), bl = bdesc0 + (uint64_t)(b_lo + j * b_j);
+                umma_f16(d, ah, bh, idesc, (kb | j) ? 1u : 0u);
+                umma_f16(d, ah, bl, idesc, 1u);
+                umma_f16(d, al, bh, idesc, 1u);
+              }
+              if (!P.b_resident) umma_commit(FB_BAR(FB_B_EMPTY + sbk));
+              if (last) umma_commit(FB_BAR(FB_ACC_FULL + acc));
+              if (last_nt) umma_commit(FB_BAR(FB_AB_EMPTY + s));
+            }
+            __syncwarp();
+            if (!P.b_resident && ++sb == (uint32_t)P.nb) sb = 0, phb ^= 1u;
           }
         }
       }
@@ -876,6 +922,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
     if (!encode_map(&tm_out, f.out + f.out_c_off, 4, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   }
   P.n_work = P.share_a ? n_sp : n_sp * w->n_tiles;
+  static const int lean = getenv("OAR_FB_LEAN") ? atoi(getenv("OAR_FB_LEAN")) : 1;
+  P.lean_mma = lean;
   if (f.k == 0) P.ep_tiles = 2;
   static const int dbg_one_team = getenv("OAR_DBG_FB_ONE_TEAM") ? atoi(getenv("OAR_DBG_FB_ONE_TEAM")) : 0;
   static const int dbg_ep = getenv("OAR_DBG_FB_EP") ? atoi(getenv("OAR_DBG_FB_EP")) : 0;
@@ -926,6 +974,8 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   // faster on this layer but showed rare run-to-run differences in the softmax statistics under host-side jitter --
   // 17 of 300 stress iterations, synccheck clean, racecheck inconclusive -- and was removed in round 2: DESIGN.md 5.2.)
   P.M = p.M, P.HW = 1;
+  static const int lean = getenv("OAR_FB_LEAN") ? atoi(getenv("OAR_FB_LEAN")) : 1;
+  P.lean_mma = lean;
   static const bool one_pass = getenv("OAR_DBG_CTC_EPI1") != nullptr;  // A/B switch
   P.ctc_two_pass = one_pass ? 0 : 1;
   // A second epilogue group (warps 16-19 of the idle convert team, one column half each): 1.00 -> 0.81 ms per step.
