@@ -88,6 +88,7 @@ struct FbParams {
   int one_team;      // K == 0: one convert team takes every k-block (the CTC head's arrangement)
   uint32_t zero;     // always 0, but only the host knows: lets an address depend on loaded data (dep_zero below)
   int lean_mma;      // MMA warp: whole-warp loop with one elected issue block per k-block (OAR_FB_LEAN=0: lane-0 loop)
+  int poll1;         // one polling lane per warp in the convert / depthwise / epilogue waits (OAR_FB_POLL1=0: all lanes)
   int dbg_fence;     // bisecting aid: the producer fences (gpu scope + async proxy) before its first TMA load
 };
 
@@ -115,6 +116,17 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // the arrive wait (register scoreboard) for the loads that produced the values.
 __device__ __forceinline__ uint32_t dep_zero(uint32_t zero, float a, float b, float c, float d) {
   return (__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c) | __float_as_uint(d)) & zero;
+}
+
+// Waits of a converged warp outside the single-thread roles: every lane polls (default), or one elected lane polls and
+// the others park at the warp barrier (OAR_FB_POLL1=1).  Measured on B200: the one-lane form is SLOWER here (3x3 blocks
+// 5.74 -> 6.29 ms, 5x5 blocks 4.69 -> 5.60 ms per step): these waits sit on the critical path of a k-block hand-off and
+// the elect + warp barrier behind the poll costs more than 32 lanes on the barrier word do.
+__device__ __forceinline__ void mbar_wait_sel(int poll1, uint32_t bar, uint32_t parity) {
+  if (poll1)
+    mbar_wait_warp(bar, parity);
+  else
+    mbar_wait(bar, parity);
 }
 
 // x = hi + lo in fp16, two channels packed per 32-bit word
@@ -150,7 +162,7 @@ __device__ __forceinline__ void ctc_epilogue_group(const FbParams& P, int group,
       bias_g[i] = n < P.N ? __ldg(P.bias + n) : 0.0f;
     }
     named_bar_sync(1 + group, FB_EPI_THREADS);
-    mbar_wait(acc_full0 + 8u * acc, aph);
+    mbar_wait_sel(P.poll1, acc_full0 + 8u * acc, aph);
     tc_fence_after();
 #pragma unroll 1
     for (int h = 0; h < n_halves; ++h) {
@@ -241,7 +253,7 @@ __device__ __forceinline__ void ctc_epilogue_two_pass(const FbParams& P, int gti
       }
       named_bar_sync(1, FB_EPI_THREADS);
     }
-    mbar_wait(acc_full0 + 8u * acc, aph);
+    mbar_wait_sel(P.poll1, acc_full0 + 8u * acc, aph);
     tc_fence_after();
 #pragma unroll 1
     for (int half = half0; half < half0 + n_halves; ++half) {
@@ -532,11 +544,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         // team has seen item it - 1 (it had then also seen every older item of its own).
         // (with an even number of stages every stage belongs to one team for good, and no handshake is needed)
         if (!ctc && (P.ns_in & 1)) {
-          if (it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
-          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+          if (it >= 1) mbar_wait_sel(P.poll1, FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
+          mbar_wait_sel(P.poll1, FB_BAR(FB_IN_FULL + s), ph);
           warp_arrive(FB_BAR(FB_SEEN + team), lane);
         } else {
-          mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+          mbar_wait_sel(P.poll1, FB_BAR(FB_IN_FULL + s), ph);
         }
         const uint8_t* src = smem + P.off_in + s * stage_bytes + q * 16;
         float4 x[4];
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           split2(x[j].x, x[j].y, hi[j][0], lo[j][0]);
           split2(x[j].z, x[j].w, hi[j][1], lo[j][1]);
         }
-        mbar_wait(FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
         uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -589,8 +601,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
         // observe box arrivals strictly in item order across the two teams (see the K == 0 loop)
         const bool handshake = (P.ns_in & 1) != 0;  // even ring: each stage has one owner team, plain parity waits do
-        if (handshake && it >= 1) mbar_wait(FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
-        mbar_wait(FB_BAR(FB_IN_FULL + s), ph);
+        if (handshake && it >= 1) mbar_wait_sel(P.poll1, FB_BAR(FB_SEEN + (team ^ 1)), ((it - 1) >> 1) & 1u);
+        mbar_wait_sel(P.poll1, FB_BAR(FB_IN_FULL + s), ph);
         if (handshake) warp_arrive(FB_BAR(FB_SEEN + team), lane);
         const uint8_t* stage = smem + P.off_in + s * stage_bytes;
         // taps [ky*K+kx][32 ch] and bias [32 ch] of this k-block sit behind the box; each is read once per thread,
@@ -645,7 +657,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             if (affine) v.x = v.x * P.dw_ps + P.dw_pb, v.y = v.y * P.dw_ps + P.dw_pb;
             split2(v.x, v.y, hi[ty][tx], lo[ty][tx]);
           }
-        mbar_wait(FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
         if (active) {
           uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
 #pragma unroll
@@ -688,7 +700,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
         c1 = tw * P.TW, c2 = (r % P.tiles_h) * P.TH, c3 = r / P.tiles_h;
       }
       const uint32_t acc = vi & 1u, aph = (vi >> 1) & 1u;
-      mbar_wait(FB_BAR(FB_ACC_FULL + acc), aph);
+      mbar_wait_sel(P.poll1, FB_BAR(FB_ACC_FULL + acc), aph);
       tc_fence_after();
       const int n_base = nt * P.BN;
       for (int c0 = 0; c0 < P.BN && n_base + c0 < P.N; c0 += 32, ++nstore) {
@@ -923,7 +935,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   }
   P.n_work = P.share_a ? n_sp : n_sp * w->n_tiles;
   static const int lean = getenv("OAR_FB_LEAN") ? atoi(getenv("OAR_FB_LEAN")) : 1;
-  P.lean_mma = lean;
+  static const int poll1 = getenv("OAR_FB_POLL1") ? atoi(getenv("OAR_FB_POLL1")) : 0;
+  P.lean_mma = lean, P.poll1 = poll1;
   if (f.k == 0) P.ep_tiles = 2;
   static const int dbg_one_team = getenv("OAR_DBG_FB_ONE_TEAM") ? atoi(getenv("OAR_DBG_FB_ONE_TEAM")) : 0;
   static const int dbg_ep = getenv("OAR_DBG_FB_EP") ? atoi(getenv("OAR_DBG_FB_EP")) : 0;
@@ -975,7 +988,8 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   // 17 of 300 stress iterations, synccheck clean, racecheck inconclusive -- and was removed in round 2: DESIGN.md 5.2.)
   P.M = p.M, P.HW = 1;
   static const int lean = getenv("OAR_FB_LEAN") ? atoi(getenv("OAR_FB_LEAN")) : 1;
-  P.lean_mma = lean;
+  static const int poll1 = getenv("OAR_FB_POLL1") ? atoi(getenv("OAR_FB_POLL1")) : 0;
+  P.lean_mma = lean, P.poll1 = poll1;
   static const bool one_pass = getenv("OAR_DBG_CTC_EPI1") != nullptr;  // A/B switch
   P.ctc_two_pass = one_pass ? 0 : 1;
   // A second epilogue group (warps 16-19 of the idle convert team, one column half each): 1.00 -> 0.81 ms per step.
