@@ -47,8 +47,8 @@ constexpr int FB_MAX_IN = 4;
 constexpr size_t FB_SMEM_MAX = 227 * 1024;
 constexpr size_t FB_CTRL_BYTES = 256 + (512 + 32) * 4;  // mbarriers + TMEM slot, then the 1x1 conv bias
 
-enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_B_EMPTY = 12, FB_A_FULL = 16, FB_AB_EMPTY = 18, FB_ACC_FULL = 20,
-       FB_ACC_EMPTY = 22, FB_SEEN = 24, FB_NBAR = 26 };  // AB_EMPTY: the A buffer of a k-block has been consumed
+enum { FB_IN_FULL = 0, FB_IN_EMPTY = 4, FB_B_FULL = 8, FB_B_EMPTY = 12, FB_A_FULL = 16, FB_AB_EMPTY = 19, FB_ACC_FULL = 22,
+       FB_ACC_EMPTY = 24, FB_SEEN = 26, FB_NBAR = 28 };  // AB_EMPTY: the A buffer of a k-block has been consumed
 
 struct FbParams {
   const float* dw_pk;  // [k-block][K*K taps | bias][32 channels], zero padded: rides along with the activation box
@@ -88,6 +88,8 @@ struct FbParams {
   int one_team;      // K == 0: one convert team takes every k-block (the CTC head's arrangement)
   uint32_t zero;     // always 0, but only the host knows: lets an address depend on loaded data (dep_zero below)
   int lean_mma;      // MMA warp: whole-warp loop with one elected issue block per k-block (OAR_FB_LEAN=0: lane-0 loop)
+  int na;            // A operand buffers (2 or 3): k-block it lives in buffer it % na.  A third buffer takes the MMA's
+                     // completion off the hand-off path: a team writing k-block it needs the MMAs of it - 3 done, not it - 2
   int poll1;         // one polling lane per warp in the convert / depthwise / epilogue waits (OAR_FB_POLL1=0: all lanes)
   int dbg_fence;     // bisecting aid: the producer fences (gpu scope + async proxy) before its first TMA load
 };
@@ -346,6 +348,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       mbar_init(FB_BAR(FB_ACC_EMPTY + i), FB_EPI_WARPS * (P.ctc_groups == 2 ? 2 : 1));
       mbar_init(FB_BAR(FB_SEEN + i), FB_CWARPS);
     }
+    mbar_init(FB_BAR(FB_A_FULL + 2), FB_CWARPS);
+    mbar_init(FB_BAR(FB_AB_EMPTY + 2), 1);
     fence_mbar_init();
   }
   if (warp == FB_WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -428,11 +432,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       const uint32_t a0 = (sbase + P.off_a) >> 4, b0 = (sbase + P.off_b) >> 4;
       const uint32_t a_j = FB_LBO >> 3, b_j = b_lbo >> 3, a_lo16 = FB_APART >> 4, b_lo16 = b_part >> 4, b_st16 = b_bytes >> 4;
       const uint32_t nt_loop = P.share_a ? (uint32_t)P.n_tiles : 1u;
-      uint32_t it = 0, ti = 0, sb = 0, phb = 0;
+      uint32_t it = 0, ti = 0, sb = 0, phb = 0, sA = 0, phA = 0;
       for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          const uint32_t s = it & 1u;
-          mbar_wait_warp(FB_BAR(FB_A_FULL + s), (it >> 1) & 1u);
+          const uint32_t s = sA;
+          mbar_wait_warp(FB_BAR(FB_A_FULL + s), phA);
+          if (++sA == (uint32_t)P.na) sA = 0, phA ^= 1u;
           const uint32_t a_hi = a0 + s * (FB_ABUF >> 4), a_lo = a_hi + a_lo16;
           for (uint32_t ntl = 0; ntl < nt_loop; ++ntl) {
             const uint32_t v = ti * nt_loop + ntl, acc = v & 1u, aph = (v >> 1) & 1u;
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       uint32_t it = 0, it_b = 0, ti = 0;
       for (int t = blockIdx.x; t < P.n_work; t += gridDim.x, ++ti) {
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+          const uint32_t s = it % (uint32_t)P.na, ph = (it / (uint32_t)P.na) & 1u;
           mbar_wait(FB_BAR(FB_A_FULL + s), ph);
           const uint32_t a_hi = sbase + P.off_a + s * FB_ABUF, a_lo = a_hi + FB_APART;
           for (uint32_t ntl = 0; ntl < nt_loop; ++ntl, ++it_b) {
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
       const int r0 = 8 * (ct >> 6) + 4 * ((ct >> 3) & 1) + ((ct >> 4) & 3);
       const uint32_t a_off = (uint32_t)(q >> 1) * FB_LBO + (uint32_t)(q & 1) * 8u;
       for (uint32_t it = it0; it < n_items; it += it_step) {
-        const uint32_t sa = it & 1u;
+        const uint32_t sa = it % (uint32_t)P.na;
         const int kb = (int)(it % (uint32_t)P.nkb);
         // squeeze-excite multipliers of this thread's (row, channel quad)s, requested before the wait for the tile
         float4 sc[4];
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
           split2(x[j].x, x[j].y, hi[j][0], lo[j][0]);
           split2(x[j].z, x[j].w, hi[j][1], lo[j][1]);
         }
-        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it / (uint32_t)P.na) & 1u) ^ 1u);
         uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -596,8 +601,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
                              (uint32_t)((2 * pgy) * P.TW + 4 * pgx) * 16u;
       const bool hsw = P.dw_act == ACT_HSWISH;
       const bool affine = P.dw_ps != 1.0f || P.dw_pb != 0.0f;
-      const uint32_t sa = (uint32_t)team;
       for (uint32_t it = (uint32_t)team; it < n_items; it += 2) {
+        const uint32_t sa = it % (uint32_t)P.na;
         const uint32_t s = it % (uint32_t)P.ns_in, ph = (it / (uint32_t)P.ns_in) & 1u;
         // observe box arrivals strictly in item order across the two teams (see the K == 0 loop)
         const bool handshake = (P.ns_in & 1) != 0;  // even ring: each stage has one owner team, plain parity waits do
@@ -657,7 +662,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) lcblock_tc(const FbParams P, co
             if (affine) v.x = v.x * P.dw_ps + P.dw_pb, v.y = v.y * P.dw_ps + P.dw_pb;
             split2(v.x, v.y, hi[ty][tx], lo[ty][tx]);
           }
-        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_sel(P.poll1, FB_BAR(FB_AB_EMPTY + sa), ((it / (uint32_t)P.na) & 1u) ^ 1u);
         if (active) {
           uint8_t* ab = smem + P.off_a + sa * FB_ABUF + a_off;
 #pragma unroll
@@ -948,7 +953,12 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   if (f.k == 0 && dbg_ep == 1) P.ep_tiles = 1;
   P.off_in = (uint32_t)P.ep_tiles * FB_EP_TILE;
   P.off_a = P.off_in + (uint32_t)P.ns_in * (P.in_bytes + P.tap_bytes);
-  P.off_b = P.off_a + 2 * FB_ABUF;
+  // a third A buffer (OAR_FB_NA=3, where it fits beside the minimum weight ring) measured exactly equal to two on every
+  // block class (3x3 blocks 5.74 vs 5.75 ms per step): the depthwise warps' wait for a free A buffer -- 48 % of their
+  // samples in ncu -- is where the pipeline's slack shows, not what bounds it
+  static const int want_na = getenv("OAR_FB_NA") ? atoi(getenv("OAR_FB_NA")) : 2;
+  P.na = (want_na >= 3 && (size_t)P.off_a + 3 * FB_ABUF + (size_t)min_b * b_stage + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ? 3 : 2;
+  P.off_b = P.off_a + (uint32_t)P.na * FB_ABUF;
   // whatever shared memory is left goes to the weight ring (up to 4 stages): a k-block of weights is an L2 round trip
   P.nb = min_b;
   while (P.nb < 4 && (size_t)P.off_b + (size_t)(P.nb + 1) * b_stage + FB_CTRL_BYTES + 1024 <= FB_SMEM_MAX) ++P.nb;
@@ -959,8 +969,8 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
   ensure_max_dynamic_smem((const void*)kern, m->ctx->device, (int)FB_SMEM_MAX);
   static const bool dbg_tiles = getenv("OAR_DBG_TILES") != nullptr;
   if (dbg_tiles)
-    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d share %d smem %zu\n",
-            f.k, f.sh, f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.nb, P.n_work, P.share_a, smem);
+    fprintf(stderr, "[fused] k=%d s=%dx%d B=%d %dx%d C=%d N=%d -> tile %dx%d stages %d staging %d wstages %d items %d share %d abufs %d smem %zu\n",
+            f.k, f.sh, f.sw, f.B, f.Ho, f.Wo, f.C, f.N, P.TH, P.TW, P.ns_in, P.ep_tiles, P.nb, P.n_work, P.share_a, P.na, smem);
   const int grid = std::min(P.n_work, m->ctx->sm_count);
   const double flops = 2.0 * M * f.N * f.C + 2.0 * M * f.C * f.k * f.k;
   const double bytes = 4.0 * ((double)f.B * f.H * f.W * f.C + (double)M * f.N);
@@ -1020,6 +1030,7 @@ bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const ch
   P.ep_tiles = 2;
   P.off_in = 0;  // the CTC epilogue stores nothing through the staging tiles
   P.off_a = P.off_in + (uint32_t)P.ns_in * P.in_bytes;
+  P.na = 2;
   P.off_b = P.off_a + 2 * FB_ABUF;
   P.nb = 2;
   if (P.b_resident) {
