@@ -602,26 +602,36 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 }
 
 // out[b,y,x,:] = a[b,y,x,:] + up[b,y/s,x/s,:]      grid (cdiv(W*C4, 256), H, B): one division per thread
+// `gate` (optional, [B][C]): a is the INPUT of a residual squeeze-excite whose apply pass was skipped -- a + a * gate is
+// formed here with se_apply_kernel's expression (same rounding), so the gated tensor never makes its own trip through HBM
 __global__ void upadd_kernel(const float* __restrict__ a, const float* __restrict__ up, float* __restrict__ o, int H,
-                             int W, int C4, int s) {
+                             int W, int C4, int s, const float* __restrict__ gate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W * C4) return;
   const int x = i / C4, c4 = i - x * C4;
   const int y = blockIdx.y, b = blockIdx.z;
   const size_t idx = ((size_t)b * H + y) * W * C4 + i;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(a) + idx);
+  float4 v = __ldg(reinterpret_cast<const float4*>(a) + idx);
+  if (gate) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gate) + (size_t)b * C4 + c4);
+    v.x = v.x + v.x * g.x, v.y = v.y + v.y * g.y, v.z = v.z + v.z * g.z, v.w = v.w + v.w * g.w;
+  }
   const float4 u = __ldg(reinterpret_cast<const float4*>(up) + (((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4);
   reinterpret_cast<float4*>(o)[idx] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
 }
 
 // out[b,y,x,c_off + c] = in[b,y/s,x/s,c]   (H,W = output dims)      grid (cdiv(W*C4, 256), H, B)
 __global__ void upsample_into_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C4, int s,
-                                     int ld4, int coff4) {
+                                     int ld4, int coff4, const float* __restrict__ gate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= W * C4) return;
   const int x = i / C4, c4 = i - x * C4;
   const int y = blockIdx.y, b = blockIdx.z;
-  const float4 u = __ldg(reinterpret_cast<const float4*>(in) + (((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4);
+  float4 u = __ldg(reinterpret_cast<const float4*>(in) + (((size_t)b * (H / s) + y / s) * (W / s) + x / s) * C4 + c4);
+  if (gate) {  // residual squeeze-excite folded in (see upadd_kernel)
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gate) + (size_t)b * C4 + c4);
+    u.x = u.x + u.x * g.x, u.y = u.y + u.y * g.y, u.z = u.z + u.z * g.z, u.w = u.w + u.w * g.w;
+  }
   reinterpret_cast<float4*>(out)[(((size_t)b * H + y) * W + x) * ld4 + coff4 + c4] = u;
 }
 
@@ -1159,6 +1169,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
     int tiles;
   };
   std::map<int, TileSums> tile_sums;  // tensor id -> per-tile channel sums left behind by the depthwise kernel
+  // tensor id -> gate of a residual squeeze-excite whose apply pass was left to its only consumer (upadd / upsample)
+  std::map<int, const float*> lazy_gate;
+  static const bool no_lazy_se = getenv("OAR_DBG_NOLAZYSE") != nullptr;  // A/B switch
   auto se_scale = [&](const OpRec& op, const Tensor& a) -> float* {
     const int c = op.p[0], cm = op.p[1], HW = a.H * a.W;
     // pool either the tensor itself or, when its producer left per-tile sums, those (1/8 .. 1/4 of the bytes)
@@ -1338,6 +1351,22 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
             continue;
           }
         }
+        // engine >= 1: a residual squeeze-excite read by exactly one upadd (as its full-resolution operand) or one
+        // upsample-into-concat is applied by that kernel (RSEFPN: three 96-channel maps and four 24-channel ones)
+        if (m->engine >= 1 && residual && uses[op.out] == 1 && !no_lazy_se && op.out != m->n_tensors - 1) {
+          bool lazy = false;
+          for (size_t oj = oi + 1; oj < m->ops.size() && !lazy; ++oj) {
+            const OpRec& cn = m->ops[oj];
+            if (cn.in0 == op.out) lazy = cn.type == OP_UPADD || cn.type == OP_UPSAMPLE;
+            if (cn.in0 == op.out || cn.in1 == op.out) break;
+          }
+          if (lazy) {
+            t[op.out] = a;  // the consumer reads the un-gated tensor and the gate
+            lazy_gate[op.out] = scale;
+            last = a;
+            break;
+          }
+        }
         Tensor& o = ensure(op.out, a.B, a.H, a.W, c);
         {
           if (a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "se op %zu: batch too large for one launch", oi);
@@ -1364,7 +1393,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         Launch l(ctx, "upadd", (double)a.numel(), 8.0 * a.numel() + 4.0 * b.numel());
         if (a.H > 65535 || a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "upadd op %zu: tensor too tall for one launch", oi);
         (void)n4;
-        upadd_kernel<<<dim3(cdiv((long long)a.W * (a.C / 4), 256), a.H, a.B), 256, 0, st>>>(a.p, b.p, o.p, a.H, a.W, a.C / 4, s);
+        auto lg = lazy_gate.find(op.in0);
+        upadd_kernel<<<dim3(cdiv((long long)a.W * (a.C / 4), 256), a.H, a.B), 256, 0, st>>>(
+            a.p, b.p, o.p, a.H, a.W, a.C / 4, s, lg == lazy_gate.end() ? nullptr : lg->second);
         break;
       }
       case OP_UPSAMPLE: {
@@ -1375,8 +1406,9 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         size_t n4 = (size_t)a.B * o.H * o.W * (a.C / 4);
         Launch l(ctx, "upsample_into", 0, 4.0 * a.numel() + 16.0 * n4);
         if (o.H > 65535 || a.B > 65535) OAR_FAIL(OAR_E_UNSUPPORTED, "upsample op %zu: tensor too tall for one launch", oi);
-        upsample_into_kernel<<<dim3(cdiv((long long)o.W * (a.C / 4), 256), o.H, a.B), 256, 0, st>>>(a.p, o.p, o.H, o.W, a.C / 4, s,
-                                                                                              ctot / 4, coff / 4);
+        auto lg = lazy_gate.find(op.in0);
+        upsample_into_kernel<<<dim3(cdiv((long long)o.W * (a.C / 4), 256), o.H, a.B), 256, 0, st>>>(
+            a.p, o.p, o.H, o.W, a.C / 4, s, ctot / 4, coff / 4, lg == lazy_gate.end() ? nullptr : lg->second);
         break;
       }
       case OP_AVGPOOL: {
