@@ -179,12 +179,15 @@ __global__ void __launch_bounds__(128) deconv_pair_kernel(const float* __restric
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
                                                           const float* __restrict__ b2, float* __restrict__ out, int H,
                                                           int W, int n_items, int segs, int act1, int act2) {
-  __shared__ __align__(16) float w1s[4 * CIN * CMID];  // [dy][dx][ci][co]
+  // [dy][dx][ci][co]; each (dy, dx) block is padded by 4 floats: the lanes of a warp read at TWO addresses (dx = 0 / 1),
+  // CIN * CMID floats apart = the same banks -- ncu: 45 % of the kernel's shared-memory wavefronts were bank conflicts
+  constexpr int W1Q = CIN * CMID + 4;
+  __shared__ __align__(16) float w1s[4 * W1Q];
   __shared__ __align__(16) float b1s[CMID];
   __shared__ __align__(16) float2 w2s[2 * CMID];  // [ey][co] -> (ex = 0, ex = 1)
   for (int i = threadIdx.x; i < 4 * CIN * CMID; i += blockDim.x) {
     const int co = i % CMID, ci = (i / CMID) % CIN, q = i / (CMID * CIN);
-    w1s[i] = w1[((size_t)q * CMID + co) * CIN + ci];
+    w1s[q * W1Q + ci * CMID + co] = w1[((size_t)q * CMID + co) * CIN + ci];
   }
   for (int i = threadIdx.x; i < CMID; i += blockDim.x) b1s[i] = b1[i];
   for (int i = threadIdx.x; i < 2 * CMID; i += blockDim.x) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(128) deconv_pair_kernel(const float* __restric
       float2 h[2][CMID / 2];
 #pragma unroll
       for (int q = 0; q < CMID / 2; ++q) h[0][q] = h[1][q] = make_float2(b1s[2 * q], b1s[2 * q + 1]);
-      const float4* wr = reinterpret_cast<const float4*>(w1s + (size_t)(dy * 2 + dx) * CIN * CMID);
+      const float4* wr = reinterpret_cast<const float4*>(w1s + (size_t)(dy * 2 + dx) * W1Q);
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
         const float2 xa = make_float2(xin[0][ci], xin[0][ci]), xb = make_float2(xin[1][ci], xin[1][ci]);
