@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
     }))
 
 
-def kernel_roofline(ctx, step_fn, extra=None, P=2):
+def kernel_roofline(ctx, step_fn, extra=None, P=2, workload="pipeline"):
     """Profiles P more steps with CUDA events around every launch; returns (roofline dict of the dominant kernel,
     per-kernel table).  Algorithmic bytes / FLOPs per launch are the ones the library states at each launch site
     (DESIGN.md 5); *_tc kernels are charged TC_PASSES fp16 MMAs per algorithmic FLOP."""
@@ -201,7 +201,8 @@ def kernel_roofline(ctx, step_fn, extra=None, P=2):
         with open(tpath) as f:
             tj = json.load(f)
         tk = tj.get("kernels", {}).get(top["name"])
-        if tk:
+        # a capture may be scoped to the workloads whose launches of that kernel it represents
+        if tk and (not tk.get("workloads") or workload in tk["workloads"]):
             # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
             # (profiles/traffic.json, keyed by kernel), scaled to the average launch of this run by the capture's
             # traffic / algorithmic ratio
@@ -441,7 +442,7 @@ def run_rec512(args, rank, local_rank, world):
     e_ms, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
     e2e_value = world * B * args.steps / (e_ms / 1000.0)
     T = last["r"]["T"]
-    roof, kernels = kernel_roofline(ctx, step_dev) if rank == 0 else (None, [])
+    roof, kernels = kernel_roofline(ctx, step_dev, workload="rec512") if rank == 0 else (None, [])
     cpu_base = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -599,7 +600,7 @@ def run_layout(args, rank, local_rank, world):
     value = world * B * args.steps / (ms / 1000.0)
     e_ms, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
     e2e_value = world * B * args.steps / (e_ms / 1000.0)
-    roof, kernels = kernel_roofline(ctx, step_dev) if rank == 0 else (None, [])
+    roof, kernels = kernel_roofline(ctx, step_dev, workload="layout") if rank == 0 else (None, [])
     cpu_base = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
