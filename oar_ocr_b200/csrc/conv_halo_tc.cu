@@ -260,41 +260,53 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_tc(const ChParams P, 
             mbar_wait_warp(CH_BAR(CB_B_FULL + sb), P.b_resident ? 0u : phb);  // resident: filled once, phase 0 stays complete
             tc_fence_after();
             const uint32_t bst = (sbase + P.off_b + sb * P.b_bytes) >> 4;
-            for (int tt = 0; tt < P.TPS; ++tt) {
-              const uint32_t b0 = bst + (uint32_t)tt * one16;
-              // the two k16 groups of this tap: their chains and accumulate flags, computed by every lane (uniform)
-              uint32_t col[2], accum[2];
+            // One elected issue block per weight stage (TPS <= 3 taps): every lane does the cheap bookkeeping -- chains,
+            // accumulate flags, row shifts -- into registers first, then one lane issues all of the stage's MMAs and
+            // commits.  (An elect + warp barrier per tap left the MMA warp at ~1100 cycles per tap in ncu.)
+            uint32_t col[3][2], accum[3][2], shift[3];
+            const bool last_cb = cb == P.ncb - 1;
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                col[j] = chain_col, accum[j] = fresh_left ? 0u : 1u;
-                if (fresh_left) --fresh_left;
-                chain_col += (uint32_t)P.BN;
-                if (chain_col == ks_cols) chain_col = 0;
-              }
-              const bool last_tap = tap0 + tt == taps - 1, last_cb = cb == P.ncb - 1;
-              if (elect_one_sync()) {
+            for (int tt = 0; tt < 3; ++tt) {
+              if (tt < P.TPS) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                  const uint64_t ah = adesc0 + (uint64_t)(a_hi + j * a_j + row_shift);
-                  const uint64_t al = adesc0 + (uint64_t)(a_lo + j * a_j + row_shift);
-                  uint32_t bb = b0 + j * b_j, d = d0 + col[j];
-                  for (int nt = 0; nt < P.n_tiles && !(P.dbg & 1); ++nt, bb += nt16, d += nt_cols) {
-                    const uint64_t bh = bdesc0 + (uint64_t)bb, bl = bdesc0 + (uint64_t)(bb + b_lo_off);
-                    umma_f16(d, ah, bh, idesc, accum[j]);
-                    umma_f16(d, ah, bl, idesc, 1u);
-                    umma_f16(d, al, bh, idesc, 1u);
+                  col[tt][j] = chain_col, accum[tt][j] = fresh_left ? 0u : 1u;
+                  if (fresh_left) --fresh_left;
+                  chain_col += (uint32_t)P.BN;
+                  if (chain_col == ks_cols) chain_col = 0;
+                }
+                shift[tt] = row_shift;
+                ++row_shift;
+                if (++kx == (uint32_t)P.kw) kx = 0, row_shift += (uint32_t)(P.P - P.kw);
+              }
+            }
+            const bool last_stage = tap0 + P.TPS == taps;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int tt = 0; tt < 3; ++tt) {
+                if (tt < P.TPS) {
+                  const uint32_t b0 = bst + (uint32_t)tt * one16;
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint64_t ah = adesc0 + (uint64_t)(a_hi + j * a_j + shift[tt]);
+                    const uint64_t al = adesc0 + (uint64_t)(a_lo + j * a_j + shift[tt]);
+                    uint32_t bb = b0 + j * b_j, d = d0 + col[tt][j];
+                    for (int nt = 0; nt < P.n_tiles && !(P.dbg & 1); ++nt, bb += nt16, d += nt_cols) {
+                      const uint64_t bh = bdesc0 + (uint64_t)bb, bl = bdesc0 + (uint64_t)(bb + b_lo_off);
+                      umma_f16(d, ah, bh, idesc, accum[tt][j]);
+                      umma_f16(d, ah, bl, idesc, 1u);
+                      umma_f16(d, al, bh, idesc, 1u);
+                    }
                   }
                 }
-                if (tt == P.TPS - 1 && !P.b_resident) umma_commit(CH_BAR(CB_B_EMPTY + sb));
-                if (last_tap) {
-                  umma_commit(CH_BAR(CB_A_EMPTY + sa));
-                  if (last_cb) umma_commit(CH_BAR(CB_ACC_FULL + acc));
-                }
               }
-              __syncwarp();
-              ++row_shift;
-              if (++kx == (uint32_t)P.kw) kx = 0, row_shift += (uint32_t)(P.P - P.kw);
+              if (!P.b_resident) umma_commit(CH_BAR(CB_B_EMPTY + sb));
+              if (last_stage) {
+                umma_commit(CH_BAR(CB_A_EMPTY + sa));
+                if (last_cb) umma_commit(CH_BAR(CB_ACC_FULL + acc));
+              }
             }
+            __syncwarp();
             if (++sb == (uint32_t)P.nb) sb = 0, phb ^= 1u;
           }
         }
