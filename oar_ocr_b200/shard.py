@@ -176,8 +176,12 @@ class GpuStages:
     def detect(self, images):
         from . import ffi
         out = []
-        for boxes, _scores in self.ocr.det.det_run(images, self.ocr.det_cfg.to_ffi()):
-            out.append(ffi.sort_quad_boxes(boxes)[0] if len(boxes) else boxes)
+        # chunks of image_batch_size, as TextDetectionAdapter::execute batches them (a page's boxes do not depend on
+        # its batch mates; the chunking bounds the activation arena by the configured batch, not by the rank's block)
+        step = max(1, int(getattr(self.ocr, "image_batch_size", 0) or len(images) or 1))
+        for s0 in range(0, len(images), step):
+            for boxes, _scores in self.ocr.det.det_run(images[s0:s0 + step], self.ocr.det_cfg.to_ffi()):
+                out.append(ffi.sort_quad_boxes(boxes)[0] if len(boxes) else boxes)
         return out
 
     def crop(self, image, boxes):
