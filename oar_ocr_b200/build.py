@@ -21,6 +21,7 @@ SOURCES = {
     "gemm_tc.cu": [],
     "fused_tc.cu": [],
     "conv_halo_tc.cu": [],
+    "dw_tma.cu": [],
     "fused_simt.cu": [],
     "jpeg_ingest.cu": [],
     "prepost.cu": ["-fmad=false"],

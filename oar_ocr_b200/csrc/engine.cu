@@ -1322,6 +1322,13 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
         int n_tiles = 0;
         if (m->engine == 2 && oi + 1 < m->ops.size() && m->ops[oi + 1].type == OP_SE && m->ops[oi + 1].in0 == op.out)
           tsums = ctx->arena.get<float>((size_t)a.B * Ho * ((Wo + 3) / 4) * c);  // bound: 1 x 4 pixel tiles
+        // engine 2: TMA-staged shared-memory tiles (dw_tma.cu); its tile sums are per 128-pixel tile
+        if (m->engine == 2 && kh == kw && ph == kh / 2 && pw == kw / 2 &&
+            tc_dw_tma(m, (int)oi, a.p, o.p, a.B, a.H, a.W, c, Ho, Wo, kh, sh, sw, op.p[7], op.f[0], op.f[1], tsums, &n_tiles,
+                      "dwconv")) {
+          if (tsums) tile_sums[op.out] = TileSums{tsums, n_tiles};
+          break;
+        }
         Launch l(ctx, "dwconv", 2.0 * o.numel() * kh * kw, 4.0 * (a.numel() + o.numel()));
         if (kh != kw || !try_dw_tiled(st, a.p, m->w(op, 0), m->w(op, 1), o.p, a.B, a.H, a.W, c, Ho, Wo, kh, sh, sw, ph, pw,
                                       op.p[7], op.f[0], op.f[1], tsums, &n_tiles))

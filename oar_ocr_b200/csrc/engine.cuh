@@ -161,6 +161,10 @@ bool tc_fused_block(oar_model* m, int key, const FusedBlock& f, const char* name
 // the caller uses tc_gemm (row-taps / im2col kernels)
 bool tc_conv_halo(oar_model* m, int key, const ConvParams& p, const char* name);
 bool tc_conv_fold(oar_model* m, int key, const ConvParams& p, const char* name);  // narrow 3 x 3: kernel columns folded into N
+// Stand-alone depthwise k x k conv on TMA-staged shared-memory tiles (dw_tma.cu); false -> the register-tiled kernel.
+// tile_sums (optional): per-(image, tile) channel sums for the squeeze-excite pool, *n_tiles = tiles per image
+bool tc_dw_tma(oar_model* m, int dw_key, const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int sh,
+               int sw, int act, float ps, float pb, float* tile_sums, int* n_tiles, const char* name);
 // CTC head (mode-2 ConvParams: part_* outputs) on the persistent kernel; false -> caller uses tc_gemm
 bool tc_ctc_head_persistent(oar_model* m, int key, const ConvParams& p, const char* name);
 void launch_ctc_combine(oar_ctx* ctx, const float* part_max, const int32_t* part_idx, const float* part_sum, size_t rows,
