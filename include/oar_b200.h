@@ -78,6 +78,9 @@ const char* oar_last_error(void);
 int32_t oar_version(void);
 /* number of kernel launches issued by this library on the calling process so far */
 int64_t oar_launch_count(void);
+/* number of host-visible submissions among them: a kernel launched directly counts one, a replayed CUDA graph of a
+ * network's layer list (one per detector / recogniser batch after its shape has been seen twice) counts one */
+int64_t oar_submit_count(void);
 
 /* ---- context / model lifetime -------------------------------------------
  * replaces OrtInfer::new / from_config + Session::builder().commit_from_memory

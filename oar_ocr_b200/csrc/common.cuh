@@ -19,6 +19,9 @@ namespace oar {
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[1024];
 extern std::atomic<long long> g_launches;  // contexts on different GPUs launch concurrently
+// host-visible submissions: a kernel launched directly counts one, a replayed CUDA graph (engine.cu: model_forward)
+// counts one however many kernels it holds -- those still count in g_launches
+extern std::atomic<long long> g_submits;
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); safe to call from concurrent contexts
 void ensure_max_dynamic_smem(const void* kernel, int device, int bytes);
 
@@ -50,9 +53,12 @@ struct Arena {
   };
   std::vector<Slab> slabs;
   size_t min_slab = (size_t)256 << 20;
+  size_t total_alloc = 0;  // bytes handed out since creation (never decreases): the footprint of a graph walk is a difference
+  bool fixed = false;      // the private arena of a captured CUDA graph: one slab sized beforehand, growing is an error
   void* alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes == 0) bytes = 256;
+    total_alloc += bytes;
     for (auto& s : slabs) {
       if (s.used + bytes <= s.cap) {
         void* p = s.base + s.used;
@@ -60,6 +66,7 @@ struct Arena {
         return p;
       }
     }
+    if (fixed) OAR_FAIL(OAR_E_CUDA, "graph arena exhausted (%zu more bytes wanted)", bytes);
     size_t cap = bytes > min_slab ? bytes : min_slab;
     char* p = nullptr;
     OAR_CUDA(cudaMalloc(&p, cap));
@@ -118,6 +125,9 @@ struct oar_ctx {
   oar::Arena arena_aux;
   cudaStream_t stream_copy = nullptr;  // page uploads of a pipeline call: overlap the detector (capi.cu: stage_upload)
   std::mutex mu;
+  bool capturing = false;       // a model_forward walk is being recorded into a CUDA graph (engine.cu)
+  long long captured = 0;       // kernels recorded by the capture in progress
+  void* graph_cache = nullptr;  // engine.cu: captured layer lists per (model, lane, shape)
   bool profile = false;
   std::vector<oar::ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
@@ -144,7 +154,12 @@ struct Launch {
   oar_ctx* ctx;
   int idx = -1;
   Launch(oar_ctx* c, const char* name, double flops = 0, double bytes = 0) : ctx(c) {
-    ++g_launches;
+    if (c->capturing) {
+      ++c->captured;  // recorded, not launched: counted when (and every time) the graph is
+    } else {
+      ++g_launches;
+      ++g_submits;
+    }
     if (c->profile) {
       ProfRec r{name, c->next_event(), c->next_event(), flops, bytes};
       cudaEventRecord(r.e0, c->stream);

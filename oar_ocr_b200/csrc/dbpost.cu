@@ -199,46 +199,50 @@ struct ContourRec {
   int len;
 };
 
-__constant__ int c_RX[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
-__constant__ int c_RY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
-// (dx+1) + 3*(dy+1) -> ring index
-__constant__ int c_DIR[9] = {1, 2, 3, 0, -1, 4, 7, 6, 5};
+// The 8-neighbour ring, clockwise from West: RX = {-1,-1,0,1,1,1,0,-1}, RY = {0,-1,-1,-1,0,1,1,1}, and its inverse
+// DIR[(dx+1) + 3*(dy+1)] = {1,2,3,0,-,4,7,6,5}.  Packed into immediates (2 / 2 / 3 bits per entry) and read with a
+// shift: as __constant__ arrays the eight probing lanes index them with eight different values, which the constant
+// cache serialises -- twice per border pixel, on the one serial chain of the whole post-process.
+__device__ __forceinline__ int ring_dx(int d) { return (int)((0x1a90u >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int ring_dy(int d) { return (int)((0xa901u >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int ring_of(int dx, int dy) { return (int)((0x5de00d1u >> (3 * ((dx + 1) + 3 * (dy + 1)))) & 7u); }
 
 // Follows one border from (sx,sy) inside the window `st` (bw x bh pixels, row stride `stride`, window origin
 // (ox,oy) in image coordinates; Wimg = image width for the right-edge rule).  start_dir = ring index of the adjacent
 // zero pixel.  All 32 lanes execute; lanes 0..7 probe.  When pts != nullptr, writes points (image coordinates) and
-// the visited marks (2 = +nbd, 3 = -nbd).  Returns the number of points.
+// the visited marks (2 = +nbd, 3 = -nbd); only the first `cap` points are stored.  Returns the number of points.
+// (The marks are idempotent: walking a border again leaves them as they are.)
 __device__ int follow_border(uint8_t* st, int stride, int bw, int bh, int ox, int oy, int Wimg, int sx, int sy,
-                             int start_dir, short2* pts, int lane) {
+                             int start_dir, short2* pts, int cap, int lane) {
   auto nonzero = [&](int x, int y) -> bool {
     return x >= 0 && y >= 0 && x < bw && y < bh && st[(size_t)y * stride + x] != 0;
   };
   int k = lane & 7;
   int d = (start_dir + k) & 7;
-  bool hit = (lane < 8) && nonzero(sx + c_RX[d], sy + c_RY[d]);
+  bool hit = (lane < 8) && nonzero(sx + ring_dx(d), sy + ring_dy(d));
   unsigned mask = __ballot_sync(0xffffffffu, hit) & 0xffu;
   if (!mask) {
     if (pts && lane == 0) {
-      pts[0] = make_short2((short)(sx + ox), (short)(sy + oy));
+      if (cap > 0) pts[0] = make_short2((short)(sx + ox), (short)(sy + oy));
       st[(size_t)sy * stride + sx] = 3;
     }
     return 1;
   }
   int k1 = __ffs(mask) - 1;
   int d1 = (start_dir + k1) & 7;
-  int p1x = sx + c_RX[d1], p1y = sy + c_RY[d1];
+  int p1x = sx + ring_dx(d1), p1y = sy + ring_dy(d1);
   int p2x = p1x, p2y = p1y, p3x = sx, p3y = sy;
   int n = 0;
   for (;;) {
-    if (pts && lane == 0) pts[n] = make_short2((short)(p3x + ox), (short)(p3y + oy));
+    if (pts && lane == 0 && n < cap) pts[n] = make_short2((short)(p3x + ox), (short)(p3y + oy));
     ++n;
-    int front = c_DIR[(p2x - p3x + 1) + 3 * (p2y - p3y + 1)];
+    int front = ring_of(p2x - p3x, p2y - p3y);
     int dk = (front - 1 - k + 16) & 7;  // k = 7 -> front itself (examined last)
-    bool h2 = (lane < 8) && nonzero(p3x + c_RX[dk], p3y + c_RY[dk]);
+    bool h2 = (lane < 8) && nonzero(p3x + ring_dx(dk), p3y + ring_dy(dk));
     unsigned m2 = __ballot_sync(0xffffffffu, h2) & 0xffu;
     int k4 = __ffs(m2) - 1;  // never -1: p2 is non-zero
     int d4 = (front - 1 - k4 + 16) & 7;
-    int p4x = p3x + c_RX[d4], p4y = p3y + c_RY[d4];
+    int p4x = p3x + ring_dx(d4), p4y = p3y + ring_dy(d4);
     int kE = (front - 5 + 16) & 7;  // the probe index that looks East
     bool right_edge = kE < k4;
     if (pts && lane == 0) {
@@ -263,13 +267,19 @@ __device__ int follow_border(uint8_t* st, int stride, int bw, int bh, int ox, in
 // state map directly (warp 0 only).
 constexpr int TRACE_TILE_BYTES = 16 * 1024;  // ~14 blocks per SM: the walk is serial per component, concurrency is what counts (48 KB tiles measured 1.6x slower)
 constexpr int TRACE_THREADS = 128;
+// Every border is walked ONCE: the walk is the serial chain of the post-process (one dependent probe per border pixel),
+// and its length is only known at its end, so the points go to a per-block staging run first and are copied into the
+// pool -- whose offset needs the length -- by the whole warp afterwards.  A border longer than the staging run (rare:
+// > 8192 points) is walked a second time straight into the pool.
+constexpr int TRACE_STAGE_POINTS = 8192;
 
 __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
     uint8_t* __restrict__ state, const int32_t* __restrict__ lab, const Comp* __restrict__ comps,
     const int* __restrict__ n_comps, int comp_cap, int H, int W, short2* __restrict__ pool,
     unsigned long long* __restrict__ pool_used, unsigned long long pool_cap, ContourRec* __restrict__ recs,
-    int* __restrict__ n_recs, int rec_cap, int* __restrict__ err) {
+    int* __restrict__ n_recs, int rec_cap, int* __restrict__ err, short2* __restrict__ stage) {
   extern __shared__ uint8_t tile[];
+  short2* my_stage = stage + (size_t)blockIdx.x * TRACE_STAGE_POINTS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = min(*n_comps, comp_cap);
   for (int comp = blockIdx.x; comp < nc; comp += gridDim.x) {
@@ -330,7 +340,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
             else if ((s == 1 || s == 2) && cx + 1 < W && st[lo + 1] == 0)
               start_dir = 4;  // hole border, adjacent = East
             if (start_dir < 0) continue;
-            const int n = follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, nullptr, lane);
+            const int n = follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, my_stage,
+                                        TRACE_STAGE_POINTS, lane);
             unsigned long long off = 0;
             int ri = -1;
             if (lane == 0) {
@@ -344,7 +355,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
               failed = true;
               break;
             }
-            follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, lane);
+            if (n <= TRACE_STAGE_POINTS) {
+              __syncwarp();  // lane 0's staged points are visible to the warp
+              for (int i = lane; i < n; i += 32) pool[off + i] = my_stage[i];
+            } else {
+              follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, 0x7fffffff, lane);
+            }
             if (lane == 0) recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
             __syncwarp();
           }
@@ -1030,9 +1046,11 @@ DbPostStatus db_postprocess_device(oar_ctx* ctx, const float* pred, int B, int H
   // surplus warps exit.  (Typical pages have tens of components per image.)
   int launch_comps = std::min(comp_cap, std::max(launch_comps_hint, std::max(4096, B * 2048)));
   {
+    const int trace_blocks = std::min(launch_comps, 8192);
+    short2* stage = A.get<short2>((size_t)trace_blocks * TRACE_STAGE_POINTS);
     Launch l(ctx, "db_trace_borders", 0, 0);
-    db_trace_kernel<<<std::min(launch_comps, 8192), TRACE_THREADS, TRACE_TILE_BYTES, st>>>(
-        state, lab, comps, n_comps, launch_comps, H, W, pool, pool_used, pool_cap, recs, n_recs, rec_cap, err);
+    db_trace_kernel<<<trace_blocks, TRACE_THREADS, TRACE_TILE_BYTES, st>>>(
+        state, lab, comps, n_comps, launch_comps, H, W, pool, pool_used, pool_cap, recs, n_recs, rec_cap, err, stage);
   }
   // sort contour records into discovery order
   int sort_n = std::min(rec_cap, launch_comps * 2);

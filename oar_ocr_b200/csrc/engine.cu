@@ -12,6 +12,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <tuple>
 
 namespace oar {
 
@@ -1127,7 +1128,7 @@ void op_attention(oar_model* m, int oi, const float* x, const float* x_qk, int B
 
 static inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
-Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc, const U8Input* u8) {
+static Tensor model_forward_eager(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc, const U8Input* u8) {
   oar_ctx* ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   std::vector<Tensor> t(m->n_tensors);
@@ -1593,6 +1594,224 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
   }
   OAR_CUDA(cudaGetLastError());
   return last;
+}
+
+// ---------------------------------------------------------------------------
+// CUDA graphs over the layer list
+// ---------------------------------------------------------------------------
+// The reference hands a batch to ONNX Runtime once per batch (ort_infer_execution.rs:121-306: one session.run); the
+// walk above turns that batch into ~100 launches whose grids, tensor maps and pointers depend on nothing but the
+// model, the engine and the batch's shape.  So the walk is recorded once per shape and launch lane and replayed.
+//
+// What makes the recording replayable:
+//  * activations come from the graph's OWN arena (one slab, sized by the eager walk that precedes the capture: the
+//    allocation sequence of a walk is a function of the key), so every pointer baked into a kernel node stays valid;
+//  * the only pointer that changes from call to call is the u8 input table (page pointers / crop jobs): it is copied
+//    into a fixed slot of the graph's arena in front of every launch, and the stem kernel reads it from there;
+//  * the launch lane (stream) is part of the key: the two recognition lanes may run the same shape concurrently, and a
+//    graph (its executable and its activations) must not overlap itself.
+// The outputs live in the graph's arena until the next walk with the same key on the same lane; every caller consumes
+// them in stream order on that lane (capi.cu: post-process / CTC decode / the copy that joins detector halves).
+namespace {
+
+struct GraphKey {
+  uint64_t uid;
+  cudaStream_t st;
+  int engine, B, H, W, flags;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(uid, st, engine, B, H, W, flags) < std::tie(o.uid, o.st, o.engine, o.B, o.H, o.W, o.flags);
+  }
+};
+
+struct GraphEntry {
+  int seen = 0;          // eager walks so far (the capture happens on the second sighting of a key)
+  int failures = 0;      // captures that did not work out; after two the key stays eager
+  size_t footprint = 0;  // bytes the eager walk took from the arena
+  Arena arena;           // fixed single slab: input slot + activations
+  cudaGraphExec_t exec = nullptr;
+  void* d_in = nullptr;
+  size_t in_bytes = 0;
+  Tensor out;
+  CtcOut ctc;
+  long long n_kernels = 0;
+  uint64_t last_use = 0;
+};
+
+struct GraphCache {
+  std::map<GraphKey, GraphEntry> entries;
+  uint64_t tick = 0;
+};
+
+void release_entry(GraphEntry& e) {
+  if (e.exec) cudaGraphExecDestroy(e.exec);
+  e.exec = nullptr;
+  e.arena.release();
+}
+
+size_t graph_bytes(const GraphCache& c) {
+  size_t n = 0;
+  for (auto& kv : c.entries)
+    for (auto& s : kv.second.arena.slabs) n += s.cap;
+  return n;
+}
+
+// least recently used captured graph other than `keep`; false when there is none
+bool evict_one(oar_ctx* ctx, GraphCache& c, const GraphEntry* keep) {
+  GraphEntry* victim = nullptr;
+  for (auto& kv : c.entries)
+    if (&kv.second != keep && kv.second.exec && (!victim || kv.second.last_use < victim->last_use)) victim = &kv.second;
+  if (!victim) return false;
+  // nothing of the victim may be in flight: both lanes are drained (rare: only under memory pressure)
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
+  release_entry(*victim);
+  victim->seen = 1;  // it may be captured again when it comes back
+  return true;
+}
+
+bool graph_safe(oar_model* m) {
+  if (m->graph_safe < 0) {
+    m->graph_safe = 1;
+    // sine positions of the layout encoder's attention are uploaded from pinned staging inside the walk
+    for (const OpRec& o : m->ops)
+      if (o.type == OP_ATTN && o.p[2] == 1) m->graph_safe = 0;
+  }
+  return m->graph_safe == 1;
+}
+
+}  // namespace
+
+void graph_cache_free(oar_ctx* ctx) {
+  GraphCache* c = static_cast<GraphCache*>(ctx->graph_cache);
+  if (!c) return;
+  for (auto& kv : c->entries) release_entry(kv.second);
+  delete c;
+  ctx->graph_cache = nullptr;
+}
+
+void graph_cache_drop_model(oar_ctx* ctx, uint64_t uid) {
+  GraphCache* c = static_cast<GraphCache*>(ctx->graph_cache);
+  if (!c) return;
+  for (auto it = c->entries.begin(); it != c->entries.end();) {
+    if (it->first.uid == uid) {
+      release_entry(it->second);
+      it = c->entries.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut* ctc, const U8Input* u8) {
+  oar_ctx* ctx = m->ctx;
+  static const int graphs_on = getenv("OAR_GRAPHS") ? atoi(getenv("OAR_GRAPHS")) : 1;
+  // at most this much HBM in graph arenas (MiB; default 48 GiB of the part's 180), and at least OAR_GRAPH_FREE_MB left
+  static const size_t max_bytes = (size_t)(getenv("OAR_GRAPH_MAX_MB") ? atoll(getenv("OAR_GRAPH_MAX_MB")) : 48 * 1024) << 20;
+  static const size_t keep_free = (size_t)(getenv("OAR_GRAPH_FREE_MB") ? atoll(getenv("OAR_GRAPH_FREE_MB")) : 16 * 1024) << 20;
+  static const bool dump_ctc = getenv("OAR_DBG_DUMP_CTC") != nullptr;  // that aid synchronises inside the walk
+  if (!graphs_on || ctx->profile || ctx->capturing || !u8 || input.p || m->engine < 1 || dump_ctc || !graph_safe(m))
+    return model_forward_eager(m, input, want_probs, ctc, u8);
+  if (u8->B <= 0 || (u8->mode == 0 ? (const void*)u8->table : (const void*)u8->jobs) == nullptr)
+    return model_forward_eager(m, input, want_probs, ctc, u8);
+
+  if (!ctx->graph_cache) ctx->graph_cache = new GraphCache();
+  GraphCache& cache = *static_cast<GraphCache*>(ctx->graph_cache);
+  cudaStream_t st = ctx->stream;
+  const GraphKey key{m->uid, st, m->engine, u8->B, u8->H, u8->W,
+                     (want_probs ? 1 : 0) | (ctc ? 2 : 0) | (u8->mode << 2) | (u8->table_aligned ? 8 : 0) | ((u8->src[0] & 3) << 4)};
+  GraphEntry& e = cache.entries[key];
+  e.last_use = ++cache.tick;
+  const void* src = u8->mode == 0 ? (const void*)u8->table : (const void*)u8->jobs;
+
+  if (e.exec) {  // ---- replay
+    OAR_CUDA(cudaMemcpyAsync(e.d_in, src, e.in_bytes, cudaMemcpyDeviceToDevice, st));
+    OAR_CUDA(cudaGraphLaunch(e.exec, st));
+    g_launches += e.n_kernels;
+    ++g_submits;
+    if (ctc) *ctc = e.ctc;
+    return e.out;
+  }
+  if (e.seen == 0 || e.failures >= 2) {  // ---- first sighting: eager, and learn the footprint
+    const size_t a0 = ctx->arena.total_alloc;
+    Tensor r = model_forward_eager(m, input, want_probs, ctc, u8);
+    e.footprint = ctx->arena.total_alloc - a0;
+    e.seen = 1;
+    return r;
+  }
+
+  // ---- second sighting: record the walk into a graph over a private arena, then launch it
+  const size_t in_bytes = u8->mode == 0 ? (size_t)u8->B * sizeof(const uint8_t*) : (size_t)u8->B * sizeof(CrnnJob);
+  const size_t cap = e.footprint + ((in_bytes + 255) & ~(size_t)255) + 4096;
+  bool room = cap <= max_bytes;
+  while (room && graph_bytes(cache) + cap > max_bytes) room = evict_one(ctx, cache, &e);
+  while (room) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+      cudaGetLastError();
+      room = false;
+    } else if (free_b >= cap + keep_free) {
+      break;
+    } else {
+      room = evict_one(ctx, cache, &e);
+    }
+  }
+  char* slab = nullptr;
+  if (room && cudaMalloc(&slab, cap) != cudaSuccess) {
+    cudaGetLastError();
+    slab = nullptr;
+  }
+  if (!slab) {  // no memory for a private copy of the activations: stay eager (and ask again next time)
+    return model_forward_eager(m, input, want_probs, ctc, u8);
+  }
+  e.arena.release();
+  e.arena.fixed = true;
+  e.arena.slabs.push_back(Arena::Slab{slab, cap, 0});
+  e.in_bytes = in_bytes;
+  e.d_in = e.arena.alloc(in_bytes);
+  U8Input fixed_in = *u8;
+  if (u8->mode == 0)
+    fixed_in.table = static_cast<const uint8_t* const*>(e.d_in);
+  else
+    fixed_in.jobs = static_cast<const CrnnJob*>(e.d_in);
+  OAR_CUDA(cudaMemcpyAsync(e.d_in, src, in_bytes, cudaMemcpyDeviceToDevice, st));
+
+  bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  const bool began = ok;
+  Tensor out;
+  CtcOut co;
+  if (began) {
+    std::swap(ctx->arena, e.arena);
+    ctx->capturing = true;
+    ctx->captured = 0;
+    try {
+      out = model_forward_eager(m, input, want_probs, ctc ? &co : nullptr, &fixed_in);
+    } catch (...) {
+      ok = false;
+    }
+    ctx->capturing = false;
+    std::swap(ctx->arena, e.arena);
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+    if (ok && cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) ok = false, e.exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (!ok) {
+    cudaGetLastError();
+    release_entry(e);
+    ++e.failures;
+    static const bool verbose = getenv("OAR_GRAPH_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "[graph] capture failed for B=%d %dx%d (model %llu): walking eagerly\n", u8->B, u8->H, u8->W,
+                         (unsigned long long)m->uid);
+    return model_forward_eager(m, input, want_probs, ctc, u8);
+  }
+  e.n_kernels = ctx->captured;
+  e.out = out;
+  e.ctc = co;
+  OAR_CUDA(cudaGraphLaunch(e.exec, st));
+  g_launches += e.n_kernels;
+  ++g_submits;
+  if (ctc) *ctc = e.ctc;
+  return e.out;
 }
 
 }  // namespace oar

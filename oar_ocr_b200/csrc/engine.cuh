@@ -110,6 +110,8 @@ struct oar_model {
   size_t n_weights = 0;
   // tensor-core engine state (gemm_tc.cu): fp16 copies of GEMM weights etc.
   void* tc_state = nullptr;
+  uint64_t uid = 0;     // unique per loaded model: names its captured CUDA graphs (an address can be reused, a uid cannot)
+  int graph_safe = -1;  // may a walk of this layer list be captured?  -1 = not decided yet (engine.cu)
 
   const float* w(const oar::OpRec& op, int i) const { return d_weights + op.w_off[i]; }
 };
@@ -121,7 +123,16 @@ namespace oar {
 // materialised in the returned tensor, otherwise only `ctc` is filled (the
 // logits never leave the head kernel's launch) and the returned tensor is empty.
 // `u8` (optional): the input is given as u8 pixels instead of `in.p` (in.p == nullptr, dims from u8).
+//
+// CUDA graphs: a walk that reads u8 pixels (the detector, recogniser and classifier of the pipeline) is recorded into a
+// CUDA graph the second time its (model, engine, launch lane, batch, height, width) comes up and replayed from then on:
+// ~100 kernel launches, their tensor-map encodes and argument marshalling become one cudaGraphLaunch.  A graph owns its
+// activations (one cudaMalloc sized by the first, eager walk), so its outputs -- the returned tensor and `ctc` -- stay
+// valid until the next walk with the same key on the same lane: consume them in stream order.  OAR_GRAPHS=0 turns it
+// off; profiling (per-kernel events) always walks eagerly.
 Tensor model_forward(oar_model* m, const Tensor& in, bool want_probs, CtcOut* ctc, const U8Input* u8 = nullptr);
+void graph_cache_free(oar_ctx* ctx);                      // every graph of a context (oar_ctx_destroy)
+void graph_cache_drop_model(oar_ctx* ctx, uint64_t uid);  // the graphs of one model (oar_model_destroy)
 
 // Single layers of a loaded model, run outside a graph walk (engine.cu; the layout decoder in layout_net.cu calls them by
 // position): 1x1 convolution as a Linear over `rows` rows, LayerNorm, multi-head attention over B sequences of T tokens

@@ -39,7 +39,10 @@ __device__ __forceinline__ float act_simt(float v, int act) {
 // writes 8 pixels x 64 B = one contiguous 512-byte run, a weight read feeds PXT pixels, and the 9 floats of a kernel
 // row sit contiguously at 6 * pixel (conflict-free across the pixels of a warp).
 // Accumulation per output: bias, then (ky, kx, ci) ascending with FMA, exactly as stem_conv_kernel (engine.cu).
-// (Tried and measured slower on B200: float2-paired staging for FFMA2 without register moves -- 4.5 M bank conflicts.)
+// (Tried and measured slower on B200: float2-paired staging for FFMA2 without register moves -- 4.5 M bank conflicts.
+// Tried and measured equal, round 2: the next item's bytes prefetched as aligned words into registers during the compute
+// phase and normalised out of shared memory -- 0.83 vs 0.79 ms per step for the two stems: the kernel is bound by the
+// ~60 instructions per staged tap and the ~26 per output, not by the latency of its loads.)
 // ---------------------------------------------------------------------------
 template <int COUT, int PXT>
 __global__ void __launch_bounds__(128) stem_u8_kernel(const U8Input S, const float* __restrict__ w,

@@ -20,6 +20,7 @@ KIND_DET, KIND_REC, KIND_CLS, KIND_FEAT = 0, 1, 2, 3
 # every symbol include/oar_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "oar_det_config_default", "oar_pipeline_config_default", "oar_last_error", "oar_version", "oar_launch_count",
+    "oar_submit_count",
     "oar_ctx_create", "oar_ctx_destroy", "oar_ctx_synchronize", "oar_model_load_blob", "oar_model_destroy",
     "oar_model_kind", "oar_model_set_engine", "oar_infer_f32", "oar_normalize_chw", "oar_db_postprocess",
     "oar_det_run", "oar_sort_quad_boxes", "oar_rotate_crop", "oar_crnn_preprocess", "oar_ctc_decode", "oar_rec_run",
@@ -103,6 +104,7 @@ def lib():
         L = C.CDLL(path)
         L.oar_last_error.restype = C.c_char_p
         L.oar_launch_count.restype = C.c_int64
+        L.oar_submit_count.restype = C.c_int64
         L.oar_ctx_destroy.restype = None
         L.oar_model_destroy.restype = None
         L.oar_det_config_default.restype = None
@@ -181,6 +183,11 @@ def check(rc: int):
 
 def launch_count() -> int:
     return int(lib().oar_launch_count())
+
+
+def submit_count() -> int:
+    """Host-visible submissions (a replayed CUDA graph counts one)."""
+    return int(lib().oar_submit_count())
 
 
 def det_config(**kw) -> DetConfig:

@@ -276,3 +276,24 @@ def test_pipeline_run_multi_two_contexts(det_blob, rec_blob):
         assert np.array_equal(one.scores[:n], two.scores[:n])
         assert np.array_equal(one.seq_len[:n], two.seq_len[:n])
         assert np.array_equal(one.max_wh_ratio[:n], two.max_wh_ratio[:n])
+
+
+def test_db_postprocess_border_longer_than_the_staging_run(ctx):
+    """dbpost.cu walks every border once into a per-block staging run of 8192 points; a longer border is walked a second
+    time straight into the pool.  A comb with 150 teeth has an outer border of > 20000 points: boxes and scores must
+    still be the oracle's, next to ordinary blobs and with holes inside the comb's spine."""
+    from oracle import cpu
+    h, w = 640, 960
+    m = np.zeros((h, w), np.float32)
+    m[40:60, 20:940] = 0.9                      # spine
+    for k in range(150):
+        m[60:130, 22 + 6 * k:25 + 6 * k] = 0.9  # teeth, 3 px wide, 3 px apart
+    m[46:54, 100:120] = 0.1                     # holes in the spine
+    m[46:54, 400:460] = 0.1
+    m[300:340, 100:500] = 0.8                   # ordinary text-line blobs
+    m[400:430, 300:900] = 0.85
+    from oar_ocr_b200 import ffi
+    got = ctx.db_postprocess(m, cfg=ffi.det_config(box_thresh=0.3))[0]
+    want = cpu.db_postprocess(m, w, h, 0.3, 0.3, 2.0)
+    assert len(want[0]) >= 3  # the comb itself is accepted at this box threshold
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
