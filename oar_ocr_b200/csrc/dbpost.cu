@@ -757,26 +757,42 @@ __device__ float box_score_fast_warp(const float* __restrict__ pred, int W, int 
   return total_px > 0 ? total / (float)total_px : 0.0f;
 }
 
-// phase 1 (one lane): contour -> simplified chain -> convex hull -> min-area rect -> ordered mini box
-__device__ bool cand_mini_box(const ContourRec& rec, const short2* __restrict__ pool, short2* __restrict__ scratch,
-                              float* hx, float* hy, float bx[4], float by[4], float* min_side, int* err) {
+// simplify_chain_points (db_bitmap.rs:207-239) by the whole warp: a point stays when the direction of the chain changes
+// at it.  Every lane tests the points lane, lane + 32, ... against their two neighbours; a ballot and a prefix count
+// keep the survivors in chain order, so `scratch` receives exactly the sequence the sequential form writes.  (As one
+// lane's loop this was the longest serial piece of the geometry kernel: a dependent L2 round trip per contour point,
+// ~2000 points on a page-wide text line.)  Returns the number of survivors.
+__device__ int simplify_chain_warp(const ContourRec& rec, const short2* __restrict__ pool, short2* __restrict__ scratch,
+                                   int lane) {
   const short2* pts = pool + rec.off;
   short2* simp = scratch + rec.off;
+  const int n = rec.len;
+  int ns = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool keep = false;
+    short2 cur = make_short2(0, 0);
+    if (i < n) {
+      const short2 prev = pts[i == 0 ? n - 1 : i - 1], nxt = pts[i + 1 == n ? 0 : i + 1];
+      cur = pts[i];
+      const int a0 = (cur.x > prev.x) - (cur.x < prev.x), a1 = (cur.y > prev.y) - (cur.y < prev.y);
+      const int b0 = (nxt.x > cur.x) - (nxt.x < cur.x), b1 = (nxt.y > cur.y) - (nxt.y < cur.y);
+      keep = a0 != b0 || a1 != b1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) simp[ns + __popc(m & ((1u << lane) - 1u))] = cur;
+    ns += __popc(m);
+  }
+  __syncwarp();  // the survivors are read back by lane 0
+  return ns;
+}
+
+// phase 1 (one lane): simplified chain (ns points in scratch, see above) -> convex hull -> min-area rect -> ordered mini box
+__device__ bool cand_mini_box(const ContourRec& rec, const short2* __restrict__ pool, const short2* scratch, int ns, float* hx, float* hy, float bx[4], float by[4], float* min_side, int* err) {
+  const short2* pts = pool + rec.off;
+  const short2* simp = scratch + rec.off;
   int n = rec.len;
   if (n < 3) return false;  // get_mini_boxes_from_points: < 3 points -> None (simplified or raw)
-  // --- simplify_chain_points (db_bitmap.rs:207-239) ---
-  int ns = 0;
-  {
-    short2 prev = pts[n - 1], cur = pts[0];
-    for (int i = 0; i < n; ++i) {
-      short2 nxt = pts[(i + 1 == n) ? 0 : i + 1];
-      int a0 = (cur.x > prev.x) - (cur.x < prev.x), a1 = (cur.y > prev.y) - (cur.y < prev.y);
-      int b0 = (nxt.x > cur.x) - (nxt.x < cur.x), b1 = (nxt.y > cur.y) - (nxt.y < cur.y);
-      if (a0 != b0 || a1 != b1) simp[ns++] = cur;
-      prev = cur;
-      cur = nxt;
-    }
-  }
   const short2* P = simp;
   int np = ns;
   if (ns < 3) {  // simplify returns the raw chain; contour helper then uses the raw points
@@ -940,10 +956,11 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) db_geometry_kernel(
   float* ws = s_ws[wib];
   float bx[4] = {0.f, 0.f, 0.f, 0.f}, by[4] = {0.f, 0.f, 0.f, 0.f}, min_side = 0.0f;
   int ok = 0;
+  const ContourRec rec = recs[order[first[b] + rank]];
+  const int ns = rec.len >= 3 ? simplify_chain_warp(rec, pool, scratch, lane) : 0;
   if (lane == 0) {
     out.valid = 0;
-    const ContourRec rec = recs[order[first[b] + rank]];
-    ok = cand_mini_box(rec, pool, scratch, ws, ws + UNCLIP_CAP, bx, by, &min_side, err) ? 1 : 0;
+    ok = cand_mini_box(rec, pool, scratch, ns, ws, ws + UNCLIP_CAP, bx, by, &min_side, err) ? 1 : 0;
     if (ok && min_side < min_size) ok = 0;
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
