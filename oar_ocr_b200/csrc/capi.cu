@@ -245,21 +245,39 @@ void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, cons
   bool pending = false;  // pages of this group still on their way?
   if (ready)
     for (int i = 0; i < B; ++i) pending = pending || (*ready)[g.members[i]] != nullptr;
-  static const int split_parts = getenv("OAR_DET_SPLIT_PARTS") ? std::max(1, atoi(getenv("OAR_DET_SPLIT_PARTS"))) : 2;
-  const int halves = (pending && split_min > 0 && B >= split_min) ? std::min(split_parts, B) : 1;
+  // Parts: the upload of the first part is the one nothing hides, and a page takes the detector three times as long as
+  // the link (0.16 ms against 0.054 ms for 960 x 960), so every part may be up to three times its predecessor and its
+  // upload still lands under the predecessor's kernels: 32 pages go as 4 + 12 + 16 (exposed upload 0.22 ms instead of
+  // the 0.86 ms of two equal halves; 27.1 -> 26.4 ms per step with 8 + 24).  OAR_DET_SPLIT_PARTS=n forces n equal
+  // parts, OAR_DET_SPLIT_FIRST=n two parts with n pages in the first.
+  static const int split_parts = getenv("OAR_DET_SPLIT_PARTS") ? std::max(1, atoi(getenv("OAR_DET_SPLIT_PARTS"))) : 0;
+  static const int split_first = getenv("OAR_DET_SPLIT_FIRST") ? atoi(getenv("OAR_DET_SPLIT_FIRST")) : 0;
+  std::vector<int> bounds{0};  // part p = pages [bounds[p], bounds[p + 1])
+  if (pending && split_min > 0 && B >= split_min) {
+    if (split_parts > 0) {
+      for (int p = 1; p <= std::min(split_parts, B); ++p) bounds.push_back(p * B / std::min(split_parts, B));
+    } else if (split_first > 0 && split_first < B) {
+      bounds.push_back(split_first), bounds.push_back(B);
+    } else {
+      int part = std::max(4, B / 8);
+      while (bounds.back() + part < B) {
+        bounds.push_back(bounds.back() + part);
+        part *= 3;
+      }
+      // a small tail would be a poor detector batch: fold it into the part before it
+      if (bounds.size() > 1 && B - bounds.back() < part / 6) bounds.pop_back();
+      bounds.push_back(B);
+    }
+  } else {
+    bounds.push_back(B);
+  }
+  const int halves = (int)bounds.size() - 1;
   const size_t plane = (size_t)g.H * g.W;
   float* prob_keep = (post_lane || halves > 1) ? ctx->arena.get<float>((size_t)B * plane) : nullptr;
   auto mark = ctx->arena.mark();
   const float* prob_p = nullptr;
-  // Two parts: the upload of the first part is the one nothing hides, and a page takes the detector three times as long
-  // as the link (0.16 ms against 0.054 ms for 960 x 960), so a quarter of the batch in front keeps the rest's upload
-  // under the first part's kernels (32 host pages: 26.9 -> 26.6 ms per step against equal halves).
-  // OAR_DET_SPLIT_FIRST=n sets the first part's size, 0 = equal parts.
-  static const int split_first_env = getenv("OAR_DET_SPLIT_FIRST") ? atoi(getenv("OAR_DET_SPLIT_FIRST")) : -1;
-  const int split_first = split_first_env >= 0 ? split_first_env : (B + 3) / 4;
   for (int hf = 0; hf < halves; ++hf) {
-    int b0 = hf * B / halves, nb = (hf + 1) * B / halves - b0;
-    if (halves == 2 && split_first > 0 && split_first < B) b0 = hf ? split_first : 0, nb = hf ? B - split_first : split_first;
+    const int b0 = bounds[hf], nb = bounds[hf + 1] - b0;
     if (ready)
       for (int i = b0; i < b0 + nb; ++i)
         if ((*ready)[g.members[i]]) OAR_CUDA(cudaStreamWaitEvent(ctx->stream, (*ready)[g.members[i]], 0));

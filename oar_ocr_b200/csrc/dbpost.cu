@@ -207,50 +207,87 @@ __device__ __forceinline__ int ring_dx(int d) { return (int)((0x1a90u >> (2 * d)
 __device__ __forceinline__ int ring_dy(int d) { return (int)((0xa901u >> (2 * d)) & 3u) - 1; }
 __device__ __forceinline__ int ring_of(int dx, int dy) { return (int)((0x5de00d1u >> (3 * ((dx + 1) + 3 * (dy + 1)))) & 7u); }
 
-// Follows one border from (sx,sy) inside the window `st` (bw x bh pixels, row stride `stride`, window origin
-// (ox,oy) in image coordinates; Wimg = image width for the right-edge rule).  start_dir = ring index of the adjacent
-// zero pixel.  All 32 lanes execute; lanes 0..7 probe.  When pts != nullptr, writes points (image coordinates) and
+// The window a border is followed in: either the global state map of the image (one byte per pixel) or the block's
+// shared-memory copy of one component, two bits per pixel (0 background, 1 component, 2 / 3 the visited marks), 16
+// pixels per word -- four times the pixels of a byte map in the same 16 KB, so a page-wide text line still walks in
+// shared memory.  Only lane 0 writes; the probing lanes only ask "non-zero?", which a mark never changes.
+struct MapU8 {
+  static constexpr bool kInside = false;  // the walk may step to the image's edge: probes are bounds-checked
+  uint8_t* p;
+  int stride;
+  __device__ __forceinline__ int get(int x, int y) const { return p[(size_t)y * stride + x]; }
+  __device__ __forceinline__ void set(int x, int y, int v) const { p[(size_t)y * stride + x] = (uint8_t)v; }
+};
+struct MapPacked {
+  static constexpr bool kInside = true;  // one ring of background around the component: its pixels' neighbours exist
+  uint32_t* p;
+  int wpr;  // words per row
+  __device__ __forceinline__ int get(int x, int y) const { return (int)((p[y * wpr + (x >> 4)] >> ((x & 15) * 2)) & 3u); }
+  __device__ __forceinline__ void set(int x, int y, int v) const {
+    uint32_t* w = p + y * wpr + (x >> 4);
+    const int sh = (x & 15) * 2;
+    *w = (*w & ~(3u << sh)) | ((uint32_t)v << sh);
+  }
+};
+
+// Follows one border from (sx,sy) inside the window `st` (bw x bh pixels, window origin (ox,oy) in image coordinates;
+// Wimg = image width for the right-edge rule).  start_dir = ring index of the adjacent
+// zero pixel.  All 32 lanes execute the same (warp-uniform) walk; lane 0 writes.  When pts != nullptr, writes points (image coordinates) and
 // the visited marks (2 = +nbd, 3 = -nbd); only the first `cap` points are stored.  Returns the number of points.
 // (The marks are idempotent: walking a border again leaves them as they are.)
-__device__ int follow_border(uint8_t* st, int stride, int bw, int bh, int ox, int oy, int Wimg, int sx, int sy,
-                             int start_dir, short2* pts, int cap, int lane) {
-  auto nonzero = [&](int x, int y) -> bool {
-    return x >= 0 && y >= 0 && x < bw && y < bh && st[(size_t)y * stride + x] != 0;
+template <class Map>
+__device__ int follow_border(const Map st, int bw, int bh, int ox, int oy, int Wimg, int sx, int sy, int start_dir,
+                             short2* pts, int cap, int lane) {
+  // bit d of the result: the neighbour of (x, y) in ring direction d is non-zero.  Eight independent loads (the
+  // directions are compile-time constants), the same on every lane: no per-lane probe, no vote -- what follows is
+  // integer arithmetic on one 8-bit mask, the shortest dependent chain per border pixel this walk allows.
+  auto ring8 = [&](int x, int y) -> unsigned {
+    unsigned m = 0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int nx = x + ring_dx(d), ny = y + ring_dy(d);
+      bool nz;
+      if (Map::kInside)
+        nz = st.get(nx, ny) != 0;
+      else
+        nz = nx >= 0 && ny >= 0 && nx < bw && ny < bh && st.get(nx, ny) != 0;
+      m |= (nz ? 1u : 0u) << d;
+    }
+    return m;
   };
-  int k = lane & 7;
-  int d = (start_dir + k) & 7;
-  bool hit = (lane < 8) && nonzero(sx + ring_dx(d), sy + ring_dy(d));
-  unsigned mask = __ballot_sync(0xffffffffu, hit) & 0xffu;
-  if (!mask) {
+  // probes k = 0..7 of the start pixel look clockwise from start_dir: direction (start_dir + k) & 7
+  const unsigned m0 = ring8(sx, sy);
+  const unsigned r0 = ((m0 >> start_dir) | (m0 << (8 - start_dir))) & 0xffu;
+  if (!r0) {
     if (pts && lane == 0) {
       if (cap > 0) pts[0] = make_short2((short)(sx + ox), (short)(sy + oy));
-      st[(size_t)sy * stride + sx] = 3;
+      st.set(sx, sy, 3);
     }
     return 1;
   }
-  int k1 = __ffs(mask) - 1;
-  int d1 = (start_dir + k1) & 7;
-  int p1x = sx + ring_dx(d1), p1y = sy + ring_dy(d1);
+  const int k1 = __ffs(r0) - 1;
+  const int d1 = (start_dir + k1) & 7;
+  const int p1x = sx + ring_dx(d1), p1y = sy + ring_dy(d1);
   int p2x = p1x, p2y = p1y, p3x = sx, p3y = sy;
   int n = 0;
   for (;;) {
     if (pts && lane == 0 && n < cap) pts[n] = make_short2((short)(p3x + ox), (short)(p3y + oy));
     ++n;
-    int front = ring_of(p2x - p3x, p2y - p3y);
-    int dk = (front - 1 - k + 16) & 7;  // k = 7 -> front itself (examined last)
-    bool h2 = (lane < 8) && nonzero(p3x + ring_dx(dk), p3y + ring_dy(dk));
-    unsigned m2 = __ballot_sync(0xffffffffu, h2) & 0xffu;
-    int k4 = __ffs(m2) - 1;  // never -1: p2 is non-zero
-    int d4 = (front - 1 - k4 + 16) & 7;
-    int p4x = p3x + ring_dx(d4), p4y = p3y + ring_dy(d4);
-    int kE = (front - 5 + 16) & 7;  // the probe index that looks East
-    bool right_edge = kE < k4;
+    const int front = ring_of(p2x - p3x, p2y - p3y);
+    // probe k looks counter-clockwise from front - 1: direction (front - 1 - k) & 7 (k = 7: front itself, examined
+    // last) = bit k of the bit-reversed mask rotated left by front
+    const unsigned rv = __brev(ring8(p3x, p3y)) >> 24;
+    const unsigned m2 = ((rv << front) | (rv >> (8 - front))) & 0xffu;
+    const int k4 = __ffs(m2) - 1;  // never -1: p2 is non-zero
+    const int d4 = (front - 1 - k4 + 16) & 7;
+    const int p4x = p3x + ring_dx(d4), p4y = p3y + ring_dy(d4);
+    const int kE = (front - 5 + 16) & 7;  // the probe index that looks East
+    const bool right_edge = kE < k4;
     if (pts && lane == 0) {
-      size_t o = (size_t)p3y * stride + p3x;
       if (p3x + ox + 1 == Wimg || right_edge)
-        st[o] = 3;
-      else if (st[o] == 1)
-        st[o] = 2;
+        st.set(p3x, p3y, 3);
+      else if (st.get(p3x, p3y) == 1)
+        st.set(p3x, p3y, 2);
     }
     if (p4x == sx && p4y == sy && p3x == p1x && p3y == p1y) break;
     p2x = p3x, p2y = p3y;
@@ -263,8 +300,9 @@ __device__ int follow_border(uint8_t* st, int stride, int bw, int bh, int ox, in
 // component's bounding box plus a one-pixel ring into shared memory as a membership mask (1 = pixel of THIS
 // component, everything else 0 -- other components are never 8-adjacent, so the borders are unchanged); warp 0 then
 // replays the raster scan and walks the borders in shared memory, where every probe costs ~30 cycles instead of an
-// L2 round trip.  The visited marks live only in that copy.  Components whose window does not fit walk the global
-// state map directly (warp 0 only).
+// L2 round trip.  The visited marks live only in that copy.  The copy holds two bits per pixel (MapPacked): windows
+// of up to 65536 pixels -- a page-wide text line -- fit the 16 KB tile; larger ones walk the global state map directly
+// (warp 0 only).
 constexpr int TRACE_TILE_BYTES = 16 * 1024;  // ~14 blocks per SM: the walk is serial per component, concurrency is what counts (48 KB tiles measured 1.6x slower)
 constexpr int TRACE_THREADS = 128;
 // Every border is walked ONCE: the walk is the serial chain of the post-process (one dependent probe per border pixel),
@@ -273,12 +311,71 @@ constexpr int TRACE_THREADS = 128;
 // > 8192 points) is walked a second time straight into the pool.
 constexpr int TRACE_STAGE_POINTS = 8192;
 
+// Raster scan of one component's window and the walks it starts (warp 0 of the block).  `st` covers the window
+// [ox, ox + ww) x [oy, oy + wh) of the image; member(x, y) tells whether a non-zero pixel of the map belongs to THIS
+// component (always true in the staged copy, a label comparison in the global map).
+template <class Map, class Member>
+__device__ void trace_component(const Map st, Member member, const Comp& c, int y0, int ox, int oy, int ww, int wh, int W,
+                                short2* __restrict__ pool, unsigned long long* __restrict__ pool_used,
+                                unsigned long long pool_cap, ContourRec* __restrict__ recs, int* __restrict__ n_recs,
+                                int rec_cap, int* __restrict__ err, short2* my_stage, int lane) {
+  bool failed = false;
+  for (int y = y0; y <= c.ymax && !failed; ++y) {
+    for (int xb = c.xmin; xb <= c.xmax && !failed; xb += 32) {
+      const int x = xb + lane;
+      bool cand = false;
+      if (x <= c.xmax) {
+        if (st.get(x - ox, y - oy) != 0 && member(x, y)) {
+          const bool wz = (x > 0) && st.get(x - ox - 1, y - oy) == 0;
+          const bool ez = (x + 1 < W) && st.get(x - ox + 1, y - oy) == 0;
+          cand = wz || ez;
+        }
+      }
+      unsigned cm = __ballot_sync(0xffffffffu, cand);
+      while (cm) {
+        const int l = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int cx = xb + l;
+        const int s = st.get(cx - ox, y - oy);
+        int start_dir = -1;
+        if (s == 1 && cx > 0 && st.get(cx - ox - 1, y - oy) == 0)
+          start_dir = 0;  // outer border, adjacent = West
+        else if ((s == 1 || s == 2) && cx + 1 < W && st.get(cx - ox + 1, y - oy) == 0)
+          start_dir = 4;  // hole border, adjacent = East
+        if (start_dir < 0) continue;
+        const int n = follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, my_stage, TRACE_STAGE_POINTS, lane);
+        unsigned long long off = 0;
+        int ri = -1;
+        if (lane == 0) {
+          off = atomicAdd(pool_used, (unsigned long long)n);
+          ri = atomicAdd(n_recs, 1);
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        ri = __shfl_sync(0xffffffffu, ri, 0);
+        if (off + n > pool_cap || ri >= rec_cap) {
+          if (lane == 0) atomicExch(err, 1);
+          failed = true;
+          break;
+        }
+        if (n <= TRACE_STAGE_POINTS) {
+          __syncwarp();  // lane 0's staged points are visible to the warp
+          for (int i = lane; i < n; i += 32) pool[off + i] = my_stage[i];
+        } else {
+          follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, 0x7fffffff, lane);
+        }
+        if (lane == 0) recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
+        __syncwarp();
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
     uint8_t* __restrict__ state, const int32_t* __restrict__ lab, const Comp* __restrict__ comps,
     const int* __restrict__ n_comps, int comp_cap, int H, int W, short2* __restrict__ pool,
     unsigned long long* __restrict__ pool_used, unsigned long long pool_cap, ContourRec* __restrict__ recs,
     int* __restrict__ n_recs, int rec_cap, int* __restrict__ err, short2* __restrict__ stage) {
-  extern __shared__ uint8_t tile[];
+  extern __shared__ uint32_t tile[];
   short2* my_stage = stage + (size_t)blockIdx.x * TRACE_STAGE_POINTS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = min(*n_comps, comp_cap);
@@ -289,83 +386,41 @@ __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
     const int32_t* L = lab + (size_t)c.img * HW;
     const int y0 = c.root / W;
     const int bw = c.xmax - c.xmin + 3, bh = c.ymax - y0 + 3;  // bounding box + ring
-    const bool staged = (size_t)bw * bh <= (size_t)TRACE_TILE_BYTES;
-    uint8_t* st;
-    int stride, ox, oy, ww, wh;
+    const int wpr = (bw + 31) >> 5 << 1;                       // 16 pixels per word, rows padded to 32 pixels
+    const bool staged = (size_t)wpr * bh * 4 <= (size_t)TRACE_TILE_BYTES;
+    const int ox = staged ? c.xmin - 1 : 0, oy = staged ? y0 - 1 : 0;
     if (staged) {
-      ox = c.xmin - 1, oy = y0 - 1, stride = bw, ww = bw, wh = bh;
-      st = tile;
+      // one warp per row, 32 pixels per step: the membership bits of a ballot, spread to two bits per pixel
       for (int ly = warp; ly < bh; ly += TRACE_THREADS / 32) {
         const int gy = oy + ly;
         const bool row_in = gy >= 0 && gy < H;
-        for (int lx = lane; lx < bw; lx += 32) {
-          const int gx = ox + lx;
-          uint8_t v = 0;
-          if (row_in && gx >= 0 && gx < W) {
+        for (int lx0 = 0; lx0 < 16 * wpr; lx0 += 32) {
+          const int lx = lx0 + lane, gx = ox + lx;
+          bool v = false;
+          if (row_in && lx < bw && gx >= 0 && gx < W) {
             const size_t o = (size_t)gy * W + gx;
-            v = (img[o] != 0 && L[o] == c.root) ? 1 : 0;
+            v = img[o] != 0 && L[o] == c.root;
           }
-          tile[ly * bw + lx] = v;
+          const unsigned m = __ballot_sync(0xffffffffu, v);
+          if ((lane & 15) == 0) {
+            uint32_t b = (m >> lane) & 0xffffu;  // 16 membership bits -> even bit positions
+            b = (b | (b << 8)) & 0x00ff00ffu;
+            b = (b | (b << 4)) & 0x0f0f0f0fu;
+            b = (b | (b << 2)) & 0x33333333u;
+            b = (b | (b << 1)) & 0x55555555u;
+            tile[ly * wpr + ((lx0 + lane) >> 4)] = b;
+          }
         }
       }
-    } else {
-      ox = 0, oy = 0, stride = W, ww = W, wh = H;
-      st = img;
     }
     __syncthreads();
     if (warp == 0) {
-      bool failed = false;
-      for (int y = y0; y <= c.ymax && !failed; ++y) {
-        for (int xb = c.xmin; xb <= c.xmax && !failed; xb += 32) {
-          const int x = xb + lane;
-          bool cand = false;
-          if (x <= c.xmax) {
-            const size_t lo = (size_t)(y - oy) * stride + (x - ox);
-            if (st[lo] != 0 && (staged || L[(size_t)y * W + x] == c.root)) {
-              const bool wz = (x > 0) && st[lo - 1] == 0;
-              const bool ez = (x + 1 < W) && st[lo + 1] == 0;
-              cand = wz || ez;
-            }
-          }
-          unsigned cm = __ballot_sync(0xffffffffu, cand);
-          while (cm) {
-            const int l = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const int cx = xb + l;
-            const size_t lo = (size_t)(y - oy) * stride + (cx - ox);
-            const uint8_t s = st[lo];
-            int start_dir = -1;
-            if (s == 1 && cx > 0 && st[lo - 1] == 0)
-              start_dir = 0;  // outer border, adjacent = West
-            else if ((s == 1 || s == 2) && cx + 1 < W && st[lo + 1] == 0)
-              start_dir = 4;  // hole border, adjacent = East
-            if (start_dir < 0) continue;
-            const int n = follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, my_stage,
-                                        TRACE_STAGE_POINTS, lane);
-            unsigned long long off = 0;
-            int ri = -1;
-            if (lane == 0) {
-              off = atomicAdd(pool_used, (unsigned long long)n);
-              ri = atomicAdd(n_recs, 1);
-            }
-            off = __shfl_sync(0xffffffffu, off, 0);
-            ri = __shfl_sync(0xffffffffu, ri, 0);
-            if (off + n > pool_cap || ri >= rec_cap) {
-              if (lane == 0) atomicExch(err, 1);
-              failed = true;
-              break;
-            }
-            if (n <= TRACE_STAGE_POINTS) {
-              __syncwarp();  // lane 0's staged points are visible to the warp
-              for (int i = lane; i < n; i += 32) pool[off + i] = my_stage[i];
-            } else {
-              follow_border(st, stride, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, 0x7fffffff, lane);
-            }
-            if (lane == 0) recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
-            __syncwarp();
-          }
-        }
-      }
+      if (staged)
+        trace_component(MapPacked{tile, wpr}, [](int, int) { return true; }, c, y0, ox, oy, bw, bh, W, pool, pool_used,
+                        pool_cap, recs, n_recs, rec_cap, err, my_stage, lane);
+      else
+        trace_component(MapU8{img, W}, [&](int x, int y) { return L[(size_t)y * W + x] == c.root; }, c, y0, 0, 0, W, H, W,
+                        pool, pool_used, pool_cap, recs, n_recs, rec_cap, err, my_stage, lane);
     }
     __syncthreads();  // the tile is reused by this block's next component
   }
@@ -787,61 +842,71 @@ __device__ int simplify_chain_warp(const ContourRec& rec, const short2* __restri
   return ns;
 }
 
-// phase 1 (one lane): simplified chain (ns points in scratch, see above) -> convex hull -> min-area rect -> ordered mini box
-__device__ bool cand_mini_box(const ContourRec& rec, const short2* __restrict__ pool, const short2* scratch, int ns, float* hx, float* hy, float bx[4], float by[4], float* min_side, int* err) {
-  const short2* pts = pool + rec.off;
-  const short2* simp = scratch + rec.off;
-  int n = rec.len;
-  if (n < 3) return false;  // get_mini_boxes_from_points: < 3 points -> None (simplified or raw)
-  const short2* P = simp;
-  int np = ns;
-  if (ns < 3) {  // simplify returns the raw chain; contour helper then uses the raw points
-    P = pts;
-    np = n;
+// Convex hull of the chain by the whole warp.  All cross products are exact integers, so the reference's Graham scan
+// yields the unique strict hull, starting at the lowest-y (then lowest-x) point in increasing polar angle; a Jarvis
+// march reproduces that sequence.  Each step is an arg-max over the points under "more clockwise seen from the
+// current vertex, farther among collinear" -- a strict weak order, because the current vertex is an extreme point and
+// every other point lies in a wedge of less than 180 degrees -- so the lanes reduce strided subsets and the partial
+// winners with the same rule and arrive at the coordinates the sequential scan finds.  (One lane's scan of ~1000
+// simplified points per hull vertex was the longest serial piece of the kernel after the simplification.)
+// hx / hy (shared, UNCLIP_CAP floats each) receive the hull; returns its size, or -1 when it does not fit.
+__device__ __forceinline__ bool hull_better(int cx, int cy, int bx, int by, int qx, int qy) {
+  const long long cr = (long long)(bx - cx) * (qy - cy) - (long long)(by - cy) * (qx - cx);
+  if (cr < 0) return true;
+  if (cr == 0) {
+    const long long d1 = (long long)(bx - cx) * (bx - cx) + (long long)(by - cy) * (by - cy);
+    const long long d2 = (long long)(qx - cx) * (qx - cx) + (long long)(qy - cy) * (qy - cy);
+    const long long dot = (long long)(bx - cx) * (qx - cx) + (long long)(by - cy) * (qy - cy);
+    return dot > 0 && d2 > d1;
   }
-  // --- convex hull of integer points.  All cross products are exact in f32 for |coord| < 4096, so the
-  // reference's Graham scan yields the unique strict hull, starting at the lowest-y (then lowest-x) point in
-  // increasing polar angle; Jarvis march reproduces that sequence. ---
-  int s = 0;
-  for (int i = 1; i < np; ++i)
-    if (P[i].y < P[s].y || (P[i].y == P[s].y && P[i].x < P[s].x)) s = i;
-  int nh = 0;
-  {
-    int cx = P[s].x, cy = P[s].y;
-    const int sx = cx, sy = cy;
-    for (;;) {
-      if (nh >= UNCLIP_CAP) {
-        atomicExch(err, 2);
-        return false;
-      }
-      hx[nh] = (float)cx, hy[nh] = (float)cy, ++nh;
-      // next = the point q such that every other point is to the left of cur->q, farthest among collinear
-      int bx_ = cx, by_ = cy;
-      bool have = false;
-      for (int i = 0; i < np; ++i) {
-        int qx = P[i].x, qy = P[i].y;
-        if (qx == cx && qy == cy) continue;
-        if (!have) {
-          bx_ = qx, by_ = qy, have = true;
-          continue;
-        }
-        long long cr = (long long)(bx_ - cx) * (qy - cy) - (long long)(by_ - cy) * (qx - cx);
-        if (cr < 0) {
-          bx_ = qx, by_ = qy;
-        } else if (cr == 0) {
-          long long d1 = (long long)(bx_ - cx) * (bx_ - cx) + (long long)(by_ - cy) * (by_ - cy);
-          long long d2 = (long long)(qx - cx) * (qx - cx) + (long long)(qy - cy) * (qy - cy);
-          long long dot = (long long)(bx_ - cx) * (qx - cx) + (long long)(by_ - cy) * (qy - cy);
-          if (dot > 0 && d2 > d1) bx_ = qx, by_ = qy;
-        }
-      }
-      if (!have) break;
-      if (bx_ == sx && by_ == sy) break;
-      // collinear degenerate set: the march would bounce between the two extremes
-      if (nh >= 2 && (float)bx_ == hx[nh - 2] && (float)by_ == hy[nh - 2]) break;
-      cx = bx_, cy = by_;
+  return false;
+}
+
+__device__ int hull_march_warp(const short2* P, int np, float* hx, float* hy, int* err, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  int sx = 0x7fffffff, sy = 0x7fffffff;
+  for (int i = lane; i < np; i += 32) {
+    const short2 q = P[i];
+    if (q.y < sy || (q.y == sy && q.x < sx)) sx = q.x, sy = q.y;
+  }
+  for (int off = 16; off; off >>= 1) {
+    const int ox = __shfl_xor_sync(FULL, sx, off), oy = __shfl_xor_sync(FULL, sy, off);
+    if (oy < sy || (oy == sy && ox < sx)) sx = ox, sy = oy;
+  }
+  int cx = sx, cy = sy, pcx = 0, pcy = 0, nh = 0;
+  for (;;) {
+    if (nh >= UNCLIP_CAP) {
+      if (lane == 0) atomicExch(err, 2);
+      return -1;
     }
+    if (lane == 0) hx[nh] = (float)cx, hy[nh] = (float)cy;
+    ++nh;
+    int bx = cx, by = cy;
+    bool have = false;
+    for (int i = lane; i < np; i += 32) {
+      const short2 q = P[i];
+      if (q.x == cx && q.y == cy) continue;
+      if (!have || hull_better(cx, cy, bx, by, q.x, q.y)) bx = q.x, by = q.y, have = true;
+    }
+    for (int off = 16; off; off >>= 1) {
+      const int ox = __shfl_xor_sync(FULL, bx, off), oy = __shfl_xor_sync(FULL, by, off);
+      const bool oh = __shfl_xor_sync(FULL, have ? 1 : 0, off) != 0;
+      if (oh && (!have || hull_better(cx, cy, bx, by, ox, oy))) bx = ox, by = oy, have = true;
+    }
+    // (duplicated points can leave different lanes with different copies of the same coordinates: harmless)
+    if (!have) break;
+    if (bx == sx && by == sy) break;
+    if (nh >= 2 && bx == pcx && by == pcy) break;  // collinear degenerate set: the march would bounce between the extremes
+    pcx = cx, pcy = cy;
+    cx = bx, cy = by;
   }
+  __syncwarp();
+  return nh;
+}
+
+// phase 1 tail (one lane): hull (nh points in hx / hy) -> min-area rect -> ordered mini box
+__device__ bool cand_mini_box(const short2* P, int np, int nh, const float* hx, const float* hy, float bx[4], float by[4],
+                              float* min_side) {
   MinRect r;
   if (nh < 3) {
     float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;  // degenerate: AABB of the points
@@ -957,10 +1022,17 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) db_geometry_kernel(
   float bx[4] = {0.f, 0.f, 0.f, 0.f}, by[4] = {0.f, 0.f, 0.f, 0.f}, min_side = 0.0f;
   int ok = 0;
   const ContourRec rec = recs[order[first[b] + rank]];
-  const int ns = rec.len >= 3 ? simplify_chain_warp(rec, pool, scratch, lane) : 0;
+  // get_mini_boxes_from_points: < 3 points -> None; a chain that simplifies to < 3 points is used raw
+  const short2* P = pool + rec.off;
+  int np = rec.len, nh = -1;
+  if (rec.len >= 3) {
+    const int ns = simplify_chain_warp(rec, pool, scratch, lane);
+    if (ns >= 3) P = scratch + rec.off, np = ns;
+    nh = hull_march_warp(P, np, ws, ws + UNCLIP_CAP, err, lane);
+  }
   if (lane == 0) {
     out.valid = 0;
-    ok = cand_mini_box(rec, pool, scratch, ns, ws, ws + UNCLIP_CAP, bx, by, &min_side, err) ? 1 : 0;
+    ok = (nh >= 0 && cand_mini_box(P, np, nh, ws, ws + UNCLIP_CAP, bx, by, &min_side)) ? 1 : 0;
     if (ok && min_side < min_size) ok = 0;
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);

@@ -1655,12 +1655,16 @@ size_t graph_bytes(const GraphCache& c) {
   return n;
 }
 
-// least recently used captured graph other than `keep`; false when there is none
+// Drops the least recently used captured graph other than `keep`; false when there is none -- or when even that one was
+// used within the last GRAPH_RECENT walks: a working set larger than the budget would otherwise evict and re-record a
+// graph on every walk (LRU's worst case on a cyclic pattern); this way the graphs recorded first stay and the rest of
+// the set walks eagerly.
+constexpr uint64_t GRAPH_RECENT = 256;
 bool evict_one(oar_ctx* ctx, GraphCache& c, const GraphEntry* keep) {
   GraphEntry* victim = nullptr;
   for (auto& kv : c.entries)
     if (&kv.second != keep && kv.second.exec && (!victim || kv.second.last_use < victim->last_use)) victim = &kv.second;
-  if (!victim) return false;
+  if (!victim || victim->last_use + GRAPH_RECENT > c.tick) return false;
   // nothing of the victim may be in flight: both lanes are drained (rare: only under memory pressure)
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
@@ -1807,6 +1811,11 @@ Tensor model_forward(oar_model* m, const Tensor& input, bool want_probs, CtcOut*
   e.n_kernels = ctx->captured;
   e.out = out;
   e.ctc = co;
+  static const bool verbose_ok = getenv("OAR_GRAPH_VERBOSE") != nullptr;
+  if (verbose_ok)
+    fprintf(stderr, "[graph] model %llu engine %d lane %p B=%d %dx%d: %lld kernels, %.1f MiB of activations (cache: %.1f MiB)\n",
+            (unsigned long long)m->uid, m->engine, (void*)st, u8->B, u8->H, u8->W, e.n_kernels, cap / 1048576.0,
+            graph_bytes(cache) / 1048576.0);
   OAR_CUDA(cudaGraphLaunch(e.exec, st));
   g_launches += e.n_kernels;
   ++g_submits;
