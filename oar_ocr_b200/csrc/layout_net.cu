@@ -354,14 +354,29 @@ float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const*
     if (hs[i] <= 0 || ws[i] <= 0 || !images[i]) OAR_FAIL(OAR_E_INVALID, "image %d is empty", i);
     total += ((size_t)hs[i] * ws[i] * 3 + 15) & ~(size_t)15;
   }
-  uint8_t* h_pages = on_device ? nullptr : (uint8_t*)ctx->pinned_get(total);
+  // host pages: page-locked ones are copied from where they lie (one transfer per page), pageable ones go through one
+  // pinned staging buffer and one transfer
+  bool pinned = !on_device;
+  for (int i = 0; i < n && pinned; ++i) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, images[i]) != cudaSuccess) {
+      cudaGetLastError();
+      pinned = false;
+    } else {
+      pinned = at.type == cudaMemoryTypeHost;
+    }
+  }
+  uint8_t* h_pages = (on_device || pinned) ? nullptr : (uint8_t*)ctx->pinned_get(total);
   uint8_t* d_pages = on_device ? nullptr : ctx->arena.get<uint8_t>(total);
   size_t off = 0;
   for (int i = 0; i < n; ++i) {
     const size_t bytes = (size_t)hs[i] * ws[i] * 3;
     const uint8_t* d = images[i];
     if (!on_device) {
-      memcpy(h_pages + off, images[i], bytes);
+      if (pinned)
+        OAR_CUDA(cudaMemcpyAsync(d_pages + off, images[i], bytes, cudaMemcpyHostToDevice, st));
+      else
+        memcpy(h_pages + off, images[i], bytes);
       d = d_pages + off;
       off += (bytes + 15) & ~(size_t)15;
     }
@@ -378,7 +393,7 @@ float* layout_rows_device(oar_model* enc, oar_model* head, const uint8_t* const*
     max_sw = std::max(max_sw, j.sw);
     ptrs[i] = j.dst;
   }
-  if (!on_device) OAR_CUDA(cudaMemcpyAsync(d_pages, h_pages, total, cudaMemcpyHostToDevice, st));
+  if (!on_device && !pinned) OAR_CUDA(cudaMemcpyAsync(d_pages, h_pages, total, cudaMemcpyHostToDevice, st));
   if (!jobs.empty()) {
     ResizeJob* d_jobs = upload(ctx, jobs);
     launch_resize_triangle(ctx, d_jobs, (int)jobs.size(), max_sw, in_w, in_h);
