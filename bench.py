@@ -722,6 +722,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout at the first
+    # communicator) would precede it; anything more verbose that a caller asked for is left alone
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.batch is None:
         args.batch = {"rec512": 512, "layout": 8}.get(args.workload, 32)
     if args.workload == "layout":
