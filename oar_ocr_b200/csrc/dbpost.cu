@@ -313,60 +313,124 @@ constexpr int TRACE_THREADS = 128;
 // > 8192 points) is walked a second time straight into the pool.
 constexpr int TRACE_STAGE_POINTS = 8192;
 
-// Raster scan of one component's window and the walks it starts (warp 0 of the block).  `st` covers the window
-// [ox, ox + ww) x [oy, oy + wh) of the image; member(x, y) tells whether a non-zero pixel of the map belongs to THIS
-// component (always true in the staged copy, a label comparison in the global map).
-template <class Map, class Member>
-__device__ void trace_component(const Map st, Member member, const Comp& c, int y0, int ox, int oy, int ww, int wh, int W,
-                                short2* __restrict__ pool, unsigned long long* __restrict__ pool_used,
-                                unsigned long long pool_cap, ContourRec* __restrict__ recs, int* __restrict__ n_recs,
-                                int rec_cap, int* __restrict__ err, short2* my_stage, int lane) {
-  bool failed = false;
-  for (int y = y0; y <= c.ymax && !failed; ++y) {
-    for (int xb = c.xmin; xb <= c.xmax && !failed; xb += 32) {
+// Where the walks' points and records go (one per kernel launch).
+struct TraceOut {
+  short2* pool;
+  unsigned long long* pool_used;
+  unsigned long long pool_cap;
+  ContourRec* recs;
+  int* n_recs;
+  int rec_cap;
+  int* err;
+};
+
+// A raster-scan candidate (cx, y) (image coordinates; a component pixel with background to its West or East): start an
+// outer or a hole border there if the visited marks say so, walk it once, publish its points and its record.  Called by
+// the whole (converged) warp; returns false when a capacity ran out.
+template <class Map>
+__device__ bool start_border(const Map st, const Comp& c, int ox, int oy, int ww, int wh, int W, int cx, int y,
+                             const TraceOut& T, short2* my_stage, int lane) {
+  const int s = st.get(cx - ox, y - oy);
+  int start_dir = -1;
+  if (s == 1 && cx > 0 && st.get(cx - ox - 1, y - oy) == 0)
+    start_dir = 0;  // outer border, adjacent = West
+  else if ((s == 1 || s == 2) && cx + 1 < W && st.get(cx - ox + 1, y - oy) == 0)
+    start_dir = 4;  // hole border, adjacent = East
+  if (start_dir < 0) return true;
+  const int n = follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, my_stage, TRACE_STAGE_POINTS, lane);
+  unsigned long long off = 0;
+  int ri = -1;
+  if (lane == 0) {
+    off = atomicAdd(T.pool_used, (unsigned long long)n);
+    ri = atomicAdd(T.n_recs, 1);
+  }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  ri = __shfl_sync(0xffffffffu, ri, 0);
+  if (off + n > T.pool_cap || ri >= T.rec_cap) {
+    if (lane == 0) atomicExch(T.err, 1);
+    return false;
+  }
+  if (n <= TRACE_STAGE_POINTS) {
+    __syncwarp();  // lane 0's staged points are visible to the warp
+    for (int i = lane; i < n; i += 32) T.pool[off + i] = my_stage[i];
+  } else {
+    follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, T.pool + off, 0x7fffffff, lane);
+  }
+  if (lane == 0) T.recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
+  __syncwarp();
+  return true;
+}
+
+// Raster scan of one component in the global state map (a window too large for the tile; warp 0 of the block): 32
+// pixels per step, one probe each.  member(x, y): does this non-zero pixel belong to THIS component (label comparison).
+template <class Member>
+__device__ void trace_component_global(const MapU8 st, Member member, const Comp& c, int y0, int H, int W, const TraceOut& T,
+                                       short2* my_stage, int lane) {
+  bool ok = true;
+  for (int y = y0; y <= c.ymax && ok; ++y) {
+    for (int xb = c.xmin; xb <= c.xmax && ok; xb += 32) {
       const int x = xb + lane;
       bool cand = false;
-      if (x <= c.xmax) {
-        if (st.get(x - ox, y - oy) != 0 && member(x, y)) {
-          const bool wz = (x > 0) && st.get(x - ox - 1, y - oy) == 0;
-          const bool ez = (x + 1 < W) && st.get(x - ox + 1, y - oy) == 0;
-          cand = wz || ez;
-        }
+      if (x <= c.xmax && st.get(x, y) != 0 && member(x, y)) {
+        const bool wz = (x > 0) && st.get(x - 1, y) == 0;
+        const bool ez = (x + 1 < W) && st.get(x + 1, y) == 0;
+        cand = wz || ez;
       }
       unsigned cm = __ballot_sync(0xffffffffu, cand);
-      while (cm) {
+      while (cm && ok) {
         const int l = __ffs(cm) - 1;
         cm &= cm - 1;
-        const int cx = xb + l;
-        const int s = st.get(cx - ox, y - oy);
-        int start_dir = -1;
-        if (s == 1 && cx > 0 && st.get(cx - ox - 1, y - oy) == 0)
-          start_dir = 0;  // outer border, adjacent = West
-        else if ((s == 1 || s == 2) && cx + 1 < W && st.get(cx - ox + 1, y - oy) == 0)
-          start_dir = 4;  // hole border, adjacent = East
-        if (start_dir < 0) continue;
-        const int n = follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, my_stage, TRACE_STAGE_POINTS, lane);
-        unsigned long long off = 0;
-        int ri = -1;
-        if (lane == 0) {
-          off = atomicAdd(pool_used, (unsigned long long)n);
-          ri = atomicAdd(n_recs, 1);
+        ok = start_border(st, c, 0, 0, W, H, W, xb + l, y, T, my_stage, lane);
+      }
+    }
+  }
+}
+
+// the non-zero-ness of the 16 two-bit pixels of a packed word as 16 bits
+__device__ __forceinline__ uint32_t packed_nz16(uint32_t w) {
+  uint32_t t = (w | (w >> 1)) & 0x55555555u;
+  t = (t | (t >> 1)) & 0x33333333u;
+  t = (t | (t >> 2)) & 0x0f0f0f0fu;
+  t = (t | (t >> 4)) & 0x00ff00ffu;
+  t = (t | (t >> 8)) & 0x0000ffffu;
+  return t;
+}
+
+// Raster scan of one component in its packed tile (warp 0 of the block).  Whether a pixel is a candidate depends on
+// membership only, never on the visited marks, so a row's candidates are found with word arithmetic -- lane j owns the
+// 32-pixel chunk j of the row: member bits, shifted copies for the West / East neighbours, the image-edge rules -- and
+// only chunks that hold a candidate are visited, in order.  (One probe per pixel made the scan of a 900 x 35 window
+// ~1000 dependent steps before the first walk could even start.)
+__device__ void trace_component_packed(const MapPacked st, const Comp& c, int y0, int ox, int oy, int bw, int bh, int W,
+                                       const TraceOut& T, short2* my_stage, int lane) {
+  const int chunks = st.wpr >> 1;
+  const int lx_w = -ox;         // window column of image column 0: no West test there (x > 0)
+  const int lx_e = W - 1 - ox;  // window column of the image's last column: no East test there (x + 1 < W)
+  bool ok = true;
+  for (int y = y0; y <= c.ymax && ok; ++y) {
+    const uint32_t* row = st.p + (y - oy) * st.wpr;
+    for (int g0 = 0; g0 < chunks && ok; g0 += 32) {
+      const int ch = g0 + lane;
+      uint32_t mask = 0;
+      if (ch < chunks) {
+        const uint32_t M = packed_nz16(row[2 * ch]) | (packed_nz16(row[2 * ch + 1]) << 16);
+        const uint32_t pw = ch > 0 ? (packed_nz16(row[2 * ch - 1]) >> 15) & 1u : 0u;
+        const uint32_t ne = 2 * ch + 2 < st.wpr ? packed_nz16(row[2 * ch + 2]) & 1u : 0u;
+        uint32_t wz = M & ~((M << 1) | pw), ez = M & ~((M >> 1) | (ne << 31));
+        if (lx_w >= 32 * ch && lx_w < 32 * ch + 32) wz &= ~(1u << (lx_w - 32 * ch));
+        if (lx_e >= 32 * ch && lx_e < 32 * ch + 32) ez &= ~(1u << (lx_e - 32 * ch));
+        mask = wz | ez;
+      }
+      unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+      while (any && ok) {
+        const int j = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t cm = __shfl_sync(0xffffffffu, mask, j);
+        while (cm && ok) {
+          const int l = __ffs(cm) - 1;
+          cm &= cm - 1;
+          ok = start_border(st, c, ox, oy, bw, bh, W, ox + 32 * (g0 + j) + l, y, T, my_stage, lane);
         }
-        off = __shfl_sync(0xffffffffu, off, 0);
-        ri = __shfl_sync(0xffffffffu, ri, 0);
-        if (off + n > pool_cap || ri >= rec_cap) {
-          if (lane == 0) atomicExch(err, 1);
-          failed = true;
-          break;
-        }
-        if (n <= TRACE_STAGE_POINTS) {
-          __syncwarp();  // lane 0's staged points are visible to the warp
-          for (int i = lane; i < n; i += 32) pool[off + i] = my_stage[i];
-        } else {
-          follow_border(st, ww, wh, ox, oy, W, cx - ox, y - oy, start_dir, pool + off, 0x7fffffff, lane);
-        }
-        if (lane == 0) recs[ri] = ContourRec{c.img, (int)((size_t)y * W + cx), (long long)off, n};
-        __syncwarp();
       }
     }
   }
@@ -392,37 +456,49 @@ __global__ void __launch_bounds__(TRACE_THREADS) db_trace_kernel(
     const bool staged = (size_t)wpr * bh * 4 <= (size_t)TRACE_TILE_BYTES;
     const int ox = staged ? c.xmin - 1 : 0, oy = staged ? y0 - 1 : 0;
     if (staged) {
-      // one warp per row, 32 pixels per step: the membership bits of a ballot, spread to two bits per pixel
+      // one warp per row, 32 pixels per step: the membership bits of a ballot, spread to two bits per pixel.  Four steps
+      // at a time with the state byte and the label loaded side by side (the label of a background pixel is never
+      // written -- db_init_kernel -- and never used: the state byte gates it), so eight loads are in flight per lane
+      // instead of two dependent ones.
       for (int ly = warp; ly < bh; ly += TRACE_THREADS / 32) {
         const int gy = oy + ly;
         const bool row_in = gy >= 0 && gy < H;
-        for (int lx0 = 0; lx0 < 16 * wpr; lx0 += 32) {
-          const int lx = lx0 + lane, gx = ox + lx;
-          bool v = false;
-          if (row_in && lx < bw && gx >= 0 && gx < W) {
-            const size_t o = (size_t)gy * W + gx;
-            v = img[o] != 0 && L[o] == c.root;
+        for (int lx0 = 0; lx0 < 16 * wpr; lx0 += 128) {
+          uint8_t sb[4];
+          int32_t lb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int lx = lx0 + 32 * u + lane, gx = ox + lx;
+            sb[u] = 0, lb[u] = 0;
+            if (row_in && lx < bw && gx >= 0 && gx < W) {
+              const size_t o = (size_t)gy * W + gx;
+              sb[u] = img[o], lb[u] = L[o];
+            }
           }
-          const unsigned m = __ballot_sync(0xffffffffu, v);
-          if ((lane & 15) == 0) {
-            uint32_t b = (m >> lane) & 0xffffu;  // 16 membership bits -> even bit positions
-            b = (b | (b << 8)) & 0x00ff00ffu;
-            b = (b | (b << 4)) & 0x0f0f0f0fu;
-            b = (b | (b << 2)) & 0x33333333u;
-            b = (b | (b << 1)) & 0x55555555u;
-            tile[ly * wpr + ((lx0 + lane) >> 4)] = b;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (lx0 + 32 * u >= 16 * wpr) break;  // uniform
+            const unsigned m = __ballot_sync(0xffffffffu, sb[u] != 0 && lb[u] == c.root);
+            if ((lane & 15) == 0) {
+              uint32_t b = (m >> lane) & 0xffffu;  // 16 membership bits -> even bit positions
+              b = (b | (b << 8)) & 0x00ff00ffu;
+              b = (b | (b << 4)) & 0x0f0f0f0fu;
+              b = (b | (b << 2)) & 0x33333333u;
+              b = (b | (b << 1)) & 0x55555555u;
+              tile[ly * wpr + ((lx0 + 32 * u + lane) >> 4)] = b;
+            }
           }
         }
       }
     }
     __syncthreads();
     if (warp == 0) {
+      const TraceOut T{pool, pool_used, pool_cap, recs, n_recs, rec_cap, err};
       if (staged)
-        trace_component(MapPacked{tile, wpr}, [](int, int) { return true; }, c, y0, ox, oy, bw, bh, W, pool, pool_used,
-                        pool_cap, recs, n_recs, rec_cap, err, my_stage, lane);
+        trace_component_packed(MapPacked{tile, wpr}, c, y0, ox, oy, bw, bh, W, T, my_stage, lane);
       else
-        trace_component(MapU8{img, W}, [&](int x, int y) { return L[(size_t)y * W + x] == c.root; }, c, y0, 0, 0, W, H, W,
-                        pool, pool_used, pool_cap, recs, n_recs, rec_cap, err, my_stage, lane);
+        trace_component_global(MapU8{img, W}, [&](int x, int y) { return L[(size_t)y * W + x] == c.root; }, c, y0, H, W, T,
+                               my_stage, lane);
     }
     __syncthreads();  // the tile is reused by this block's next component
   }
