@@ -80,6 +80,10 @@ pub struct oar_ocr_result {
 unsafe extern "C" {
     pub fn oar_last_error() -> *const c_char;
     pub fn oar_version() -> i32;
+    /// kernels launched by the library in this process / host-visible submissions among them (a replayed CUDA graph of a
+    /// network batch counts one)
+    pub fn oar_launch_count() -> i64;
+    pub fn oar_submit_count() -> i64;
     pub fn oar_det_config_default(cfg: *mut oar_det_config);
     pub fn oar_pipeline_config_default(cfg: *mut oar_pipeline_config);
 

@@ -23,7 +23,7 @@ def _sys():
 
 def _c_functions(h):
     out = {}
-    for m in re.finditer(r"\b(?:int32_t|void|const char\*)\s+(oar_\w+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S):
+    for m in re.finditer(r"\b(?:int32_t|int64_t|void|const char\*)\s+(oar_\w+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return out
