@@ -722,10 +722,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout at the first
-    # communicator) would precede it; anything more verbose that a caller asked for is left alone
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries ONE JSON line.  Libraries print there too (NCCL's version banner comes out of a plain printf at the
+    # first communicator): file descriptor 1 is pointed at stderr for the whole run, and Python's sys.stdout -- which
+    # only the JSON line goes through -- keeps the real one.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.batch is None:
         args.batch = {"rec512": 512, "layout": 8}.get(args.workload, 32)
     if args.workload == "layout":
