@@ -44,6 +44,51 @@ def test_find_contours_matches_opencv_border_sets(seed):
     assert n_outer >= len(cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)[0])
 
 
+def _noise_map(seed, h=120, w=160):
+    rng = np.random.default_rng(seed)
+    m = (rng.random((h, w)) > 0.55).astype(np.uint8) * 255
+    return cv2.morphologyEx(m, cv2.MORPH_OPEN, np.ones((2, 2), np.uint8))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_find_contours_equals_opencv_point_for_point(seed):
+    """Stronger than the border sets: every contour is the SAME SEQUENCE of points as OpenCV's (same start pixel, same
+    direction, same repeated pixels on one-pixel-wide parts), and the contours come in the same discovery order
+    (cv2.findContours with RETR_LIST prepends, so its list is ours reversed)."""
+    m = _blobs(seed)
+    ours, _ = cpu.find_contours(m)
+    theirs, _ = cv2.findContours(m, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+    assert [c.tolist() for c in ours] == [c.reshape(-1, 2).tolist() for c in theirs][::-1]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_find_contours_equals_opencv_on_noise_away_from_the_frame(seed):
+    """~400 contours of thresholded noise (holes inside holes, one-pixel bridges, diagonal contacts): identical to
+    OpenCV point for point and in order once no component touches the image frame.  With components ON the frame the
+    two differ, and only there: imageproc 0.27 starts no outer border at x = 0 and applies its right-edge rule at
+    x = W - 1 (db_bitmap.rs:84-150 calls it on the un-padded mask; the oracle restates that), OpenCV pads the image
+    with a background frame first."""
+    raw = _noise_map(seed)
+    framed = raw.copy()
+    framed[[0, -1], :] = 0
+    framed[:, [0, -1]] = 0
+    ours, _ = cpu.find_contours(framed)
+    theirs, _ = cv2.findContours(framed, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+    assert len(ours) >= 300
+    assert [c.tolist() for c in ours] == [c.reshape(-1, 2).tolist() for c in theirs][::-1]
+    ours, _ = cpu.find_contours(raw)
+    theirs, _ = cv2.findContours(raw, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+    assert len(ours) == len(theirs)
+    h, w = raw.shape
+    differing = 0
+    for a, b in zip([c.tolist() for c in ours], [c.reshape(-1, 2).tolist() for c in theirs][::-1]):
+        if a != b:
+            differing += 1
+            xs, ys = [p[0] for p in a], [p[1] for p in a]
+            assert min(xs) == 0 or max(xs) == w - 1 or min(ys) == 0 or max(ys) == h - 1, "differs away from the frame"
+    assert differing >= 1  # the frame rule is exercised
+
+
 def test_find_contours_single_pixel_and_order():
     m = np.zeros((8, 8), np.uint8)
     m[2, 5] = 255
@@ -71,6 +116,23 @@ def test_resize_triangle_close_to_antialiased_bilinear(dims):
         assert np.array_equal(ours, img)
     assert np.abs(ours - ref).max() <= 1
     assert (ours != ref).mean() < 0.02
+
+
+@pytest.mark.parametrize("dims", [((60, 200), (48, 160)), ((31, 700), (48, 1084)), ((100, 37), (48, 18)),
+                                  ((20, 90), (48, 216)), ((200, 800), (48, 192)), ((48, 320), (48, 320))])
+def test_resize_triangle_within_one_level_of_pillow(dims):
+    """Pillow's BILINEAR resize is the same algorithm family as image 0.25's FilterType::Triangle (separable, the
+    filter's support scaled by the reduction factor), with fixed-point coefficients and an 8-bit intermediate where
+    the crate keeps f32: the two may differ by one grey level, never by more, shrinking or enlarging."""
+    PIL = pytest.importorskip("PIL.Image")
+    (sh, sw), (dh, dw) = dims
+    img = np.random.default_rng(sh * 1000 + sw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    ours = cpu.resize_triangle(img, dw, dh)
+    theirs = np.asarray(PIL.fromarray(img).resize((dw, dh), PIL.BILINEAR))
+    d = np.abs(ours.astype(np.int32) - theirs.astype(np.int32))
+    assert d.max() <= 1
+    if (sh, sw) == (dh, dw):
+        assert d.max() == 0  # identity resize copies
 
 
 def test_perspective_transform_matches_opencv():
