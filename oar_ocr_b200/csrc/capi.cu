@@ -211,7 +211,7 @@ struct DetGroup {
 // synchronised.  With `post_lane` the post-process (threshold, labelling, border tracing, box geometry: latency-bound,
 // a fraction of the SMs) runs on the context's second lane behind an event, so it overlaps the NEXT group's network.
 // `ready` (optional): per image of the caller's list, the event after which its pixels are in HBM.  With uploads in
-// flight the network runs in two halves -- the second half's pages land while the first half is in the detector -- and
+// flight the network runs in parts of growing size -- a part's pages land while its predecessor is in the detector -- and
 // the post-process still sees ONE batch (an image's map does not depend on its batch mates, and the post-process is
 // latency-bound: two half-size passes would cost more than the copy that joins the halves).
 void launch_det_group(oar_model* det, const std::vector<DevImage>& resized, const std::vector<int32_t>& src_h,
